@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — LM-solved UWB windows per second (BASELINE.json metric) on N B200s of one node.
+
+A step = one pass of the hot path (optimizer.initializeOptimization() + optimize(10), i.e.
+uwbgo_solve_batch) over one batch of synthetic C3 windows: 65,536 UWB-only windows per GPU,
+8 anchors, 50-pose window, 10 LM iterations.  Windows are independent, so
+ranks shard them with no data-path collective (weak scaling: 65,536 windows per GPU); the one
+NCCL gather of final poses to rank 0 that north_star allows is inside the timed region.
+
+  value  windows/s with the batch already resident in HBM (uwbgo_solve_batch_device)
+  e2e    windows/s through the host-pointer C-ABI call (uwbgo_solve_batch) with pinned HOST
+         buffers: host->device and device->host copies inside the timed region
+  --impl reference   the CPU restatement of the reference's g2o LM (oracle/) on all host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOWS_PER_GPU = 65536
+N_POSES, N_ANCHORS, LM_ITERS = 50, 8, 10
+METRIC = "LM-solved UWB windows/sec"
+UNIT = "windows/s"
+WORKLOAD = ("C3: synthetic UWB-only windows, 65536 per GPU, 8 anchors, 50-pose window, "
+            "10 LM iterations, 99 edges (50 anchor-range + 49 trajectory), Cauchy kernel")
+# algorithmic bytes per window of the fused solve (inputs 4,584 + outputs 2,824)
+ALGO_BYTES_SOLVE = 7408
+ALGO_BYTES_LINEARIZE = 35496
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(topo, batch, cfg, budget_s=12.0):
+    """oracle (CPU restatement of the reference's g2o LM) on a bounded sample, all host threads"""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    probe = min(batch.n_windows, 64 * cores)
+    t0 = time.perf_counter()
+    oracle.solve(topo, batch.slice(0, probe), cfg, n_threads=cores)
+    dt = time.perf_counter() - t0
+    n = int(min(batch.n_windows, max(probe, probe * budget_s / max(dt, 1e-6))))
+    t0 = time.perf_counter()
+    oracle.solve(topo, batch.slice(0, n), cfg, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} of the {batch.n_windows} C3 windows, {cores} threads, {dt:.2f} s"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (its g2o/CHOLMOD cannot be built offline; this is
+    the g2o-faithful port in oracle/) on all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    from localization_b200 import Config, synthetic
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    cfg = Config(max_iterations=LM_ITERS)
+    n = 512 * cores
+    topo, batch, _ = synthetic.uwb_only(n, N_POSES, N_ANCHORS)
+    for _ in range(max(args.warmup, 1)):
+        oracle.solve(topo, batch.slice(0, max(n // 8, 1)), cfg, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.solve(topo, batch, cfg, n_threads=cores)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_windows_per_step": n},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} C3 windows per step x {args.steps} steps"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="windows per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--stages", action="store_true", help="also time the stage kernels")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from localization_b200 import Config, Solver, synthetic, _ffi
+    from localization_b200.solver import pinned_empty
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = args.windows
+    cfg = Config(max_iterations=LM_ITERS)
+    topo, batch, _ = synthetic.uwb_only(W, N_POSES, N_ANCHORS, seed=synthetic.SEED_C3 + rank)
+    solver = Solver(local)
+    N = N_POSES
+
+    # ---- device-resident leg ------------------------------------------------------------
+    d_in = {k: torch.from_numpy(getattr(batch, k)).to(dev) for k in ("pose_t", "anchors", "range_d", "range_info")}
+    d_pose = torch.empty((W, N, 3), dtype=torch.float64, device=dev)
+    d_chi2 = torch.empty((W, 4), dtype=torch.float64, device=dev)
+    d_status = torch.empty((W, 4), dtype=torch.int32, device=dev)
+    gather = [torch.empty_like(d_pose) for _ in range(world)] if (world > 1 and rank == 0) else None
+    import ctypes as C
+    cb = _ffi.CBatch()
+    cb.n_windows = W
+    pd = lambda t: C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_double))
+    cb.pose_t, cb.anchors, cb.range_d, cb.range_info = (pd(d_in["pose_t"]), pd(d_in["anchors"]),
+                                                        pd(d_in["range_d"]), pd(d_in["range_info"]))
+    cr = _ffi.CResult()
+    cr.pose_t, cr.chi2 = pd(d_pose), pd(d_chi2)
+    cr.status = C.cast(C.c_void_p(d_status.data_ptr()), C.POINTER(C.c_int32))
+    stream = torch.cuda.current_stream(dev)
+    solver.set_profiling(True)
+
+    def step_device():
+        solver.solve_device(topo, cb, cfg, cr, stream.cuda_stream)
+        if world > 1:
+            dist.gather(d_pose, gather, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    l0 = solver.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        kernel_ms.append(None)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = solver.launch_count - l0
+    # kernel-only duration of the fused LM kernel (events recorded by the library on this stream)
+    k_ms = []
+    for _ in range(3):
+        solver.solve_device(topo, cb, cfg, cr, stream.cuda_stream)
+        k_ms.append(solver.last_kernel_ms())
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = W * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end leg: host buffers through uwbgo_solve_batch ----------------------------
+    from localization_b200 import Batch, Result
+    hb = Batch(pose_t=batch.pose_t, anchors=batch.anchors, range_d=batch.range_d, range_info=batch.range_info)
+    for k in ("pose_t", "anchors", "range_d", "range_info"):
+        a = pinned_empty(getattr(batch, k).shape)
+        a[...] = getattr(batch, k)
+        setattr(hb, k, a)
+    hres = Result(pinned_empty((W, N, 3)), None, None, pinned_empty((W, 4)), pinned_empty((W, 4), np.int32))
+    h2d = sum(getattr(hb, k).nbytes for k in ("pose_t", "anchors", "range_d", "range_info"))
+    d2h = hres.pose_t.nbytes + hres.chi2.nbytes + hres.status.nbytes
+
+    class _R(Result):
+        pass
+    def step_host():
+        t_, b_, c_ = topo.c_struct(), hb.c_struct(), cfg.c_struct()
+        r_ = _ffi.CResult()
+        r_.pose_t, r_.chi2 = pd_np(hres.pose_t), pd_np(hres.chi2)
+        r_.status = hres.status.ctypes.data_as(C.POINTER(C.c_int32))
+        rc = solver._lib.uwbgo_solve_batch(solver._h, C.byref(t_), C.byref(b_), C.byref(c_), C.byref(r_))
+        if rc:
+            raise RuntimeError(solver._lib.uwbgo_last_error().decode())
+    pd_np = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for _ in range(args.warmup):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = W * world * args.steps / e2e_s
+    # the two legs must agree bit for bit
+    same = bool(np.array_equal(hres.pose_t, d_pose.cpu().numpy()))
+
+    line = None
+    if rank == 0:
+        hbm, how = peaks()
+        k_best = float(np.median([k for k in k_ms if k and k > 0])) if k_ms else None
+        achieved = ALGO_BYTES_SOLVE * W / (k_best * 1e-3) / 1e9 if k_best else None
+        roof = {"bound": "hbm", "kernel": "lm_fast_kernel (fused LM: linearise + assemble + block Cholesky + damping loop)",
+                "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if achieved else None,
+                "traffic": None, "peak_source": how, "kernel_ms": k_best,
+                "algorithmic_bytes_per_window": ALGO_BYTES_SOLVE,
+                "note": "the fused solve is FP64-latency bound by design (SURVEY 8d); its working set "
+                        "streams through HBM in the tile layout, see DESIGN.md"}
+        fp64, _ = solver.measure_fp64_peak()
+        roof["fp64_peak_tflops_measured"] = fp64 / 1e12
+        stages = None
+        if args.stages:
+            stages = time_stages(solver, topo, batch, cfg, dev, hbm)
+        cpu = None if args.no_cpu else cpu_baseline(topo, batch, cfg)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "windows_per_gpu": W, "n_poses": N, "n_anchors": N_ANCHORS,
+                           "lm_iterations": LM_ITERS, "parallelism": f"windows sharded x{world}, no data-path collective",
+                           "l2": "inputs (300 MB) and workspace (1.2 GB) per step exceed the 126 MB L2"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "matches_device_leg": same},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        if stages:
+            line["stages"] = stages
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_stages(solver, topo, batch, cfg, dev, hbm):
+    """stage kernels: linearise (HBM roofline) and factor/solve"""
+    import ctypes as C
+    import torch
+    from localization_b200 import _ffi
+    W, N = batch.n_windows, topo.n_poses
+    d = {k: torch.from_numpy(getattr(batch, k)).to(dev) for k in ("pose_t", "anchors", "range_d", "range_info")}
+    Hd = torch.empty((W, N, 36), dtype=torch.float64, device=dev)
+    Ho = torch.empty((W, N - 1, 36), dtype=torch.float64, device=dev)
+    b = torch.empty((W, N, 6), dtype=torch.float64, device=dev)
+    chi = torch.empty((W, 2), dtype=torch.float64, device=dev)
+    cb = _ffi.CBatch()
+    cb.n_windows = W
+    pd = lambda t: C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_double))
+    cb.pose_t, cb.anchors, cb.range_d, cb.range_info = pd(d["pose_t"]), pd(d["anchors"]), pd(d["range_d"]), pd(d["range_info"])
+    st = torch.cuda.current_stream(dev).cuda_stream
+    ms = []
+    for _ in range(4):
+        solver.linearize_device(topo, cb, cfg, Hd.data_ptr(), Ho.data_ptr(), b.data_ptr(), chi.data_ptr(), st)
+        ms.append(solver.last_kernel_ms())
+    torch.cuda.synchronize(dev)
+    k = float(np.median(ms[1:]))
+    ach = ALGO_BYTES_LINEARIZE * W / (k * 1e-3) / 1e9
+    return {"linearize": {"kernel_ms": k, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                          "algorithmic_bytes_per_window": ALGO_BYTES_LINEARIZE}}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,193 @@
+/*
+ * uwbgo.h — C ABI of the B200-native batched sliding-window LM solver.
+ *
+ * This is the drop-in boundary for the one hot path of sair-lab/localization:
+ * Localization::solve() (reference src/localization/localization.cpp:164-192), i.e.
+ *   optimizer.initializeOptimization(); optimizer.optimize(iteration_max);
+ * run over W independent windows at once.  A window is what the g2o graph holds at the
+ * moment of that call: N moving VertexSE3 poses (src/localization/robot.cpp:39-55,75-110),
+ * A fixed anchor vertices, and E edges in g2o insertion order
+ * (EdgeSE3Range  src/types/types_edge_se3range.cpp:105-114,
+ *  EdgeSE3Prior  localization.cpp:462-535, EdgeSE3 localization.cpp:438-459,560-605).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no C++/torch types; nothing throws across the ABI
+ *   - every function returns 0 on success or a negative UWBGO_E_* code;
+ *     uwbgo_last_error() gives the text of the last failure on the calling thread
+ *   - the caller owns every buffer it passes in; the library owns its device workspace
+ *     inside the context; one context per GPU, used by one host thread at a time
+ *   - all floating point is IEEE FP64, all indices int32, window-major C-contiguous arrays
+ *   - there is NO CPU fallback: uwbgo_create() fails if no sm_100 device is present
+ */
+#ifndef UWBGO_H
+#define UWBGO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UWBGO_ABI_VERSION 1
+
+/* error codes */
+#define UWBGO_OK              0
+#define UWBGO_E_INVALID     (-1)  /* bad argument / inconsistent sizes            */
+#define UWBGO_E_TOPOLOGY    (-2)  /* window is not a chain (block-tridiagonal H)  */
+#define UWBGO_E_CUDA        (-3)  /* CUDA runtime error (text in last_error)      */
+#define UWBGO_E_NODEVICE    (-4)  /* no usable sm_100 GPU                         */
+#define UWBGO_E_NOMEM       (-5)
+
+/* edge kinds (the four edge types Localization creates) */
+#define UWBGO_EDGE_RANGE_ANCHOR 0 /* EdgeSE3Range(pose, fixed anchor)   localization.cpp:331,350 */
+#define UWBGO_EDGE_RANGE_POSE   1 /* EdgeSE3Range(prev pose, new pose), measurement 0  localization.cpp:338 */
+#define UWBGO_EDGE_PRIOR        2 /* EdgeSE3Prior on one pose (IMU / lidar)            localization.cpp:481,520 */
+#define UWBGO_EDGE_SE3          3 /* EdgeSE3(prev pose, new pose) (twist)              localization.cpp:588 */
+
+/*
+ * Topology: the structure of the g2o graph, shared by every window of one batch
+ * (all windows of a Monte-Carlo replay / parameter sweep / synthetic config have the same
+ * structure; the host packer buckets windows by topology).  Edges are listed in g2o
+ * insertion order, which is the order g2o accumulates them into H and b.
+ *
+ * Per-kind data slots are assigned by counting: the k-th RANGE_* edge of the list reads
+ * range_d[w][k]; the k-th PRIOR edge reads prior_Z[w][k]; the k-th SE3 edge reads se3_Z[w][k].
+ */
+typedef struct uwbgo_topology {
+    int32_t n_poses;      /* N  = robot/trajectory_length (localization.cpp:72)             */
+    int32_t n_anchors;    /* A  = fixed Robot vertices (localization.cpp:97-98)             */
+    int32_t n_antennas;   /* K  = entries of /uwb/antennaOffset (localization.cpp:111-123)  */
+    int32_t n_edges;      /* E                                                              */
+    const int32_t *edge_kind;   /* [E] UWBGO_EDGE_*                                          */
+    const int32_t *edge_a;      /* [E] vertex 0: pose index 0..N-1 (0 = oldest)              */
+    const int32_t *edge_b;      /* [E] vertex 1: anchor index (RANGE_ANCHOR), pose index =   */
+                                /*     edge_a+1 (RANGE_POSE, SE3), ignored (PRIOR)           */
+    const int32_t *edge_ant;    /* [E] RANGE_*: antenna number of the vertex-0 offset,       */
+                                /*     0 = identity, k>0 = ant_offsets[k-1] (localization.cpp:333) */
+    const int32_t *edge_robust; /* [E] 1 = RobustKernelCauchy (delta 1), 0 = no kernel       */
+} uwbgo_topology;
+
+/* Per-window numeric data, window-major.  Er/Ep/Es = number of RANGE_*, PRIOR, SE3 edges. */
+typedef struct uwbgo_batch {
+    int64_t n_windows;            /* W */
+    const double  *pose_t;        /* [W][N][3]  initial translations                              */
+    const double  *pose_R;        /* [W][N][9]  initial rotations, row-major; NULL = identity     */
+    const int32_t *oplus_count;   /* [W][N]     VertexSE3::_numOplusCalls carried in; NULL = 0    */
+    const double  *anchors;       /* [W][A][3]  fixed anchor positions                            */
+    const double  *ant_offsets;   /* [K][3]     antenna lever arms (shared); NULL iff K == 0      */
+    const double  *range_d;       /* [W][Er]    EdgeSE3Range measurement                          */
+    const double  *range_info;    /* [W][Er]    EdgeSE3Range information (1x1)                    */
+    const double  *prior_Z;       /* [W][Ep][12] EdgeSE3Prior measurement: R row-major (9), t (3) */
+    const double  *prior_info;    /* [W][Ep][36] information, row-major                           */
+    const double  *se3_Z;         /* [W][Es][12] EdgeSE3 measurement                              */
+    const double  *se3_info;      /* [W][Es][36] information, row-major                           */
+} uwbgo_batch;
+
+/* Solver constants; uwbgo_config_default() fills g2o's defaults at the pinned commit. */
+typedef struct uwbgo_config {
+    int32_t max_iterations;       /* optimizer/maximum_iteration (localization.cpp:65), default 20 */
+    int32_t max_trials;           /* LM maxTrialsAfterFailure, 10                                  */
+    int32_t orthogonalize_after;  /* VertexSE3::orthogonalizeAfter, 1000                           */
+    int32_t reserved;
+    double  tau;                  /* LM initial-lambda factor, 1e-5                                */
+    double  good_step_lower;      /* 1/3                                                           */
+    double  good_step_upper;      /* 2/3                                                           */
+    double  kernel_delta;         /* RobustKernelCauchy delta, 1.0                                 */
+    double  jacobian_delta;       /* numeric-Jacobian step of BaseBinaryEdge, 1e-9                 */
+} uwbgo_config;
+
+#define UWBGO_CHI2_STRIDE   4   /* chi2[w] = {plain chi2 at final estimate, robust chi2 at final   */
+                                /*  estimate, g2o optimizer.chi2() as publish() reads it           */
+                                /*  (localization.cpp:197: errors of the LAST trial, maybe         */
+                                /*  rejected), final lambda}                                       */
+#define UWBGO_STATUS_STRIDE 4   /* status[w] = {iterations run, total LM trials, flags, trials of  */
+                                /*  the last iteration}                                            */
+#define UWBGO_FLAG_CHOL_FAIL   1  /* some trial hit a non-positive pivot (trial rejected)          */
+#define UWBGO_FLAG_TERMINATED  2  /* LM returned Terminate (max trials reached or rho == 0)        */
+#define UWBGO_FLAG_NONFINITE   4  /* a trial produced a non-finite robust chi2                     */
+
+typedef struct uwbgo_result {
+    double  *pose_t;       /* [W][N][3]                                   */
+    double  *pose_R;       /* [W][N][9]; may be NULL                      */
+    int32_t *oplus_count;  /* [W][N];    may be NULL                      */
+    double  *chi2;         /* [W][UWBGO_CHI2_STRIDE]                      */
+    int32_t *status;       /* [W][UWBGO_STATUS_STRIDE]                    */
+} uwbgo_result;
+
+typedef struct uwbgo_ctx uwbgo_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int  uwbgo_abi_version(void);
+void uwbgo_config_default(uwbgo_config *cfg);
+/* Replaces the solver chain built in Localization::Localization (localization.cpp:44-52). */
+int  uwbgo_create(int device, uwbgo_ctx **out);
+void uwbgo_destroy(uwbgo_ctx *ctx);
+const char *uwbgo_last_error(void);
+
+/* Tuning of the host-pointer entry points: windows per pipeline chunk (rounded up to 32) and
+ * number of concurrent stream lanes (1..4).  Defaults: 16384 windows, 3 lanes. */
+int  uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes);
+/* Page-locked host memory.  The host-pointer entry points accept any host memory; with buffers
+ * from uwbgo_host_alloc their copies overlap the kernels of neighbouring chunks. */
+void *uwbgo_host_alloc(size_t bytes);
+void  uwbgo_host_free(void *p);
+
+/* ---- the hot path ----------------------------------------------------------------------
+ * Replaces optimizer.initializeOptimization(); optimizer.optimize(iteration_max)
+ * (localization.cpp:168-170) for W windows.  HOST buffers in, HOST buffers out; the
+ * host<->device copies are inside the call (pipelined in chunks over CUDA streams). */
+int uwbgo_solve_batch(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
+                      const uwbgo_config *cfg, uwbgo_result *out);
+
+/* Same, but every pointer inside `in` (except the struct itself and ant_offsets, which is
+ * host memory) and `out` is a DEVICE pointer on the context's GPU, and the work is queued on
+ * `stream` (a cudaStream_t; NULL = the default stream) without synchronising. */
+int uwbgo_solve_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
+                             const uwbgo_config *cfg, uwbgo_result *out, void *stream);
+
+/* ---- stages, exposed for parity tests and roofline measurement -------------------------
+ * One linearisation at the given estimates: computeActiveErrors + buildSystem
+ * (g2o BlockSolver; numeric Jacobians of BaseBinaryEdge for the range edges).
+ *   H_diag [W][N][36]   diagonal 6x6 blocks, row-major, both triangles
+ *   H_off  [W][N-1][36] block (i, i+1), rows of pose i, columns of pose i+1
+ *   b      [W][N][6]
+ *   chi2   [W][2]       {plain, robust} at the linearisation point
+ * host pointers. */
+int uwbgo_linearize_batch(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
+                          const uwbgo_config *cfg, double *H_diag, double *H_off, double *b,
+                          double *chi2);
+/* device-pointer variant, queued on `stream` */
+int uwbgo_linearize_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo,
+                                 const uwbgo_batch *in, const uwbgo_config *cfg, double *H_diag,
+                                 double *H_off, double *b, double *chi2, void *stream);
+
+/* Solve (H + lambda I) x = b for W block-tridiagonal systems (replaces
+ * LinearSolverCholmod::solve, localization.h:84).  ok[w] = 0 when a pivot was not positive
+ * (x[w] is then all zero).  Host pointers. */
+int uwbgo_factor_solve_batch(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_windows,
+                             const double *H_diag, const double *H_off, const double *b,
+                             const double *lambda, double *x, int32_t *ok);
+int uwbgo_factor_solve_batch_device(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_windows,
+                                    const double *H_diag, const double *H_off, const double *b,
+                                    const double *lambda, double *x, int32_t *ok, void *stream);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+/* number of kernels this library launched on ctx since creation (bench "gpu_launches") */
+int64_t uwbgo_launch_count(const uwbgo_ctx *ctx);
+/* 1 if the last solve on ctx used the translation-only (R = I, zero offsets) instantiation */
+int     uwbgo_last_path(const uwbgo_ctx *ctx);
+/* Kernel timing for roofline reports: with profiling on, every *_device call records CUDA events
+ * on its stream immediately before and after its main kernel (the fused LM kernel of
+ * uwbgo_solve_batch_device, the linearisation kernel of uwbgo_linearize_batch_device);
+ * uwbgo_last_kernel_ms waits for the last such kernel and returns its duration (-1 if none). */
+int     uwbgo_set_profiling(uwbgo_ctx *ctx, int on);
+double  uwbgo_last_kernel_ms(uwbgo_ctx *ctx);
+/* FP64 FMA micro-benchmark on the context's GPU: returns achieved FP64 FLOP/s (2 per FMA),
+ * used as the measured FP64 roofline denominator (MEASURED_PEAKS.json has none). */
+double  uwbgo_measure_fp64_peak(uwbgo_ctx *ctx, double *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UWBGO_H */

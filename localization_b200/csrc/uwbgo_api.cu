@@ -1,0 +1,910 @@
+/*
+ * uwbgo_api.cu — the C ABI of include/uwbgo.h: contexts, topology compilation, workspace
+ * management and the chunked host<->device pipeline around the kernels in uwbgo_kernels.cu.
+ *
+ * There is no CPU path in this library: every entry point that computes needs an sm_100
+ * device and fails with UWBGO_E_NODEVICE otherwise.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "uwbgo_internal.h"
+
+using namespace uwbgo;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *what)
+{
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return UWBGO_E_CUDA;
+}
+#define CU(call)                                             \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+/* grow-only device buffer */
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            return fail(UWBGO_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+/* a compiled topology, resident on the device */
+struct TopoEntry {
+    std::vector<int32_t> key;
+    DevTopo gen{};        /* edge table with antenna numbers                   */
+    DevTopo fast{};       /* edge table with carry slots (fast-eligible only)  */
+    bool fast_ok = false;
+    void *dmem = nullptr;
+    uint64_t stamp = 0;
+};
+
+/* one pipeline lane: a stream, its device-side window-major staging and its tile workspace */
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf stage; /* window-major staging (host API only) */
+    DevBuf tile;  /* tile-layout workspace */
+};
+
+constexpr int MAX_LANES = 4;
+
+}  // namespace
+
+struct uwbgo_ctx {
+    int device = 0;
+    int n_lanes = 3;
+    int64_t chunk = 16384;
+    Lane lane[MAX_LANES];
+    DevBuf misc;          /* ant offsets + factor_solve scratch + lambda etc. */
+    DevBuf ant;
+    std::vector<std::unique_ptr<TopoEntry>> topos;
+    uint64_t stamp = 0;
+    int64_t launches = 0;
+    int last_path = 0;
+    cudaEvent_t ws_free = nullptr; /* completion of the last user-stream call on lane 0's workspace */
+    bool ws_pending = false;
+    bool profile = false;          /* bracket the main kernel of device-API calls with events */
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    bool k_valid = false;
+};
+
+namespace {
+
+struct Slots {
+    int Er = 0, Ep = 0, Es = 0;
+};
+
+int validate_topology(const uwbgo_topology *T, std::vector<int32_t> &slot, Slots &sl)
+{
+    if (!T) return fail(UWBGO_E_INVALID, "topology is NULL");
+    if (T->n_poses < 1) return fail(UWBGO_E_INVALID, "n_poses must be >= 1");
+    if (T->n_anchors < 0 || T->n_antennas < 0 || T->n_edges < 0)
+        return fail(UWBGO_E_INVALID, "negative size in topology");
+    if (T->n_edges > 0 && (!T->edge_kind || !T->edge_a || !T->edge_b || !T->edge_robust))
+        return fail(UWBGO_E_INVALID, "edge arrays missing");
+    slot.assign((size_t)T->n_edges, 0);
+    for (int e = 0; e < T->n_edges; ++e) {
+        int a = T->edge_a[e], b = T->edge_b[e];
+        if (a < 0 || a >= T->n_poses) return fail(UWBGO_E_INVALID, "edge_a out of range");
+        switch (T->edge_kind[e]) {
+        case UWBGO_EDGE_RANGE_ANCHOR:
+            if (b < 0 || b >= T->n_anchors) return fail(UWBGO_E_INVALID, "anchor index out of range");
+            slot[e] = sl.Er++;
+            break;
+        case UWBGO_EDGE_RANGE_POSE:
+            if (b != a + 1 || b >= T->n_poses)
+                return fail(UWBGO_E_TOPOLOGY, "pose-pose range edge must join consecutive poses");
+            slot[e] = sl.Er++;
+            break;
+        case UWBGO_EDGE_PRIOR:
+            slot[e] = sl.Ep++;
+            break;
+        case UWBGO_EDGE_SE3:
+            if (b != a + 1 || b >= T->n_poses)
+                return fail(UWBGO_E_TOPOLOGY, "SE3 edge must join consecutive poses");
+            slot[e] = sl.Es++;
+            break;
+        default:
+            return fail(UWBGO_E_INVALID, "unknown edge kind");
+        }
+        if (T->edge_kind[e] <= UWBGO_EDGE_RANGE_POSE && T->edge_ant &&
+            (T->edge_ant[e] < 0 || T->edge_ant[e] > T->n_antennas))
+            return fail(UWBGO_E_INVALID, "edge_ant out of range");
+    }
+    return 0;
+}
+
+/* initializeOptimization(): everything g2o derives from the graph structure alone */
+int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
+{
+    std::vector<int32_t> slot;
+    Slots sl;
+    int rc = validate_topology(T, slot, sl);
+    if (rc) return rc;
+    const int N = T->n_poses, E = T->n_edges;
+    std::vector<int32_t> key;
+    key.reserve(5 + 5 * (size_t)E);
+    key.push_back(N);
+    key.push_back(T->n_anchors);
+    key.push_back(T->n_antennas);
+    key.push_back(E);
+    for (int e = 0; e < E; ++e) {
+        key.push_back(T->edge_kind[e]);
+        key.push_back(T->edge_a[e]);
+        key.push_back(T->edge_b[e]);
+        key.push_back(T->edge_ant ? T->edge_ant[e] : 0);
+        key.push_back(T->edge_robust[e] ? 1 : 0);
+    }
+    for (auto &t : ctx->topos)
+        if (t->key == key) {
+            t->stamp = ++ctx->stamp;
+            *out = t.get();
+            return 0;
+        }
+
+    std::vector<EdgeRec> edges((size_t)E), fedges((size_t)E);
+    std::vector<int32_t> calls((size_t)N, 0), carry((size_t)N, 0);
+    std::vector<std::vector<PoseOp>> per_pose((size_t)N);
+    bool fast_ok = true;
+    for (int e = 0; e < E; ++e) {
+        EdgeRec r{};
+        r.kind = T->edge_kind[e];
+        r.a = T->edge_a[e];
+        r.b = T->edge_b[e];
+        r.slot = slot[e];
+        r.ant = (r.kind <= UWBGO_EDGE_RANGE_POSE && T->edge_ant) ? T->edge_ant[e] : 0;
+        r.robust = T->edge_robust[e] ? 1 : 0;
+        if (r.kind <= UWBGO_EDGE_RANGE_POSE) { /* BaseBinaryEdge numeric Jacobian: 12 oplus per free vertex */
+            r.base_a = calls[r.a];
+            calls[r.a] += 12;
+            if (r.kind == UWBGO_EDGE_RANGE_POSE) {
+                r.base_b = calls[r.b];
+                calls[r.b] += 12;
+            }
+        }
+        edges[e] = r;
+        per_pose[r.a].push_back(PoseOp{e, 0});
+        if (r.kind == UWBGO_EDGE_RANGE_POSE || r.kind == UWBGO_EDGE_SE3)
+            per_pose[r.b].push_back(PoseOp{e, 1});
+        EdgeRec f = r;
+        if (r.kind > UWBGO_EDGE_RANGE_POSE || r.ant != 0) fast_ok = false;
+        if (r.kind == UWBGO_EDGE_RANGE_POSE) {
+            int k = carry[r.a]++;
+            if (k >= 2) fast_ok = false;
+            f.ant = (r.a & 1) * 2 + k; /* shared-memory carry slot of the vertex-1 terms */
+        }
+        fedges[e] = f;
+    }
+    std::vector<PoseOp> ops;
+    std::vector<int32_t> op_begin((size_t)N + 1, 0);
+    for (int i = 0; i < N; ++i) {
+        op_begin[i] = (int32_t)ops.size();
+        ops.insert(ops.end(), per_pose[i].begin(), per_pose[i].end());
+    }
+    op_begin[N] = (int32_t)ops.size();
+
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o_edges = 0;
+    size_t o_fedges = o_edges + al(sizeof(EdgeRec) * std::max(E, 1));
+    size_t o_ops = o_fedges + al(sizeof(EdgeRec) * std::max(E, 1));
+    size_t o_begin = o_ops + al(sizeof(PoseOp) * std::max<size_t>(ops.size(), 1));
+    size_t o_calls = o_begin + al(sizeof(int32_t) * (N + 1));
+    size_t total = o_calls + al(sizeof(int32_t) * N);
+    std::vector<char> host(total, 0);
+    if (E) {
+        memcpy(host.data() + o_edges, edges.data(), sizeof(EdgeRec) * E);
+        memcpy(host.data() + o_fedges, fedges.data(), sizeof(EdgeRec) * E);
+    }
+    if (!ops.empty()) memcpy(host.data() + o_ops, ops.data(), sizeof(PoseOp) * ops.size());
+    memcpy(host.data() + o_begin, op_begin.data(), sizeof(int32_t) * (N + 1));
+    memcpy(host.data() + o_calls, calls.data(), sizeof(int32_t) * N);
+
+    auto ent = std::make_unique<TopoEntry>();
+    CU(cudaMalloc(&ent->dmem, total));
+    cudaError_t ce = cudaMemcpy(ent->dmem, host.data(), total, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        cudaFree(ent->dmem);
+        return fail_cuda(ce, "cudaMemcpy(topology)");
+    }
+    char *d = static_cast<char *>(ent->dmem);
+    DevTopo g{};
+    g.N = N;
+    g.A = T->n_anchors;
+    g.K = T->n_antennas;
+    g.E = E;
+    g.Er = sl.Er;
+    g.Ep = sl.Ep;
+    g.Es = sl.Es;
+    g.fast = 0;
+    g.edges = reinterpret_cast<const EdgeRec *>(d + o_edges);
+    g.ops = reinterpret_cast<const PoseOp *>(d + o_ops);
+    g.op_begin = reinterpret_cast<const int32_t *>(d + o_begin);
+    g.num_calls = reinterpret_cast<const int32_t *>(d + o_calls);
+    ent->gen = g;
+    ent->fast = g;
+    ent->fast.fast = 1;
+    ent->fast.edges = reinterpret_cast<const EdgeRec *>(d + o_fedges);
+    ent->fast_ok = fast_ok;
+    ent->key = std::move(key);
+    ent->stamp = ++ctx->stamp;
+    if (ctx->topos.size() >= 32) { /* evict the least recently used */
+        size_t victim = 0;
+        for (size_t k = 1; k < ctx->topos.size(); ++k)
+            if (ctx->topos[k]->stamp < ctx->topos[victim]->stamp) victim = k;
+        cudaDeviceSynchronize();
+        cudaFree(ctx->topos[victim]->dmem);
+        ctx->topos.erase(ctx->topos.begin() + (long)victim);
+    }
+    ctx->topos.push_back(std::move(ent));
+    *out = ctx->topos.back().get();
+    return 0;
+}
+
+int make_cfg(const uwbgo_config *c, DevCfg &d)
+{
+    if (!c) return fail(UWBGO_E_INVALID, "config is NULL");
+    if (c->max_iterations < 0 || c->max_trials < 1 || c->orthogonalize_after < 0 ||
+        c->orthogonalize_after > 1000000000)
+        return fail(UWBGO_E_INVALID, "bad iteration / trial / orthogonalize_after setting");
+    d.max_iterations = c->max_iterations;
+    d.max_trials = c->max_trials;
+    d.orth_mod = c->orthogonalize_after + 1;
+    d.tau = c->tau;
+    d.good_lo = c->good_step_lower;
+    d.good_hi = c->good_step_upper;
+    d.kdelta = c->kernel_delta;
+    d.jdelta = c->jacobian_delta;
+    return 0;
+}
+
+int check_batch(const TopoEntry &te, const uwbgo_batch *in)
+{
+    if (!in) return fail(UWBGO_E_INVALID, "batch is NULL");
+    if (in->n_windows < 0) return fail(UWBGO_E_INVALID, "n_windows < 0");
+    const DevTopo &g = te.gen;
+    if (in->n_windows == 0) return 0;
+    if (!in->pose_t) return fail(UWBGO_E_INVALID, "pose_t is NULL");
+    if (g.A > 0 && !in->anchors) return fail(UWBGO_E_INVALID, "anchors is NULL");
+    if (g.K > 0 && !in->ant_offsets) return fail(UWBGO_E_INVALID, "ant_offsets is NULL");
+    if (g.Er > 0 && (!in->range_d || !in->range_info)) return fail(UWBGO_E_INVALID, "range data NULL");
+    if (g.Ep > 0 && (!in->prior_Z || !in->prior_info)) return fail(UWBGO_E_INVALID, "prior data NULL");
+    if (g.Es > 0 && (!in->se3_Z || !in->se3_info)) return fail(UWBGO_E_INVALID, "se3 data NULL");
+    return 0;
+}
+
+/* carve the tile workspace of one launch out of a lane's buffer */
+struct TileLayout {
+    size_t bytes = 0;
+    size_t off_T[2], off_R[2], off_cnt, off_anch, off_rd, off_ri, off_pZ, off_pI, off_sZ, off_sI, off_HB,
+        off_LR, off_chi2, off_status;
+};
+TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bool want_LR)
+{
+    TileLayout L;
+    const size_t tw = (size_t)n_tiles(W) * TILE; /* padded window count */
+    size_t o = 0;
+    auto take = [&](size_t rows, size_t elem) {
+        size_t at = o;
+        o += (rows * tw * elem + 255) & ~(size_t)255;
+        return at;
+    };
+    const size_t N = (size_t)t.N;
+    L.off_T[0] = take(N * 3, 8);
+    L.off_T[1] = take(N * 3, 8);
+    L.off_R[0] = fast ? 0 : take(N * 9, 8);
+    L.off_R[1] = fast ? 0 : take(N * 9, 8);
+    L.off_cnt = (fast && !want_cnt) ? 0 : take(N, 4);
+    L.off_anch = take((size_t)t.A * 3, 8);
+    L.off_rd = take((size_t)t.Er, 8);
+    L.off_ri = take((size_t)t.Er, 8);
+    L.off_pZ = take((size_t)t.Ep * 12, 8);
+    L.off_pI = take((size_t)t.Ep * 36, 8);
+    L.off_sZ = take((size_t)t.Es * 12, 8);
+    L.off_sI = take((size_t)t.Es * 36, 8);
+    L.off_HB = take(N * (fast ? HR_FAST : HR_GEN), 8);
+    L.off_LR = want_LR ? take(N * (fast ? HR_FAST : HR_GEN), 8) : 0;
+    L.off_chi2 = take(4, 8);
+    L.off_status = take(4, 4);
+    L.bytes = o;
+    return L;
+}
+
+/* device-side core shared by every entry point: inputs/outputs are DEVICE window-major arrays.
+ * mode 0: full LM solve.  mode 1: one linearisation (H_diag/H_off/b/chi2 out). */
+struct StageOut {
+    double *H_diag, *H_off, *b, *chi2;
+};
+int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
+               const uwbgo_batch *in, const double *d_ant, uwbgo_result *out, const StageOut *so,
+               cudaStream_t st)
+{
+    const int64_t W = in->n_windows;
+    if (W == 0) return 0;
+    const bool fast = te.fast_ok && in->pose_R == nullptr;
+    const DevTopo &tp = fast ? te.fast : te.gen;
+    const bool want_cnt = (in->oplus_count != nullptr) || (out && out->oplus_count != nullptr);
+    TileLayout L = tile_layout(tp, fast, W, want_cnt, so == nullptr);
+    int rc = ln.tile.reserve(L.bytes);
+    if (rc) return rc;
+    char *base = static_cast<char *>(ln.tile.p);
+    DevWs ws{};
+    ws.W = W;
+    ws.T[0] = reinterpret_cast<double *>(base + L.off_T[0]);
+    ws.T[1] = reinterpret_cast<double *>(base + L.off_T[1]);
+    if (!fast) {
+        ws.Rm[0] = reinterpret_cast<double *>(base + L.off_R[0]);
+        ws.Rm[1] = reinterpret_cast<double *>(base + L.off_R[1]);
+    }
+    const bool have_cnt = !fast || want_cnt;
+    ws.cnt = have_cnt ? reinterpret_cast<int32_t *>(base + L.off_cnt) : nullptr;
+    ws.anch = reinterpret_cast<double *>(base + L.off_anch);
+    ws.rd = reinterpret_cast<double *>(base + L.off_rd);
+    ws.ri = reinterpret_cast<double *>(base + L.off_ri);
+    ws.pZ = reinterpret_cast<double *>(base + L.off_pZ);
+    ws.pI = reinterpret_cast<double *>(base + L.off_pI);
+    ws.sZ = reinterpret_cast<double *>(base + L.off_sZ);
+    ws.sI = reinterpret_cast<double *>(base + L.off_sI);
+    ws.HB = reinterpret_cast<double *>(base + L.off_HB);
+    ws.LR = so ? nullptr : reinterpret_cast<double *>(base + L.off_LR);
+    ws.ant = d_ant;
+    ws.chi2 = reinterpret_cast<double *>(base + L.off_chi2);
+    ws.status = reinterpret_cast<int32_t *>(base + L.off_status);
+
+    XposeJobs pj{};
+    pj.W = W;
+    auto add = [&](XposeJobs &J, const void *src, void *dst, int C, int elem, int mode) {
+        if (C <= 0) return;
+        XposeJob &j = J.job[J.n++];
+        j.src = src;
+        j.dst = dst;
+        j.C = C;
+        j.elem = elem;
+        j.mode = mode;
+        j.aux = 0;
+    };
+    add(pj, in->pose_t, ws.T[0], tp.N * 3, 8, 0);
+    if (!fast) {
+        if (in->pose_R)
+            add(pj, in->pose_R, ws.Rm[0], tp.N * 9, 8, 0);
+        else
+            add(pj, nullptr, ws.Rm[0], tp.N * 9, 8, 1);
+    }
+    if (have_cnt) {
+        if (in->oplus_count)
+            add(pj, in->oplus_count, ws.cnt, tp.N, 4, 0);
+        else
+            add(pj, nullptr, ws.cnt, tp.N, 4, 3);
+    }
+    add(pj, in->anchors, const_cast<double *>(ws.anch), tp.A * 3, 8, 0);
+    add(pj, in->range_d, const_cast<double *>(ws.rd), tp.Er, 8, 0);
+    add(pj, in->range_info, const_cast<double *>(ws.ri), tp.Er, 8, 0);
+    add(pj, in->prior_Z, const_cast<double *>(ws.pZ), tp.Ep * 12, 8, 0);
+    add(pj, in->prior_info, const_cast<double *>(ws.pI), tp.Ep * 36, 8, 0);
+    add(pj, in->se3_Z, const_cast<double *>(ws.sZ), tp.Es * 12, 8, 0);
+    add(pj, in->se3_info, const_cast<double *>(ws.sI), tp.Es * 36, 8, 0);
+    CU(launch_pack(pj, st));
+    ctx->launches += 1;
+
+    XposeJobs uj{};
+    uj.W = W;
+    const bool timed = ctx->profile && &ln == &ctx->lane[0];
+    if (timed) CU(cudaEventRecord(ctx->k0, st));
+    if (so) {
+        CU(launch_linearize(tp, cfg, ws, st));
+        if (timed) CU(cudaEventRecord(ctx->k1, st));
+        CU(launch_expand_H(tp, ws, so->H_diag, so->H_off, so->b, st));
+        ctx->launches += 2;
+        if (so->chi2) add(uj, ws.chi2, so->chi2, 2, 8, 0);
+    } else {
+        CU(launch_solve(tp, cfg, ws, st));
+        if (timed) CU(cudaEventRecord(ctx->k1, st));
+        ctx->launches += 1;
+        add(uj, ws.T[0], out->pose_t, tp.N * 3, 8, 0);
+        if (out->pose_R) {
+            if (fast)
+                add(uj, nullptr, out->pose_R, tp.N * 9, 8, 2);
+            else
+                add(uj, ws.Rm[0], out->pose_R, tp.N * 9, 8, 0);
+        }
+        if (out->oplus_count) add(uj, ws.cnt, out->oplus_count, tp.N, 4, 0);
+        if (out->chi2) add(uj, ws.chi2, out->chi2, 4, 8, 0);
+        if (out->status) add(uj, ws.status, out->status, 4, 4, 0);
+    }
+    if (uj.n) {
+        CU(launch_unpack(uj, st));
+        ctx->launches += 1;
+    }
+    ctx->last_path = fast ? 1 : 0;
+    if (timed) ctx->k_valid = true;
+    return 0;
+}
+
+int upload_ant(uwbgo_ctx *ctx, const DevTopo &g, const uwbgo_batch *in, cudaStream_t st,
+               const double **d_ant)
+{
+    *d_ant = nullptr;
+    if (g.K <= 0) return 0;
+    int rc = ctx->ant.reserve(sizeof(double) * 3 * (size_t)g.K);
+    if (rc) return rc;
+    /* ant_offsets is host memory in both API flavours; tiny, copied synchronously w.r.t. host */
+    CU(cudaMemcpyAsync(ctx->ant.p, in->ant_offsets, sizeof(double) * 3 * (size_t)g.K,
+                       cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    *d_ant = static_cast<const double *>(ctx->ant.p);
+    return 0;
+}
+
+int user_stream_begin(uwbgo_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->ws_pending) CU(cudaStreamWaitEvent(st, ctx->ws_free, 0));
+    return 0;
+}
+int user_stream_end(uwbgo_ctx *ctx, cudaStream_t st)
+{
+    CU(cudaEventRecord(ctx->ws_free, st));
+    ctx->ws_pending = true;
+    return 0;
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" {
+
+int uwbgo_abi_version(void) { return UWBGO_ABI_VERSION; }
+
+void uwbgo_config_default(uwbgo_config *cfg)
+{
+    if (!cfg) return;
+    cfg->max_iterations = 20;       /* optimizer/maximum_iteration default, localization.cpp:65 */
+    cfg->max_trials = 10;           /* g2o OptimizationAlgorithmLevenberg maxTrialsAfterFailure  */
+    cfg->orthogonalize_after = 1000;/* g2o VertexSE3::orthogonalizeAfter                         */
+    cfg->reserved = 0;
+    cfg->tau = 1e-5;
+    cfg->good_step_lower = 1.0 / 3.0;
+    cfg->good_step_upper = 2.0 / 3.0;
+    cfg->kernel_delta = 1.0;        /* RobustKernelCauchy default delta, localization.cpp:624    */
+    cfg->jacobian_delta = 1e-9;     /* BaseBinaryEdge::linearizeOplus numeric step              */
+}
+
+const char *uwbgo_last_error(void) { return g_last_error.c_str(); }
+
+int uwbgo_create(int device, uwbgo_ctx **out)
+{
+    if (!out) return fail(UWBGO_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(UWBGO_E_NODEVICE, "no CUDA device visible (this library has no CPU path)");
+    }
+    if (device < 0 || device >= n) return fail(UWBGO_E_NODEVICE, "device index out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(UWBGO_E_NODEVICE, std::string("device is sm_") + std::to_string(prop.major) +
+                                          std::to_string(prop.minor) + ", kernels are built for sm_100a only");
+    CU(cudaSetDevice(device));
+    auto ctx = new uwbgo_ctx();
+    ctx->device = device;
+    for (int k = 0; k < MAX_LANES; ++k) {
+        e = cudaStreamCreateWithFlags(&ctx->lane[k].st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lane[k].done, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            uwbgo_destroy(ctx);
+            return fail_cuda(e, "stream/event creation");
+        }
+    }
+    e = cudaEventCreateWithFlags(&ctx->ws_free, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->k0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->k1);
+    if (e != cudaSuccess) {
+        uwbgo_destroy(ctx);
+        return fail_cuda(e, "event creation");
+    }
+    *out = ctx;
+    return 0;
+}
+
+void uwbgo_destroy(uwbgo_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < MAX_LANES; ++k) {
+        ctx->lane[k].stage.release();
+        ctx->lane[k].tile.release();
+        if (ctx->lane[k].done) cudaEventDestroy(ctx->lane[k].done);
+        if (ctx->lane[k].st) cudaStreamDestroy(ctx->lane[k].st);
+    }
+    ctx->misc.release();
+    ctx->ant.release();
+    for (auto &t : ctx->topos) cudaFree(t->dmem);
+    if (ctx->ws_free) cudaEventDestroy(ctx->ws_free);
+    if (ctx->k0) cudaEventDestroy(ctx->k0);
+    if (ctx->k1) cudaEventDestroy(ctx->k1);
+    delete ctx;
+}
+
+int uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    if (windows_per_chunk < 32 || n_lanes < 1 || n_lanes > MAX_LANES)
+        return fail(UWBGO_E_INVALID, "windows_per_chunk >= 32 and 1 <= n_lanes <= 4 required");
+    ctx->chunk = (windows_per_chunk + 31) / 32 * 32;
+    ctx->n_lanes = n_lanes;
+    return 0;
+}
+
+/* pinned host memory for callers that want the host API to overlap copies with compute */
+void *uwbgo_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        g_last_error = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+void uwbgo_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int uwbgo_solve_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
+                             const uwbgo_config *cfg, uwbgo_result *out, void *stream)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    if (!out || (in && in->n_windows > 0 && !out->pose_t)) return fail(UWBGO_E_INVALID, "result.pose_t is NULL");
+    CU(cudaSetDevice(ctx->device));
+    TopoEntry *te = nullptr;
+    int rc = compile_topology(ctx, topo, &te);
+    if (rc) return rc;
+    DevCfg dc;
+    if ((rc = make_cfg(cfg, dc))) return rc;
+    if ((rc = check_batch(*te, in))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = user_stream_begin(ctx, st))) return rc;
+    const double *d_ant = nullptr;
+    if ((rc = upload_ant(ctx, te->gen, in, st, &d_ant))) return rc;
+    if ((rc = run_device(ctx, ctx->lane[0], *te, dc, in, d_ant, out, nullptr, st))) return rc;
+    return user_stream_end(ctx, st);
+}
+
+int uwbgo_linearize_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo,
+                                 const uwbgo_batch *in, const uwbgo_config *cfg, double *H_diag,
+                                 double *H_off, double *b, double *chi2, void *stream)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    TopoEntry *te = nullptr;
+    int rc = compile_topology(ctx, topo, &te);
+    if (rc) return rc;
+    if (!H_diag || !b || (te->gen.N > 1 && !H_off)) return fail(UWBGO_E_INVALID, "output array is NULL");
+    DevCfg dc;
+    if ((rc = make_cfg(cfg, dc))) return rc;
+    if ((rc = check_batch(*te, in))) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = user_stream_begin(ctx, st))) return rc;
+    const double *d_ant = nullptr;
+    if ((rc = upload_ant(ctx, te->gen, in, st, &d_ant))) return rc;
+    StageOut so{H_diag, H_off, b, chi2};
+    if ((rc = run_device(ctx, ctx->lane[0], *te, dc, in, d_ant, nullptr, &so, st))) return rc;
+    return user_stream_end(ctx, st);
+}
+
+int uwbgo_factor_solve_batch_device(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_windows,
+                                    const double *H_diag, const double *H_off, const double *b,
+                                    const double *lambda, double *x, int32_t *ok, void *stream)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    if (n_poses < 1 || n_windows < 0) return fail(UWBGO_E_INVALID, "bad sizes");
+    if (n_windows == 0) return 0;
+    if (!H_diag || !b || !lambda || !x || (n_poses > 1 && !H_off))
+        return fail(UWBGO_E_INVALID, "array is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if ((rc = user_stream_begin(ctx, st))) return rc;
+    if ((rc = ctx->lane[0].tile.reserve(factor_solve_scratch_bytes(n_poses, n_windows)))) return rc;
+    CU(launch_factor_solve(n_poses, n_windows, H_diag, H_off, b, lambda, x, ok,
+                           static_cast<double *>(ctx->lane[0].tile.p), st));
+    ctx->launches += 2;
+    return user_stream_end(ctx, st);
+}
+
+/* ---- host-pointer flavours: chunked, multi-stream pipeline -------------------------------- */
+namespace {
+struct StageLayout {
+    size_t bytes = 0;
+    size_t in_pose_t, in_pose_R, in_cnt, in_anch, in_rd, in_ri, in_pZ, in_pI, in_sZ, in_sI;
+    size_t out_pose_t, out_pose_R, out_cnt, out_chi2, out_status;
+    size_t out_Hd, out_Ho, out_b;
+};
+}  // namespace
+
+static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
+                         const uwbgo_config *cfg, uwbgo_result *out, double *H_diag, double *H_off,
+                         double *b, double *chi2, bool linearize)
+{
+    CU(cudaSetDevice(ctx->device));
+    TopoEntry *te = nullptr;
+    int rc = compile_topology(ctx, topo, &te);
+    if (rc) return rc;
+    DevCfg dc;
+    if ((rc = make_cfg(cfg, dc))) return rc;
+    if ((rc = check_batch(*te, in))) return rc;
+    const DevTopo &g = te->gen;
+    const int64_t W = in->n_windows;
+    if (W == 0) return 0;
+    if (ctx->ws_pending) { /* a device-API call may still own lane 0's workspace */
+        CU(cudaEventSynchronize(ctx->ws_free));
+        ctx->ws_pending = false;
+    }
+    const double *d_ant = nullptr;
+    if ((rc = upload_ant(ctx, g, in, ctx->lane[0].st, &d_ant))) return rc;
+
+    const size_t N = (size_t)g.N;
+    const int64_t chunk = std::min<int64_t>(ctx->chunk, (W + 31) / 32 * 32);
+    StageLayout S;
+    {
+        size_t o = 0;
+        auto take = [&](bool need, size_t per_window) {
+            size_t at = o;
+            if (need) o += ((size_t)chunk * per_window + 255) & ~(size_t)255;
+            return at;
+        };
+        S.in_pose_t = take(true, N * 3 * 8);
+        S.in_pose_R = take(in->pose_R != nullptr, N * 9 * 8);
+        S.in_cnt = take(in->oplus_count != nullptr, N * 4);
+        S.in_anch = take(g.A > 0, (size_t)g.A * 3 * 8);
+        S.in_rd = take(g.Er > 0, (size_t)g.Er * 8);
+        S.in_ri = take(g.Er > 0, (size_t)g.Er * 8);
+        S.in_pZ = take(g.Ep > 0, (size_t)g.Ep * 12 * 8);
+        S.in_pI = take(g.Ep > 0, (size_t)g.Ep * 36 * 8);
+        S.in_sZ = take(g.Es > 0, (size_t)g.Es * 12 * 8);
+        S.in_sI = take(g.Es > 0, (size_t)g.Es * 36 * 8);
+        if (linearize) {
+            S.out_Hd = take(true, N * 36 * 8);
+            S.out_Ho = take(N > 1, (N - 1) * 36 * 8);
+            S.out_b = take(true, N * 6 * 8);
+            S.out_chi2 = take(chi2 != nullptr, 2 * 8);
+        } else {
+            S.out_pose_t = take(true, N * 3 * 8);
+            S.out_pose_R = take(out->pose_R != nullptr, N * 9 * 8);
+            S.out_cnt = take(out->oplus_count != nullptr, N * 4);
+            S.out_chi2 = take(out->chi2 != nullptr, 4 * 8);
+            S.out_status = take(out->status != nullptr, 4 * 4);
+        }
+        S.bytes = o;
+    }
+    const int n_lanes = (int)std::min<int64_t>(ctx->n_lanes, (W + chunk - 1) / chunk);
+    for (int k = 0; k < n_lanes; ++k)
+        if ((rc = ctx->lane[k].stage.reserve(S.bytes))) return rc;
+
+    int first_err = 0;
+    int64_t c = 0;
+    for (int64_t w0 = 0; w0 < W; w0 += chunk, ++c) {
+        Lane &ln = ctx->lane[c % n_lanes];
+        const int64_t wc = std::min<int64_t>(chunk, W - w0);
+        char *sb = static_cast<char *>(ln.stage.p);
+        cudaStream_t st = ln.st;
+        auto h2d = [&](const void *src, size_t off, size_t per_window) -> cudaError_t {
+            if (!src) return cudaSuccess;
+            return cudaMemcpyAsync(sb + off, static_cast<const char *>(src) + (size_t)w0 * per_window,
+                                   (size_t)wc * per_window, cudaMemcpyHostToDevice, st);
+        };
+        auto d2h = [&](void *dst, size_t off, size_t per_window) -> cudaError_t {
+            if (!dst) return cudaSuccess;
+            return cudaMemcpyAsync(static_cast<char *>(dst) + (size_t)w0 * per_window, sb + off,
+                                   (size_t)wc * per_window, cudaMemcpyDeviceToHost, st);
+        };
+        CU(h2d(in->pose_t, S.in_pose_t, N * 3 * 8));
+        CU(h2d(in->pose_R, S.in_pose_R, N * 9 * 8));
+        CU(h2d(in->oplus_count, S.in_cnt, N * 4));
+        CU(h2d(g.A > 0 ? in->anchors : nullptr, S.in_anch, (size_t)g.A * 3 * 8));
+        CU(h2d(g.Er > 0 ? in->range_d : nullptr, S.in_rd, (size_t)g.Er * 8));
+        CU(h2d(g.Er > 0 ? in->range_info : nullptr, S.in_ri, (size_t)g.Er * 8));
+        CU(h2d(g.Ep > 0 ? in->prior_Z : nullptr, S.in_pZ, (size_t)g.Ep * 12 * 8));
+        CU(h2d(g.Ep > 0 ? in->prior_info : nullptr, S.in_pI, (size_t)g.Ep * 36 * 8));
+        CU(h2d(g.Es > 0 ? in->se3_Z : nullptr, S.in_sZ, (size_t)g.Es * 12 * 8));
+        CU(h2d(g.Es > 0 ? in->se3_info : nullptr, S.in_sI, (size_t)g.Es * 36 * 8));
+        uwbgo_batch db{};
+        db.n_windows = wc;
+        db.pose_t = reinterpret_cast<double *>(sb + S.in_pose_t);
+        db.pose_R = in->pose_R ? reinterpret_cast<double *>(sb + S.in_pose_R) : nullptr;
+        db.oplus_count = in->oplus_count ? reinterpret_cast<int32_t *>(sb + S.in_cnt) : nullptr;
+        db.anchors = reinterpret_cast<double *>(sb + S.in_anch);
+        db.ant_offsets = in->ant_offsets;
+        db.range_d = reinterpret_cast<double *>(sb + S.in_rd);
+        db.range_info = reinterpret_cast<double *>(sb + S.in_ri);
+        db.prior_Z = reinterpret_cast<double *>(sb + S.in_pZ);
+        db.prior_info = reinterpret_cast<double *>(sb + S.in_pI);
+        db.se3_Z = reinterpret_cast<double *>(sb + S.in_sZ);
+        db.se3_info = reinterpret_cast<double *>(sb + S.in_sI);
+        if (linearize) {
+            StageOut so{reinterpret_cast<double *>(sb + S.out_Hd),
+                        reinterpret_cast<double *>(sb + S.out_Ho),
+                        reinterpret_cast<double *>(sb + S.out_b),
+                        chi2 ? reinterpret_cast<double *>(sb + S.out_chi2) : nullptr};
+            rc = run_device(ctx, ln, *te, dc, &db, d_ant, nullptr, &so, st);
+            if (rc) { first_err = rc; break; }
+            CU(d2h(H_diag, S.out_Hd, N * 36 * 8));
+            if (N > 1) CU(d2h(H_off, S.out_Ho, (N - 1) * 36 * 8));
+            CU(d2h(b, S.out_b, N * 6 * 8));
+            CU(d2h(chi2, S.out_chi2, 2 * 8));
+        } else {
+            uwbgo_result dr{};
+            dr.pose_t = reinterpret_cast<double *>(sb + S.out_pose_t);
+            dr.pose_R = out->pose_R ? reinterpret_cast<double *>(sb + S.out_pose_R) : nullptr;
+            dr.oplus_count = out->oplus_count ? reinterpret_cast<int32_t *>(sb + S.out_cnt) : nullptr;
+            dr.chi2 = out->chi2 ? reinterpret_cast<double *>(sb + S.out_chi2) : nullptr;
+            dr.status = out->status ? reinterpret_cast<int32_t *>(sb + S.out_status) : nullptr;
+            rc = run_device(ctx, ln, *te, dc, &db, d_ant, &dr, nullptr, st);
+            if (rc) { first_err = rc; break; }
+            CU(d2h(out->pose_t, S.out_pose_t, N * 3 * 8));
+            CU(d2h(out->pose_R, S.out_pose_R, N * 9 * 8));
+            CU(d2h(out->oplus_count, S.out_cnt, N * 4));
+            CU(d2h(out->chi2, S.out_chi2, 4 * 8));
+            CU(d2h(out->status, S.out_status, 4 * 4));
+        }
+    }
+    for (int k = 0; k < n_lanes; ++k) {
+        cudaError_t e = cudaStreamSynchronize(ctx->lane[k].st);
+        if (e != cudaSuccess && !first_err) first_err = fail_cuda(e, "cudaStreamSynchronize");
+    }
+    return first_err;
+}
+
+int uwbgo_solve_batch(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
+                      const uwbgo_config *cfg, uwbgo_result *out)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    if (!out || (in && in->n_windows > 0 && !out->pose_t)) return fail(UWBGO_E_INVALID, "result.pose_t is NULL");
+    return host_pipeline(ctx, topo, in, cfg, out, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+int uwbgo_linearize_batch(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
+                          const uwbgo_config *cfg, double *H_diag, double *H_off, double *b,
+                          double *chi2)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    if (!H_diag || !b || (topo && topo->n_poses > 1 && !H_off))
+        return fail(UWBGO_E_INVALID, "output array is NULL");
+    return host_pipeline(ctx, topo, in, cfg, nullptr, H_diag, H_off, b, chi2, true);
+}
+
+int uwbgo_factor_solve_batch(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_windows,
+                             const double *H_diag, const double *H_off, const double *b,
+                             const double *lambda, double *x, int32_t *ok)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    if (n_poses < 1 || n_windows < 0) return fail(UWBGO_E_INVALID, "bad sizes");
+    if (n_windows == 0) return 0;
+    if (!H_diag || !b || !lambda || !x || (n_poses > 1 && !H_off))
+        return fail(UWBGO_E_INVALID, "array is NULL");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->ws_pending) {
+        CU(cudaEventSynchronize(ctx->ws_free));
+        ctx->ws_pending = false;
+    }
+    const size_t N = (size_t)n_poses, W = (size_t)n_windows;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o_Hd = 0, o_Ho = o_Hd + al(W * N * 36 * 8), o_b = o_Ho + al(W * (N - 1) * 36 * 8 + 8),
+           o_l = o_b + al(W * N * 6 * 8), o_x = o_l + al(W * 8), o_ok = o_x + al(W * N * 6 * 8),
+           total = o_ok + al(W * 4);
+    int rc = ctx->misc.reserve(total);
+    if (rc) return rc;
+    char *m = static_cast<char *>(ctx->misc.p);
+    cudaStream_t st = ctx->lane[0].st;
+    CU(cudaMemcpyAsync(m + o_Hd, H_diag, W * N * 36 * 8, cudaMemcpyHostToDevice, st));
+    if (N > 1) CU(cudaMemcpyAsync(m + o_Ho, H_off, W * (N - 1) * 36 * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m + o_b, b, W * N * 6 * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(m + o_l, lambda, W * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = ctx->lane[0].tile.reserve(factor_solve_scratch_bytes(n_poses, n_windows)))) return rc;
+    CU(launch_factor_solve(n_poses, n_windows, reinterpret_cast<double *>(m + o_Hd),
+                           reinterpret_cast<double *>(m + o_Ho), reinterpret_cast<double *>(m + o_b),
+                           reinterpret_cast<double *>(m + o_l), reinterpret_cast<double *>(m + o_x),
+                           reinterpret_cast<int32_t *>(m + o_ok),
+                           static_cast<double *>(ctx->lane[0].tile.p), st));
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(x, m + o_x, W * N * 6 * 8, cudaMemcpyDeviceToHost, st));
+    if (ok) CU(cudaMemcpyAsync(ok, m + o_ok, W * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int uwbgo_set_profiling(uwbgo_ctx *ctx, int on)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    ctx->profile = on != 0;
+    ctx->k_valid = false;
+    return 0;
+}
+
+double uwbgo_last_kernel_ms(uwbgo_ctx *ctx)
+{
+    if (!ctx || !ctx->k_valid) return -1.0;
+    if (cudaEventSynchronize(ctx->k1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->k0, ctx->k1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+int64_t uwbgo_launch_count(const uwbgo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int uwbgo_last_path(const uwbgo_ctx *ctx) { return ctx ? ctx->last_path : 0; }
+
+double uwbgo_measure_fp64_peak(uwbgo_ctx *ctx, double *elapsed_ms)
+{
+    if (!ctx) return 0.0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0.0;
+    const int iters = 1 << 16;
+    int blocks = 0, threads = 0;
+    if (ctx->misc.reserve(sizeof(double) * 148 * 16 * 256)) return 0.0;
+    cudaStream_t st = ctx->lane[0].st;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    launch_fp64_peak(static_cast<double *>(ctx->misc.p), 1 << 10, st, &blocks, &threads); /* warm-up */
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        launch_fp64_peak(static_cast<double *>(ctx->misc.p), iters, st, &blocks, &threads);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (cudaGetLastError() != cudaSuccess || !(best > 0.f)) return 0.0;
+    if (elapsed_ms) *elapsed_ms = best;
+    double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    return flops / (best * 1e-3);
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+/*
+ * uwbgo_internal.h — types shared by the kernels (uwbgo_kernels.cu) and the C-ABI host layer
+ * (uwbgo_api.cu).  Not part of the public ABI (include/uwbgo.h).
+ *
+ * Device data layout ("tile layout").  One GPU thread solves one window; a warp therefore
+ * owns a TILE of 32 consecutive windows.  Every per-window array lives in HBM as
+ *     arr[tile][row][lane]          (lane = window % 32 fastest)
+ * so that a warp-wide access to one row is one fully coalesced 256-byte transaction and a
+ * tile's rows are one contiguous block that the warp streams front to back (linearise,
+ * substitution sweep) or back to front (factor sweep).  The window-major arrays of the public
+ * ABI are transposed into / out of this layout by the pack / unpack kernels.
+ */
+#ifndef UWBGO_INTERNAL_H
+#define UWBGO_INTERNAL_H
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#include "../../include/uwbgo.h"
+
+namespace uwbgo {
+
+constexpr int TILE = 32;          /* windows per tile = lanes per warp            */
+constexpr int CTA_THREADS = 128;  /* 4 tiles per CTA                              */
+
+/* rows per pose of the H / L records */
+constexpr int HR_FAST = 18;       /* Hd upper 6 | link block 9 | b 3              */
+constexpr int HR_GEN = 63;        /* Hd upper 21 | link block 36 | b 6            */
+
+/* One edge of the shared topology, in g2o insertion order. */
+struct EdgeRec {
+    int32_t kind;    /* UWBGO_EDGE_*                                                       */
+    int32_t a, b;    /* vertex 0 pose index; vertex 1 pose index or anchor index           */
+    int32_t slot;    /* per-kind data slot                                                 */
+    int32_t ant;     /* antenna number of the vertex-0 offset (0 = none)                   */
+    int32_t robust;  /* Cauchy kernel on/off                                               */
+    int32_t base_a;  /* numeric-Jacobian oplus calls made on pose a before this edge's,    */
+    int32_t base_b;  /*   resp. on pose b, within one linearisation (VertexSE3 counter)    */
+};
+
+/* Per-pose gather program for Hessian assembly: the edges touching pose i, in insertion
+ * order, with the role pose i plays (0 = vertex 0 / owner, 1 = vertex 1). */
+struct PoseOp {
+    int32_t edge;
+    int32_t role;
+};
+
+struct DevTopo {
+    int32_t N, A, K, E, Er, Ep, Es;
+    int32_t fast;               /* 1: range edges only, no offsets -> translation-only path */
+    const EdgeRec *edges;       /* [E]                                                       */
+    const PoseOp *ops;          /* concatenated per-pose op lists                            */
+    const int32_t *op_begin;    /* [N+1]                                                     */
+    const int32_t *num_calls;   /* [N] numeric oplus calls per linearisation on pose i       */
+};
+
+struct DevCfg {
+    int32_t max_iterations, max_trials, orth_mod; /* orth_mod = orthogonalize_after + 1 */
+    double tau, good_lo, good_hi, kdelta, jdelta;
+};
+
+/* tile-layout workspace of one launch (all device pointers) */
+struct DevWs {
+    int64_t W;          /* windows in this launch                     */
+    double *T[2];       /* translations   [tile][N*3][32], two buffers */
+    double *Rm[2];      /* rotations      [tile][N*9][32]  (general)  */
+    int32_t *cnt;       /* oplus counters [tile][N][32]   (general)   */
+    const double *anch; /* [tile][A*3][32]                            */
+    const double *rd;   /* [tile][Er][32]                             */
+    const double *ri;   /* [tile][Er][32]                             */
+    const double *pZ;   /* [tile][Ep*12][32]                          */
+    const double *pI;   /* [tile][Ep*36][32]                          */
+    const double *sZ;   /* [tile][Es*12][32]                          */
+    const double *sI;   /* [tile][Es*36][32]                          */
+    double *HB;         /* H records      [tile][N*HR][32]            */
+    double *LR;         /* L records      [tile][N*HR][32]            */
+    const double *ant;  /* [K][3] antenna offsets, plain              */
+    double *chi2;       /* [tile][4][32] (solve) or [tile][2][32]     */
+    int32_t *status;    /* [tile][4][32]                              */
+};
+
+/* pack / unpack job: transpose between window-major [W][C] and tile layout [tile][C][32] */
+struct XposeJob {
+    const void *src;
+    void *dst;
+    int32_t C;       /* columns per window                                  */
+    int32_t elem;    /* element size: 8 (double) or 4 (int32)               */
+    int32_t mode;    /* 0 transpose; 1 identity rotations (tile layout dst); 2 identity rotations */
+                     /* (window-major dst); 3 zero fill (tile layout dst)                       */
+    int32_t aux;
+};
+constexpr int MAX_XPOSE_JOBS = 12;
+struct XposeJobs {
+    int32_t n;
+    int32_t pad;
+    int64_t W;
+    XposeJob job[MAX_XPOSE_JOBS];
+};
+
+/* launchers (uwbgo_kernels.cu); all asynchronous on `st`, return cudaGetLastError() */
+cudaError_t launch_pack(const XposeJobs &jobs, cudaStream_t st);
+cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st);
+cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st);
+cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,
+                             cudaStream_t st);
+/* expand H records (tile layout) into the public window-major H_diag/H_off/b arrays */
+cudaError_t launch_expand_H(const DevTopo &topo, const DevWs &ws, double *H_diag, double *H_off,
+                            double *b, cudaStream_t st);
+/* (H + lambda I) x = b on window-major public arrays */
+cudaError_t launch_factor_solve(int32_t N, int64_t W, const double *H_diag, const double *H_off,
+                                const double *b, const double *lambda, double *x, int32_t *ok,
+                                double *scratch, cudaStream_t st);
+size_t factor_solve_scratch_bytes(int32_t N, int64_t W);
+cudaError_t launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads);
+
+inline int64_t n_tiles(int64_t W) { return (W + TILE - 1) / TILE; }
+
+}  // namespace uwbgo
+#endif

@@ -1,0 +1,1394 @@
+/*
+ * uwbgo_kernels.cu — sm_100a kernels of the batched sliding-window LM solver.
+ *
+ * What is replaced (reference sair-lab/localization): everything below
+ * Localization::solve() (src/localization/localization.cpp:164-192), i.e. g2o's
+ * initializeOptimization() + optimize(iteration_max) with BlockSolver_6_3,
+ * OptimizationAlgorithmLevenberg and LinearSolverCholmod (localization.h:82-85), over
+ * EdgeSE3Range (src/types/types_edge_se3range.cpp:105-114, numeric Jacobian of
+ * BaseBinaryEdge), EdgeSE3Prior (localization.cpp:462-535) and EdgeSE3 (localization.cpp:560-605).
+ *
+ * Mapping to the machine.  Windows are independent and every window of a batch has the same
+ * graph structure, so ONE THREAD SOLVES ONE WINDOW: all 32 lanes of a warp execute the same
+ * instruction on 32 different windows, there is no intra-window reduction, no idle lane in the
+ * sequential block-Cholesky chain, and the FP64 pipe sees 32 independent dependency chains per
+ * warp.  Per-window state (poses, H, L) does not fit in registers or shared memory for 512
+ * windows per SM, so it is streamed through HBM/L2 in the tile layout of uwbgo_internal.h:
+ * every access is a coalesced 256-byte row and every sweep walks a tile's rows monotonically.
+ *
+ * Two instantiations:
+ *   FAST    range edges only, R = I, no antenna offsets.  Rotation rows/columns of H and b are
+ *           exactly zero there (the residual never reads R), so only the translation 3x3 blocks
+ *           are carried; this is bit-identical to carrying the full 6x6 blocks.
+ *   GENERAL full 6x6 blocks: rotations, antenna offsets, EdgeSE3Prior, EdgeSE3.
+ *
+ * Compile with --fmad=false (see uwbgo_math.cuh).
+ */
+#include "uwbgo_internal.h"
+#include "uwbgo_math.cuh"
+
+namespace uwbgo {
+
+/* ------------------------------------------------------------------------------------------ */
+/* small helpers                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+#define ROW(p, r) ((p)[(size_t)(r) * TILE])
+
+UWBGO_DI EdgeRec load_edge(const EdgeRec *e)
+{
+    const int4 *p = reinterpret_cast<const int4 *>(e);
+    int4 u = __ldg(p), v = __ldg(p + 1);
+    EdgeRec r;
+    r.kind = u.x; r.a = u.y; r.b = u.z; r.slot = u.w;
+    r.ant = v.x; r.robust = v.y; r.base_a = v.z; r.base_b = v.w;
+    return r;
+}
+
+struct Cauchy {
+    double dsqr, dsqrReci;
+    UWBGO_DI void init(double delta)
+    {
+        dsqr = delta * delta;
+        dsqrReci = 1.0 / dsqr;
+    }
+    UWBGO_DI double rho0(double e2) const { return dsqr * det_log(dsqrReci * e2 + 1.0); }
+    UWBGO_DI double rho1(double e2) const { return 1.0 / (dsqrReci * e2 + 1.0); }
+};
+
+/* thread-private view of the tile-layout workspace */
+struct Ptrs {
+    double *T[2];  /* translations [N*3] rows */
+    double *Rm[2]; /* rotations    [N*9] rows (GENERAL only) */
+    int32_t *cnt;
+    const double *anch, *rd, *ri, *pZ, *pI, *sZ, *sI;
+    double *HB, *LR;
+};
+
+template <int HR>
+UWBGO_DI Ptrs thread_ptrs(const DevTopo &tp, const DevWs &ws, int64_t w)
+{
+    int64_t tile = w / TILE;
+    int lane = (int)(w % TILE);
+    Ptrs p;
+    p.T[0] = ws.T[0] + (tile * (size_t)tp.N * 3) * TILE + lane;
+    p.T[1] = ws.T[1] + (tile * (size_t)tp.N * 3) * TILE + lane;
+    p.Rm[0] = ws.Rm[0] ? ws.Rm[0] + (tile * (size_t)tp.N * 9) * TILE + lane : nullptr;
+    p.Rm[1] = ws.Rm[1] ? ws.Rm[1] + (tile * (size_t)tp.N * 9) * TILE + lane : nullptr;
+    p.cnt = ws.cnt ? ws.cnt + (tile * (size_t)tp.N) * TILE + lane : nullptr;
+    p.anch = ws.anch ? ws.anch + (tile * (size_t)tp.A * 3) * TILE + lane : nullptr;
+    p.rd = ws.rd ? ws.rd + (tile * (size_t)tp.Er) * TILE + lane : nullptr;
+    p.ri = ws.ri ? ws.ri + (tile * (size_t)tp.Er) * TILE + lane : nullptr;
+    p.pZ = ws.pZ ? ws.pZ + (tile * (size_t)tp.Ep * 12) * TILE + lane : nullptr;
+    p.pI = ws.pI ? ws.pI + (tile * (size_t)tp.Ep * 36) * TILE + lane : nullptr;
+    p.sZ = ws.sZ ? ws.sZ + (tile * (size_t)tp.Es * 12) * TILE + lane : nullptr;
+    p.sI = ws.sI ? ws.sI + (tile * (size_t)tp.Es * 36) * TILE + lane : nullptr;
+    p.HB = ws.HB + (tile * (size_t)tp.N * HR) * TILE + lane;
+    p.LR = ws.LR ? ws.LR + (tile * (size_t)tp.N * HR) * TILE + lane : nullptr;
+    return p;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* linear solver: block-tridiagonal Cholesky of H + lambda I, chain eliminated newest pose       */
+/* first (replaces LinearSolverCholmod::solve).  D = 3 (FAST) or 6 (GENERAL).                   */
+/*   H record of pose i:  Hd_i upper packed | H_{i-1,i} (rows i-1, cols i) | b_i                 */
+/*   L record of pose i:  L_i lower packed, diagonal stored inverted | G_{i-1} | z_i             */
+/* ------------------------------------------------------------------------------------------ */
+template <int D>
+UWBGO_DI bool factor_sweep(const double *__restrict__ HB, double *__restrict__ LR, int N,
+                           double lambda)
+{
+    constexpr int TRI = D * (D + 1) / 2, SQ = D * D, REC = TRI + SQ + D;
+    double G[SQ], zn[D];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < SQ; ++k) G[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) zn[k] = 0.0;
+    for (int i = N - 1; i >= 0; --i) {
+        const double *h = HB + (size_t)i * REC * TILE;
+        double *l = LR + (size_t)i * REC * TILE;
+        const bool link = i + 1 < N;
+        double S[TRI], L[TRI], z[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) {
+                double s = ROW(h, up_idx(D, c, r));
+                if (r == c) s = s + lambda;
+                if (link) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s = fma(-G[r * D + k], G[c * D + k], s);
+                }
+                S[lo_idx(r, c)] = s;
+            }
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double s = S[lo_idx(j, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
+            if (!(s > 0.0)) ok = false;
+            double inv = 1.0 / sqrt(s);
+            L[lo_idx(j, j)] = inv;
+#pragma unroll
+            for (int r = j + 1; r < D; ++r) {
+                double t = S[lo_idx(r, j)];
+#pragma unroll
+                for (int k = 0; k < j; ++k) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
+                L[lo_idx(r, j)] = t * inv;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            double s = ROW(h, TRI + SQ + r);
+            if (link) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) s = fma(-G[r * D + k], zn[k], s);
+            }
+#pragma unroll
+            for (int k = 0; k < r; ++k) s = fma(-L[lo_idx(r, k)], z[k], s);
+            z[r] = s * L[lo_idx(r, r)];
+        }
+#pragma unroll
+        for (int k = 0; k < TRI; ++k) ROW(l, k) = L[k];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            ROW(l, TRI + SQ + k) = z[k];
+            zn[k] = z[k];
+        }
+        if (i > 0) {
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    double s = ROW(h, TRI + r * D + c);
+#pragma unroll
+                    for (int k = 0; k < c; ++k) s = fma(-G[r * D + k], L[lo_idx(c, k)], s);
+                    /* G is overwritten row by row: entries k < c of row r are already new */
+                    G[r * D + c] = s * L[lo_idx(c, c)];
+                }
+#pragma unroll
+            for (int k = 0; k < SQ; ++k) ROW(l, TRI + k) = G[k];
+        }
+    }
+    return ok;
+}
+
+/* x_i = L_i^-T (z_i - G_{i-1}^T x_{i-1}), ascending; xp holds x_{i-1} on entry, x_i on exit */
+template <int D>
+UWBGO_DI void subst_step(const double *__restrict__ l, bool link, double *xp)
+{
+    constexpr int TRI = D * (D + 1) / 2, SQ = D * D;
+    double L[TRI], x[D];
+#pragma unroll
+    for (int k = 0; k < TRI; ++k) L[k] = ROW(l, k);
+#pragma unroll
+    for (int r = D - 1; r >= 0; --r) {
+        double s = ROW(l, TRI + SQ + r);
+        if (link) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(-ROW(l, TRI + k * D + r), xp[k], s);
+        }
+#pragma unroll
+        for (int k = r + 1; k < D; ++k) s = fma(-L[lo_idx(k, r)], x[k], s);
+        x[r] = s * L[lo_idx(r, r)];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) xp[k] = x[k];
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* FAST path (translation-only): EdgeSE3Range with identity offsets on identity rotations       */
+/* ------------------------------------------------------------------------------------------ */
+constexpr int FAST_MAX_CARRY = 2; /* pose-pose range edges between one consecutive pair */
+
+struct FastEnv {
+    const DevTopo *tp;
+    Ptrs p;
+    Cauchy ck;
+    double delta, scalar;
+    double *stash; /* shared memory: [2*FAST_MAX_CARRY][5][CTA_THREADS], this thread's column */
+};
+
+/* computeActiveErrors + activeRobustChi2 / chi2, edges in insertion order */
+UWBGO_DI void fast_chi_pass(const FastEnv &E, const double *__restrict__ T, double &plain,
+                            double &robust)
+{
+    const DevTopo &tp = *E.tp;
+    double p = 0.0, r = 0.0;
+    for (int e = 0; e < tp.E; ++e) {
+        EdgeRec er = load_edge(tp.edges + e);
+        const double *ta = T + (size_t)er.a * 3 * TILE;
+        const double *tb = (er.kind == UWBGO_EDGE_RANGE_ANCHOR ? E.p.anch : T) + (size_t)er.b * 3 * TILE;
+        double n = dist3(ROW(ta, 0), ROW(ta, 1), ROW(ta, 2), ROW(tb, 0), ROW(tb, 1), ROW(tb, 2));
+        double err = ROW(E.p.rd, er.slot) - n;
+        double Oe = ROW(E.p.ri, er.slot) * err;
+        double chi = err * Oe;
+        p = p + chi;
+        r = r + (er.robust ? E.ck.rho0(chi) : chi);
+    }
+    plain = p;
+    robust = r;
+}
+
+/* numeric Jacobian columns 0..2 of a range residual with respect to the translation of the
+ * perturbed end point (px,py,pz); the other end point is (qx,qy,qz).  sign = +1: the perturbed
+ * point is vertex 0 (dt = P - Q); sign = -1: vertex 1 (dt = Q - P, so pass P/Q swapped).
+ * BaseBinaryEdge::linearizeOplus: J[d] = (e(+delta) - e(-delta)) / (2 delta). */
+UWBGO_DI void fast_jac_v0(double px, double py, double pz, double qx, double qy, double qz,
+                          double d, double delta, double scalar, double *J)
+{
+    double ep, em;
+    ep = d - dist3(delta + px, py, pz, qx, qy, qz);
+    em = d - dist3(-delta + px, py, pz, qx, qy, qz);
+    J[0] = scalar * (ep - em);
+    ep = d - dist3(px, delta + py, pz, qx, qy, qz);
+    em = d - dist3(px, -delta + py, pz, qx, qy, qz);
+    J[1] = scalar * (ep - em);
+    ep = d - dist3(px, py, delta + pz, qx, qy, qz);
+    em = d - dist3(px, py, -delta + pz, qx, qy, qz);
+    J[2] = scalar * (ep - em);
+}
+UWBGO_DI void fast_jac_v1(double px, double py, double pz, double qx, double qy, double qz,
+                          double d, double delta, double scalar, double *J)
+{
+    double ep, em;
+    ep = d - dist3(px, py, pz, delta + qx, qy, qz);
+    em = d - dist3(px, py, pz, -delta + qx, qy, qz);
+    J[0] = scalar * (ep - em);
+    ep = d - dist3(px, py, pz, qx, delta + qy, qz);
+    em = d - dist3(px, py, pz, qx, -delta + qy, qz);
+    J[1] = scalar * (ep - em);
+    ep = d - dist3(px, py, pz, qx, qy, delta + qz);
+    em = d - dist3(px, py, pz, qx, qy, -delta + qz);
+    J[2] = scalar * (ep - em);
+}
+
+/* BlockSolver::buildSystem for one window: per pose, gather its edges in insertion order.
+ * Writes the H records; returns max |H_kk| (computeLambdaInit). */
+UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
+{
+    const DevTopo &tp = *E.tp;
+    const int N = tp.N;
+    double maxdiag = 0.0;
+    double cx = ROW(T, 0), cy = ROW(T, 1), cz = ROW(T, 2); /* pose i */
+    double nx = 0.0, ny = 0.0, nz = 0.0;                   /* pose i+1 */
+    for (int i = 0; i < N; ++i) {
+        if (i + 1 < N) {
+            const double *tn = T + (size_t)(i + 1) * 3 * TILE;
+            nx = ROW(tn, 0); ny = ROW(tn, 1); nz = ROW(tn, 2);
+        }
+        double hd[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        double ho[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        double bb[3] = {0.0, 0.0, 0.0};
+        const int ob = __ldg(tp.op_begin + i), oe = __ldg(tp.op_begin + i + 1);
+        for (int o = ob; o < oe; ++o) {
+            int2 op = __ldg(reinterpret_cast<const int2 *>(tp.ops + o));
+            EdgeRec er = load_edge(tp.edges + op.x);
+            double J[3], Ow, omega_r;
+            if (op.y == 0) {
+                double qx, qy, qz;
+                if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+                    const double *an = E.p.anch + (size_t)er.b * 3 * TILE;
+                    qx = ROW(an, 0); qy = ROW(an, 1); qz = ROW(an, 2);
+                } else {
+                    qx = nx; qy = ny; qz = nz;
+                }
+                double d = ROW(E.p.rd, er.slot), info = ROW(E.p.ri, er.slot);
+                double err = d - dist3(cx, cy, cz, qx, qy, qz);
+                fast_jac_v0(cx, cy, cz, qx, qy, qz, d, E.delta, E.scalar, J);
+                double Oe = info * err;
+                omega_r = -Oe;
+                Ow = info;
+                if (er.robust) {
+                    double r1 = E.ck.rho1(err * Oe);
+                    omega_r = omega_r * r1;
+                    Ow = r1 * info;
+                }
+                if (er.kind == UWBGO_EDGE_RANGE_POSE) {
+                    double B[3];
+                    fast_jac_v1(cx, cy, cz, qx, qy, qz, d, E.delta, E.scalar, B);
+                    double AtO[3] = {J[0] * Ow, J[1] * Ow, J[2] * Ow};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) ho[3 * r + c] = fma(AtO[r], B[c], ho[3 * r + c]);
+                    double *st = E.stash + (size_t)er.ant * 5 * CTA_THREADS; /* ant = carry slot */
+                    st[0 * CTA_THREADS] = B[0];
+                    st[1 * CTA_THREADS] = B[1];
+                    st[2 * CTA_THREADS] = B[2];
+                    st[3 * CTA_THREADS] = Ow;
+                    st[4 * CTA_THREADS] = omega_r;
+                }
+            } else {
+                const double *st = E.stash + (size_t)er.ant * 5 * CTA_THREADS;
+                J[0] = st[0 * CTA_THREADS];
+                J[1] = st[1 * CTA_THREADS];
+                J[2] = st[2 * CTA_THREADS];
+                Ow = st[3 * CTA_THREADS];
+                omega_r = st[4 * CTA_THREADS];
+            }
+            /* constructQuadraticForm, 1-D error: b += J^T omega_r ; H += (J^T Ow) J */
+#pragma unroll
+            for (int r = 0; r < 3; ++r) bb[r] = fma(J[r], omega_r, bb[r]);
+            double JtO[3] = {J[0] * Ow, J[1] * Ow, J[2] * Ow};
+            hd[0] = fma(JtO[0], J[0], hd[0]);
+            hd[1] = fma(JtO[0], J[1], hd[1]);
+            hd[2] = fma(JtO[0], J[2], hd[2]);
+            hd[3] = fma(JtO[1], J[1], hd[3]);
+            hd[4] = fma(JtO[1], J[2], hd[4]);
+            hd[5] = fma(JtO[2], J[2], hd[5]);
+        }
+        double *h = E.p.HB + (size_t)i * HR_FAST * TILE;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ROW(h, k) = hd[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ROW(h, 15 + k) = bb[k];
+        if (i + 1 < N) {
+            double *hn = h + (size_t)HR_FAST * TILE;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) ROW(hn, 6 + k) = ho[k];
+        }
+        double v;
+        v = fabs(hd[0]); if (v > maxdiag) maxdiag = v;
+        v = fabs(hd[3]); if (v > maxdiag) maxdiag = v;
+        v = fabs(hd[5]); if (v > maxdiag) maxdiag = v;
+        cx = nx; cy = ny; cz = nz;
+    }
+    return maxdiag;
+}
+
+/* substitution sweep fused with computeScale() and the estimate update (oplus with R = I) */
+UWBGO_DI double fast_solve_update(const FastEnv &E, bool ok, double lambda,
+                                  const double *__restrict__ Tc, double *__restrict__ Tn)
+{
+    const int N = E.tp->N;
+    double xp[3] = {0.0, 0.0, 0.0};
+    double scale = 0.0;
+    for (int i = 0; i < N; ++i) {
+        subst_step<3>(E.p.LR + (size_t)i * HR_FAST * TILE, i > 0, xp);
+        if (!ok) xp[0] = xp[1] = xp[2] = 0.0;
+        const double *h = E.p.HB + (size_t)i * HR_FAST * TILE;
+        const double *t = Tc + (size_t)i * 3 * TILE;
+        double *tn = Tn + (size_t)i * 3 * TILE;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            scale = scale + xp[k] * (lambda * xp[k] + ROW(h, 15 + k));
+            ROW(tn, k) = xp[k] + ROW(t, k);
+        }
+    }
+    return scale;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* GENERAL path: 6x6 blocks                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+struct GenEnv {
+    const DevTopo *tp;
+    const DevCfg *cfg;
+    Ptrs p;
+    const double *ant;
+    Cauchy ck;
+    double delta, scalar;
+};
+
+/* a pose buffer of the GENERAL path: translations and rotations in separate tile arrays */
+struct PoseBuf {
+    double *t, *R;
+};
+UWBGO_DI void load_pose(const PoseBuf &T, int i, Pose &X)
+{
+    const double *q = T.t + (size_t)i * 3 * TILE;
+    const double *m = T.R + (size_t)i * 9 * TILE;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) X.t[k] = ROW(q, k);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) X.R[k] = ROW(m, k);
+}
+UWBGO_DI void store_pose(const PoseBuf &T, int i, const Pose &X)
+{
+    double *q = T.t + (size_t)i * 3 * TILE;
+    double *m = T.R + (size_t)i * 9 * TILE;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ROW(q, k) = X.t[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) ROW(m, k) = X.R[k];
+}
+UWBGO_DI void load_Zinv(const double *__restrict__ Zrows, int slot, Pose &Zinv)
+{
+    Pose Z;
+    const double *q = Zrows + (size_t)slot * 12 * TILE;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Z.R[k] = ROW(q, k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Z.t[k] = ROW(q, 9 + k);
+    pose_inv(Z, Zinv);
+}
+
+/* (X * offset).translation() for a translation-only offset: R o + t */
+UWBGO_DI void offset_point(const GenEnv &E, const Pose &X, int ant, double *P)
+{
+    if (ant > 0) {
+        double o[3] = {__ldg(E.ant + 3 * (ant - 1)), __ldg(E.ant + 3 * (ant - 1) + 1),
+                       __ldg(E.ant + 3 * (ant - 1) + 2)};
+        mat3_vec_add(X.R, o, X.t, P);
+    } else {
+        P[0] = X.t[0]; P[1] = X.t[1]; P[2] = X.t[2];
+    }
+}
+
+/* toVectorMQT(Zinv * Xi^-1 * Xj) */
+UWBGO_DI void se3_error(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *e)
+{
+    Pose Xi_inv, T, Dl;
+    pose_inv(Xi, Xi_inv);
+    pose_mul(Zinv, Xi_inv, T);
+    pose_mul(T, Xj, Dl);
+    double q[4];
+    R_to_quat(Dl.R, q);
+    e[0] = Dl.t[0]; e[1] = Dl.t[1]; e[2] = Dl.t[2];
+    e[3] = q[0]; e[4] = q[1]; e[5] = q[2];
+}
+
+/* chi2 = e . (Omega e) for a 6-D edge; Oe returned */
+UWBGO_DI double chi2_6(const double *__restrict__ Irows, int slot, const double *e, double *Oe)
+{
+    const double *O = Irows + (size_t)slot * 36 * TILE;
+    double chi = 0.0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double s = ROW(O, 6 * r) * e[0];
+#pragma unroll
+        for (int c = 1; c < 6; ++c) s = s + ROW(O, 6 * r + c) * e[c];
+        Oe[r] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) chi = chi + e[r] * Oe[r];
+    return chi;
+}
+
+UWBGO_DI void gen_chi_pass(const GenEnv &E, const PoseBuf &T, double &plain, double &robust)
+{
+    const DevTopo &tp = *E.tp;
+    double p = 0.0, r = 0.0;
+    for (int e = 0; e < tp.E; ++e) {
+        EdgeRec er = load_edge(tp.edges + e);
+        double chi;
+        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
+            Pose Xa;
+            load_pose(T, er.a, Xa);
+            double P0[3], Q[3];
+            offset_point(E, Xa, er.ant, P0);
+            if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+                const double *an = E.p.anch + (size_t)er.b * 3 * TILE;
+                Q[0] = ROW(an, 0); Q[1] = ROW(an, 1); Q[2] = ROW(an, 2);
+            } else {
+                const double *tb = T.t + (size_t)er.b * 3 * TILE;
+                Q[0] = ROW(tb, 0); Q[1] = ROW(tb, 1); Q[2] = ROW(tb, 2);
+            }
+            double err = ROW(E.p.rd, er.slot) - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
+            double Oe = ROW(E.p.ri, er.slot) * err;
+            chi = err * Oe;
+        } else if (er.kind == UWBGO_EDGE_PRIOR) {
+            Pose Zinv, X, Dl;
+            load_Zinv(E.p.pZ, er.slot, Zinv);
+            load_pose(T, er.a, X);
+            pose_mul(Zinv, X, Dl);
+            double q[4], e6[6], Oe[6];
+            R_to_quat(Dl.R, q);
+            e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
+            e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
+            chi = chi2_6(E.p.pI, er.slot, e6, Oe);
+        } else {
+            Pose Zinv, Xi, Xj;
+            load_Zinv(E.p.sZ, er.slot, Zinv);
+            load_pose(T, er.a, Xi);
+            load_pose(T, er.b, Xj);
+            double e6[6], Oe[6];
+            se3_error(Zinv, Xi, Xj, e6);
+            chi = chi2_6(E.p.sI, er.slot, e6, Oe);
+        }
+        p = p + chi;
+        r = r + (er.robust ? E.ck.rho0(chi) : chi);
+    }
+    plain = p;
+    robust = r;
+}
+
+/* numeric Jacobian of a range residual wrt vertex 0 (pose X with antenna offset `ant`); Q is the
+ * other end point.  c0 = the pose's oplus counter when this linearisation started, base = oplus
+ * calls made on it by earlier edges of this linearisation.  Call k trips the re-orthogonalisation
+ * of the PERTURBED estimate when (c0 + k) % mod == 0 (VertexSE3::oplusImpl; push/pop restores the
+ * estimate, not the counter). */
+UWBGO_DI void gen_jac_v0(const GenEnv &E, const Pose &X, int ant, const double *Q, double d, int c0,
+                         int base, double *J)
+{
+    const int mod = E.cfg->orth_mod;
+    double o[3] = {0.0, 0.0, 0.0};
+    if (ant > 0) {
+        o[0] = __ldg(E.ant + 3 * (ant - 1));
+        o[1] = __ldg(E.ant + 3 * (ant - 1) + 1);
+        o[2] = __ldg(E.ant + 3 * (ant - 1) + 2);
+    }
+    int call = c0 + base;
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+        double epm[2];
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            ++call;
+            double v = sg == 0 ? E.delta : -E.delta;
+            double tp[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) tp[r] = X.R[3 * r + dd] * v + X.t[r];
+            double P[3];
+            if (ant > 0) {
+                if (call % mod == 0) {
+                    double Rp[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Rp[k] = X.R[k];
+                    orthogonalize(Rp);
+                    mat3_vec_add(Rp, o, tp, P);
+                } else
+                    mat3_vec_add(X.R, o, tp, P);
+            } else {
+                P[0] = tp[0]; P[1] = tp[1]; P[2] = tp[2];
+            }
+            epm[sg] = d - dist3(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
+        }
+        J[dd] = E.scalar * (epm[0] - epm[1]);
+    }
+    if (ant > 0) {
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd) {
+            double epm[2];
+#pragma unroll
+            for (int sg = 0; sg < 2; ++sg) {
+                ++call;
+                double q[3] = {0.0, 0.0, 0.0};
+                q[dd] = sg == 0 ? E.delta : -E.delta;
+                double Rinc[9], Rp[9], P[3];
+                increment_R(q, Rinc);
+                mat3_mul(X.R, Rinc, Rp);
+                if (call % mod == 0) orthogonalize(Rp);
+                mat3_vec_add(Rp, o, X.t, P);
+                epm[sg] = d - dist3(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
+            }
+            J[3 + dd] = E.scalar * (epm[0] - epm[1]);
+        }
+    } else {
+        J[3] = 0.0; J[4] = 0.0; J[5] = 0.0;
+    }
+}
+
+/* numeric Jacobian wrt vertex 1 (pose X, identity offset); P0 is the unperturbed vertex-0 point.
+ * Its point is X.t, which only translation increments move: rotation columns are exactly 0 and a
+ * re-orthogonalisation of the perturbed R is unobservable. */
+UWBGO_DI void gen_jac_v1(const GenEnv &E, const double *P0, const Pose &X, double d, double *J)
+{
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+        double epm[2];
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            double v = sg == 0 ? E.delta : -E.delta;
+            double tp[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) tp[r] = X.R[3 * r + dd] * v + X.t[r];
+            epm[sg] = d - dist3(P0[0], P0[1], P0[2], tp[0], tp[1], tp[2]);
+        }
+        J[dd] = E.scalar * (epm[0] - epm[1]);
+    }
+    J[3] = 0.0; J[4] = 0.0; J[5] = 0.0;
+}
+
+/* rows of the quaternion product matrices, 4-vectors ordered {w,x,y,z}; q = {x,y,z,w} */
+UWBGO_DI void quat_left(const double *q, double *M)
+{
+    double w = q[3], x = q[0], y = q[1], z = q[2];
+    M[0] = w;  M[1] = -x; M[2] = -y;  M[3] = -z;
+    M[4] = x;  M[5] = w;  M[6] = -z;  M[7] = y;
+    M[8] = y;  M[9] = z;  M[10] = w;  M[11] = -x;
+    M[12] = z; M[13] = -y; M[14] = x; M[15] = w;
+}
+UWBGO_DI void quat_right(const double *q, double *M)
+{
+    double w = q[3], x = q[0], y = q[1], z = q[2];
+    M[0] = w;  M[1] = -x; M[2] = -y;  M[3] = -z;
+    M[4] = x;  M[5] = w;  M[6] = z;   M[7] = -y;
+    M[8] = y;  M[9] = -z; M[10] = w;  M[11] = x;
+    M[12] = z; M[13] = y; M[14] = -x; M[15] = w;
+}
+
+/* d(vector part of qE (x) dq)/d(dq) = w I + [q]x */
+UWBGO_DI void set_jqq(const double *q, double *J /* 6x6, block (3,3) */)
+{
+    double w = q[3], x = q[0], y = q[1], z = q[2];
+    J[6 * 3 + 3] = w;  J[6 * 3 + 4] = -z; J[6 * 3 + 5] = y;
+    J[6 * 4 + 3] = z;  J[6 * 4 + 4] = w;  J[6 * 4 + 5] = -x;
+    J[6 * 5 + 3] = -y; J[6 * 5 + 4] = x;  J[6 * 5 + 5] = w;
+}
+
+/* analytic Jacobians of EdgeSE3 (computeEdgeSE3Gradient with identity offsets) */
+UWBGO_DI void se3_jacobians(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *Ji, double *Jj,
+                            bool want_i)
+{
+    Pose Xi_inv, Bm, AB;
+    pose_inv(Xi, Xi_inv);
+    pose_mul(Xi_inv, Xj, Bm);
+    pose_mul(Zinv, Bm, AB);
+#pragma unroll
+    for (int k = 0; k < 36; ++k) Jj[k] = 0.0;
+    double qE[4];
+    R_to_quat(AB.R, qE);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Jj[6 * r + c] = AB.R[3 * r + c];
+    set_jqq(qE, Jj);
+    if (!want_i) return;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) Ji[k] = 0.0;
+    const double *Ra = Zinv.R, *tb = Bm.t;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Ji[6 * r + c] = -Ra[3 * r + c];
+    double S[9] = {0.0, -2.0 * tb[2], 2.0 * tb[1], 2.0 * tb[2], 0.0, -2.0 * tb[0],
+                   -2.0 * tb[1], 2.0 * tb[0], 0.0};
+    double RaS[9];
+    mat3_mul(Ra, S, RaS);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Ji[6 * r + 3 + c] = RaS[3 * r + c];
+    double qA[4], qB[4], Lm[16], Rm[16];
+    R_to_quat(Ra, qA);
+    R_to_quat(Bm.R, qB);
+    quat_left(qA, Lm);
+    quat_right(qB, Rm);
+    double wAB = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wAB = wAB + Lm[k] * Rm[4 * k];
+    double sgn = wAB < 0.0 ? 1.0 : -1.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s = s + Lm[4 * (r + 1) + k] * Rm[4 * k + (c + 1)];
+            Ji[6 * (3 + r) + 3 + c] = sgn * s;
+        }
+}
+
+/* constructQuadraticForm pieces.  hd = upper packed 6x6 (21), ho = 6x6, bb = 6 */
+UWBGO_DI void acc1_diag(const double *J, double Ow, double omega_r, double *hd, double *bb)
+{
+#pragma unroll
+    for (int r = 0; r < 6; ++r) bb[r] = fma(J[r], omega_r, bb[r]);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double JtO = J[r] * Ow;
+#pragma unroll
+        for (int c = r; c < 6; ++c) hd[up_idx(6, r, c)] = fma(JtO, J[c], hd[up_idx(6, r, c)]);
+    }
+}
+UWBGO_DI void acc1_off(const double *A, const double *B, double Ow, double *ho)
+{
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double AtO = A[r] * Ow;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) ho[6 * r + c] = fma(AtO, B[c], ho[6 * r + c]);
+    }
+}
+/* JtO = J^T Ow (6x6, Ow row-major rows in tile layout scaled by r1 when robust) */
+UWBGO_DI void jt_omega(const double *J, const double *__restrict__ O, bool robust, double r1,
+                       double *JtO)
+{
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double ow[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double v = ROW(O, 6 * k + c);
+            ow[k] = robust ? r1 * v : v;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double s = J[r] * ow[0];
+#pragma unroll
+            for (int k = 1; k < 6; ++k) s = fma(J[6 * k + r], ow[k], s);
+            JtO[6 * r + c] = s;
+        }
+    }
+}
+UWBGO_DI void acc6_b(const double *J, const double *omega_r, double *bb)
+{
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double s = J[r] * omega_r[0];
+#pragma unroll
+        for (int k = 1; k < 6; ++k) s = fma(J[6 * k + r], omega_r[k], s);
+        bb[r] = bb[r] + s;
+    }
+}
+UWBGO_DI void acc6_diag(const double *JtO, const double *J, double *hd)
+{
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) {
+            double s = JtO[6 * r] * J[c];
+#pragma unroll
+            for (int k = 1; k < 6; ++k) s = fma(JtO[6 * r + k], J[6 * k + c], s);
+            hd[up_idx(6, r, c)] = hd[up_idx(6, r, c)] + s;
+        }
+}
+UWBGO_DI void acc6_off(const double *AtO, const double *B, double *ho)
+{
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double s = AtO[6 * r] * B[c];
+#pragma unroll
+            for (int k = 1; k < 6; ++k) s = fma(AtO[6 * r + k], B[6 * k + c], s);
+            ho[6 * r + c] = ho[6 * r + c] + s;
+        }
+}
+
+/* BlockSolver::buildSystem, general edges.  Advances the oplus counters by the numeric-Jacobian
+ * calls.  Returns max |H_kk|. */
+__device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
+{
+    const DevTopo &tp = *E.tp;
+    const int N = tp.N, mod = E.cfg->orth_mod;
+    double maxdiag = 0.0;
+    for (int i = 0; i < N; ++i) {
+        Pose Xi;
+        load_pose(T, i, Xi);
+        const int ci = E.p.cnt[(size_t)i * TILE];
+        double hd[21], ho[36], bb[6];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) hd[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 36; ++k) ho[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bb[k] = 0.0;
+        const int ob = __ldg(tp.op_begin + i), oe = __ldg(tp.op_begin + i + 1);
+        for (int o = ob; o < oe; ++o) {
+            int2 op = __ldg(reinterpret_cast<const int2 *>(tp.ops + o));
+            EdgeRec er = load_edge(tp.edges + op.x);
+            if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
+                double d = ROW(E.p.rd, er.slot), info = ROW(E.p.ri, er.slot);
+                double P0[3], Q[3], J[6];
+                Pose Xo; /* the other pose of a pose-pose edge */
+                if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+                    const double *an = E.p.anch + (size_t)er.b * 3 * TILE;
+                    Q[0] = ROW(an, 0); Q[1] = ROW(an, 1); Q[2] = ROW(an, 2);
+                    offset_point(E, Xi, er.ant, P0);
+                } else if (op.y == 0) {
+                    load_pose(T, er.b, Xo);
+                    Q[0] = Xo.t[0]; Q[1] = Xo.t[1]; Q[2] = Xo.t[2];
+                    offset_point(E, Xi, er.ant, P0);
+                } else {
+                    load_pose(T, er.a, Xo);
+                    Q[0] = Xi.t[0]; Q[1] = Xi.t[1]; Q[2] = Xi.t[2];
+                    offset_point(E, Xo, er.ant, P0);
+                }
+                double err = d - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
+                double Oe = info * err;
+                double omega_r = -Oe, Ow = info;
+                if (er.robust) {
+                    double r1 = E.ck.rho1(err * Oe);
+                    omega_r = omega_r * r1;
+                    Ow = r1 * info;
+                }
+                if (op.y == 0) {
+                    gen_jac_v0(E, Xi, er.ant, Q, d, ci, er.base_a, J);
+                    acc1_diag(J, Ow, omega_r, hd, bb);
+                    if (er.kind == UWBGO_EDGE_RANGE_POSE) {
+                        double B[6];
+                        gen_jac_v1(E, P0, Xo, d, B);
+                        acc1_off(J, B, Ow, ho);
+                    }
+                } else {
+                    gen_jac_v1(E, P0, Xi, d, J);
+                    acc1_diag(J, Ow, omega_r, hd, bb);
+                }
+            } else if (er.kind == UWBGO_EDGE_PRIOR) {
+                Pose Zinv, Dl;
+                load_Zinv(E.p.pZ, er.slot, Zinv);
+                pose_mul(Zinv, Xi, Dl);
+                double q[4], e6[6], Oe[6], J[36], JtO[36];
+                R_to_quat(Dl.R, q);
+                e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
+                e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
+                double chi = chi2_6(E.p.pI, er.slot, e6, Oe);
+                double r1 = er.robust ? E.ck.rho1(chi) : 1.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    Oe[k] = -Oe[k];
+                    if (er.robust) Oe[k] = Oe[k] * r1;
+                }
+#pragma unroll
+                for (int k = 0; k < 36; ++k) J[k] = 0.0;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) J[6 * r + c] = Dl.R[3 * r + c];
+                set_jqq(q, J);
+                acc6_b(J, Oe, bb);
+                jt_omega(J, E.p.pI + (size_t)er.slot * 36 * TILE, er.robust != 0, r1, JtO);
+                acc6_diag(JtO, J, hd);
+            } else { /* EdgeSE3 */
+                Pose Zinv, Xo;
+                load_Zinv(E.p.sZ, er.slot, Zinv);
+                double e6[6], Oe[6], Ji[36], Jj[36], JtO[36];
+                if (op.y == 0) {
+                    load_pose(T, er.b, Xo);
+                    se3_error(Zinv, Xi, Xo, e6);
+                    se3_jacobians(Zinv, Xi, Xo, Ji, Jj, true);
+                } else {
+                    load_pose(T, er.a, Xo);
+                    se3_error(Zinv, Xo, Xi, e6);
+                    se3_jacobians(Zinv, Xo, Xi, Ji, Jj, false);
+                }
+                double chi = chi2_6(E.p.sI, er.slot, e6, Oe);
+                double r1 = er.robust ? E.ck.rho1(chi) : 1.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    Oe[k] = -Oe[k];
+                    if (er.robust) Oe[k] = Oe[k] * r1;
+                }
+                const double *O = E.p.sI + (size_t)er.slot * 36 * TILE;
+                if (op.y == 0) {
+                    acc6_b(Ji, Oe, bb);
+                    jt_omega(Ji, O, er.robust != 0, r1, JtO);
+                    acc6_diag(JtO, Ji, hd);
+                    acc6_off(JtO, Jj, ho);
+                } else {
+                    acc6_b(Jj, Oe, bb);
+                    jt_omega(Jj, O, er.robust != 0, r1, JtO);
+                    acc6_diag(JtO, Jj, hd);
+                }
+            }
+        }
+        double *h = E.p.HB + (size_t)i * HR_GEN * TILE;
+#pragma unroll
+        for (int k = 0; k < 21; ++k) ROW(h, k) = hd[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ROW(h, 57 + k) = bb[k];
+        if (i + 1 < N) {
+            double *hn = h + (size_t)HR_GEN * TILE;
+#pragma unroll
+            for (int k = 0; k < 36; ++k) ROW(hn, 21 + k) = ho[k];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double v = fabs(hd[up_idx(6, r, r)]);
+            if (v > maxdiag) maxdiag = v;
+        }
+        E.p.cnt[(size_t)i * TILE] = (ci + __ldg(tp.num_calls + i)) % mod;
+    }
+    return maxdiag;
+}
+
+__device__ __noinline__ double gen_solve_update(const GenEnv &E, bool ok, double lambda,
+                                                const PoseBuf &Tc, const PoseBuf &Tn)
+{
+    const int N = E.tp->N, mod = E.cfg->orth_mod;
+    double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double scale = 0.0;
+    for (int i = 0; i < N; ++i) {
+        subst_step<6>(E.p.LR + (size_t)i * HR_GEN * TILE, i > 0, xp);
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) xp[k] = 0.0;
+        }
+        const double *h = E.p.HB + (size_t)i * HR_GEN * TILE;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) scale = scale + xp[k] * (lambda * xp[k] + ROW(h, 57 + k));
+        Pose X;
+        load_pose(Tc, i, X);
+        int c = E.p.cnt[(size_t)i * TILE];
+        pose_oplus(X, xp, c, mod);
+        E.p.cnt[(size_t)i * TILE] = c;
+        store_pose(Tn, i, X);
+    }
+    return scale;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* optimize(iteration_max) with OptimizationAlgorithmLevenberg, one window per thread           */
+/* ------------------------------------------------------------------------------------------ */
+template <bool FAST>
+struct Path;
+
+template <>
+struct Path<true> {
+    FastEnv E;
+    UWBGO_DI void chi(int buf, double &p, double &r) const { fast_chi_pass(E, E.p.T[buf], p, r); }
+    UWBGO_DI double linearize(int buf) const { return fast_linearize(E, E.p.T[buf]); }
+    UWBGO_DI bool factor(double lambda) const
+    {
+        if (!(lambda > 0.0)) return false; /* rotation pivots are exactly lambda */
+        return factor_sweep<3>(E.p.HB, E.p.LR, E.tp->N, lambda);
+    }
+    UWBGO_DI double update(bool ok, double lambda, int from, int to) const
+    {
+        return fast_solve_update(E, ok, lambda, E.p.T[from], E.p.T[to]);
+    }
+};
+template <>
+struct Path<false> {
+    GenEnv E;
+    UWBGO_DI PoseBuf buf(int k) const { return PoseBuf{E.p.T[k], E.p.Rm[k]}; }
+    UWBGO_DI void chi(int k, double &p, double &r) const { gen_chi_pass(E, buf(k), p, r); }
+    UWBGO_DI double linearize(int k) const { return gen_linearize(E, buf(k)); }
+    UWBGO_DI bool factor(double lambda) const
+    {
+        return factor_sweep<6>(E.p.HB, E.p.LR, E.tp->N, lambda);
+    }
+    UWBGO_DI double update(bool ok, double lambda, int from, int to) const
+    {
+        return gen_solve_update(E, ok, lambda, buf(from), buf(to));
+    }
+};
+
+template <bool FAST>
+UWBGO_DI void lm_window(const Path<FAST> &P, const DevCfg &cfg, double *chi2_out,
+                        int32_t *status_out, int &cur_out)
+{
+    double lambda = 0.0, ni = 2.0, stale, plainCur, currentChi;
+    int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0;
+    P.chi(cur, plainCur, currentChi);
+    stale = plainCur;
+    for (int it = 0; it < cfg.max_iterations; ++it) {
+        stale = plainCur; /* computeActiveErrors at unchanged estimates */
+        double maxdiag = P.linearize(cur);
+        if (it == 0) {
+            lambda = cfg.tau * maxdiag;
+            ni = 2.0;
+        }
+        double rho = 0.0;
+        int q = 0;
+        do {
+            bool ok = P.factor(lambda);
+            if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;
+            double scale = P.update(ok, lambda, cur, cur ^ 1);
+            double tplain, tempChi;
+            P.chi(cur ^ 1, tplain, tempChi);
+            stale = tplain;
+            if (!ok) tempChi = DBL_MAX;
+            scale = scale + 1e-3;
+            rho = (currentChi - tempChi) / scale;
+            const bool fin = isfinite(tempChi);
+            if (!fin) flags |= UWBGO_FLAG_NONFINITE;
+            if (rho > 0.0 && fin) {
+                double t = 2.0 * rho - 1.0;
+                double alpha = 1.0 - (t * t) * t;
+                alpha = (cfg.good_hi < alpha) ? cfg.good_hi : alpha;
+                double sf = (cfg.good_lo < alpha) ? alpha : cfg.good_lo;
+                lambda = lambda * sf;
+                ni = 2.0;
+                currentChi = tempChi;
+                plainCur = tplain;
+                cur ^= 1;
+            } else {
+                lambda = lambda * ni;
+                ni = ni * 2.0;
+            }
+            ++q;
+            ++trials_total;
+        } while (rho < 0.0 && q < cfg.max_trials);
+        ++iterations;
+        qlast = q;
+        if (q == cfg.max_trials || rho == 0.0) {
+            flags |= UWBGO_FLAG_TERMINATED;
+            break;
+        }
+    }
+    ROW(chi2_out, 0) = plainCur;
+    ROW(chi2_out, 1) = currentChi;
+    ROW(chi2_out, 2) = stale;
+    ROW(chi2_out, 3) = lambda;
+    ROW(status_out, 0) = iterations;
+    ROW(status_out, 1) = trials_total;
+    ROW(status_out, 2) = flags;
+    ROW(status_out, 3) = qlast;
+    cur_out = cur;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 4)
+lm_fast_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
+{
+    __shared__ double stash[2 * FAST_MAX_CARRY * 5 * CTA_THREADS];
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (w >= ws.W) return;
+    Path<true> P;
+    P.E.tp = &tp;
+    P.E.p = thread_ptrs<HR_FAST>(tp, ws, w);
+    P.E.ck.init(cfg.kdelta);
+    P.E.delta = cfg.jdelta;
+    P.E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    P.E.stash = stash + threadIdx.x;
+    const int64_t tile = w / TILE;
+    const int lane = (int)(w % TILE);
+    int cur;
+    lm_window<true>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
+    if (cur) { /* result always leaves in buffer 0 */
+        for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T[0], r) = ROW(P.E.p.T[1], r);
+    }
+    if (P.E.p.cnt) { /* VertexSE3::_numOplusCalls: 12 per range edge end per linearisation, 1 per trial */
+        const int it = ROW(ws.status + tile * 4 * TILE + lane, 0), tr = ROW(ws.status + tile * 4 * TILE + lane, 1);
+        for (int i = 0; i < tp.N; ++i) {
+            long long c = (long long)P.E.p.cnt[(size_t)i * TILE] + (long long)it * __ldg(tp.num_calls + i) + tr;
+            P.E.p.cnt[(size_t)i * TILE] = (int)(c % cfg.orth_mod);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS)
+lm_general_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
+{
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (w >= ws.W) return;
+    Path<false> P;
+    P.E.tp = &tp;
+    P.E.cfg = &cfg;
+    P.E.p = thread_ptrs<HR_GEN>(tp, ws, w);
+    P.E.ant = ws.ant;
+    P.E.ck.init(cfg.kdelta);
+    P.E.delta = cfg.jdelta;
+    P.E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    const int64_t tile = w / TILE;
+    const int lane = (int)(w % TILE);
+    int cur;
+    lm_window<false>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
+    if (cur) {
+        for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T[0], r) = ROW(P.E.p.T[1], r);
+        for (int r = 0; r < tp.N * 9; ++r) ROW(P.E.p.Rm[0], r) = ROW(P.E.p.Rm[1], r);
+    }
+}
+
+/* one linearisation: computeActiveErrors + buildSystem; chi2 = {plain, robust} */
+__global__ void __launch_bounds__(CTA_THREADS, 4)
+linearize_fast_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
+{
+    __shared__ double stash[2 * FAST_MAX_CARRY * 5 * CTA_THREADS];
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (w >= ws.W) return;
+    FastEnv E;
+    E.tp = &tp;
+    E.p = thread_ptrs<HR_FAST>(tp, ws, w);
+    E.ck.init(cfg.kdelta);
+    E.delta = cfg.jdelta;
+    E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    E.stash = stash + threadIdx.x;
+    double p, r;
+    fast_chi_pass(E, E.p.T[0], p, r);
+    fast_linearize(E, E.p.T[0]);
+    double *c = ws.chi2 + (w / TILE) * 2 * TILE + (w % TILE);
+    ROW(c, 0) = p;
+    ROW(c, 1) = r;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS)
+linearize_general_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
+{
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (w >= ws.W) return;
+    GenEnv E;
+    E.tp = &tp;
+    E.cfg = &cfg;
+    E.p = thread_ptrs<HR_GEN>(tp, ws, w);
+    E.ant = ws.ant;
+    E.ck.init(cfg.kdelta);
+    E.delta = cfg.jdelta;
+    E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    double p, r;
+    PoseBuf T0{E.p.T[0], E.p.Rm[0]};
+    gen_chi_pass(E, T0, p, r);
+    gen_linearize(E, T0);
+    double *c = ws.chi2 + (w / TILE) * 2 * TILE + (w % TILE);
+    ROW(c, 0) = p;
+    ROW(c, 1) = r;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* layout kernels                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+/* window-major [W][C] -> tile layout [tile][C][32] (pack) and back (unpack), through a padded
+ * shared-memory tile so both sides are coalesced.  grid = (tiles, column chunks of 32, jobs),
+ * block = (32, 8). */
+template <typename T, bool PACK>
+UWBGO_DI void xpose_body(const XposeJob &j, int64_t W, T (*sm)[33])
+{
+    const int64_t tile = blockIdx.x;
+    const int c0 = blockIdx.y * 32;
+    if (c0 >= j.C) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const T *src = static_cast<const T *>(j.src);
+    T *dst = static_cast<T *>(j.dst);
+    if (PACK) {
+        /* read: x runs along columns of one window */
+        for (int y = ty; y < 32; y += 8) {
+            int64_t w = tile * TILE + y;
+            int c = c0 + tx;
+            T v = T(0);
+            if (w < W && c < j.C) v = src[w * j.C + c];
+            sm[y][tx] = v;
+        }
+        __syncthreads();
+        for (int y = ty; y < 32; y += 8) {
+            int c = c0 + y;
+            if (c < j.C) dst[(tile * j.C + c) * TILE + tx] = sm[tx][y];
+        }
+    } else {
+        for (int y = ty; y < 32; y += 8) {
+            int c = c0 + y;
+            T v = T(0);
+            if (c < j.C) v = src[(tile * j.C + c) * TILE + tx];
+            sm[y][tx] = v;
+        }
+        __syncthreads();
+        for (int y = ty; y < 32; y += 8) {
+            int64_t w = tile * TILE + y;
+            int c = c0 + tx;
+            if (w < W && c < j.C) dst[w * j.C + c] = sm[tx][y];
+        }
+    }
+}
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) xpose_kernel(XposeJobs jobs)
+{
+    __shared__ double sm[32][33];
+    const XposeJob &j = jobs.job[blockIdx.z];
+    if (j.mode == 1) { /* identity rotations into a tile-layout [tile][C = N*9][32] array */
+        const int64_t tile = blockIdx.x;
+        const int c0 = blockIdx.y * 32;
+        for (int y = threadIdx.y; y < 32; y += 8) {
+            int c = c0 + y;
+            if (c >= j.C) continue;
+            int k = c % 9;
+            static_cast<double *>(j.dst)[(tile * j.C + c) * TILE + threadIdx.x] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0;
+        }
+        return;
+    }
+    if (j.mode == 2) { /* identity rotations into a window-major [W][C = N*9] array */
+        const int64_t tile = blockIdx.x;
+        const int c0 = blockIdx.y * 32;
+        for (int y = threadIdx.y; y < 32; y += 8) {
+            int64_t w = tile * TILE + y;
+            int c = c0 + threadIdx.x;
+            if (w >= jobs.W || c >= j.C) continue;
+            int k = c % 9;
+            static_cast<double *>(j.dst)[w * j.C + c] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0;
+        }
+        return;
+    }
+    if (j.mode == 3) { /* zero fill of a tile-layout int32/double array, C rows */
+        const int64_t tile = blockIdx.x;
+        const int c0 = blockIdx.y * 32;
+        for (int y = threadIdx.y; y < 32; y += 8) {
+            int c = c0 + y;
+            if (c >= j.C) continue;
+            if (j.elem == 8)
+                static_cast<double *>(j.dst)[(tile * j.C + c) * TILE + threadIdx.x] = 0.0;
+            else
+                static_cast<int32_t *>(j.dst)[(tile * j.C + c) * TILE + threadIdx.x] = 0;
+        }
+        return;
+    }
+    if (j.elem == 8)
+        xpose_body<double, PACK>(j, jobs.W, sm);
+    else
+        xpose_body<int32_t, PACK>(j, jobs.W, reinterpret_cast<int32_t(*)[33]>(sm));
+}
+
+static cudaError_t launch_xpose(const XposeJobs &jobs, bool pack, cudaStream_t st)
+{
+    if (jobs.n <= 0 || jobs.W <= 0) return cudaSuccess;
+    int maxC = 0;
+    for (int k = 0; k < jobs.n; ++k) maxC = jobs.job[k].C > maxC ? jobs.job[k].C : maxC;
+    dim3 grid((unsigned)n_tiles(jobs.W), (unsigned)((maxC + 31) / 32), (unsigned)jobs.n);
+    dim3 block(32, 8);
+    if (pack)
+        xpose_kernel<true><<<grid, block, 0, st>>>(jobs);
+    else
+        xpose_kernel<false><<<grid, block, 0, st>>>(jobs);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack(const XposeJobs &jobs, cudaStream_t st) { return launch_xpose(jobs, true, st); }
+cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st) { return launch_xpose(jobs, false, st); }
+
+static unsigned window_blocks(int64_t W) { return (unsigned)((W + CTA_THREADS - 1) / CTA_THREADS); }
+
+cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st)
+{
+    if (ws.W <= 0) return cudaSuccess;
+    if (topo.fast)
+        lm_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
+    else
+        lm_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,
+                             cudaStream_t st)
+{
+    if (ws.W <= 0) return cudaSuccess;
+    if (topo.fast)
+        linearize_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
+    else
+        linearize_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
+    return cudaGetLastError();
+}
+
+/* H records (tile layout) -> public H_diag [W][N][36] (both triangles), H_off [W][N-1][36],
+ * b [W][N][6].  One thread per (window, pose); reads coalesced, writes are 36-double runs. */
+__global__ void __launch_bounds__(CTA_THREADS)
+expand_H_kernel(DevTopo tp, DevWs ws, double *__restrict__ H_diag, double *__restrict__ H_off,
+                double *__restrict__ b)
+{
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    const int i = blockIdx.y;
+    if (w >= ws.W) return;
+    const int N = tp.N;
+    const int64_t tile = w / TILE;
+    const int lane = (int)(w % TILE);
+    double *hd = H_diag + ((size_t)w * N + i) * 36;
+    double *bo = b + ((size_t)w * N + i) * 6;
+    if (tp.fast) {
+        const double *h = ws.HB + ((tile * N + i) * (size_t)HR_FAST) * TILE + lane;
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c) {
+                double v = 0.0;
+                if (r < 3 && c < 3) v = r <= c ? ROW(h, up_idx(3, r, c)) : ROW(h, up_idx(3, c, r));
+                hd[6 * r + c] = v;
+            }
+        for (int r = 0; r < 6; ++r) bo[r] = r < 3 ? ROW(h, 15 + r) : 0.0;
+        if (i > 0) {
+            double *ho = H_off + ((size_t)w * (N - 1) + (i - 1)) * 36;
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c < 6; ++c) ho[6 * r + c] = (r < 3 && c < 3) ? ROW(h, 6 + 3 * r + c) : 0.0;
+        }
+    } else {
+        const double *h = ws.HB + ((tile * N + i) * (size_t)HR_GEN) * TILE + lane;
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c)
+                hd[6 * r + c] = r <= c ? ROW(h, up_idx(6, r, c)) : ROW(h, up_idx(6, c, r));
+        for (int r = 0; r < 6; ++r) bo[r] = ROW(h, 57 + r);
+        if (i > 0) {
+            double *ho = H_off + ((size_t)w * (N - 1) + (i - 1)) * 36;
+            for (int k = 0; k < 36; ++k) ho[k] = ROW(h, 21 + k);
+        }
+    }
+}
+
+cudaError_t launch_expand_H(const DevTopo &topo, const DevWs &ws, double *H_diag, double *H_off,
+                            double *b, cudaStream_t st)
+{
+    if (ws.W <= 0) return cudaSuccess;
+    dim3 grid(window_blocks(ws.W), (unsigned)topo.N);
+    expand_H_kernel<<<grid, CTA_THREADS, 0, st>>>(topo, ws, H_diag, H_off, b);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* stand-alone linear solve on the public window-major arrays (LinearSolverCholmod::solve)      */
+/* ------------------------------------------------------------------------------------------ */
+/* gather one window's H_diag/H_off/b into H records (tile layout), one thread per (window,pose) */
+__global__ void __launch_bounds__(CTA_THREADS)
+compress_H_kernel(int N, int64_t W, const double *__restrict__ H_diag,
+                  const double *__restrict__ H_off, const double *__restrict__ b,
+                  double *__restrict__ HB)
+{
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    const int i = blockIdx.y;
+    if (w >= W) return;
+    const int64_t tile = w / TILE;
+    const int lane = (int)(w % TILE);
+    double *h = HB + ((tile * N + i) * (size_t)HR_GEN) * TILE + lane;
+    const double *hd = H_diag + ((size_t)w * N + i) * 36;
+    for (int r = 0; r < 6; ++r)
+        for (int c = r; c < 6; ++c) ROW(h, up_idx(6, r, c)) = hd[6 * c + r]; /* lower triangle is read */
+    const double *bo = b + ((size_t)w * N + i) * 6;
+    for (int r = 0; r < 6; ++r) ROW(h, 57 + r) = bo[r];
+    if (i > 0) {
+        const double *ho = H_off + ((size_t)w * (N - 1) + (i - 1)) * 36;
+        for (int k = 0; k < 36; ++k) ROW(h, 21 + k) = ho[k];
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS)
+factor_solve_kernel(int N, int64_t W, double *__restrict__ HB, double *__restrict__ LR,
+                    const double *__restrict__ lambda, double *__restrict__ x,
+                    int32_t *__restrict__ okv)
+{
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (w >= W) return;
+    const int64_t tile = w / TILE;
+    const int lane = (int)(w % TILE);
+    double *hb = HB + (tile * (size_t)N * HR_GEN) * TILE + lane;
+    double *lr = LR + (tile * (size_t)N * HR_GEN) * TILE + lane;
+    bool ok = factor_sweep<6>(hb, lr, N, lambda[w]);
+    double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < N; ++i) {
+        subst_step<6>(lr + (size_t)i * HR_GEN * TILE, i > 0, xp);
+        double *xo = x + ((size_t)w * N + i) * 6;
+        for (int k = 0; k < 6; ++k) xo[k] = ok ? xp[k] : 0.0;
+    }
+    if (okv) okv[w] = ok ? 1 : 0;
+}
+
+size_t factor_solve_scratch_bytes(int32_t N, int64_t W)
+{
+    return 2 * (size_t)n_tiles(W) * TILE * (size_t)N * HR_GEN * sizeof(double);
+}
+
+cudaError_t launch_factor_solve(int32_t N, int64_t W, const double *H_diag, const double *H_off,
+                                const double *b, const double *lambda, double *x, int32_t *ok,
+                                double *scratch, cudaStream_t st)
+{
+    if (W <= 0) return cudaSuccess;
+    double *HB = scratch;
+    double *LR = scratch + (size_t)n_tiles(W) * TILE * (size_t)N * HR_GEN;
+    dim3 grid(window_blocks(W), (unsigned)N);
+    compress_H_kernel<<<grid, CTA_THREADS, 0, st>>>(N, W, H_diag, H_off, b, HB);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    factor_solve_kernel<<<window_blocks(W), CTA_THREADS, 0, st>>>(N, W, HB, LR, lambda, x, ok);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* FP64 FMA micro-benchmark: 8 independent chains per thread                                    */
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0,
+           a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 0.999999, c = 1e-6;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+cudaError_t launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    *blocks = sms * 8;
+    *threads = 256;
+    fp64_peak_kernel<<<*blocks, *threads, 0, st>>>(out, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace uwbgo

@@ -1,0 +1,285 @@
+"""GPU parity: the CUDA path (through the C ABI of libuwbgo.so) against the CPU oracle on the same
+seeded inputs.  The bar (BASELINE.json north_star): poses within 1e-6 m, final chi2 within 1e-9
+relative.  Because both sides execute the same IEEE operation sequence the tests ask for more:
+bit-identical poses, chi2, lambda and LM status words."""
+import numpy as np
+import pytest
+
+from localization_b200 import Batch, Config, Topology, synthetic
+from localization_b200._ffi import (EDGE_PRIOR, EDGE_RANGE_ANCHOR, EDGE_RANGE_POSE, EDGE_SE3,
+                                    FLAG_CHOL_FAIL, FLAG_TERMINATED)
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-6       # BASELINE.json: within 1e-6 m on poses
+CHI2_RTOL = 1e-9        # BASELINE.json: within 1e-9 relative on final chi2
+
+
+def assert_parity(got, ref, exact=True):
+    dp = np.abs(got.pose_t - ref.pose_t).max() if got.pose_t.size else 0.0
+    assert dp <= POSE_TOL_M, f"pose error {dp}"
+    den = np.maximum(np.abs(ref.chi2[:, :2]), 1e-300)
+    dc = (np.abs(got.chi2[:, :2] - ref.chi2[:, :2]) / den).max() if got.chi2.size else 0.0
+    assert dc <= CHI2_RTOL, f"relative chi2 error {dc}"
+    if exact:
+        assert np.array_equal(got.status, ref.status)
+        assert np.array_equal(got.pose_t, ref.pose_t), f"poses not bit-identical (max diff {dp})"
+        assert np.array_equal(got.pose_R, ref.pose_R)
+        assert np.array_equal(got.chi2, ref.chi2), f"chi2 not bit-identical (max rel {dc})"
+        assert np.array_equal(got.oplus_count, ref.oplus_count)
+
+
+@pytest.mark.parametrize("W,N,A", [(256, 50, 8), (33, 10, 4), (1, 12, 4), (96, 200, 16)])
+def test_uwb_only_fast_path(solver, W, N, A):
+    topo, batch, _ = synthetic.uwb_only(W, N, A, seed=7 + W)
+    cfg = Config(max_iterations=10)
+    got = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 1
+    ref = oracle.solve(topo, batch, cfg)
+    assert_parity(got, ref)
+    assert (ref.status[:, 0] == 10).all()
+
+
+def test_general_path_equals_fast_path(solver):
+    """identity rotations passed explicitly route through the 6x6 kernel: same bits"""
+    topo, batch, _ = synthetic.uwb_only(64, 20, 8, seed=3)
+    cfg = Config(max_iterations=10)
+    fast = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 1
+    batch.pose_R = np.tile(np.eye(3), (64, 20, 1, 1))
+    gen = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 0
+    assert_parity(gen, fast)
+    assert_parity(gen, oracle.solve(topo, batch, cfg))
+
+
+def test_uwb_imu_lidar(solver):
+    topo, batch, _ = synthetic.uwb_imu_lidar(128, 20, 8)
+    cfg = Config(max_iterations=20)
+    got = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 0
+    assert_parity(got, oracle.solve(topo, batch, cfg))
+
+
+def test_uwb_imu_c2_shape(solver):
+    topo, batch, _ = synthetic.uwb_imu_lidar(64, 12, 4, v_max=3.0, antennas=0, lidar=False, seed=11)
+    cfg = Config(max_iterations=10)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+
+
+def test_uwb_twist(solver):
+    topo, batch, _ = synthetic.uwb_twist(128, 15, 8)
+    cfg = Config(max_iterations=12)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+
+
+def test_oplus_counter_carry_and_reorthogonalisation(solver):
+    """VertexSE3::_numOplusCalls carried in close to orthogonalizeAfter: the re-orthogonalisation
+    trips inside numeric Jacobians and inside trial updates"""
+    topo, batch, _ = synthetic.uwb_imu_lidar(64, 12, 8, seed=5)
+    rng = np.random.default_rng(1)
+    batch.oplus_count = rng.integers(900, 1001, size=(64, 12)).astype(np.int32)
+    cfg = Config(max_iterations=8)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+    cfg = Config(max_iterations=4, orthogonalize_after=7)
+    batch.oplus_count = rng.integers(0, 8, size=(64, 12)).astype(np.int32)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+    # fast path only tracks the counter
+    topo, batch, _ = synthetic.uwb_only(40, 10, 4, seed=2)
+    batch.oplus_count = rng.integers(0, 1001, size=(40, 10)).astype(np.int32)
+    cfg = Config(max_iterations=10)
+    got = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 1
+    assert_parity(got, oracle.solve(topo, batch, cfg))
+
+
+def test_linearize_bit_exact(solver):
+    for make, kw in ((synthetic.uwb_only, dict(W=96, N=50, A=8)),
+                     (synthetic.uwb_imu_lidar, dict(W=64)), (synthetic.uwb_twist, dict(W=64))):
+        topo, batch, _ = make(**kw)
+        cfg = Config()
+        Hd, Ho, b, chi = solver.linearize(topo, batch, cfg)
+        rHd, rHo, rb, rchi = oracle.linearize(topo, batch, cfg)
+        assert np.array_equal(Hd, rHd)
+        assert np.array_equal(Ho, rHo)
+        assert np.array_equal(b, rb)
+        assert np.array_equal(chi, rchi)
+
+
+def test_factor_solve_bit_exact(solver):
+    topo, batch, _ = synthetic.uwb_imu_lidar(64, 20, 8)
+    Hd, Ho, b, _ = oracle.linearize(topo, batch, Config())
+    lam = np.full(64, 0.5)
+    lam[::7] = 1e-3
+    x, ok = solver.factor_solve(Hd, Ho, b, lam)
+    rx, rok = oracle.factor_solve(Hd, Ho, b, lam)
+    assert np.array_equal(ok, rok) and ok.all()
+    assert np.array_equal(x, rx)
+    # against a dense solve (not bit-exact: different elimination order)
+    W, N = 64, 20
+    for w in (0, 63):
+        H = np.zeros((6 * N, 6 * N))
+        for i in range(N):
+            H[6 * i:6 * i + 6, 6 * i:6 * i + 6] = Hd[w, i]
+            if i + 1 < N:
+                H[6 * i:6 * i + 6, 6 * i + 6:6 * i + 12] = Ho[w, i]
+                H[6 * i + 6:6 * i + 12, 6 * i:6 * i + 6] = Ho[w, i].T
+        xd = np.linalg.solve(H + lam[w] * np.eye(6 * N), b[w].reshape(-1))
+        assert np.allclose(x[w].reshape(-1), xd, rtol=1e-7, atol=1e-10)
+    # a non-positive pivot is reported, x = 0
+    Hd2 = Hd.copy()
+    Hd2[3, 5] = -np.eye(6)
+    x, ok = solver.factor_solve(Hd2, Ho, b, lam)
+    rx, rok = oracle.factor_solve(Hd2, Ho, b, lam)
+    assert ok[3] == 0 and np.array_equal(ok, rok)
+    assert not x[3].any() and np.array_equal(x, rx)
+
+
+def test_edge_cases(solver):
+    cfg = Config(max_iterations=5)
+    # single pose, single anchor edge
+    topo = Topology.uwb_chain(1, 3)
+    batch = Batch(pose_t=np.array([[[0.1, 0.2, 1.0]]]), anchors=np.array([[[3., 3, 0], [-3, 3, 1], [0, -3, 2]]]),
+                  range_d=np.array([[4.0]]), range_info=np.array([[300.0]]))
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+    # two poses
+    topo, batch, _ = synthetic.uwb_only(5, 2, 4, seed=9)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+    # zero iterations: estimates untouched, chi2 of the initial estimate
+    topo, batch, _ = synthetic.uwb_only(5, 6, 4, seed=9)
+    got = solver.solve(topo, batch, Config(max_iterations=0))
+    assert np.array_equal(got.pose_t, batch.pose_t)
+    assert_parity(got, oracle.solve(topo, batch, Config(max_iterations=0)))
+    # no edges at all: H = 0, lambda = 0, every trial fails, LM terminates after max_trials
+    topo = Topology.from_edges(3, 0, 0, [])
+    batch = Batch(pose_t=np.zeros((2, 3, 3)))
+    got = solver.solve(topo, batch, cfg)
+    ref = oracle.solve(topo, batch, cfg)
+    assert_parity(got, ref)
+    assert (got.status[:, 2] & FLAG_CHOL_FAIL).all() and (got.status[:, 2] & FLAG_TERMINATED).all()
+    # empty batch
+    topo, batch, _ = synthetic.uwb_only(4, 6, 4)
+    got = solver.solve(topo, batch.slice(0, 0), cfg)
+    assert got.pose_t.shape[0] == 0
+    # exact measurements from the start: chi2 = 0
+    topo = Topology.uwb_chain(4, 4)
+    anchors = np.array([[[3., 3, 0], [-3, 3, 1], [0, -3, 2], [2, -2, 1.5]]])
+    pts = np.array([[[0., 0, 1], [0.1, 0, 1], [0.2, 0, 1], [0.3, 0, 1]]])
+    d = np.zeros((1, 7)); info = np.full((1, 7), 100.0)
+    slot = 0
+    for k in range(4):
+        d[0, slot] = np.linalg.norm(pts[0, k] - anchors[0, k]); slot += 1
+        if k > 0:
+            d[0, slot] = np.linalg.norm(pts[0, k] - pts[0, k - 1]); slot += 1
+    batch = Batch(pose_t=pts, anchors=anchors, range_d=d, range_info=info)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+
+
+def test_multiple_range_edges_per_pose_and_unordered_insertion(solver):
+    """merged-covariance branch: extra anchor edges on a pose without a new vertex; two
+    pose-pose range edges on one pair; edges inserted out of pose order"""
+    rng = np.random.default_rng(4)
+    N, A, W = 6, 4, 48
+    edges = []
+    for k in (3, 0, 5, 1, 4, 2):
+        edges.append((EDGE_RANGE_ANCHOR, k, k % A, 0, 1))
+        edges.append((EDGE_RANGE_ANCHOR, k, (k + 1) % A, 0, 0))
+    for k in (4, 0, 2, 1, 3):
+        edges.append((EDGE_RANGE_POSE, k, k + 1, 0, 1))
+    edges.append((EDGE_RANGE_POSE, 2, 3, 0, 0))
+    topo = Topology.from_edges(N, A, 0, edges)
+    er = topo.counts()[0]
+    batch = Batch(pose_t=rng.normal(0, 1, (W, N, 3)), anchors=rng.normal(0, 3, (W, A, 3)),
+                  range_d=np.abs(rng.normal(3, 1, (W, er))), range_info=rng.uniform(10, 400, (W, er)))
+    cfg = Config(max_iterations=6)
+    got = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 1
+    assert_parity(got, oracle.solve(topo, batch, cfg))
+    # a third edge on the same pair exceeds the fast path's carry slots -> general path, same bits
+    topo3 = Topology.from_edges(N, A, 0, edges + [(EDGE_RANGE_POSE, 2, 3, 0, 1)])
+    b3 = Batch(pose_t=batch.pose_t, anchors=batch.anchors,
+               range_d=np.concatenate([batch.range_d, batch.range_d[:, :1]], 1),
+               range_info=np.concatenate([batch.range_info, batch.range_info[:, :1]], 1))
+    got = solver.solve(topo3, b3, cfg)
+    assert solver.last_path == 0
+    assert_parity(got, oracle.solve(topo3, b3, cfg))
+
+
+def test_mixed_edge_kinds_general(solver):
+    """every edge kind in one window, priors with dense information, robust and plain"""
+    rng = np.random.default_rng(8)
+    N, A, W, K = 5, 3, 40, 2
+    edges = [(EDGE_RANGE_ANCHOR, 0, 0, 1, 1), (EDGE_PRIOR, 0, 0, 0, 1)]
+    for k in range(1, N):
+        edges += [(EDGE_SE3, k - 1, k, 0, k % 2), (EDGE_RANGE_ANCHOR, k, k % A, 1 + k % K, 1),
+                  (EDGE_RANGE_POSE, k - 1, k, k % (K + 1), 0), (EDGE_PRIOR, k, 0, 0, 0)]
+    topo = Topology.from_edges(N, A, K, edges)
+    er, ep, es = topo.counts()
+
+    def rand_R(shape):
+        q = rng.normal(size=shape + (4,))
+        q /= np.linalg.norm(q, axis=-1, keepdims=True)
+        w, x, y, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+        R = np.empty(shape + (3, 3))
+        R[..., 0, 0] = 1 - 2 * (y * y + z * z); R[..., 0, 1] = 2 * (x * y - z * w); R[..., 0, 2] = 2 * (x * z + y * w)
+        R[..., 1, 0] = 2 * (x * y + z * w); R[..., 1, 1] = 1 - 2 * (x * x + z * z); R[..., 1, 2] = 2 * (y * z - x * w)
+        R[..., 2, 0] = 2 * (x * z - y * w); R[..., 2, 1] = 2 * (y * z + x * w); R[..., 2, 2] = 1 - 2 * (x * x + y * y)
+        return R
+
+    def spd(shape):
+        M = rng.normal(size=shape + (6, 6))
+        return M @ np.swapaxes(M, -1, -2) + 0.5 * np.eye(6)
+    pR = rand_R((W, N))
+    pZ = np.concatenate([rand_R((W, ep)).reshape(W, ep, 9), rng.normal(0, 1, (W, ep, 3))], -1)
+    sZ = np.concatenate([rand_R((W, es)).reshape(W, es, 9), rng.normal(0, .3, (W, es, 3))], -1)
+    batch = Batch(pose_t=rng.normal(0, 1, (W, N, 3)), pose_R=pR, anchors=rng.normal(0, 3, (W, A, 3)),
+                  range_d=np.abs(rng.normal(3, 1, (W, er))), range_info=rng.uniform(10, 400, (W, er)),
+                  ant_offsets=rng.normal(0, 0.2, (K, 3)), prior_Z=pZ, prior_info=spd((W, ep)),
+                  se3_Z=sZ, se3_info=spd((W, es)))
+    cfg = Config(max_iterations=6)
+    got = solver.solve(topo, batch, cfg)
+    assert_parity(got, oracle.solve(topo, batch, cfg))
+    Hd, Ho, b, chi = solver.linearize(topo, batch, cfg)
+    rHd, rHo, rb, rchi = oracle.linearize(topo, batch, cfg)
+    assert np.array_equal(Hd, rHd) and np.array_equal(Ho, rHo) and np.array_equal(b, rb)
+    assert np.array_equal(chi, rchi)
+
+
+def test_chunked_pipeline_is_shard_invariant(solver):
+    """results do not depend on how windows are chunked over streams (nor, therefore, on how
+    they are sharded over GPUs)"""
+    topo, batch, _ = synthetic.uwb_only(1000, 12, 4, seed=21)
+    cfg = Config(max_iterations=6)
+    whole = solver.solve(topo, batch, cfg)
+    solver.set_pipeline(96, 3)
+    try:
+        parts = solver.solve(topo, batch, cfg)
+    finally:
+        solver.set_pipeline(16384, 3)
+    assert_parity(parts, whole)
+    halves = [solver.solve(topo, batch.slice(0, 500), cfg), solver.solve(topo, batch.slice(500, 1000), cfg)]
+    assert np.array_equal(np.concatenate([h.pose_t for h in halves]), whole.pose_t)
+    assert np.array_equal(np.concatenate([h.chi2 for h in halves]), whole.chi2)
+
+
+def test_properties_at_full_size(solver):
+    """BASELINE headline size (65,536 x N=50): size-independent properties instead of the oracle
+    on everything: accepted LM steps never increase the robust chi2, R stays identity, and a
+    sample of windows matches the oracle bit for bit"""
+    W = 65536
+    topo, batch, truth = synthetic.uwb_only(W, 50, 8)
+    cfg = Config(max_iterations=10)
+    got = solver.solve(topo, batch, cfg)
+    _, _, _, chi0 = solver.linearize(topo, batch.slice(0, 4096), cfg)
+    assert (got.chi2[:4096, 1] <= chi0[:, 1]).all()
+    assert np.array_equal(got.pose_R, np.broadcast_to(np.eye(3), got.pose_R.shape))
+    assert (got.status[:, 0] == 10).all() and (got.status[:, 2] == 0).all()
+    assert np.abs(got.pose_t - truth).mean() < np.abs(batch.pose_t - truth).mean()
+    idx = np.arange(0, W, 257)
+    sub = Batch(pose_t=batch.pose_t[idx], anchors=batch.anchors[idx], range_d=batch.range_d[idx],
+                range_info=batch.range_info[idx])
+    ref = oracle.solve(topo, sub, cfg)
+    assert np.array_equal(got.pose_t[idx], ref.pose_t)
+    assert np.array_equal(got.chi2[idx], ref.chi2)
+    assert np.array_equal(got.status[idx], ref.status)

@@ -1,7 +1,7 @@
 """Synthetic window generators for the BASELINE.json configurations.
 
-Data only: numpy draws in a fixed order from default_rng(seed), FP64, so oracle and GPU are fed
-identical buffers.  Edge parameters follow the reference's factories:
+Data only: numpy draws in a fixed order from default_rng(seed), FP64, so the CPU checker and the GPU are
+fed identical buffers.  Edge parameters follow the reference's factories:
   range information = 1 / distance_err^2            (localization.cpp:318,331,608-627)
   trajectory edge   = EdgeSE3Range(prev, new), measurement 0, information
                       1 / (v_max * dt / 3)^2        (localization.cpp:319,338)

@@ -1,0 +1,131 @@
+"""CPU tests of the host layer: the C-ABI library loads and exports every symbol the header
+declares, fails loudly without a GPU, topology builders, sharding over a world_size-2 gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from localization_b200 import Batch, Config, Topology, _ffi, synthetic
+from localization_b200.shard import window_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "uwbgo.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(uwbgo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_ffi.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/uwbgo.h but not exported"
+    assert sorted(_ffi.SYMBOLS) == names, "ctypes table and header disagree"
+    assert _ffi.load_library().uwbgo_abi_version() == _ffi.ABI_VERSION
+
+
+def test_structs_match_header_layout():
+    assert ctypes.sizeof(_ffi.CTopology) == 16 + 5 * 8
+    assert ctypes.sizeof(_ffi.CBatch) == 8 + 11 * 8
+    assert ctypes.sizeof(_ffi.CConfig) == 16 + 5 * 8
+    assert ctypes.sizeof(_ffi.CResult) == 5 * 8
+    c = _ffi.CConfig()
+    _ffi.load_library().uwbgo_config_default(ctypes.byref(c))
+    d = Config()
+    assert (c.max_iterations, c.max_trials, c.orthogonalize_after) == (d.max_iterations, d.max_trials, d.orthogonalize_after)
+    assert (c.tau, c.good_step_lower, c.good_step_upper, c.kernel_delta, c.jacobian_delta) == (
+        d.tau, d.good_step_lower, d.good_step_upper, d.kernel_delta, d.jacobian_delta)
+
+
+def test_no_cpu_fallback():
+    """without a GPU the product refuses to run instead of computing on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from localization_b200 import Solver, UwbgoError
+    with pytest.raises(UwbgoError) as ei:
+        Solver(0)
+    assert ei.value.code == _ffi.E_NODEVICE
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "localization_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"import\s+oracle|from\s+oracle|libuwbgo_oracle|oracle[/\\.]", text), \
+                    f"{f} reaches into oracle/"
+
+
+def test_topology_builders():
+    t = Topology.uwb_chain(10, 4)
+    assert t.n_edges == 19 and t.counts() == (19, 0, 0)
+    # insertion order of Localization::addRangeEdge: anchor edge of the new vertex, then trajectory edge
+    assert list(t.edge_kind[:5]) == [0, 0, 1, 0, 1]
+    assert list(t.edge_a[:5]) == [0, 1, 0, 2, 1] and list(t.edge_b[:5]) == [0, 1, 1, 2, 2]
+    t = Topology.uwb_chain(12, 4, imu=True)
+    assert t.counts() == (23, 11, 0)            # 12 + 11 range-type edges, 11 IMU priors
+    t = Topology.uwb_twist(15, 8, antennas=3)
+    assert t.counts() == (15, 0, 14)
+    topo, batch, _ = synthetic.uwb_only(5, 6, 4)
+    batch.check(topo)
+    with pytest.raises(ValueError):
+        Batch(pose_t=np.zeros((5, 6, 3))).check(topo)
+    # newest pose is a copy of its predecessor (robot.cpp:90)
+    assert np.array_equal(batch.pose_t[:, -1], batch.pose_t[:, -2])
+    # trajectory edges carry measurement 0 (localization.cpp:338)
+    assert not batch.range_d[:, 2::2].any()
+
+
+def test_window_range_partitions():
+    for W in (0, 1, 7, 65536, 100003):
+        for world in (1, 2, 3, 8):
+            parts = [window_range(W, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == W
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["UWBGO_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from localization_b200 import Config, synthetic
+from localization_b200.shard import shard_batch, gather_to_root
+from oracle import oracle
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+topo, batch, _ = synthetic.uwb_only(37, 8, 4, seed=5)       # ragged: 18 + 19 windows
+cfg = Config(max_iterations=4)
+mine = shard_batch(batch, rank, world)
+res = oracle.solve(topo, mine, cfg, n_threads=1)            # CPU stand-in for the per-rank solve
+poses = gather_to_root(torch.from_numpy(res.pose_t))
+chi2 = gather_to_root(torch.from_numpy(res.chi2))
+if rank == 0:
+    whole = oracle.solve(topo, batch, cfg, n_threads=1)
+    assert np.array_equal(poses.numpy(), whole.pose_t)
+    assert np.array_equal(chi2.numpy(), whole.chi2)
+    print("SHARD_OK")
+else:
+    assert poses is None
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    """N > 1 path on CPU: shard, solve per rank, one gather to rank 0; identical to one rank"""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, UWBGO_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "SHARD_OK" in out.stdout

@@ -1,0 +1,127 @@
+"""CPU tests (no GPU): the oracle against the independent numpy restatement, stage by stage,
+against the committed golden vectors, and basic invariants.  The reference publishes no golden
+vectors for this path: parity with g2o itself is unpinned."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from localization_b200 import Batch, Config, Topology, synthetic
+from oracle import oracle, oracle_np
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def dense_H(Hd, Ho):
+    W, N = Hd.shape[:2]
+    H = np.zeros((W, 6 * N, 6 * N))
+    for i in range(N):
+        H[:, 6 * i:6 * i + 6, 6 * i:6 * i + 6] = Hd[:, i]
+        if i + 1 < N:
+            H[:, 6 * i:6 * i + 6, 6 * i + 6:6 * i + 12] = Ho[:, i]
+            H[:, 6 * i + 6:6 * i + 12, 6 * i:6 * i + 6] = np.swapaxes(Ho[:, i], 1, 2)
+    return H
+
+
+def test_det_log_matches_libm():
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([1.0 + rng.uniform(0, 1e-3, 200), rng.uniform(1, 50, 400), 10 ** rng.uniform(-300, 300, 200),
+                         [1.0, 2.0, 0.5, math.sqrt(2), 1 / math.sqrt(2), 5e-324, 1.7e308]])
+    for x in xs:
+        a, b = oracle.det_log(x), math.log(x)
+        assert abs(a - b) <= 2 ** -52 * max(abs(b), 2 ** -60) * 1.01, (x, a, b)
+    assert oracle.det_log(0.0) == -math.inf and math.isnan(oracle.det_log(-1.0))
+    assert oracle.det_log(math.inf) == math.inf and math.isnan(oracle.det_log(math.nan))
+
+
+@pytest.mark.parametrize("make,kw", [
+    (synthetic.uwb_only, dict(W=6, N=8, A=4, seed=1)),
+    (synthetic.uwb_imu_lidar, dict(W=4, N=6, A=4, seed=2)),
+    (synthetic.uwb_twist, dict(W=4, N=6, A=4, seed=3)),
+])
+def test_linearize_against_numpy_restatement(make, kw):
+    topo, batch, _ = make(**kw)
+    cfg = Config()
+    Hd, Ho, b, chi = oracle.linearize(topo, batch, cfg)
+    H2, b2, chi2 = oracle_np.linearize(topo, batch, cfg)
+    assert np.allclose(chi, chi2, rtol=1e-12, atol=1e-12)      # residuals, information, Cauchy rho
+    H = dense_H(Hd, Ho)
+    # numeric range Jacobians carry ~1e-7 relative round-off (delta = 1e-9), SURVEY Appendix B
+    scale = np.abs(H).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(H - H2) / scale).max() < 5e-6
+    assert (np.abs(b.reshape(b2.shape) - b2) / np.abs(b2).max(axis=1, keepdims=True)).max() < 5e-6
+
+
+def test_factor_solve_against_dense():
+    topo, batch, _ = synthetic.uwb_imu_lidar(8, 10, 4, seed=4)
+    Hd, Ho, b, _ = oracle.linearize(topo, batch, Config())
+    lam = np.linspace(1e-3, 2.0, 8)
+    x, ok = oracle.factor_solve(Hd, Ho, b, lam)
+    assert ok.all()
+    H = dense_H(Hd, Ho)
+    for w in range(8):
+        xd = np.linalg.solve(H[w] + lam[w] * np.eye(60), b[w].reshape(-1))
+        assert np.allclose(x[w].reshape(-1), xd, rtol=1e-8, atol=1e-11)
+    Hd[2, 4] = -np.eye(6)
+    x, ok = oracle.factor_solve(Hd, Ho, b, lam)
+    assert ok[2] == 0 and not x[2].any() and ok.sum() == 7
+
+
+@pytest.mark.parametrize("make,kw,iters", [
+    (synthetic.uwb_only, dict(W=4, N=8, A=4, seed=5), 10),
+    (synthetic.uwb_imu_lidar, dict(W=3, N=6, A=4, seed=6), 8),
+    (synthetic.uwb_twist, dict(W=3, N=6, A=4, seed=7), 8),
+])
+def test_full_lm_against_numpy_restatement(make, kw, iters):
+    """two independent roundings of the same algorithm: same accept/reject history, poses within
+    1e-6 m, chi2 within 1e-4 relative (SURVEY Appendix B measured ~1e-6..1e-5 as the floor)"""
+    topo, batch, _ = make(**kw)
+    cfg = Config(max_iterations=iters)
+    ref = oracle.solve(topo, batch, cfg)
+    pt, pR, chi2, st = oracle_np.solve(topo, batch, cfg)
+    assert np.array_equal(ref.status[:, :2], st)
+    assert np.abs(ref.pose_t - pt).max() < 1e-6
+    assert np.abs(ref.pose_R - pR).max() < 1e-6
+    assert np.allclose(ref.chi2[:, :2], chi2, rtol=1e-4)
+
+
+def test_invariants():
+    topo, batch, truth = synthetic.uwb_only(64, 20, 8, seed=8)
+    cfg = Config(max_iterations=10)
+    r = oracle.solve(topo, batch, cfg, trace=True)
+    # UWB-only keeps R = I bit-exactly (rotation columns of the numeric Jacobian are exactly 0)
+    assert np.array_equal(r.pose_R, np.broadcast_to(np.eye(3), r.pose_R.shape))
+    # accepted steps never increase the robust chi2
+    chis = r.trace[:, :, 0]
+    assert (np.diff(chis, axis=1) <= 0).all()
+    _, _, _, chi0 = oracle.linearize(topo, batch, cfg)
+    assert (r.chi2[:, 1] <= chi0[:, 1]).all()
+    assert np.abs(r.pose_t - truth).mean() < np.abs(batch.pose_t - truth).mean()
+    # the zero-length trajectory edge of the duplicated newest pose has J = 0 exactly:
+    Hd, Ho, b, _ = oracle.linearize(topo, batch, cfg)
+    assert not Ho[:, -1].any()
+    # thread count does not change results
+    r1 = oracle.solve(topo, batch, cfg, n_threads=1)
+    assert np.array_equal(r1.pose_t, r.pose_t) and np.array_equal(r1.chi2, r.chi2)
+    # oplus counter: 12 numeric calls per range-edge end per iteration + 1 per trial
+    calls = np.array([12 + (12 if k > 0 else 0) + (12 if k < 19 else 0) for k in range(20)])
+    assert np.array_equal(r.oplus_count, 10 * calls[None, :] + r.status[:, 1:2])
+
+
+def test_golden_vectors():
+    """committed outputs of the oracle (tests/golden/make_golden.py) — regression pin"""
+    g = np.load(os.path.join(GOLDEN, "oracle_golden.npz"))
+    cases = {"uwb_only": (synthetic.uwb_only, dict(W=8, N=10, A=4, seed=101), 10),
+             "uwb_imu_lidar": (synthetic.uwb_imu_lidar, dict(W=6, N=8, A=4, seed=102), 20),
+             "uwb_twist": (synthetic.uwb_twist, dict(W=6, N=7, A=4, seed=103), 12)}
+    for name, (make, kw, iters) in cases.items():
+        topo, batch, _ = make(**kw)
+        assert np.array_equal(batch.pose_t, g[f"{name}_in_pose_t"]), "generator changed"
+        r = oracle.solve(topo, batch, Config(max_iterations=iters))
+        assert np.array_equal(r.pose_t, g[f"{name}_pose_t"])
+        assert np.array_equal(r.pose_R, g[f"{name}_pose_R"])
+        assert np.array_equal(r.chi2, g[f"{name}_chi2"])
+        assert np.array_equal(r.status, g[f"{name}_status"])
+        Hd, Ho, b, chi = oracle.linearize(topo, batch, Config())
+        assert np.array_equal(Hd, g[f"{name}_Hd"]) and np.array_equal(b, g[f"{name}_b"])

@@ -222,6 +222,20 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
         ops.insert(ops.end(), per_pose[i].begin(), per_pose[i].end());
     }
     op_begin[N] = (int32_t)ops.size();
+    /* fused substitution + residual sweep: produce poses in ascending order, evaluate every edge
+     * (insertion order) as soon as both its poses exist */
+    std::vector<SchedOp> sched;
+    {
+        int produced = 0;
+        for (int e = 0; e < E; ++e) {
+            int need = edges[e].a;
+            if (edges[e].kind == UWBGO_EDGE_RANGE_POSE || edges[e].kind == UWBGO_EDGE_SE3)
+                need = std::max(need, edges[e].b);
+            while (produced <= need) sched.push_back(SchedOp{0, produced++});
+            sched.push_back(SchedOp{1, e});
+        }
+        while (produced < N) sched.push_back(SchedOp{0, produced++});
+    }
 
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o_edges = 0;
@@ -229,7 +243,8 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     size_t o_ops = o_fedges + al(sizeof(EdgeRec) * std::max(E, 1));
     size_t o_begin = o_ops + al(sizeof(PoseOp) * std::max<size_t>(ops.size(), 1));
     size_t o_calls = o_begin + al(sizeof(int32_t) * (N + 1));
-    size_t total = o_calls + al(sizeof(int32_t) * N);
+    size_t o_sched = o_calls + al(sizeof(int32_t) * N);
+    size_t total = o_sched + al(sizeof(SchedOp) * sched.size());
     std::vector<char> host(total, 0);
     if (E) {
         memcpy(host.data() + o_edges, edges.data(), sizeof(EdgeRec) * E);
@@ -238,6 +253,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     if (!ops.empty()) memcpy(host.data() + o_ops, ops.data(), sizeof(PoseOp) * ops.size());
     memcpy(host.data() + o_begin, op_begin.data(), sizeof(int32_t) * (N + 1));
     memcpy(host.data() + o_calls, calls.data(), sizeof(int32_t) * N);
+    memcpy(host.data() + o_sched, sched.data(), sizeof(SchedOp) * sched.size());
 
     auto ent = std::make_unique<TopoEntry>();
     CU(cudaMalloc(&ent->dmem, total));
@@ -260,6 +276,8 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     g.ops = reinterpret_cast<const PoseOp *>(d + o_ops);
     g.op_begin = reinterpret_cast<const int32_t *>(d + o_begin);
     g.num_calls = reinterpret_cast<const int32_t *>(d + o_calls);
+    g.sched = reinterpret_cast<const SchedOp *>(d + o_sched);
+    g.n_sched = (int32_t)sched.size();
     ent->gen = g;
     ent->fast = g;
     ent->fast.fast = 1;
@@ -342,7 +360,7 @@ TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bo
     L.off_sZ = take((size_t)t.Es * 12, 8);
     L.off_sI = take((size_t)t.Es * 36, 8);
     L.off_HB = take(N * (fast ? HR_FAST : HR_GEN), 8);
-    L.off_LR = want_LR ? take(N * (fast ? HR_FAST : HR_GEN), 8) : 0;
+    L.off_LR = want_LR ? take(N * (fast ? LR_FAST : LR_GEN), 8) : 0;
     L.off_chi2 = take(4, 8);
     L.off_status = take(4, 4);
     L.bytes = o;

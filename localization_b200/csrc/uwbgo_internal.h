@@ -26,6 +26,8 @@ constexpr int CTA_THREADS = 128;  /* 4 tiles per CTA                            
 /* rows per pose of the H / L records */
 constexpr int HR_FAST = 18;       /* Hd upper 6 | link block 9 | b 3              */
 constexpr int HR_GEN = 63;        /* Hd upper 21 | link block 36 | b 6            */
+constexpr int LR_FAST = 12;       /* c 3 | M 9     (x_i = c_i - M_i x_{i-1})      */
+constexpr int LR_GEN = 42;        /* c 6 | M 36                                   */
 
 /* One edge of the shared topology, in g2o insertion order. */
 struct EdgeRec {
@@ -45,9 +47,18 @@ struct PoseOp {
     int32_t role;
 };
 
+/* Schedule of the fused substitution + residual sweep: poses are produced in ascending order,
+ * every edge is evaluated (in insertion order) as soon as both its poses exist. */
+struct SchedOp {
+    int32_t kind; /* 0 = produce pose idx, 1 = evaluate edge idx */
+    int32_t idx;
+};
+
 struct DevTopo {
     int32_t N, A, K, E, Er, Ep, Es;
     int32_t fast;               /* 1: range edges only, no offsets -> translation-only path */
+    int32_t n_sched, pad;
+    const SchedOp *sched;       /* [n_sched = N + E]                                         */
     const EdgeRec *edges;       /* [E]                                                       */
     const PoseOp *ops;          /* concatenated per-pose op lists                            */
     const int32_t *op_begin;    /* [N+1]                                                     */
@@ -73,7 +84,7 @@ struct DevWs {
     const double *sZ;   /* [tile][Es*12][32]                          */
     const double *sI;   /* [tile][Es*36][32]                          */
     double *HB;         /* H records      [tile][N*HR][32]            */
-    double *LR;         /* L records      [tile][N*HR][32]            */
+    double *LR;         /* L records      [tile][N*LR][32]            */
     const double *ant;  /* [K][3] antenna offsets, plain              */
     double *chi2;       /* [tile][4][32] (solve) or [tile][2][32]     */
     int32_t *status;    /* [tile][4][32]                              */

@@ -64,7 +64,7 @@ struct Ptrs {
     double *HB, *LR;
 };
 
-template <int HR>
+template <int HR, int LRR>
 UWBGO_DI Ptrs thread_ptrs(const DevTopo &tp, const DevWs &ws, int64_t w)
 {
     int64_t tile = w / TILE;
@@ -83,7 +83,7 @@ UWBGO_DI Ptrs thread_ptrs(const DevTopo &tp, const DevWs &ws, int64_t w)
     p.sZ = ws.sZ ? ws.sZ + (tile * (size_t)tp.Es * 12) * TILE + lane : nullptr;
     p.sI = ws.sI ? ws.sI + (tile * (size_t)tp.Es * 36) * TILE + lane : nullptr;
     p.HB = ws.HB + (tile * (size_t)tp.N * HR) * TILE + lane;
-    p.LR = ws.LR ? ws.LR + (tile * (size_t)tp.N * HR) * TILE + lane : nullptr;
+    p.LR = ws.LR ? ws.LR + (tile * (size_t)tp.N * LRR) * TILE + lane : nullptr;
     return p;
 }
 
@@ -91,106 +91,155 @@ UWBGO_DI Ptrs thread_ptrs(const DevTopo &tp, const DevWs &ws, int64_t w)
 /* linear solver: block-tridiagonal Cholesky of H + lambda I, chain eliminated newest pose       */
 /* first (replaces LinearSolverCholmod::solve).  D = 3 (FAST) or 6 (GENERAL).                   */
 /*   H record of pose i:  Hd_i upper packed | H_{i-1,i} (rows i-1, cols i) | b_i                 */
-/*   L record of pose i:  L_i lower packed, diagonal stored inverted | G_{i-1} | z_i             */
+/*   L record of pose i:  c_i | M_i      with the substitution  x_i = c_i - M_i x_{i-1}          */
+/* The factor sweep walks the H records back to front and prefetches record i-1 into registers   */
+/* while record i is being eliminated (D = 3), so the HBM latency of the stream hides behind     */
+/* the sqrt/div dependency chain of the 3x3 potrf.                                               */
 /* ------------------------------------------------------------------------------------------ */
+template <int D>
+struct Rec {
+    static constexpr int TRI = D * (D + 1) / 2, SQ = D * D;
+    static constexpr int H = TRI + SQ + D; /* rows of an H record */
+    static constexpr int L = D + SQ;       /* rows of an L record */
+};
+
+template <int D>
+UWBGO_DI void load_hrec(const double *__restrict__ h, double *r)
+{
+#pragma unroll
+    for (int k = 0; k < Rec<D>::H; ++k) r[k] = ROW(h, k);
+}
+
+/* one elimination step on the H record held in `h`; G/zn carry G_i and z_{i+1} in, G_{i-1} and
+ * z_i out */
+template <int D>
+UWBGO_DI void factor_step(const double *h, double *__restrict__ l, bool link, bool has_prev,
+                          double lambda, double *G, double *zn, bool &ok)
+{
+    constexpr int TRI = Rec<D>::TRI, SQ = Rec<D>::SQ;
+    double S[TRI], L[TRI], z[D], c[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int cc = 0; cc <= r; ++cc) {
+            double s = h[up_idx(D, cc, r)];
+            if (r == cc) s = s + lambda;
+            if (link) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) s = fma(-G[r * D + k], G[cc * D + k], s);
+            }
+            S[lo_idx(r, cc)] = s;
+        }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double s = S[lo_idx(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
+        if (!(s > 0.0)) ok = false;
+        double inv = 1.0 / sqrt(s);
+        L[lo_idx(j, j)] = inv;
+#pragma unroll
+        for (int r = j + 1; r < D; ++r) {
+            double t = S[lo_idx(r, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
+            L[lo_idx(r, j)] = t * inv;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        double s = h[TRI + SQ + r];
+        if (link) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) s = fma(-G[r * D + k], zn[k], s);
+        }
+#pragma unroll
+        for (int k = 0; k < r; ++k) s = fma(-L[lo_idx(r, k)], z[k], s);
+        z[r] = s * L[lo_idx(r, r)];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) zn[k] = z[k];
+#pragma unroll
+    for (int r = D - 1; r >= 0; --r) {
+        double s = z[r];
+#pragma unroll
+        for (int k = r + 1; k < D; ++k) s = fma(-L[lo_idx(k, r)], c[k], s);
+        c[r] = s * L[lo_idx(r, r)];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) ROW(l, k) = c[k];
+    if (has_prev) {
+        double M[SQ];
+#pragma unroll
+        for (int r = 0; r < D; ++r)
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) {
+                double s = h[TRI + r * D + cc];
+#pragma unroll
+                for (int k = 0; k < cc; ++k) s = fma(-G[r * D + k], L[lo_idx(cc, k)], s);
+                G[r * D + cc] = s * L[lo_idx(cc, cc)]; /* row r: entries k < cc are already new */
+            }
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+            for (int r = D - 1; r >= 0; --r) {
+                double s = G[j * D + r];
+#pragma unroll
+                for (int k = r + 1; k < D; ++k) s = fma(-L[lo_idx(k, r)], M[k * D + j], s);
+                M[r * D + j] = s * L[lo_idx(r, r)];
+            }
+#pragma unroll
+        for (int k = 0; k < SQ; ++k) ROW(l, D + k) = M[k];
+    }
+}
+
 template <int D>
 UWBGO_DI bool factor_sweep(const double *__restrict__ HB, double *__restrict__ LR, int N,
                            double lambda)
 {
-    constexpr int TRI = D * (D + 1) / 2, SQ = D * D, REC = TRI + SQ + D;
+    constexpr int SQ = Rec<D>::SQ, RH = Rec<D>::H, RL = Rec<D>::L;
     double G[SQ], zn[D];
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < SQ; ++k) G[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) zn[k] = 0.0;
-    for (int i = N - 1; i >= 0; --i) {
-        const double *h = HB + (size_t)i * REC * TILE;
-        double *l = LR + (size_t)i * REC * TILE;
-        const bool link = i + 1 < N;
-        double S[TRI], L[TRI], z[D];
-#pragma unroll
-        for (int r = 0; r < D; ++r)
-#pragma unroll
-            for (int c = 0; c <= r; ++c) {
-                double s = ROW(h, up_idx(D, c, r));
-                if (r == c) s = s + lambda;
-                if (link) {
-#pragma unroll
-                    for (int k = 0; k < D; ++k) s = fma(-G[r * D + k], G[c * D + k], s);
-                }
-                S[lo_idx(r, c)] = s;
-            }
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            double s = S[lo_idx(j, j)];
-#pragma unroll
-            for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
-            if (!(s > 0.0)) ok = false;
-            double inv = 1.0 / sqrt(s);
-            L[lo_idx(j, j)] = inv;
-#pragma unroll
-            for (int r = j + 1; r < D; ++r) {
-                double t = S[lo_idx(r, j)];
-#pragma unroll
-                for (int k = 0; k < j; ++k) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
-                L[lo_idx(r, j)] = t * inv;
-            }
+    if (D == 3) {
+        double ra[RH], rb[RH];
+        int i = N - 1;
+        load_hrec<D>(HB + (size_t)i * RH * TILE, ra);
+        while (i >= 0) {
+            if (i > 0) load_hrec<D>(HB + (size_t)(i - 1) * RH * TILE, rb);
+            factor_step<D>(ra, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok);
+            --i;
+            if (i < 0) break;
+            if (i > 0) load_hrec<D>(HB + (size_t)(i - 1) * RH * TILE, ra);
+            factor_step<D>(rb, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok);
+            --i;
         }
-#pragma unroll
-        for (int r = 0; r < D; ++r) {
-            double s = ROW(h, TRI + SQ + r);
-            if (link) {
-#pragma unroll
-                for (int k = 0; k < D; ++k) s = fma(-G[r * D + k], zn[k], s);
-            }
-#pragma unroll
-            for (int k = 0; k < r; ++k) s = fma(-L[lo_idx(r, k)], z[k], s);
-            z[r] = s * L[lo_idx(r, r)];
-        }
-#pragma unroll
-        for (int k = 0; k < TRI; ++k) ROW(l, k) = L[k];
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            ROW(l, TRI + SQ + k) = z[k];
-            zn[k] = z[k];
-        }
-        if (i > 0) {
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    double s = ROW(h, TRI + r * D + c);
-#pragma unroll
-                    for (int k = 0; k < c; ++k) s = fma(-G[r * D + k], L[lo_idx(c, k)], s);
-                    /* G is overwritten row by row: entries k < c of row r are already new */
-                    G[r * D + c] = s * L[lo_idx(c, c)];
-                }
-#pragma unroll
-            for (int k = 0; k < SQ; ++k) ROW(l, TRI + k) = G[k];
+    } else {
+        for (int i = N - 1; i >= 0; --i) {
+            double r[RH];
+            load_hrec<D>(HB + (size_t)i * RH * TILE, r);
+            factor_step<D>(r, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok);
         }
     }
     return ok;
 }
 
-/* x_i = L_i^-T (z_i - G_{i-1}^T x_{i-1}), ascending; xp holds x_{i-1} on entry, x_i on exit */
+/* x_i = c_i - M_i x_{i-1}; l = L record values (registers); xp holds x_{i-1} in, x_i out */
 template <int D>
-UWBGO_DI void subst_step(const double *__restrict__ l, bool link, double *xp)
+UWBGO_DI void subst_step(const double *l, bool link, double *xp)
 {
-    constexpr int TRI = D * (D + 1) / 2, SQ = D * D;
-    double L[TRI], x[D];
+    double x[D];
 #pragma unroll
-    for (int k = 0; k < TRI; ++k) L[k] = ROW(l, k);
-#pragma unroll
-    for (int r = D - 1; r >= 0; --r) {
-        double s = ROW(l, TRI + SQ + r);
+    for (int r = 0; r < D; ++r) {
+        double s = l[r];
         if (link) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) s = fma(-ROW(l, TRI + k * D + r), xp[k], s);
+            for (int j = 0; j < D; ++j) s = fma(-l[D + r * D + j], xp[j], s);
         }
-#pragma unroll
-        for (int k = r + 1; k < D; ++k) s = fma(-L[lo_idx(k, r)], x[k], s);
-        x[r] = s * L[lo_idx(r, r)];
+        x[r] = s;
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) xp[k] = x[k];
@@ -206,8 +255,11 @@ struct FastEnv {
     Ptrs p;
     Cauchy ck;
     double delta, scalar;
-    double *stash; /* shared memory: [2*FAST_MAX_CARRY][5][CTA_THREADS], this thread's column */
+    double *stash;      /* shared memory: [2*FAST_MAX_CARRY][5][CTA_THREADS], this thread's column */
+    const double *anch; /* anchors: shared-memory copy (stride CTA_THREADS) or the tile rows (TILE) */
+    int anch_stride;
 };
+#define ANCH(E, k) ((E).anch[(size_t)(k) * (E).anch_stride])
 
 /* computeActiveErrors + activeRobustChi2 / chi2, edges in insertion order */
 UWBGO_DI void fast_chi_pass(const FastEnv &E, const double *__restrict__ T, double &plain,
@@ -218,8 +270,14 @@ UWBGO_DI void fast_chi_pass(const FastEnv &E, const double *__restrict__ T, doub
     for (int e = 0; e < tp.E; ++e) {
         EdgeRec er = load_edge(tp.edges + e);
         const double *ta = T + (size_t)er.a * 3 * TILE;
-        const double *tb = (er.kind == UWBGO_EDGE_RANGE_ANCHOR ? E.p.anch : T) + (size_t)er.b * 3 * TILE;
-        double n = dist3(ROW(ta, 0), ROW(ta, 1), ROW(ta, 2), ROW(tb, 0), ROW(tb, 1), ROW(tb, 2));
+        double qx, qy, qz;
+        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+            qx = ANCH(E, er.b * 3); qy = ANCH(E, er.b * 3 + 1); qz = ANCH(E, er.b * 3 + 2);
+        } else {
+            const double *tb = T + (size_t)er.b * 3 * TILE;
+            qx = ROW(tb, 0); qy = ROW(tb, 1); qz = ROW(tb, 2);
+        }
+        double n = dist3(ROW(ta, 0), ROW(ta, 1), ROW(ta, 2), qx, qy, qz);
         double err = ROW(E.p.rd, er.slot) - n;
         double Oe = ROW(E.p.ri, er.slot) * err;
         double chi = err * Oe;
@@ -272,10 +330,15 @@ UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
     double maxdiag = 0.0;
     double cx = ROW(T, 0), cy = ROW(T, 1), cz = ROW(T, 2); /* pose i */
     double nx = 0.0, ny = 0.0, nz = 0.0;                   /* pose i+1 */
+    double fx = 0.0, fy = 0.0, fz = 0.0;                   /* pose i+2, in flight */
+    if (N > 1) {
+        const double *tn = T + (size_t)3 * TILE;
+        nx = ROW(tn, 0); ny = ROW(tn, 1); nz = ROW(tn, 2);
+    }
     for (int i = 0; i < N; ++i) {
-        if (i + 1 < N) {
-            const double *tn = T + (size_t)(i + 1) * 3 * TILE;
-            nx = ROW(tn, 0); ny = ROW(tn, 1); nz = ROW(tn, 2);
+        if (i + 2 < N) {
+            const double *tf = T + (size_t)(i + 2) * 3 * TILE;
+            fx = ROW(tf, 0); fy = ROW(tf, 1); fz = ROW(tf, 2);
         }
         double hd[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         double ho[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -288,8 +351,7 @@ UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
             if (op.y == 0) {
                 double qx, qy, qz;
                 if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
-                    const double *an = E.p.anch + (size_t)er.b * 3 * TILE;
-                    qx = ROW(an, 0); qy = ROW(an, 1); qz = ROW(an, 2);
+                    qx = ANCH(E, er.b * 3); qy = ANCH(E, er.b * 3 + 1); qz = ANCH(E, er.b * 3 + 2);
                 } else {
                     qx = nx; qy = ny; qz = nz;
                 }
@@ -353,30 +415,103 @@ UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
         v = fabs(hd[3]); if (v > maxdiag) maxdiag = v;
         v = fabs(hd[5]); if (v > maxdiag) maxdiag = v;
         cx = nx; cy = ny; cz = nz;
+        nx = fx; ny = fy; nz = fz;
     }
     return maxdiag;
 }
 
-/* substitution sweep fused with computeScale() and the estimate update (oplus with R = I) */
-UWBGO_DI double fast_solve_update(const FastEnv &E, bool ok, double lambda,
-                                  const double *__restrict__ Tc, double *__restrict__ Tn)
+/* One pass after the factor sweep: substitution x_i = c_i - M_i x_{i-1} (ascending), computeScale(),
+ * the estimate update (oplus with R = I: t + x) and computeActiveErrors + activeRobustChi2 at the
+ * new estimates, following the schedule of DevTopo::sched: edges are summed in insertion order,
+ * each as soon as both its poses exist.  The two newest poses stay in registers; an edge that
+ * refers further back re-reads the pose it needs.  The L record / b / t of pose i+1 are in flight
+ * while pose i and its edges are processed. */
+UWBGO_DI void fast_solve_chi(const FastEnv &E, bool ok, double lambda, const double *__restrict__ Tc,
+                             double *__restrict__ Tn, double &scale_out, double &plain,
+                             double &robust)
 {
-    const int N = E.tp->N;
+    const DevTopo &tp = *E.tp;
+    const int N = tp.N;
     double xp[3] = {0.0, 0.0, 0.0};
-    double scale = 0.0;
-    for (int i = 0; i < N; ++i) {
-        subst_step<3>(E.p.LR + (size_t)i * HR_FAST * TILE, i > 0, xp);
-        if (!ok) xp[0] = xp[1] = xp[2] = 0.0;
-        const double *h = E.p.HB + (size_t)i * HR_FAST * TILE;
-        const double *t = Tc + (size_t)i * 3 * TILE;
-        double *tn = Tn + (size_t)i * 3 * TILE;
+    double scale = 0.0, p = 0.0, r = 0.0;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0; /* poses ic and ic-1 */
+    int ic = -1;
+    double nl[LR_FAST], nb[3], nt[3]; /* prefetched inputs of the next pose */
+    {
+        const double *l = E.p.LR;
+#pragma unroll
+        for (int k = 0; k < LR_FAST; ++k) nl[k] = ROW(l, k);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            scale = scale + xp[k] * (lambda * xp[k] + ROW(h, 15 + k));
-            ROW(tn, k) = xp[k] + ROW(t, k);
+            nb[k] = ROW(E.p.HB, 15 + k);
+            nt[k] = ROW(Tc, k);
         }
     }
-    return scale;
+    const int ns = tp.n_sched;
+    for (int s = 0; s < ns; ++s) {
+        int2 op = __ldg(reinterpret_cast<const int2 *>(tp.sched + s));
+        if (op.x == 0) {
+            const int i = op.y;
+            double l[LR_FAST], b[3], t[3];
+#pragma unroll
+            for (int k = 0; k < LR_FAST; ++k) l[k] = nl[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                b[k] = nb[k];
+                t[k] = nt[k];
+            }
+            if (i + 1 < N) {
+                const double *ln = E.p.LR + (size_t)(i + 1) * LR_FAST * TILE;
+                const double *hn = E.p.HB + (size_t)(i + 1) * HR_FAST * TILE;
+                const double *tn = Tc + (size_t)(i + 1) * 3 * TILE;
+#pragma unroll
+                for (int k = 0; k < LR_FAST; ++k) nl[k] = ROW(ln, k);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    nb[k] = ROW(hn, 15 + k);
+                    nt[k] = ROW(tn, k);
+                }
+            }
+            subst_step<3>(l, i > 0, xp);
+            if (!ok) xp[0] = xp[1] = xp[2] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) scale = scale + xp[k] * (lambda * xp[k] + b[k]);
+            v0 = c0; v1 = c1; v2 = c2;
+            c0 = xp[0] + t[0]; c1 = xp[1] + t[1]; c2 = xp[2] + t[2];
+            ic = i;
+            double *to = Tn + (size_t)i * 3 * TILE;
+            ROW(to, 0) = c0; ROW(to, 1) = c1; ROW(to, 2) = c2;
+        } else {
+            EdgeRec er = load_edge(tp.edges + op.y);
+            double ax, ay, az, qx, qy, qz;
+            if (er.a == ic) {
+                ax = c0; ay = c1; az = c2;
+            } else if (er.a == ic - 1) {
+                ax = v0; ay = v1; az = v2;
+            } else {
+                const double *ta = Tn + (size_t)er.a * 3 * TILE;
+                ax = ROW(ta, 0); ay = ROW(ta, 1); az = ROW(ta, 2);
+            }
+            if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+                qx = ANCH(E, er.b * 3); qy = ANCH(E, er.b * 3 + 1); qz = ANCH(E, er.b * 3 + 2);
+            } else if (er.b == ic) {
+                qx = c0; qy = c1; qz = c2;
+            } else if (er.b == ic - 1) {
+                qx = v0; qy = v1; qz = v2;
+            } else {
+                const double *tb = Tn + (size_t)er.b * 3 * TILE;
+                qx = ROW(tb, 0); qy = ROW(tb, 1); qz = ROW(tb, 2);
+            }
+            double err = ROW(E.p.rd, er.slot) - dist3(ax, ay, az, qx, qy, qz);
+            double Oe = ROW(E.p.ri, er.slot) * err;
+            double chi = err * Oe;
+            p = p + chi;
+            r = r + (er.robust ? E.ck.rho0(chi) : chi);
+        }
+    }
+    scale_out = scale;
+    plain = p;
+    robust = r;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -902,7 +1037,13 @@ __device__ __noinline__ double gen_solve_update(const GenEnv &E, bool ok, double
     double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double scale = 0.0;
     for (int i = 0; i < N; ++i) {
-        subst_step<6>(E.p.LR + (size_t)i * HR_GEN * TILE, i > 0, xp);
+        {
+            const double *lp = E.p.LR + (size_t)i * LR_GEN * TILE;
+            double l[LR_GEN];
+#pragma unroll
+            for (int k = 0; k < LR_GEN; ++k) l[k] = ROW(lp, k);
+            subst_step<6>(l, i > 0, xp);
+        }
         if (!ok) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) xp[k] = 0.0;
@@ -931,14 +1072,13 @@ struct Path<true> {
     FastEnv E;
     UWBGO_DI void chi(int buf, double &p, double &r) const { fast_chi_pass(E, E.p.T[buf], p, r); }
     UWBGO_DI double linearize(int buf) const { return fast_linearize(E, E.p.T[buf]); }
-    UWBGO_DI bool factor(double lambda) const
+    /* factor + substitution + update + residuals of one LM trial */
+    UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
     {
-        if (!(lambda > 0.0)) return false; /* rotation pivots are exactly lambda */
-        return factor_sweep<3>(E.p.HB, E.p.LR, E.tp->N, lambda);
-    }
-    UWBGO_DI double update(bool ok, double lambda, int from, int to) const
-    {
-        return fast_solve_update(E, ok, lambda, E.p.T[from], E.p.T[to]);
+        /* the rotation pivots of the 6x6 blocks are exactly lambda */
+        bool ok = (lambda > 0.0) && factor_sweep<3>(E.p.HB, E.p.LR, E.tp->N, lambda);
+        fast_solve_chi(E, ok, lambda, E.p.T[from], E.p.T[to], scale, p, r);
+        return ok;
     }
 };
 template <>
@@ -947,67 +1087,78 @@ struct Path<false> {
     UWBGO_DI PoseBuf buf(int k) const { return PoseBuf{E.p.T[k], E.p.Rm[k]}; }
     UWBGO_DI void chi(int k, double &p, double &r) const { gen_chi_pass(E, buf(k), p, r); }
     UWBGO_DI double linearize(int k) const { return gen_linearize(E, buf(k)); }
-    UWBGO_DI bool factor(double lambda) const
+    UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
     {
-        return factor_sweep<6>(E.p.HB, E.p.LR, E.tp->N, lambda);
-    }
-    UWBGO_DI double update(bool ok, double lambda, int from, int to) const
-    {
-        return gen_solve_update(E, ok, lambda, buf(from), buf(to));
+        bool ok = factor_sweep<6>(E.p.HB, E.p.LR, E.tp->N, lambda);
+        scale = gen_solve_update(E, ok, lambda, buf(from), buf(to));
+        gen_chi_pass(E, buf(to), p, r);
+        return ok;
     }
 };
 
+/* g2o's optimize() is a loop over iterations, each holding a loop over LM trials.  The 32
+ * windows of a warp reject different numbers of trials, so that nesting would leave lanes idle
+ * while their neighbours retry.  It is flattened into ONE loop whose body is "linearise if the
+ * last trial ended an iteration, then run one trial": every pass of a warp does useful trial work
+ * on every unfinished lane, and only the (cheaper) linearisation runs on a subset of lanes.  The
+ * per-window arithmetic and its order are unchanged. */
 template <bool FAST>
 UWBGO_DI void lm_window(const Path<FAST> &P, const DevCfg &cfg, double *chi2_out,
                         int32_t *status_out, int &cur_out)
 {
-    double lambda = 0.0, ni = 2.0, stale, plainCur, currentChi;
-    int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0;
+    double lambda = 0.0, ni = 2.0, stale, plainCur, currentChi, rho = 0.0;
+    int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0, q = 0, it = 0;
     P.chi(cur, plainCur, currentChi);
     stale = plainCur;
-    for (int it = 0; it < cfg.max_iterations; ++it) {
-        stale = plainCur; /* computeActiveErrors at unchanged estimates */
-        double maxdiag = P.linearize(cur);
-        if (it == 0) {
-            lambda = cfg.tau * maxdiag;
-            ni = 2.0;
-        }
-        double rho = 0.0;
-        int q = 0;
-        do {
-            bool ok = P.factor(lambda);
-            if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;
-            double scale = P.update(ok, lambda, cur, cur ^ 1);
-            double tplain, tempChi;
-            P.chi(cur ^ 1, tplain, tempChi);
-            stale = tplain;
-            if (!ok) tempChi = DBL_MAX;
-            scale = scale + 1e-3;
-            rho = (currentChi - tempChi) / scale;
-            const bool fin = isfinite(tempChi);
-            if (!fin) flags |= UWBGO_FLAG_NONFINITE;
-            if (rho > 0.0 && fin) {
-                double t = 2.0 * rho - 1.0;
-                double alpha = 1.0 - (t * t) * t;
-                alpha = (cfg.good_hi < alpha) ? cfg.good_hi : alpha;
-                double sf = (cfg.good_lo < alpha) ? alpha : cfg.good_lo;
-                lambda = lambda * sf;
+    bool need_lin = true, done = cfg.max_iterations <= 0;
+    while (!done) {
+        if (need_lin) {
+            stale = plainCur; /* computeActiveErrors at unchanged estimates */
+            double maxdiag = P.linearize(cur);
+            if (it == 0) {
+                lambda = cfg.tau * maxdiag;
                 ni = 2.0;
-                currentChi = tempChi;
-                plainCur = tplain;
-                cur ^= 1;
-            } else {
-                lambda = lambda * ni;
-                ni = ni * 2.0;
             }
-            ++q;
-            ++trials_total;
-        } while (rho < 0.0 && q < cfg.max_trials);
-        ++iterations;
-        qlast = q;
-        if (q == cfg.max_trials || rho == 0.0) {
-            flags |= UWBGO_FLAG_TERMINATED;
-            break;
+            rho = 0.0;
+            q = 0;
+            need_lin = false;
+        }
+        double scale, tplain, tempChi;
+        const bool ok = P.trial(lambda, cur, cur ^ 1, scale, tplain, tempChi);
+        if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;
+        stale = tplain;
+        if (!ok) tempChi = DBL_MAX;
+        scale = scale + 1e-3;
+        rho = (currentChi - tempChi) / scale;
+        const bool fin = isfinite(tempChi);
+        if (!fin) flags |= UWBGO_FLAG_NONFINITE;
+        if (rho > 0.0 && fin) {
+            double t = 2.0 * rho - 1.0;
+            double alpha = 1.0 - (t * t) * t;
+            alpha = (cfg.good_hi < alpha) ? cfg.good_hi : alpha;
+            double sf = (cfg.good_lo < alpha) ? alpha : cfg.good_lo;
+            lambda = lambda * sf;
+            ni = 2.0;
+            currentChi = tempChi;
+            plainCur = tplain;
+            cur ^= 1;
+        } else {
+            lambda = lambda * ni;
+            ni = ni * 2.0;
+        }
+        ++q;
+        ++trials_total;
+        if (!(rho < 0.0 && q < cfg.max_trials)) { /* this iteration is over */
+            ++iterations;
+            qlast = q;
+            if (q == cfg.max_trials || rho == 0.0) {
+                flags |= UWBGO_FLAG_TERMINATED;
+                done = true;
+            } else if (++it >= cfg.max_iterations) {
+                done = true;
+            } else {
+                need_lin = true;
+            }
         }
     }
     ROW(chi2_out, 0) = plainCur;
@@ -1021,19 +1172,38 @@ UWBGO_DI void lm_window(const Path<FAST> &P, const DevCfg &cfg, double *chi2_out
     cur_out = cur;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 4)
-lm_fast_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
+/* dynamic shared memory of the FAST kernels: carry stash, then (when they fit) the anchors */
+constexpr int STASH_DOUBLES = 2 * FAST_MAX_CARRY * 5 * CTA_THREADS;
+
+UWBGO_DI void fast_env_init(FastEnv &E, const DevTopo &tp, const DevCfg &cfg, const DevWs &ws,
+                            int64_t w, double *smem, int anchors_in_smem)
 {
-    __shared__ double stash[2 * FAST_MAX_CARRY * 5 * CTA_THREADS];
+    E.tp = &tp;
+    E.p = thread_ptrs<HR_FAST, LR_FAST>(tp, ws, w);
+    E.ck.init(cfg.kdelta);
+    E.delta = cfg.jdelta;
+    E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    E.stash = smem + threadIdx.x;
+    if (anchors_in_smem) {
+        double *a = smem + STASH_DOUBLES + threadIdx.x;
+        for (int k = 0; k < tp.A * 3; ++k) a[(size_t)k * CTA_THREADS] = ROW(E.p.anch, k);
+        E.anch = a;
+        E.anch_stride = CTA_THREADS;
+    } else {
+        E.anch = E.p.anch;
+        E.anch_stride = TILE;
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 4)
+lm_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+               const __grid_constant__ DevWs ws, int anchors_in_smem)
+{
+    extern __shared__ double smem[];
     const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     if (w >= ws.W) return;
     Path<true> P;
-    P.E.tp = &tp;
-    P.E.p = thread_ptrs<HR_FAST>(tp, ws, w);
-    P.E.ck.init(cfg.kdelta);
-    P.E.delta = cfg.jdelta;
-    P.E.scalar = 1.0 / (2.0 * cfg.jdelta);
-    P.E.stash = stash + threadIdx.x;
+    fast_env_init(P.E, tp, cfg, ws, w, smem, anchors_in_smem);
     const int64_t tile = w / TILE;
     const int lane = (int)(w % TILE);
     int cur;
@@ -1050,19 +1220,25 @@ lm_fast_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
     }
 }
 
+UWBGO_DI void gen_env_init(GenEnv &E, const DevTopo &tp, const DevCfg &cfg, const DevWs &ws, int64_t w)
+{
+    E.tp = &tp;
+    E.cfg = &cfg;
+    E.p = thread_ptrs<HR_GEN, LR_GEN>(tp, ws, w);
+    E.ant = ws.ant;
+    E.ck.init(cfg.kdelta);
+    E.delta = cfg.jdelta;
+    E.scalar = 1.0 / (2.0 * cfg.jdelta);
+}
+
 __global__ void __launch_bounds__(CTA_THREADS)
-lm_general_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
+lm_general_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+                  const __grid_constant__ DevWs ws)
 {
     const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     if (w >= ws.W) return;
     Path<false> P;
-    P.E.tp = &tp;
-    P.E.cfg = &cfg;
-    P.E.p = thread_ptrs<HR_GEN>(tp, ws, w);
-    P.E.ant = ws.ant;
-    P.E.ck.init(cfg.kdelta);
-    P.E.delta = cfg.jdelta;
-    P.E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    gen_env_init(P.E, tp, cfg, ws, w);
     const int64_t tile = w / TILE;
     const int lane = (int)(w % TILE);
     int cur;
@@ -1075,18 +1251,14 @@ lm_general_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
 
 /* one linearisation: computeActiveErrors + buildSystem; chi2 = {plain, robust} */
 __global__ void __launch_bounds__(CTA_THREADS, 4)
-linearize_fast_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
+linearize_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+                      const __grid_constant__ DevWs ws, int anchors_in_smem)
 {
-    __shared__ double stash[2 * FAST_MAX_CARRY * 5 * CTA_THREADS];
+    extern __shared__ double smem[];
     const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     if (w >= ws.W) return;
     FastEnv E;
-    E.tp = &tp;
-    E.p = thread_ptrs<HR_FAST>(tp, ws, w);
-    E.ck.init(cfg.kdelta);
-    E.delta = cfg.jdelta;
-    E.scalar = 1.0 / (2.0 * cfg.jdelta);
-    E.stash = stash + threadIdx.x;
+    fast_env_init(E, tp, cfg, ws, w, smem, anchors_in_smem);
     double p, r;
     fast_chi_pass(E, E.p.T[0], p, r);
     fast_linearize(E, E.p.T[0]);
@@ -1096,18 +1268,13 @@ linearize_fast_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
 }
 
 __global__ void __launch_bounds__(CTA_THREADS)
-linearize_general_kernel(DevTopo tp, DevCfg cfg, DevWs ws)
+linearize_general_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+                         const __grid_constant__ DevWs ws)
 {
     const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     if (w >= ws.W) return;
     GenEnv E;
-    E.tp = &tp;
-    E.cfg = &cfg;
-    E.p = thread_ptrs<HR_GEN>(tp, ws, w);
-    E.ant = ws.ant;
-    E.ck.init(cfg.kdelta);
-    E.delta = cfg.jdelta;
-    E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    gen_env_init(E, tp, cfg, ws, w);
     double p, r;
     PoseBuf T0{E.p.T[0], E.p.Rm[0]};
     gen_chi_pass(E, T0, p, r);
@@ -1227,12 +1394,25 @@ cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st) { return launc
 
 static unsigned window_blocks(int64_t W) { return (unsigned)((W + CTA_THREADS - 1) / CTA_THREADS); }
 
+/* dynamic shared memory of a FAST launch; anchors go to shared memory when 4 CTAs/SM still fit */
+static size_t fast_smem_bytes(const DevTopo &topo, int *anchors_in_smem)
+{
+    size_t stash = sizeof(double) * STASH_DOUBLES;
+    size_t anch = sizeof(double) * (size_t)topo.A * 3 * CTA_THREADS;
+    *anchors_in_smem = (topo.A > 0 && stash + anch <= 56 * 1024) ? 1 : 0;
+    return stash + (*anchors_in_smem ? anch : 0);
+}
+
 cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st)
 {
     if (ws.W <= 0) return cudaSuccess;
-    if (topo.fast)
-        lm_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
-    else
+    if (topo.fast) {
+        int ais = 0;
+        size_t sm = fast_smem_bytes(topo, &ais);
+        cudaError_t e = cudaFuncSetAttribute(lm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        lm_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, sm, st>>>(topo, cfg, ws, ais);
+    } else
         lm_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
     return cudaGetLastError();
 }
@@ -1241,9 +1421,13 @@ cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs
                              cudaStream_t st)
 {
     if (ws.W <= 0) return cudaSuccess;
-    if (topo.fast)
-        linearize_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
-    else
+    if (topo.fast) {
+        int ais = 0;
+        size_t sm = fast_smem_bytes(topo, &ais);
+        cudaError_t e = cudaFuncSetAttribute(linearize_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        linearize_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, sm, st>>>(topo, cfg, ws, ais);
+    } else
         linearize_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
     return cudaGetLastError();
 }
@@ -1334,11 +1518,14 @@ factor_solve_kernel(int N, int64_t W, double *__restrict__ HB, double *__restric
     const int64_t tile = w / TILE;
     const int lane = (int)(w % TILE);
     double *hb = HB + (tile * (size_t)N * HR_GEN) * TILE + lane;
-    double *lr = LR + (tile * (size_t)N * HR_GEN) * TILE + lane;
+    double *lr = LR + (tile * (size_t)N * LR_GEN) * TILE + lane;
     bool ok = factor_sweep<6>(hb, lr, N, lambda[w]);
     double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int i = 0; i < N; ++i) {
-        subst_step<6>(lr + (size_t)i * HR_GEN * TILE, i > 0, xp);
+        const double *lp = lr + (size_t)i * LR_GEN * TILE;
+        double l[LR_GEN];
+        for (int k = 0; k < LR_GEN; ++k) l[k] = ROW(lp, k);
+        subst_step<6>(l, i > 0, xp);
         double *xo = x + ((size_t)w * N + i) * 6;
         for (int k = 0; k < 6; ++k) xo[k] = ok ? xp[k] : 0.0;
     }

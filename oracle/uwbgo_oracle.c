@@ -294,9 +294,9 @@ typedef struct {
     double *Ho;   /* [N-1][36] block (i,i+1) */
     double *b;    /* [N][6] */
     double *x;    /* [N][6] */
-    double *Ld;   /* [N][36] lower-triangular factor blocks (diagonal holds 1/L_jj) */
-    double *Lo;   /* [N-1][36] L_{i+1,i} */
-    double *y;    /* [N][6] */
+    double *Ld;   /* [N][36] M_i of the substitution x_i = c_i - M_i x_{i-1} */
+    double *Lo;   /* [N-1][36] scratch G_i */
+    double *y;    /* [N][6] c_i */
 } window_t;
 
 static const double ZERO3[3] = {0.0, 0.0, 0.0};
@@ -673,18 +673,21 @@ static void build_system(window_t *W)
 /* own AMD permutation P, so ANY exact FP64 Cholesky agrees with it up to round-off (SURVEY     */
 /* A.8).  The elimination order chosen here is the chain REVERSED (newest pose first): the      */
 /* factor sweep runs i = N-1..0 and the substitution sweep runs i = 0..N-1, so x comes out in    */
-/* ascending order, the order g2o's computeScale() and update() consume it.                     */
-/*   Ld[i]  = L_i   lower factor of M_i = H_ii + lambda I - G_i G_i^T, diagonal stored as 1/L_jj */
-/*   Lo[i]  = G_i   = H_{i,i+1} L_{i+1}^-T   (rows of pose i, columns of pose i+1), i < N-1     */
-/*   y[i]   = z_i   = L_i^-1 (b_i - G_i z_{i+1})                                                */
-/*   x[i]   = L_i^-T (z_i - G_{i-1}^T x_{i-1})                                                  */
+/* ascending order, the order g2o's computeScale() and update() consume it.  The factor sweep   */
+/* leaves the substitution in the form x_i = c_i - M_i x_{i-1}:                                 */
+/*   L_i   lower factor of S_i = H_ii + lambda I - G_i G_i^T, diagonal kept inverted            */
+/*   G_i   = H_{i,i+1} L_{i+1}^-T   (rows of pose i, columns of pose i+1), i < N-1              */
+/*   z_i   = L_i^-1 (b_i - G_i z_{i+1})                                                         */
+/*   c_i   = L_i^-T z_i              -> y[i]                                                    */
+/*   M_i   = L_i^-T G_{i-1}^T        -> Ld[i]  (i > 0)                                          */
+/* Lo[i] is scratch for G_i.                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 static int factor_solve(int N, const double *Hd, const double *Ho, const double *b, double lambda,
                         double *Ld, double *Lo, double *y, double *x)
 {
+    double z[6] = {0, 0, 0, 0, 0, 0}, zn[6];
     for (int i = N - 1; i >= 0; --i) {
-        double S[36];
-        double *L = Ld + 36 * i;
+        double S[36], L[36];
         const double *G = i + 1 < N ? Lo + 36 * i : NULL;
         for (int r = 0; r < 6; ++r)
             for (int c = 0; c <= r; ++c) {
@@ -694,7 +697,7 @@ static int factor_solve(int N, const double *Hd, const double *Ho, const double 
                     for (int k = 0; k < 6; ++k) s = fma(-G[6 * r + k], G[6 * c + k], s);
                 S[6 * r + c] = s;
             }
-        memset(L, 0, 36 * sizeof(double));
+        memset(L, 0, sizeof L);
         for (int j = 0; j < 6; ++j) {
             double s = S[6 * j + j];
             for (int k = 0; k < j; ++k) s = fma(-L[6 * j + k], L[6 * j + k], s);
@@ -708,34 +711,48 @@ static int factor_solve(int N, const double *Hd, const double *Ho, const double 
             }
         }
         /* z_i = L_i^-1 (b_i - G_i z_{i+1}) */
+        memcpy(zn, z, sizeof zn);
         for (int r = 0; r < 6; ++r) {
             double s = b[6 * i + r];
             if (G)
-                for (int k = 0; k < 6; ++k) s = fma(-G[6 * r + k], y[6 * (i + 1) + k], s);
-            for (int k = 0; k < r; ++k) s = fma(-L[6 * r + k], y[6 * i + k], s);
-            y[6 * i + r] = s * L[6 * r + r];
+                for (int k = 0; k < 6; ++k) s = fma(-G[6 * r + k], zn[k], s);
+            for (int k = 0; k < r; ++k) s = fma(-L[6 * r + k], z[k], s);
+            z[r] = s * L[6 * r + r];
         }
-        /* G_{i-1} = H_{i-1,i} L_i^-T ; H_{i-1,i} = Ho[i-1] as stored (rows of i-1, cols of i) */
+        /* c_i = L_i^-T z_i */
+        double *c = y + 6 * i;
+        for (int r = 5; r >= 0; --r) {
+            double s = z[r];
+            for (int k = r + 1; k < 6; ++k) s = fma(-L[6 * k + r], c[k], s);
+            c[r] = s * L[6 * r + r];
+        }
         if (i > 0) {
+            /* G_{i-1} = H_{i-1,i} L_i^-T ; H_{i-1,i} = Ho[i-1] as stored (rows of i-1, cols of i) */
             double *X = Lo + 36 * (i - 1);
             for (int r = 0; r < 6; ++r)
-                for (int c = 0; c < 6; ++c) {
-                    double s = Ho[36 * (i - 1) + 6 * r + c];
-                    for (int k = 0; k < c; ++k) s = fma(-X[6 * r + k], L[6 * c + k], s);
-                    X[6 * r + c] = s * L[6 * c + c];
+                for (int cc = 0; cc < 6; ++cc) {
+                    double s = Ho[36 * (i - 1) + 6 * r + cc];
+                    for (int k = 0; k < cc; ++k) s = fma(-X[6 * r + k], L[6 * cc + k], s);
+                    X[6 * r + cc] = s * L[6 * cc + cc];
+                }
+            /* M_i = L_i^-T G_{i-1}^T */
+            double *M = Ld + 36 * i;
+            for (int j = 0; j < 6; ++j)
+                for (int r = 5; r >= 0; --r) {
+                    double s = X[6 * j + r];
+                    for (int k = r + 1; k < 6; ++k) s = fma(-L[6 * k + r], M[6 * k + j], s);
+                    M[6 * r + j] = s * L[6 * r + r];
                 }
         }
     }
-    /* substitution, ascending: L_i^T x_i = z_i - G_{i-1}^T x_{i-1} */
+    /* substitution, ascending: x_i = c_i - M_i x_{i-1} */
     for (int i = 0; i < N; ++i) {
-        const double *L = Ld + 36 * i;
-        const double *Gp = i > 0 ? Lo + 36 * (i - 1) : NULL;
-        for (int r = 5; r >= 0; --r) {
+        const double *M = Ld + 36 * i;
+        for (int r = 0; r < 6; ++r) {
             double s = y[6 * i + r];
-            if (Gp)
-                for (int k = 0; k < 6; ++k) s = fma(-Gp[6 * k + r], x[6 * (i - 1) + k], s);
-            for (int k = r + 1; k < 6; ++k) s = fma(-L[6 * k + r], x[6 * i + k], s);
-            x[6 * i + r] = s * L[6 * r + r];
+            if (i > 0)
+                for (int j = 0; j < 6; ++j) s = fma(-M[6 * r + j], x[6 * (i - 1) + j], s);
+            x[6 * i + r] = s;
         }
     }
     return 1;

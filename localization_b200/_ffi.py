@@ -99,7 +99,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("UWBGO_LIB") or LIB_PATH  # UWBGO_LIB: developer override (A/B builds)
     if not os.path.exists(p):
         raise ImportError(
             f"{p} not found: build it with `make -C localization_b200/csrc` "

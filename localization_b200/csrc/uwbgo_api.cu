@@ -359,7 +359,8 @@ TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bo
     L.off_pI = take((size_t)t.Ep * 36, 8);
     L.off_sZ = take((size_t)t.Es * 12, 8);
     L.off_sI = take((size_t)t.Es * 36, 8);
-    L.off_HB = take(N * (fast ? HR_FAST : HR_GEN), 8);
+    /* FAST solves rebuild H inside the factor sweep and never store it */
+    L.off_HB = (fast && want_LR) ? 0 : take(N * (fast ? HR_FAST : HR_GEN), 8);
     L.off_LR = want_LR ? take(N * (fast ? LR_FAST : LR_GEN), 8) : 0;
     L.off_chi2 = take(4, 8);
     L.off_status = take(4, 4);

@@ -26,7 +26,7 @@ constexpr int CTA_THREADS = 128;  /* 4 tiles per CTA                            
 /* rows per pose of the H / L records */
 constexpr int HR_FAST = 18;       /* Hd upper 6 | link block 9 | b 3              */
 constexpr int HR_GEN = 63;        /* Hd upper 21 | link block 36 | b 6            */
-constexpr int LR_FAST = 12;       /* c 3 | M 9     (x_i = c_i - M_i x_{i-1})      */
+constexpr int LR_FAST = 15;       /* c 3 | M 9 | b 3   (x_i = c_i - M_i x_{i-1})  */
 constexpr int LR_GEN = 42;        /* c 6 | M 36                                   */
 
 /* One edge of the shared topology, in g2o insertion order. */

@@ -34,6 +34,25 @@ namespace uwbgo {
 /* ------------------------------------------------------------------------------------------ */
 #define ROW(p, r) ((p)[(size_t)(r) * TILE])
 
+/* developer knobs for A/B builds (see DESIGN.md "prefetch") */
+#ifndef UWBGO_FACTOR_PF
+#define UWBGO_FACTOR_PF 1 /* 0 none, 1 register double buffer, 2 L2 prefetch */
+#endif
+#ifndef UWBGO_SOLVE_REGPF
+#define UWBGO_SOLVE_REGPF 1 /* L record of the next pose prefetched into registers */
+#endif
+#ifndef UWBGO_L2PF_DIST
+#define UWBGO_L2PF_DIST 2 /* > 0: prefetch.global.L2 this many records ahead of the sweeps */
+#endif
+
+UWBGO_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int ROWS>
+UWBGO_DI void prefetch_rows_l2(const double *p)
+{
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) prefetch_l2(p + (size_t)k * TILE);
+}
+
 UWBGO_DI EdgeRec load_edge(const EdgeRec *e)
 {
     const int4 *p = reinterpret_cast<const int4 *>(e);
@@ -57,8 +76,10 @@ struct Cauchy {
 
 /* thread-private view of the tile-layout workspace */
 struct Ptrs {
-    double *T[2];  /* translations [N*3] rows */
-    double *Rm[2]; /* rotations    [N*9] rows (GENERAL only) */
+    double *T0, *T1;   /* translations [N*3] rows, two buffers (selected with ?: so the struct */
+    double *Rm0, *Rm1; /* rotations    [N*9] rows (GENERAL)      never needs a local-memory copy) */
+    UWBGO_DI double *T(int k) const { return k ? T1 : T0; }
+    UWBGO_DI double *Rm(int k) const { return k ? Rm1 : Rm0; }
     int32_t *cnt;
     const double *anch, *rd, *ri, *pZ, *pI, *sZ, *sI;
     double *HB, *LR;
@@ -70,10 +91,10 @@ UWBGO_DI Ptrs thread_ptrs(const DevTopo &tp, const DevWs &ws, int64_t w)
     int64_t tile = w / TILE;
     int lane = (int)(w % TILE);
     Ptrs p;
-    p.T[0] = ws.T[0] + (tile * (size_t)tp.N * 3) * TILE + lane;
-    p.T[1] = ws.T[1] + (tile * (size_t)tp.N * 3) * TILE + lane;
-    p.Rm[0] = ws.Rm[0] ? ws.Rm[0] + (tile * (size_t)tp.N * 9) * TILE + lane : nullptr;
-    p.Rm[1] = ws.Rm[1] ? ws.Rm[1] + (tile * (size_t)tp.N * 9) * TILE + lane : nullptr;
+    p.T0 = ws.T[0] + (tile * (size_t)tp.N * 3) * TILE + lane;
+    p.T1 = ws.T[1] + (tile * (size_t)tp.N * 3) * TILE + lane;
+    p.Rm0 = ws.Rm[0] ? ws.Rm[0] + (tile * (size_t)tp.N * 9) * TILE + lane : nullptr;
+    p.Rm1 = ws.Rm[1] ? ws.Rm[1] + (tile * (size_t)tp.N * 9) * TILE + lane : nullptr;
     p.cnt = ws.cnt ? ws.cnt + (tile * (size_t)tp.N) * TILE + lane : nullptr;
     p.anch = ws.anch ? ws.anch + (tile * (size_t)tp.A * 3) * TILE + lane : nullptr;
     p.rd = ws.rd ? ws.rd + (tile * (size_t)tp.Er) * TILE + lane : nullptr;
@@ -204,7 +225,7 @@ UWBGO_DI bool factor_sweep(const double *__restrict__ HB, double *__restrict__ L
     for (int k = 0; k < SQ; ++k) G[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) zn[k] = 0.0;
-    if (D == 3) {
+    if (D == 3 && UWBGO_FACTOR_PF == 1) {
         double ra[RH], rb[RH];
         int i = N - 1;
         load_hrec<D>(HB + (size_t)i * RH * TILE, ra);
@@ -220,6 +241,8 @@ UWBGO_DI bool factor_sweep(const double *__restrict__ HB, double *__restrict__ L
     } else {
         for (int i = N - 1; i >= 0; --i) {
             double r[RH];
+            if (D == 3 && UWBGO_L2PF_DIST > 0 && i - UWBGO_L2PF_DIST >= 0)
+                prefetch_rows_l2<RH>(HB + (size_t)(i - UWBGO_L2PF_DIST) * RH * TILE);
             load_hrec<D>(HB + (size_t)i * RH * TILE, r);
             factor_step<D>(r, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok);
         }
@@ -323,6 +346,7 @@ UWBGO_DI void fast_jac_v1(double px, double py, double pz, double qx, double qy,
 
 /* BlockSolver::buildSystem for one window: per pose, gather its edges in insertion order.
  * Writes the H records; returns max |H_kk| (computeLambdaInit). */
+template <bool WRITE>
 UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
 {
     const DevTopo &tp = *E.tp;
@@ -400,15 +424,17 @@ UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
             hd[4] = fma(JtO[1], J[2], hd[4]);
             hd[5] = fma(JtO[2], J[2], hd[5]);
         }
-        double *h = E.p.HB + (size_t)i * HR_FAST * TILE;
+        if (WRITE) {
+            double *h = E.p.HB + (size_t)i * HR_FAST * TILE;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) ROW(h, k) = hd[k];
+            for (int k = 0; k < 6; ++k) ROW(h, k) = hd[k];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) ROW(h, 15 + k) = bb[k];
-        if (i + 1 < N) {
-            double *hn = h + (size_t)HR_FAST * TILE;
+            for (int k = 0; k < 3; ++k) ROW(h, 15 + k) = bb[k];
+            if (i + 1 < N) {
+                double *hn = h + (size_t)HR_FAST * TILE;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) ROW(hn, 6 + k) = ho[k];
+                for (int k = 0; k < 9; ++k) ROW(hn, 6 + k) = ho[k];
+            }
         }
         double v;
         v = fabs(hd[0]); if (v > maxdiag) maxdiag = v;
@@ -418,6 +444,114 @@ UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
         nx = fx; ny = fy; nz = fz;
     }
     return maxdiag;
+}
+
+/* Matrix-free factor sweep of one LM trial.  H + lambda I is never stored: walking the chain
+ * from the newest pose down, the H record of pose i (Hd_i, H_{i-1,i}, b_i) is rebuilt in
+ * registers from the current estimates and the measurements (7 rows of HBM traffic instead of
+ * 18) and eliminated at once; only the substitution record (c_i, M_i, b_i) is written.  The
+ * arithmetic is that of fast_linearize: the edges touching pose i are gathered in insertion
+ * order; a pose-pose edge (i-1, i) is linearised when the sweep is at pose i (both Jacobians),
+ * its vertex-0 terms travel to pose i-1 through the shared-memory stash. */
+UWBGO_DI bool fast_factor_mf(const FastEnv &E, const double *__restrict__ T, double lambda)
+{
+    const DevTopo &tp = *E.tp;
+    const int N = tp.N;
+    double G[9], zn[3];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) G[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) zn[k] = 0.0;
+    const double *tl = T + (size_t)(N - 1) * 3 * TILE;
+    double cx = ROW(tl, 0), cy = ROW(tl, 1), cz = ROW(tl, 2); /* pose i   */
+    double px = 0.0, py = 0.0, pz = 0.0;                      /* pose i-1 */
+    double fx = 0.0, fy = 0.0, fz = 0.0;                      /* pose i-2, in flight */
+    if (N > 1) {
+        const double *tq = tl - (size_t)3 * TILE;
+        px = ROW(tq, 0); py = ROW(tq, 1); pz = ROW(tq, 2);
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        if (i >= 2) {
+            const double *tf = T + (size_t)(i - 2) * 3 * TILE;
+            fx = ROW(tf, 0); fy = ROW(tf, 1); fz = ROW(tf, 2);
+        }
+        double h[HR_FAST];
+#pragma unroll
+        for (int k = 0; k < HR_FAST; ++k) h[k] = 0.0;
+        const int ob = __ldg(tp.op_begin + i), oe = __ldg(tp.op_begin + i + 1);
+        for (int o = ob; o < oe; ++o) {
+            int2 op = __ldg(reinterpret_cast<const int2 *>(tp.ops + o));
+            EdgeRec er = load_edge(tp.edges + op.x);
+            double J[3], Ow, omega_r;
+            if (er.kind == UWBGO_EDGE_RANGE_POSE && op.y == 0) {
+                /* edge (i, i+1): vertex-0 terms left by pose i+1 */
+                const double *st = E.stash + (size_t)er.ant * 5 * CTA_THREADS;
+                J[0] = st[0 * CTA_THREADS];
+                J[1] = st[1 * CTA_THREADS];
+                J[2] = st[2 * CTA_THREADS];
+                Ow = st[3 * CTA_THREADS];
+                omega_r = st[4 * CTA_THREADS];
+            } else {
+                if (UWBGO_L2PF_DIST > 0 && er.slot >= 3 * UWBGO_L2PF_DIST) {
+                    prefetch_l2(E.p.rd + (size_t)(er.slot - 3 * UWBGO_L2PF_DIST) * TILE);
+                    prefetch_l2(E.p.ri + (size_t)(er.slot - 3 * UWBGO_L2PF_DIST) * TILE);
+                }
+                const double d = ROW(E.p.rd, er.slot), info = ROW(E.p.ri, er.slot);
+                double ax, ay, az, qx, qy, qz;
+                if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+                    ax = cx; ay = cy; az = cz;
+                    qx = ANCH(E, er.b * 3); qy = ANCH(E, er.b * 3 + 1); qz = ANCH(E, er.b * 3 + 2);
+                } else { /* edge (i-1, i): vertex 0 is pose i-1 */
+                    ax = px; ay = py; az = pz;
+                    qx = cx; qy = cy; qz = cz;
+                }
+                const double err = d - dist3(ax, ay, az, qx, qy, qz);
+                const double Oe = info * err;
+                omega_r = -Oe;
+                Ow = info;
+                if (er.robust) {
+                    double r1 = E.ck.rho1(err * Oe);
+                    omega_r = omega_r * r1;
+                    Ow = r1 * info;
+                }
+                if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+                    fast_jac_v0(ax, ay, az, qx, qy, qz, d, E.delta, E.scalar, J);
+                } else {
+                    double A[3];
+                    fast_jac_v0(ax, ay, az, qx, qy, qz, d, E.delta, E.scalar, A);
+                    fast_jac_v1(ax, ay, az, qx, qy, qz, d, E.delta, E.scalar, J);
+                    double AtO[3] = {A[0] * Ow, A[1] * Ow, A[2] * Ow};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) h[6 + 3 * r + c] = fma(AtO[r], J[c], h[6 + 3 * r + c]);
+                    double *st = E.stash + (size_t)er.ant * 5 * CTA_THREADS;
+                    st[0 * CTA_THREADS] = A[0];
+                    st[1 * CTA_THREADS] = A[1];
+                    st[2 * CTA_THREADS] = A[2];
+                    st[3 * CTA_THREADS] = Ow;
+                    st[4 * CTA_THREADS] = omega_r;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) h[15 + r] = fma(J[r], omega_r, h[15 + r]);
+            double JtO[3] = {J[0] * Ow, J[1] * Ow, J[2] * Ow};
+            h[0] = fma(JtO[0], J[0], h[0]);
+            h[1] = fma(JtO[0], J[1], h[1]);
+            h[2] = fma(JtO[0], J[2], h[2]);
+            h[3] = fma(JtO[1], J[1], h[3]);
+            h[4] = fma(JtO[1], J[2], h[4]);
+            h[5] = fma(JtO[2], J[2], h[5]);
+        }
+        double *l = E.p.LR + (size_t)i * LR_FAST * TILE;
+        factor_step<3>(h, l, i + 1 < N, i > 0, lambda, G, zn, ok);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ROW(l, 12 + k) = h[15 + k];
+        cx = px; cy = py; cz = pz;
+        px = fx; py = fy; pz = fz;
+    }
+    return ok;
 }
 
 /* One pass after the factor sweep: substitution x_i = c_i - M_i x_{i-1} (ascending), computeScale(),
@@ -436,16 +570,13 @@ UWBGO_DI void fast_solve_chi(const FastEnv &E, bool ok, double lambda, const dou
     double scale = 0.0, p = 0.0, r = 0.0;
     double c0 = 0.0, c1 = 0.0, c2 = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0; /* poses ic and ic-1 */
     int ic = -1;
-    double nl[LR_FAST], nb[3], nt[3]; /* prefetched inputs of the next pose */
+    double nl[LR_FAST], nt[3]; /* prefetched inputs of the next pose */
     {
         const double *l = E.p.LR;
 #pragma unroll
         for (int k = 0; k < LR_FAST; ++k) nl[k] = ROW(l, k);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            nb[k] = ROW(E.p.HB, 15 + k);
-            nt[k] = ROW(Tc, k);
-        }
+        for (int k = 0; k < 3; ++k) nt[k] = ROW(Tc, k);
     }
     const int ns = tp.n_sched;
     for (int s = 0; s < ns; ++s) {
@@ -453,24 +584,32 @@ UWBGO_DI void fast_solve_chi(const FastEnv &E, bool ok, double lambda, const dou
         if (op.x == 0) {
             const int i = op.y;
             double l[LR_FAST], b[3], t[3];
+            if (UWBGO_SOLVE_REGPF) {
 #pragma unroll
-            for (int k = 0; k < LR_FAST; ++k) l[k] = nl[k];
+                for (int k = 0; k < LR_FAST; ++k) l[k] = nl[k];
+            } else {
+                const double *lc = E.p.LR + (size_t)i * LR_FAST * TILE;
+#pragma unroll
+                for (int k = 0; k < LR_FAST; ++k) l[k] = ROW(lc, k);
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                b[k] = nb[k];
+                b[k] = l[12 + k];
                 t[k] = nt[k];
+            }
+            if (UWBGO_L2PF_DIST > 0 && i + UWBGO_L2PF_DIST < N) {
+                prefetch_rows_l2<LR_FAST>(E.p.LR + (size_t)(i + UWBGO_L2PF_DIST) * LR_FAST * TILE);
+                prefetch_rows_l2<3>(Tc + (size_t)(i + UWBGO_L2PF_DIST) * 3 * TILE);
             }
             if (i + 1 < N) {
                 const double *ln = E.p.LR + (size_t)(i + 1) * LR_FAST * TILE;
-                const double *hn = E.p.HB + (size_t)(i + 1) * HR_FAST * TILE;
                 const double *tn = Tc + (size_t)(i + 1) * 3 * TILE;
+                if (UWBGO_SOLVE_REGPF) {
 #pragma unroll
-                for (int k = 0; k < LR_FAST; ++k) nl[k] = ROW(ln, k);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    nb[k] = ROW(hn, 15 + k);
-                    nt[k] = ROW(tn, k);
+                    for (int k = 0; k < LR_FAST; ++k) nl[k] = ROW(ln, k);
                 }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) nt[k] = ROW(tn, k);
             }
             subst_step<3>(l, i > 0, xp);
             if (!ok) xp[0] = xp[1] = xp[2] = 0.0;
@@ -501,6 +640,10 @@ UWBGO_DI void fast_solve_chi(const FastEnv &E, bool ok, double lambda, const dou
             } else {
                 const double *tb = Tn + (size_t)er.b * 3 * TILE;
                 qx = ROW(tb, 0); qy = ROW(tb, 1); qz = ROW(tb, 2);
+            }
+            if (UWBGO_L2PF_DIST > 0 && er.slot + 2 * UWBGO_L2PF_DIST < tp.Er) {
+                prefetch_l2(E.p.rd + (size_t)(er.slot + 2 * UWBGO_L2PF_DIST) * TILE);
+                prefetch_l2(E.p.ri + (size_t)(er.slot + 2 * UWBGO_L2PF_DIST) * TILE);
             }
             double err = ROW(E.p.rd, er.slot) - dist3(ax, ay, az, qx, qy, qz);
             double Oe = ROW(E.p.ri, er.slot) * err;
@@ -1070,21 +1213,21 @@ struct Path;
 template <>
 struct Path<true> {
     FastEnv E;
-    UWBGO_DI void chi(int buf, double &p, double &r) const { fast_chi_pass(E, E.p.T[buf], p, r); }
-    UWBGO_DI double linearize(int buf) const { return fast_linearize(E, E.p.T[buf]); }
+    UWBGO_DI void chi(int buf, double &p, double &r) const { fast_chi_pass(E, E.p.T(buf), p, r); }
+    UWBGO_DI double linearize(int buf) const { return fast_linearize<false>(E, E.p.T(buf)); }
     /* factor + substitution + update + residuals of one LM trial */
     UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
     {
         /* the rotation pivots of the 6x6 blocks are exactly lambda */
-        bool ok = (lambda > 0.0) && factor_sweep<3>(E.p.HB, E.p.LR, E.tp->N, lambda);
-        fast_solve_chi(E, ok, lambda, E.p.T[from], E.p.T[to], scale, p, r);
+        bool ok = fast_factor_mf(E, E.p.T(from), lambda) && (lambda > 0.0);
+        fast_solve_chi(E, ok, lambda, E.p.T(from), E.p.T(to), scale, p, r);
         return ok;
     }
 };
 template <>
 struct Path<false> {
     GenEnv E;
-    UWBGO_DI PoseBuf buf(int k) const { return PoseBuf{E.p.T[k], E.p.Rm[k]}; }
+    UWBGO_DI PoseBuf buf(int k) const { return PoseBuf{E.p.T(k), E.p.Rm(k)}; }
     UWBGO_DI void chi(int k, double &p, double &r) const { gen_chi_pass(E, buf(k), p, r); }
     UWBGO_DI double linearize(int k) const { return gen_linearize(E, buf(k)); }
     UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
@@ -1114,10 +1257,14 @@ UWBGO_DI void lm_window(const Path<FAST> &P, const DevCfg &cfg, double *chi2_out
     while (!done) {
         if (need_lin) {
             stale = plainCur; /* computeActiveErrors at unchanged estimates */
-            double maxdiag = P.linearize(cur);
-            if (it == 0) {
-                lambda = cfg.tau * maxdiag;
-                ni = 2.0;
+            /* GENERAL: buildSystem() into the H records.  FAST: H is rebuilt inside every trial's
+             * factor sweep; only computeLambdaInit() needs a pass of its own. */
+            if (!FAST || it == 0) {
+                double maxdiag = P.linearize(cur);
+                if (it == 0) {
+                    lambda = cfg.tau * maxdiag;
+                    ni = 2.0;
+                }
             }
             rho = 0.0;
             q = 0;
@@ -1209,7 +1356,7 @@ lm_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCf
     int cur;
     lm_window<true>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
     if (cur) { /* result always leaves in buffer 0 */
-        for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T[0], r) = ROW(P.E.p.T[1], r);
+        for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T0, r) = ROW(P.E.p.T1, r);
     }
     if (P.E.p.cnt) { /* VertexSE3::_numOplusCalls: 12 per range edge end per linearisation, 1 per trial */
         const int it = ROW(ws.status + tile * 4 * TILE + lane, 0), tr = ROW(ws.status + tile * 4 * TILE + lane, 1);
@@ -1244,8 +1391,8 @@ lm_general_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ De
     int cur;
     lm_window<false>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
     if (cur) {
-        for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T[0], r) = ROW(P.E.p.T[1], r);
-        for (int r = 0; r < tp.N * 9; ++r) ROW(P.E.p.Rm[0], r) = ROW(P.E.p.Rm[1], r);
+        for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T0, r) = ROW(P.E.p.T1, r);
+        for (int r = 0; r < tp.N * 9; ++r) ROW(P.E.p.Rm0, r) = ROW(P.E.p.Rm1, r);
     }
 }
 
@@ -1260,8 +1407,8 @@ linearize_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
     FastEnv E;
     fast_env_init(E, tp, cfg, ws, w, smem, anchors_in_smem);
     double p, r;
-    fast_chi_pass(E, E.p.T[0], p, r);
-    fast_linearize(E, E.p.T[0]);
+    fast_chi_pass(E, E.p.T0, p, r);
+    fast_linearize<true>(E, E.p.T0);
     double *c = ws.chi2 + (w / TILE) * 2 * TILE + (w % TILE);
     ROW(c, 0) = p;
     ROW(c, 1) = r;
@@ -1276,7 +1423,7 @@ linearize_general_kernel(const __grid_constant__ DevTopo tp, const __grid_consta
     GenEnv E;
     gen_env_init(E, tp, cfg, ws, w);
     double p, r;
-    PoseBuf T0{E.p.T[0], E.p.Rm[0]};
+    PoseBuf T0{E.p.T0, E.p.Rm0};
     gen_chi_pass(E, T0, p, r);
     gen_linearize(E, T0);
     double *c = ws.chi2 + (w / TILE) * 2 * TILE + (w % TILE);

@@ -1,0 +1,24 @@
+"""Developer loop: end-to-end (host buffers) timing of uwbgo_solve_batch vs pipeline settings."""
+import ctypes as C, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from localization_b200 import Batch, Config, Result, Solver, synthetic, _ffi
+from localization_b200.solver import pinned_empty
+W, N, A = 65536, 50, 8
+topo, batch, _ = synthetic.uwb_only(W, N, A)
+cfg = Config(max_iterations=10)
+s = Solver(0)
+hb = Batch(pose_t=batch.pose_t, anchors=batch.anchors, range_d=batch.range_d, range_info=batch.range_info)
+for k in ("pose_t", "anchors", "range_d", "range_info"):
+    a = pinned_empty(getattr(batch, k).shape); a[...] = getattr(batch, k); setattr(hb, k, a)
+res = Result(pinned_empty((W, N, 3)), None, None, pinned_empty((W, 4)), pinned_empty((W, 4), np.int32))
+def run():
+    s.solve(topo, hb, cfg, out=res)
+settings = [(16384, 3), (8192, 4), (8192, 3), (4096, 4), (32768, 2), (65536, 1), (16384, 4), (12288, 4), (2048, 4)]
+for chunk, lanes in settings:
+    s.set_pipeline(chunk, lanes)
+    for _ in range(2): run()
+    t0 = time.perf_counter()
+    for _ in range(4): run()
+    dt = (time.perf_counter() - t0) / 4
+    print(f"chunk={chunk:6d} lanes={lanes}  {dt*1e3:7.2f} ms/step  {W/dt/1e6:.2f} M windows/s", flush=True)

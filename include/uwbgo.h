@@ -126,7 +126,7 @@ void uwbgo_destroy(uwbgo_ctx *ctx);
 const char *uwbgo_last_error(void);
 
 /* Tuning of the host-pointer entry points: windows per pipeline chunk (rounded up to 32) and
- * number of concurrent stream lanes (1..4).  Defaults: 16384 windows, 3 lanes. */
+ * number of concurrent stream lanes (1..8).  Defaults: 16384 windows, 4 lanes. */
 int  uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes);
 /* Page-locked host memory.  The host-pointer entry points accept any host memory; with buffers
  * from uwbgo_host_alloc their copies overlap the kernels of neighbouring chunks. */

@@ -86,13 +86,13 @@ struct Lane {
     DevBuf tile;  /* tile-layout workspace */
 };
 
-constexpr int MAX_LANES = 4;
+constexpr int MAX_LANES = 8;
 
 }  // namespace
 
 struct uwbgo_ctx {
     int device = 0;
-    int n_lanes = 3;
+    int n_lanes = 4;
     int64_t chunk = 16384;
     Lane lane[MAX_LANES];
     DevBuf misc;          /* ant offsets + factor_solve scratch + lambda etc. */
@@ -590,7 +590,7 @@ int uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes)
 {
     if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
     if (windows_per_chunk < 32 || n_lanes < 1 || n_lanes > MAX_LANES)
-        return fail(UWBGO_E_INVALID, "windows_per_chunk >= 32 and 1 <= n_lanes <= 4 required");
+        return fail(UWBGO_E_INVALID, "windows_per_chunk >= 32 and 1 <= n_lanes <= 8 required");
     ctx->chunk = (windows_per_chunk + 31) / 32 * 32;
     ctx->n_lanes = n_lanes;
     return 0;
@@ -706,7 +706,10 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
     if ((rc = upload_ant(ctx, g, in, ctx->lane[0].st, &d_ant))) return rc;
 
     const size_t N = (size_t)g.N;
-    const int64_t chunk = std::min<int64_t>(ctx->chunk, (W + 31) / 32 * 32);
+    /* the LM kernel's duration is set by per-window latency, not by the chunk size, so a batch
+     * that fits n_lanes chunks is split evenly and all its chunks run concurrently */
+    int64_t chunk = std::min<int64_t>(ctx->chunk, (W + 31) / 32 * 32);
+    if (W <= ctx->chunk * ctx->n_lanes) chunk = std::max<int64_t>(32, ((W + ctx->n_lanes - 1) / ctx->n_lanes + 31) / 32 * 32);
     StageLayout S;
     {
         size_t o = 0;

@@ -256,7 +256,7 @@ def test_chunked_pipeline_is_shard_invariant(solver):
     try:
         parts = solver.solve(topo, batch, cfg)
     finally:
-        solver.set_pipeline(16384, 3)
+        solver.set_pipeline(16384, 4)
     assert_parity(parts, whole)
     halves = [solver.solve(topo, batch.slice(0, 500), cfg), solver.solve(topo, batch.slice(500, 1000), cfg)]
     assert np.array_equal(np.concatenate([h.pose_t for h in halves]), whole.pose_t)

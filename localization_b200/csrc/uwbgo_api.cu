@@ -74,6 +74,7 @@ struct TopoEntry {
     DevTopo gen{};        /* edge table with antenna numbers                   */
     DevTopo fast{};       /* edge table with carry slots (fast-eligible only)  */
     bool fast_ok = false;
+    bool chain_ok = false; /* standard addRangeEdge chain: straight-line sweeps */
     void *dmem = nullptr;
     uint64_t stamp = 0;
 };
@@ -215,6 +216,21 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
         }
         fedges[e] = f;
     }
+    /* the window Localization::addRangeEdge builds: per pose k its anchor range edge, then (k > 0)
+     * the trajectory edge (k-1, k) -- localization.cpp:331-340 */
+    std::vector<ChainPose> chain((size_t)N, ChainPose{0, 0});
+    bool chain_ok = fast_ok && E == 2 * N - 1;
+    for (int k = 0, e = 0; chain_ok && k < N; ++k) {
+        const EdgeRec &ra = edges[e++];
+        chain_ok = ra.kind == UWBGO_EDGE_RANGE_ANCHOR && ra.a == k;
+        chain[k].anchor = ra.b;
+        chain[k].robust = ra.robust ? 1 : 0;
+        if (chain_ok && k > 0) {
+            const EdgeRec &rt = edges[e++];
+            chain_ok = rt.kind == UWBGO_EDGE_RANGE_POSE && rt.a == k - 1 && rt.b == k;
+            chain[k].robust |= rt.robust ? 2 : 0;
+        }
+    }
     std::vector<PoseOp> ops;
     std::vector<int32_t> op_begin((size_t)N + 1, 0);
     for (int i = 0; i < N; ++i) {
@@ -244,7 +260,8 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     size_t o_begin = o_ops + al(sizeof(PoseOp) * std::max<size_t>(ops.size(), 1));
     size_t o_calls = o_begin + al(sizeof(int32_t) * (N + 1));
     size_t o_sched = o_calls + al(sizeof(int32_t) * N);
-    size_t total = o_sched + al(sizeof(SchedOp) * sched.size());
+    size_t o_chain = o_sched + al(sizeof(SchedOp) * sched.size());
+    size_t total = o_chain + al(sizeof(ChainPose) * N);
     std::vector<char> host(total, 0);
     if (E) {
         memcpy(host.data() + o_edges, edges.data(), sizeof(EdgeRec) * E);
@@ -254,6 +271,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     memcpy(host.data() + o_begin, op_begin.data(), sizeof(int32_t) * (N + 1));
     memcpy(host.data() + o_calls, calls.data(), sizeof(int32_t) * N);
     memcpy(host.data() + o_sched, sched.data(), sizeof(SchedOp) * sched.size());
+    memcpy(host.data() + o_chain, chain.data(), sizeof(ChainPose) * N);
 
     auto ent = std::make_unique<TopoEntry>();
     CU(cudaMalloc(&ent->dmem, total));
@@ -278,9 +296,11 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     g.num_calls = reinterpret_cast<const int32_t *>(d + o_calls);
     g.sched = reinterpret_cast<const SchedOp *>(d + o_sched);
     g.n_sched = (int32_t)sched.size();
+    g.chain = reinterpret_cast<const ChainPose *>(d + o_chain);
     ent->gen = g;
     ent->fast = g;
-    ent->fast.fast = 1;
+    ent->fast.fast = chain_ok ? 2 : 1;
+    ent->chain_ok = chain_ok;
     ent->fast.edges = reinterpret_cast<const EdgeRec *>(d + o_fedges);
     ent->fast_ok = fast_ok;
     ent->key = std::move(key);
@@ -473,7 +493,7 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
         CU(launch_unpack(uj, st));
         ctx->launches += 1;
     }
-    ctx->last_path = fast ? 1 : 0;
+    ctx->last_path = fast ? tp.fast : 0;
     if (timed) ctx->k_valid = true;
     return 0;
 }

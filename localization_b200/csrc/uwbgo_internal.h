@@ -54,10 +54,19 @@ struct SchedOp {
     int32_t idx;
 };
 
+/* CHAIN path: per-pose table of the window Localization::addRangeEdge builds (one anchor range
+ * edge per pose, then the trajectory edge to its predecessor) */
+struct ChainPose {
+    int32_t anchor; /* anchor index of the pose's range edge                         */
+    int32_t robust; /* bit 0: anchor edge has a kernel; bit 1: trajectory edge (k-1,k) */
+};
+
 struct DevTopo {
     int32_t N, A, K, E, Er, Ep, Es;
-    int32_t fast;               /* 1: range edges only, no offsets -> translation-only path */
+    int32_t fast;               /* 0 general 6x6 path; 1 translation-only path; 2 translation-only, */
+                                /* standard chain (straight-line sweeps)                            */
     int32_t n_sched, pad;
+    const ChainPose *chain;     /* [N], fast == 2 only                                       */
     const SchedOp *sched;       /* [n_sched = N + E]                                         */
     const EdgeRec *edges;       /* [E]                                                       */
     const PoseOp *ops;          /* concatenated per-pose op lists                            */

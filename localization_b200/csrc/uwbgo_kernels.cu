@@ -279,8 +279,9 @@ struct FastEnv {
     Cauchy ck;
     double delta, scalar;
     double *stash;      /* shared memory: [2*FAST_MAX_CARRY][5][CTA_THREADS], this thread's column */
-    const double *anch; /* anchors: shared-memory copy (stride CTA_THREADS) or the tile rows (TILE) */
+    const double *anch; /* anchors: shared-memory copy (stride blockDim.x) or the tile rows (TILE) */
     int anch_stride;
+    int bs;             /* blockDim.x: stride of the shared-memory columns */
 };
 #define ANCH(E, k) ((E).anch[(size_t)(k) * (E).anch_stride])
 
@@ -398,20 +399,20 @@ UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
                     for (int r = 0; r < 3; ++r)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) ho[3 * r + c] = fma(AtO[r], B[c], ho[3 * r + c]);
-                    double *st = E.stash + (size_t)er.ant * 5 * CTA_THREADS; /* ant = carry slot */
-                    st[0 * CTA_THREADS] = B[0];
-                    st[1 * CTA_THREADS] = B[1];
-                    st[2 * CTA_THREADS] = B[2];
-                    st[3 * CTA_THREADS] = Ow;
-                    st[4 * CTA_THREADS] = omega_r;
+                    double *st = E.stash + (size_t)er.ant * 5 * E.bs; /* ant = carry slot */
+                    st[0 * E.bs] = B[0];
+                    st[1 * E.bs] = B[1];
+                    st[2 * E.bs] = B[2];
+                    st[3 * E.bs] = Ow;
+                    st[4 * E.bs] = omega_r;
                 }
             } else {
-                const double *st = E.stash + (size_t)er.ant * 5 * CTA_THREADS;
-                J[0] = st[0 * CTA_THREADS];
-                J[1] = st[1 * CTA_THREADS];
-                J[2] = st[2 * CTA_THREADS];
-                Ow = st[3 * CTA_THREADS];
-                omega_r = st[4 * CTA_THREADS];
+                const double *st = E.stash + (size_t)er.ant * 5 * E.bs;
+                J[0] = st[0 * E.bs];
+                J[1] = st[1 * E.bs];
+                J[2] = st[2 * E.bs];
+                Ow = st[3 * E.bs];
+                omega_r = st[4 * E.bs];
             }
             /* constructQuadraticForm, 1-D error: b += J^T omega_r ; H += (J^T Ow) J */
 #pragma unroll
@@ -486,12 +487,12 @@ UWBGO_DI bool fast_factor_mf(const FastEnv &E, const double *__restrict__ T, dou
             double J[3], Ow, omega_r;
             if (er.kind == UWBGO_EDGE_RANGE_POSE && op.y == 0) {
                 /* edge (i, i+1): vertex-0 terms left by pose i+1 */
-                const double *st = E.stash + (size_t)er.ant * 5 * CTA_THREADS;
-                J[0] = st[0 * CTA_THREADS];
-                J[1] = st[1 * CTA_THREADS];
-                J[2] = st[2 * CTA_THREADS];
-                Ow = st[3 * CTA_THREADS];
-                omega_r = st[4 * CTA_THREADS];
+                const double *st = E.stash + (size_t)er.ant * 5 * E.bs;
+                J[0] = st[0 * E.bs];
+                J[1] = st[1 * E.bs];
+                J[2] = st[2 * E.bs];
+                Ow = st[3 * E.bs];
+                omega_r = st[4 * E.bs];
             } else {
                 if (UWBGO_L2PF_DIST > 0 && er.slot >= 3 * UWBGO_L2PF_DIST) {
                     prefetch_l2(E.p.rd + (size_t)(er.slot - 3 * UWBGO_L2PF_DIST) * TILE);
@@ -526,12 +527,12 @@ UWBGO_DI bool fast_factor_mf(const FastEnv &E, const double *__restrict__ T, dou
                     for (int r = 0; r < 3; ++r)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) h[6 + 3 * r + c] = fma(AtO[r], J[c], h[6 + 3 * r + c]);
-                    double *st = E.stash + (size_t)er.ant * 5 * CTA_THREADS;
-                    st[0 * CTA_THREADS] = A[0];
-                    st[1 * CTA_THREADS] = A[1];
-                    st[2 * CTA_THREADS] = A[2];
-                    st[3 * CTA_THREADS] = Ow;
-                    st[4 * CTA_THREADS] = omega_r;
+                    double *st = E.stash + (size_t)er.ant * 5 * E.bs;
+                    st[0 * E.bs] = A[0];
+                    st[1 * E.bs] = A[1];
+                    st[2 * E.bs] = A[2];
+                    st[3 * E.bs] = Ow;
+                    st[4 * E.bs] = omega_r;
                 }
             }
 #pragma unroll
@@ -651,6 +652,239 @@ UWBGO_DI void fast_solve_chi(const FastEnv &E, bool ok, double lambda, const dou
             p = p + chi;
             r = r + (er.robust ? E.ck.rho0(chi) : chi);
         }
+    }
+    scale_out = scale;
+    plain = p;
+    robust = r;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* CHAIN path: the FAST path specialised for the window Localization::addRangeEdge builds         */
+/* (localization.cpp:331-340): edges in insertion order are, for pose k = 0..N-1, the anchor     */
+/* range edge of pose k followed (k > 0) by the trajectory edge (k-1, k).  With the structure     */
+/* known, both sweeps are straight-line code per pose: no edge-table decode, everything the next  */
+/* pose needs is loaded one pose ahead, and in the factor sweep the H record of pose i-1 is        */
+/* rebuilt in the same basic block in which pose i is eliminated, so the 18 independent sqrt       */
+/* chains of the numeric Jacobians fill the issue slots of the sqrt/div dependency chain of the   */
+/* 3x3 potrf.  Same arithmetic, same order, same bits as the table-driven FAST path.              */
+/* ------------------------------------------------------------------------------------------ */
+UWBGO_DI void chain_weights(const FastEnv &E, double err, double info, bool robust, double &Ow,
+                            double &omega_r)
+{
+    const double Oe = info * err;
+    const double r1 = E.ck.rho1(err * Oe);
+    omega_r = robust ? (-Oe) * r1 : -Oe;
+    Ow = robust ? r1 * info : info;
+}
+UWBGO_DI void chain_acc(const double *J, double Ow, double omega_r, double *h)
+{
+#pragma unroll
+    for (int r = 0; r < 3; ++r) h[15 + r] = fma(J[r], omega_r, h[15 + r]);
+    const double JtO[3] = {J[0] * Ow, J[1] * Ow, J[2] * Ow};
+    h[0] = fma(JtO[0], J[0], h[0]);
+    h[1] = fma(JtO[0], J[1], h[1]);
+    h[2] = fma(JtO[0], J[2], h[2]);
+    h[3] = fma(JtO[1], J[1], h[3]);
+    h[4] = fma(JtO[1], J[2], h[4]);
+    h[5] = fma(JtO[2], J[2], h[5]);
+}
+
+/* inputs of one pose of the factor sweep, loaded one pose ahead */
+struct ChainIn {
+    double px, py, pz;      /* t_{i-1} */
+    double da, ia, dt, it;  /* anchor edge of pose i: d, info; edge (i-1, i): d, info */
+    int anchor, robust;
+};
+template <bool PREV>
+UWBGO_DI void chain_load(const FastEnv &E, const double *__restrict__ T, int i, ChainIn &in)
+{
+    const int2 tb = __ldg(reinterpret_cast<const int2 *>(E.tp->chain + i));
+    in.anchor = tb.x;
+    in.robust = tb.y;
+    const int sa = i == 0 ? 0 : 2 * i - 1;
+    in.da = ROW(E.p.rd, sa);
+    in.ia = ROW(E.p.ri, sa);
+    if (PREV) {
+        const double *tq = T + (size_t)(i - 1) * 3 * TILE;
+        in.px = ROW(tq, 0); in.py = ROW(tq, 1); in.pz = ROW(tq, 2);
+        in.dt = ROW(E.p.rd, 2 * i);
+        in.it = ROW(E.p.ri, 2 * i);
+    } else {
+        in.px = in.py = in.pz = in.dt = in.it = 0.0;
+    }
+}
+
+/* H record of pose i from (cx,cy,cz) = t_i and `in`; carry = vertex-0 terms of edge (i, i+1) on
+ * entry (zeros at the newest pose: an exact no-op), of edge (i-1, i) on exit */
+template <bool PREV>
+UWBGO_DI void chain_build(const FastEnv &E, double cx, double cy, double cz, const ChainIn &in,
+                          double *carry, double *h)
+{
+#pragma unroll
+    for (int k = 0; k < HR_FAST; ++k) h[k] = 0.0;
+    double J[3], Ow, omega_r;
+    {
+        const double qx = ANCH(E, in.anchor * 3), qy = ANCH(E, in.anchor * 3 + 1), qz = ANCH(E, in.anchor * 3 + 2);
+        const double err = in.da - dist3(cx, cy, cz, qx, qy, qz);
+        fast_jac_v0(cx, cy, cz, qx, qy, qz, in.da, E.delta, E.scalar, J);
+        chain_weights(E, err, in.ia, (in.robust & 1) != 0, Ow, omega_r);
+        chain_acc(J, Ow, omega_r, h);
+    }
+    double nA[3] = {0.0, 0.0, 0.0}, nOw = 0.0, nOr = 0.0;
+    if (PREV) {
+        const double err = in.dt - dist3(in.px, in.py, in.pz, cx, cy, cz);
+        fast_jac_v0(in.px, in.py, in.pz, cx, cy, cz, in.dt, E.delta, E.scalar, nA);
+        fast_jac_v1(in.px, in.py, in.pz, cx, cy, cz, in.dt, E.delta, E.scalar, J);
+        chain_weights(E, err, in.it, (in.robust & 2) != 0, nOw, nOr);
+        const double AtO[3] = {nA[0] * nOw, nA[1] * nOw, nA[2] * nOw};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) h[6 + 3 * r + c] = fma(AtO[r], J[c], h[6 + 3 * r + c]);
+        chain_acc(J, nOw, nOr, h);
+    }
+    chain_acc(carry, carry[3], carry[4], h);
+    carry[0] = nA[0]; carry[1] = nA[1]; carry[2] = nA[2];
+    carry[3] = nOw; carry[4] = nOr;
+}
+
+UWBGO_DI void chain_store_b(double *__restrict__ l, const double *h)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ROW(l, 12 + k) = h[15 + k];
+}
+
+UWBGO_DI bool chain_factor(const FastEnv &E, const double *__restrict__ T, double lambda)
+{
+    const int N = E.tp->N;
+    double G[9], zn[3], carry[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) G[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) zn[k] = 0.0;
+    double *LR = E.p.LR;
+    const double *tl = T + (size_t)(N - 1) * 3 * TILE;
+    double cx = ROW(tl, 0), cy = ROW(tl, 1), cz = ROW(tl, 2);
+    double hc[HR_FAST], hn[HR_FAST];
+    ChainIn in, nx;
+    if (N == 1) {
+        chain_load<false>(E, T, 0, in);
+        chain_build<false>(E, cx, cy, cz, in, carry, hc);
+        factor_step<3>(hc, LR, true, false, lambda, G, zn, ok);
+        chain_store_b(LR, hc);
+        return ok;
+    }
+    chain_load<true>(E, T, N - 1, in);
+    if (N > 2) chain_load<true>(E, T, N - 2, nx);
+    else chain_load<false>(E, T, 0, nx);
+    chain_build<true>(E, cx, cy, cz, in, carry, hc);
+    cx = in.px; cy = in.py; cz = in.pz;
+    in = nx;
+    for (int i = N - 1; i >= 2; --i) {
+        /* inputs of pose i-2 go in flight; pose i-1 is rebuilt while pose i is eliminated */
+        if (i > 2) chain_load<true>(E, T, i - 2, nx);
+        else chain_load<false>(E, T, 0, nx);
+        if (UWBGO_L2PF_DIST > 0 && i >= 2 + 2 * UWBGO_L2PF_DIST) {
+            const int j = i - 2 - 2 * UWBGO_L2PF_DIST;
+            prefetch_rows_l2<3>(T + (size_t)j * 3 * TILE);
+            prefetch_l2(E.p.rd + (size_t)(2 * j) * TILE);
+            prefetch_l2(E.p.ri + (size_t)(2 * j) * TILE);
+            prefetch_l2(E.p.rd + (size_t)(2 * j + 1) * TILE);
+            prefetch_l2(E.p.ri + (size_t)(2 * j + 1) * TILE);
+        }
+        chain_build<true>(E, cx, cy, cz, in, carry, hn);
+        double *l = LR + (size_t)i * LR_FAST * TILE;
+        factor_step<3>(hc, l, true, true, lambda, G, zn, ok);
+        chain_store_b(l, hc);
+#pragma unroll
+        for (int k = 0; k < HR_FAST; ++k) hc[k] = hn[k];
+        cx = in.px; cy = in.py; cz = in.pz;
+        in = nx;
+    }
+    /* i == 1: pose 0 has no predecessor */
+    chain_build<false>(E, cx, cy, cz, in, carry, hn);
+    {
+        double *l = LR + (size_t)LR_FAST * TILE;
+        factor_step<3>(hc, l, true, true, lambda, G, zn, ok);
+        chain_store_b(l, hc);
+    }
+    factor_step<3>(hn, LR, true, false, lambda, G, zn, ok);
+    chain_store_b(LR, hn);
+    return ok;
+}
+
+/* inputs of one pose of the substitution sweep */
+struct ChainSub {
+    double l[LR_FAST];
+    double tx, ty, tz;
+    double da, ia, dt, it;
+    int anchor, robust;
+};
+UWBGO_DI void chain_sub_load(const FastEnv &E, const double *__restrict__ Tc, int i, ChainSub &s)
+{
+    const double *l = E.p.LR + (size_t)i * LR_FAST * TILE;
+#pragma unroll
+    for (int k = 0; k < LR_FAST; ++k) s.l[k] = ROW(l, k);
+    const double *t = Tc + (size_t)i * 3 * TILE;
+    s.tx = ROW(t, 0); s.ty = ROW(t, 1); s.tz = ROW(t, 2);
+    const int2 tb = __ldg(reinterpret_cast<const int2 *>(E.tp->chain + i));
+    s.anchor = tb.x;
+    s.robust = tb.y;
+    const int sa = i == 0 ? 0 : 2 * i - 1;
+    s.da = ROW(E.p.rd, sa);
+    s.ia = ROW(E.p.ri, sa);
+    if (i > 0) {
+        s.dt = ROW(E.p.rd, 2 * i);
+        s.it = ROW(E.p.ri, 2 * i);
+    } else {
+        s.dt = s.it = 0.0;
+    }
+}
+
+UWBGO_DI void chain_solve_chi(const FastEnv &E, bool ok, double lambda, const double *__restrict__ Tc,
+                              double *__restrict__ Tn, double &scale_out, double &plain,
+                              double &robust)
+{
+    const int N = E.tp->N;
+    double xp[3] = {0.0, 0.0, 0.0};
+    double scale = 0.0, p = 0.0, r = 0.0;
+    double vx = 0.0, vy = 0.0, vz = 0.0; /* new estimate of pose i-1 */
+    ChainSub cur, nxt;
+    chain_sub_load(E, Tc, 0, cur);
+    for (int i = 0; i < N; ++i) {
+        if (i + 1 < N) chain_sub_load(E, Tc, i + 1, nxt);
+        if (UWBGO_L2PF_DIST > 0 && i + 1 + UWBGO_L2PF_DIST < N) {
+            const int j = i + 1 + UWBGO_L2PF_DIST;
+            prefetch_rows_l2<LR_FAST>(E.p.LR + (size_t)j * LR_FAST * TILE);
+            prefetch_rows_l2<3>(Tc + (size_t)j * 3 * TILE);
+            prefetch_l2(E.p.rd + (size_t)(2 * j) * TILE);
+            prefetch_l2(E.p.ri + (size_t)(2 * j) * TILE);
+            prefetch_l2(E.p.rd + (size_t)(2 * j - 1) * TILE);
+            prefetch_l2(E.p.ri + (size_t)(2 * j - 1) * TILE);
+        }
+        subst_step<3>(cur.l, i > 0, xp);
+        if (!ok) xp[0] = xp[1] = xp[2] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) scale = scale + xp[k] * (lambda * xp[k] + cur.l[12 + k]);
+        const double cx = xp[0] + cur.tx, cy = xp[1] + cur.ty, cz = xp[2] + cur.tz;
+        double *to = Tn + (size_t)i * 3 * TILE;
+        ROW(to, 0) = cx; ROW(to, 1) = cy; ROW(to, 2) = cz;
+        {
+            const double err = cur.da - dist3(cx, cy, cz, ANCH(E, cur.anchor * 3), ANCH(E, cur.anchor * 3 + 1),
+                                              ANCH(E, cur.anchor * 3 + 2));
+            const double chi = err * (cur.ia * err);
+            p = p + chi;
+            r = r + ((cur.robust & 1) ? E.ck.rho0(chi) : chi);
+        }
+        if (i > 0) {
+            const double err = cur.dt - dist3(vx, vy, vz, cx, cy, cz);
+            const double chi = err * (cur.it * err);
+            p = p + chi;
+            r = r + ((cur.robust & 2) ? E.ck.rho0(chi) : chi);
+        }
+        vx = cx; vy = cy; vz = cz;
+        cur = nxt;
     }
     scale_out = scale;
     plain = p;
@@ -1207,11 +1441,25 @@ __device__ __noinline__ double gen_solve_update(const GenEnv &E, bool ok, double
 /* ------------------------------------------------------------------------------------------ */
 /* optimize(iteration_max) with OptimizationAlgorithmLevenberg, one window per thread           */
 /* ------------------------------------------------------------------------------------------ */
-template <bool FAST>
+/* MODE 0: GENERAL, 1: FAST (table-driven), 2: CHAIN */
+template <int MODE>
 struct Path;
 
 template <>
-struct Path<true> {
+struct Path<2> {
+    FastEnv E;
+    UWBGO_DI void chi(int buf, double &p, double &r) const { fast_chi_pass(E, E.p.T(buf), p, r); }
+    UWBGO_DI double linearize(int buf) const { return fast_linearize<false>(E, E.p.T(buf)); }
+    UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
+    {
+        bool ok = chain_factor(E, E.p.T(from), lambda) && (lambda > 0.0);
+        chain_solve_chi(E, ok, lambda, E.p.T(from), E.p.T(to), scale, p, r);
+        return ok;
+    }
+};
+
+template <>
+struct Path<1> {
     FastEnv E;
     UWBGO_DI void chi(int buf, double &p, double &r) const { fast_chi_pass(E, E.p.T(buf), p, r); }
     UWBGO_DI double linearize(int buf) const { return fast_linearize<false>(E, E.p.T(buf)); }
@@ -1225,7 +1473,7 @@ struct Path<true> {
     }
 };
 template <>
-struct Path<false> {
+struct Path<0> {
     GenEnv E;
     UWBGO_DI PoseBuf buf(int k) const { return PoseBuf{E.p.T(k), E.p.Rm(k)}; }
     UWBGO_DI void chi(int k, double &p, double &r) const { gen_chi_pass(E, buf(k), p, r); }
@@ -1245,10 +1493,11 @@ struct Path<false> {
  * last trial ended an iteration, then run one trial": every pass of a warp does useful trial work
  * on every unfinished lane, and only the (cheaper) linearisation runs on a subset of lanes.  The
  * per-window arithmetic and its order are unchanged. */
-template <bool FAST>
-UWBGO_DI void lm_window(const Path<FAST> &P, const DevCfg &cfg, double *chi2_out,
+template <int MODE>
+UWBGO_DI void lm_window(const Path<MODE> &P, const DevCfg &cfg, double *chi2_out,
                         int32_t *status_out, int &cur_out)
 {
+    constexpr bool FAST = MODE != 0;
     double lambda = 0.0, ni = 2.0, stale, plainCur, currentChi, rho = 0.0;
     int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0, q = 0, it = 0;
     P.chi(cur, plainCur, currentChi);
@@ -1320,7 +1569,7 @@ UWBGO_DI void lm_window(const Path<FAST> &P, const DevCfg &cfg, double *chi2_out
 }
 
 /* dynamic shared memory of the FAST kernels: carry stash, then (when they fit) the anchors */
-constexpr int STASH_DOUBLES = 2 * FAST_MAX_CARRY * 5 * CTA_THREADS;
+constexpr int STASH_PER_THREAD = 2 * FAST_MAX_CARRY * 5;
 
 UWBGO_DI void fast_env_init(FastEnv &E, const DevTopo &tp, const DevCfg &cfg, const DevWs &ws,
                             int64_t w, double *smem, int anchors_in_smem)
@@ -1330,31 +1579,31 @@ UWBGO_DI void fast_env_init(FastEnv &E, const DevTopo &tp, const DevCfg &cfg, co
     E.ck.init(cfg.kdelta);
     E.delta = cfg.jdelta;
     E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    E.bs = (int)blockDim.x;
     E.stash = smem + threadIdx.x;
     if (anchors_in_smem) {
-        double *a = smem + STASH_DOUBLES + threadIdx.x;
-        for (int k = 0; k < tp.A * 3; ++k) a[(size_t)k * CTA_THREADS] = ROW(E.p.anch, k);
+        double *a = smem + (size_t)STASH_PER_THREAD * blockDim.x + threadIdx.x;
+        for (int k = 0; k < tp.A * 3; ++k) a[(size_t)k * blockDim.x] = ROW(E.p.anch, k);
         E.anch = a;
-        E.anch_stride = CTA_THREADS;
+        E.anch_stride = (int)blockDim.x;
     } else {
         E.anch = E.p.anch;
         E.anch_stride = TILE;
     }
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 4)
-lm_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
-               const __grid_constant__ DevWs ws, int anchors_in_smem)
+template <int MODE>
+UWBGO_DI void lm_fast_body(const DevTopo &tp, const DevCfg &cfg, const DevWs &ws, int anchors_in_smem,
+                           double *smem)
 {
-    extern __shared__ double smem[];
-    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= ws.W) return;
-    Path<true> P;
+    Path<MODE> P;
     fast_env_init(P.E, tp, cfg, ws, w, smem, anchors_in_smem);
     const int64_t tile = w / TILE;
     const int lane = (int)(w % TILE);
     int cur;
-    lm_window<true>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
+    lm_window<MODE>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
     if (cur) { /* result always leaves in buffer 0 */
         for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T0, r) = ROW(P.E.p.T1, r);
     }
@@ -1365,6 +1614,29 @@ lm_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCf
             P.E.p.cnt[(size_t)i * TILE] = (int)(c % cfg.orth_mod);
         }
     }
+}
+
+#ifndef UWBGO_FAST_MINB
+#define UWBGO_FAST_MINB 4
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, UWBGO_FAST_MINB)
+lm_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+               const __grid_constant__ DevWs ws, int anchors_in_smem)
+{
+    extern __shared__ double smem[];
+    lm_fast_body<1>(tp, cfg, ws, anchors_in_smem, smem);
+}
+
+#ifndef UWBGO_CHAIN_THREADS
+#define UWBGO_CHAIN_THREADS 64
+#define UWBGO_CHAIN_REGS 255
+#endif
+__global__ void __maxnreg__(UWBGO_CHAIN_REGS)
+lm_chain_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+                const __grid_constant__ DevWs ws, int anchors_in_smem)
+{
+    extern __shared__ double smem[];
+    lm_fast_body<2>(tp, cfg, ws, anchors_in_smem, smem);
 }
 
 UWBGO_DI void gen_env_init(GenEnv &E, const DevTopo &tp, const DevCfg &cfg, const DevWs &ws, int64_t w)
@@ -1384,12 +1656,12 @@ lm_general_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ De
 {
     const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     if (w >= ws.W) return;
-    Path<false> P;
+    Path<0> P;
     gen_env_init(P.E, tp, cfg, ws, w);
     const int64_t tile = w / TILE;
     const int lane = (int)(w % TILE);
     int cur;
-    lm_window<false>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
+    lm_window<0>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
     if (cur) {
         for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T0, r) = ROW(P.E.p.T1, r);
         for (int r = 0; r < tp.N * 9; ++r) ROW(P.E.p.Rm0, r) = ROW(P.E.p.Rm1, r);
@@ -1542,11 +1814,12 @@ cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st) { return launc
 static unsigned window_blocks(int64_t W) { return (unsigned)((W + CTA_THREADS - 1) / CTA_THREADS); }
 
 /* dynamic shared memory of a FAST launch; anchors go to shared memory when 4 CTAs/SM still fit */
-static size_t fast_smem_bytes(const DevTopo &topo, int *anchors_in_smem)
+static size_t fast_smem_bytes(const DevTopo &topo, int threads, int *anchors_in_smem)
 {
-    size_t stash = sizeof(double) * STASH_DOUBLES;
-    size_t anch = sizeof(double) * (size_t)topo.A * 3 * CTA_THREADS;
-    *anchors_in_smem = (topo.A > 0 && stash + anch <= 56 * 1024) ? 1 : 0;
+    size_t stash = sizeof(double) * STASH_PER_THREAD * threads;
+    size_t anch = sizeof(double) * (size_t)topo.A * 3 * threads;
+    /* budget: the CTAs that fill an SM (512 threads) must fit in its 227 KB */
+    *anchors_in_smem = (topo.A > 0 && (stash + anch) * (512 / threads) <= 220 * 1024) ? 1 : 0;
     return stash + (*anchors_in_smem ? anch : 0);
 }
 
@@ -1555,10 +1828,12 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
     if (ws.W <= 0) return cudaSuccess;
     if (topo.fast) {
         int ais = 0;
-        size_t sm = fast_smem_bytes(topo, &ais);
-        cudaError_t e = cudaFuncSetAttribute(lm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        const int threads = topo.fast == 2 ? UWBGO_CHAIN_THREADS : CTA_THREADS;
+        size_t sm = fast_smem_bytes(topo, threads, &ais);
+        auto kern = topo.fast == 2 ? lm_chain_kernel : lm_fast_kernel;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
-        lm_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, sm, st>>>(topo, cfg, ws, ais);
+        kern<<<(unsigned)((ws.W + threads - 1) / threads), threads, sm, st>>>(topo, cfg, ws, ais);
     } else
         lm_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
     return cudaGetLastError();
@@ -1570,7 +1845,7 @@ cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs
     if (ws.W <= 0) return cudaSuccess;
     if (topo.fast) {
         int ais = 0;
-        size_t sm = fast_smem_bytes(topo, &ais);
+        size_t sm = fast_smem_bytes(topo, CTA_THREADS, &ais);
         cudaError_t e = cudaFuncSetAttribute(linearize_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         linearize_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, sm, st>>>(topo, cfg, ws, ais);

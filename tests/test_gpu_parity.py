@@ -35,7 +35,7 @@ def test_uwb_only_fast_path(solver, W, N, A):
     topo, batch, _ = synthetic.uwb_only(W, N, A, seed=7 + W)
     cfg = Config(max_iterations=10)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 1
+    assert solver.last_path in (1, 2)
     ref = oracle.solve(topo, batch, cfg)
     assert_parity(got, ref)
     assert (ref.status[:, 0] == 10).all()
@@ -46,7 +46,7 @@ def test_general_path_equals_fast_path(solver):
     topo, batch, _ = synthetic.uwb_only(64, 20, 8, seed=3)
     cfg = Config(max_iterations=10)
     fast = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 1
+    assert solver.last_path in (1, 2)
     batch.pose_R = np.tile(np.eye(3), (64, 20, 1, 1))
     gen = solver.solve(topo, batch, cfg)
     assert solver.last_path == 0
@@ -90,7 +90,7 @@ def test_oplus_counter_carry_and_reorthogonalisation(solver):
     batch.oplus_count = rng.integers(0, 1001, size=(40, 10)).astype(np.int32)
     cfg = Config(max_iterations=10)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 1
+    assert solver.last_path in (1, 2)
     assert_parity(got, oracle.solve(topo, batch, cfg))
 
 
@@ -194,7 +194,7 @@ def test_multiple_range_edges_per_pose_and_unordered_insertion(solver):
                   range_d=np.abs(rng.normal(3, 1, (W, er))), range_info=rng.uniform(10, 400, (W, er)))
     cfg = Config(max_iterations=6)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 1
+    assert solver.last_path in (1, 2)
     assert_parity(got, oracle.solve(topo, batch, cfg))
     # a third edge on the same pair exceeds the fast path's carry slots -> general path, same bits
     topo3 = Topology.from_edges(N, A, 0, edges + [(EDGE_RANGE_POSE, 2, 3, 0, 1)])

@@ -275,9 +275,9 @@ def main():
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp) and W == WINDOWS_PER_GPU:
             with open(tp) as f:
-                tj = json.load(f)["lm_fast_kernel"]
+                tj = json.load(f)["lm_chain_kernel"]
             traffic, traffic_src = tj["dram_bytes_per_launch"] / 1e9, tj["source"]
-        roof = {"bound": "hbm", "kernel": "lm_fast_kernel (fused LM: linearise + assemble + block Cholesky + damping loop)",
+        roof = {"bound": "hbm", "kernel": "lm_chain_kernel (fused LM: linearise + assemble + block Cholesky + damping loop)",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if achieved else None,
                 "traffic": traffic, "traffic_unit": "GB per launch (dram read+write, ncu)", "traffic_source": traffic_src,
                 "peak_source": how, "kernel_ms": k_best,

@@ -1,0 +1,153 @@
+"""CPU tests of the host layer (ROS-free Localization / Robot, rows f1-f2 of SURVEY §8): the example
+recording replayed through the C++ host library with the CPU oracle plugged in as the solver (the
+product backend needs a GPU), window shapes, gates, log format, ATE against Vicon."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from localization_b200.host import Fleet, LocParams
+from localization_b200.tools import ate
+from localization_b200.tools.replay import load_messages, node_params, replay
+from oracle import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MSGS = os.path.join(HERE, "golden", "bag_example_msgs.npz")
+REF_CFG = "/root/reference/cfg"
+
+# cfg/uwb_only.yaml and cfg/uwb_imu.yaml values (committed here: /root/reference is absent on the GPU box)
+UWB_ONLY = dict(trajectory_length=10, maximum_velocity=5.0, distance_outlier=1.0, maximum_iteration=10,
+                minimum_optimize_error=2000.0, publish_range=True)
+UWB_IMU = dict(trajectory_length=12, maximum_velocity=3.0, distance_outlier=3.0, maximum_iteration=10,
+               minimum_optimize_error=1000.0, publish_range=True, publish_imu=False)
+
+
+def oracle_backend(record=None):
+    lib = oracle.load()
+
+    def fn(_user, topo, batch, cfg, out):
+        if record is not None:
+            t, b = topo.contents, batch.contents
+            record.append((t.n_poses, t.n_anchors, t.n_edges, int(b.n_windows), bool(b.pose_R)))
+        return lib.uwbgo_oracle_solve_batch(topo, batch, cfg, out, None, 1)
+    return fn
+
+
+def test_cfg_values_match_reference_yaml():
+    if not os.path.isdir(REF_CFG):
+        pytest.skip("reference tree not present")
+    p = LocParams.from_yaml(os.path.join(REF_CFG, "uwb_only.yaml"))
+    assert {k: getattr(p, k) for k in UWB_ONLY} == UWB_ONLY
+    p = LocParams.from_yaml(os.path.join(REF_CFG, "uwb_imu.yaml"))
+    assert {k: getattr(p, k) for k in UWB_IMU} == UWB_IMU
+
+
+def test_bag_fixture_matches_bag():
+    """the committed message fixture is what the rosbag reader extracts from the reference's bag"""
+    bag = "/root/reference/bag/data_example.bag"
+    if not os.path.exists(bag):
+        pytest.skip("reference tree not present")
+    from localization_b200.tools.rosbag_reader import load_example_bag
+    b, m = load_example_bag(bag), load_messages(MSGS)
+    assert len(b.uwb_stamp) == 1444 and len(b.imu_sec) == 4514 and len(b.vicon_stamp) == 1965
+    assert np.array_equal(b.uwb_distance.astype(np.float32), m["uwb_distance"])
+    assert np.array_equal(b.imu_quat_xyzw, m["imu_quat_xyzw"])
+    assert set(b.uwb_frame) == {"uwb"} and set(b.imu_frame) == {"imu_link"}
+    # anchors: SURVEY §4.3
+    loc = {int(r): tuple(l) for r, l in zip(b.uwb_responder, b.uwb_responder_location)}
+    assert loc == {100: (3.0, -3.0, 0.58), 101: (3.0, 3.0, 1.97), 102: (-3.0, 3.0, 0.54), 103: (-3.0, -3.0, 1.76)}
+
+
+def test_uwb_only_replay(tmp_path):
+    """BASELINE configs[0]: data_example.bag through cfg/uwb_only.yaml, single robot"""
+    msgs = load_messages(MSGS)
+    rec = []
+    fleet = Fleet(solve_fn=oracle_backend(rec))
+    prm = LocParams(**UWB_ONLY, filename_prefix=str(tmp_path / "run"), filename_suffix="_t.txt")
+    replay(msgs, prm, fleet, members=1)
+    st = fleet.stats(0)
+    # 1444 ranges, solve once the window has filled: SURVEY §4.3 (1,434 solves, 10 poses, 19 edges)
+    assert st["solves"] == 1434 and st["errors"] == 0 and st["skipped"] == 0
+    assert all(r == (10, 4, 19, 1, False) for r in rec)   # identity rotations -> pose_R NULL -> fast path
+    rt, op, err = fleet.published(0)
+    assert len(rt) == 1434 - st["rejected"] or len(rt) == 1434
+    assert (err < 2000).all() and np.median(err) < 10
+    gt_t, gt_p = msgs["vicon_stamp"], msgs["vicon_pos"]
+    res = ate.evaluate_ate(gt_t, gt_p, rt[:, 0], rt[:, 1:4])
+    assert res["pairs"] > 1000 and res["rmse"] < 0.30, res          # decimetre level (0.18 m raw 3-D)
+    assert res["rmse_xy_raw"] < 0.12, res                           # 6.5 cm xy in the survey probe
+    res_opt = ate.evaluate_ate(gt_t, gt_p, op[:, 0], op[:, 1:4])
+    assert res_opt["rmse"] < 0.30
+    # TUM log: 3 '#' header lines, then "stamp x y z qx qy qz qw" per publish
+    fleet.close()
+    lines = open(str(tmp_path / "run_realtime_t.txt")).read().splitlines()
+    assert lines[0] == "# iteration_max:10" and lines[1] == "# trajectory_length:10"
+    body = [l for l in lines if not l.startswith("#")]
+    assert len(body) == len(rt) and len(body[0].split()) == 8
+    s, x = ate.read_trajectory(str(tmp_path / "run_realtime_t.txt"))
+    assert np.allclose(s, rt[:, 0]) and np.allclose(x, rt[:, 1:4], atol=1e-5)
+    # the destructor appends the newer half of the final window to the optimized log (localization.cpp:705-716)
+    s2, _ = ate.read_trajectory(str(tmp_path / "run_optimized_t.txt"))
+    assert len(s2) == len(op) + 5
+
+
+def test_uwb_imu_replay_window_shape():
+    """BASELINE configs[1] window shape: 12 poses, 12 + 11 range-type edges, 11 IMU priors"""
+    msgs = load_messages(MSGS)
+    rec = []
+    fleet = Fleet(solve_fn=oracle_backend(rec))
+    replay(msgs, LocParams(**UWB_IMU), fleet, members=1, use_imu=True, max_ranges=200)
+    st = fleet.stats(0)
+    assert st["solves"] == 200 - 12 and st["errors"] == 0
+    assert all(r == (12, 4, 34, 1, True) for r in rec[5:])           # 23 range + 11 prior edges, rotations present
+    rt, _, err = fleet.published(0)
+    assert len(rt) > 150 and (err < 1000).all()
+    res = ate.evaluate_ate(msgs["vicon_stamp"], msgs["vicon_pos"], rt[:, 0], rt[:, 1:4])
+    assert res["rmse"] < 0.5, res
+
+
+def test_fleet_batches_by_structure():
+    """M replicas in lockstep -> one batch of M windows per flush; replicas with identical inputs
+    stay identical, a perturbed replica diverges"""
+    msgs = load_messages(MSGS)
+    rec = []
+    fleet = Fleet(solve_fn=oracle_backend(rec))
+    noise = np.zeros((3, len(msgs["uwb_distance"])))
+    noise[2] = np.random.default_rng(0).normal(0, 0.05, noise.shape[1])
+    replay(msgs, LocParams(**UWB_ONLY), fleet, members=3, range_noise=noise, max_ranges=60)
+    assert all(r[3] == 3 for r in rec) and len(rec) == 50
+    a, b, c = (fleet.published(i)[0] for i in range(3))
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert fleet.stats(0)["fleet_windows"] == 150 and fleet.stats(0)["fleet_batches"] == 50
+
+
+def test_outlier_gate_and_chi2_gate():
+    msgs = load_messages(MSGS)
+    fleet = Fleet(solve_fn=oracle_backend())
+    p = node_params(msgs, LocParams(**{**UWB_ONLY, "minimum_optimize_error": 1e-9}))
+    fleet.add(p)
+    for i in range(30):
+        d = float(msgs["uwb_distance"][i]) + (5.0 if i == 20 else 0.0)   # a 5 m outlier after warm-up
+        fleet.add_range(0, int(msgs["uwb_seq"][i]), int(msgs["uwb_sec"][i]), int(msgs["uwb_nsec"][i]), "uwb",
+                        200, int(msgs["uwb_responder"][i]), d, float(msgs["uwb_distance_err"][i]), 1)
+        fleet.flush()
+    st = fleet.stats(0)
+    assert st["rejected"] == 1                       # |estimate - d| > distance_outlier (localization.cpp:308)
+    assert st["solves"] == 30 - 10 - 1
+    assert st["skipped"] == st["solves"]             # every error >= minimum_optimize_error -> publish skipped
+    assert len(fleet.published(0)[0]) == 0
+
+
+def test_non_chain_pose_edges_are_refused():
+    """addPoseEdge ties every new pose to a key vertex (localization.cpp:258-267): not a chain"""
+    msgs = load_messages(MSGS)
+    fleet = Fleet(solve_fn=oracle_backend())
+    p = node_params(msgs, LocParams(**{**UWB_ONLY, "publish_range": False, "publish_pose": True}))
+    fleet.add(p)
+    cov = np.eye(6).reshape(-1) * 0.01
+    for k in range(4):
+        fleet.add_pose(0, k, 100 + k, 0, "kf0", [0.1 * k, 0, 1.0], [0, 0, 0, 1], cov)
+        fleet.flush()
+    st = fleet.stats(0)
+    assert st["errors"] >= 1 and "non-consecutive" in fleet.last_error(0)

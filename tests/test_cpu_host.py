@@ -15,9 +15,10 @@ from localization_b200.shard import window_range
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "uwbgo.h")).read()
+def header_functions(name="uwbgo.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef[^;]*\(\s*\*\s*\w+\s*\)[^;]*;", "", src)   # function-pointer typedefs are not symbols
     return sorted(set(re.findall(r"\b(uwbgo_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -29,6 +30,17 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/uwbgo.h but not exported"
     assert sorted(_ffi.SYMBOLS) == names, "ctypes table and header disagree"
     assert _ffi.load_library().uwbgo_abi_version() == _ffi.ABI_VERSION
+
+
+def test_host_library_exports_every_declared_symbol():
+    from localization_b200 import host
+    lib = host.load_host_library()
+    names = header_functions("uwbgo_host.h")
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/uwbgo_host.h but not exported"
+    assert sorted(host.HOST_SYMBOLS) == names, "ctypes table and header disagree"
+    assert ctypes.sizeof(host.CLocParams) == 8 + 24 + 8 + 24 + 24 + 16
 
 
 def test_structs_match_header_layout():

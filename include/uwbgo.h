@@ -34,16 +34,16 @@ extern "C" {
 /* error codes */
 #define UWBGO_OK              0
 #define UWBGO_E_INVALID     (-1)  /* bad argument / inconsistent sizes            */
-#define UWBGO_E_TOPOLOGY    (-2)  /* window is not a chain (block-tridiagonal H)  */
+#define UWBGO_E_TOPOLOGY    (-2)  /* some pose has two different older neighbours  */
 #define UWBGO_E_CUDA        (-3)  /* CUDA runtime error (text in last_error)      */
 #define UWBGO_E_NODEVICE    (-4)  /* no usable sm_100 GPU                         */
 #define UWBGO_E_NOMEM       (-5)
 
 /* edge kinds (the four edge types Localization creates) */
 #define UWBGO_EDGE_RANGE_ANCHOR 0 /* EdgeSE3Range(pose, fixed anchor)   localization.cpp:331,350 */
-#define UWBGO_EDGE_RANGE_POSE   1 /* EdgeSE3Range(prev pose, new pose), measurement 0  localization.cpp:338 */
+#define UWBGO_EDGE_RANGE_POSE   1 /* EdgeSE3Range(older pose, newer pose), measurement 0 localization.cpp:338 */
 #define UWBGO_EDGE_PRIOR        2 /* EdgeSE3Prior on one pose (IMU / lidar)            localization.cpp:481,520 */
-#define UWBGO_EDGE_SE3          3 /* EdgeSE3(prev pose, new pose) (twist)              localization.cpp:588 */
+#define UWBGO_EDGE_SE3          3 /* EdgeSE3(older pose, newer pose): twist localization.cpp:588, pose :263 */
 
 /*
  * Topology: the structure of the g2o graph, shared by every window of one batch
@@ -61,8 +61,11 @@ typedef struct uwbgo_topology {
     int32_t n_edges;      /* E                                                              */
     const int32_t *edge_kind;   /* [E] UWBGO_EDGE_*                                          */
     const int32_t *edge_a;      /* [E] vertex 0: pose index 0..N-1 (0 = oldest)              */
-    const int32_t *edge_b;      /* [E] vertex 1: anchor index (RANGE_ANCHOR), pose index =   */
-                                /*     edge_a+1 (RANGE_POSE, SE3), ignored (PRIOR)           */
+    const int32_t *edge_b;      /* [E] vertex 1: anchor index (RANGE_ANCHOR); a NEWER pose    */
+                                /*     index > edge_a (RANGE_POSE, SE3); ignored (PRIOR).     */
+                                /*     Every pose may have at most ONE older pose neighbour   */
+                                /*     (chains: its predecessor; addPoseEdge: its key vertex, */
+                                /*     localization.cpp:258-267), else UWBGO_E_TOPOLOGY       */
     const int32_t *edge_ant;    /* [E] RANGE_*: antenna number of the vertex-0 offset,       */
                                 /*     0 = identity, k>0 = ant_offsets[k-1] (localization.cpp:333) */
     const int32_t *edge_robust; /* [E] 1 = RobustKernelCauchy (delta 1), 0 = no kernel       */
@@ -150,7 +153,8 @@ int uwbgo_solve_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo, const u
  * One linearisation at the given estimates: computeActiveErrors + buildSystem
  * (g2o BlockSolver; numeric Jacobians of BaseBinaryEdge for the range edges).
  *   H_diag [W][N][36]   diagonal 6x6 blocks, row-major, both triangles
- *   H_off  [W][N-1][36] block (i, i+1), rows of pose i, columns of pose i+1
+ *   H_off  [W][N-1][36] H_off[j] = block (parent(j+1), j+1): rows of the older neighbour of
+ *                       pose j+1 (chains: pose j), columns of pose j+1
  *   b      [W][N][6]
  *   chi2   [W][2]       {plain, robust} at the linearisation point
  * host pointers. */

@@ -133,16 +133,16 @@ int validate_topology(const uwbgo_topology *T, std::vector<int32_t> &slot, Slots
             slot[e] = sl.Er++;
             break;
         case UWBGO_EDGE_RANGE_POSE:
-            if (b != a + 1 || b >= T->n_poses)
-                return fail(UWBGO_E_TOPOLOGY, "pose-pose range edge must join consecutive poses");
+            if (b <= a || b >= T->n_poses)
+                return fail(UWBGO_E_TOPOLOGY, "pose-pose edge: vertex 1 must be a newer pose than vertex 0");
             slot[e] = sl.Er++;
             break;
         case UWBGO_EDGE_PRIOR:
             slot[e] = sl.Ep++;
             break;
         case UWBGO_EDGE_SE3:
-            if (b != a + 1 || b >= T->n_poses)
-                return fail(UWBGO_E_TOPOLOGY, "SE3 edge must join consecutive poses");
+            if (b <= a || b >= T->n_poses)
+                return fail(UWBGO_E_TOPOLOGY, "pose-pose edge: vertex 1 must be a newer pose than vertex 0");
             slot[e] = sl.Es++;
             break;
         default:
@@ -183,6 +183,26 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
             return 0;
         }
 
+    /* forest rule: the newest-first elimination has no fill iff every pose has at most one older
+     * neighbour (chains: its predecessor; pose edges: the key vertex of its keyframe) */
+    std::vector<int32_t> parent((size_t)N, -1);
+    bool tree = false;
+    for (int e = 0; e < E; ++e) {
+        const int k = T->edge_kind[e];
+        if (k != UWBGO_EDGE_RANGE_POSE && k != UWBGO_EDGE_SE3) continue;
+        const int a = T->edge_a[e], b = T->edge_b[e];
+        if (parent[b] >= 0 && parent[b] != a)
+            return fail(UWBGO_E_TOPOLOGY, "a pose with two different older neighbours needs a fill-in aware solver");
+        parent[b] = a;
+        if (a != b - 1) tree = true;
+    }
+    std::vector<int32_t> child_begin((size_t)N + 1, 0), children;
+    for (int i = 0; i < N; ++i) {
+        child_begin[i] = (int32_t)children.size();
+        for (int c = N - 1; c > i; --c)
+            if (parent[c] == i) children.push_back(c);
+    }
+    child_begin[N] = (int32_t)children.size();
     std::vector<EdgeRec> edges((size_t)E), fedges((size_t)E);
     std::vector<int32_t> calls((size_t)N, 0), carry((size_t)N, 0);
     std::vector<std::vector<PoseOp>> per_pose((size_t)N);
@@ -211,7 +231,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
         if (r.kind > UWBGO_EDGE_RANGE_POSE || r.ant != 0) fast_ok = false;
         if (r.kind == UWBGO_EDGE_RANGE_POSE) {
             int k = carry[r.a]++;
-            if (k >= 2) fast_ok = false;
+            if (k >= 2 || r.b != r.a + 1) fast_ok = false;
             f.ant = (r.a & 1) * 2 + k; /* shared-memory carry slot of the vertex-1 terms */
         }
         fedges[e] = f;
@@ -261,7 +281,10 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     size_t o_calls = o_begin + al(sizeof(int32_t) * (N + 1));
     size_t o_sched = o_calls + al(sizeof(int32_t) * N);
     size_t o_chain = o_sched + al(sizeof(SchedOp) * sched.size());
-    size_t total = o_chain + al(sizeof(ChainPose) * N);
+    size_t o_parent = o_chain + al(sizeof(ChainPose) * N);
+    size_t o_cbegin = o_parent + al(sizeof(int32_t) * N);
+    size_t o_children = o_cbegin + al(sizeof(int32_t) * (N + 1));
+    size_t total = o_children + al(sizeof(int32_t) * std::max<size_t>(children.size(), 1));
     std::vector<char> host(total, 0);
     if (E) {
         memcpy(host.data() + o_edges, edges.data(), sizeof(EdgeRec) * E);
@@ -272,6 +295,9 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     memcpy(host.data() + o_calls, calls.data(), sizeof(int32_t) * N);
     memcpy(host.data() + o_sched, sched.data(), sizeof(SchedOp) * sched.size());
     memcpy(host.data() + o_chain, chain.data(), sizeof(ChainPose) * N);
+    memcpy(host.data() + o_parent, parent.data(), sizeof(int32_t) * N);
+    memcpy(host.data() + o_cbegin, child_begin.data(), sizeof(int32_t) * (N + 1));
+    if (!children.empty()) memcpy(host.data() + o_children, children.data(), sizeof(int32_t) * children.size());
 
     auto ent = std::make_unique<TopoEntry>();
     CU(cudaMalloc(&ent->dmem, total));
@@ -297,6 +323,10 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     g.sched = reinterpret_cast<const SchedOp *>(d + o_sched);
     g.n_sched = (int32_t)sched.size();
     g.chain = reinterpret_cast<const ChainPose *>(d + o_chain);
+    g.tree = tree ? 1 : 0;
+    g.parent = reinterpret_cast<const int32_t *>(d + o_parent);
+    g.child_begin = reinterpret_cast<const int32_t *>(d + o_cbegin);
+    g.children = reinterpret_cast<const int32_t *>(d + o_children);
     ent->gen = g;
     ent->fast = g;
     ent->fast.fast = chain_ok ? 2 : 1;
@@ -381,7 +411,7 @@ TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bo
     L.off_sI = take((size_t)t.Es * 36, 8);
     /* FAST solves rebuild H inside the factor sweep and never store it */
     L.off_HB = (fast && want_LR) ? 0 : take(N * (fast ? HR_FAST : HR_GEN), 8);
-    L.off_LR = want_LR ? take(N * (fast ? LR_FAST : LR_GEN), 8) : 0;
+    L.off_LR = want_LR ? take(N * (fast ? LR_FAST : (t.tree ? LR_TREE : LR_GEN)), 8) : 0;
     L.off_chi2 = take(4, 8);
     L.off_status = take(4, 4);
     L.bytes = o;

@@ -28,6 +28,7 @@ constexpr int HR_FAST = 18;       /* Hd upper 6 | link block 9 | b 3            
 constexpr int HR_GEN = 63;        /* Hd upper 21 | link block 36 | b 6            */
 constexpr int LR_FAST = 15;       /* c 3 | M 9 | b 3   (x_i = c_i - M_i x_{i-1})  */
 constexpr int LR_GEN = 42;        /* c 6 | M 36                                   */
+constexpr int LR_TREE = 90;       /* c 6 | M 36 | G 36 | z 6 | x 6  (forest windows) */
 
 /* One edge of the shared topology, in g2o insertion order. */
 struct EdgeRec {
@@ -65,8 +66,12 @@ struct DevTopo {
     int32_t N, A, K, E, Er, Ep, Es;
     int32_t fast;               /* 0 general 6x6 path; 1 translation-only path; 2 translation-only, */
                                 /* standard chain (straight-line sweeps)                            */
-    int32_t n_sched, pad;
+    int32_t n_sched;
+    int32_t tree;               /* 1: some pose's older neighbour is not its predecessor     */
     const ChainPose *chain;     /* [N], fast == 2 only                                       */
+    const int32_t *parent;      /* [N] the one older neighbour of pose j, -1 = none          */
+    const int32_t *child_begin; /* [N+1] CSR over `children`                                 */
+    const int32_t *children;    /* children of each pose, descending                         */
     const SchedOp *sched;       /* [n_sched = N + E]                                         */
     const EdgeRec *edges;       /* [E]                                                       */
     const PoseOp *ops;          /* concatenated per-pose op lists                            */

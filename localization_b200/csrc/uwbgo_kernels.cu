@@ -104,7 +104,7 @@ UWBGO_DI Ptrs thread_ptrs(const DevTopo &tp, const DevWs &ws, int64_t w)
     p.sZ = ws.sZ ? ws.sZ + (tile * (size_t)tp.Es * 12) * TILE + lane : nullptr;
     p.sI = ws.sI ? ws.sI + (tile * (size_t)tp.Es * 36) * TILE + lane : nullptr;
     p.HB = ws.HB + (tile * (size_t)tp.N * HR) * TILE + lane;
-    p.LR = ws.LR ? ws.LR + (tile * (size_t)tp.N * LRR) * TILE + lane : nullptr;
+    p.LR = ws.LR ? ws.LR + (tile * (size_t)tp.N * (tp.tree ? LR_TREE : LRR)) * TILE + lane : nullptr;
     return p;
 }
 
@@ -1320,14 +1320,16 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
                 if (op.y == 0) {
                     gen_jac_v0(E, Xi, er.ant, Q, d, ci, er.base_a, J);
                     acc1_diag(J, Ow, omega_r, hd, bb);
-                    if (er.kind == UWBGO_EDGE_RANGE_POSE) {
-                        double B[6];
-                        gen_jac_v1(E, P0, Xo, d, B);
-                        acc1_off(J, B, Ow, ho);
-                    }
                 } else {
+                    /* vertex 1: its own terms, and the block H_{a,i} = A^T Ow B of the pair.  Pose a was
+                     * swept earlier, so its counter already includes this linearisation's calls. */
                     gen_jac_v1(E, P0, Xi, d, J);
                     acc1_diag(J, Ow, omega_r, hd, bb);
+                    double A[6];
+                    const int ca_now = E.p.cnt[(size_t)er.a * TILE];
+                    const int ca = ((ca_now - __ldg(tp.num_calls + er.a)) % mod + mod) % mod;
+                    gen_jac_v0(E, Xo, er.ant, Q, d, ca, er.base_a, A);
+                    acc1_off(A, J, Ow, ho);
                 }
             } else if (er.kind == UWBGO_EDGE_PRIOR) {
                 Pose Zinv, Dl;
@@ -1365,7 +1367,7 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
                 } else {
                     load_pose(T, er.a, Xo);
                     se3_error(Zinv, Xo, Xi, e6);
-                    se3_jacobians(Zinv, Xo, Xi, Ji, Jj, false);
+                    se3_jacobians(Zinv, Xo, Xi, Ji, Jj, true);
                 }
                 double chi = chi2_6(E.p.sI, er.slot, e6, Oe);
                 double r1 = er.robust ? E.ck.rho1(chi) : 1.0;
@@ -1379,11 +1381,12 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
                     acc6_b(Ji, Oe, bb);
                     jt_omega(Ji, O, er.robust != 0, r1, JtO);
                     acc6_diag(JtO, Ji, hd);
-                    acc6_off(JtO, Jj, ho);
                 } else {
                     acc6_b(Jj, Oe, bb);
                     jt_omega(Jj, O, er.robust != 0, r1, JtO);
                     acc6_diag(JtO, Jj, hd);
+                    jt_omega(Ji, O, er.robust != 0, r1, JtO);
+                    acc6_off(JtO, Jj, ho); /* H_{a,i}: rows of pose a, columns of pose i */
                 }
             }
         }
@@ -1392,11 +1395,8 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
         for (int k = 0; k < 21; ++k) ROW(h, k) = hd[k];
 #pragma unroll
         for (int k = 0; k < 6; ++k) ROW(h, 57 + k) = bb[k];
-        if (i + 1 < N) {
-            double *hn = h + (size_t)HR_GEN * TILE;
 #pragma unroll
-            for (int k = 0; k < 36; ++k) ROW(hn, 21 + k) = ho[k];
-        }
+        for (int k = 0; k < 36; ++k) ROW(h, 21 + k) = ho[k]; /* H_{parent(i), i} */
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             double v = fabs(hd[up_idx(6, r, r)]);
@@ -1407,14 +1407,142 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
     return maxdiag;
 }
 
+/* Forest windows (pose edges to a key vertex, localization.cpp:258-267): every pose has at most one
+ * older neighbour parent(i) < i, not necessarily i-1.  Same elimination as factor_sweep<6>, newest
+ * pose first and therefore without fill, but a pose may have several children, whose G and z are
+ * read back from their L records:  L record (tree) = c 6 | M 36 | G 36 | z 6 | x 6. */
+__device__ __noinline__ bool factor_sweep_tree(const DevTopo &tp, const double *__restrict__ HB,
+                                               double *__restrict__ LR, double lambda)
+{
+    const int N = tp.N;
+    bool ok = true;
+    for (int i = N - 1; i >= 0; --i) {
+        const double *h = HB + (size_t)i * HR_GEN * TILE;
+        double *l = LR + (size_t)i * LR_TREE * TILE;
+        double S[21], L[21], z[6], c[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int cc = 0; cc <= r; ++cc) {
+                double s = ROW(h, up_idx(6, cc, r));
+                if (r == cc) s = s + lambda;
+                S[lo_idx(r, cc)] = s;
+            }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) z[r] = ROW(h, 57 + r);
+        const int cb = __ldg(tp.child_begin + i), ce = __ldg(tp.child_begin + i + 1);
+        for (int q = cb; q < ce; ++q) { /* children in descending order */
+            const double *lc = LR + (size_t)__ldg(tp.children + q) * LR_TREE * TILE;
+            double G[36], zc[6];
+#pragma unroll
+            for (int k = 0; k < 36; ++k) G[k] = ROW(lc, 42 + k);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) zc[k] = ROW(lc, 78 + k);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int cc = 0; cc <= r; ++cc) {
+                    double s = S[lo_idx(r, cc)];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s = fma(-G[r * 6 + k], G[cc * 6 + k], s);
+                    S[lo_idx(r, cc)] = s;
+                }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                double s = z[r];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s = fma(-G[r * 6 + k], zc[k], s);
+                z[r] = s;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double s = S[lo_idx(j, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
+            if (!(s > 0.0)) ok = false;
+            double inv = 1.0 / sqrt(s);
+            L[lo_idx(j, j)] = inv;
+#pragma unroll
+            for (int r = j + 1; r < 6; ++r) {
+                double t = S[lo_idx(r, j)];
+#pragma unroll
+                for (int k = 0; k < j; ++k) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
+                L[lo_idx(r, j)] = t * inv;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double s = z[r];
+#pragma unroll
+            for (int k = 0; k < r; ++k) s = fma(-L[lo_idx(r, k)], z[k], s);
+            z[r] = s * L[lo_idx(r, r)];
+        }
+#pragma unroll
+        for (int r = 5; r >= 0; --r) {
+            double s = z[r];
+#pragma unroll
+            for (int k = r + 1; k < 6; ++k) s = fma(-L[lo_idx(k, r)], c[k], s);
+            c[r] = s * L[lo_idx(r, r)];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            ROW(l, k) = c[k];
+            ROW(l, 78 + k) = z[k];
+        }
+        if (__ldg(tp.parent + i) >= 0) {
+            double G[36], M[36];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 6; ++cc) {
+                    double s = ROW(h, 21 + r * 6 + cc);
+#pragma unroll
+                    for (int k = 0; k < cc; ++k) s = fma(-G[r * 6 + k], L[lo_idx(cc, k)], s);
+                    G[r * 6 + cc] = s * L[lo_idx(cc, cc)];
+                }
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+#pragma unroll
+                for (int r = 5; r >= 0; --r) {
+                    double s = G[j * 6 + r];
+#pragma unroll
+                    for (int k = r + 1; k < 6; ++k) s = fma(-L[lo_idx(k, r)], M[k * 6 + j], s);
+                    M[r * 6 + j] = s * L[lo_idx(r, r)];
+                }
+#pragma unroll
+            for (int k = 0; k < 36; ++k) {
+                ROW(l, 6 + k) = M[k];
+                ROW(l, 42 + k) = G[k];
+            }
+        }
+    }
+    return ok;
+}
+
 __device__ __noinline__ double gen_solve_update(const GenEnv &E, bool ok, double lambda,
                                                 const PoseBuf &Tc, const PoseBuf &Tn)
 {
     const int N = E.tp->N, mod = E.cfg->orth_mod;
     double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double scale = 0.0;
+    const bool tree = E.tp->tree != 0;
     for (int i = 0; i < N; ++i) {
-        {
+        if (tree) { /* x_i = c_i - M_i x_{parent(i)}; x kept in the L records */
+            double *lp = E.p.LR + (size_t)i * LR_TREE * TILE;
+            const int par = __ldg(E.tp->parent + i);
+            double l[LR_GEN];
+#pragma unroll
+            for (int k = 0; k < LR_GEN; ++k) l[k] = ROW(lp, k);
+            if (par >= 0) {
+                const double *pp = E.p.LR + (size_t)par * LR_TREE * TILE;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) xp[k] = ROW(pp, 84 + k);
+            }
+            subst_step<6>(l, par >= 0, xp);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ROW(lp, 84 + k) = ok ? xp[k] : 0.0;
+        } else {
             const double *lp = E.p.LR + (size_t)i * LR_GEN * TILE;
             double l[LR_GEN];
 #pragma unroll
@@ -1480,7 +1608,8 @@ struct Path<0> {
     UWBGO_DI double linearize(int k) const { return gen_linearize(E, buf(k)); }
     UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
     {
-        bool ok = factor_sweep<6>(E.p.HB, E.p.LR, E.tp->N, lambda);
+        bool ok = E.tp->tree ? factor_sweep_tree(*E.tp, E.p.HB, E.p.LR, lambda)
+                             : factor_sweep<6>(E.p.HB, E.p.LR, E.tp->N, lambda);
         scale = gen_solve_update(E, ok, lambda, buf(from), buf(to));
         gen_chi_pass(E, buf(to), p, r);
         return ok;

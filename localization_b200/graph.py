@@ -117,6 +117,29 @@ class Topology:
         return Topology.from_edges(n_poses, n_anchors, antennas, edges)
 
 
+    @staticmethod
+    def uwb_pose(n_poses: int, n_anchors: int, keyframe_len: int = 4, antennas: int = 0) -> "Topology":
+        """uwb_pose window: vertices are created by Localization::addPoseEdge
+        (localization.cpp:254-290): EdgeSE3(key_vertex, new) with Cauchy kernel, where key_vertex only
+        moves when the keyframe (frame_id) changes, i.e. a star per keyframe, not a chain; range
+        messages in between take the merged-covariance branch (localization.cpp:348-357)."""
+        edges = []
+        for k in range(n_poses):
+            if k > 0:
+                edges.append((EDGE_SE3, ((k - 1) // keyframe_len) * keyframe_len, k, 0, 1))
+            ant = 1 + k % antennas if antennas > 0 else 0
+            edges.append((EDGE_RANGE_ANCHOR, k, k % n_anchors, ant, 1))
+        return Topology.from_edges(n_poses, n_anchors, antennas, edges)
+
+    def parents(self) -> np.ndarray:
+        """the one older neighbour of every pose (-1: none)"""
+        par = np.full(self.n_poses, -1, np.int32)
+        for k, a, b in zip(self.edge_kind, self.edge_a, self.edge_b):
+            if k in (EDGE_RANGE_POSE, EDGE_SE3):
+                par[b] = a
+        return par
+
+
 @dataclass
 class Batch:
     """Per-window numbers of W windows sharing one Topology (see include/uwbgo.h)."""

@@ -195,8 +195,8 @@ bool Localization::pack(PackedWindow &w, std::string &err)
             } else {
                 kind = UWBGO_EDGE_RANGE_POSE;
                 auto pb = pose_index.find(e.to);
-                if (pb == pose_index.end() || pb->second != pa->second + 1) {
-                    err = "range edge between non-consecutive poses";
+                if (pb == pose_index.end() || pb->second <= pa->second) {
+                    err = "range edge whose vertex 1 is not a newer pose of the window";
                     return false;
                 }
                 b = pb->second;
@@ -210,8 +210,8 @@ bool Localization::pack(PackedWindow &w, std::string &err)
         } else {
             kind = UWBGO_EDGE_SE3;
             auto pb = pose_index.find(e.to);
-            if (pb == pose_index.end() || pb->second != pa->second + 1) {
-                err = "EdgeSE3 between non-consecutive poses (key-vertex pose edges need the block-banded path)";
+            if (pb == pose_index.end() || pb->second <= pa->second) {
+                err = "EdgeSE3 whose vertex 1 is not a newer pose of the window";
                 return false;
             }
             b = pb->second;

@@ -221,3 +221,47 @@ def uwb_twist(W: int, N: int = 15, A: int = 8, v_max: float = 1.0, seed: int = S
     batch = Batch(pose_t=init_t, pose_R=init_R, anchors=anchors, range_d=rd, range_info=ri,
                   ant_offsets=off, se3_Z=sZ, se3_info=sI)
     return topo, batch, p
+
+
+def uwb_pose(W: int, N: int = 24, A: int = 8, keyframe_len: int = 4, seed: int = SEED_C3 + 6,
+             antennas: int = 3, v_max: float = 0.5):
+    """Keyframe-relative pose edges (cfg/uwb_pose.yaml): EdgeSE3(key vertex, new vertex) stars plus
+    merged-covariance anchor ranges.  Z = key^-1 * pose + noise, information = Sigma^-1
+    (localization.cpp:271-277)."""
+    rng = np.random.default_rng(seed)
+    anchors = _anchors(rng, W, A)
+    p, vel, dt = _trajectory(rng, W, N)
+    yaw = rng.uniform(-np.pi, np.pi, size=(W, 1)) + np.cumsum(rng.normal(0.0, 0.03, size=(W, N)), axis=1)
+    R_true = _yaw_R(yaw)
+    K = antennas
+    off = ANTENNA_OFFSETS[:K] if K > 0 else None
+    pts = p + np.einsum("wnij,nj->wni", R_true, off[np.arange(N) % K]) if K > 0 else p
+    d, info = _ranges(rng, pts, anchors, A)
+    topo = Topology.uwb_pose(N, A, keyframe_len, antennas=K)
+    par = topo.parents()
+    er, _, es = topo.counts()
+    rd, ri = np.zeros((W, er)), np.zeros((W, er))
+    sZ, sI = np.zeros((W, es, 12)), np.zeros((W, es, 6, 6))
+    sig = np.array([0.02, 0.02, 0.02, 0.01, 0.01, 0.01])
+    for k in range(N):
+        if k > 0:
+            a = par[k]
+            Rrel = np.swapaxes(R_true[:, a], 1, 2) @ R_true[:, k]
+            trel = np.einsum("wji,wj->wi", R_true[:, a], p[:, k] - p[:, a])
+            nz = rng.normal(0, sig[3], (W, 3))
+            sZ[:, k - 1, :9] = (Rrel @ _rpy_R(nz[:, 0], nz[:, 1], nz[:, 2])).reshape(W, 9)
+            sZ[:, k - 1, 9:] = trel + rng.normal(0, sig[0], (W, 3))
+            M = rng.normal(0, 0.1, (W, 6, 6))
+            cov = np.einsum("i,wij,j->wij", sig, np.eye(6)[None] + 0.1 * (M + np.swapaxes(M, 1, 2)), sig)
+            sI[:, k - 1] = np.linalg.inv(cov)
+        rd[:, k] = d[:, k]
+        ri[:, k] = 1.0 / (1.0 / info[:, k] + (v_max * dt[:, max(k - 1, 0)] / 3.0) ** 2)
+    init_t = p + rng.normal(0.0, 0.05, size=(W, N, 3))
+    nz = rng.normal(0.0, 0.02, size=(W, N, 3))
+    init_R = R_true @ _rpy_R(nz[..., 0], nz[..., 1], nz[..., 2])
+    if N > 1:
+        init_t[:, N - 1] = init_t[:, N - 2]
+        init_R[:, N - 1] = init_R[:, N - 2]
+    batch = Batch(pose_t=init_t, pose_R=init_R, anchors=anchors, range_d=rd, range_info=ri,
+                  ant_offsets=off, se3_Z=sZ, se3_info=sI)
+    return topo, batch, p

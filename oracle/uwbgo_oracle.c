@@ -291,12 +291,14 @@ typedef struct {
     int32_t *cnt;
     double *err;  /* [E][6] last computed errors */
     double *Hd;   /* [N][36] diagonal blocks (both triangles) */
-    double *Ho;   /* [N-1][36] block (i,i+1) */
+    double *Ho;   /* [N][36] Ho[j] = block (parent(j), j): rows of the parent, columns of pose j */
+    const int32_t *parent; /* [N] the one older neighbour of pose j (-1: none); chains: j-1 */
     double *b;    /* [N][6] */
     double *x;    /* [N][6] */
     double *Ld;   /* [N][36] M_i of the substitution x_i = c_i - M_i x_{i-1} */
     double *Lo;   /* [N-1][36] scratch G_i */
     double *y;    /* [N][6] c_i */
+    double *zs;   /* [N][6] z_i */
 } window_t;
 
 static const double ZERO3[3] = {0.0, 0.0, 0.0};
@@ -484,7 +486,7 @@ static void accumulate(window_t *W, int D, int i, int j, const double *A, const 
         for (int r = 0; r < 6; ++r)
             for (int c = r; c < 6; ++c) Hii[6 * r + c] = fma(AtO[r], A[c], Hii[6 * r + c]);
         if (B) {
-            double *Hij = W->Ho + 36 * i, *Hjj = W->Hd + 36 * j, *bj = W->b + 6 * j;
+            double *Hij = W->Ho + 36 * j, *Hjj = W->Hd + 36 * j, *bj = W->b + 6 * j;
             double BtO[6];
             for (int r = 0; r < 6; ++r)
                 for (int c = 0; c < 6; ++c) Hij[6 * r + c] = fma(AtO[r], B[c], Hij[6 * r + c]);
@@ -515,7 +517,7 @@ static void accumulate(window_t *W, int D, int i, int j, const double *A, const 
             Hii[6 * r + c] = Hii[6 * r + c] + s;
         }
     if (B) {
-        double *Hij = W->Ho + 36 * i, *Hjj = W->Hd + 36 * j, *bj = W->b + 6 * j;
+        double *Hij = W->Ho + 36 * j, *Hjj = W->Hd + 36 * j, *bj = W->b + 6 * j;
         for (int r = 0; r < 6; ++r)
             for (int c = 0; c < 6; ++c) {
                 double s = AtO[6 * r] * B[c];
@@ -608,7 +610,7 @@ static void build_system(window_t *W)
     const uwbgo_topology *T = W->topo;
     int N = W->N;
     memset(W->Hd, 0, (size_t)N * 36 * sizeof(double));
-    if (N > 1) memset(W->Ho, 0, (size_t)(N - 1) * 36 * sizeof(double));
+    memset(W->Ho, 0, (size_t)N * 36 * sizeof(double));
     memset(W->b, 0, (size_t)N * 6 * sizeof(double));
     for (int e = 0; e < W->E; ++e) {
         int kind = T->edge_kind[e], a = T->edge_a[e], s = W->slot[e];
@@ -668,35 +670,47 @@ static void build_system(window_t *W)
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* linear solver: block-tridiagonal Cholesky of H + lambda I                                    */
-/* Stands in for LinearSolverCholmod (localization.h:84): CHOLMOD factorises P H P^T for its    */
-/* own AMD permutation P, so ANY exact FP64 Cholesky agrees with it up to round-off (SURVEY     */
-/* A.8).  The elimination order chosen here is the chain REVERSED (newest pose first): the      */
-/* factor sweep runs i = N-1..0 and the substitution sweep runs i = 0..N-1, so x comes out in    */
-/* ascending order, the order g2o's computeScale() and update() consume it.  The factor sweep   */
-/* leaves the substitution in the form x_i = c_i - M_i x_{i-1}:                                 */
-/*   L_i   lower factor of S_i = H_ii + lambda I - G_i G_i^T, diagonal kept inverted            */
-/*   G_i   = H_{i,i+1} L_{i+1}^-T   (rows of pose i, columns of pose i+1), i < N-1              */
-/*   z_i   = L_i^-1 (b_i - G_i z_{i+1})                                                         */
-/*   c_i   = L_i^-T z_i              -> y[i]                                                    */
-/*   M_i   = L_i^-T G_{i-1}^T        -> Ld[i]  (i > 0)                                          */
-/* Lo[i] is scratch for G_i.                                                                    */
+/* linear solver: sparse block Cholesky of H + lambda I for windows whose pose graph is a        */
+/* forest in which every pose has at most ONE older neighbour, parent(j) < j.  Chains            */
+/* (parent(j) = j-1: range / twist windows) give block-tridiagonal H; pose edges to a key vertex */
+/* (localization.cpp:258-267) give stars.  Eliminating the NEWEST pose first creates no fill in  */
+/* such a graph (a pose's only not-yet-eliminated neighbour is its parent).                      */
+/* Stands in for LinearSolverCholmod (localization.h:84): CHOLMOD factorises P H P^T for its     */
+/* own AMD permutation P, so ANY exact FP64 Cholesky agrees with it up to round-off (SURVEY      */
+/* A.8).  The factor sweep runs j = N-1..0, the substitution sweep j = 0..N-1, so x comes out in  */
+/* ascending order, the order g2o's computeScale() and update() consume it:                      */
+/*   S_j   = H_jj + lambda I - sum over children c of j (descending c) of G_c G_c^T               */
+/*   L_j   = lower Cholesky factor of S_j, diagonal kept inverted                                 */
+/*   z_j   = L_j^-1 (b_j - sum over children c (descending) of G_c z_c)                           */
+/*   G_j   = H_{parent(j),j} L_j^-T      (rows of the parent, columns of pose j)   -> Lo[j]       */
+/*   c_j   = L_j^-T z_j                  -> y[j]                                                  */
+/*   M_j   = L_j^-T G_j^T                -> Ld[j]                                                 */
+/*   x_j   = c_j - M_j x_{parent(j)}                                                             */
+/* zs [N][6] is scratch for the z_j.                                                             */
 /* ------------------------------------------------------------------------------------------ */
-static int factor_solve(int N, const double *Hd, const double *Ho, const double *b, double lambda,
-                        double *Ld, double *Lo, double *y, double *x)
+static int factor_solve(int N, const int32_t *parent, const double *Hd, const double *Ho,
+                        const double *b, double lambda, double *Ld, double *Lo, double *y,
+                        double *zs, double *x)
 {
-    double z[6] = {0, 0, 0, 0, 0, 0}, zn[6];
     for (int i = N - 1; i >= 0; --i) {
         double S[36], L[36];
-        const double *G = i + 1 < N ? Lo + 36 * i : NULL;
+        double *z = zs + 6 * i;
         for (int r = 0; r < 6; ++r)
             for (int c = 0; c <= r; ++c) {
                 double s = Hd[36 * i + 6 * r + c];
                 if (r == c) s = s + lambda;
-                if (G)
-                    for (int k = 0; k < 6; ++k) s = fma(-G[6 * r + k], G[6 * c + k], s);
                 S[6 * r + c] = s;
             }
+        for (int ch = N - 1; ch > i; --ch) {
+            if ((parent ? parent[ch] : ch - 1) != i) continue;
+            const double *G = Lo + 36 * ch;
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c <= r; ++c) {
+                    double s = S[6 * r + c];
+                    for (int k = 0; k < 6; ++k) s = fma(-G[6 * r + k], G[6 * c + k], s);
+                    S[6 * r + c] = s;
+                }
+        }
         memset(L, 0, sizeof L);
         for (int j = 0; j < 6; ++j) {
             double s = S[6 * j + j];
@@ -710,32 +724,30 @@ static int factor_solve(int N, const double *Hd, const double *Ho, const double 
                 L[6 * r + j] = t * inv;
             }
         }
-        /* z_i = L_i^-1 (b_i - G_i z_{i+1}) */
-        memcpy(zn, z, sizeof zn);
         for (int r = 0; r < 6; ++r) {
             double s = b[6 * i + r];
-            if (G)
-                for (int k = 0; k < 6; ++k) s = fma(-G[6 * r + k], zn[k], s);
+            for (int ch = N - 1; ch > i; --ch) {
+                if ((parent ? parent[ch] : ch - 1) != i) continue;
+                const double *G = Lo + 36 * ch, *zc = zs + 6 * ch;
+                for (int k = 0; k < 6; ++k) s = fma(-G[6 * r + k], zc[k], s);
+            }
             for (int k = 0; k < r; ++k) s = fma(-L[6 * r + k], z[k], s);
             z[r] = s * L[6 * r + r];
         }
-        /* c_i = L_i^-T z_i */
         double *c = y + 6 * i;
         for (int r = 5; r >= 0; --r) {
             double s = z[r];
             for (int k = r + 1; k < 6; ++k) s = fma(-L[6 * k + r], c[k], s);
             c[r] = s * L[6 * r + r];
         }
-        if (i > 0) {
-            /* G_{i-1} = H_{i-1,i} L_i^-T ; H_{i-1,i} = Ho[i-1] as stored (rows of i-1, cols of i) */
-            double *X = Lo + 36 * (i - 1);
+        if ((parent ? parent[i] : i - 1) >= 0) {
+            double *X = Lo + 36 * i;
             for (int r = 0; r < 6; ++r)
                 for (int cc = 0; cc < 6; ++cc) {
-                    double s = Ho[36 * (i - 1) + 6 * r + cc];
+                    double s = Ho[36 * i + 6 * r + cc];
                     for (int k = 0; k < cc; ++k) s = fma(-X[6 * r + k], L[6 * cc + k], s);
                     X[6 * r + cc] = s * L[6 * cc + cc];
                 }
-            /* M_i = L_i^-T G_{i-1}^T */
             double *M = Ld + 36 * i;
             for (int j = 0; j < 6; ++j)
                 for (int r = 5; r >= 0; --r) {
@@ -745,13 +757,13 @@ static int factor_solve(int N, const double *Hd, const double *Ho, const double 
                 }
         }
     }
-    /* substitution, ascending: x_i = c_i - M_i x_{i-1} */
     for (int i = 0; i < N; ++i) {
         const double *M = Ld + 36 * i;
+        const int p = parent ? parent[i] : i - 1;
         for (int r = 0; r < 6; ++r) {
             double s = y[6 * i + r];
-            if (i > 0)
-                for (int j = 0; j < 6; ++j) s = fma(-M[6 * r + j], x[6 * (i - 1) + j], s);
+            if (p >= 0)
+                for (int j = 0; j < 6; ++j) s = fma(-M[6 * r + j], x[6 * p + j], s);
             x[6 * i + r] = s;
         }
     }
@@ -761,32 +773,35 @@ static int factor_solve(int N, const double *Hd, const double *Ho, const double 
 /* ------------------------------------------------------------------------------------------ */
 /* window set-up / tear-down                                                                    */
 /* ------------------------------------------------------------------------------------------ */
-static int count_slots(const uwbgo_topology *T, int32_t *slot, int *Er, int *Ep, int *Es)
+/* per-kind data slots, argument checks, and the parent of every pose: the one older neighbour it
+ * shares a pose-pose edge with (-1: none).  Two different older neighbours = not a forest. */
+static int count_slots(const uwbgo_topology *T, int32_t *slot, int32_t *parent, int *Er, int *Ep,
+                       int *Es)
 {
     int er = 0, ep = 0, es = 0;
+    for (int i = 0; i < T->n_poses; ++i) parent[i] = -1;
     for (int e = 0; e < T->n_edges; ++e) {
-        int a = T->edge_a[e], b = T->edge_b[e];
+        int a = T->edge_a[e], b = T->edge_b[e], kind = T->edge_kind[e];
         if (a < 0 || a >= T->n_poses) return UWBGO_E_INVALID;
-        switch (T->edge_kind[e]) {
+        switch (kind) {
         case UWBGO_EDGE_RANGE_ANCHOR:
             if (b < 0 || b >= T->n_anchors) return UWBGO_E_INVALID;
-            slot[e] = er++;
-            break;
-        case UWBGO_EDGE_RANGE_POSE:
-            if (b != a + 1 || b >= T->n_poses) return UWBGO_E_TOPOLOGY;
             slot[e] = er++;
             break;
         case UWBGO_EDGE_PRIOR:
             slot[e] = ep++;
             break;
+        case UWBGO_EDGE_RANGE_POSE:
         case UWBGO_EDGE_SE3:
-            if (b != a + 1 || b >= T->n_poses) return UWBGO_E_TOPOLOGY;
-            slot[e] = es++;
+            if (b <= a || b >= T->n_poses) return UWBGO_E_TOPOLOGY;
+            if (parent[b] >= 0 && parent[b] != a) return UWBGO_E_TOPOLOGY;
+            parent[b] = a;
+            slot[e] = kind == UWBGO_EDGE_SE3 ? es++ : er++;
             break;
         default:
             return UWBGO_E_INVALID;
         }
-        if (T->edge_kind[e] <= UWBGO_EDGE_RANGE_POSE && T->edge_ant &&
+        if (kind <= UWBGO_EDGE_RANGE_POSE && T->edge_ant &&
             (T->edge_ant[e] < 0 || T->edge_ant[e] > T->n_antennas))
             return UWBGO_E_INVALID;
     }
@@ -797,7 +812,7 @@ static int count_slots(const uwbgo_topology *T, int32_t *slot, int *Er, int *Ep,
 }
 
 static int window_alloc(window_t *W, const uwbgo_topology *T, const uwbgo_config *cfg,
-                        const int32_t *slot, int Er, int Ep, int Es)
+                        const int32_t *slot, const int32_t *parent, int Er, int Ep, int Es)
 {
     memset(W, 0, sizeof *W);
     W->topo = T;
@@ -809,6 +824,7 @@ static int window_alloc(window_t *W, const uwbgo_topology *T, const uwbgo_config
     W->Ep = Ep;
     W->Es = Es;
     W->slot = slot;
+    W->parent = parent;
     size_t N = (size_t)W->N, E = (size_t)W->E;
     W->X = (pose_t *)malloc(N * sizeof(pose_t));
     W->Xbak = (pose_t *)malloc(N * sizeof(pose_t));
@@ -821,8 +837,9 @@ static int window_alloc(window_t *W, const uwbgo_topology *T, const uwbgo_config
     W->Ld = (double *)malloc(N * 36 * sizeof(double));
     W->Lo = (double *)malloc(N * 36 * sizeof(double));
     W->y = (double *)malloc(N * 6 * sizeof(double));
+    W->zs = (double *)malloc(N * 6 * sizeof(double));
     return (W->X && W->Xbak && W->cnt && W->err && W->Hd && W->Ho && W->b && W->x && W->Ld &&
-            W->Lo && W->y)
+            W->Lo && W->y && W->zs)
                ? 0
                : UWBGO_E_NOMEM;
 }
@@ -830,7 +847,7 @@ static int window_alloc(window_t *W, const uwbgo_topology *T, const uwbgo_config
 static void window_free(window_t *W)
 {
     free(W->X); free(W->Xbak); free(W->cnt); free(W->err); free(W->Hd); free(W->Ho);
-    free(W->b); free(W->x); free(W->Ld); free(W->Lo); free(W->y);
+    free(W->b); free(W->x); free(W->Ld); free(W->Lo); free(W->y); free(W->zs);
 }
 
 static void window_load(window_t *W, const uwbgo_batch *in, int64_t w)
@@ -892,7 +909,7 @@ static void solve_window(window_t *W, double *chi2_out, int32_t *status_out, dou
         int q = 0;
         do {
             memcpy(W->Xbak, W->X, (size_t)N * sizeof(pose_t)); /* push */
-            int ok = factor_solve(N, W->Hd, W->Ho, W->b, lambda, W->Ld, W->Lo, W->y, W->x);
+            int ok = factor_solve(N, W->parent, W->Hd, W->Ho, W->b, lambda, W->Ld, W->Lo, W->y, W->zs, W->x);
             if (!ok) {
                 memset(W->x, 0, (size_t)N * 6 * sizeof(double));
                 flags |= UWBGO_FLAG_CHOL_FAIL;
@@ -964,7 +981,7 @@ typedef struct {
     const uwbgo_config *cfg;
     uwbgo_result *out;
     double *H_diag, *H_off, *b, *chi2, *trace;
-    const int32_t *slot;
+    const int32_t *slot, *parent;
     int Er, Ep, Es, tid, nthreads, rc;
 } job_t;
 
@@ -972,7 +989,7 @@ static void *worker(void *arg)
 {
     job_t *J = (job_t *)arg;
     window_t W;
-    J->rc = window_alloc(&W, J->topo, J->cfg, J->slot, J->Er, J->Ep, J->Es);
+    J->rc = window_alloc(&W, J->topo, J->cfg, J->slot, J->parent, J->Er, J->Ep, J->Es);
     if (J->rc) {
         window_free(&W);
         return NULL;
@@ -1001,7 +1018,7 @@ static void *worker(void *arg)
             build_system(&W);
             memcpy(J->H_diag + (size_t)w * N * 36, W.Hd, (size_t)N * 36 * sizeof(double));
             if (N > 1)
-                memcpy(J->H_off + (size_t)w * (N - 1) * 36, W.Ho, (size_t)(N - 1) * 36 * sizeof(double));
+                memcpy(J->H_off + (size_t)w * (N - 1) * 36, W.Ho + 36, (size_t)(N - 1) * 36 * sizeof(double));
             memcpy(J->b + (size_t)w * N * 6, W.b, (size_t)N * 6 * sizeof(double));
             if (J->chi2) {
                 J->chi2[2 * w] = p;
@@ -1017,14 +1034,16 @@ static int run_jobs(job_t *proto, int n_threads)
 {
     const uwbgo_topology *T = proto->topo;
     if (!T || !proto->in || !proto->cfg || T->n_poses < 1 || T->n_edges < 0) return UWBGO_E_INVALID;
-    int32_t *slot = (int32_t *)malloc(((size_t)T->n_edges + 1) * sizeof(int32_t));
+    int32_t *slot = (int32_t *)malloc(((size_t)T->n_edges + 1 + (size_t)T->n_poses) * sizeof(int32_t));
     if (!slot) return UWBGO_E_NOMEM;
-    int rc = count_slots(T, slot, &proto->Er, &proto->Ep, &proto->Es);
+    int32_t *parent = slot + T->n_edges + 1;
+    int rc = count_slots(T, slot, parent, &proto->Er, &proto->Ep, &proto->Es);
     if (rc) {
         free(slot);
         return rc;
     }
     proto->slot = slot;
+    proto->parent = parent;
     if (n_threads < 1) n_threads = 1;
     if ((int64_t)n_threads > proto->in->n_windows) n_threads = (int)proto->in->n_windows;
     if (n_threads < 1) n_threads = 1;
@@ -1087,22 +1106,25 @@ int uwbgo_oracle_factor_solve_batch(int32_t n_poses, int64_t n_windows, const do
                                     const double *H_off, const double *b, const double *lambda,
                                     double *x, int32_t *ok)
 {
+    /* chains only: H_off[w][j] = block (j, j+1) = Ho[j+1] of the window */
     size_t N = (size_t)n_poses;
     double *Ld = (double *)malloc(N * 36 * sizeof(double));
     double *Lo = (double *)malloc(N * 36 * sizeof(double));
+    double *Ho = (double *)calloc(N * 36, sizeof(double));
     double *y = (double *)malloc(N * 6 * sizeof(double));
-    if (!Ld || !Lo || !y) {
-        free(Ld); free(Lo); free(y);
+    double *zs = (double *)malloc(N * 6 * sizeof(double));
+    if (!Ld || !Lo || !Ho || !y || !zs) {
+        free(Ld); free(Lo); free(Ho); free(y); free(zs);
         return UWBGO_E_NOMEM;
     }
     for (int64_t w = 0; w < n_windows; ++w) {
-        int good = factor_solve(n_poses, H_diag + (size_t)w * N * 36,
-                                H_off ? H_off + (size_t)w * (N - 1) * 36 : NULL,
-                                b + (size_t)w * N * 6, lambda[w], Ld, Lo, y, x + (size_t)w * N * 6);
+        if (N > 1) memcpy(Ho + 36, H_off + (size_t)w * (N - 1) * 36, (N - 1) * 36 * sizeof(double));
+        int good = factor_solve(n_poses, NULL, H_diag + (size_t)w * N * 36, Ho, b + (size_t)w * N * 6,
+                                lambda[w], Ld, Lo, y, zs, x + (size_t)w * N * 6);
         if (!good) memset(x + (size_t)w * N * 6, 0, N * 6 * sizeof(double));
         if (ok) ok[w] = good;
     }
-    free(Ld); free(Lo); free(y);
+    free(Ld); free(Lo); free(Ho); free(y); free(zs);
     return 0;
 }
 

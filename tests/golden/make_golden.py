@@ -13,7 +13,8 @@ from oracle import oracle  # noqa: E402
 
 cases = {"uwb_only": (synthetic.uwb_only, dict(W=8, N=10, A=4, seed=101), 10),
          "uwb_imu_lidar": (synthetic.uwb_imu_lidar, dict(W=6, N=8, A=4, seed=102), 20),
-         "uwb_twist": (synthetic.uwb_twist, dict(W=6, N=7, A=4, seed=103), 12)}
+         "uwb_twist": (synthetic.uwb_twist, dict(W=6, N=7, A=4, seed=103), 12),
+         "uwb_pose": (synthetic.uwb_pose, dict(W=6, N=11, A=4, keyframe_len=4, seed=104), 10)}
 out = {}
 for name, (make, kw, iters) in cases.items():
     topo, batch, _ = make(**kw)

@@ -139,15 +139,28 @@ def test_outlier_gate_and_chi2_gate():
     assert len(fleet.published(0)[0]) == 0
 
 
-def test_non_chain_pose_edges_are_refused():
-    """addPoseEdge ties every new pose to a key vertex (localization.cpp:258-267): not a chain"""
+def test_pose_edges_to_a_key_vertex():
+    """addPoseEdge ties every new pose of a keyframe to one key vertex (localization.cpp:258-267): a
+    star, not a chain; solved by the forest elimination.  cfg/uwb_pose.yaml style: pose + range."""
     msgs = load_messages(MSGS)
-    fleet = Fleet(solve_fn=oracle_backend())
-    p = node_params(msgs, LocParams(**{**UWB_ONLY, "publish_range": False, "publish_pose": True}))
+    rec = []
+    fleet = Fleet(solve_fn=oracle_backend(rec))
+    p = node_params(msgs, LocParams(**{**UWB_ONLY, "trajectory_length": 8, "publish_range": False,
+                                      "publish_pose": True, "maximum_iteration": 10}))
     fleet.add(p)
-    cov = np.eye(6).reshape(-1) * 0.01
-    for k in range(4):
-        fleet.add_pose(0, k, 100 + k, 0, "kf0", [0.1 * k, 0, 1.0], [0, 0, 0, 1], cov)
+    cov = (np.eye(6) * 1e-4).reshape(-1)
+    rng = np.random.default_rng(0)
+    n = 0
+    for k in range(20):
+        frame = f"kf{k // 5}"                       # keyframe changes every 5 poses
+        rel = np.array([0.05 * (k % 5 + 1), 0.0, 0.0]) + rng.normal(0, 0.003, 3)
+        fleet.add_pose(0, k, 100 + k, 0, frame, rel, [0, 0, 0, 1], cov)
         fleet.flush()
+        i = k % len(msgs["uwb_distance"])
+        fleet.add_range(0, k, 100 + k, 5000, "other", 200, int(msgs["uwb_responder"][i]),
+                        float(msgs["uwb_distance"][i]), 0.5, 0)   # merged-covariance branch: no new vertex
+        n += 1
     st = fleet.stats(0)
-    assert st["errors"] >= 1 and "non-consecutive" in fleet.last_error(0)
+    assert st["errors"] == 0 and st["solves"] == 20, fleet.last_error(0)
+    assert rec[-1][0] == 8 and rec[-1][4]           # full window of 8 poses, rotations present
+    assert len(fleet.published(0)[0]) > 0

@@ -74,6 +74,30 @@ def test_uwb_twist(solver):
     assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
 
 
+@pytest.mark.parametrize("N,K", [(24, 4), (9, 8), (40, 7), (5, 1)])
+def test_uwb_pose_key_vertex_stars(solver, N, K):
+    """pose edges to a key vertex (localization.cpp:258-267): forest windows, no fill-in"""
+    topo, batch, _ = synthetic.uwb_pose(96, N, 8, keyframe_len=K, seed=N)
+    cfg = Config(max_iterations=10)
+    got = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 0
+    assert_parity(got, oracle.solve(topo, batch, cfg))
+    Hd, Ho, b, chi = solver.linearize(topo, batch, cfg)
+    rHd, rHo, rb, rchi = oracle.linearize(topo, batch, cfg)
+    assert np.array_equal(Hd, rHd) and np.array_equal(Ho, rHo) and np.array_equal(b, rb)
+
+
+def test_two_older_neighbours_are_refused(solver):
+    from localization_b200 import UwbgoError
+    topo = Topology.from_edges(4, 1, 0, [(EDGE_RANGE_ANCHOR, 0, 0, 0, 1), (EDGE_SE3, 0, 1, 0, 1), (EDGE_SE3, 1, 2, 0, 1),
+                                         (EDGE_SE3, 0, 3, 0, 1), (EDGE_SE3, 2, 3, 0, 1)])
+    b = Batch(pose_t=np.zeros((1, 4, 3)), anchors=np.ones((1, 1, 3)), range_d=np.ones((1, 1)), range_info=np.ones((1, 1)),
+              se3_Z=np.tile(np.r_[np.eye(3).ravel(), 0, 0, 0], (1, 4, 1)), se3_info=np.tile(np.eye(6), (1, 4, 1, 1)))
+    with pytest.raises(UwbgoError) as ei:
+        solver.solve(topo, b, Config(max_iterations=1))
+    assert ei.value.code == -2
+
+
 def test_oplus_counter_carry_and_reorthogonalisation(solver):
     """VertexSE3::_numOplusCalls carried in close to orthogonalizeAfter: the re-orthogonalisation
     trips inside numeric Jacobians and inside trial updates"""
@@ -204,6 +228,23 @@ def test_multiple_range_edges_per_pose_and_unordered_insertion(solver):
     got = solver.solve(topo3, b3, cfg)
     assert solver.last_path == 0
     assert_parity(got, oracle.solve(topo3, b3, cfg))
+
+
+def test_range_edges_between_non_adjacent_poses(solver):
+    """pose-pose range edges to an older, non-adjacent pose (forest): general path"""
+    rng = np.random.default_rng(12)
+    N, A, W = 7, 3, 40
+    edges = [(EDGE_RANGE_ANCHOR, k, k % A, 0, 1) for k in range(N)]
+    edges += [(EDGE_RANGE_POSE, 0, 1, 0, 1), (EDGE_RANGE_POSE, 0, 2, 0, 1), (EDGE_RANGE_POSE, 2, 3, 0, 0),
+              (EDGE_RANGE_POSE, 2, 4, 0, 1), (EDGE_RANGE_POSE, 2, 5, 0, 1), (EDGE_RANGE_POSE, 5, 6, 0, 1)]
+    topo = Topology.from_edges(N, A, 0, edges)
+    er = topo.counts()[0]
+    batch = Batch(pose_t=rng.normal(0, 1, (W, N, 3)), anchors=rng.normal(0, 3, (W, A, 3)),
+                  range_d=np.abs(rng.normal(2, 1, (W, er))), range_info=rng.uniform(10, 400, (W, er)))
+    cfg = Config(max_iterations=6)
+    got = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 0
+    assert_parity(got, oracle.solve(topo, batch, cfg))
 
 
 def test_mixed_edge_kinds_general(solver):

@@ -141,3 +141,33 @@ def test_two_rank_sharding_gloo(tmp_path):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "SHARD_OK" in out.stdout
+
+
+def test_g2o_text_round_trip(tmp_path):
+    """EDGE_RANGE / EDGE_RANGE_OFFSET / VERTEX_SE3:QUAT / EDGE_SE3:QUAT / EDGE_SE3_PRIOR interchange:
+    a window written as g2o text and read back solves to the same result (UWB-only: same bits)"""
+    from localization_b200.tools import g2o_text
+    from oracle import oracle
+    topo, batch, _ = synthetic.uwb_only(3, 8, 4, seed=31)
+    f = str(tmp_path / "w.g2o")
+    g2o_text.write_window(f, topo, batch, w=1)
+    text = open(f).read()
+    assert "EDGE_RANGE 200 100 " in text and "VERTEX_SE3:QUAT 2300 " in text and "FIX 103" in text
+    t2, b2 = g2o_text.read_window(f)
+    assert np.array_equal(t2.edge_kind, topo.edge_kind) and np.array_equal(t2.edge_a, topo.edge_a)
+    assert np.array_equal(t2.edge_b, topo.edge_b) and np.array_equal(t2.edge_robust, topo.edge_robust)
+    cfg = Config(max_iterations=5)
+    a, b = oracle.solve(topo, batch.slice(1, 2), cfg), oracle.solve(t2, b2, cfg)
+    assert np.array_equal(a.pose_t, b.pose_t) and np.array_equal(a.chi2, b.chi2)   # repr() floats round-trip
+    for make, kw in ((synthetic.uwb_imu_lidar, dict(W=2, N=6, A=4, seed=32)), (synthetic.uwb_twist, dict(W=2, N=6, A=4, seed=33)),
+                     (synthetic.uwb_pose, dict(W=2, N=9, A=4, seed=34))):
+        topo, batch, _ = make(**kw)
+        g2o_text.write_window(f, topo, batch, w=0)
+        assert "EDGE_RANGE_OFFSET" in open(f).read()
+        t2, b2 = g2o_text.read_window(f)
+        assert t2.counts() == topo.counts() and np.array_equal(t2.edge_ant, topo.edge_ant)
+        a, b = oracle.solve(topo, batch.slice(0, 1), cfg), oracle.solve(t2, b2, cfg)
+        # rotations go through quaternions: a 1e-16 perturbation of the inputs, amplified by the numeric
+        # Jacobians and the unconverged LM to ~1e-8 m (SURVEY Appendix B) -- still inside the 1e-6 m bar
+        assert np.abs(a.pose_t - b.pose_t).max() < 1e-6
+        assert np.allclose(a.chi2[:, :2], b.chi2[:, :2], rtol=1e-4)

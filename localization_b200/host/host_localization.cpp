@@ -1,4 +1,5 @@
 #include "host_localization.h"
+#include "edge_types.h"
 
 #include <cmath>
 #include <cstdio>
@@ -330,14 +331,13 @@ void Localization::publish()
 /* localization.cpp:608-627 */
 Edge Localization::make_range_edge(VertexSE3 *v1, VertexSE3 *v2, double distance, double covariance)
 {
-    Edge e;
-    e.kind = EdgeKind::Range;
-    e.from = v1;
-    e.to = v2;
-    e.range = distance;
-    e.rangeInformation = 1.0 / covariance; /* 1x1 covariance_matrix.inverse() */
-    e.cauchy = true;
-    return e;
+    EdgeSE3Range edge;
+    edge.vertices()[0] = v1;
+    edge.vertices()[1] = v2;
+    edge.setMeasurement(distance);
+    edge.setInformation(1.0 / covariance); /* 1x1 covariance_matrix.inverse() */
+    edge.setRobustKernel(new RobustKernelCauchy());
+    return edge.asEdge(0);
 }
 
 /* localization.cpp:560-605 */

@@ -171,3 +171,11 @@ def test_g2o_text_round_trip(tmp_path):
         # Jacobians and the unconverged LM to ~1e-8 m -- still inside the 1e-6 m bar
         assert np.abs(a.pose_t - b.pose_t).max() < 1e-6
         assert np.allclose(a.chi2[:, :2], b.chi2[:, :2], rtol=1e-4)
+
+
+def test_cpp_type_api():
+    """EdgeSE3Range / EdgeSE3RangeOffset / Robot drop-ins (localization_b200/host/test_types.cpp)"""
+    host_dir = os.path.join(ROOT, "localization_b200", "host")
+    subprocess.check_call(["make", "-s", "-C", host_dir, "test_types"])
+    out = subprocess.run([os.path.join(host_dir, "test_types")], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "host type API ok" in out.stdout, out.stdout + out.stderr

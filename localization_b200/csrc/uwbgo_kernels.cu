@@ -45,6 +45,13 @@ namespace uwbgo {
 #define UWBGO_L2PF_DIST 2 /* > 0: prefetch.global.L2 this many records ahead of the sweeps */
 #endif
 
+#ifndef UWBGO_CHAIN_UNROLL
+#define UWBGO_CHAIN_UNROLL 1 /* unroll factor of the CHAIN sweeps' pose loops */
+#endif
+#define UWBGO_PRAGMA_(x) _Pragma(#x)
+#define UWBGO_PRAGMA(x) UWBGO_PRAGMA_(x)
+#define UWBGO_CHAIN_UNROLL_PRAGMA UWBGO_PRAGMA(unroll UWBGO_CHAIN_UNROLL)
+
 UWBGO_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int ROWS>
 UWBGO_DI void prefetch_rows_l2(const double *p)
@@ -781,6 +788,7 @@ UWBGO_DI bool chain_factor(const FastEnv &E, const double *__restrict__ T, doubl
     chain_build<true>(E, cx, cy, cz, in, carry, hc);
     cx = in.px; cy = in.py; cz = in.pz;
     in = nx;
+    UWBGO_CHAIN_UNROLL_PRAGMA
     for (int i = N - 1; i >= 2; --i) {
         /* inputs of pose i-2 go in flight; pose i-1 is rebuilt while pose i is eliminated */
         if (i > 2) chain_load<true>(E, T, i - 2, nx);
@@ -852,6 +860,7 @@ UWBGO_DI void chain_solve_chi(const FastEnv &E, bool ok, double lambda, const do
     double vx = 0.0, vy = 0.0, vz = 0.0; /* new estimate of pose i-1 */
     ChainSub cur, nxt;
     chain_sub_load(E, Tc, 0, cur);
+    UWBGO_CHAIN_UNROLL_PRAGMA
     for (int i = 0; i < N; ++i) {
         if (i + 1 < N) chain_sub_load(E, Tc, i + 1, nxt);
         if (UWBGO_L2PF_DIST > 0 && i + 1 + UWBGO_L2PF_DIST < N) {

@@ -271,14 +271,15 @@ def main():
         hbm, how = peaks()
         k_best = float(np.median([k for k in k_ms if k and k > 0])) if k_ms else None
         achieved = ALGO_BYTES_SOLVE * W / (k_best * 1e-3) / 1e9 if k_best else None
-        traffic, traffic_src, fp64_flop = None, None, None
+        traffic, traffic_src, fp64_flop, fp64_pipe = None, None, None, None
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp) and W == WINDOWS_PER_GPU:
             with open(tp) as f:
-                tj = json.load(f)["lm_chain_kernel"]
+                tj = json.load(f)["lm_chain_ws_kernel"]
             traffic, traffic_src = tj["dram_bytes_per_launch"] / 1e9, tj["source"]
             fp64_flop = tj.get("fp64_flop_per_launch")
-        roof = {"bound": "hbm", "kernel": "lm_chain_kernel (fused LM: linearise + assemble + block Cholesky + damping loop)",
+            fp64_pipe = tj.get("fp64_pipe_active_pct")
+        roof = {"bound": "hbm", "kernel": "lm_chain_ws_kernel (fused LM: linearise + assemble + block Cholesky + damping loop)",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if achieved else None,
                 "traffic": traffic, "traffic_unit": "GB per launch (dram read+write, ncu)", "traffic_source": traffic_src,
                 "peak_source": how, "kernel_ms": k_best,
@@ -293,6 +294,7 @@ def main():
             roof["fp64_achieved_tflops"] = fp64_flop / (k_best * 1e-3) / 1e12
             roof["fp64_frac"] = roof["fp64_achieved_tflops"] / (fp64 / 1e12)
             roof["fp64_flop_per_window"] = fp64_flop / W
+            roof["fp64_pipe_active_pct_ncu"] = fp64_pipe
         stages = None
         if args.stages:
             stages = time_stages(solver, topo, batch, cfg, dev, hbm)

@@ -1777,6 +1777,363 @@ lm_chain_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevC
     lm_fast_body<2>(tp, cfg, ws, anchors_in_smem, smem);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* CHAIN path, warp-specialised: one CTA = one tile of 32 windows = two warps.                   */
+/*   warp 0 (P, "edge warp")   linearises the trajectory edge (i-1, i) of every pose -- both      */
+/*                             numeric Jacobians, weights -- and, in the substitution phase,     */
+/*                             evaluates all residuals / chi2 at the new estimates;              */
+/*   warp 1 (C, "chain warp")  linearises the anchor edge, assembles the H record, runs the      */
+/*                             elimination chain and the substitution, owns the LM state.        */
+/* The two halves of a pose's work are about the same number of instructions, so the dependency  */
+/* chains of twice as many warps are in flight per scheduler for the same register budget per    */
+/* window.  The warps move in lockstep, one named barrier per pose and phase, handing 8 (edge     */
+/* terms) resp. 3 (new estimate) doubles per window through shared memory.  Per-window arithmetic */
+/* and its order are those of the single-warp CHAIN path: same bits.                             */
+/* ------------------------------------------------------------------------------------------ */
+struct WsShared {
+    double traj[2][8][TILE]; /* P -> C: A(3), B(3), Ow, omega_r of edge (i-1, i), double buffered */
+    double tnew[2][3][TILE]; /* C -> P: new estimate of pose i                                    */
+    double chi[2][TILE];     /* P -> C: plain and robust chi2 of the trial                        */
+    int cur[TILE];           /* C -> P: which pose buffer is current                              */
+    int act[TILE];           /* C -> P: window still being optimised                              */
+    double stash[STASH_PER_THREAD][TILE];
+};
+
+UWBGO_DI void ws_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+#ifndef UWBGO_WS_MINB
+#define UWBGO_WS_MINB 8
+#endif
+__global__ void __launch_bounds__(64, UWBGO_WS_MINB)
+lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+                   const __grid_constant__ DevWs ws)
+{
+    __shared__ WsShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t wreal = (int64_t)blockIdx.x * TILE + lane;
+    const bool valid = wreal < ws.W;
+    const int64_t w = wreal; /* tail lanes own zero-filled pad columns of the tile layout: harmless garbage */
+    const int N = tp.N;
+    FastEnv E;
+    E.tp = &tp;
+    E.p = thread_ptrs<HR_FAST, LR_FAST>(tp, ws, w);
+    E.ck.init(cfg.kdelta);
+    E.delta = cfg.jdelta;
+    E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    E.bs = TILE;
+    E.stash = &sh.stash[0][lane];
+    E.anch = E.p.anch;
+    E.anch_stride = TILE;
+
+    /* LM state, chain warp only */
+    double lambda = 0.0, ni = 2.0, stale = 0.0, plainCur = 0.0, currentChi = 0.0, rho = 0.0;
+    int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0, q = 0, it = 0;
+    bool done = !valid || cfg.max_iterations <= 0;
+    if (warp == 1) {
+        fast_chi_pass(E, E.p.T0, plainCur, currentChi);
+        stale = plainCur;
+        const double maxdiag = fast_linearize<false>(E, E.p.T0);
+        if (cfg.max_iterations > 0) lambda = cfg.tau * maxdiag;
+        sh.cur[lane] = 0;
+        sh.act[lane] = done ? 0 : 1;
+    }
+    ws_barrier();
+    for (;;) {
+        const bool act = sh.act[lane] != 0;
+        const int c = sh.cur[lane];
+        if (__ballot_sync(0xffffffffu, act) == 0u) break;
+        ws_barrier(); /* everybody has read act/cur before the chain warp may overwrite them */
+        const double *Tc = E.p.T(c);
+        double *Tn = E.p.T(c ^ 1);
+        if (warp == 0) {
+            /* ---------------- edge warp, factor phase: edges (i-1, i), i = N-1 .. 1 ---------------- */
+            {
+                double cx = 0.0, cy = 0.0, cz = 0.0, px = 0.0, py = 0.0, pz = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+                double dt = 0.0, it_ = 0.0, ndt = 0.0, nit = 0.0;
+                int rob = 0, nrob = 0;
+                {
+                    const double *tl = Tc + (size_t)(N - 1) * 3 * TILE;
+                    cx = ROW(tl, 0); cy = ROW(tl, 1); cz = ROW(tl, 2);
+                    if (N > 1) {
+                        const double *tq = tl - (size_t)3 * TILE;
+                        px = ROW(tq, 0); py = ROW(tq, 1); pz = ROW(tq, 2);
+                        dt = ROW(E.p.rd, 2 * (N - 1));
+                        it_ = ROW(E.p.ri, 2 * (N - 1));
+                        rob = __ldg(&tp.chain[N - 1].robust);
+                    }
+                }
+                for (int k = 0; k <= N; ++k) {
+                    const int i = N - 1 - k; /* edge (i-1, i) */
+                    if (i >= 1) {
+                        if (i >= 2) { /* inputs of the next edge go in flight */
+                            const double *tf = Tc + (size_t)(i - 2) * 3 * TILE;
+                            fx = ROW(tf, 0); fy = ROW(tf, 1); fz = ROW(tf, 2);
+                            ndt = ROW(E.p.rd, 2 * (i - 1));
+                            nit = ROW(E.p.ri, 2 * (i - 1));
+                            nrob = __ldg(&tp.chain[i - 1].robust);
+                        }
+                        if (UWBGO_L2PF_DIST > 0 && i >= 2 + 2 * UWBGO_L2PF_DIST) {
+                            const int j = i - 2 - 2 * UWBGO_L2PF_DIST;
+                            prefetch_rows_l2<3>(Tc + (size_t)j * 3 * TILE);
+                            prefetch_l2(E.p.rd + (size_t)(2 * j) * TILE);
+                            prefetch_l2(E.p.ri + (size_t)(2 * j) * TILE);
+                        }
+                        double A[3], B[3], Ow, omega_r;
+                        const double err = dt - dist3(px, py, pz, cx, cy, cz);
+                        fast_jac_v0(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, A);
+                        fast_jac_v1(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, B);
+                        chain_weights(E, err, it_, (rob & 2) != 0, Ow, omega_r);
+                        double(*o)[TILE] = sh.traj[k & 1];
+                        o[0][lane] = A[0]; o[1][lane] = A[1]; o[2][lane] = A[2];
+                        o[3][lane] = B[0]; o[4][lane] = B[1]; o[5][lane] = B[2];
+                        o[6][lane] = Ow;   o[7][lane] = omega_r;
+                        cx = px; cy = py; cz = pz;
+                        px = fx; py = fy; pz = fz;
+                        dt = ndt; it_ = nit; rob = nrob;
+                    }
+                    ws_barrier();
+                }
+            }
+            /* ---------------- edge warp, substitution phase: chi2 at the new estimates ---------------- */
+            {
+                double p = 0.0, r = 0.0, vx = 0.0, vy = 0.0, vz = 0.0;
+                double da = ROW(E.p.rd, 0), ia = ROW(E.p.ri, 0), dt = 0.0, it_ = 0.0;
+                int2 tb = __ldg(reinterpret_cast<const int2 *>(tp.chain));
+                double qx = ANCH(E, tb.x * 3), qy = ANCH(E, tb.x * 3 + 1), qz = ANCH(E, tb.x * 3 + 2);
+                for (int k = 0; k <= N; ++k) {
+                    if (k >= 1) {
+                        const int i = k - 1; /* pose i was produced in the previous step */
+                        double nda = 0.0, nia = 0.0, ndt = 0.0, nit = 0.0, nqx = 0.0, nqy = 0.0, nqz = 0.0;
+                        int2 ntb = tb;
+                        if (i + 1 < N) {
+                            ntb = __ldg(reinterpret_cast<const int2 *>(tp.chain + i + 1));
+                            nda = ROW(E.p.rd, 2 * i + 1);
+                            nia = ROW(E.p.ri, 2 * i + 1);
+                            ndt = ROW(E.p.rd, 2 * i + 2);
+                            nit = ROW(E.p.ri, 2 * i + 2);
+                            nqx = ANCH(E, ntb.x * 3); nqy = ANCH(E, ntb.x * 3 + 1); nqz = ANCH(E, ntb.x * 3 + 2);
+                        }
+                        if (UWBGO_L2PF_DIST > 0 && i + 1 + UWBGO_L2PF_DIST < N) {
+                            const int j = i + 1 + UWBGO_L2PF_DIST;
+                            prefetch_l2(E.p.rd + (size_t)(2 * j) * TILE);
+                            prefetch_l2(E.p.ri + (size_t)(2 * j) * TILE);
+                            prefetch_l2(E.p.rd + (size_t)(2 * j - 1) * TILE);
+                            prefetch_l2(E.p.ri + (size_t)(2 * j - 1) * TILE);
+                        }
+                        const double(*tn)[TILE] = sh.tnew[i & 1];
+                        const double cx = tn[0][lane], cy = tn[1][lane], cz = tn[2][lane];
+                        {
+                            const double err = da - dist3(cx, cy, cz, qx, qy, qz);
+                            const double chi = err * (ia * err);
+                            p = p + chi;
+                            r = r + ((tb.y & 1) ? E.ck.rho0(chi) : chi);
+                        }
+                        if (i > 0) {
+                            const double err = dt - dist3(vx, vy, vz, cx, cy, cz);
+                            const double chi = err * (it_ * err);
+                            p = p + chi;
+                            r = r + ((tb.y & 2) ? E.ck.rho0(chi) : chi);
+                        }
+                        vx = cx; vy = cy; vz = cz;
+                        da = nda; ia = nia; dt = ndt; it_ = nit; qx = nqx; qy = nqy; qz = nqz; tb = ntb;
+                    }
+                    ws_barrier();
+                }
+                sh.chi[0][lane] = p;
+                sh.chi[1][lane] = r;
+            }
+            ws_barrier(); /* chi2 published */
+            ws_barrier(); /* LM state published */
+        } else {
+            /* ---------------- chain warp, factor phase: poses i = N-1 .. 0 ---------------- */
+            bool ok = true;
+            {
+                double G[9], zn[3], carry[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < 9; ++k) G[k] = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) zn[k] = 0.0;
+                /* inputs of the anchor edge of pose i, one pose ahead */
+                double cx, cy, cz, da, ia, qx, qy, qz;
+                int rob;
+                {
+                    const int i = N - 1;
+                    const double *tl = Tc + (size_t)i * 3 * TILE;
+                    cx = ROW(tl, 0); cy = ROW(tl, 1); cz = ROW(tl, 2);
+                    const int2 tb = __ldg(reinterpret_cast<const int2 *>(tp.chain + i));
+                    const int sa = i == 0 ? 0 : 2 * i - 1;
+                    da = ROW(E.p.rd, sa); ia = ROW(E.p.ri, sa);
+                    qx = ANCH(E, tb.x * 3); qy = ANCH(E, tb.x * 3 + 1); qz = ANCH(E, tb.x * 3 + 2);
+                    rob = tb.y;
+                }
+                ws_barrier(); /* step 0: the edge warp produces edge (N-2, N-1) */
+                for (int k = 1; k <= N; ++k) {
+                    const int i = N - k;
+                    double ncx = 0.0, ncy = 0.0, ncz = 0.0, nda = 0.0, nia = 0.0, nqx = 0.0, nqy = 0.0, nqz = 0.0;
+                    int nrob = 0;
+                    if (i >= 1) {
+                        const int j = i - 1;
+                        const double *tl = Tc + (size_t)j * 3 * TILE;
+                        ncx = ROW(tl, 0); ncy = ROW(tl, 1); ncz = ROW(tl, 2);
+                        const int2 tb = __ldg(reinterpret_cast<const int2 *>(tp.chain + j));
+                        const int sa = j == 0 ? 0 : 2 * j - 1;
+                        nda = ROW(E.p.rd, sa); nia = ROW(E.p.ri, sa);
+                        nqx = ANCH(E, tb.x * 3); nqy = ANCH(E, tb.x * 3 + 1); nqz = ANCH(E, tb.x * 3 + 2);
+                        nrob = tb.y;
+                    }
+                    if (UWBGO_L2PF_DIST > 0 && i >= 1 + 2 * UWBGO_L2PF_DIST) {
+                        const int j = i - 1 - 2 * UWBGO_L2PF_DIST;
+                        prefetch_rows_l2<3>(Tc + (size_t)j * 3 * TILE);
+                        prefetch_l2(E.p.rd + (size_t)(j == 0 ? 0 : 2 * j - 1) * TILE);
+                        prefetch_l2(E.p.ri + (size_t)(j == 0 ? 0 : 2 * j - 1) * TILE);
+                    }
+                    double h[HR_FAST];
+#pragma unroll
+                    for (int m = 0; m < HR_FAST; ++m) h[m] = 0.0;
+                    {
+                        double J[3], Ow, omega_r;
+                        const double err = da - dist3(cx, cy, cz, qx, qy, qz);
+                        fast_jac_v0(cx, cy, cz, qx, qy, qz, da, E.delta, E.scalar, J);
+                        chain_weights(E, err, ia, (rob & 1) != 0, Ow, omega_r);
+                        chain_acc(J, Ow, omega_r, h);
+                    }
+                    double nA[3] = {0.0, 0.0, 0.0}, nOw = 0.0, nOr = 0.0;
+                    if (i >= 1) { /* edge (i-1, i), linearised by the edge warp in step k-1 */
+                        const double(*t)[TILE] = sh.traj[(k - 1) & 1];
+                        nA[0] = t[0][lane]; nA[1] = t[1][lane]; nA[2] = t[2][lane];
+                        double B[3] = {t[3][lane], t[4][lane], t[5][lane]};
+                        nOw = t[6][lane];
+                        nOr = t[7][lane];
+                        const double AtO[3] = {nA[0] * nOw, nA[1] * nOw, nA[2] * nOw};
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) h[6 + 3 * r + cc] = fma(AtO[r], B[cc], h[6 + 3 * r + cc]);
+                        chain_acc(B, nOw, nOr, h);
+                    }
+                    chain_acc(carry, carry[3], carry[4], h);
+                    carry[0] = nA[0]; carry[1] = nA[1]; carry[2] = nA[2]; carry[3] = nOw; carry[4] = nOr;
+                    /* tail / finished lanes write to a scratch record of their own window: harmless */
+                    double *l = E.p.LR + (size_t)i * LR_FAST * TILE;
+                    factor_step<3>(h, l, true, i > 0, lambda, G, zn, ok);
+                    chain_store_b(l, h);
+                    cx = ncx; cy = ncy; cz = ncz; da = nda; ia = nia; qx = nqx; qy = nqy; qz = nqz; rob = nrob;
+                    ws_barrier();
+                }
+                ok = ok && (lambda > 0.0);
+            }
+            /* ---------------- chain warp, substitution phase ---------------- */
+            double scale = 0.0;
+            {
+                double xp[3] = {0.0, 0.0, 0.0};
+                double l[LR_FAST], nl[LR_FAST], t[3], nt[3];
+#pragma unroll
+                for (int m = 0; m < LR_FAST; ++m) nl[m] = ROW(E.p.LR, m);
+#pragma unroll
+                for (int m = 0; m < 3; ++m) nt[m] = ROW(Tc, m);
+                for (int k = 0; k <= N; ++k) {
+                    if (k < N) {
+                        const int i = k;
+#pragma unroll
+                        for (int m = 0; m < LR_FAST; ++m) l[m] = nl[m];
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) t[m] = nt[m];
+                        if (i + 1 < N) {
+                            const double *ln = E.p.LR + (size_t)(i + 1) * LR_FAST * TILE;
+                            const double *tn = Tc + (size_t)(i + 1) * 3 * TILE;
+#pragma unroll
+                            for (int m = 0; m < LR_FAST; ++m) nl[m] = ROW(ln, m);
+#pragma unroll
+                            for (int m = 0; m < 3; ++m) nt[m] = ROW(tn, m);
+                        }
+                        if (UWBGO_L2PF_DIST > 0 && i + 1 + UWBGO_L2PF_DIST < N) {
+                            prefetch_rows_l2<LR_FAST>(E.p.LR + (size_t)(i + 1 + UWBGO_L2PF_DIST) * LR_FAST * TILE);
+                            prefetch_rows_l2<3>(Tc + (size_t)(i + 1 + UWBGO_L2PF_DIST) * 3 * TILE);
+                        }
+                        subst_step<3>(l, i > 0, xp);
+                        if (!ok) xp[0] = xp[1] = xp[2] = 0.0;
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) scale = scale + xp[m] * (lambda * xp[m] + l[12 + m]);
+                        const double nx = xp[0] + t[0], ny = xp[1] + t[1], nz = xp[2] + t[2];
+                        double(*o)[TILE] = sh.tnew[i & 1];
+                        o[0][lane] = nx; o[1][lane] = ny; o[2][lane] = nz;
+                        if (act) {
+                            double *to = Tn + (size_t)i * 3 * TILE;
+                            ROW(to, 0) = nx; ROW(to, 1) = ny; ROW(to, 2) = nz;
+                        }
+                    }
+                    ws_barrier();
+                }
+            }
+            ws_barrier(); /* chi2 published by the edge warp */
+            if (act) {
+                const double tplain = sh.chi[0][lane];
+                double tempChi = sh.chi[1][lane];
+                if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;
+                stale = tplain;
+                if (!ok) tempChi = DBL_MAX;
+                scale = scale + 1e-3;
+                rho = (currentChi - tempChi) / scale;
+                const bool fin = isfinite(tempChi);
+                if (!fin) flags |= UWBGO_FLAG_NONFINITE;
+                if (rho > 0.0 && fin) {
+                    double tt = 2.0 * rho - 1.0;
+                    double alpha = 1.0 - (tt * tt) * tt;
+                    alpha = (cfg.good_hi < alpha) ? cfg.good_hi : alpha;
+                    double sf = (cfg.good_lo < alpha) ? alpha : cfg.good_lo;
+                    lambda = lambda * sf;
+                    ni = 2.0;
+                    currentChi = tempChi;
+                    plainCur = tplain;
+                    cur ^= 1;
+                } else {
+                    lambda = lambda * ni;
+                    ni = ni * 2.0;
+                }
+                ++q;
+                ++trials_total;
+                if (!(rho < 0.0 && q < cfg.max_trials)) {
+                    ++iterations;
+                    qlast = q;
+                    if (q == cfg.max_trials || rho == 0.0) {
+                        flags |= UWBGO_FLAG_TERMINATED;
+                        done = true;
+                    } else if (++it >= cfg.max_iterations) {
+                        done = true;
+                    }
+                    rho = 0.0;
+                    q = 0;
+                }
+                sh.cur[lane] = cur;
+                sh.act[lane] = done ? 0 : 1;
+            }
+            ws_barrier(); /* LM state published */
+        }
+    }
+    if (warp == 1 && valid) {
+        const int64_t tile = wreal / TILE;
+        double *chi2_out = ws.chi2 + tile * 4 * TILE + lane;
+        int32_t *status_out = ws.status + tile * 4 * TILE + lane;
+        ROW(chi2_out, 0) = plainCur;
+        ROW(chi2_out, 1) = currentChi;
+        ROW(chi2_out, 2) = stale;
+        ROW(chi2_out, 3) = lambda;
+        ROW(status_out, 0) = iterations;
+        ROW(status_out, 1) = trials_total;
+        ROW(status_out, 2) = flags;
+        ROW(status_out, 3) = qlast;
+        if (cur) {
+            for (int r = 0; r < N * 3; ++r) ROW(E.p.T0, r) = ROW(E.p.T1, r);
+        }
+        if (E.p.cnt) {
+            for (int i = 0; i < N; ++i) {
+                long long cc = (long long)E.p.cnt[(size_t)i * TILE] + (long long)iterations * __ldg(tp.num_calls + i) + trials_total;
+                E.p.cnt[(size_t)i * TILE] = (int)(cc % cfg.orth_mod);
+            }
+        }
+    }
+}
+
 UWBGO_DI void gen_env_init(GenEnv &E, const DevTopo &tp, const DevCfg &cfg, const DevWs &ws, int64_t w)
 {
     E.tp = &tp;
@@ -1965,6 +2322,13 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
 {
     if (ws.W <= 0) return cudaSuccess;
     if (topo.fast) {
+#ifndef UWBGO_CHAIN_WS
+#define UWBGO_CHAIN_WS 1 /* 1: warp-specialised CHAIN kernel, 0: single-warp CHAIN kernel */
+#endif
+        if (topo.fast == 2 && UWBGO_CHAIN_WS) {
+            lm_chain_ws_kernel<<<(unsigned)n_tiles(ws.W), 64, 0, st>>>(topo, cfg, ws);
+            return cudaGetLastError();
+        }
         int ais = 0;
         const int threads = topo.fast == 2 ? UWBGO_CHAIN_THREADS : CTA_THREADS;
         size_t sm = fast_smem_bytes(topo, threads, &ais);

@@ -324,3 +324,75 @@ def test_properties_at_full_size(solver):
     assert np.array_equal(got.pose_t[idx], ref.pose_t)
     assert np.array_equal(got.chi2[idx], ref.chi2)
     assert np.array_equal(got.status[idx], ref.status)
+
+
+def test_non_finite_inputs_are_contained(solver):
+    """a NaN / inf measurement poisons only its own window: flagged, no hang, neighbours bit-exact"""
+    from localization_b200._ffi import FLAG_NONFINITE
+    topo, batch, _ = synthetic.uwb_only(70, 10, 4, seed=41)
+    cfg = Config(max_iterations=6)
+    clean = solver.solve(topo, batch, cfg)
+    batch.range_d[3, 4] = np.nan
+    batch.range_d[40, 0] = np.inf
+    batch.pose_t[65, 2, 1] = np.nan
+    got = solver.solve(topo, batch, cfg)
+    ref = oracle.solve(topo, batch, cfg)
+    bad = np.array([3, 40, 65])
+    good = np.setdiff1d(np.arange(70), bad)
+    assert np.array_equal(got.pose_t[good], clean.pose_t[good]) and np.array_equal(got.chi2[good], clean.chi2[good])
+    # NaN in H fails the first pivot test (a NaN is not > 0): every trial is rejected like a non-SPD system
+    # (and rho = NaN ends the trial loop after one trial, as g2o's `while (rho < 0 ...)` would)
+    assert (got.status[bad, 2] & (FLAG_NONFINITE | FLAG_CHOL_FAIL)).all()
+    assert np.array_equal(got.status, ref.status)
+    assert np.array_equal(got.pose_t[bad], ref.pose_t[bad], equal_nan=True)
+
+
+def test_long_pose_window(solver):
+    """cfg/uwb_pose.yaml keeps 500 poses; keyframe stars over a long window (general path, forest)"""
+    topo, batch, _ = synthetic.uwb_pose(8, 500, 8, keyframe_len=20, seed=43)
+    cfg = Config(max_iterations=4)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+
+
+def test_random_forests(solver):
+    """random window structures obeying the forest rule, every edge kind, random insertion order"""
+    rng = np.random.default_rng(77)
+    for trial in range(6):
+        N, A, K, W = int(rng.integers(2, 12)), int(rng.integers(1, 5)), int(rng.integers(0, 3)), 33
+        parent = [-1] + [int(rng.integers(0, j)) if rng.random() < 0.85 else -1 for j in range(1, N)]
+        edges = []
+        for j in range(N):
+            for _ in range(int(rng.integers(0, 3))):
+                edges.append((EDGE_RANGE_ANCHOR, j, int(rng.integers(0, A)), int(rng.integers(0, K + 1)), int(rng.integers(0, 2))))
+            if rng.random() < 0.4:
+                edges.append((EDGE_PRIOR, j, 0, 0, int(rng.integers(0, 2))))
+            if parent[j] >= 0:
+                for _ in range(int(rng.integers(1, 3))):
+                    kind = EDGE_SE3 if rng.random() < 0.5 else EDGE_RANGE_POSE
+                    edges.append((kind, parent[j], j, int(rng.integers(0, K + 1)) if kind == EDGE_RANGE_POSE else 0,
+                                  int(rng.integers(0, 2))))
+        order = rng.permutation(len(edges))
+        topo = Topology.from_edges(N, A, K, [edges[k] for k in order])
+        er, ep, es = topo.counts()
+
+        def rand_R(shape):
+            q = rng.normal(size=shape + (4,)); q /= np.linalg.norm(q, axis=-1, keepdims=True)
+            w, x, y, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+            R = np.empty(shape + (3, 3))
+            R[..., 0, 0] = 1 - 2 * (y * y + z * z); R[..., 0, 1] = 2 * (x * y - z * w); R[..., 0, 2] = 2 * (x * z + y * w)
+            R[..., 1, 0] = 2 * (x * y + z * w); R[..., 1, 1] = 1 - 2 * (x * x + z * z); R[..., 1, 2] = 2 * (y * z - x * w)
+            R[..., 2, 0] = 2 * (x * z - y * w); R[..., 2, 1] = 2 * (y * z + x * w); R[..., 2, 2] = 1 - 2 * (x * x + y * y)
+            return R
+
+        def spd(shape):
+            M = rng.normal(size=shape + (6, 6))
+            return M @ np.swapaxes(M, -1, -2) + 0.5 * np.eye(6)
+        batch = Batch(pose_t=rng.normal(0, 1, (W, N, 3)), pose_R=rand_R((W, N)), anchors=rng.normal(0, 3, (W, A, 3)),
+                      range_d=np.abs(rng.normal(3, 1, (W, er))), range_info=rng.uniform(10, 400, (W, er)),
+                      ant_offsets=rng.normal(0, 0.2, (K, 3)) if K else None,
+                      prior_Z=np.concatenate([rand_R((W, ep)).reshape(W, ep, 9), rng.normal(0, 1, (W, ep, 3))], -1),
+                      prior_info=spd((W, ep)),
+                      se3_Z=np.concatenate([rand_R((W, es)).reshape(W, es, 9), rng.normal(0, .3, (W, es, 3))], -1),
+                      se3_info=spd((W, es)))
+        cfg = Config(max_iterations=4)
+        assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))

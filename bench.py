@@ -57,7 +57,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -141,7 +141,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="windows per GPU")
@@ -223,7 +223,6 @@ def main():
         solver.solve_device(topo, cb, cfg, cr, stream.cuda_stream)
         k_ms.append(solver.last_kernel_ms())
     torch.cuda.synchronize(dev)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -263,6 +262,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = W * world * args.steps / e2e_s
+    clocks = sampler.stop() if rank == 0 else None   # sampled across both timed regions
     # the two legs must agree bit for bit
     same = bool(np.array_equal(hres.pose_t, d_pose.cpu().numpy()))
 

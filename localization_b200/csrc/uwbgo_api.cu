@@ -82,7 +82,6 @@ struct TopoEntry {
 /* one pipeline lane: a stream, its device-side window-major staging and its tile workspace */
 struct Lane {
     cudaStream_t st = nullptr;
-    cudaEvent_t done = nullptr;
     DevBuf stage; /* window-major staging (host API only) */
     DevBuf tile;  /* tile-layout workspace */
 };
@@ -96,7 +95,7 @@ struct uwbgo_ctx {
     int n_lanes = 4;
     int64_t chunk = 16384;
     Lane lane[MAX_LANES];
-    DevBuf misc;          /* ant offsets + factor_solve scratch + lambda etc. */
+    DevBuf misc;          /* staging of the stand-alone factor/solve call, FP64 peak probe */
     DevBuf ant;
     std::vector<std::unique_ptr<TopoEntry>> topos;
     uint64_t stamp = 0;
@@ -599,7 +598,6 @@ int uwbgo_create(int device, uwbgo_ctx **out)
     ctx->device = device;
     for (int k = 0; k < MAX_LANES; ++k) {
         e = cudaStreamCreateWithFlags(&ctx->lane[k].st, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lane[k].done, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             uwbgo_destroy(ctx);
             return fail_cuda(e, "stream/event creation");
@@ -624,7 +622,6 @@ void uwbgo_destroy(uwbgo_ctx *ctx)
     for (int k = 0; k < MAX_LANES; ++k) {
         ctx->lane[k].stage.release();
         ctx->lane[k].tile.release();
-        if (ctx->lane[k].done) cudaEventDestroy(ctx->lane[k].done);
         if (ctx->lane[k].st) cudaStreamDestroy(ctx->lane[k].st);
     }
     ctx->misc.release();

@@ -396,3 +396,36 @@ def test_random_forests(solver):
                       se3_info=spd((W, es)))
         cfg = Config(max_iterations=4)
         assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+
+
+def test_abi_error_paths(solver):
+    """the C ABI reports bad arguments with negative codes and a message, never crashes"""
+    import ctypes as C
+    from localization_b200 import UwbgoError, _ffi
+    lib = _ffi.load_library()
+    topo, batch, _ = synthetic.uwb_only(4, 6, 4)
+    cfg = Config(max_iterations=2)
+    t, b, c = topo.c_struct(), batch.c_struct(), cfg.c_struct()
+    r = _ffi.CResult()   # pose_t NULL
+    assert lib.uwbgo_solve_batch(solver._h, C.byref(t), C.byref(b), C.byref(c), C.byref(r)) == _ffi.E_INVALID
+    assert b"pose_t" in lib.uwbgo_last_error()
+    assert lib.uwbgo_solve_batch(None, C.byref(t), C.byref(b), C.byref(c), C.byref(r)) == _ffi.E_INVALID
+    b.range_d = None
+    res = solver.solve(topo, batch, cfg).c_struct()
+    assert lib.uwbgo_solve_batch(solver._h, C.byref(t), C.byref(b), C.byref(c), C.byref(res)) == _ffi.E_INVALID
+    bad = Topology.from_edges(3, 1, 0, [(EDGE_RANGE_ANCHOR, 0, 5, 0, 1)])          # anchor index out of range
+    with pytest.raises(UwbgoError) as ei:
+        solver.solve(bad, Batch(pose_t=np.zeros((1, 3, 3)), anchors=np.zeros((1, 1, 3)), range_d=np.ones((1, 1)),
+                                range_info=np.ones((1, 1))), cfg)
+    assert ei.value.code == _ffi.E_INVALID
+    bad = Topology.from_edges(3, 1, 0, [(EDGE_RANGE_POSE, 2, 1, 0, 1)])            # vertex 1 older than vertex 0
+    with pytest.raises(UwbgoError) as ei:
+        solver.solve(bad, Batch(pose_t=np.zeros((1, 3, 3)), anchors=np.zeros((1, 1, 3)), range_d=np.ones((1, 1)),
+                                range_info=np.ones((1, 1))), cfg)
+    assert ei.value.code == _ffi.E_TOPOLOGY
+    with pytest.raises(UwbgoError):
+        solver.solve(topo, batch, Config(max_iterations=-1))
+    with pytest.raises(UwbgoError):
+        solver.set_pipeline(8, 1)
+    got = solver.solve(topo, batch, cfg)                                            # context still healthy
+    assert_parity(got, oracle.solve(topo, batch, cfg))

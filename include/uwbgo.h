@@ -183,7 +183,8 @@ int64_t uwbgo_launch_count(const uwbgo_ctx *ctx);
 int     uwbgo_last_path(const uwbgo_ctx *ctx);
 /* Kernel timing for roofline reports: with profiling on, every *_device call records CUDA events
  * on its stream immediately before and after its main kernel (the fused LM kernel of
- * uwbgo_solve_batch_device, the linearisation kernel of uwbgo_linearize_batch_device);
+ * uwbgo_solve_batch_device; the linearisation kernel plus the expansion of H to the public
+ * full-block layout for uwbgo_linearize_batch_device);
  * uwbgo_last_kernel_ms waits for the last such kernel and returns its duration (-1 if none). */
 int     uwbgo_set_profiling(uwbgo_ctx *ctx, int on);
 double  uwbgo_last_kernel_ms(uwbgo_ctx *ctx);

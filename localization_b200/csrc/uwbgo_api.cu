@@ -499,8 +499,8 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     if (timed) CU(cudaEventRecord(ctx->k0, st));
     if (so) {
         CU(launch_linearize(tp, cfg, ws, st));
-        if (timed) CU(cudaEventRecord(ctx->k1, st));
         CU(launch_expand_H(tp, ws, so->H_diag, so->H_off, so->b, st));
+        if (timed) CU(cudaEventRecord(ctx->k1, st)); /* stage = linearise + expansion to the public layout */
         ctx->launches += 2;
         if (so->chi2) add(uj, ws.chi2, so->chi2, 2, 8, 0);
     } else {

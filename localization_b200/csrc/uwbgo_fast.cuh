@@ -90,7 +90,10 @@ UWBGO_DI void fast_jac_v1(double px, double py, double pz, double qx, double qy,
 
 /* BlockSolver::buildSystem for one window: per pose, gather its edges in insertion order.
  * Writes the H records; returns max |H_kk| (computeLambdaInit). */
-template <bool WRITE>
+/* where fast_linearize puts the system: nowhere (lambda init only) or the tile-layout H records */
+enum { SINK_NONE = 0, SINK_RECORDS = 1 };
+
+template <int SINK>
 UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
 {
     const DevTopo &tp = *E.tp;
@@ -168,7 +171,7 @@ UWBGO_DI double fast_linearize(const FastEnv &E, const double *__restrict__ T)
             hd[4] = fma(JtO[1], J[2], hd[4]);
             hd[5] = fma(JtO[2], J[2], hd[5]);
         }
-        if (WRITE) {
+        if (SINK == SINK_RECORDS) {
             double *h = E.p.HB + (size_t)i * HR_FAST * TILE;
 #pragma unroll
             for (int k = 0; k < 6; ++k) ROW(h, k) = hd[k];

@@ -47,7 +47,7 @@ template <>
 struct Path<2> {
     FastEnv E;
     UWBGO_DI void chi(int buf, double &p, double &r) const { fast_chi_pass(E, E.p.T(buf), p, r); }
-    UWBGO_DI double linearize(int buf) const { return fast_linearize<false>(E, E.p.T(buf)); }
+    UWBGO_DI double linearize(int buf) const { return fast_linearize<SINK_NONE>(E, E.p.T(buf)); }
     UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
     {
         bool ok = chain_factor(E, E.p.T(from), lambda) && (lambda > 0.0);
@@ -60,7 +60,7 @@ template <>
 struct Path<1> {
     FastEnv E;
     UWBGO_DI void chi(int buf, double &p, double &r) const { fast_chi_pass(E, E.p.T(buf), p, r); }
-    UWBGO_DI double linearize(int buf) const { return fast_linearize<false>(E, E.p.T(buf)); }
+    UWBGO_DI double linearize(int buf) const { return fast_linearize<SINK_NONE>(E, E.p.T(buf)); }
     /* factor + substitution + update + residuals of one LM trial */
     UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
     {
@@ -293,7 +293,7 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
     if (warp == 1) {
         fast_chi_pass(E, E.p.T0, plainCur, currentChi);
         stale = plainCur;
-        const double maxdiag = fast_linearize<false>(E, E.p.T0);
+        const double maxdiag = fast_linearize<SINK_NONE>(E, E.p.T0);
         if (cfg.max_iterations > 0) lambda = cfg.tau * maxdiag;
         sh.cur[lane] = 0;
         sh.act[lane] = done ? 0 : 1;
@@ -636,7 +636,7 @@ linearize_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
     fast_env_init(E, tp, cfg, ws, w, smem, anchors_in_smem);
     double p, r;
     fast_chi_pass(E, E.p.T0, p, r);
-    fast_linearize<true>(E, E.p.T0);
+    fast_linearize<SINK_RECORDS>(E, E.p.T0);
     double *c = ws.chi2 + (w / TILE) * 2 * TILE + (w % TILE);
     ROW(c, 0) = p;
     ROW(c, 1) = r;
@@ -818,43 +818,59 @@ cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs
 }
 
 /* H records (tile layout) -> public H_diag [W][N][36] (both triangles), H_off [W][N-1][36],
- * b [W][N][6].  One thread per (window, pose); reads coalesced, writes are 36-double runs. */
-__global__ void __launch_bounds__(CTA_THREADS)
-expand_H_kernel(DevTopo tp, DevWs ws, double *__restrict__ H_diag, double *__restrict__ H_off,
-                double *__restrict__ b)
+ * b [W][N][6].  One warp per (tile, pose): the record is expanded into a padded shared-memory
+ * panel [78][33] with coalesced row reads, then written out window by window as contiguous
+ * 288-byte / 48-byte runs. */
+constexpr int EXPAND_WARPS = 2;
+__global__ void __launch_bounds__(EXPAND_WARPS * 32)
+expand_H_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevWs ws,
+                double *__restrict__ H_diag, double *__restrict__ H_off, double *__restrict__ b)
 {
-    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
-    const int i = blockIdx.y;
-    if (w >= ws.W) return;
+    __shared__ double sm[EXPAND_WARPS][78][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = tp.N;
-    const int64_t tile = w / TILE;
-    const int lane = (int)(w % TILE);
-    double *hd = H_diag + ((size_t)w * N + i) * 36;
-    double *bo = b + ((size_t)w * N + i) * 6;
+    const int64_t item = (int64_t)blockIdx.x * EXPAND_WARPS + warp;
+    if (item >= n_tiles(ws.W) * N) return;
+    const int64_t tile = item / N;
+    const int i = (int)(item % N);
+    double(*p)[33] = sm[warp];
     if (tp.fast) {
         const double *h = ws.HB + ((tile * N + i) * (size_t)HR_FAST) * TILE + lane;
+#pragma unroll
         for (int r = 0; r < 6; ++r)
+#pragma unroll
             for (int c = 0; c < 6; ++c) {
-                double v = 0.0;
-                if (r < 3 && c < 3) v = r <= c ? ROW(h, up_idx(3, r, c)) : ROW(h, up_idx(3, c, r));
-                hd[6 * r + c] = v;
+                const bool in = r < 3 && c < 3;
+                p[6 * r + c][lane] = in ? (r <= c ? ROW(h, up_idx(3, r, c)) : ROW(h, up_idx(3, c, r))) : 0.0;
+                p[36 + 6 * r + c][lane] = in ? ROW(h, 6 + 3 * r + c) : 0.0;
             }
-        for (int r = 0; r < 6; ++r) bo[r] = r < 3 ? ROW(h, 15 + r) : 0.0;
-        if (i > 0) {
-            double *ho = H_off + ((size_t)w * (N - 1) + (i - 1)) * 36;
-            for (int r = 0; r < 6; ++r)
-                for (int c = 0; c < 6; ++c) ho[6 * r + c] = (r < 3 && c < 3) ? ROW(h, 6 + 3 * r + c) : 0.0;
-        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) p[72 + r][lane] = r < 3 ? ROW(h, 15 + r) : 0.0;
     } else {
         const double *h = ws.HB + ((tile * N + i) * (size_t)HR_GEN) * TILE + lane;
+#pragma unroll
         for (int r = 0; r < 6; ++r)
-            for (int c = 0; c < 6; ++c)
-                hd[6 * r + c] = r <= c ? ROW(h, up_idx(6, r, c)) : ROW(h, up_idx(6, c, r));
-        for (int r = 0; r < 6; ++r) bo[r] = ROW(h, 57 + r);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                p[6 * r + c][lane] = r <= c ? ROW(h, up_idx(6, r, c)) : ROW(h, up_idx(6, c, r));
+                p[36 + 6 * r + c][lane] = ROW(h, 21 + 6 * r + c);
+            }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) p[72 + r][lane] = ROW(h, 57 + r);
+    }
+    __syncwarp();
+    for (int wl = 0; wl < TILE; ++wl) {
+        const int64_t w = tile * TILE + wl;
+        if (w >= ws.W) break;
+        double *hd = H_diag + ((size_t)w * N + i) * 36;
+        hd[lane] = p[lane][wl];
+        if (lane < 4) hd[32 + lane] = p[32 + lane][wl];
         if (i > 0) {
             double *ho = H_off + ((size_t)w * (N - 1) + (i - 1)) * 36;
-            for (int k = 0; k < 36; ++k) ho[k] = ROW(h, 21 + k);
+            ho[lane] = p[36 + lane][wl];
+            if (lane < 4) ho[32 + lane] = p[68 + lane][wl];
         }
+        if (lane < 6) b[((size_t)w * N + i) * 6 + lane] = p[72 + lane][wl];
     }
 }
 
@@ -862,8 +878,9 @@ cudaError_t launch_expand_H(const DevTopo &topo, const DevWs &ws, double *H_diag
                             double *b, cudaStream_t st)
 {
     if (ws.W <= 0) return cudaSuccess;
-    dim3 grid(window_blocks(ws.W), (unsigned)topo.N);
-    expand_H_kernel<<<grid, CTA_THREADS, 0, st>>>(topo, ws, H_diag, H_off, b);
+    const int64_t items = n_tiles(ws.W) * topo.N;
+    expand_H_kernel<<<(unsigned)((items + EXPAND_WARPS - 1) / EXPAND_WARPS), EXPAND_WARPS * 32, 0, st>>>(
+        topo, ws, H_diag, H_off, b);
     return cudaGetLastError();
 }
 

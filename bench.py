@@ -36,6 +36,22 @@ ALGO_BYTES_SOLVE = 7408
 ALGO_BYTES_LINEARIZE = 35496
 
 
+ARRAYS = ("pose_t", "pose_R", "anchors", "range_d", "range_info", "prior_Z", "prior_info", "se3_Z", "se3_info")
+# name -> (description, default windows per GPU, generator, LM iterations, SURVEY algorithmic bytes per window or None)
+WORKLOADS = {
+    "c3": (WORKLOAD, WINDOWS_PER_GPU, lambda syn, W, seed: syn.uwb_only(W, N_POSES, N_ANCHORS, seed=seed), LM_ITERS, ALGO_BYTES_SOLVE),
+    "c4a": ("C4a: synthetic uwb_imu_lidar windows, 8 anchors, 20-pose window, 3 antennas with lever arms, IMU + lidar "
+            "EdgeSE3Prior on every pose but the newest, 20 LM iterations", 8192,
+            lambda syn, W, seed: syn.uwb_imu_lidar(W, 20, 8, seed=seed), 20, None),
+    "c4b": ("C4b: synthetic uwb_twist windows, 8 anchors, 15-pose window, twist EdgeSE3 chain, merged-covariance "
+            "ranges with 3 antennas, 12 LM iterations", 8192,
+            lambda syn, W, seed: syn.uwb_twist(W, 15, 8, seed=seed), 12, None),
+    "c5": ("C5: synthetic UWB-only Monte-Carlo windows, 16 anchors, 200-pose window, 10 LM iterations "
+           "(1,048,576 windows over 8 GPUs = 131,072 per GPU)", 131072,
+           lambda syn, W, seed: syn.uwb_only(W, 200, 16, seed=seed), 10, 29200),
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -93,7 +109,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(topo, batch, cfg, budget_s=12.0):
+def cpu_baseline(topo, batch, cfg, budget_s=12.0, name="C3"):
     """oracle (CPU restatement of the reference's g2o LM) on a bounded sample, all host threads"""
     from oracle import oracle
     cores = os.cpu_count() or 1
@@ -106,7 +122,7 @@ def cpu_baseline(topo, batch, cfg, budget_s=12.0):
     oracle.solve(topo, batch.slice(0, n), cfg, n_threads=cores)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} of the {batch.n_windows} C3 windows, {cores} threads, {dt:.2f} s"}
+            "sample": f"{n} of the {batch.n_windows} {name} windows, {cores} threads, {dt:.2f} s"}
 
 
 def run_reference(args, rank, world):
@@ -144,9 +160,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="windows per GPU")
+    ap.add_argument("--windows", type=int, default=0, help="windows per GPU (0 = the workload's own)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--stages", action="store_true", help="also time the stage kernels")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="c3 = BASELINE metric config (default); the others are the remaining BASELINE configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -165,15 +183,21 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    W = args.windows
-    cfg = Config(max_iterations=LM_ITERS)
-    topo, batch, _ = synthetic.uwb_only(W, N_POSES, N_ANCHORS, seed=synthetic.SEED_C3 + rank)
+    wl_desc, wl_W, wl_make, wl_iters, wl_bytes = WORKLOADS[args.workload]
+    W = args.windows or wl_W
+    cfg = Config(max_iterations=wl_iters)
+    topo, batch, _ = wl_make(synthetic, W, synthetic.SEED_C3 + rank)
     solver = Solver(local)
-    N = N_POSES
+    N = topo.n_poses
+    present = [k for k in ARRAYS if getattr(batch, k) is not None]
+    general = batch.pose_R is not None
+    if wl_bytes is None:   # inputs as passed + estimates, chi2 and status out
+        wl_bytes = sum(getattr(batch, k).nbytes for k in present) // W + N * (96 if general else 24) + 48
 
     # ---- device-resident leg ------------------------------------------------------------
-    d_in = {k: torch.from_numpy(getattr(batch, k)).to(dev) for k in ("pose_t", "anchors", "range_d", "range_info")}
+    d_in = {k: torch.from_numpy(getattr(batch, k)).to(dev) for k in present}
     d_pose = torch.empty((W, N, 3), dtype=torch.float64, device=dev)
+    d_rot = torch.empty((W, N, 9), dtype=torch.float64, device=dev) if general else None
     d_chi2 = torch.empty((W, 4), dtype=torch.float64, device=dev)
     d_status = torch.empty((W, 4), dtype=torch.int32, device=dev)
     gather = [torch.empty_like(d_pose) for _ in range(world)] if (world > 1 and rank == 0) else None
@@ -181,10 +205,14 @@ def main():
     cb = _ffi.CBatch()
     cb.n_windows = W
     pd = lambda t: C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_double))
-    cb.pose_t, cb.anchors, cb.range_d, cb.range_info = (pd(d_in["pose_t"]), pd(d_in["anchors"]),
-                                                        pd(d_in["range_d"]), pd(d_in["range_info"]))
+    for k in present:
+        setattr(cb, k, pd(d_in[k]))
+    if batch.ant_offsets is not None:
+        cb.ant_offsets = batch.ant_offsets.ctypes.data_as(C.POINTER(C.c_double))
     cr = _ffi.CResult()
     cr.pose_t, cr.chi2 = pd(d_pose), pd(d_chi2)
+    if general:
+        cr.pose_R = pd(d_rot)
     cr.status = C.cast(C.c_void_p(d_status.data_ptr()), C.POINTER(C.c_int32))
     stream = torch.cuda.current_stream(dev)
     solver.set_profiling(True)
@@ -231,19 +259,22 @@ def main():
 
     # ---- end-to-end leg: host buffers through uwbgo_solve_batch ----------------------------
     from localization_b200 import Batch, Result
-    hb = Batch(pose_t=batch.pose_t, anchors=batch.anchors, range_d=batch.range_d, range_info=batch.range_info)
-    for k in ("pose_t", "anchors", "range_d", "range_info"):
+    hb = Batch(pose_t=batch.pose_t, ant_offsets=batch.ant_offsets)
+    for k in present:
         a = pinned_empty(getattr(batch, k).shape)
         a[...] = getattr(batch, k)
         setattr(hb, k, a)
-    hres = Result(pinned_empty((W, N, 3)), None, None, pinned_empty((W, 4)), pinned_empty((W, 4), np.int32))
-    h2d = sum(getattr(hb, k).nbytes for k in ("pose_t", "anchors", "range_d", "range_info"))
-    d2h = hres.pose_t.nbytes + hres.chi2.nbytes + hres.status.nbytes
+    hres = Result(pinned_empty((W, N, 3)), pinned_empty((W, N, 3, 3)) if general else None, None,
+                  pinned_empty((W, 4)), pinned_empty((W, 4), np.int32))
+    h2d = sum(getattr(hb, k).nbytes for k in present)
+    d2h = hres.pose_t.nbytes + hres.chi2.nbytes + hres.status.nbytes + (hres.pose_R.nbytes if general else 0)
 
     def step_host():
         t_, b_, c_ = topo.c_struct(), hb.c_struct(), cfg.c_struct()
         r_ = _ffi.CResult()
         r_.pose_t, r_.chi2 = pd_np(hres.pose_t), pd_np(hres.chi2)
+        if general:
+            r_.pose_R = pd_np(hres.pose_R)
         r_.status = hres.status.ctypes.data_as(C.POINTER(C.c_int32))
         rc = solver._lib.uwbgo_solve_batch(solver._h, C.byref(t_), C.byref(b_), C.byref(c_), C.byref(r_))
         if rc:
@@ -270,20 +301,21 @@ def main():
     if rank == 0:
         hbm, how = peaks()
         k_best = float(np.median([k for k in k_ms if k and k > 0])) if k_ms else None
-        achieved = ALGO_BYTES_SOLVE * W / (k_best * 1e-3) / 1e9 if k_best else None
+        achieved = wl_bytes * W / (k_best * 1e-3) / 1e9 if k_best else None
         traffic, traffic_src, fp64_flop, fp64_pipe = None, None, None, None
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp) and W == WINDOWS_PER_GPU:
+        if os.path.exists(tp) and W == WINDOWS_PER_GPU and args.workload == "c3":
             with open(tp) as f:
                 tj = json.load(f)["lm_chain_ws_kernel"]
             traffic, traffic_src = tj["dram_bytes_per_launch"] / 1e9, tj["source"]
             fp64_flop = tj.get("fp64_flop_per_launch")
             fp64_pipe = tj.get("fp64_pipe_active_pct")
-        roof = {"bound": "hbm", "kernel": "lm_chain_ws_kernel (fused LM: linearise + assemble + block Cholesky + damping loop)",
+        kname = {1: "lm_fast_kernel", 2: "lm_chain_ws_kernel"}.get(solver.last_path, "lm_general_kernel")
+        roof = {"bound": "hbm", "kernel": kname + " (fused LM: linearise + assemble + block Cholesky + damping loop)",
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm if achieved else None,
                 "traffic": traffic, "traffic_unit": "GB per launch (dram read+write, ncu)", "traffic_source": traffic_src,
                 "peak_source": how, "kernel_ms": k_best,
-                "algorithmic_bytes_per_window": ALGO_BYTES_SOLVE,
+                "algorithmic_bytes_per_window": wl_bytes,
                 "note": "7.4 KB of algorithmic bytes per window against ~1.8 M FP64-heavy thread-instructions: the "
                         "fused solve is FP64 issue/latency bound by construction (SURVEY 8d), so its HBM fraction is "
                         "small; traffic above the algorithmic bytes is the per-window substitution record streamed "
@@ -296,15 +328,16 @@ def main():
             roof["fp64_flop_per_window"] = fp64_flop / W
             roof["fp64_pipe_active_pct_ncu"] = fp64_pipe
         stages = None
-        if args.stages:
+        if args.stages and args.workload == "c3":
             stages = time_stages(solver, topo, batch, cfg, dev, hbm)
-        cpu = None if args.no_cpu else cpu_baseline(topo, batch, cfg)
+        cpu = None if args.no_cpu else cpu_baseline(topo, batch, cfg, name=args.workload.upper())
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "windows_per_gpu": W, "n_poses": N, "n_anchors": N_ANCHORS,
-                           "lm_iterations": LM_ITERS, "parallelism": f"windows sharded x{world}, no data-path collective",
-                           "l2": "inputs (300 MB) and workspace (1.2 GB) per step exceed the 126 MB L2"},
+                "config": {"workload": wl_desc, "windows_per_gpu": W, "n_poses": N, "n_anchors": topo.n_anchors,
+                           "lm_iterations": wl_iters, "parallelism": f"windows sharded x{world}, no data-path collective",
+                           "l2": f"inputs ({h2d / 1e6:.0f} MB) and workspace per step exceed the 126 MB L2"
+                                 if h2d > 126e6 else f"inputs {h2d / 1e6:.0f} MB; the LM workspace is rewritten every trial"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "matches_device_leg": same},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}

@@ -59,8 +59,7 @@ UWBGO_DI void load_Zinv(const double *__restrict__ Zrows, int slot, Pose &Zinv)
 UWBGO_DI void offset_point(const GenEnv &E, const Pose &X, int ant, double *P)
 {
     if (ant > 0) {
-        double o[3] = {__ldg(E.ant + 3 * (ant - 1)), __ldg(E.ant + 3 * (ant - 1) + 1),
-                       __ldg(E.ant + 3 * (ant - 1) + 2)};
+        double o[3] = {E.ant[3 * (ant - 1)], E.ant[3 * (ant - 1) + 1], E.ant[3 * (ant - 1) + 2]};
         mat3_vec_add(X.R, o, X.t, P);
     } else {
         P[0] = X.t[0]; P[1] = X.t[1]; P[2] = X.t[2];
@@ -156,9 +155,9 @@ UWBGO_DI void gen_jac_v0(const GenEnv &E, const Pose &X, int ant, const double *
     const int mod = E.cfg->orth_mod;
     double o[3] = {0.0, 0.0, 0.0};
     if (ant > 0) {
-        o[0] = __ldg(E.ant + 3 * (ant - 1));
-        o[1] = __ldg(E.ant + 3 * (ant - 1) + 1);
-        o[2] = __ldg(E.ant + 3 * (ant - 1) + 2);
+        o[0] = E.ant[3 * (ant - 1)];
+        o[1] = E.ant[3 * (ant - 1) + 1];
+        o[2] = E.ant[3 * (ant - 1) + 2];
     }
     int call = c0 + base;
 #pragma unroll

@@ -595,12 +595,15 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
     }
 }
 
-UWBGO_DI void gen_env_init(GenEnv &E, const DevTopo &tp, const DevCfg &cfg, const DevWs &ws, int64_t w)
+/* antenna lever arms: a handful of doubles every range edge reads -> shared memory, loaded once */
+constexpr int MAX_SMEM_ANTENNAS = 16;
+UWBGO_DI void gen_env_init(GenEnv &E, const DevTopo &tp, const DevCfg &cfg, const DevWs &ws, int64_t w,
+                           double *s_ant)
 {
     E.tp = &tp;
     E.cfg = &cfg;
     E.p = thread_ptrs<HR_GEN, LR_GEN>(tp, ws, w);
-    E.ant = ws.ant;
+    E.ant = (tp.K > 0 && tp.K <= MAX_SMEM_ANTENNAS) ? s_ant : ws.ant;
     E.ck.init(cfg.kdelta);
     E.delta = cfg.jdelta;
     E.scalar = 1.0 / (2.0 * cfg.jdelta);
@@ -610,10 +613,14 @@ __global__ void __launch_bounds__(CTA_THREADS)
 lm_general_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                   const __grid_constant__ DevWs ws)
 {
+    __shared__ double s_ant[3 * MAX_SMEM_ANTENNAS];
+    if (tp.K <= MAX_SMEM_ANTENNAS)
+        for (int k = threadIdx.x; k < 3 * tp.K; k += CTA_THREADS) s_ant[k] = ws.ant[k];
+    __syncthreads();
     const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     if (w >= ws.W) return;
     Path<0> P;
-    gen_env_init(P.E, tp, cfg, ws, w);
+    gen_env_init(P.E, tp, cfg, ws, w, s_ant);
     const int64_t tile = w / TILE;
     const int lane = (int)(w % TILE);
     int cur;
@@ -646,10 +653,14 @@ __global__ void __launch_bounds__(CTA_THREADS)
 linearize_general_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                          const __grid_constant__ DevWs ws)
 {
+    __shared__ double s_ant[3 * MAX_SMEM_ANTENNAS];
+    if (tp.K <= MAX_SMEM_ANTENNAS)
+        for (int k = threadIdx.x; k < 3 * tp.K; k += CTA_THREADS) s_ant[k] = ws.ant[k];
+    __syncthreads();
     const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
     if (w >= ws.W) return;
     GenEnv E;
-    gen_env_init(E, tp, cfg, ws, w);
+    gen_env_init(E, tp, cfg, ws, w, s_ant);
     double p, r;
     PoseBuf T0{E.p.T0, E.p.Rm0};
     gen_chi_pass(E, T0, p, r);

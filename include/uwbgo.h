@@ -191,6 +191,14 @@ double  uwbgo_last_kernel_ms(uwbgo_ctx *ctx);
 /* FP64 FMA micro-benchmark on the context's GPU: returns achieved FP64 FLOP/s (2 per FMA),
  * used as the measured FP64 roofline denominator (MEASURED_PEAKS.json has none). */
 double  uwbgo_measure_fp64_peak(uwbgo_ctx *ctx, double *elapsed_ms);
+/* Arithmetic self-test of the branch-free sqrt / reciprocal / division / logarithm sequences the
+ * CHAIN kernels use (uwbgo_math.cuh, NbMath) against the IEEE operations, on about n_operands
+ * pseudo-random operands.  mode 0: operands over the whole binary64 encoding space; mode 1:
+ * magnitudes 2^-60..2^60.  counts[0] = results compared or flagged, counts[1] = results that
+ * differ in bits from IEEE although the sequence did not flag its operand (must be 0),
+ * counts[2] = operands flagged as outside the safe range (the solver re-runs those trials with
+ * the IEEE operations). */
+int     uwbgo_selftest_math(uwbgo_ctx *ctx, uint64_t seed, int64_t n_operands, int mode, int64_t counts[3]);
 
 #ifdef __cplusplus
 }

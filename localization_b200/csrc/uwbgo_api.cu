@@ -976,4 +976,23 @@ double uwbgo_measure_fp64_peak(uwbgo_ctx *ctx, double *elapsed_ms)
     return flops / (best * 1e-3);
 }
 
+int uwbgo_selftest_math(uwbgo_ctx *ctx, uint64_t seed, int64_t n_operands, int mode, int64_t counts[3])
+{
+    if (!ctx || !counts || n_operands <= 0 || (mode != 0 && mode != 1)) return fail(UWBGO_E_INVALID, "selftest_math: bad argument");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(UWBGO_E_CUDA, "cudaSetDevice failed");
+    if (ctx->misc.reserve(3 * sizeof(unsigned long long))) return fail(UWBGO_E_NOMEM, "selftest_math: workspace");
+    cudaStream_t st = ctx->lane[0].st;
+    unsigned long long *d = static_cast<unsigned long long *>(ctx->misc.p);
+    const int per_thread = 64, blocks = (int)std::min<int64_t>((n_operands + 256LL * per_thread * 4 - 1) / (256LL * per_thread * 4), 1 << 20);
+    unsigned long long h[3] = {0, 0, 0};
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof h, st);
+    if (e == cudaSuccess) e = launch_math_selftest(seed, blocks, per_thread, mode, d, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    ctx->launches += 1;
+    if (e != cudaSuccess) return fail(UWBGO_E_CUDA, cudaGetErrorString(e));
+    for (int k = 0; k < 3; ++k) counts[k] = (int64_t)h[k];
+    return UWBGO_OK;
+}
+
 }  // extern "C"

@@ -35,10 +35,12 @@ UWBGO_DI void load_hrec(const double *__restrict__ h, double *r)
 
 /* one elimination step on the H record held in `h`; G/zn carry G_i and z_{i+1} in, G_{i-1} and
  * z_i out */
-template <int D>
+template <int D, class M = IeeeMath>
 UWBGO_DI void factor_step(const double *h, double *__restrict__ l, bool link, bool has_prev,
-                          double lambda, double *G, double *zn, bool &ok)
+                          double lambda, double *G, double *zn, bool &ok, unsigned *badp = nullptr)
 {
+    unsigned bad_local = 0;
+    unsigned &bad = badp ? *badp : bad_local;
     constexpr int TRI = Rec<D>::TRI, SQ = Rec<D>::SQ;
     double S[TRI], L[TRI], z[D], c[D];
 #pragma unroll
@@ -59,7 +61,7 @@ UWBGO_DI void factor_step(const double *h, double *__restrict__ l, bool link, bo
 #pragma unroll
         for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
         if (!(s > 0.0)) ok = false;
-        double inv = 1.0 / sqrt(s);
+        double inv = M::rcp(M::sqrt_(s, bad), bad);
         L[lo_idx(j, j)] = inv;
 #pragma unroll
         for (int r = j + 1; r < D; ++r) {

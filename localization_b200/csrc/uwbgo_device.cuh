@@ -61,6 +61,10 @@ struct Cauchy {
     }
     UWBGO_DI double rho0(double e2) const { return dsqr * det_log(dsqrReci * e2 + 1.0); }
     UWBGO_DI double rho1(double e2) const { return 1.0 / (dsqrReci * e2 + 1.0); }
+    template <class M>
+    UWBGO_DI double rho0m(double e2, unsigned &bad) const { return dsqr * M::log_(dsqrReci * e2 + 1.0, bad); }
+    template <class M>
+    UWBGO_DI double rho1m(double e2, unsigned &bad) const { return M::rcp(dsqrReci * e2 + 1.0, bad); }
 };
 
 /* thread-private view of the tile-layout workspace */

@@ -59,32 +59,38 @@ UWBGO_DI void fast_chi_pass(const FastEnv &E, const double *__restrict__ T, doub
  * perturbed end point (px,py,pz); the other end point is (qx,qy,qz).  sign = +1: the perturbed
  * point is vertex 0 (dt = P - Q); sign = -1: vertex 1 (dt = Q - P, so pass P/Q swapped).
  * BaseBinaryEdge::linearizeOplus: J[d] = (e(+delta) - e(-delta)) / (2 delta). */
+template <class M = IeeeMath>
 UWBGO_DI void fast_jac_v0(double px, double py, double pz, double qx, double qy, double qz,
-                          double d, double delta, double scalar, double *J)
+                          double d, double delta, double scalar, double *J, unsigned *badp = nullptr)
 {
+    unsigned bl = 0;
+    unsigned &bad = badp ? *badp : bl;
     double ep, em;
-    ep = d - dist3(delta + px, py, pz, qx, qy, qz);
-    em = d - dist3(-delta + px, py, pz, qx, qy, qz);
+    ep = d - dist3m<M>(delta + px, py, pz, qx, qy, qz, bad);
+    em = d - dist3m<M>(-delta + px, py, pz, qx, qy, qz, bad);
     J[0] = scalar * (ep - em);
-    ep = d - dist3(px, delta + py, pz, qx, qy, qz);
-    em = d - dist3(px, -delta + py, pz, qx, qy, qz);
+    ep = d - dist3m<M>(px, delta + py, pz, qx, qy, qz, bad);
+    em = d - dist3m<M>(px, -delta + py, pz, qx, qy, qz, bad);
     J[1] = scalar * (ep - em);
-    ep = d - dist3(px, py, delta + pz, qx, qy, qz);
-    em = d - dist3(px, py, -delta + pz, qx, qy, qz);
+    ep = d - dist3m<M>(px, py, delta + pz, qx, qy, qz, bad);
+    em = d - dist3m<M>(px, py, -delta + pz, qx, qy, qz, bad);
     J[2] = scalar * (ep - em);
 }
+template <class M = IeeeMath>
 UWBGO_DI void fast_jac_v1(double px, double py, double pz, double qx, double qy, double qz,
-                          double d, double delta, double scalar, double *J)
+                          double d, double delta, double scalar, double *J, unsigned *badp = nullptr)
 {
+    unsigned bl = 0;
+    unsigned &bad = badp ? *badp : bl;
     double ep, em;
-    ep = d - dist3(px, py, pz, delta + qx, qy, qz);
-    em = d - dist3(px, py, pz, -delta + qx, qy, qz);
+    ep = d - dist3m<M>(px, py, pz, delta + qx, qy, qz, bad);
+    em = d - dist3m<M>(px, py, pz, -delta + qx, qy, qz, bad);
     J[0] = scalar * (ep - em);
-    ep = d - dist3(px, py, pz, qx, delta + qy, qz);
-    em = d - dist3(px, py, pz, qx, -delta + qy, qz);
+    ep = d - dist3m<M>(px, py, pz, qx, delta + qy, qz, bad);
+    em = d - dist3m<M>(px, py, pz, qx, -delta + qy, qz, bad);
     J[1] = scalar * (ep - em);
-    ep = d - dist3(px, py, pz, qx, qy, delta + qz);
-    em = d - dist3(px, py, pz, qx, qy, -delta + qz);
+    ep = d - dist3m<M>(px, py, pz, qx, qy, delta + qz, bad);
+    em = d - dist3m<M>(px, py, pz, qx, qy, -delta + qz, bad);
     J[2] = scalar * (ep - em);
 }
 
@@ -414,11 +420,14 @@ UWBGO_DI void fast_solve_chi(const FastEnv &E, bool ok, double lambda, const dou
 /* chains of the numeric Jacobians fill the issue slots of the sqrt/div dependency chain of the   */
 /* 3x3 potrf.  Same arithmetic, same order, same bits as the table-driven FAST path.              */
 /* ------------------------------------------------------------------------------------------ */
+template <class M = IeeeMath>
 UWBGO_DI void chain_weights(const FastEnv &E, double err, double info, bool robust, double &Ow,
-                            double &omega_r)
+                            double &omega_r, unsigned *badp = nullptr)
 {
+    unsigned bl = 0;
+    unsigned &bad = badp ? *badp : bl;
     const double Oe = info * err;
-    const double r1 = E.ck.rho1(err * Oe);
+    const double r1 = E.ck.template rho1m<M>(err * Oe, bad);
     omega_r = robust ? (-Oe) * r1 : -Oe;
     Ow = robust ? r1 * info : info;
 }
@@ -462,26 +471,28 @@ UWBGO_DI void chain_load(const FastEnv &E, const double *__restrict__ T, int i, 
 
 /* H record of pose i from (cx,cy,cz) = t_i and `in`; carry = vertex-0 terms of edge (i, i+1) on
  * entry (zeros at the newest pose: an exact no-op), of edge (i-1, i) on exit */
-template <bool PREV>
+template <bool PREV, class M = IeeeMath>
 UWBGO_DI void chain_build(const FastEnv &E, double cx, double cy, double cz, const ChainIn &in,
-                          double *carry, double *h)
+                          double *carry, double *h, unsigned *badp = nullptr)
 {
+    unsigned bl = 0;
+    unsigned &bad = badp ? *badp : bl;
 #pragma unroll
     for (int k = 0; k < HR_FAST; ++k) h[k] = 0.0;
     double J[3], Ow, omega_r;
     {
         const double qx = ANCH(E, in.anchor * 3), qy = ANCH(E, in.anchor * 3 + 1), qz = ANCH(E, in.anchor * 3 + 2);
-        const double err = in.da - dist3(cx, cy, cz, qx, qy, qz);
-        fast_jac_v0(cx, cy, cz, qx, qy, qz, in.da, E.delta, E.scalar, J);
-        chain_weights(E, err, in.ia, (in.robust & 1) != 0, Ow, omega_r);
+        const double err = in.da - dist3m<M>(cx, cy, cz, qx, qy, qz, bad);
+        fast_jac_v0<M>(cx, cy, cz, qx, qy, qz, in.da, E.delta, E.scalar, J, &bad);
+        chain_weights<M>(E, err, in.ia, (in.robust & 1) != 0, Ow, omega_r, &bad);
         chain_acc(J, Ow, omega_r, h);
     }
     double nA[3] = {0.0, 0.0, 0.0}, nOw = 0.0, nOr = 0.0;
     if (PREV) {
-        const double err = in.dt - dist3(in.px, in.py, in.pz, cx, cy, cz);
-        fast_jac_v0(in.px, in.py, in.pz, cx, cy, cz, in.dt, E.delta, E.scalar, nA);
-        fast_jac_v1(in.px, in.py, in.pz, cx, cy, cz, in.dt, E.delta, E.scalar, J);
-        chain_weights(E, err, in.it, (in.robust & 2) != 0, nOw, nOr);
+        const double err = in.dt - dist3m<M>(in.px, in.py, in.pz, cx, cy, cz, bad);
+        fast_jac_v0<M>(in.px, in.py, in.pz, cx, cy, cz, in.dt, E.delta, E.scalar, nA, &bad);
+        fast_jac_v1<M>(in.px, in.py, in.pz, cx, cy, cz, in.dt, E.delta, E.scalar, J, &bad);
+        chain_weights<M>(E, err, in.it, (in.robust & 2) != 0, nOw, nOr, &bad);
         const double AtO[3] = {nA[0] * nOw, nA[1] * nOw, nA[2] * nOw};
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -500,8 +511,11 @@ UWBGO_DI void chain_store_b(double *__restrict__ l, const double *h)
     for (int k = 0; k < 3; ++k) ROW(l, 12 + k) = h[15 + k];
 }
 
-UWBGO_DI bool chain_factor(const FastEnv &E, const double *__restrict__ T, double lambda)
+template <class M = IeeeMath>
+UWBGO_DI bool chain_factor(const FastEnv &E, const double *__restrict__ T, double lambda, unsigned *badp = nullptr)
 {
+    unsigned bl = 0;
+    unsigned &bad = badp ? *badp : bl;
     const int N = E.tp->N;
     double G[9], zn[3], carry[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     bool ok = true;
@@ -516,15 +530,15 @@ UWBGO_DI bool chain_factor(const FastEnv &E, const double *__restrict__ T, doubl
     ChainIn in, nx;
     if (N == 1) {
         chain_load<false>(E, T, 0, in);
-        chain_build<false>(E, cx, cy, cz, in, carry, hc);
-        factor_step<3>(hc, LR, true, false, lambda, G, zn, ok);
+        chain_build<false, M>(E, cx, cy, cz, in, carry, hc, &bad);
+        factor_step<3, M>(hc, LR, true, false, lambda, G, zn, ok, &bad);
         chain_store_b(LR, hc);
         return ok;
     }
     chain_load<true>(E, T, N - 1, in);
     if (N > 2) chain_load<true>(E, T, N - 2, nx);
     else chain_load<false>(E, T, 0, nx);
-    chain_build<true>(E, cx, cy, cz, in, carry, hc);
+    chain_build<true, M>(E, cx, cy, cz, in, carry, hc, &bad);
     cx = in.px; cy = in.py; cz = in.pz;
     in = nx;
     UWBGO_CHAIN_UNROLL_PRAGMA
@@ -540,9 +554,9 @@ UWBGO_DI bool chain_factor(const FastEnv &E, const double *__restrict__ T, doubl
             prefetch_l2(E.p.rd + (size_t)(2 * j + 1) * TILE);
             prefetch_l2(E.p.ri + (size_t)(2 * j + 1) * TILE);
         }
-        chain_build<true>(E, cx, cy, cz, in, carry, hn);
+        chain_build<true, M>(E, cx, cy, cz, in, carry, hn, &bad);
         double *l = LR + (size_t)i * LR_FAST * TILE;
-        factor_step<3>(hc, l, true, true, lambda, G, zn, ok);
+        factor_step<3, M>(hc, l, true, true, lambda, G, zn, ok, &bad);
         chain_store_b(l, hc);
 #pragma unroll
         for (int k = 0; k < HR_FAST; ++k) hc[k] = hn[k];
@@ -550,13 +564,13 @@ UWBGO_DI bool chain_factor(const FastEnv &E, const double *__restrict__ T, doubl
         in = nx;
     }
     /* i == 1: pose 0 has no predecessor */
-    chain_build<false>(E, cx, cy, cz, in, carry, hn);
+    chain_build<false, M>(E, cx, cy, cz, in, carry, hn, &bad);
     {
         double *l = LR + (size_t)LR_FAST * TILE;
-        factor_step<3>(hc, l, true, true, lambda, G, zn, ok);
+        factor_step<3, M>(hc, l, true, true, lambda, G, zn, ok, &bad);
         chain_store_b(l, hc);
     }
-    factor_step<3>(hn, LR, true, false, lambda, G, zn, ok);
+    factor_step<3, M>(hn, LR, true, false, lambda, G, zn, ok, &bad);
     chain_store_b(LR, hn);
     return ok;
 }
@@ -589,10 +603,13 @@ UWBGO_DI void chain_sub_load(const FastEnv &E, const double *__restrict__ Tc, in
     }
 }
 
+template <class M = IeeeMath>
 UWBGO_DI void chain_solve_chi(const FastEnv &E, bool ok, double lambda, const double *__restrict__ Tc,
                               double *__restrict__ Tn, double &scale_out, double &plain,
-                              double &robust)
+                              double &robust, unsigned *badp = nullptr)
 {
+    unsigned bl = 0;
+    unsigned &bad = badp ? *badp : bl;
     const int N = E.tp->N;
     double xp[3] = {0.0, 0.0, 0.0};
     double scale = 0.0, p = 0.0, r = 0.0;
@@ -619,17 +636,17 @@ UWBGO_DI void chain_solve_chi(const FastEnv &E, bool ok, double lambda, const do
         double *to = Tn + (size_t)i * 3 * TILE;
         ROW(to, 0) = cx; ROW(to, 1) = cy; ROW(to, 2) = cz;
         {
-            const double err = cur.da - dist3(cx, cy, cz, ANCH(E, cur.anchor * 3), ANCH(E, cur.anchor * 3 + 1),
-                                              ANCH(E, cur.anchor * 3 + 2));
+            const double err = cur.da - dist3m<M>(cx, cy, cz, ANCH(E, cur.anchor * 3), ANCH(E, cur.anchor * 3 + 1),
+                                                  ANCH(E, cur.anchor * 3 + 2), bad);
             const double chi = err * (cur.ia * err);
             p = p + chi;
-            r = r + ((cur.robust & 1) ? E.ck.rho0(chi) : chi);
+            r = r + ((cur.robust & 1) ? E.ck.template rho0m<M>(chi, bad) : chi);
         }
         if (i > 0) {
-            const double err = cur.dt - dist3(vx, vy, vz, cx, cy, cz);
+            const double err = cur.dt - dist3m<M>(vx, vy, vz, cx, cy, cz, bad);
             const double chi = err * (cur.it * err);
             p = p + chi;
-            r = r + ((cur.robust & 2) ? E.ck.rho0(chi) : chi);
+            r = r + ((cur.robust & 2) ? E.ck.template rho0m<M>(chi, bad) : chi);
         }
         vx = cx; vy = cy; vz = cz;
         cur = nxt;

@@ -137,6 +137,8 @@ cudaError_t launch_factor_solve(int32_t N, int64_t W, const double *H_diag, cons
                                 double *scratch, cudaStream_t st);
 size_t factor_solve_scratch_bytes(int32_t N, int64_t W);
 cudaError_t launch_fp64_peak(double *out, int iters, cudaStream_t st, int *blocks, int *threads);
+cudaError_t launch_math_selftest(unsigned long long seed, int blocks, int per_thread, int mode,
+                                 unsigned long long *counts, cudaStream_t st);
 
 __host__ __device__ inline int64_t n_tiles(int64_t W) { return (W + TILE - 1) / TILE; }
 

@@ -50,8 +50,16 @@ struct Path<2> {
     UWBGO_DI double linearize(int buf) const { return fast_linearize<SINK_NONE>(E, E.p.T(buf)); }
     UWBGO_DI bool trial(double lambda, int from, int to, double &scale, double &p, double &r) const
     {
-        bool ok = chain_factor(E, E.p.T(from), lambda) && (lambda > 0.0);
-        chain_solve_chi(E, ok, lambda, E.p.T(from), E.p.T(to), scale, p, r);
+        /* branch-free arithmetic first; operands outside its safe range (never in sane data) raise
+         * `bad` and the trial -- which only writes L records and the trial estimates -- runs again
+         * with the IEEE sequences */
+        unsigned bad = 0;
+        bool ok = chain_factor<NbMath>(E, E.p.T(from), lambda, &bad) && (lambda > 0.0);
+        chain_solve_chi<NbMath>(E, ok, lambda, E.p.T(from), E.p.T(to), scale, p, r, &bad);
+        if (bad) {
+            ok = chain_factor<IeeeMath>(E, E.p.T(from), lambda) && (lambda > 0.0);
+            chain_solve_chi<IeeeMath>(E, ok, lambda, E.p.T(from), E.p.T(to), scale, p, r);
+        }
         return ok;
     }
 };
@@ -257,6 +265,7 @@ struct WsShared {
     double chi[2][TILE];     /* P -> C: plain and robust chi2 of the trial                        */
     int cur[TILE];           /* C -> P: which pose buffer is current                              */
     int act[TILE];           /* C -> P: window still being optimised                              */
+    unsigned bad[2];         /* per warp: some active lane left the safe range of NbMath          */
     double stash[STASH_PER_THREAD][TILE];
 };
 
@@ -306,6 +315,17 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
         ws_barrier(); /* everybody has read act/cur before the chain warp may overwrite them */
         const double *Tc = E.p.T(c);
         double *Tn = E.p.T(c ^ 1);
+        bool ok = true;
+        double scale = 0.0;
+        /* one trial = factor phase + substitution phase of both warps.  It only writes the L records,
+         * the trial estimates and the shared hand-off buffers, so it can be repeated: first with the
+         * branch-free arithmetic (NbMath), and -- when any active lane of the tile saw an operand
+         * outside NbMath's safe range -- once more with the IEEE sequences. */
+        auto trial = [&](auto math_tag) {
+        using M = decltype(math_tag);
+        unsigned bad = 0;
+        ok = true;
+        scale = 0.0;
         if (warp == 0) {
             /* ---------------- edge warp, factor phase: edges (i-1, i), i = N-1 .. 1 ---------------- */
             {
@@ -340,10 +360,10 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
                             prefetch_l2(E.p.ri + (size_t)(2 * j) * TILE);
                         }
                         double A[3], B[3], Ow, omega_r;
-                        const double err = dt - dist3(px, py, pz, cx, cy, cz);
-                        fast_jac_v0(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, A);
-                        fast_jac_v1(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, B);
-                        chain_weights(E, err, it_, (rob & 2) != 0, Ow, omega_r);
+                        const double err = dt - dist3m<M>(px, py, pz, cx, cy, cz, bad);
+                        fast_jac_v0<M>(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, A, &bad);
+                        fast_jac_v1<M>(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, B, &bad);
+                        chain_weights<M>(E, err, it_, (rob & 2) != 0, Ow, omega_r, &bad);
                         double(*o)[TILE] = sh.traj[k & 1];
                         o[0][lane] = A[0]; o[1][lane] = A[1]; o[2][lane] = A[2];
                         o[3][lane] = B[0]; o[4][lane] = B[1]; o[5][lane] = B[2];
@@ -384,16 +404,16 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
                         const double(*tn)[TILE] = sh.tnew[i & 1];
                         const double cx = tn[0][lane], cy = tn[1][lane], cz = tn[2][lane];
                         {
-                            const double err = da - dist3(cx, cy, cz, qx, qy, qz);
+                            const double err = da - dist3m<M>(cx, cy, cz, qx, qy, qz, bad);
                             const double chi = err * (ia * err);
                             p = p + chi;
-                            r = r + ((tb.y & 1) ? E.ck.rho0(chi) : chi);
+                            r = r + ((tb.y & 1) ? E.ck.template rho0m<M>(chi, bad) : chi);
                         }
                         if (i > 0) {
-                            const double err = dt - dist3(vx, vy, vz, cx, cy, cz);
+                            const double err = dt - dist3m<M>(vx, vy, vz, cx, cy, cz, bad);
                             const double chi = err * (it_ * err);
                             p = p + chi;
-                            r = r + ((tb.y & 2) ? E.ck.rho0(chi) : chi);
+                            r = r + ((tb.y & 2) ? E.ck.template rho0m<M>(chi, bad) : chi);
                         }
                         vx = cx; vy = cy; vz = cz;
                         da = nda; ia = nia; dt = ndt; it_ = nit; qx = nqx; qy = nqy; qz = nqz; tb = ntb;
@@ -403,11 +423,8 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
                 sh.chi[0][lane] = p;
                 sh.chi[1][lane] = r;
             }
-            ws_barrier(); /* chi2 published */
-            ws_barrier(); /* LM state published */
         } else {
             /* ---------------- chain warp, factor phase: poses i = N-1 .. 0 ---------------- */
-            bool ok = true;
             {
                 double G[9], zn[3], carry[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -453,9 +470,9 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
                     for (int m = 0; m < HR_FAST; ++m) h[m] = 0.0;
                     {
                         double J[3], Ow, omega_r;
-                        const double err = da - dist3(cx, cy, cz, qx, qy, qz);
-                        fast_jac_v0(cx, cy, cz, qx, qy, qz, da, E.delta, E.scalar, J);
-                        chain_weights(E, err, ia, (rob & 1) != 0, Ow, omega_r);
+                        const double err = da - dist3m<M>(cx, cy, cz, qx, qy, qz, bad);
+                        fast_jac_v0<M>(cx, cy, cz, qx, qy, qz, da, E.delta, E.scalar, J, &bad);
+                        chain_weights<M>(E, err, ia, (rob & 1) != 0, Ow, omega_r, &bad);
                         chain_acc(J, Ow, omega_r, h);
                     }
                     double nA[3] = {0.0, 0.0, 0.0}, nOw = 0.0, nOr = 0.0;
@@ -476,7 +493,7 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
                     carry[0] = nA[0]; carry[1] = nA[1]; carry[2] = nA[2]; carry[3] = nOw; carry[4] = nOr;
                     /* tail / finished lanes write to a scratch record of their own window: harmless */
                     double *l = E.p.LR + (size_t)i * LR_FAST * TILE;
-                    factor_step<3>(h, l, true, i > 0, lambda, G, zn, ok);
+                    factor_step<3, M>(h, l, true, i > 0, lambda, G, zn, ok, &bad);
                     chain_store_b(l, h);
                     cx = ncx; cy = ncy; cz = ncz; da = nda; ia = nia; qx = nqx; qy = nqy; qz = nqz; rob = nrob;
                     ws_barrier();
@@ -484,7 +501,6 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
                 ok = ok && (lambda > 0.0);
             }
             /* ---------------- chain warp, substitution phase ---------------- */
-            double scale = 0.0;
             {
                 double xp[3] = {0.0, 0.0, 0.0};
                 double l[LR_FAST], nl[LR_FAST], t[3], nt[3];
@@ -526,7 +542,16 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
                     ws_barrier();
                 }
             }
-            ws_barrier(); /* chi2 published by the edge warp */
+        }
+        const unsigned wb = __ballot_sync(0xffffffffu, act && bad != 0u);
+        if (lane == 0) sh.bad[warp] = wb;
+        ws_barrier(); /* chi2 and the range flags published */
+        };
+        trial(NbMath{});
+        if (sh.bad[0] | sh.bad[1]) trial(IeeeMath{}); /* uniform over the CTA */
+        if (warp == 0) {
+            ws_barrier(); /* LM state published */
+        } else {
             if (act) {
                 const double tplain = sh.chi[0][lane];
                 double tempChi = sh.chi[1][lane];
@@ -988,6 +1013,70 @@ cudaError_t launch_fp64_peak(double *out, int iters, cudaStream_t st, int *block
     *blocks = sms * 8;
     *threads = 256;
     fp64_peak_kernel<<<*blocks, *threads, 0, st>>>(out, iters);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Arithmetic self-test: NbMath against the IEEE operations on pseudo-random operands.           */
+/* counts[0] operands tried, [1] results that differ in bits while NbMath did not raise its flag  */
+/* (must be 0), [2] operands flagged (fall back to IEEE in the solver).                          */
+/* mode 0: operands spread over the whole binary64 encoding space (every exponent, both signs,     */
+/* NaN / inf / denormals); mode 1: magnitudes the solver sees (2^-60 .. 2^60).                    */
+/* ------------------------------------------------------------------------------------------ */
+UWBGO_DI unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+UWBGO_DI double selftest_operand(unsigned long long r, int mode)
+{
+    if (mode == 0) return __longlong_as_double((long long)r);
+    const unsigned long long mant = r & 0x000fffffffffffffULL;
+    const unsigned long long e = 1023ULL - 60ULL + ((r >> 52) % 121ULL);
+    const unsigned long long sign = (r >> 63) << 63;
+    return __longlong_as_double((long long)(sign | (e << 52) | mant));
+}
+UWBGO_DI bool same_bits(double a, double b)
+{
+    if (a != a && b != b) return true; /* NaN payloads are not part of the contract */
+    return __double_as_longlong(a) == __double_as_longlong(b);
+}
+__global__ void __launch_bounds__(256) math_selftest_kernel(unsigned long long seed, int per_thread, int mode,
+                                                           unsigned long long *counts)
+{
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long tried = 0, wrong = 0, flagged = 0;
+    for (int k = 0; k < per_thread; ++k) {
+        const unsigned long long r0 = mix64(seed ^ (tid * 0x100000001b3ULL + (unsigned long long)k * 2ULL));
+        const unsigned long long r1 = mix64(r0 ^ 0x5851f42d4c957f2dULL);
+        const double a = selftest_operand(r0, mode), b = selftest_operand(r1, mode);
+        const double xs = mode == 1 ? fabs(a) : a;
+        unsigned bad;
+        bad = 0;
+        const double s = NbMath::sqrt_(xs, bad);
+        if (bad) ++flagged; else if (!same_bits(s, sqrt(xs))) ++wrong;
+        bad = 0;
+        const double rc = NbMath::rcp(b, bad);
+        if (bad) ++flagged; else if (!same_bits(rc, 1.0 / b)) ++wrong;
+        bad = 0;
+        const double q = NbMath::div(a, b, bad);
+        if (bad) ++flagged; else if (!same_bits(q, a / b)) ++wrong;
+        bad = 0;
+        const double lg = NbMath::log_(xs, bad);
+        if (bad) ++flagged; else if (!same_bits(lg, det_log(xs))) ++wrong;
+        tried += 4;
+    }
+    atomicAdd(counts + 0, tried);
+    atomicAdd(counts + 1, wrong);
+    atomicAdd(counts + 2, flagged);
+}
+
+cudaError_t launch_math_selftest(unsigned long long seed, int blocks, int per_thread, int mode,
+                                 unsigned long long *counts, cudaStream_t st)
+{
+    math_selftest_kernel<<<blocks, 256, 0, st>>>(seed, per_thread, mode, counts);
     return cudaGetLastError();
 }
 

@@ -135,6 +135,13 @@ class Solver:
         return float(flops), float(ms.value)
 
 
+    def selftest_math(self, n_operands: int, mode: int = 0, seed: int = 1):
+        """uwbgo_selftest_math: (compared, mismatching, flagged) counts."""
+        counts = (C.c_int64 * 3)()
+        self._check(self._lib.uwbgo_selftest_math(self._h, seed, n_operands, mode, counts))
+        return int(counts[0]), int(counts[1]), int(counts[2])
+
+
 class _PinnedOwner:
     def __init__(self, lib, ptr):
         self._lib, self._ptr = lib, ptr

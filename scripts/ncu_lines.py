@@ -10,7 +10,8 @@ for r in rows[h + 1:]:
     if len(r) < len(hdr): continue
     try: samples.append((float(r[ci["# Samples"]] or 0), float(r[ci["Instructions Executed"]] or 0), float(r[ci["stall_long_sb"]] or 0), r[ci["Source"]]))
     except ValueError: pass
-subprocess.run(["cuobjdump", "-xelf", "all", so], cwd="/tmp", capture_output=True)
+import os
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd="/tmp", capture_output=True)
 import glob
 cubin = sorted(glob.glob("/tmp/*uwbgo_kernels*.cubin"))[-1]
 dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout

@@ -429,3 +429,39 @@ def test_abi_error_paths(solver):
         solver.set_pipeline(8, 1)
     got = solver.solve(topo, batch, cfg)                                            # context still healthy
     assert_parity(got, oracle.solve(topo, batch, cfg))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_branch_free_arithmetic_matches_ieee(solver, mode):
+    """The CHAIN kernels' branch-free sqrt / reciprocal / division / log sequences (NbMath) return the
+    bits of the IEEE operations whenever they do not flag their operand; flagged operands make the
+    solver re-run the trial with the IEEE operations.  2^28 operands per mode."""
+    compared, wrong, flagged = solver.selftest_math(1 << 28, mode=mode, seed=20260101 + mode)
+    assert compared >= 1 << 28
+    assert wrong == 0
+    if mode == 1:
+        assert flagged == 0          # magnitudes the solver works with never leave the fast path
+    else:
+        assert 0 < flagged < compared  # NaN / inf / denormal / extreme exponents are flagged
+
+
+def test_coincident_points_and_extreme_magnitudes(solver):
+    """sqrt(0) (poses initialised on top of each other, a pose on an anchor) stays on the branch-free
+    arithmetic; denormal-scale and huge coordinates leave its safe range and the trial is re-run with
+    the IEEE operations -- both bit-identical to the oracle, window by window inside one tile."""
+    topo, batch, _ = synthetic.uwb_only(64, 12, 4, seed=43)
+    cfg = Config(max_iterations=5)
+    batch.pose_t[0, :, :] = batch.pose_t[0, 0, :]            # all poses of the window coincide
+    batch.pose_t[1, 3, :] = batch.anchors[1, 0, :]                    # a pose sits on anchor 0
+    batch.pose_t[2] *= 1e-160                                # squares underflow to denormals / zero
+    batch.anchors[2] *= 1e-160
+    batch.range_d[2] *= 1e-160
+    batch.pose_t[3] *= 1e150                                 # squares overflow
+    batch.anchors[3] *= 1e150
+    batch.range_info[4] *= 1e-300                            # denormal-scale weights
+    got = solver.solve(topo, batch, cfg)
+    ref = oracle.solve(topo, batch, cfg)
+    assert np.array_equal(got.status, ref.status)
+    assert np.array_equal(got.pose_t, ref.pose_t, equal_nan=True)
+    assert np.array_equal(got.chi2, ref.chi2, equal_nan=True)

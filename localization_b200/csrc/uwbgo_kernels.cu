@@ -620,6 +620,10 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
     }
 }
 
+}  // namespace uwbgo
+#include "uwbgo_chain_tma.cuh"
+namespace uwbgo {
+
 /* antenna lever arms: a handful of doubles every range edge reads -> shared memory, loaded once */
 constexpr int MAX_SMEM_ANTENNAS = 16;
 UWBGO_DI void gen_env_init(GenEnv &E, const DevTopo &tp, const DevCfg &cfg, const DevWs &ws, int64_t w,
@@ -822,6 +826,13 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
 #ifndef UWBGO_CHAIN_WS
 #define UWBGO_CHAIN_WS 1 /* 1: warp-specialised CHAIN kernel, 0: single-warp CHAIN kernel */
 #endif
+#ifndef UWBGO_CHAIN_TMA
+#define UWBGO_CHAIN_TMA 1 /* 1: operands of the warp-specialised CHAIN kernel staged by the copy engine */
+#endif
+        if (topo.fast == 2 && UWBGO_CHAIN_WS && UWBGO_CHAIN_TMA) {
+            lm_chain_tma_kernel<<<(unsigned)n_tiles(ws.W), 64, 0, st>>>(topo, cfg, ws);
+            return cudaGetLastError();
+        }
         if (topo.fast == 2 && UWBGO_CHAIN_WS) {
             lm_chain_ws_kernel<<<(unsigned)n_tiles(ws.W), 64, 0, st>>>(topo, cfg, ws);
             return cudaGetLastError();

@@ -46,7 +46,14 @@ for r in rows[h + 1:]:
         pass
 tot = sum(d[0] for d in data) or 1
 print("=" * 100)
-print(f"hottest SASS instructions by warp-stall samples (total {tot:.0f}); lsb = long scoreboard")
+print(f"hottest SASS instructions by warp-stall samples (total {tot:.0f}); top two stall reasons each")
+reasons = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
+agg = {n: 0.0 for n in reasons}
+for samp, r in data:
+    for n in reasons:
+        agg[n] += float(r[ci[n]] or 0)
+print("kernel-wide stall samples: " + ", ".join(f"{n[6:]}={v / tot * 100:.1f}%" for n, v in sorted(agg.items(), key=lambda x: -x[1]) if v / tot > 0.005))
 for samp, r in sorted(data, key=lambda x: -x[0])[:topn]:
-    print(f"{samp / tot * 100:5.1f}%  lsb={r[ci['stall_long_sb']]:>6} wait={r[ci['stall_wait']]:>6} "
-          f"execs={r[ci['Instructions Executed']]:>10}  {r[ci['Source']][:90]}")
+    top = sorted(((float(r[ci[n]] or 0), n[6:]) for n in reasons), reverse=True)[:2]
+    why = " ".join(f"{n}={v:.0f}" for v, n in top if v > 0)
+    print(f"{samp / tot * 100:5.1f}%  execs={r[ci['Instructions Executed']]:>10}  {r[ci['Source']][:70]:70s} {why}")

@@ -223,15 +223,17 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
     double lambda = 0.0, ni = 2.0, stale = 0.0, plainCur = 0.0, currentChi = 0.0, rho = 0.0;
     int iterations = 0, trials_total = 0, flags = 0, qlast = 0, q = 0, it = 0, cur = 0;
     bool done = !valid || cfg.max_iterations <= 0;
+    double maxdiag = 0.0;
     if (warp == 1) {
-        fast_chi_pass(E, E.p.T0, plainCur, currentChi);
-        stale = plainCur;
-        const double maxdiag = fast_linearize<SINK_NONE>(E, E.p.T0);
-        if (cfg.max_iterations > 0) lambda = cfg.tau * maxdiag;
-        sh.act[lane] = done ? 0 : 1;
+        sh.act[lane] = valid ? 1 : 0;
         sh.cur[lane] = 0;
     }
     __syncthreads();
+    /* The first pass of the loop below is not a trial but the initial evaluation, run through the same
+     * two-warp machinery: its factor sweep yields max diag(H) (g2o's computeLambdaInit), its
+     * substitution sweep is forced to x = 0 so that the edge warp's chi2 is the chi2 of the initial
+     * estimate. */
+    bool init = true;
     unsigned ev = 0;       /* factor steps so far: buffer = ev & 1, mbarrier parity = (ev >> 1) & 1 */
     int sslot = 0;         /* substitution ring: slot of the next step to consume ...               */
     unsigned spar = 0;     /* ... and the parity to wait for, one bit per slot                      */
@@ -252,6 +254,8 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
             unsigned bad = 0;
             ok = true;
             scale = 0.0;
+            maxdiag = 0.0;
+            const double lam = init ? 1.0 : lambda;
             /* ================= factor sweep: steps k = 0 .. N ================= */
             if (issuerF) issue_factor_step(tp, g, sh, N, 0, ev);
             {
@@ -278,10 +282,8 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
                             const double px = tp_[0][lane], py = tp_[1][lane], pz = tp_[2][lane];
                             const double dt = sh.in.f.D[b][0][lane], it_ = sh.in.f.I[b][0][lane];
                             const int rob = __ldg(&tp.chain[i].robust);
-                            double A[3], B[3], Ow, omega_r;
-                            const double err = dt - dist3m<M>(px, py, pz, cx, cy, cz, bad);
-                            fast_jac_v0<M>(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, A, &bad);
-                            fast_jac_v1<M>(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, B, &bad);
+                            double A[3], B[3], Ow, omega_r, err;
+                            range_linearize<M, true, true>(px, py, pz, cx, cy, cz, dt, E.delta, E.scalar, err, A, B, bad);
                             chain_weights<M>(E, err, it_, (rob & 2) != 0, Ow, omega_r, &bad);
                             double(*o)[TILE] = sh.traj[k & 1];
                             o[0][lane] = A[0]; o[1][lane] = A[1]; o[2][lane] = A[2];
@@ -301,9 +303,8 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
 #pragma unroll
                         for (int m = 0; m < HR_FAST; ++m) h[m] = 0.0;
                         {
-                            double J[3], Ow, omega_r;
-                            const double err = da - dist3m<M>(px, py, pz, qx, qy, qz, bad);
-                            fast_jac_v0<M>(px, py, pz, qx, qy, qz, da, E.delta, E.scalar, J, &bad);
+                            double J[3], Ow, omega_r, err;
+                            range_linearize<M, true, false>(px, py, pz, qx, qy, qz, da, E.delta, E.scalar, err, J, nullptr, bad);
                             chain_weights<M>(E, err, ia, (rob & 1) != 0, Ow, omega_r, &bad);
                             chain_acc(J, Ow, omega_r, h);
                         }
@@ -323,8 +324,14 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
                         }
                         chain_acc(carry, carry[3], carry[4], h);
                         carry[0] = nA[0]; carry[1] = nA[1]; carry[2] = nA[2]; carry[3] = nOw; carry[4] = nOr;
+                        if (init) {
+                            double v;
+                            v = fabs(h[0]); if (v > maxdiag) maxdiag = v;
+                            v = fabs(h[3]); if (v > maxdiag) maxdiag = v;
+                            v = fabs(h[5]); if (v > maxdiag) maxdiag = v;
+                        }
                         double *l = &sh.in.f.L[k & 1][0][lane];
-                        factor_step<3, M>(h, l, true, i > 0, lambda, G, zn, ok, &bad);
+                        factor_step<3, M>(h, l, true, i > 0, lam, G, zn, ok, &bad);
                         chain_store_b(l, h);
                         fence_async_smem();
                         __syncwarp();
@@ -335,7 +342,7 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
                     }
                     tma_barrier();
                 }
-                ok = ok && (lambda > 0.0);
+                ok = !init && ok && (lambda > 0.0);
             }
             ev += (unsigned)N + 1u;
             /* ================= substitution sweep: steps k = 0 .. N, fetched two steps ahead ================= */
@@ -372,7 +379,7 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
                             subst_step<3>(l, i > 0, xp);
                             if (!ok) xp[0] = xp[1] = xp[2] = 0.0;
 #pragma unroll
-                            for (int m = 0; m < 3; ++m) scale = scale + xp[m] * (lambda * xp[m] + l[12 + m]);
+                            for (int m = 0; m < 3; ++m) scale = scale + xp[m] * (lam * xp[m] + l[12 + m]);
                             const double nx = xp[0] + t0, ny = xp[1] + t1, nz = xp[2] + t2;
                             double(*o)[TILE] = sh.tnew[i & 1];
                             o[0][lane] = nx; o[1][lane] = ny; o[2][lane] = nz;
@@ -416,7 +423,14 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
         };
         trial(NbMath{});
         if (sh.bad[0] | sh.bad[1]) trial(IeeeMath{}); /* uniform over the CTA */
-        if (warp == 1) {
+        if (warp == 1 && init) {
+            plainCur = sh.chi[0][lane];
+            currentChi = sh.chi[1][lane];
+            stale = plainCur;
+            if (cfg.max_iterations > 0) lambda = cfg.tau * maxdiag;
+            sh.act[lane] = done ? 0 : 1;
+            fence_async_all();
+        } else if (warp == 1) {
             if (act) {
                 const double tplain = sh.chi[0][lane];
                 double tempChi = sh.chi[1][lane];
@@ -461,6 +475,7 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
             fence_async_all(); /* the copy engine reads the trial estimates of this sweep in the next trial */
         }
         tma_barrier(); /* LM state published */
+        init = false;
     }
     if (warp == 1 && valid) {
         const int64_t tile = w / TILE;

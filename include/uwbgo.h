@@ -129,7 +129,7 @@ void uwbgo_destroy(uwbgo_ctx *ctx);
 const char *uwbgo_last_error(void);
 
 /* Tuning of the host-pointer entry points: windows per pipeline chunk (rounded up to 32) and
- * number of concurrent stream lanes (1..8).  Defaults: 16384 windows, 4 lanes. */
+ * number of concurrent stream lanes (1..8).  Defaults: 8192 windows, 8 lanes. */
 int  uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes);
 /* Page-locked host memory.  The host-pointer entry points accept any host memory; with buffers
  * from uwbgo_host_alloc their copies overlap the kernels of neighbouring chunks. */
@@ -185,9 +185,11 @@ int     uwbgo_last_path(const uwbgo_ctx *ctx);
  * on its stream immediately before and after its main kernel (the fused LM kernel of
  * uwbgo_solve_batch_device; the linearisation kernel plus the expansion of H to the public
  * full-block layout for uwbgo_linearize_batch_device);
- * uwbgo_last_kernel_ms waits for the last such kernel and returns its duration (-1 if none). */
+ * uwbgo_last_kernel_ms waits for the last such kernel and returns its duration (-1 if none);
+ * uwbgo_mean_kernel_ms averages the durations of the last `last_n` (<= 64) such calls. */
 int     uwbgo_set_profiling(uwbgo_ctx *ctx, int on);
 double  uwbgo_last_kernel_ms(uwbgo_ctx *ctx);
+double  uwbgo_mean_kernel_ms(uwbgo_ctx *ctx, int last_n);
 /* FP64 FMA micro-benchmark on the context's GPU: returns achieved FP64 FLOP/s (2 per FMA),
  * used as the measured FP64 roofline denominator (MEASURED_PEAKS.json has none). */
 double  uwbgo_measure_fp64_peak(uwbgo_ctx *ctx, double *elapsed_ms);

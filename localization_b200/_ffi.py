@@ -87,6 +87,7 @@ SYMBOLS = {
     "uwbgo_last_path": (C.c_int, [_vp]),
     "uwbgo_set_profiling": (C.c_int, [_vp, C.c_int]),
     "uwbgo_last_kernel_ms": (C.c_double, [_vp]),
+    "uwbgo_mean_kernel_ms": (C.c_double, [_vp, C.c_int]),
     "uwbgo_measure_fp64_peak": (C.c_double, [_vp, _pd]),
     "uwbgo_selftest_math": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
 }

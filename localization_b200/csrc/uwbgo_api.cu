@@ -92,8 +92,8 @@ constexpr int MAX_LANES = 8;
 
 struct uwbgo_ctx {
     int device = 0;
-    int n_lanes = 4;
-    int64_t chunk = 16384;
+    int n_lanes = 8;
+    int64_t chunk = 8192;
     Lane lane[MAX_LANES];
     DevBuf misc;          /* staging of the stand-alone factor/solve call, FP64 peak probe */
     DevBuf ant;
@@ -104,8 +104,9 @@ struct uwbgo_ctx {
     cudaEvent_t ws_free = nullptr; /* completion of the last user-stream call on lane 0's workspace */
     bool ws_pending = false;
     bool profile = false;          /* bracket the main kernel of device-API calls with events */
-    cudaEvent_t k0 = nullptr, k1 = nullptr;
-    bool k_valid = false;
+    static constexpr int K_RING = 64; /* event pairs of the last profiled calls */
+    cudaEvent_t k0[K_RING] = {}, k1[K_RING] = {};
+    int64_t k_count = 0;           /* profiled calls since profiling was switched on */
 };
 
 namespace {
@@ -496,16 +497,17 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     XposeJobs uj{};
     uj.W = W;
     const bool timed = ctx->profile && &ln == &ctx->lane[0];
-    if (timed) CU(cudaEventRecord(ctx->k0, st));
+    const int kslot = (int)(ctx->k_count % uwbgo_ctx::K_RING);
+    if (timed) CU(cudaEventRecord(ctx->k0[kslot], st));
     if (so) {
         CU(launch_linearize(tp, cfg, ws, st));
         CU(launch_expand_H(tp, ws, so->H_diag, so->H_off, so->b, st));
-        if (timed) CU(cudaEventRecord(ctx->k1, st)); /* stage = linearise + expansion to the public layout */
+        if (timed) CU(cudaEventRecord(ctx->k1[kslot], st)); /* stage = linearise + expansion to the public layout */
         ctx->launches += 2;
         if (so->chi2) add(uj, ws.chi2, so->chi2, 2, 8, 0);
     } else {
         CU(launch_solve(tp, cfg, ws, st));
-        if (timed) CU(cudaEventRecord(ctx->k1, st));
+        if (timed) CU(cudaEventRecord(ctx->k1[kslot], st));
         ctx->launches += 1;
         add(uj, ws.T[0], out->pose_t, tp.N * 3, 8, 0);
         if (out->pose_R) {
@@ -523,7 +525,7 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
         ctx->launches += 1;
     }
     ctx->last_path = fast ? tp.fast : 0;
-    if (timed) ctx->k_valid = true;
+    if (timed) ctx->k_count += 1;
     return 0;
 }
 
@@ -604,8 +606,10 @@ int uwbgo_create(int device, uwbgo_ctx **out)
         }
     }
     e = cudaEventCreateWithFlags(&ctx->ws_free, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreate(&ctx->k0);
-    if (e == cudaSuccess) e = cudaEventCreate(&ctx->k1);
+    for (int k = 0; k < uwbgo_ctx::K_RING; ++k) {
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->k0[k]);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->k1[k]);
+    }
     if (e != cudaSuccess) {
         uwbgo_destroy(ctx);
         return fail_cuda(e, "event creation");
@@ -628,8 +632,10 @@ void uwbgo_destroy(uwbgo_ctx *ctx)
     ctx->ant.release();
     for (auto &t : ctx->topos) cudaFree(t->dmem);
     if (ctx->ws_free) cudaEventDestroy(ctx->ws_free);
-    if (ctx->k0) cudaEventDestroy(ctx->k0);
-    if (ctx->k1) cudaEventDestroy(ctx->k1);
+    for (int k = 0; k < uwbgo_ctx::K_RING; ++k) {
+        if (ctx->k0[k]) cudaEventDestroy(ctx->k0[k]);
+        if (ctx->k1[k]) cudaEventDestroy(ctx->k1[k]);
+    }
     delete ctx;
 }
 
@@ -929,18 +935,26 @@ int uwbgo_set_profiling(uwbgo_ctx *ctx, int on)
 {
     if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
     ctx->profile = on != 0;
-    ctx->k_valid = false;
+    ctx->k_count = 0;
     return 0;
 }
 
-double uwbgo_last_kernel_ms(uwbgo_ctx *ctx)
+double uwbgo_mean_kernel_ms(uwbgo_ctx *ctx, int last_n)
 {
-    if (!ctx || !ctx->k_valid) return -1.0;
-    if (cudaEventSynchronize(ctx->k1) != cudaSuccess) return -1.0;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->k0, ctx->k1) != cudaSuccess) return -1.0;
-    return (double)ms;
+    if (!ctx || ctx->k_count <= 0 || last_n <= 0) return -1.0;
+    const int64_t n = std::min<int64_t>(std::min<int64_t>(last_n, ctx->k_count), uwbgo_ctx::K_RING);
+    double sum = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        const int slot = (int)((ctx->k_count - 1 - j) % uwbgo_ctx::K_RING);
+        if (cudaEventSynchronize(ctx->k1[slot]) != cudaSuccess) return -1.0;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->k0[slot], ctx->k1[slot]) != cudaSuccess) return -1.0;
+        sum += (double)ms;
+    }
+    return sum / (double)n;
 }
+
+double uwbgo_last_kernel_ms(uwbgo_ctx *ctx) { return uwbgo_mean_kernel_ms(ctx, 1); }
 
 int64_t uwbgo_launch_count(const uwbgo_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int uwbgo_last_path(const uwbgo_ctx *ctx) { return ctx ? ctx->last_path : 0; }

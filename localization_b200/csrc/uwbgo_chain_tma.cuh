@@ -60,6 +60,36 @@ UWBGO_DI void bulk_load(void *dst, const void *src, unsigned bytes, unsigned lon
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+/* the same with an L2 eviction policy (createpolicy) for the lines the copy touches */
+UWBGO_DI void bulk_load_hint(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long pol)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+        : "memory");
+}
+UWBGO_DI void bulk_store_hint(void *dst, const void *src, unsigned bytes, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+                 "r"(smem_addr(src)), "r"(bytes), "l"(pol)
+                 : "memory");
+}
+UWBGO_DI unsigned long long l2_policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+UWBGO_DI unsigned long long l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#ifndef UWBGO_TMA_HINTS
+#define UWBGO_TMA_HINTS 0 /* 1: L records evict_last on the way out, evict_first on the way back; 2: also the streamed operands evict_first */
+#endif
 /* shared -> global, tracked by the issuing thread's bulk groups */
 UWBGO_DI void bulk_store(void *dst, const void *src, unsigned bytes)
 {
@@ -80,6 +110,12 @@ UWBGO_DI void bulk_wait()
 /* order this thread's generic-proxy writes before later async-proxy (copy engine) accesses */
 UWBGO_DI void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 UWBGO_DI void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+#define BULK_STREAM(dst, src, bytes, bar) \
+    do { \
+        if (UWBGO_TMA_HINTS >= 2) bulk_load_hint(dst, src, bytes, bar, l2_policy_evict_first()); \
+        else bulk_load(dst, src, bytes, bar); \
+    } while (0)
 
 constexpr unsigned ROW_BYTES = TILE * sizeof(double); /* one row of a tile: 256 B */
 constexpr int TMA_STASH_DOUBLES = 2 * FAST_MAX_CARRY * 5 * TILE;
@@ -134,18 +170,18 @@ UWBGO_DI void issue_factor_step(const DevTopo &tp, const TileBase &g, TmaShared 
     const unsigned bytes = ((jT >= 0 ? 6u : 0u) + (first ? 6u : 0u) + 2u * drows + (first ? 0u : 3u)) * ROW_BYTES;
     mbar_expect_tx(bar, bytes);
     if (first) {
-        bulk_load(sh.in.f.T[(N - 1) & 3][0], g.T0 + (size_t)(N - 1) * 3 * TILE, 3 * ROW_BYTES, bar);
-        bulk_load(sh.in.f.T[(N - 1) & 3][1], g.T1 + (size_t)(N - 1) * 3 * TILE, 3 * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.f.T[(N - 1) & 3][0], g.T0 + (size_t)(N - 1) * 3 * TILE, 3 * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.f.T[(N - 1) & 3][1], g.T1 + (size_t)(N - 1) * 3 * TILE, 3 * ROW_BYTES, bar);
     }
     if (jT >= 0) {
-        bulk_load(sh.in.f.T[jT & 3][0], g.T0 + (size_t)jT * 3 * TILE, 3 * ROW_BYTES, bar);
-        bulk_load(sh.in.f.T[jT & 3][1], g.T1 + (size_t)jT * 3 * TILE, 3 * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.f.T[jT & 3][0], g.T0 + (size_t)jT * 3 * TILE, 3 * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.f.T[jT & 3][1], g.T1 + (size_t)jT * 3 * TILE, 3 * ROW_BYTES, bar);
     }
     {
         /* first: row 2N-2 -> [0]; last: row 0 -> [1]; otherwise rows (2 iC - 2, 2 iC - 1) -> [0], [1] */
         const int r0 = last ? 0 : 2 * iC - 2;
-        bulk_load(sh.in.f.D[b][last ? 1 : 0], g.rd + (size_t)r0 * TILE, drows * ROW_BYTES, bar);
-        bulk_load(sh.in.f.I[b][last ? 1 : 0], g.ri + (size_t)r0 * TILE, drows * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.f.D[b][last ? 1 : 0], g.rd + (size_t)r0 * TILE, drows * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.f.I[b][last ? 1 : 0], g.ri + (size_t)r0 * TILE, drows * ROW_BYTES, bar);
     }
     if (!first) {
         const int anchor = __ldg(&tp.chain[iC].anchor);
@@ -163,15 +199,16 @@ UWBGO_DI void issue_subst_step(const DevTopo &tp, const TileBase &g, TmaShared &
     const unsigned bytes = (doC ? (unsigned)(LR_FAST + 6) : 0u) * ROW_BYTES + (doP ? (2u * prow + 3u) : 0u) * ROW_BYTES;
     mbar_expect_tx(bar, bytes);
     if (doC) {
-        bulk_load(sh.in.s.L[slot], g.LR + (size_t)k * LR_FAST * TILE, LR_FAST * ROW_BYTES, bar);
-        bulk_load(sh.in.s.T[slot][0], g.T0 + (size_t)k * 3 * TILE, 3 * ROW_BYTES, bar);
-        bulk_load(sh.in.s.T[slot][1], g.T1 + (size_t)k * 3 * TILE, 3 * ROW_BYTES, bar);
+        if (UWBGO_TMA_HINTS >= 1) bulk_load_hint(sh.in.s.L[slot], g.LR + (size_t)k * LR_FAST * TILE, LR_FAST * ROW_BYTES, bar, l2_policy_evict_first());
+        else bulk_load(sh.in.s.L[slot], g.LR + (size_t)k * LR_FAST * TILE, LR_FAST * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.s.T[slot][0], g.T0 + (size_t)k * 3 * TILE, 3 * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.s.T[slot][1], g.T1 + (size_t)k * 3 * TILE, 3 * ROW_BYTES, bar);
     }
     if (doP) {
         const int anchor = __ldg(&tp.chain[j].anchor);
         const int r0 = j == 0 ? 0 : 2 * j - 1;
-        bulk_load(sh.in.s.D[slot], g.rd + (size_t)r0 * TILE, prow * ROW_BYTES, bar);
-        bulk_load(sh.in.s.I[slot], g.ri + (size_t)r0 * TILE, prow * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.s.D[slot], g.rd + (size_t)r0 * TILE, prow * ROW_BYTES, bar);
+        BULK_STREAM(sh.in.s.I[slot], g.ri + (size_t)r0 * TILE, prow * ROW_BYTES, bar);
         bulk_load(sh.in.s.A[slot], g.anch + (size_t)anchor * 3 * TILE, 3 * ROW_BYTES, bar);
     }
 }
@@ -336,7 +373,8 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            bulk_store(g.LR + (size_t)i * LR_FAST * TILE, sh.in.f.L[k & 1], LR_FAST * ROW_BYTES);
+                            if (UWBGO_TMA_HINTS >= 1) bulk_store_hint(g.LR + (size_t)i * LR_FAST * TILE, sh.in.f.L[k & 1], LR_FAST * ROW_BYTES, l2_policy_evict_last());
+                            else bulk_store(g.LR + (size_t)i * LR_FAST * TILE, sh.in.f.L[k & 1], LR_FAST * ROW_BYTES);
                             bulk_commit();
                         }
                     }

@@ -129,6 +129,9 @@ class Solver:
     def last_kernel_ms(self) -> float:
         return float(self._lib.uwbgo_last_kernel_ms(self._h))
 
+    def mean_kernel_ms(self, last_n: int) -> float:
+        return float(self._lib.uwbgo_mean_kernel_ms(self._h, int(last_n)))
+
     def measure_fp64_peak(self):
         ms = C.c_double(0.0)
         flops = self._lib.uwbgo_measure_fp64_peak(self._h, C.byref(ms))

@@ -384,7 +384,7 @@ int check_batch(const TopoEntry &te, const uwbgo_batch *in)
 struct TileLayout {
     size_t bytes = 0;
     size_t off_T[2], off_R[2], off_cnt, off_anch, off_rd, off_ri, off_pZ, off_pI, off_sZ, off_sI, off_HB,
-        off_LR, off_chi2, off_status;
+        off_LR, off_chi2, off_status, off_echi;
 };
 TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bool want_LR)
 {
@@ -414,6 +414,7 @@ TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bo
     L.off_LR = want_LR ? take(N * (fast ? LR_FAST : (t.tree ? LR_TREE : LR_GEN)), 8) : 0;
     L.off_chi2 = take(4, 8);
     L.off_status = take(4, 4);
+    L.off_echi = (!fast && want_LR) ? take((size_t)t.E * 2, 8) : 0;
     L.bytes = o;
     return L;
 }
@@ -458,6 +459,7 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     ws.ant = d_ant;
     ws.chi2 = reinterpret_cast<double *>(base + L.off_chi2);
     ws.status = reinterpret_cast<int32_t *>(base + L.off_status);
+    ws.echi = (!fast && !so) ? reinterpret_cast<double *>(base + L.off_echi) : nullptr;
 
     XposeJobs pj{};
     pj.W = W;

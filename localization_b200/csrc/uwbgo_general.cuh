@@ -96,49 +96,110 @@ UWBGO_DI double chi2_6(const double *__restrict__ Irows, int slot, const double 
     return chi;
 }
 
-UWBGO_DI void gen_chi_pass(const GenEnv &E, const PoseBuf &T, double &plain, double &robust)
+/* the 6x6 information matrix of a 6-D edge into registers, ahead of the arithmetic that produces
+ * the error (its IEEE sqrt / division sequences end in branches, which the loads cannot cross) */
+UWBGO_DI void load_info6(const double *__restrict__ Irows, int slot, double *O)
+{
+    const double *p = Irows + (size_t)slot * 36 * TILE;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) O[k] = ROW(p, k);
+}
+UWBGO_DI double chi2_6_reg(const double *O, const double *e, double *Oe)
+{
+    double chi = 0.0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double s = O[6 * r] * e[0];
+#pragma unroll
+        for (int c = 1; c < 6; ++c) s = s + O[6 * r + c] * e[c];
+        Oe[r] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) chi = chi + e[r] * Oe[r];
+    return chi;
+}
+
+/* L2 prefetch of everything the evaluation / linearisation of edge e will read */
+UWBGO_DI void gen_edge_prefetch(const GenEnv &E, const PoseBuf &T, int e)
+{
+    EdgeRec er = load_edge(E.tp->edges + e);
+    prefetch_rows_l2<3>(T.t + (size_t)er.a * 3 * TILE);
+    prefetch_rows_l2<9>(T.R + (size_t)er.a * 9 * TILE);
+    if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
+        prefetch_l2(E.p.rd + (size_t)er.slot * TILE);
+        prefetch_l2(E.p.ri + (size_t)er.slot * TILE);
+        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR)
+            prefetch_rows_l2<3>(E.p.anch + (size_t)er.b * 3 * TILE);
+        else
+            prefetch_rows_l2<3>(T.t + (size_t)er.b * 3 * TILE);
+    } else if (er.kind == UWBGO_EDGE_PRIOR) {
+        prefetch_rows_l2<12>(E.p.pZ + (size_t)er.slot * 12 * TILE);
+        prefetch_rows_l2<36>(E.p.pI + (size_t)er.slot * 36 * TILE);
+    } else {
+        prefetch_rows_l2<3>(T.t + (size_t)er.b * 3 * TILE);
+        prefetch_rows_l2<9>(T.R + (size_t)er.b * 9 * TILE);
+        prefetch_rows_l2<12>(E.p.sZ + (size_t)er.slot * 12 * TILE);
+        prefetch_rows_l2<36>(E.p.sI + (size_t)er.slot * 36 * TILE);
+    }
+}
+
+/* computeError + chi2 of edge e at the estimates T: plain chi2 and its robustified value */
+UWBGO_DI void gen_edge_chi(const GenEnv &E, const PoseBuf &T, int e, double &chi_out, double &rob_out)
 {
     const DevTopo &tp = *E.tp;
-    double p = 0.0, r = 0.0;
-    for (int e = 0; e < tp.E; ++e) {
-        EdgeRec er = load_edge(tp.edges + e);
-        double chi;
-        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
-            Pose Xa;
-            load_pose(T, er.a, Xa);
-            double P0[3], Q[3];
-            offset_point(E, Xa, er.ant, P0);
-            if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
-                const double *an = E.p.anch + (size_t)er.b * 3 * TILE;
-                Q[0] = ROW(an, 0); Q[1] = ROW(an, 1); Q[2] = ROW(an, 2);
-            } else {
-                const double *tb = T.t + (size_t)er.b * 3 * TILE;
-                Q[0] = ROW(tb, 0); Q[1] = ROW(tb, 1); Q[2] = ROW(tb, 2);
-            }
-            double err = ROW(E.p.rd, er.slot) - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
-            double Oe = ROW(E.p.ri, er.slot) * err;
-            chi = err * Oe;
-        } else if (er.kind == UWBGO_EDGE_PRIOR) {
-            Pose Zinv, X, Dl;
-            load_Zinv(E.p.pZ, er.slot, Zinv);
-            load_pose(T, er.a, X);
-            pose_mul(Zinv, X, Dl);
-            double q[4], e6[6], Oe[6];
-            R_to_quat(Dl.R, q);
-            e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
-            e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
-            chi = chi2_6(E.p.pI, er.slot, e6, Oe);
+    EdgeRec er = load_edge(tp.edges + e);
+    double chi;
+    if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
+        Pose Xa;
+        load_pose(T, er.a, Xa);
+        double P0[3], Q[3];
+        offset_point(E, Xa, er.ant, P0);
+        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+            const double *an = E.p.anch + (size_t)er.b * 3 * TILE;
+            Q[0] = ROW(an, 0); Q[1] = ROW(an, 1); Q[2] = ROW(an, 2);
         } else {
-            Pose Zinv, Xi, Xj;
-            load_Zinv(E.p.sZ, er.slot, Zinv);
-            load_pose(T, er.a, Xi);
-            load_pose(T, er.b, Xj);
-            double e6[6], Oe[6];
-            se3_error(Zinv, Xi, Xj, e6);
-            chi = chi2_6(E.p.sI, er.slot, e6, Oe);
+            const double *tb = T.t + (size_t)er.b * 3 * TILE;
+            Q[0] = ROW(tb, 0); Q[1] = ROW(tb, 1); Q[2] = ROW(tb, 2);
         }
+        double err = ROW(E.p.rd, er.slot) - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
+        double Oe = ROW(E.p.ri, er.slot) * err;
+        chi = err * Oe;
+    } else if (er.kind == UWBGO_EDGE_PRIOR) {
+        Pose Zinv, X, Dl;
+        double O[36];
+        load_info6(E.p.pI, er.slot, O);
+        load_pose(T, er.a, X);
+        load_Zinv(E.p.pZ, er.slot, Zinv);
+        pose_mul(Zinv, X, Dl);
+        double q[4], e6[6], Oe[6];
+        R_to_quat(Dl.R, q);
+        e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
+        e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
+        chi = chi2_6_reg(O, e6, Oe);
+    } else {
+        Pose Zinv, Xi, Xj;
+        double O[36];
+        load_info6(E.p.sI, er.slot, O);
+        load_pose(T, er.a, Xi);
+        load_pose(T, er.b, Xj);
+        load_Zinv(E.p.sZ, er.slot, Zinv);
+        double e6[6], Oe[6];
+        se3_error(Zinv, Xi, Xj, e6);
+        chi = chi2_6_reg(O, e6, Oe);
+    }
+    chi_out = chi;
+    rob_out = er.robust ? E.ck.rho0(chi) : chi;
+}
+
+/* computeActiveErrors + activeChi2 / activeRobustChi2: edges summed in insertion order */
+UWBGO_DI void gen_chi_pass(const GenEnv &E, const PoseBuf &T, double &plain, double &robust)
+{
+    double p = 0.0, r = 0.0;
+    for (int e = 0; e < E.tp->E; ++e) {
+        double chi, rob;
+        gen_edge_chi(E, T, e, chi, rob);
         p = p + chi;
-        r = r + (er.robust ? E.ck.rho0(chi) : chi);
+        r = r + rob;
     }
     plain = p;
     robust = r;
@@ -388,14 +449,19 @@ UWBGO_DI void acc6_off(const double *AtO, const double *B, double *ho)
         }
 }
 
-/* BlockSolver::buildSystem, general edges.  Advances the oplus counters by the numeric-Jacobian
- * calls.  Returns max |H_kk|. */
-__device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
+/* BlockSolver::buildSystem for ONE pose: the H record of pose i (H_ii, H_{parent(i),i}, b_i) gathered
+ * from the edges touching it, in insertion order.  Returns max |H_kk| over the pose's diagonal.
+ * Reads the oplus counters, does not advance them.  SWEPT: poses are linearised in ascending order
+ * by one thread that advances each pose's counter right after its record (gen_linearize), so the
+ * counter of an older pose already includes this linearisation's calls; !SWEPT: every counter
+ * still holds its value from before the linearisation (poses linearised concurrently). */
+template <bool SWEPT>
+UWBGO_DI double gen_linearize_pose(const GenEnv &E, const PoseBuf &T, const int i)
 {
     const DevTopo &tp = *E.tp;
-    const int N = tp.N, mod = E.cfg->orth_mod;
+    const int mod = E.cfg->orth_mod;
     double maxdiag = 0.0;
-    for (int i = 0; i < N; ++i) {
+    {
         Pose Xi;
         load_pose(T, i, Xi);
         const int ci = E.p.cnt[(size_t)i * TILE];
@@ -410,6 +476,7 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
         for (int o = ob; o < oe; ++o) {
             int2 op = __ldg(reinterpret_cast<const int2 *>(tp.ops + o));
             EdgeRec er = load_edge(tp.edges + op.x);
+            if (!SWEPT && o + 1 < oe) gen_edge_prefetch(E, T, __ldg(&tp.ops[o + 1].edge));
             if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
                 double d = ROW(E.p.rd, er.slot), info = ROW(E.p.ri, er.slot);
                 double P0[3], Q[3], J[6];
@@ -445,7 +512,7 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
                     acc1_diag(J, Ow, omega_r, hd, bb);
                     double A[6];
                     const int ca_now = E.p.cnt[(size_t)er.a * TILE];
-                    const int ca = ((ca_now - __ldg(tp.num_calls + er.a)) % mod + mod) % mod;
+                    const int ca = SWEPT ? ((ca_now - __ldg(tp.num_calls + er.a)) % mod + mod) % mod : ca_now;
                     gen_jac_v0(E, Xo, er.ant, Q, d, ca, er.base_a, A);
                     acc1_off(A, J, Ow, ho);
                 }
@@ -520,7 +587,21 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
             double v = fabs(hd[up_idx(6, r, r)]);
             if (v > maxdiag) maxdiag = v;
         }
-        E.p.cnt[(size_t)i * TILE] = (ci + __ldg(tp.num_calls + i)) % mod;
+    }
+    return maxdiag;
+}
+
+/* BlockSolver::buildSystem, general edges, one thread per window.  Advances the oplus counters by
+ * the numeric-Jacobian calls.  Returns max |H_kk|. */
+__device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
+{
+    const DevTopo &tp = *E.tp;
+    const int N = tp.N, mod = E.cfg->orth_mod;
+    double maxdiag = 0.0;
+    for (int i = 0; i < N; ++i) {
+        double m = gen_linearize_pose<true>(E, T, i);
+        if (m > maxdiag) maxdiag = m;
+        E.p.cnt[(size_t)i * TILE] = (E.p.cnt[(size_t)i * TILE] + __ldg(tp.num_calls + i)) % mod;
     }
     return maxdiag;
 }
@@ -682,6 +763,63 @@ __device__ __noinline__ double gen_solve_update(const GenEnv &E, bool ok, double
         store_pose(Tn, i, X);
     }
     return scale;
+}
+
+/* gen_solve_update cut in two for the CTA kernel.  First the serial part, one thread per window:
+ * the substitution x_i = c_i - M_i x_parent(i) and computeScale(); x_i is left in the L record
+ * (chain: over c_i, which is dead once x_i exists; forest: its x slot). */
+__device__ __noinline__ double gen_subst_scale(const GenEnv &E, bool ok, double lambda)
+{
+    const int N = E.tp->N;
+    double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double scale = 0.0;
+    const bool tree = E.tp->tree != 0;
+    for (int i = 0; i < N; ++i) {
+        double *lp = E.p.LR + (size_t)i * (tree ? LR_TREE : LR_GEN) * TILE;
+        double l[LR_GEN];
+#pragma unroll
+        for (int k = 0; k < LR_GEN; ++k) l[k] = ROW(lp, k);
+        bool link = i > 0;
+        if (tree) {
+            const int par = __ldg(E.tp->parent + i);
+            link = par >= 0;
+            if (link) {
+                const double *pp = E.p.LR + (size_t)par * LR_TREE * TILE;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) xp[k] = ROW(pp, 84 + k);
+            }
+        }
+        subst_step<6>(l, link, xp);
+        if (!ok) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) xp[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ROW(lp, (tree ? 84 : 0) + k) = xp[k];
+        const double *h = E.p.HB + (size_t)i * HR_GEN * TILE;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) scale = scale + xp[k] * (lambda * xp[k] + ROW(h, 57 + k));
+    }
+    return scale;
+}
+
+/* ... then the update of pose i, independent of every other pose: estimate (+) x_i into the trial
+ * buffer, oplus counter advanced */
+UWBGO_DI void gen_update_pose(const GenEnv &E, int i, const PoseBuf &Tc, const PoseBuf &Tn, bool linearised)
+{
+    const bool tree = E.tp->tree != 0;
+    const double *lp = E.p.LR + (size_t)i * (tree ? LR_TREE : LR_GEN) * TILE;
+    double x[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = ROW(lp, (tree ? 84 : 0) + k);
+    Pose X;
+    load_pose(Tc, i, X);
+    int c = E.p.cnt[(size_t)i * TILE];
+    /* the numeric Jacobians of this iteration's buildSystem advanced the counter first */
+    if (linearised) c = (c + __ldg(E.tp->num_calls + i)) % E.cfg->orth_mod;
+    pose_oplus(X, x, c, E.cfg->orth_mod);
+    E.p.cnt[(size_t)i * TILE] = c;
+    store_pose(Tn, i, X);
 }
 
 }  // namespace uwbgo

@@ -102,6 +102,7 @@ struct DevWs {
     const double *ant;  /* [K][3] antenna offsets, plain              */
     double *chi2;       /* [tile][4][32] (solve) or [tile][2][32]     */
     int32_t *status;    /* [tile][4][32]                              */
+    double *echi;       /* [tile][E*2][32] per-edge chi2 | rho0 (general CTA kernel) */
 };
 
 /* pack / unpack job: transpose between window-major [W][C] and tile layout [tile][C][32] */

@@ -660,6 +660,10 @@ lm_general_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ De
     }
 }
 
+}  // namespace uwbgo
+#include "uwbgo_general_cta.cuh"
+namespace uwbgo {
+
 /* one linearisation: computeActiveErrors + buildSystem; chi2 = {plain, robust} */
 __global__ void __launch_bounds__(CTA_THREADS, 4)
 linearize_fast_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
@@ -844,8 +848,15 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         kern<<<(unsigned)((ws.W + threads - 1) / threads), threads, sm, st>>>(topo, cfg, ws, ais);
-    } else
-        lm_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
+    } else {
+#ifndef UWBGO_GEN_CTA
+#define UWBGO_GEN_CTA 1 /* 1: one CTA per tile, phases split over its warps; 0: one thread per window */
+#endif
+        if (UWBGO_GEN_CTA && ws.echi)
+            lm_general_cta_kernel<<<(unsigned)n_tiles(ws.W), UWBGO_GCTA_WARPS * 32, 0, st>>>(topo, cfg, ws);
+        else
+            lm_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
+    }
     return cudaGetLastError();
 }
 

@@ -62,4 +62,6 @@ else:
         print("kernel ms", s.last_kernel_ms())
 torch.cuda.synchronize()
 print("trials mean", status[:, 1].double().mean().item() if a.stage == "solve" else "-")
+import hashlib  # noqa: E402
+print("digest", hashlib.sha1(pose.cpu().numpy().tobytes() + chi2.cpu().numpy().tobytes()).hexdigest()[:12])
 s.close()

@@ -502,8 +502,16 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     const int kslot = (int)(ctx->k_count % uwbgo_ctx::K_RING);
     if (timed) CU(cudaEventRecord(ctx->k0[kslot], st));
     if (so) {
-        CU(launch_linearize(tp, cfg, ws, st));
-        CU(launch_expand_H(tp, ws, so->H_diag, so->H_off, so->b, st));
+#ifndef UWBGO_LIN_FUSED
+#define UWBGO_LIN_FUSED 1 /* CHAIN windows: one fused linearise kernel instead of records + expansion */
+#endif
+        if (UWBGO_LIN_FUSED && fast && linearize_chain_fused_ok(tp, so->H_diag, so->H_off, so->b)) {
+            CU(launch_linearize_chain_fused(tp, cfg, ws, so->H_diag, so->H_off, so->b, so->chi2 != nullptr, st));
+            ctx->launches -= 1; /* one kernel */
+        } else {
+            CU(launch_linearize(tp, cfg, ws, st));
+            CU(launch_expand_H(tp, ws, so->H_diag, so->H_off, so->b, st));
+        }
         if (timed) CU(cudaEventRecord(ctx->k1[kslot], st)); /* stage = linearise + expansion to the public layout */
         ctx->launches += 2;
         if (so->chi2) add(uj, ws.chi2, so->chi2, 2, 8, 0);

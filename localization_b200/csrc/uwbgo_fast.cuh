@@ -472,8 +472,8 @@ UWBGO_DI void chain_load(const FastEnv &E, const double *__restrict__ T, int i, 
 /* H record of pose i from (cx,cy,cz) = t_i and `in`; carry = vertex-0 terms of edge (i, i+1) on
  * entry (zeros at the newest pose: an exact no-op), of edge (i-1, i) on exit */
 template <bool PREV, class M = IeeeMath>
-UWBGO_DI void chain_build(const FastEnv &E, double cx, double cy, double cz, const ChainIn &in,
-                          double *carry, double *h, unsigned *badp = nullptr)
+UWBGO_DI void chain_build_q(const FastEnv &E, double cx, double cy, double cz, double qx, double qy,
+                            double qz, const ChainIn &in, double *carry, double *h, unsigned *badp = nullptr)
 {
     unsigned bl = 0;
     unsigned &bad = badp ? *badp : bl;
@@ -481,7 +481,6 @@ UWBGO_DI void chain_build(const FastEnv &E, double cx, double cy, double cz, con
     for (int k = 0; k < HR_FAST; ++k) h[k] = 0.0;
     double J[3], Ow, omega_r;
     {
-        const double qx = ANCH(E, in.anchor * 3), qy = ANCH(E, in.anchor * 3 + 1), qz = ANCH(E, in.anchor * 3 + 2);
         const double err = in.da - dist3m<M>(cx, cy, cz, qx, qy, qz, bad);
         fast_jac_v0<M>(cx, cy, cz, qx, qy, qz, in.da, E.delta, E.scalar, J, &bad);
         chain_weights<M>(E, err, in.ia, (in.robust & 1) != 0, Ow, omega_r, &bad);
@@ -503,6 +502,15 @@ UWBGO_DI void chain_build(const FastEnv &E, double cx, double cy, double cz, con
     chain_acc(carry, carry[3], carry[4], h);
     carry[0] = nA[0]; carry[1] = nA[1]; carry[2] = nA[2];
     carry[3] = nOw; carry[4] = nOr;
+}
+
+/* ... with the anchor of pose i read from the anchor rows */
+template <bool PREV, class M = IeeeMath>
+UWBGO_DI void chain_build(const FastEnv &E, double cx, double cy, double cz, const ChainIn &in,
+                          double *carry, double *h, unsigned *badp = nullptr)
+{
+    chain_build_q<PREV, M>(E, cx, cy, cz, ANCH(E, in.anchor * 3), ANCH(E, in.anchor * 3 + 1),
+                           ANCH(E, in.anchor * 3 + 2), in, carry, h, badp);
 }
 
 UWBGO_DI void chain_store_b(double *__restrict__ l, const double *h)

@@ -220,20 +220,21 @@ UWBGO_DI void gen_jac_v0(const GenEnv &E, const Pose &X, int ant, const double *
         o[1] = E.ant[3 * (ant - 1) + 1];
         o[2] = E.ant[3 * (ant - 1) + 2];
     }
-    int call = c0 + base;
+    /* call = (c0 + base + k) mod `mod` of the k-th oplus, kept reduced: one division per edge */
+    int call = (c0 + base) % mod;
 #pragma unroll
     for (int dd = 0; dd < 3; ++dd) {
         double epm[2];
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg) {
-            ++call;
+            if (++call == mod) call = 0;
             double v = sg == 0 ? E.delta : -E.delta;
             double tp[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) tp[r] = X.R[3 * r + dd] * v + X.t[r];
             double P[3];
             if (ant > 0) {
-                if (call % mod == 0) {
+                if (call == 0) {
                     double Rp[9];
 #pragma unroll
                     for (int k = 0; k < 9; ++k) Rp[k] = X.R[k];
@@ -254,13 +255,13 @@ UWBGO_DI void gen_jac_v0(const GenEnv &E, const Pose &X, int ant, const double *
             double epm[2];
 #pragma unroll
             for (int sg = 0; sg < 2; ++sg) {
-                ++call;
+                if (++call == mod) call = 0;
                 double q[3] = {0.0, 0.0, 0.0};
                 q[dd] = sg == 0 ? E.delta : -E.delta;
                 double Rinc[9], Rp[9], P[3];
                 increment_R(q, Rinc);
                 mat3_mul(X.R, Rinc, Rp);
-                if (call % mod == 0) orthogonalize(Rp);
+                if (call == 0) orthogonalize(Rp);
                 mat3_vec_add(Rp, o, X.t, P);
                 epm[sg] = d - dist3(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
             }
@@ -774,11 +775,26 @@ __device__ __noinline__ double gen_subst_scale(const GenEnv &E, bool ok, double 
     double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double scale = 0.0;
     const bool tree = E.tp->tree != 0;
-    for (int i = 0; i < N; ++i) {
-        double *lp = E.p.LR + (size_t)i * (tree ? LR_TREE : LR_GEN) * TILE;
-        double l[LR_GEN];
+    const size_t lstride = (size_t)(tree ? LR_TREE : LR_GEN) * TILE;
+    /* the record and b of pose i + 1 are fetched while pose i is substituted */
+    double l[LR_GEN], ln[LR_GEN], b[6], bn[6];
 #pragma unroll
-        for (int k = 0; k < LR_GEN; ++k) l[k] = ROW(lp, k);
+    for (int k = 0; k < LR_GEN; ++k) ln[k] = ROW(E.p.LR, k);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bn[k] = ROW(E.p.HB, 57 + k);
+    for (int i = 0; i < N; ++i) {
+        double *lp = E.p.LR + (size_t)i * lstride;
+#pragma unroll
+        for (int k = 0; k < LR_GEN; ++k) l[k] = ln[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) b[k] = bn[k];
+        if (i + 1 < N) {
+            const double *h = E.p.HB + (size_t)(i + 1) * HR_GEN * TILE;
+#pragma unroll
+            for (int k = 0; k < LR_GEN; ++k) ln[k] = ROW(lp + lstride, k);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) bn[k] = ROW(h, 57 + k);
+        }
         bool link = i > 0;
         if (tree) {
             const int par = __ldg(E.tp->parent + i);
@@ -796,9 +812,8 @@ __device__ __noinline__ double gen_subst_scale(const GenEnv &E, bool ok, double 
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) ROW(lp, (tree ? 84 : 0) + k) = xp[k];
-        const double *h = E.p.HB + (size_t)i * HR_GEN * TILE;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) scale = scale + xp[k] * (lambda * xp[k] + ROW(h, 57 + k));
+        for (int k = 0; k < 6; ++k) scale = scale + xp[k] * (lambda * xp[k] + b[k]);
     }
     return scale;
 }

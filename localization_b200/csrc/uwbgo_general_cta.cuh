@@ -19,6 +19,9 @@
  */
 #ifndef UWBGO_GENERAL_CTA_CUH
 #define UWBGO_GENERAL_CTA_CUH
+#ifdef UWBGO_GCTA_TIMING
+#include <cstdio>
+#endif
 
 namespace uwbgo {
 
@@ -77,7 +80,18 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
     };
     auto chi_sum = [&](double &p, double &r) {
         double pp = 0.0, rr = 0.0;
-        for (int e = 0; e < NE; ++e) {
+        int e = 0;
+        for (; e + 8 <= NE; e += 8) { /* loads first, then the two ordered sums */
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = ROW(echi, 2 * e + k);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                pp = pp + v[2 * k];
+                rr = rr + v[2 * k + 1];
+            }
+        }
+        for (; e < NE; ++e) {
             pp = pp + ROW(echi, 2 * e);
             rr = rr + ROW(echi, 2 * e + 1);
         }
@@ -111,6 +125,12 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
     }
     __syncthreads();
 
+#ifdef UWBGO_GCTA_TIMING
+    long long tph[6] = {0, 0, 0, 0, 0, 0}, tq = clock64();
+#define GCTA_TICK(k) do { long long tn_ = clock64(); tph[k] += tn_ - tq; tq = tn_; } while (0)
+#else
+#define GCTA_TICK(k)
+#endif
     while (sh.go) {
         if (sh.anylin) { /* phase L */
             double md = 0.0;
@@ -123,6 +143,7 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
             }
             sh.maxd[warp][lane] = md;
             __syncthreads();
+            GCTA_TICK(0);
         }
         if (warp == 0 && !done) { /* phase F */
             if (need_lin) {
@@ -144,6 +165,7 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
             const bool ok = tp.tree ? factor_sweep_tree(tp, E.p.HB, E.p.LR, lambda)
                                     : factor_sweep<6>(E.p.HB, E.p.LR, N, lambda);
             if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;
+            GCTA_TICK(1);
             tscale = gen_subst_scale(E, ok, lambda);
             tok = ok;
         } else if (warp != 0 && NW > 1) {
@@ -154,14 +176,17 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
                 prefetch_l2(hb + off);
         }
         __syncthreads();
+        GCTA_TICK(2);
         if (sh.act[lane]) { /* phase U: estimate (+) x into the trial buffer, pose by pose */
             const int c = sh.cur[lane];
             const bool lin = sh.lin[lane] != 0;
             for (int i = warp; i < N; i += NW) gen_update_pose(E, i, buf(c), buf(c ^ 1), lin);
         }
         __syncthreads();
+        GCTA_TICK(3);
         chi_phase(sh.act, 1); /* phase C at the trial estimates */
         __syncthreads();
+        GCTA_TICK(4);
         if (warp == 0) { /* phase D */
             if (!done) {
                 const bool ok = tok;
@@ -205,7 +230,13 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
             publish();
         }
         __syncthreads();
+        GCTA_TICK(5);
     }
+#ifdef UWBGO_GCTA_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 2)
+        printf("tile %d cycles: L %lld  factor %lld  subst %lld  U %lld  C %lld  D %lld\n", (int)blockIdx.x, tph[0],
+               tph[1], tph[2], tph[3], tph[4], tph[5]);
+#endif
 
     if (warp == 0 && valid) {
         double *chi2_out = ws.chi2 + (int64_t)blockIdx.x * 4 * TILE + lane;

@@ -129,6 +129,11 @@ cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st);
 cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st);
 cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,
                              cudaStream_t st);
+/* CHAIN windows: linearise straight into the public window-major arrays, one kernel (+ chi2 pass) */
+bool linearize_chain_fused_ok(const DevTopo &topo, const double *H_diag, const double *H_off, const double *b);
+cudaError_t launch_linearize_chain_fused(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,
+                                         double *H_diag, double *H_off, double *b, bool want_chi,
+                                         cudaStream_t st);
 /* expand H records (tile layout) into the public window-major H_diag/H_off/b arrays */
 cudaError_t launch_expand_H(const DevTopo &topo, const DevWs &ws, double *H_diag, double *H_off,
                             double *b, cudaStream_t st);

@@ -875,6 +875,212 @@ cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs
     return cudaGetLastError();
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Linearise stage, CHAIN windows, ONE kernel: tile-layout inputs -> public window-major blocks.  */
+/* One warp owns (tile, run of LCF_RUN consecutive poses), lane = window.  The warp walks its run   */
+/* from the newest pose down with the straight-line chain_build of the LM kernels (the vertex-0     */
+/* terms of the trajectory edge above the run are recomputed first: 7 of the ~20 square roots of a  */
+/* pose, once per run), so a tile is linearised by N / LCF_RUN independent warps instead of one     */
+/* thread per window: enough FP64 work in flight to hide behind the output stream.  Each pose's     */
+/* 18-number record goes through a padded shared-memory panel [18][33] and leaves as full 6x6       */
+/* blocks (zeros synthesised on the way out), 288-byte / 48-byte runs per window, so the kernel's   */
+/* DRAM traffic is the algorithmic bytes: inputs once, public arrays once, no H records in between. */
+/* ------------------------------------------------------------------------------------------ */
+#ifndef UWBGO_LCF_RUN
+#define UWBGO_LCF_RUN 5
+#endif
+#ifndef UWBGO_LCF_WARPS
+#define UWBGO_LCF_WARPS 8
+#endif
+#ifndef UWBGO_LCF_MINB
+#define UWBGO_LCF_MINB 2
+#endif
+constexpr int LCF_ROWS = HR_FAST + 1; /* panel rows: the record, then a row of zeros */
+
+/* inputs of pose i for the run: chain_load plus the anchor of its range edge */
+struct LcfIn {
+    ChainIn in;
+    double qx, qy, qz;
+};
+UWBGO_DI void lcf_load(const FastEnv &E, const double *__restrict__ T, int i, LcfIn &x)
+{
+    if (i > 0)
+        chain_load<true>(E, T, i, x.in);
+    else
+        chain_load<false>(E, T, 0, x.in);
+    const double *an = E.p.anch + (size_t)x.in.anchor * 3 * TILE;
+    x.qx = ROW(an, 0); x.qy = ROW(an, 1); x.qz = ROW(an, 2);
+}
+
+/* which 16-byte chunk of a window's output this lane writes, per pose.  A window's blocks are
+ * H_diag 36 doubles = 18 chunks, H_off 18 chunks, b 3 chunks = 39 chunks: store A covers chunks
+ * 0..31 (lanes 0-17 H_diag, 18-31 H_off chunks 0-13), store B the rest (lanes 0-3 H_off chunks 14-17,
+ * lanes 4-6 b).  r0 / r1 = panel rows of the chunk's two doubles (HR_FAST = the zero row). */
+struct LcfLane {
+    int a0, a1, b0, b1;
+    int arr_a, arr_b; /* 0 H_diag, 1 H_off, 2 b, -1 idle */
+    int off_a, off_b; /* double offset inside the block */
+};
+UWBGO_DI int lcf_row(int arr, int k)
+{
+    if (arr == 2) return k < 3 ? 15 + k : HR_FAST;
+    const int r = k / 6, c = k % 6;
+    if (r >= 3 || c >= 3) return HR_FAST;
+    if (arr == 0) return r <= c ? up_idx(3, r, c) : up_idx(3, c, r);
+    return 6 + 3 * r + c;
+}
+UWBGO_DI LcfLane lcf_lane(int lane)
+{
+    LcfLane L;
+    L.arr_a = lane < 18 ? 0 : 1;
+    L.off_a = lane < 18 ? 2 * lane : 2 * (lane - 18);
+    L.arr_b = lane < 4 ? 1 : (lane < 7 ? 2 : -1);
+    L.off_b = lane < 4 ? 2 * (14 + lane) : 2 * (lane - 4);
+    L.a0 = lcf_row(L.arr_a, L.off_a);
+    L.a1 = lcf_row(L.arr_a, L.off_a + 1);
+    L.b0 = L.arr_b < 0 ? HR_FAST : lcf_row(L.arr_b, L.off_b);
+    L.b1 = L.arr_b < 0 ? HR_FAST : lcf_row(L.arr_b, L.off_b + 1);
+    return L;
+}
+
+template <class M>
+UWBGO_DI void lcf_run(const FastEnv &E, const double *__restrict__ T, const int N, const int i_lo,
+                      const int i_hi, const int64_t tile, const int lane, const int64_t W,
+                      double (*panel)[33], double *__restrict__ H_diag, double *__restrict__ H_off,
+                      double *__restrict__ b, unsigned &bad)
+{
+    LcfIn cur, nxt;
+    lcf_load(E, T, i_hi, cur);
+    const double *th = T + (size_t)i_hi * 3 * TILE;
+    double cx = ROW(th, 0), cy = ROW(th, 1), cz = ROW(th, 2);
+    double carry[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (i_hi + 1 < N) { /* vertex-0 terms of edge (i_hi, i_hi + 1) */
+        const int j = i_hi + 1;
+        const double *tp1 = T + (size_t)j * 3 * TILE;
+        const double nx = ROW(tp1, 0), ny = ROW(tp1, 1), nz = ROW(tp1, 2);
+        const double dt = ROW(E.p.rd, 2 * j), it = ROW(E.p.ri, 2 * j);
+        const int rb = __ldg(&E.tp->chain[j].robust);
+        if (i_hi > i_lo) lcf_load(E, T, i_hi - 1, nxt);
+        const double err = dt - dist3m<M>(cx, cy, cz, nx, ny, nz, bad);
+        fast_jac_v0<M>(cx, cy, cz, nx, ny, nz, dt, E.delta, E.scalar, carry, &bad);
+        chain_weights<M>(E, err, it, (rb & 2) != 0, carry[3], carry[4], &bad);
+    } else if (i_hi > i_lo)
+        lcf_load(E, T, i_hi - 1, nxt);
+    const LcfLane L = lcf_lane(lane);
+    const int nw = (int)((W - tile * TILE) < TILE ? (W - tile * TILE) : TILE);
+    for (int i = i_hi; i >= i_lo; --i) {
+        double h[HR_FAST];
+        if (i > 0)
+            chain_build_q<true, M>(E, cx, cy, cz, cur.qx, cur.qy, cur.qz, cur.in, carry, h, &bad);
+        else
+            chain_build_q<false, M>(E, cx, cy, cz, cur.qx, cur.qy, cur.qz, cur.in, carry, h, &bad);
+        if (__any_sync(0xffffffffu, bad != 0)) return; /* the caller repeats the run with IEEE operations */
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < HR_FAST; ++k) panel[k][lane] = h[k];
+        __syncwarp();
+        /* next pose: its estimate came with this pose's inputs, the rest was fetched during the build */
+        cx = cur.in.px; cy = cur.in.py; cz = cur.in.pz;
+        cur = nxt;
+        if (i - 2 >= i_lo) lcf_load(E, T, i - 2, nxt);
+        const size_t wb = (size_t)tile * TILE;
+        double *pa = L.arr_a == 0 ? H_diag + (wb * N + i) * 36 + L.off_a
+                                  : (i > 0 ? H_off + (wb * (N - 1) + (i - 1)) * 36 + L.off_a : nullptr);
+        double *pb = L.arr_b == 1 ? (i > 0 ? H_off + (wb * (N - 1) + (i - 1)) * 36 + L.off_b : nullptr)
+                                  : (L.arr_b == 2 ? b + (wb * N + i) * 6 + L.off_b : nullptr);
+        const size_t sa = L.arr_a == 0 ? (size_t)N * 36 : (size_t)(N - 1) * 36;
+        const size_t sb = L.arr_b == 1 ? (size_t)(N - 1) * 36 : (size_t)N * 6;
+#pragma unroll 4
+        for (int wl = 0; wl < nw; ++wl) {
+            if (pa) {
+                *reinterpret_cast<double2 *>(pa) = make_double2(panel[L.a0][wl], panel[L.a1][wl]);
+                pa += sa;
+            }
+            if (pb) {
+                *reinterpret_cast<double2 *>(pb) = make_double2(panel[L.b0][wl], panel[L.b1][wl]);
+                pb += sb;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(UWBGO_LCF_WARPS * 32, UWBGO_LCF_MINB)
+linearize_chain_fused_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+                             const __grid_constant__ DevWs ws, double *__restrict__ H_diag,
+                             double *__restrict__ H_off, double *__restrict__ b, int runs, int want_chi)
+{
+    __shared__ double sm[UWBGO_LCF_WARPS][LCF_ROWS][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    sm[warp][HR_FAST][lane] = 0.0;
+    /* the first CTAs hold the chi2 passes (one warp per tile; long, so they start first and share
+     * CTAs only with each other), the rest one (tile, run) per warp */
+    const int64_t tiles = n_tiles(ws.W);
+    const int64_t chi_ctas = want_chi ? (tiles + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS : 0;
+    int64_t tile;
+    int run;
+    if ((int64_t)blockIdx.x < chi_ctas) {
+        tile = (int64_t)blockIdx.x * UWBGO_LCF_WARPS + warp;
+        run = -1;
+        if (tile >= tiles) return;
+    } else {
+        const int64_t item = ((int64_t)blockIdx.x - chi_ctas) * UWBGO_LCF_WARPS + warp;
+        if (item >= tiles * runs) return;
+        tile = item / runs;
+        run = (int)(item % runs);
+    }
+    const int N = tp.N;
+    FastEnv E;
+    E.tp = &tp;
+    E.p = thread_ptrs<HR_FAST, LR_FAST>(tp, ws, tile * TILE + lane); /* workspaces are whole tiles */
+    E.ck.init(cfg.kdelta);
+    E.delta = cfg.jdelta;
+    E.scalar = 1.0 / (2.0 * cfg.jdelta);
+    E.bs = 0;
+    E.stash = nullptr;
+    E.anch = E.p.anch;
+    E.anch_stride = TILE;
+    if (run < 0) { /* computeActiveErrors + chi2: lane = window, the sums run in insertion order */
+        if (tile * TILE + lane < ws.W) {
+            double p, r;
+            fast_chi_pass(E, E.p.T0, p, r);
+            double *c = ws.chi2 + tile * 2 * TILE + lane;
+            ROW(c, 0) = p;
+            ROW(c, 1) = r;
+        }
+        return;
+    }
+    const int i_lo = run * UWBGO_LCF_RUN;
+    const int i_hi = (i_lo + UWBGO_LCF_RUN < N ? i_lo + UWBGO_LCF_RUN : N) - 1;
+    unsigned bad = 0;
+    lcf_run<NbMath>(E, E.p.T0, N, i_lo, i_hi, tile, lane, ws.W, sm[warp], H_diag, H_off, b, bad);
+    if (__any_sync(0xffffffffu, bad != 0)) {
+        bad = 0;
+        lcf_run<IeeeMath>(E, E.p.T0, N, i_lo, i_hi, tile, lane, ws.W, sm[warp], H_diag, H_off, b, bad);
+    }
+}
+
+/* the output arrays must be 16-byte aligned (the blocks leave as 16-byte stores) */
+bool linearize_chain_fused_ok(const DevTopo &topo, const double *H_diag, const double *H_off, const double *b)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(H_diag) | reinterpret_cast<uintptr_t>(H_off) |
+                        reinterpret_cast<uintptr_t>(b);
+    return topo.fast == 2 && (a & 15u) == 0;
+}
+
+cudaError_t launch_linearize_chain_fused(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,
+                                         double *H_diag, double *H_off, double *b, bool want_chi,
+                                         cudaStream_t st)
+{
+    if (ws.W <= 0) return cudaSuccess;
+    const int runs = (topo.N + UWBGO_LCF_RUN - 1) / UWBGO_LCF_RUN;
+    const int64_t tiles = n_tiles(ws.W);
+    const int64_t ctas = (tiles * runs + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS +
+                         (want_chi ? (tiles + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS : 0);
+    linearize_chain_fused_kernel<<<(unsigned)ctas, UWBGO_LCF_WARPS * 32, 0, st>>>(topo, cfg, ws, H_diag, H_off, b, runs,
+                                                                  want_chi ? 1 : 0);
+    return cudaGetLastError();
+}
+
 /* H records (tile layout) -> public H_diag [W][N][36] (both triangles), H_off [W][N-1][36],
  * b [W][N][6].  One warp per (tile, pose): the record is expanded into a padded shared-memory
  * panel [78][33] with coalesced row reads, then written out window by window as contiguous

@@ -451,9 +451,8 @@ struct ChainIn {
     int anchor, robust;
 };
 template <bool PREV>
-UWBGO_DI void chain_load(const FastEnv &E, const double *__restrict__ T, int i, ChainIn &in)
+UWBGO_DI void chain_load_t(const FastEnv &E, const double *__restrict__ T, int i, const int2 tb, ChainIn &in)
 {
-    const int2 tb = __ldg(reinterpret_cast<const int2 *>(E.tp->chain + i));
     in.anchor = tb.x;
     in.robust = tb.y;
     const int sa = i == 0 ? 0 : 2 * i - 1;
@@ -467,6 +466,12 @@ UWBGO_DI void chain_load(const FastEnv &E, const double *__restrict__ T, int i, 
     } else {
         in.px = in.py = in.pz = in.dt = in.it = 0.0;
     }
+}
+
+template <bool PREV>
+UWBGO_DI void chain_load(const FastEnv &E, const double *__restrict__ T, int i, ChainIn &in)
+{
+    chain_load_t<PREV>(E, T, i, __ldg(reinterpret_cast<const int2 *>(E.tp->chain + i)), in);
 }
 
 /* H record of pose i from (cx,cy,cz) = t_i and `in`; carry = vertex-0 terms of edge (i, i+1) on

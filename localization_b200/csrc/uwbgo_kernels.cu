@@ -877,23 +877,29 @@ cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs
 
 /* ------------------------------------------------------------------------------------------ */
 /* Linearise stage, CHAIN windows, ONE kernel: tile-layout inputs -> public window-major blocks.  */
-/* One warp owns (tile, run of LCF_RUN consecutive poses), lane = window.  The warp walks its run   */
-/* from the newest pose down with the straight-line chain_build of the LM kernels (the vertex-0     */
-/* terms of the trajectory edge above the run are recomputed first: 7 of the ~20 square roots of a  */
-/* pose, once per run), so a tile is linearised by N / LCF_RUN independent warps instead of one     */
-/* thread per window: enough FP64 work in flight to hide behind the output stream.  Each pose's     */
-/* 18-number record goes through a padded shared-memory panel [18][33] and leaves as full 6x6       */
-/* blocks (zeros synthesised on the way out), 288-byte / 48-byte runs per window, so the kernel's   */
-/* DRAM traffic is the algorithmic bytes: inputs once, public arrays once, no H records in between. */
+/* One warp owns (tile, run of LCF_RUN consecutive poses), lane = window, and walks its run from    */
+/* the newest pose down with the straight-line chain_build of the LM kernels; the vertex-0 terms of */
+/* the trajectory edge above the run are recomputed first (7 of the ~20 square roots of a pose).    */
+/* Each pose's 18-number record goes through a padded shared-memory panel [19][33] (row 18 = zeros) */
+/* and leaves as full 6x6 blocks, 16 bytes per lane: store A covers H_diag (lanes 0-17) and the     */
+/* first 14 chunks of H_off, store B the rest of H_off and b.  DRAM traffic = the algorithmic bytes: */
+/* inputs once, public arrays once, no H records in between.                                        */
+/* What bounds it is the store stream, and what the store stream wants is measured in                */
+/* scripts/micro/store_pattern.cu: 288-byte rows at a 14.4 KB stride reach the fill bandwidth        */
+/* (7.2 TB/s) when the warps that are resident together cover neighbouring poses, 4.7 TB/s when      */
+/* each warp walks 5 poses on its own (at any instant a window then has isolated rows 1,440 bytes    */
+/* apart in flight).  Hence LCF_RUN = 1: consecutive warps take consecutive poses of a tile, at     */
+/* the price of 27 instead of 20 square roots per pose (the kernel without its stores is 0.25 ms).  */
+/* C3 on one B200: run 5 -> 0.67 ms, run 2 -> 0.55 ms, run 1 -> 0.51 ms.                            */
 /* ------------------------------------------------------------------------------------------ */
 #ifndef UWBGO_LCF_RUN
-#define UWBGO_LCF_RUN 5
+#define UWBGO_LCF_RUN 1
 #endif
 #ifndef UWBGO_LCF_WARPS
-#define UWBGO_LCF_WARPS 8
+#define UWBGO_LCF_WARPS 1 /* warps per CTA; measured on C3: 1 -> 0.51 ms, 4 -> 0.54 ms, 8 -> 0.55 ms */
 #endif
 #ifndef UWBGO_LCF_MINB
-#define UWBGO_LCF_MINB 2
+#define UWBGO_LCF_MINB 16 /* 16 warps per SM at 128 registers; 102 / 85 registers spill: 1.05 / 1.20 ms */
 #endif
 constexpr int LCF_ROWS = HR_FAST + 1; /* panel rows: the record, then a row of zeros */
 
@@ -970,10 +976,16 @@ UWBGO_DI void lcf_run(const FastEnv &E, const double *__restrict__ T, const int 
     const int nw = (int)((W - tile * TILE) < TILE ? (W - tile * TILE) : TILE);
     for (int i = i_hi; i >= i_lo; --i) {
         double h[HR_FAST];
+#ifdef UWBGO_LCF_NOLOAD
+        for (int k = 0; k < HR_FAST; ++k) h[k] = (double)(i + k);
+#elif defined(UWBGO_LCF_NOCOMPUTE)
+        for (int k = 0; k < HR_FAST; ++k) h[k] = cx + k;
+#else
         if (i > 0)
             chain_build_q<true, M>(E, cx, cy, cz, cur.qx, cur.qy, cur.qz, cur.in, carry, h, &bad);
         else
             chain_build_q<false, M>(E, cx, cy, cz, cur.qx, cur.qy, cur.qz, cur.in, carry, h, &bad);
+#endif
         if (__any_sync(0xffffffffu, bad != 0)) return; /* the caller repeats the run with IEEE operations */
         __syncwarp();
 #pragma unroll
@@ -990,7 +1002,13 @@ UWBGO_DI void lcf_run(const FastEnv &E, const double *__restrict__ T, const int 
                                   : (L.arr_b == 2 ? b + (wb * N + i) * 6 + L.off_b : nullptr);
         const size_t sa = L.arr_a == 0 ? (size_t)N * 36 : (size_t)(N - 1) * 36;
         const size_t sb = L.arr_b == 1 ? (size_t)(N - 1) * 36 : (size_t)N * 6;
-#pragma unroll 4
+#ifdef UWBGO_LCF_NOSTORE
+        if (h[0] == 123.456)
+#endif
+#ifndef UWBGO_LCF_UNROLL
+#define UWBGO_LCF_UNROLL 8
+#endif
+        UWBGO_PRAGMA(unroll UWBGO_LCF_UNROLL)
         for (int wl = 0; wl < nw; ++wl) {
             if (pa) {
                 *reinterpret_cast<double2 *>(pa) = make_double2(panel[L.a0][wl], panel[L.a1][wl]);
@@ -1007,23 +1025,30 @@ UWBGO_DI void lcf_run(const FastEnv &E, const double *__restrict__ T, const int 
 __global__ void __launch_bounds__(UWBGO_LCF_WARPS * 32, UWBGO_LCF_MINB)
 linearize_chain_fused_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                              const __grid_constant__ DevWs ws, double *__restrict__ H_diag,
-                             double *__restrict__ H_off, double *__restrict__ b, int runs, int want_chi)
+                             double *__restrict__ H_off, double *__restrict__ b, int runs, int want_chi,
+                             int chi_every)
 {
     __shared__ double sm[UWBGO_LCF_WARPS][LCF_ROWS][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     sm[warp][HR_FAST][lane] = 0.0;
-    /* the first CTAs hold the chi2 passes (one warp per tile; long, so they start first and share
-     * CTAs only with each other), the rest one (tile, run) per warp */
+    /* the chi2 passes (one warp per tile) are long and get CTAs of their own: CTA b is a chi2 CTA iff
+     * b % chi_every == 0 and b / chi_every < chi_ctas (chi_every = 1: they lead the grid) */
     const int64_t tiles = n_tiles(ws.W);
     const int64_t chi_ctas = want_chi ? (tiles + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS : 0;
+    const int64_t bid = blockIdx.x;
     int64_t tile;
     int run;
-    if ((int64_t)blockIdx.x < chi_ctas) {
-        tile = (int64_t)blockIdx.x * UWBGO_LCF_WARPS + warp;
+    if (chi_ctas > 0 && bid % chi_every == 0 && bid / chi_every < chi_ctas) {
+        tile = (bid / chi_every) * UWBGO_LCF_WARPS + warp;
         run = -1;
         if (tile >= tiles) return;
     } else {
-        const int64_t item = ((int64_t)blockIdx.x - chi_ctas) * UWBGO_LCF_WARPS + warp;
+        int64_t before = 0; /* chi2 CTAs with a smaller block index */
+        if (chi_ctas > 0) {
+            before = bid / chi_every + 1;
+            if (before > chi_ctas) before = chi_ctas;
+        }
+        const int64_t item = (bid - before) * UWBGO_LCF_WARPS + warp;
         if (item >= tiles * runs) return;
         tile = item / runs;
         run = (int)(item % runs);
@@ -1074,10 +1099,17 @@ cudaError_t launch_linearize_chain_fused(const DevTopo &topo, const DevCfg &cfg,
     if (ws.W <= 0) return cudaSuccess;
     const int runs = (topo.N + UWBGO_LCF_RUN - 1) / UWBGO_LCF_RUN;
     const int64_t tiles = n_tiles(ws.W);
-    const int64_t ctas = (tiles * runs + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS +
-                         (want_chi ? (tiles + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS : 0);
+    const int64_t run_ctas = (tiles * runs + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS;
+    const int64_t chi_ctas = want_chi ? (tiles + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS : 0;
+    const int64_t ctas = run_ctas + chi_ctas;
+    /* chi2 CTAs lead the grid (every = 1); spreading them over the grid measured slower (0.60 vs 0.55 ms) */
+#ifndef UWBGO_LCF_CHI_SPREAD
+#define UWBGO_LCF_CHI_SPREAD 0
+#endif
+    int64_t every = (UWBGO_LCF_CHI_SPREAD && chi_ctas) ? (ctas * 3 / 4) / chi_ctas : 1;
+    if (every < 1) every = 1;
     linearize_chain_fused_kernel<<<(unsigned)ctas, UWBGO_LCF_WARPS * 32, 0, st>>>(topo, cfg, ws, H_diag, H_off, b, runs,
-                                                                  want_chi ? 1 : 0);
+                                                                                  want_chi ? 1 : 0, (int)every);
     return cudaGetLastError();
 }
 

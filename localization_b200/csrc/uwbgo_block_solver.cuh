@@ -118,9 +118,9 @@ UWBGO_DI void factor_step(const double *h, double *__restrict__ l, bool link, bo
     }
 }
 
-template <int D>
+template <int D, class M = IeeeMath>
 UWBGO_DI bool factor_sweep(const double *__restrict__ HB, double *__restrict__ LR, int N,
-                           double lambda)
+                           double lambda, unsigned *badp = nullptr)
 {
     constexpr int SQ = Rec<D>::SQ, RH = Rec<D>::H, RL = Rec<D>::L;
     double G[SQ], zn[D];
@@ -135,11 +135,11 @@ UWBGO_DI bool factor_sweep(const double *__restrict__ HB, double *__restrict__ L
         load_hrec<D>(HB + (size_t)i * RH * TILE, ra);
         while (i >= 0) {
             if (i > 0) load_hrec<D>(HB + (size_t)(i - 1) * RH * TILE, rb);
-            factor_step<D>(ra, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok);
+            factor_step<D, M>(ra, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok, badp);
             --i;
             if (i < 0) break;
             if (i > 0) load_hrec<D>(HB + (size_t)(i - 1) * RH * TILE, ra);
-            factor_step<D>(rb, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok);
+            factor_step<D, M>(rb, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok, badp);
             --i;
         }
     } else {
@@ -148,7 +148,7 @@ UWBGO_DI bool factor_sweep(const double *__restrict__ HB, double *__restrict__ L
             if (D == 3 && UWBGO_L2PF_DIST > 0 && i - UWBGO_L2PF_DIST >= 0)
                 prefetch_rows_l2<RH>(HB + (size_t)(i - UWBGO_L2PF_DIST) * RH * TILE);
             load_hrec<D>(HB + (size_t)i * RH * TILE, r);
-            factor_step<D>(r, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok);
+            factor_step<D, M>(r, LR + (size_t)i * RL * TILE, i + 1 < N, i > 0, lambda, G, zn, ok, badp);
         }
     }
     return ok;

@@ -374,7 +374,15 @@ UWBGO_DI void se3_jacobians(const Pose &Zinv, const Pose &Xi, const Pose &Xj, do
 }
 
 /* constructQuadraticForm pieces.  hd = upper packed 6x6 (21), ho = 6x6, bb = 6 */
-UWBGO_DI void acc1_diag(const double *J, double Ow, double omega_r, double *hd, double *bb)
+/* accumulator views: a plain array (registers) or a shared-memory column, element k at p[k * STRIDE] */
+template <int STRIDE>
+struct SmemAcc {
+    double *p;
+    UWBGO_DI double &operator[](int k) const { return p[(size_t)k * STRIDE]; }
+};
+
+template <class AH, class AB>
+UWBGO_DI void acc1_diag(const double *J, double Ow, double omega_r, AH hd, AB bb)
 {
 #pragma unroll
     for (int r = 0; r < 6; ++r) bb[r] = fma(J[r], omega_r, bb[r]);
@@ -385,7 +393,8 @@ UWBGO_DI void acc1_diag(const double *J, double Ow, double omega_r, double *hd, 
         for (int c = r; c < 6; ++c) hd[up_idx(6, r, c)] = fma(JtO, J[c], hd[up_idx(6, r, c)]);
     }
 }
-UWBGO_DI void acc1_off(const double *A, const double *B, double Ow, double *ho)
+template <class AO>
+UWBGO_DI void acc1_off(const double *A, const double *B, double Ow, AO ho)
 {
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
@@ -415,7 +424,8 @@ UWBGO_DI void jt_omega(const double *J, const double *__restrict__ O, bool robus
         }
     }
 }
-UWBGO_DI void acc6_b(const double *J, const double *omega_r, double *bb)
+template <class AB>
+UWBGO_DI void acc6_b(const double *J, const double *omega_r, AB bb)
 {
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
@@ -425,7 +435,8 @@ UWBGO_DI void acc6_b(const double *J, const double *omega_r, double *bb)
         bb[r] = bb[r] + s;
     }
 }
-UWBGO_DI void acc6_diag(const double *JtO, const double *J, double *hd)
+template <class AH>
+UWBGO_DI void acc6_diag(const double *JtO, const double *J, AH hd)
 {
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -437,7 +448,8 @@ UWBGO_DI void acc6_diag(const double *JtO, const double *J, double *hd)
             hd[up_idx(6, r, c)] = hd[up_idx(6, r, c)] + s;
         }
 }
-UWBGO_DI void acc6_off(const double *AtO, const double *B, double *ho)
+template <class AO>
+UWBGO_DI void acc6_off(const double *AtO, const double *B, AO ho)
 {
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -456,8 +468,8 @@ UWBGO_DI void acc6_off(const double *AtO, const double *B, double *ho)
  * by one thread that advances each pose's counter right after its record (gen_linearize), so the
  * counter of an older pose already includes this linearisation's calls; !SWEPT: every counter
  * still holds its value from before the linearisation (poses linearised concurrently). */
-template <bool SWEPT>
-UWBGO_DI double gen_linearize_pose(const GenEnv &E, const PoseBuf &T, const int i)
+template <bool SWEPT, class AH, class AO, class AB>
+UWBGO_DI double gen_linearize_pose_acc(const GenEnv &E, const PoseBuf &T, const int i, AH hd, AO ho, AB bb)
 {
     const DevTopo &tp = *E.tp;
     const int mod = E.cfg->orth_mod;
@@ -466,7 +478,6 @@ UWBGO_DI double gen_linearize_pose(const GenEnv &E, const PoseBuf &T, const int 
         Pose Xi;
         load_pose(T, i, Xi);
         const int ci = E.p.cnt[(size_t)i * TILE];
-        double hd[21], ho[36], bb[6];
 #pragma unroll
         for (int k = 0; k < 21; ++k) hd[k] = 0.0;
 #pragma unroll
@@ -590,6 +601,14 @@ UWBGO_DI double gen_linearize_pose(const GenEnv &E, const PoseBuf &T, const int 
         }
     }
     return maxdiag;
+}
+
+/* ... with the accumulators of the pose in registers */
+template <bool SWEPT>
+UWBGO_DI double gen_linearize_pose(const GenEnv &E, const PoseBuf &T, const int i)
+{
+    double hd[21], ho[36], bb[6];
+    return gen_linearize_pose_acc<SWEPT, double *, double *, double *>(E, T, i, hd, ho, bb);
 }
 
 /* BlockSolver::buildSystem, general edges, one thread per window.  Advances the oplus counters by

@@ -31,6 +31,11 @@ namespace uwbgo {
 #ifndef UWBGO_GCTA_MINB
 #define UWBGO_GCTA_MINB 2
 #endif
+#ifndef UWBGO_GCTA_SMEM_ACC
+#define UWBGO_GCTA_SMEM_ACC 0 /* 1: accumulators of the linearise phase in shared memory -- fewer spills (2.4 KB -> 0.6 KB
+                                * of spill code) but slower: 11.2 vs 10.5 ms on C4a, 85.5 vs 76.9 ms at 65,536 windows */
+#endif
+constexpr size_t GCTA_DYN_SMEM = UWBGO_GCTA_SMEM_ACC ? sizeof(double) * HR_GEN * UWBGO_GCTA_WARPS * 32 : 0;
 
 struct GctaShared {
     double ant[3 * MAX_SMEM_ANTENNAS];
@@ -47,6 +52,9 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
 {
     constexpr int NW = UWBGO_GCTA_WARPS;
     __shared__ GctaShared sh;
+#if UWBGO_GCTA_SMEM_ACC
+    extern __shared__ double gcta_acc[]; /* [HR_GEN][NW * 32] */
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (tp.K <= MAX_SMEM_ANTENNAS)
         for (int k = threadIdx.x; k < 3 * tp.K; k += NW * 32) sh.ant[k] = ws.ant[k];
@@ -137,7 +145,16 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
             if (sh.lin[lane]) {
                 const PoseBuf T = buf(sh.cur[lane]);
                 for (int i = warp; i < N; i += NW) {
+#if UWBGO_GCTA_SMEM_ACC
+                    /* the 63 accumulators of the pose's H record live in this thread's shared-memory
+                     * column instead of 126 registers the linearisation of a 6-D edge does not have */
+                    constexpr int ST = NW * 32;
+                    double *col = gcta_acc + threadIdx.x;
+                    double m = gen_linearize_pose_acc<false>(E, T, i, SmemAcc<ST>{col}, SmemAcc<ST>{col + 21 * ST},
+                                                             SmemAcc<ST>{col + 57 * ST});
+#else
                     double m = gen_linearize_pose<false>(E, T, i);
+#endif
                     if (m > md) md = m;
                 }
             }
@@ -162,6 +179,8 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
                 q = 0;
                 need_lin = false;
             }
+            /* (the branch-free sqrt / reciprocal of the CHAIN kernels lose here: 11.4 vs 10.4 ms on C4a,
+             * the 6x6 elimination step is already out of registers) */
             const bool ok = tp.tree ? factor_sweep_tree(tp, E.p.HB, E.p.LR, lambda)
                                     : factor_sweep<6>(E.p.HB, E.p.LR, N, lambda);
             if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;

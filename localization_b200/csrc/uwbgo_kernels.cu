@@ -852,8 +852,14 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
 #ifndef UWBGO_GEN_CTA
 #define UWBGO_GEN_CTA 1 /* 1: one CTA per tile, phases split over its warps; 0: one thread per window */
 #endif
-        if (UWBGO_GEN_CTA && ws.echi)
-            lm_general_cta_kernel<<<(unsigned)n_tiles(ws.W), UWBGO_GCTA_WARPS * 32, 0, st>>>(topo, cfg, ws);
+        if (UWBGO_GEN_CTA && ws.echi) {
+            if (GCTA_DYN_SMEM > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(lm_general_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)GCTA_DYN_SMEM);
+                if (e != cudaSuccess) return e;
+            }
+            lm_general_cta_kernel<<<(unsigned)n_tiles(ws.W), UWBGO_GCTA_WARPS * 32, GCTA_DYN_SMEM, st>>>(topo, cfg, ws);
+        }
         else
             lm_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
     }

@@ -131,6 +131,45 @@ def test_linearize_bit_exact(solver):
         assert np.array_equal(chi, rchi)
 
 
+def test_linearize_chain_fused_ragged_and_unaligned(solver):
+    """the one-kernel linearise stage of CHAIN windows: ragged tiles, 1- and 2-pose windows, a window
+    longer than a pose run, and output arrays that are not 16-byte aligned (two-kernel fallback)"""
+    import ctypes as C
+    import torch
+    from localization_b200 import _ffi
+    for W, N, A in ((1, 1, 3), (33, 2, 4), (95, 7, 8), (40, 50, 8), (31, 200, 16)):
+        topo, batch, _ = synthetic.uwb_only(W, N, A, seed=W + N)
+        cfg = Config()
+        Hd, Ho, b, chi = solver.linearize(topo, batch, cfg)
+        rHd, rHo, rb, rchi = oracle.linearize(topo, batch, cfg)
+        assert np.array_equal(Hd, rHd) and np.array_equal(Ho, rHo) and np.array_equal(b, rb)
+        assert np.array_equal(chi, rchi)
+    # device API with output pointers 8 bytes off a 16-byte boundary
+    W, N, A = 70, 12, 5
+    topo, batch, _ = synthetic.uwb_only(W, N, A, seed=9)
+    cfg = Config()
+    dev = torch.device("cuda", 0)
+    keep = {k: torch.from_numpy(getattr(batch, k)).to(dev) for k in ("pose_t", "anchors", "range_d", "range_info")}
+    cb = _ffi.CBatch()
+    cb.n_windows = W
+    for k, v in keep.items():
+        setattr(cb, k, C.cast(C.c_void_p(v.data_ptr()), C.POINTER(C.c_double)))
+    outs = []
+    for off in (0, 1):
+        bufs = [torch.zeros(n + 1, dtype=torch.float64, device=dev) for n in (W * N * 36, W * (N - 1) * 36, W * N * 6, W * 2)]
+        views = [t[off:off + t.numel() - 1] for t in bufs]
+        assert all((v.data_ptr() % 16 == 0) == (off == 0) for v in views[:3])
+        solver.linearize_device(topo, cb, cfg, *[v.data_ptr() for v in views], torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize(dev)
+        outs.append([v.cpu().numpy() for v in views])
+    rHd, rHo, rb, rchi = oracle.linearize(topo, batch, cfg)
+    for o in outs:
+        assert np.array_equal(o[0].reshape(rHd.shape), rHd)
+        assert np.array_equal(o[1].reshape(rHo.shape), rHo)
+        assert np.array_equal(o[2].reshape(rb.shape), rb)
+        assert np.array_equal(o[3].reshape(rchi.shape), rchi)
+
+
 def test_factor_solve_bit_exact(solver):
     topo, batch, _ = synthetic.uwb_imu_lidar(64, 20, 8)
     Hd, Ho, b, _ = oracle.linearize(topo, batch, Config())

@@ -94,6 +94,7 @@ struct uwbgo_ctx {
     int device = 0;
     int n_lanes = 8;
     int64_t chunk = 8192;
+    bool pipeline_set = false; /* uwbgo_set_pipeline was called: the caller's split is taken as is */
     Lane lane[MAX_LANES];
     DevBuf misc;          /* staging of the stand-alone factor/solve call, FP64 peak probe */
     DevBuf ant;
@@ -656,6 +657,7 @@ int uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes)
         return fail(UWBGO_E_INVALID, "windows_per_chunk >= 32 and 1 <= n_lanes <= 8 required");
     ctx->chunk = (windows_per_chunk + 31) / 32 * 32;
     ctx->n_lanes = n_lanes;
+    ctx->pipeline_set = true;
     return 0;
 }
 
@@ -773,6 +775,11 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
      * that fits n_lanes chunks is split evenly and all its chunks run concurrently */
     int64_t chunk = std::min<int64_t>(ctx->chunk, (W + 31) / 32 * 32);
     if (W <= ctx->chunk * ctx->n_lanes) chunk = std::max<int64_t>(32, ((W + ctx->n_lanes - 1) / ctx->n_lanes + 31) / 32 * 32);
+    /* 6x6 windows: the CTA-per-tile kernel holds 2 tiles per SM and a tile takes the whole kernel time
+     * whatever the launch size, so up to one device-full of tiles a split only delays the last chunk's
+     * start by the copies ahead of it (C4a, 8,192 windows: 14.0 ms in one chunk, 18.3 ms in eight) */
+    const bool six = !(te->fast_ok && in->pose_R == nullptr);
+    if (six && !ctx->pipeline_set && W <= 2 * 148 * TILE) chunk = (W + 31) / 32 * 32;
     StageLayout S;
     {
         size_t o = 0;

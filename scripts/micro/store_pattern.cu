@@ -33,13 +33,35 @@ __global__ void k(double2 *out, int N, int R, long tiles, int streaming)
     }
 }
 
+// mode 2: the four fragments the linearise kernel writes per (window, pose): H_diag 288 B, H_off 224 + 64 B, b 48 B;
+// one pose per warp; launch bounds pin the occupancy (OCC CTAs of 32 threads per SM) like the real kernel's registers do
+template <int OCC>
+__global__ void __launch_bounds__(32, OCC) k4(double2 *Hd, double2 *Ho, double2 *B, int N, long tiles)
+{
+    extern __shared__ double dyn[]; // occupancy limiter
+    const int lane = threadIdx.x & 31;
+    const long item = blockIdx.x;
+    if (item >= tiles * N) return;
+    const long tile = item / N;
+    const int i = (int)(item % N);
+    const double2 v = make_double2((double)item, (double)lane);
+#pragma unroll 8
+    for (int wl = 0; wl < 32; ++wl) {
+        const long w = tile * 32 + wl;
+        double2 *pa = lane < 18 ? Hd + (w * N + i) * 18 + lane : Ho + (w * N + i) * 18 + (lane - 18);
+        *pa = v;
+        if (lane < 4) Ho[(w * N + i) * 18 + 14 + lane] = v;
+        else if (lane < 7) B[(w * N + i) * 3 + (lane - 4)] = v;
+    }
+}
+
 int main()
 {
     const int N = 50;
     const long W = 65536 * 2, tiles = W / 32;   // 2 x H_diag-sized = 1.89 GB
     const size_t bytes = (size_t)W * N * 288;
     double2 *out;
-    CK(cudaMalloc(&out, bytes));
+    CK(cudaMalloc(&out, bytes + (size_t)65536 * 50 * 48 + 4096));
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     auto run = [&](const char *name, auto launch) {
@@ -62,6 +84,26 @@ int main()
             char nm[96]; snprintf(nm, 96, "mode1 32-lane, %d B contiguous per window%s", R * 288, st ? " (st.cs)" : "");
             int runs = (N + R - 1) / R; long warps = tiles * runs;
             run(nm, [&] { k<1><<<(unsigned)((warps * 32 + 255) / 256), 256>>>(out, N, R, tiles, st); });
+        }
+    }
+    {
+        const long W4 = 65536, tiles4 = W4 / 32;
+        double2 *Hd = out, *Ho = out + (size_t)W4 * N * 18, *B = Ho + (size_t)W4 * N * 18;   // 2 x 0.94 GB + 0.16 GB < 1.89 GB
+        const size_t b4 = (size_t)W4 * N * (288 + 288 + 48);
+        auto run4 = [&](const char *name, auto launch) {
+            float best = 1e9;
+            for (int r = 0; r < 5; ++r) {
+                cudaEventRecord(a); launch(); cudaEventRecord(b); cudaEventSynchronize(b);
+                float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
+            }
+            printf("%-44s %.3f ms  %.0f GB/s\n", name, best, b4 / best / 1e6);
+        };
+        // dynamic smem pins CTAs per SM: 227 KB / occ
+        cudaFuncSetAttribute(k4<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int occ : {32, 24, 16, 8}) {
+            char nm[96]; snprintf(nm, 96, "4-fragment pattern, %d warps per SM", occ);
+            size_t sm = occ == 32 ? 0 : (size_t)(220 * 1024 / occ) - 1024;
+            run4(nm, [&] { k4<32><<<(unsigned)(tiles4 * N), 32, sm>>>(Hd, Ho, B, N, tiles4); });
         }
     }
     CK(cudaDeviceSynchronize());

@@ -55,6 +55,36 @@ __global__ void __launch_bounds__(32, OCC) k4(double2 *Hd, double2 *Ho, double2 
     }
 }
 
+// mode 3: the same four-fragment output, but through the bulk-copy engine: each warp fills a window-major panel
+// [32 windows][78 doubles] in shared memory, then every lane hands its window's three rows (288 + 288 + 48 B) to
+// cp.async.bulk (shared -> global).  WARPS warps per CTA, panel per warp 19,968 B.
+__device__ __forceinline__ unsigned saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) kbulk(double *Hd, double *Ho, double *B, int N, long tiles, int items_per_warp)
+{
+    extern __shared__ __align__(16) double panel_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *panel = panel_all + (size_t)warp * 32 * 78;
+    double *mine = panel + lane * 78;
+    for (int k = 0; k < 78; ++k) mine[k] = 0.0;
+    const long first = ((long)blockIdx.x * WARPS + warp) * items_per_warp;
+    for (int it = 0; it < items_per_warp; ++it) {
+        const long item = first + it;
+        if (item >= tiles * N) break;
+        const long tile = item / N;
+        const int i = (int)(item % N);
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        for (int k = 0; k < 21; ++k) mine[(k * 7) % 78] = (double)(item + k);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const long w = tile * 32 + lane;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Hd + (w * N + i) * 36), "r"(saddr(mine)), "r"(288) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Ho + (w * N + i) * 36), "r"(saddr(mine + 36)), "r"(288) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(B + (w * N + i) * 6), "r"(saddr(mine + 72)), "r"(48) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main()
 {
     const int N = 50;
@@ -104,6 +134,29 @@ int main()
             char nm[96]; snprintf(nm, 96, "4-fragment pattern, %d warps per SM", occ);
             size_t sm = occ == 32 ? 0 : (size_t)(220 * 1024 / occ) - 1024;
             run4(nm, [&] { k4<32><<<(unsigned)(tiles4 * N), 32, sm>>>(Hd, Ho, B, N, tiles4); });
+        }
+    }
+    {
+        const long W4 = 65536, tiles4 = W4 / 32;
+        double *Hd = (double *)out, *Ho = Hd + (size_t)W4 * N * 36, *B = Ho + (size_t)W4 * N * 36;
+        const size_t b4 = (size_t)W4 * N * (288 + 288 + 48);
+        auto run4 = [&](const char *name, auto launch) {
+            float best = 1e9;
+            for (int r = 0; r < 5; ++r) {
+                cudaEventRecord(a); launch(); cudaEventRecord(b); cudaEventSynchronize(b);
+                float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
+            }
+            printf("%-52s %.3f ms  %.0f GB/s\n", name, best, b4 / best / 1e6);
+        };
+        const size_t per_warp = 32 * 78 * 8;
+        cudaFuncSetAttribute(kbulk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_warp);
+        cudaFuncSetAttribute(kbulk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per_warp));
+        for (int ipw : {1, 4, 16}) {
+            char nm[96]; snprintf(nm, 96, "bulk store, 1-warp CTAs, %d items per warp", ipw);
+            long warps = (tiles4 * N + ipw - 1) / ipw;
+            run4(nm, [&] { kbulk<1><<<(unsigned)warps, 32, per_warp>>>(Hd, Ho, B, N, tiles4, ipw); });
+            snprintf(nm, 96, "bulk store, 4-warp CTAs, %d items per warp", ipw);
+            run4(nm, [&] { kbulk<4><<<(unsigned)((warps + 3) / 4), 128, 4 * per_warp>>>(Hd, Ho, B, N, tiles4, ipw); });
         }
     }
     CK(cudaDeviceSynchronize());

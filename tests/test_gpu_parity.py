@@ -365,6 +365,32 @@ def test_properties_at_full_size(solver):
     assert np.array_equal(got.status[idx], ref.status)
 
 
+@pytest.mark.parametrize("make,iters", [(synthetic.uwb_imu_lidar, 20), (synthetic.uwb_twist, 12)])
+def test_general_properties_at_full_size(solver, make, iters):
+    """BASELINE C4 size (two halves of 8,192 windows, 6x6 blocks, CTA-per-tile kernel, one chunk):
+    accepted LM steps never increase the robust chi2, rotations stay orthonormal, every window runs
+    its iterations, and a sample of windows matches the oracle bit for bit"""
+    W = 8192
+    topo, batch, _ = make(W)
+    cfg = Config(max_iterations=iters)
+    got = solver.solve(topo, batch, cfg)
+    assert solver.last_path == 0
+    _, _, _, chi0 = solver.linearize(topo, batch.slice(0, 1024), cfg)
+    assert (got.chi2[:1024, 1] <= chi0[:, 1]).all()
+    R = got.pose_R.reshape(W, -1, 3, 3)
+    assert np.abs(np.einsum("wnij,wnkj->wnik", R, R) - np.eye(3)).max() < 1e-9
+    assert (got.status[:, 0] >= 1).all() and (got.status[:, 0] <= iters).all()
+    assert ((got.status[:, 2] & ~2) == 0).all()   # at most UWBGO_FLAG_TERMINATED
+    idx = np.arange(0, W, 61)
+    sub = Batch(**{k: (getattr(batch, k)[idx] if k != "ant_offsets" else getattr(batch, k))
+                   for k in ("pose_t", "pose_R", "anchors", "ant_offsets", "range_d", "range_info", "prior_Z",
+                             "prior_info", "se3_Z", "se3_info") if getattr(batch, k) is not None})
+    assert_parity(solver.solve(topo, sub, cfg), oracle.solve(topo, sub, cfg))
+    ref = oracle.solve(topo, sub, cfg)
+    assert np.array_equal(got.pose_t[idx], ref.pose_t) and np.array_equal(got.pose_R[idx], ref.pose_R)
+    assert np.array_equal(got.chi2[idx], ref.chi2) and np.array_equal(got.status[idx], ref.status)
+
+
 def test_non_finite_inputs_are_contained(solver):
     """a NaN / inf measurement poisons only its own window: flagged, no hang, neighbours bit-exact"""
     from localization_b200._ffi import FLAG_NONFINITE

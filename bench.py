@@ -303,9 +303,10 @@ def main():
         achieved = wl_bytes * W / (k_best * 1e-3) / 1e9 if k_best else None
         traffic, traffic_src, fp64_flop, fp64_pipe = None, None, None, None
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp) and W == WINDOWS_PER_GPU and args.workload == "c3":
+        tkey = {"c3": ("lm_chain_tma_kernel", WINDOWS_PER_GPU), "c4a": ("lm_general_cta_kernel", 8192)}.get(args.workload)
+        if os.path.exists(tp) and tkey and W == tkey[1]:
             with open(tp) as f:
-                tj = json.load(f)["lm_chain_tma_kernel"]
+                tj = json.load(f)[tkey[0]]
             traffic, traffic_src = tj["dram_bytes_per_launch"] / 1e9, tj["source"]
             fp64_flop = tj.get("fp64_flop_per_launch")
             fp64_pipe = tj.get("fp64_pipe_active_pct")
@@ -376,7 +377,14 @@ def time_stages(solver, topo, batch, cfg, dev, hbm):
     torch.cuda.synchronize(dev)
     k = float(np.median(ms[1:]))
     ach = ALGO_BYTES_LINEARIZE * W / (k * 1e-3) / 1e9
-    return {"linearize": {"kernel_ms": k, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and W == WINDOWS_PER_GPU:
+        with open(tp) as f:
+            traffic = json.load(f).get("linearize_chain_fused_kernel", {}).get("dram_bytes_per_launch")
+    return {"linearize": {"kernel_ms": k, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "bound": "hbm",
+                          "traffic": traffic / 1e9 if traffic else None,
+                          "traffic_unit": "GB per launch (dram read+write, ncu; algorithmic = %.2f GB)" % (ALGO_BYTES_LINEARIZE * W / 1e9),
                           "algorithmic_bytes_per_window": ALGO_BYTES_LINEARIZE,
                           "what": "linearize_chain_fused_kernel (uwbgo_linearize_batch_device): computeActiveErrors + "
                                   "buildSystem of every window, written as full 6x6 blocks in the public window-major "

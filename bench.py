@@ -36,6 +36,18 @@ ALGO_BYTES_SOLVE = 7408
 ALGO_BYTES_LINEARIZE = 35496
 
 
+NOTE_C3 = ("7.4 KB of algorithmic bytes per window against ~1.1 Mflop of FP64 per window: by the algorithmic "
+                        "bytes the fused solve is far from the HBM roof (SURVEY 8d).  What it really moves is its scratch: "
+                        "the per-pose substitution records and estimates are streamed out and back once per LM trial "
+                        "(traffic, from ncu), and at the measured kernel time that stream runs at traffic_rate_gbs = "
+                        "traffic_frac of the HBM peak -- the kernel is bounded by its own scratch traffic and by FP64 "
+                        "issue latency at the same time (DESIGN.md section 4)")
+NOTE_GENERAL = ("6x6 windows (rotations, antenna offsets, EdgeSE3Prior / EdgeSE3): by the algorithmic bytes the fused solve is "
+                "far from the HBM roof; the CTA-per-tile kernel runs 8 warps per SM at 255 registers and is bounded by FP64 / "
+                "load latency (DESIGN.md sections 3.2 and 4.2); traffic = H and L records, information matrices and spills "
+                "streamed once per LM trial")
+
+
 ARRAYS = ("pose_t", "pose_R", "anchors", "range_d", "range_info", "prior_Z", "prior_info", "se3_Z", "se3_info")
 # name -> (description, default windows per GPU, generator, LM iterations, SURVEY algorithmic bytes per window or None)
 WORKLOADS = {
@@ -316,12 +328,7 @@ def main():
                 "traffic": traffic, "traffic_unit": "GB per launch (dram read+write, ncu)", "traffic_source": traffic_src,
                 "peak_source": how, "kernel_ms": k_best,
                 "algorithmic_bytes_per_window": wl_bytes,
-                "note": "7.4 KB of algorithmic bytes per window against ~1.1 Mflop of FP64 per window: by the algorithmic "
-                        "bytes the fused solve is far from the HBM roof (SURVEY 8d).  What it really moves is its scratch: "
-                        "the per-pose substitution records and estimates are streamed out and back once per LM trial "
-                        "(traffic, from ncu), and at the measured kernel time that stream runs at traffic_rate_gbs = "
-                        "traffic_frac of the HBM peak -- the kernel is bounded by its own scratch traffic and by FP64 "
-                        "issue latency at the same time (DESIGN.md section 4)"}
+                "note": NOTE_C3 if args.workload in ("c3", "c5") else NOTE_GENERAL}
         if traffic and k_best:
             roof["traffic_rate_gbs"] = traffic / (k_best * 1e-3)
             roof["traffic_frac"] = roof["traffic_rate_gbs"] / hbm

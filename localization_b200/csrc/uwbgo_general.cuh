@@ -119,6 +119,9 @@ UWBGO_DI double chi2_6_reg(const double *O, const double *e, double *Oe)
     return chi;
 }
 
+#ifndef UWBGO_GCTA_PF
+#define UWBGO_GCTA_PF 3 /* bit 0: next op's rows in the linearise phase, bit 1: next edge's rows in the residual phase */
+#endif
 /* L2 prefetch of everything the evaluation / linearisation of edge e will read */
 UWBGO_DI void gen_edge_prefetch(const GenEnv &E, const PoseBuf &T, int e)
 {
@@ -488,7 +491,7 @@ UWBGO_DI double gen_linearize_pose_acc(const GenEnv &E, const PoseBuf &T, const 
         for (int o = ob; o < oe; ++o) {
             int2 op = __ldg(reinterpret_cast<const int2 *>(tp.ops + o));
             EdgeRec er = load_edge(tp.edges + op.x);
-            if (!SWEPT && o + 1 < oe) gen_edge_prefetch(E, T, __ldg(&tp.ops[o + 1].edge));
+            if (!SWEPT && (UWBGO_GCTA_PF & 1) && o + 1 < oe) gen_edge_prefetch(E, T, __ldg(&tp.ops[o + 1].edge));
             if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
                 double d = ROW(E.p.rd, er.slot), info = ROW(E.p.ri, er.slot);
                 double P0[3], Q[3], J[6];

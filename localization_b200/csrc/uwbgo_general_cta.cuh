@@ -79,7 +79,7 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
             const PoseBuf T = buf(sh.cur[lane] ^ sel);
             for (int e = warp; e < NE; e += NW) {
                 double chi, rob;
-                if (e + NW < NE) gen_edge_prefetch(E, T, e + NW);
+                if ((UWBGO_GCTA_PF & 2) && e + NW < NE) gen_edge_prefetch(E, T, e + NW);
                 gen_edge_chi(E, T, e, chi, rob);
                 ROW(echi, 2 * e) = chi;
                 ROW(echi, 2 * e + 1) = rob;

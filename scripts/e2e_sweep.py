@@ -14,7 +14,7 @@ for k in ("pose_t", "anchors", "range_d", "range_info"):
 res = Result(pinned_empty((W, N, 3)), None, None, pinned_empty((W, 4)), pinned_empty((W, 4), np.int32))
 def run():
     s.solve(topo, hb, cfg, out=res)
-settings = [(16384, 4), (8192, 8), (10944, 6), (13120, 5), (21856, 3), (32768, 2), (65536, 1), (4096, 8)]
+settings = [(16384, 4), (8192, 8), (10944, 6), (13120, 5), (21856, 3), (32768, 2), (65536, 1), (4096, 8), (6144, 8), (5472, 8), (8192, 4), (12288, 8)]
 for chunk, lanes in settings:
     s.set_pipeline(chunk, lanes)
     for _ in range(2): run()

@@ -415,7 +415,8 @@ TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bo
     L.off_LR = want_LR ? take(N * (fast ? LR_FAST : (t.tree ? LR_TREE : LR_GEN)), 8) : 0;
     L.off_chi2 = take(4, 8);
     L.off_status = take(4, 4);
-    L.off_echi = (!fast && want_LR) ? take((size_t)t.E * 2, 8) : 0;
+    /* per-edge chi2 terms: the general LM kernel, and the fused linearise stage of CHAIN windows */
+    L.off_echi = ((!fast && want_LR) || (fast && !want_LR)) ? take((size_t)t.E * 2, 8) : 0;
     L.bytes = o;
     return L;
 }
@@ -460,7 +461,7 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     ws.ant = d_ant;
     ws.chi2 = reinterpret_cast<double *>(base + L.off_chi2);
     ws.status = reinterpret_cast<int32_t *>(base + L.off_status);
-    ws.echi = (!fast && !so) ? reinterpret_cast<double *>(base + L.off_echi) : nullptr;
+    ws.echi = ((!fast && !so) || (fast && so)) ? reinterpret_cast<double *>(base + L.off_echi) : nullptr;
 
     XposeJobs pj{};
     pj.W = W;

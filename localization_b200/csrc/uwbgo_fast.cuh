@@ -476,9 +476,12 @@ UWBGO_DI void chain_load(const FastEnv &E, const double *__restrict__ T, int i, 
 
 /* H record of pose i from (cx,cy,cz) = t_i and `in`; carry = vertex-0 terms of edge (i, i+1) on
  * entry (zeros at the newest pose: an exact no-op), of edge (i-1, i) on exit */
-template <bool PREV, class M = IeeeMath>
+/* CHI: also return in chi4 the chi2 and robustified chi2 of the anchor edge of pose i, then of edge
+ * (i-1, i) -- what computeActiveErrors + activeChi2 / activeRobustChi2 sum, term by term */
+template <bool PREV, class M = IeeeMath, bool CHI = false>
 UWBGO_DI void chain_build_q(const FastEnv &E, double cx, double cy, double cz, double qx, double qy,
-                            double qz, const ChainIn &in, double *carry, double *h, unsigned *badp = nullptr)
+                            double qz, const ChainIn &in, double *carry, double *h, unsigned *badp = nullptr,
+                            double *chi4 = nullptr)
 {
     unsigned bl = 0;
     unsigned &bad = badp ? *badp : bl;
@@ -487,6 +490,11 @@ UWBGO_DI void chain_build_q(const FastEnv &E, double cx, double cy, double cz, d
     double J[3], Ow, omega_r;
     {
         const double err = in.da - dist3m<M>(cx, cy, cz, qx, qy, qz, bad);
+        if (CHI) {
+            const double chi = err * (in.ia * err);
+            chi4[0] = chi;
+            chi4[1] = (in.robust & 1) ? E.ck.template rho0m<M>(chi, bad) : chi;
+        }
         fast_jac_v0<M>(cx, cy, cz, qx, qy, qz, in.da, E.delta, E.scalar, J, &bad);
         chain_weights<M>(E, err, in.ia, (in.robust & 1) != 0, Ow, omega_r, &bad);
         chain_acc(J, Ow, omega_r, h);
@@ -494,6 +502,11 @@ UWBGO_DI void chain_build_q(const FastEnv &E, double cx, double cy, double cz, d
     double nA[3] = {0.0, 0.0, 0.0}, nOw = 0.0, nOr = 0.0;
     if (PREV) {
         const double err = in.dt - dist3m<M>(in.px, in.py, in.pz, cx, cy, cz, bad);
+        if (CHI) {
+            const double chi = err * (in.it * err);
+            chi4[2] = chi;
+            chi4[3] = (in.robust & 2) ? E.ck.template rho0m<M>(chi, bad) : chi;
+        }
         fast_jac_v0<M>(in.px, in.py, in.pz, cx, cy, cz, in.dt, E.delta, E.scalar, nA, &bad);
         fast_jac_v1<M>(in.px, in.py, in.pz, cx, cy, cz, in.dt, E.delta, E.scalar, J, &bad);
         chain_weights<M>(E, err, in.it, (in.robust & 2) != 0, nOw, nOr, &bad);

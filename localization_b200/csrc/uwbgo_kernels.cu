@@ -955,8 +955,21 @@ UWBGO_DI LcfLane lcf_lane(int lane)
     return L;
 }
 
-template <class M>
-UWBGO_DI void lcf_run(const FastEnv &E, const double *__restrict__ T, const int N, const int i_lo,
+/* per-edge chi2 | robustified chi2 of pose i's two edges into the scratch [tile][2E][32] (edge = data slot
+ * in CHAIN windows: anchor edge of pose i at 2i - 1 (0 for pose 0), edge (i-1, i) at 2i) */
+UWBGO_DI void lcf_put_chi(double *__restrict__ echi, int i, const double *chi4)
+{
+    const int sa = i == 0 ? 0 : 2 * i - 1;
+    ROW(echi, 2 * sa) = chi4[0];
+    ROW(echi, 2 * sa + 1) = chi4[1];
+    if (i > 0) {
+        ROW(echi, 4 * i) = chi4[2];
+        ROW(echi, 4 * i + 1) = chi4[3];
+    }
+}
+
+template <class M, bool CHI>
+UWBGO_DI void lcf_run(const FastEnv &E, const double *__restrict__ T, double *__restrict__ echi, const int N, const int i_lo,
                       const int i_hi, const int64_t tile, const int lane, const int64_t W,
                       double (*panel)[33], double *__restrict__ H_diag, double *__restrict__ H_off,
                       double *__restrict__ b, unsigned &bad)
@@ -981,16 +994,17 @@ UWBGO_DI void lcf_run(const FastEnv &E, const double *__restrict__ T, const int 
     const LcfLane L = lcf_lane(lane);
     const int nw = (int)((W - tile * TILE) < TILE ? (W - tile * TILE) : TILE);
     for (int i = i_hi; i >= i_lo; --i) {
-        double h[HR_FAST];
+        double h[HR_FAST], chi4[4];
 #ifdef UWBGO_LCF_NOLOAD
         for (int k = 0; k < HR_FAST; ++k) h[k] = (double)(i + k);
 #elif defined(UWBGO_LCF_NOCOMPUTE)
         for (int k = 0; k < HR_FAST; ++k) h[k] = cx + k;
 #else
         if (i > 0)
-            chain_build_q<true, M>(E, cx, cy, cz, cur.qx, cur.qy, cur.qz, cur.in, carry, h, &bad);
+            chain_build_q<true, M, CHI>(E, cx, cy, cz, cur.qx, cur.qy, cur.qz, cur.in, carry, h, &bad, chi4);
         else
-            chain_build_q<false, M>(E, cx, cy, cz, cur.qx, cur.qy, cur.qz, cur.in, carry, h, &bad);
+            chain_build_q<false, M, CHI>(E, cx, cy, cz, cur.qx, cur.qy, cur.qz, cur.in, carry, h, &bad, chi4);
+        if (CHI) lcf_put_chi(echi, i, chi4);
 #endif
         if (__any_sync(0xffffffffu, bad != 0)) return; /* the caller repeats the run with IEEE operations */
         __syncwarp();
@@ -1028,6 +1042,9 @@ UWBGO_DI void lcf_run(const FastEnv &E, const double *__restrict__ T, const int 
     }
 }
 
+/* CHI_TERMS: the run warps also write the per-edge chi2 terms (summed by chi_sum_kernel); otherwise, when
+ * want_chi, the leading CTAs walk every tile's edges (fast_chi_pass) */
+template <bool CHI_TERMS>
 __global__ void __launch_bounds__(UWBGO_LCF_WARPS * 32, UWBGO_LCF_MINB)
 linearize_chain_fused_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                              const __grid_constant__ DevWs ws, double *__restrict__ H_diag,
@@ -1083,11 +1100,42 @@ linearize_chain_fused_kernel(const __grid_constant__ DevTopo tp, const __grid_co
     const int i_lo = run * UWBGO_LCF_RUN;
     const int i_hi = (i_lo + UWBGO_LCF_RUN < N ? i_lo + UWBGO_LCF_RUN : N) - 1;
     unsigned bad = 0;
-    lcf_run<NbMath>(E, E.p.T0, N, i_lo, i_hi, tile, lane, ws.W, sm[warp], H_diag, H_off, b, bad);
+    double *echi = CHI_TERMS ? ws.echi + (tile * (size_t)tp.E * 2) * TILE + lane : nullptr;
+    lcf_run<NbMath, CHI_TERMS>(E, E.p.T0, echi, N, i_lo, i_hi, tile, lane, ws.W, sm[warp], H_diag, H_off, b, bad);
     if (__any_sync(0xffffffffu, bad != 0)) {
         bad = 0;
-        lcf_run<IeeeMath>(E, E.p.T0, N, i_lo, i_hi, tile, lane, ws.W, sm[warp], H_diag, H_off, b, bad);
+        lcf_run<IeeeMath, CHI_TERMS>(E, E.p.T0, echi, N, i_lo, i_hi, tile, lane, ws.W, sm[warp], H_diag, H_off, b, bad);
     }
+}
+
+/* activeChi2 / activeRobustChi2 of the stage: the per-edge terms summed in insertion order */
+__global__ void __launch_bounds__(CTA_THREADS)
+chi_sum_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevWs ws)
+{
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (w >= ws.W) return;
+    const int64_t tile = w / TILE;
+    const int lane = (int)(w % TILE);
+    const double *e = ws.echi + (tile * (size_t)tp.E * 2) * TILE + lane;
+    double p = 0.0, r = 0.0;
+    int k = 0;
+    for (; k + 8 <= tp.E; k += 8) {
+        double v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = ROW(e, 2 * k + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            p = p + v[2 * j];
+            r = r + v[2 * j + 1];
+        }
+    }
+    for (; k < tp.E; ++k) {
+        p = p + ROW(e, 2 * k);
+        r = r + ROW(e, 2 * k + 1);
+    }
+    double *c = ws.chi2 + tile * 2 * TILE + lane;
+    ROW(c, 0) = p;
+    ROW(c, 1) = r;
 }
 
 /* the output arrays must be 16-byte aligned (the blocks leave as 16-byte stores) */
@@ -1106,16 +1154,19 @@ cudaError_t launch_linearize_chain_fused(const DevTopo &topo, const DevCfg &cfg,
     const int runs = (topo.N + UWBGO_LCF_RUN - 1) / UWBGO_LCF_RUN;
     const int64_t tiles = n_tiles(ws.W);
     const int64_t run_ctas = (tiles * runs + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS;
-    const int64_t chi_ctas = want_chi ? (tiles + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS : 0;
-    const int64_t ctas = run_ctas + chi_ctas;
-    /* chi2 CTAs lead the grid (every = 1); spreading them over the grid measured slower (0.60 vs 0.55 ms) */
-#ifndef UWBGO_LCF_CHI_SPREAD
-#define UWBGO_LCF_CHI_SPREAD 0
+#ifndef UWBGO_LCF_CHI_TERMS
+#define UWBGO_LCF_CHI_TERMS 1 /* 1: per-edge chi2 terms from the run warps + chi_sum_kernel; 0: chi2 CTAs lead the grid */
 #endif
-    int64_t every = (UWBGO_LCF_CHI_SPREAD && chi_ctas) ? (ctas * 3 / 4) / chi_ctas : 1;
-    if (every < 1) every = 1;
-    linearize_chain_fused_kernel<<<(unsigned)ctas, UWBGO_LCF_WARPS * 32, 0, st>>>(topo, cfg, ws, H_diag, H_off, b, runs,
-                                                                                  want_chi ? 1 : 0, (int)every);
+    const bool terms = want_chi && UWBGO_LCF_CHI_TERMS && ws.echi;
+    const int64_t chi_ctas = (want_chi && !terms) ? (tiles + UWBGO_LCF_WARPS - 1) / UWBGO_LCF_WARPS : 0;
+    const int64_t ctas = run_ctas + chi_ctas;
+    if (terms) {
+        linearize_chain_fused_kernel<true><<<(unsigned)ctas, UWBGO_LCF_WARPS * 32, 0, st>>>(topo, cfg, ws, H_diag, H_off, b,
+                                                                                            runs, 0, 1);
+        chi_sum_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, ws);
+    } else
+        linearize_chain_fused_kernel<false><<<(unsigned)ctas, UWBGO_LCF_WARPS * 32, 0, st>>>(topo, cfg, ws, H_diag, H_off, b,
+                                                                                             runs, want_chi ? 1 : 0, 1);
     return cudaGetLastError();
 }
 

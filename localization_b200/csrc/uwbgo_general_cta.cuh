@@ -35,22 +35,25 @@ namespace uwbgo {
 #define UWBGO_GCTA_SMEM_ACC 0 /* 1: accumulators of the linearise phase in shared memory -- fewer spills (2.4 KB -> 0.6 KB
                                 * of spill code) but slower: 11.2 vs 10.5 ms on C4a, 85.5 vs 76.9 ms at 65,536 windows */
 #endif
-constexpr size_t GCTA_DYN_SMEM = UWBGO_GCTA_SMEM_ACC ? sizeof(double) * HR_GEN * UWBGO_GCTA_WARPS * 32 : 0;
+constexpr size_t gcta_dyn_smem(int nw) { return UWBGO_GCTA_SMEM_ACC ? sizeof(double) * HR_GEN * nw * 32 : 0; }
 
+constexpr int GCTA_MAX_WARPS = 8;
 struct GctaShared {
     double ant[3 * MAX_SMEM_ANTENNAS];
-    double maxd[UWBGO_GCTA_WARPS][TILE]; /* L -> F: max |H_kk| over the poses each warp linearised */
+    double maxd[GCTA_MAX_WARPS][TILE];   /* L -> F: max |H_kk| over the poses each warp linearised */
     int lin[TILE];                       /* D -> L: window starts an iteration (buildSystem)       */
     int cur[TILE];                       /* D -> all: which pose buffer holds the estimate         */
     int act[TILE];                       /* D -> all: window still being optimised                 */
     int go, anylin;
 };
 
-__global__ void __launch_bounds__(UWBGO_GCTA_WARPS * 32, UWBGO_GCTA_MINB)
+/* NW warps per tile: 4 (two CTAs per SM at 255 registers) is the default; when the batch has no more tiles
+ * than the device has SMs, 8 warps and one CTA per SM halve the rounds of the L / U / C phases */
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                       const __grid_constant__ DevWs ws)
 {
-    constexpr int NW = UWBGO_GCTA_WARPS;
     __shared__ GctaShared sh;
 #if UWBGO_GCTA_SMEM_ACC
     extern __shared__ double gcta_acc[]; /* [HR_GEN][NW * 32] */

@@ -853,12 +853,32 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
 #define UWBGO_GEN_CTA 1 /* 1: one CTA per tile, phases split over its warps; 0: one thread per window */
 #endif
         if (UWBGO_GEN_CTA && ws.echi) {
-            if (GCTA_DYN_SMEM > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(lm_general_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)GCTA_DYN_SMEM);
-                if (e != cudaSuccess) return e;
+            static int sms = 0;
+            if (!sms) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             }
-            lm_general_cta_kernel<<<(unsigned)n_tiles(ws.W), UWBGO_GCTA_WARPS * 32, GCTA_DYN_SMEM, st>>>(topo, cfg, ws);
+            const unsigned tiles = (unsigned)n_tiles(ws.W);
+#ifndef UWBGO_GCTA_WIDE
+#define UWBGO_GCTA_WIDE 1 /* 8-warp CTAs for batches of at most one tile per SM */
+#endif
+            if (UWBGO_GCTA_WIDE && (int)tiles <= sms) {
+                auto kern = lm_general_cta_kernel<8, 1>;
+                if (gcta_dyn_smem(8) > 48 * 1024) {
+                    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gcta_dyn_smem(8));
+                    if (e != cudaSuccess) return e;
+                }
+                kern<<<tiles, 8 * 32, gcta_dyn_smem(8), st>>>(topo, cfg, ws);
+            } else {
+                auto kern = lm_general_cta_kernel<UWBGO_GCTA_WARPS, UWBGO_GCTA_MINB>;
+                if (gcta_dyn_smem(UWBGO_GCTA_WARPS) > 48 * 1024) {
+                    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)gcta_dyn_smem(UWBGO_GCTA_WARPS));
+                    if (e != cudaSuccess) return e;
+                }
+                kern<<<tiles, UWBGO_GCTA_WARPS * 32, gcta_dyn_smem(UWBGO_GCTA_WARPS), st>>>(topo, cfg, ws);
+            }
         }
         else
             lm_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);

@@ -133,8 +133,13 @@ def cpu_baseline(topo, batch, cfg, budget_s=12.0, name="C3"):
     t0 = time.perf_counter()
     oracle.solve(topo, batch.slice(0, n), cfg, n_threads=cores)
     dt = time.perf_counter() - t0
+    n1 = int(min(batch.n_windows, max(64, n / dt / cores * 1.5)))   # about 1.5 s on one thread
+    t0 = time.perf_counter()
+    oracle.solve(topo, batch.slice(0, n1), cfg, n_threads=1)
+    dt1 = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} of the {batch.n_windows} {name} windows, {cores} threads, {dt:.2f} s"}
+            "sample": f"{n} of the {batch.n_windows} {name} windows, {cores} threads, {dt:.2f} s",
+            "single_core": {"value": n1 / dt1, "unit": UNIT, "sample": f"{n1} windows, 1 thread, {dt1:.2f} s"}}
 
 
 def run_reference(args, rank, world):

@@ -509,7 +509,7 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
 #endif
         if (UWBGO_LIN_FUSED && fast && linearize_chain_fused_ok(tp, so->H_diag, so->H_off, so->b)) {
             CU(launch_linearize_chain_fused(tp, cfg, ws, so->H_diag, so->H_off, so->b, so->chi2 != nullptr, st));
-            ctx->launches -= 1; /* one kernel */
+            if (!so->chi2) ctx->launches -= 1; /* the fused kernel alone, or the fused kernel + chi_sum_kernel */
         } else {
             CU(launch_linearize(tp, cfg, ws, st));
             CU(launch_expand_H(tp, ws, so->H_diag, so->H_off, so->b, st));

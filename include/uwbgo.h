@@ -161,7 +161,8 @@ int uwbgo_solve_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo, const u
 int uwbgo_linearize_batch(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
                           const uwbgo_config *cfg, double *H_diag, double *H_off, double *b,
                           double *chi2);
-/* device-pointer variant, queued on `stream` */
+/* device-pointer variant, queued on `stream`.  Any alignment of the output arrays is accepted; with
+ * 16-byte aligned H_diag / H_off / b the windows addRangeEdge builds take the one-kernel path. */
 int uwbgo_linearize_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo,
                                  const uwbgo_batch *in, const uwbgo_config *cfg, double *H_diag,
                                  double *H_off, double *b, double *chi2, void *stream);

@@ -121,6 +121,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Several ranks on one host: run this rank (and first-touch its pinned host buffers) on the CPUs NVML reports
+    as closest to its GPU, so the end-to-end leg's host<->device copies do not cross sockets.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus ({min(cpus)}-{max(cpus)})"
+    except Exception as e:  # noqa: BLE001
+        return f"unavailable: {type(e).__name__}"
+    return None
+
+
 def cpu_baseline(topo, batch, cfg, budget_s=12.0, name="C3"):
     """oracle (CPU restatement of the reference's g2o LM) on a bounded sample, all host threads"""
     from oracle import oracle
@@ -197,6 +216,7 @@ def main():
     from localization_b200 import Config, Solver, synthetic, _ffi
     from localization_b200.solver import pinned_empty
 
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -347,12 +367,14 @@ def main():
         stages = None
         if (args.stages or world == 1) and not args.no_stages and args.workload == "c3":
             stages = time_stages(solver, topo, batch, cfg, dev, hbm)
-        cpu = None if args.no_cpu else cpu_baseline(topo, batch, cfg, name=args.workload.upper())
+        # the CPU leg runs at N = 1 only (the contract; at N > 1 this rank is bound to its GPU's CPUs)
+        cpu = None if (args.no_cpu or world > 1) else cpu_baseline(topo, batch, cfg, name=args.workload.upper())
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl_desc, "windows_per_gpu": W, "n_poses": N, "n_anchors": topo.n_anchors,
                            "lm_iterations": wl_iters, "parallelism": f"windows sharded x{world}, no data-path collective",
+                           "host_affinity": numa,
                            "l2": f"inputs ({h2d / 1e6:.0f} MB) and workspace per step exceed the 126 MB L2"
                                  if h2d > 126e6 else f"inputs {h2d / 1e6:.0f} MB; the LM workspace is rewritten every trial"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

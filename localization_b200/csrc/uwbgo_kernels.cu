@@ -703,6 +703,38 @@ linearize_general_kernel(const __grid_constant__ DevTopo tp, const __grid_consta
     ROW(c, 1) = r;
 }
 
+/* The same stage with the work list of a tile spread out: one warp (= one CTA) per (tile, pose) builds that
+ * pose's H record (gen_linearize_pose, lane = window); the chi2 passes -- one warp walks a tile's edges in
+ * insertion order -- lead the grid.  Thread-per-window gives a 6x6 batch of a few thousand windows a handful
+ * of warps per SM; this gives it N + 1 times as many.  Same device functions, same bits. */
+__global__ void __launch_bounds__(32)
+linearize_general_pose_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+                              const __grid_constant__ DevWs ws)
+{
+    __shared__ double s_ant[3 * MAX_SMEM_ANTENNAS];
+    const int lane = threadIdx.x;
+    if (tp.K <= MAX_SMEM_ANTENNAS)
+        for (int k = lane; k < 3 * tp.K; k += 32) s_ant[k] = ws.ant[k];
+    __syncwarp();
+    const int64_t tiles = n_tiles(ws.W);
+    const bool chi = (int64_t)blockIdx.x < tiles;
+    const int64_t item = (int64_t)blockIdx.x - tiles;
+    const int64_t tile = chi ? (int64_t)blockIdx.x : item / tp.N;
+    const int64_t w = tile * TILE + lane;
+    if (w >= ws.W) return; /* padded lanes of the last tile */
+    GenEnv E;
+    gen_env_init(E, tp, cfg, ws, w, s_ant);
+    const PoseBuf T0{E.p.T0, E.p.Rm0};
+    if (chi) {
+        double p, r;
+        gen_chi_pass(E, T0, p, r);
+        double *c = ws.chi2 + tile * 2 * TILE + lane;
+        ROW(c, 0) = p;
+        ROW(c, 1) = r;
+    } else
+        gen_linearize_pose<false>(E, T0, (int)(item % tp.N));
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* layout kernels                                                                               */
 /* ------------------------------------------------------------------------------------------ */
@@ -896,8 +928,15 @@ cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs
         cudaError_t e = cudaFuncSetAttribute(linearize_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         linearize_fast_kernel<<<window_blocks(ws.W), CTA_THREADS, sm, st>>>(topo, cfg, ws, ais);
-    } else
-        linearize_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
+    } else {
+#ifndef UWBGO_LIN_GEN_POSE
+#define UWBGO_LIN_GEN_POSE 1 /* 1: one warp per (tile, pose); 0: one thread per window */
+#endif
+        if (UWBGO_LIN_GEN_POSE)
+            linearize_general_pose_kernel<<<(unsigned)(n_tiles(ws.W) * (topo.N + 1)), 32, 0, st>>>(topo, cfg, ws);
+        else
+            linearize_general_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, cfg, ws);
+    }
     return cudaGetLastError();
 }
 

@@ -179,3 +179,18 @@ def test_cpp_type_api():
     subprocess.check_call(["make", "-s", "-C", host_dir, "test_types"])
     out = subprocess.run([os.path.join(host_dir, "test_types")], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "host type API ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_pin_set_export(tmp_path):
+    """tests/export_pin_set.py: windows as g2o text + the oracle's answers, for checking against a real g2o"""
+    import json
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(__file__), "export_pin_set.py")
+    subprocess.check_call([sys.executable, script, "--out", str(tmp_path), "--windows", "1"])
+    exp = json.load(open(tmp_path / "expected.json"))
+    assert len(exp) == 5
+    from localization_b200.tools import g2o_text
+    for f, e in exp.items():
+        topo, batch = g2o_text.read_window(str(tmp_path / f))[:2]
+        assert len(e["pose_t"]) == topo.n_poses and e["iterations"] >= 1

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UWBGO_ABI_VERSION 1
+#define UWBGO_ABI_VERSION 2
 
 /* error codes */
 #define UWBGO_OK              0
@@ -67,8 +67,17 @@ typedef struct uwbgo_topology {
                                 /*     (chains: its predecessor; addPoseEdge: its key vertex, */
                                 /*     localization.cpp:258-267), else UWBGO_E_TOPOLOGY       */
     const int32_t *edge_ant;    /* [E] RANGE_*: antenna number of the vertex-0 offset,       */
-                                /*     0 = identity, k>0 = ant_offsets[k-1] (localization.cpp:333) */
+                                /*     0 = identity, k>0 = ant_offsets[k-1] (localization.cpp:333). */
+                                /*     Only the translation of an offset isometry reaches the      */
+                                /*     residual: (X * O).translation() = R_X t_O + t_X             */
     const int32_t *edge_robust; /* [E] 1 = RobustKernelCauchy (delta 1), 0 = no kernel       */
+    const int32_t *edge_ant_b;  /* [E] RANGE_*: antenna number of the vertex-1 offset, same      */
+                                /*     numbering as edge_ant: offset[1] of EdgeSE3Range           */
+                                /*     (types_edge_se3range.cpp:99-114), pidTo of                  */
+                                /*     EdgeSE3RangeOffset (types_edge_se3range_offset.cpp:126-149). */
+                                /*     Anchors are identity-rotation vertices, so on RANGE_ANCHOR  */
+                                /*     the offset adds to the anchor position.  NULL = all 0       */
+                                /*     (what Localization creates, localization.cpp:333)           */
 } uwbgo_topology;
 
 /* Per-window numeric data, window-major.  Er/Ep/Es = number of RANGE_*, PRIOR, SE3 edges. */

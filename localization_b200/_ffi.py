@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EDGE_RANGE_ANCHOR = 0
 EDGE_RANGE_POSE = 1
@@ -33,7 +33,7 @@ class CTopology(C.Structure):
         ("n_poses", C.c_int32), ("n_anchors", C.c_int32), ("n_antennas", C.c_int32),
         ("n_edges", C.c_int32),
         ("edge_kind", _pi), ("edge_a", _pi), ("edge_b", _pi), ("edge_ant", _pi),
-        ("edge_robust", _pi),
+        ("edge_robust", _pi), ("edge_ant_b", _pi),
     ]
 
 

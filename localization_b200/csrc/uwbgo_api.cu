@@ -152,6 +152,9 @@ int validate_topology(const uwbgo_topology *T, std::vector<int32_t> &slot, Slots
         if (T->edge_kind[e] <= UWBGO_EDGE_RANGE_POSE && T->edge_ant &&
             (T->edge_ant[e] < 0 || T->edge_ant[e] > T->n_antennas))
             return fail(UWBGO_E_INVALID, "edge_ant out of range");
+        if (T->edge_kind[e] <= UWBGO_EDGE_RANGE_POSE && T->edge_ant_b &&
+            (T->edge_ant_b[e] < 0 || T->edge_ant_b[e] > T->n_antennas))
+            return fail(UWBGO_E_INVALID, "edge_ant_b out of range");
     }
     return 0;
 }
@@ -165,7 +168,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     if (rc) return rc;
     const int N = T->n_poses, E = T->n_edges;
     std::vector<int32_t> key;
-    key.reserve(5 + 5 * (size_t)E);
+    key.reserve(5 + 6 * (size_t)E);
     key.push_back(N);
     key.push_back(T->n_anchors);
     key.push_back(T->n_antennas);
@@ -176,6 +179,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
         key.push_back(T->edge_b[e]);
         key.push_back(T->edge_ant ? T->edge_ant[e] : 0);
         key.push_back(T->edge_robust[e] ? 1 : 0);
+        key.push_back((T->edge_ant_b && T->edge_kind[e] <= UWBGO_EDGE_RANGE_POSE) ? T->edge_ant_b[e] : 0);
     }
     for (auto &t : ctx->topos)
         if (t->key == key) {
@@ -216,6 +220,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
         r.slot = slot[e];
         r.ant = (r.kind <= UWBGO_EDGE_RANGE_POSE && T->edge_ant) ? T->edge_ant[e] : 0;
         r.robust = T->edge_robust[e] ? 1 : 0;
+        r.ant_b = (r.kind <= UWBGO_EDGE_RANGE_POSE && T->edge_ant_b) ? T->edge_ant_b[e] : 0;
         if (r.kind <= UWBGO_EDGE_RANGE_POSE) { /* BaseBinaryEdge numeric Jacobian: 12 oplus per free vertex */
             r.base_a = calls[r.a];
             calls[r.a] += 12;
@@ -229,7 +234,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
         if (r.kind == UWBGO_EDGE_RANGE_POSE || r.kind == UWBGO_EDGE_SE3)
             per_pose[r.b].push_back(PoseOp{e, 1});
         EdgeRec f = r;
-        if (r.kind > UWBGO_EDGE_RANGE_POSE || r.ant != 0) fast_ok = false;
+        if (r.kind > UWBGO_EDGE_RANGE_POSE || r.ant != 0 || r.ant_b != 0) fast_ok = false;
         if (r.kind == UWBGO_EDGE_RANGE_POSE) {
             int k = carry[r.a]++;
             if (k >= 2 || r.b != r.a + 1) fast_ok = false;

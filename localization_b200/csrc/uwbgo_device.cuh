@@ -49,6 +49,15 @@ UWBGO_DI EdgeRec load_edge(const EdgeRec *e)
     EdgeRec r;
     r.kind = u.x; r.a = u.y; r.b = u.z; r.slot = u.w;
     r.ant = v.x; r.robust = v.y; r.base_a = v.z; r.base_b = v.w;
+    r.ant_b = 0; /* the translation-only paths never carry offsets; the general path reads it below */
+    return r;
+}
+
+/* general path: the record with its vertex-1 antenna number */
+UWBGO_DI EdgeRec load_edge_full(const EdgeRec *e)
+{
+    EdgeRec r = load_edge(e);
+    r.ant_b = __ldg(&e->ant_b);
     return r;
 }
 

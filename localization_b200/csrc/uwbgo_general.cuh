@@ -66,6 +66,20 @@ UWBGO_DI void offset_point(const GenEnv &E, const Pose &X, int ant, double *P)
     }
 }
 
+/* vertex 1 of an anchor range edge: a fixed identity-rotation vertex at the anchor, times its offset */
+UWBGO_DI void anchor_point(const GenEnv &E, int b, int ant_b, double *Q)
+{
+    const double *an = E.p.anch + (size_t)b * 3 * TILE;
+    if (ant_b > 0) {
+        const double I3[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+        double o[3] = {E.ant[3 * (ant_b - 1)], E.ant[3 * (ant_b - 1) + 1], E.ant[3 * (ant_b - 1) + 2]};
+        double a[3] = {ROW(an, 0), ROW(an, 1), ROW(an, 2)};
+        mat3_vec_add(I3, o, a, Q);
+    } else {
+        Q[0] = ROW(an, 0); Q[1] = ROW(an, 1); Q[2] = ROW(an, 2);
+    }
+}
+
 /* toVectorMQT(Zinv * Xi^-1 * Xj) */
 UWBGO_DI void se3_error(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *e)
 {
@@ -150,7 +164,7 @@ UWBGO_DI void gen_edge_prefetch(const GenEnv &E, const PoseBuf &T, int e)
 UWBGO_DI void gen_edge_chi(const GenEnv &E, const PoseBuf &T, int e, double &chi_out, double &rob_out)
 {
     const DevTopo &tp = *E.tp;
-    EdgeRec er = load_edge(tp.edges + e);
+    EdgeRec er = load_edge_full(tp.edges + e);
     double chi;
     if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
         Pose Xa;
@@ -158,8 +172,11 @@ UWBGO_DI void gen_edge_chi(const GenEnv &E, const PoseBuf &T, int e, double &chi
         double P0[3], Q[3];
         offset_point(E, Xa, er.ant, P0);
         if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
-            const double *an = E.p.anch + (size_t)er.b * 3 * TILE;
-            Q[0] = ROW(an, 0); Q[1] = ROW(an, 1); Q[2] = ROW(an, 2);
+            anchor_point(E, er.b, er.ant_b, Q);
+        } else if (er.ant_b > 0) {
+            Pose Xb;
+            load_pose(T, er.b, Xb);
+            offset_point(E, Xb, er.ant_b, Q);
         } else {
             const double *tb = T.t + (size_t)er.b * 3 * TILE;
             Q[0] = ROW(tb, 0); Q[1] = ROW(tb, 1); Q[2] = ROW(tb, 2);
@@ -213,6 +230,7 @@ UWBGO_DI void gen_chi_pass(const GenEnv &E, const PoseBuf &T, double &plain, dou
  * calls made on it by earlier edges of this linearisation.  Call k trips the re-orthogonalisation
  * of the PERTURBED estimate when (c0 + k) % mod == 0 (VertexSE3::oplusImpl; push/pop restores the
  * estimate, not the counter). */
+template <bool SECOND = false> /* SECOND: the perturbed pose is vertex 1, its point the subtrahend */
 UWBGO_DI void gen_jac_v0(const GenEnv &E, const Pose &X, int ant, const double *Q, double d, int c0,
                          int base, double *J)
 {
@@ -248,7 +266,8 @@ UWBGO_DI void gen_jac_v0(const GenEnv &E, const Pose &X, int ant, const double *
             } else {
                 P[0] = tp[0]; P[1] = tp[1]; P[2] = tp[2];
             }
-            epm[sg] = d - dist3(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
+            epm[sg] = SECOND ? d - dist3(Q[0], Q[1], Q[2], P[0], P[1], P[2])
+                             : d - dist3(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
         }
         J[dd] = E.scalar * (epm[0] - epm[1]);
     }
@@ -266,7 +285,8 @@ UWBGO_DI void gen_jac_v0(const GenEnv &E, const Pose &X, int ant, const double *
                 mat3_mul(X.R, Rinc, Rp);
                 if (call == 0) orthogonalize(Rp);
                 mat3_vec_add(Rp, o, X.t, P);
-                epm[sg] = d - dist3(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
+                epm[sg] = SECOND ? d - dist3(Q[0], Q[1], Q[2], P[0], P[1], P[2])
+                                 : d - dist3(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
             }
             J[3 + dd] = E.scalar * (epm[0] - epm[1]);
         }
@@ -490,23 +510,22 @@ UWBGO_DI double gen_linearize_pose_acc(const GenEnv &E, const PoseBuf &T, const 
         const int ob = __ldg(tp.op_begin + i), oe = __ldg(tp.op_begin + i + 1);
         for (int o = ob; o < oe; ++o) {
             int2 op = __ldg(reinterpret_cast<const int2 *>(tp.ops + o));
-            EdgeRec er = load_edge(tp.edges + op.x);
+            EdgeRec er = load_edge_full(tp.edges + op.x);
             if (!SWEPT && (UWBGO_GCTA_PF & 1) && o + 1 < oe) gen_edge_prefetch(E, T, __ldg(&tp.ops[o + 1].edge));
             if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
                 double d = ROW(E.p.rd, er.slot), info = ROW(E.p.ri, er.slot);
                 double P0[3], Q[3], J[6];
                 Pose Xo; /* the other pose of a pose-pose edge */
                 if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
-                    const double *an = E.p.anch + (size_t)er.b * 3 * TILE;
-                    Q[0] = ROW(an, 0); Q[1] = ROW(an, 1); Q[2] = ROW(an, 2);
+                    anchor_point(E, er.b, er.ant_b, Q);
                     offset_point(E, Xi, er.ant, P0);
                 } else if (op.y == 0) {
                     load_pose(T, er.b, Xo);
-                    Q[0] = Xo.t[0]; Q[1] = Xo.t[1]; Q[2] = Xo.t[2];
+                    offset_point(E, Xo, er.ant_b, Q);
                     offset_point(E, Xi, er.ant, P0);
                 } else {
                     load_pose(T, er.a, Xo);
-                    Q[0] = Xi.t[0]; Q[1] = Xi.t[1]; Q[2] = Xi.t[2];
+                    offset_point(E, Xi, er.ant_b, Q);
                     offset_point(E, Xo, er.ant, P0);
                 }
                 double err = d - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
@@ -523,7 +542,10 @@ UWBGO_DI double gen_linearize_pose_acc(const GenEnv &E, const PoseBuf &T, const 
                 } else {
                     /* vertex 1: its own terms, and the block H_{a,i} = A^T Ow B of the pair.  Pose a was
                      * swept earlier, so its counter already includes this linearisation's calls. */
-                    gen_jac_v1(E, P0, Xi, d, J);
+                    if (er.ant_b > 0) /* lever arm on vertex 1: rotation columns, counter-driven re-orthogonalisation */
+                        gen_jac_v0<true>(E, Xi, er.ant_b, P0, d, ci, er.base_b, J);
+                    else
+                        gen_jac_v1(E, P0, Xi, d, J);
                     acc1_diag(J, Ow, omega_r, hd, bb);
                     double A[6];
                     const int ca_now = E.p.cnt[(size_t)er.a * TILE];

@@ -39,6 +39,8 @@ struct EdgeRec {
     int32_t robust;  /* Cauchy kernel on/off                                               */
     int32_t base_a;  /* numeric-Jacobian oplus calls made on pose a before this edge's,    */
     int32_t base_b;  /*   resp. on pose b, within one linearisation (VertexSE3 counter)    */
+    int32_t ant_b;   /* antenna number of the vertex-1 offset (0 = none)                   */
+    int32_t pad[3];  /* records stay 16-byte aligned (load_edge reads them as int4)        */
 };
 
 /* Per-pose gather program for Hessian assembly: the edges touching pose i, in insertion

@@ -44,6 +44,7 @@ class Topology:
     edge_b: np.ndarray
     edge_ant: np.ndarray
     edge_robust: np.ndarray
+    edge_ant_b: np.ndarray | None = None  # vertex-1 antenna numbers (offset[1] / pidTo); None = all 0
 
     def __post_init__(self):
         self.edge_kind = _i32(self.edge_kind)
@@ -52,6 +53,12 @@ class Topology:
         self.edge_ant = _i32(self.edge_ant)
         self.edge_robust = _i32(self.edge_robust)
         n = len(self.edge_kind)
+        if self.edge_ant_b is not None:
+            self.edge_ant_b = _i32(self.edge_ant_b)
+            if len(self.edge_ant_b) != n:
+                raise ValueError("edge arrays differ in length")
+            if not self.edge_ant_b.any():
+                self.edge_ant_b = None
         for a in (self.edge_a, self.edge_b, self.edge_ant, self.edge_robust):
             if len(a) != n:
                 raise ValueError("edge arrays differ in length")
@@ -71,14 +78,16 @@ class Topology:
             self.n_poses, self.n_anchors, self.n_antennas, self.n_edges)
         t.edge_kind, t.edge_a, t.edge_b = _pi(self.edge_kind), _pi(self.edge_a), _pi(self.edge_b)
         t.edge_ant, t.edge_robust = _pi(self.edge_ant), _pi(self.edge_robust)
+        t.edge_ant_b = _pi(self.edge_ant_b)
         return t
 
     # -- the window shapes Localization builds -------------------------------------------------
     @staticmethod
     def from_edges(n_poses, n_anchors, n_antennas, edges) -> "Topology":
-        """edges: iterable of (kind, a, b, ant, robust)."""
-        e = np.asarray(list(edges), dtype=np.int32).reshape(-1, 5)
-        return Topology(n_poses, n_anchors, n_antennas, e[:, 0], e[:, 1], e[:, 2], e[:, 3], e[:, 4])
+        """edges: iterable of (kind, a, b, ant, robust) or (kind, a, b, ant, robust, ant_b)."""
+        edges = [tuple(x) + (0,) * (6 - len(x)) for x in edges]
+        e = np.asarray(edges, dtype=np.int32).reshape(-1, 6)
+        return Topology(n_poses, n_anchors, n_antennas, e[:, 0], e[:, 1], e[:, 2], e[:, 3], e[:, 4], e[:, 5])
 
     @staticmethod
     def uwb_chain(n_poses: int, n_anchors: int, antennas: int = 0, imu: bool = False,

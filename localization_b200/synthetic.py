@@ -265,3 +265,14 @@ def uwb_pose(W: int, N: int = 24, A: int = 8, keyframe_len: int = 4, seed: int =
     batch = Batch(pose_t=init_t, pose_R=init_R, anchors=anchors, range_d=rd, range_info=ri,
                   ant_offsets=off, se3_Z=sZ, se3_info=sI)
     return topo, batch, p
+
+
+def with_vertex1_offsets(topo: Topology, seed: int = 0) -> Topology:
+    """The same window with antenna offsets on vertex 1 of its range edges as well
+    (EdgeSE3Range::setVertexOffset(1, .) / EdgeSE3RangeOffset pidTo; the reference's own factories
+    never set them, localization.cpp:333): random antenna numbers 0..K on every range edge."""
+    rng = np.random.default_rng(seed)
+    is_range = topo.edge_kind <= 1
+    ant_b = np.where(is_range, rng.integers(0, topo.n_antennas + 1, size=topo.n_edges), 0)
+    return Topology(topo.n_poses, topo.n_anchors, topo.n_antennas, topo.edge_kind, topo.edge_a, topo.edge_b,
+                    topo.edge_ant, topo.edge_robust, ant_b)

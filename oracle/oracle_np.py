@@ -86,7 +86,9 @@ class Window:
         if k in (EDGE_RANGE_ANCHOR, EDGE_RANGE_POSE):
             o = self.off[tp.edge_ant[e] - 1] if tp.edge_ant[e] > 0 else np.zeros(3)
             P0 = X[a][:3, :3] @ o + X[a][:3, 3]
-            Q = self.anch[b] if k == EDGE_RANGE_ANCHOR else X[b][:3, 3]
+            ab = 0 if tp.edge_ant_b is None else tp.edge_ant_b[e]
+            ob = self.off[ab - 1] if ab > 0 else np.zeros(3)
+            Q = self.anch[b] + ob if k == EDGE_RANGE_ANCHOR else X[b][:3, :3] @ ob + X[b][:3, 3]
             return np.array([self.rd[s] - np.linalg.norm(P0 - Q)])
         if k == EDGE_PRIOR:
             Z = T_from(self.pZ[s][:9].reshape(3, 3), self.pZ[s][9:])

@@ -233,21 +233,29 @@ void uwbgo_oracle_R_to_quat(const double *R, double *q_xyzw) { R_to_quat(R, q_xy
 
 /* EdgeSE3Range::computeError (types_edge_se3range.cpp:105-114):
  *   dt = (X0 * offset0).translation() - (X1 * offset1).translation();  e = d - |dt|
- * offsets are translation-only isometries (localization.cpp:111-123), o1 is always zero here. */
-static double range_error(const pose_t *X0, const double *o0, const double *t1, double d)
+ * Only the translation o of an offset isometry O reaches the residual: (X * O).translation() =
+ * R_X o + t_X.  Same for EdgeSE3RangeOffset (types_edge_se3range_offset.cpp:126-131, n2w of the
+ * CacheSE3Offset = estimate * offset parameter). */
+static double range_error(const pose_t *X0, const double *o0, const double *P1, double d)
 {
     double P0[3];
     mat3_vec_add(X0->R, o0, X0->t, P0);
-    double dx = P0[0] - t1[0], dy = P0[1] - t1[1], dz = P0[2] - t1[2];
+    double dx = P0[0] - P1[0], dy = P0[1] - P1[1], dz = P0[2] - P1[2];
     double n = sqrt((dx * dx + dy * dy) + dz * dz);
     return d - n;
 }
 
-/* translation of (X * 0-offset): R*0 + t, exactly t for finite R */
-static void pose_point(const pose_t *X, double *P)
+/* translation of (X * offset): R*o + t (exactly t for o = 0 and finite R) */
+static void pose_point(const pose_t *X, const double *o, double *P)
 {
-    static const double zero[3] = {0.0, 0.0, 0.0};
-    mat3_vec_add(X->R, zero, X->t, P);
+    mat3_vec_add(X->R, o, X->t, P);
+}
+
+/* vertex 1 of an anchor range edge: a fixed vertex with identity rotation at the anchor position */
+static void anchor_point(const double *anchor, const double *o, double *P)
+{
+    static const double I3[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+    mat3_vec_add(I3, o, anchor, P);
 }
 
 /* g2o internal::toVectorMQT(Isometry): [t; x,y,z of the normalised quaternion with w >= 0] */
@@ -308,6 +316,27 @@ static const double *edge_offset(const window_t *W, int e)
     int a = W->topo->edge_ant ? W->topo->edge_ant[e] : 0;
     return a > 0 ? W->ant + 3 * (a - 1) : ZERO3;
 }
+static const double *edge_offset_b(const window_t *W, int e)
+{
+    int a = W->topo->edge_ant_b ? W->topo->edge_ant_b[e] : 0;
+    return a > 0 ? W->ant + 3 * (a - 1) : ZERO3;
+}
+
+/* error of range edge e at the current estimates */
+static double range_edge_error(const window_t *W, int e)
+{
+    const uwbgo_topology *T = W->topo;
+    double P1[3];
+    if (T->edge_kind[e] == UWBGO_EDGE_RANGE_ANCHOR) {
+        const double *an = W->anchors + 3 * T->edge_b[e];
+        if (T->edge_ant_b && T->edge_ant_b[e] > 0)
+            anchor_point(an, edge_offset_b(W, e), P1);
+        else
+            memcpy(P1, an, sizeof P1);
+    } else
+        pose_point(&W->X[T->edge_b[e]], edge_offset_b(W, e), P1);
+    return range_error(&W->X[T->edge_a[e]], edge_offset(W, e), P1, W->range_d[W->slot[e]]);
+}
 
 /* EdgeSE3::computeError: delta = Zinv * Xi^-1 * Xj, evaluated left to right */
 static void se3_error(const pose_t *Zinv, const pose_t *Xi, const pose_t *Xj, double *e)
@@ -344,15 +373,9 @@ static void compute_errors(window_t *W)
         int a = T->edge_a[e], s = W->slot[e];
         switch (T->edge_kind[e]) {
         case UWBGO_EDGE_RANGE_ANCHOR:
-            er[0] = range_error(&W->X[a], edge_offset(W, e), W->anchors + 3 * T->edge_b[e],
-                                W->range_d[s]);
+        case UWBGO_EDGE_RANGE_POSE:
+            er[0] = range_edge_error(W, e);
             break;
-        case UWBGO_EDGE_RANGE_POSE: {
-            double P1[3];
-            pose_point(&W->X[T->edge_b[e]], P1);
-            er[0] = range_error(&W->X[a], edge_offset(W, e), P1, W->range_d[s]);
-            break;
-        }
         case UWBGO_EDGE_PRIOR: {
             pose_t Z, Zinv;
             load_Z(W->prior_Z + 12 * s, &Z);
@@ -427,9 +450,8 @@ static void range_numeric_jacobian(window_t *W, int e, int which, double *J)
     const uwbgo_topology *T = W->topo;
     const double delta = W->cfg->jacobian_delta;
     const double scalar = 1.0 / (2.0 * delta);
-    int a = T->edge_a[e], kind = T->edge_kind[e], s = W->slot[e];
+    int a = T->edge_a[e];
     int vidx = which == 0 ? a : T->edge_b[e];
-    const double *o0 = edge_offset(W, e);
     for (int d = 0; d < 6; ++d) {
         double ep[2];
         for (int sgn = 0; sgn < 2; ++sgn) {
@@ -437,13 +459,7 @@ static void range_numeric_jacobian(window_t *W, int e, int which, double *J)
             add[d] = sgn == 0 ? delta : -delta;
             pose_t keep = W->X[vidx];                                  /* push */
             pose_oplus(&W->X[vidx], add, &W->cnt[vidx], W->cfg->orthogonalize_after);
-            if (kind == UWBGO_EDGE_RANGE_ANCHOR)
-                ep[sgn] = range_error(&W->X[a], o0, W->anchors + 3 * T->edge_b[e], W->range_d[s]);
-            else {
-                double P1[3];
-                pose_point(&W->X[T->edge_b[e]], P1);
-                ep[sgn] = range_error(&W->X[a], o0, P1, W->range_d[s]);
-            }
+            ep[sgn] = range_edge_error(W, e);
             W->X[vidx] = keep;                                         /* pop */
         }
         J[d] = scalar * (ep[0] - ep[1]);
@@ -803,6 +819,9 @@ static int count_slots(const uwbgo_topology *T, int32_t *slot, int32_t *parent, 
         }
         if (kind <= UWBGO_EDGE_RANGE_POSE && T->edge_ant &&
             (T->edge_ant[e] < 0 || T->edge_ant[e] > T->n_antennas))
+            return UWBGO_E_INVALID;
+        if (kind <= UWBGO_EDGE_RANGE_POSE && T->edge_ant_b &&
+            (T->edge_ant_b[e] < 0 || T->edge_ant_b[e] > T->n_antennas))
             return UWBGO_E_INVALID;
     }
     *Er = er;

@@ -57,6 +57,31 @@ def test_linearize_against_numpy_restatement(make, kw):
     assert (np.abs(b.reshape(b2.shape) - b2) / np.abs(b2).max(axis=1, keepdims=True)).max() < 5e-6
 
 
+def test_vertex1_offsets_against_numpy_restatement():
+    """offset[1] of EdgeSE3Range / pidTo of EdgeSE3RangeOffset (types_edge_se3range.cpp:99-114,
+    types_edge_se3range_offset.cpp:126-149): antenna offsets on vertex 1, anchors included"""
+    topo, batch, _ = synthetic.uwb_imu_lidar(4, 6, 4, seed=12)
+    topo = synthetic.with_vertex1_offsets(topo, seed=3)
+    assert topo.edge_ant_b is not None and (topo.edge_ant_b[topo.edge_kind == 1] > 0).any()
+    assert (topo.edge_ant_b[topo.edge_kind == 0] > 0).any()
+    cfg = Config(max_iterations=6)
+    Hd, Ho, b, chi = oracle.linearize(topo, batch, cfg)
+    H2, b2, chi2 = oracle_np.linearize(topo, batch, cfg)
+    assert np.allclose(chi, chi2, rtol=1e-12, atol=1e-12)
+    H = dense_H(Hd, Ho, topo.parents())
+    scale = np.abs(H).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(H - H2) / scale).max() < 5e-6
+    # the offsets are seen: the same window without them linearises differently
+    base = synthetic.uwb_imu_lidar(4, 6, 4, seed=12)[0]
+    assert not np.array_equal(oracle.linearize(base, batch, cfg)[0], Hd)
+    ref = oracle.solve(topo, batch, cfg)
+    pt, pR, c2, st = oracle_np.solve(topo, batch, cfg)
+    assert np.array_equal(ref.status[:, :2], st)
+    # two roundings of numeric Jacobians with random lever arms on both ends: ~1e-6 m floor
+    assert np.abs(ref.pose_t - pt).max() < 5e-6
+    assert np.allclose(ref.chi2[:, :2], c2, rtol=1e-4)
+
+
 def test_factor_solve_against_dense():
     topo, batch, _ = synthetic.uwb_imu_lidar(8, 10, 4, seed=4)
     Hd, Ho, b, _ = oracle.linearize(topo, batch, Config())

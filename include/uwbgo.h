@@ -140,6 +140,13 @@ const char *uwbgo_last_error(void);
 /* Tuning of the host-pointer entry points: windows per pipeline chunk (rounded up to 32) and
  * number of concurrent stream lanes (1..8).  Defaults: 8192 windows, 8 lanes. */
 int  uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes);
+/* Small batches -- the reference's own call pattern is ONE window per range message
+ * (localization.cpp:371-375) -- take the WINDOW path: one CTA per window, the window's state in
+ * shared memory, the arrays of uwbgo_batch read in place, one kernel launch per call.  Batches of up
+ * to `max_windows` windows go that way (default 296; 0 switches the path off, a negative value
+ * restores the default); larger ones, and windows whose state does not fit the shared memory of
+ * one SM, take the tile kernels.  Results are the same bits either way. */
+int  uwbgo_set_window_path(uwbgo_ctx *ctx, int64_t max_windows);
 /* Page-locked host memory.  The host-pointer entry points accept any host memory; with buffers
  * from uwbgo_host_alloc their copies overlap the kernels of neighbouring chunks. */
 void *uwbgo_host_alloc(size_t bytes);
@@ -154,7 +161,8 @@ int uwbgo_solve_batch(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_ba
 
 /* Same, but every pointer inside `in` (except the struct itself and ant_offsets, which is
  * host memory) and `out` is a DEVICE pointer on the context's GPU, and the work is queued on
- * `stream` (a cudaStream_t; NULL = the default stream) without synchronising. */
+ * `stream` (a cudaStream_t; NULL = the default stream) without synchronising (exception: a call whose
+ * ant_offsets differ from the previous call's waits for the device once, to replace the table). */
 int uwbgo_solve_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo_batch *in,
                              const uwbgo_config *cfg, uwbgo_result *out, void *stream);
 
@@ -189,7 +197,8 @@ int uwbgo_factor_solve_batch_device(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_w
 /* ---- introspection ---------------------------------------------------------------------- */
 /* number of kernels this library launched on ctx since creation (bench "gpu_launches") */
 int64_t uwbgo_launch_count(const uwbgo_ctx *ctx);
-/* 1 if the last solve on ctx used the translation-only (R = I, zero offsets) instantiation */
+/* path of the last solve on ctx: 0 = 6x6 tile kernel, 1 = translation-only tile kernel (R = I, zero
+ * offsets), 2 = its straight-line instantiation for the window addRangeEdge builds, 3 = WINDOW path */
 int     uwbgo_last_path(const uwbgo_ctx *ctx);
 /* Kernel timing for roofline reports: with profiling on, every *_device call records CUDA events
  * on its stream immediately before and after its main kernel (the fused LM kernel of

@@ -70,6 +70,7 @@ SYMBOLS = {
     "uwbgo_destroy": (None, [_vp]),
     "uwbgo_last_error": (C.c_char_p, []),
     "uwbgo_set_pipeline": (C.c_int, [_vp, C.c_int64, C.c_int]),
+    "uwbgo_set_window_path": (C.c_int, [_vp, C.c_int64]),
     "uwbgo_host_alloc": (_vp, [C.c_size_t]),
     "uwbgo_host_free": (None, [_vp]),
     "uwbgo_solve_batch": (C.c_int, [_vp, C.POINTER(CTopology), C.POINTER(CBatch),

@@ -68,6 +68,38 @@ struct DevBuf {
     }
 };
 
+/* grow-only mapped pinned host buffer: the WINDOW path's kernel reads and writes it in place */
+struct PinBuf {
+    void *p = nullptr, *dp = nullptr; /* host address, device address */
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        release();
+        size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer(&dp, p, 0);
+        if (e != cudaSuccess) {
+            release();
+            cudaGetLastError();
+            return fail(UWBGO_E_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = dp = nullptr;
+        cap = 0;
+    }
+};
+
+/* largest batch the WINDOW path takes by default: about two CTAs per SM; beyond that the tile kernels
+ * (lane = window) have enough windows to fill their warps */
+constexpr int64_t WIN_MAX_DEFAULT = 296;
+constexpr size_t WIN_SMEM_LIMIT = 227 * 1024 - 256;
+
 /* a compiled topology, resident on the device */
 struct TopoEntry {
     std::vector<int32_t> key;
@@ -98,6 +130,9 @@ struct uwbgo_ctx {
     Lane lane[MAX_LANES];
     DevBuf misc;          /* staging of the stand-alone factor/solve call, FP64 peak probe */
     DevBuf ant;
+    std::vector<double> ant_host; /* the antenna table `ant` holds */
+    int64_t win_max = WIN_MAX_DEFAULT; /* batches up to this size take the WINDOW path */
+    PinBuf pin;           /* mapped pinned staging of the WINDOW path (host API) */
     std::vector<std::unique_ptr<TopoEntry>> topos;
     uint64_t stamp = 0;
     int64_t launches = 0;
@@ -279,6 +314,14 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
         while (produced < N) sched.push_back(SchedOp{0, produced++});
     }
 
+    /* data slot -> edge: range slots, then prior slots, then se3 slots (WINDOW path work lists) */
+    std::vector<int32_t> slot_edge((size_t)std::max(E, 1), 0);
+    for (int e = 0; e < E; ++e) {
+        const int k = edges[e].kind;
+        const int at = k <= UWBGO_EDGE_RANGE_POSE ? 0 : (k == UWBGO_EDGE_PRIOR ? sl.Er : sl.Er + sl.Ep);
+        slot_edge[(size_t)at + edges[e].slot] = e;
+    }
+
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o_edges = 0;
     size_t o_fedges = o_edges + al(sizeof(EdgeRec) * std::max(E, 1));
@@ -290,8 +333,10 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     size_t o_parent = o_chain + al(sizeof(ChainPose) * N);
     size_t o_cbegin = o_parent + al(sizeof(int32_t) * N);
     size_t o_children = o_cbegin + al(sizeof(int32_t) * (N + 1));
-    size_t total = o_children + al(sizeof(int32_t) * std::max<size_t>(children.size(), 1));
+    size_t o_slotedge = o_children + al(sizeof(int32_t) * std::max<size_t>(children.size(), 1));
+    size_t total = o_slotedge + al(sizeof(int32_t) * slot_edge.size());
     std::vector<char> host(total, 0);
+    memcpy(host.data() + o_slotedge, slot_edge.data(), sizeof(int32_t) * slot_edge.size());
     if (E) {
         memcpy(host.data() + o_edges, edges.data(), sizeof(EdgeRec) * E);
         memcpy(host.data() + o_fedges, fedges.data(), sizeof(EdgeRec) * E);
@@ -333,6 +378,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     g.parent = reinterpret_cast<const int32_t *>(d + o_parent);
     g.child_begin = reinterpret_cast<const int32_t *>(d + o_cbegin);
     g.children = reinterpret_cast<const int32_t *>(d + o_children);
+    g.slot_edge = reinterpret_cast<const int32_t *>(d + o_slotedge);
     ent->gen = g;
     ent->fast = g;
     ent->fast.fast = chain_ok ? 2 : 1;
@@ -551,13 +597,139 @@ int upload_ant(uwbgo_ctx *ctx, const DevTopo &g, const uwbgo_batch *in, cudaStre
 {
     *d_ant = nullptr;
     if (g.K <= 0) return 0;
-    int rc = ctx->ant.reserve(sizeof(double) * 3 * (size_t)g.K);
+    const size_t n = 3 * (size_t)g.K;
+    /* ant_offsets is host memory in both API flavours.  The device copy is kept across calls: the
+     * stream is synchronised only when the table CHANGES (the copy reads caller memory, and kernels
+     * of earlier calls may still be reading the old table); in the steady state nothing is copied
+     * and the *_device entry points queue their work without synchronising */
+    if (ctx->ant.p && ctx->ant_host.size() == n && memcmp(ctx->ant_host.data(), in->ant_offsets, n * sizeof(double)) == 0) {
+        *d_ant = static_cast<const double *>(ctx->ant.p);
+        return 0;
+    }
+    CU(cudaDeviceSynchronize());
+    int rc = ctx->ant.reserve(sizeof(double) * n);
     if (rc) return rc;
-    /* ant_offsets is host memory in both API flavours; tiny, copied synchronously w.r.t. host */
-    CU(cudaMemcpyAsync(ctx->ant.p, in->ant_offsets, sizeof(double) * 3 * (size_t)g.K,
-                       cudaMemcpyHostToDevice, st));
+    ctx->ant_host.assign(in->ant_offsets, in->ant_offsets + n);
+    CU(cudaMemcpyAsync(ctx->ant.p, ctx->ant_host.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
     *d_ant = static_cast<const double *>(ctx->ant.p);
+    return 0;
+}
+
+/* WINDOW path eligibility: small batch, window state fits the shared memory of one SM */
+bool window_path_ok(const uwbgo_ctx *ctx, const TopoEntry &te, int64_t W)
+{
+    return W > 0 && W <= ctx->win_max && window_path_smem_bytes(te.gen) <= WIN_SMEM_LIMIT;
+}
+
+/* WINDOW path on window-major arrays the device can address (device memory, or mapped pinned host
+ * memory): ONE launch, no transposition */
+int run_window(uwbgo_ctx *ctx, const TopoEntry &te, const DevCfg &cfg, const uwbgo_batch *in, const double *d_ant,
+               uwbgo_result *out, cudaStream_t st)
+{
+    WinIo io{};
+    io.W = in->n_windows;
+    io.pose_t = in->pose_t;
+    io.pose_R = in->pose_R;
+    io.cnt_in = in->oplus_count;
+    io.anchors = in->anchors;
+    io.rd = in->range_d;
+    io.ri = in->range_info;
+    io.pZ = in->prior_Z;
+    io.pI = in->prior_info;
+    io.sZ = in->se3_Z;
+    io.sI = in->se3_info;
+    io.ant = d_ant;
+    io.o_pose_t = out->pose_t;
+    io.o_pose_R = out->pose_R;
+    io.o_cnt = out->oplus_count;
+    io.o_chi2 = out->chi2;
+    io.o_status = out->status;
+    const bool timed = ctx->profile;
+    const int kslot = (int)(ctx->k_count % uwbgo_ctx::K_RING);
+    if (timed) CU(cudaEventRecord(ctx->k0[kslot], st));
+    CU(launch_solve_window(te.gen, cfg, io, ctx->device, st));
+    if (timed) {
+        CU(cudaEventRecord(ctx->k1[kslot], st));
+        ctx->k_count += 1;
+    }
+    ctx->launches += 1;
+    ctx->last_path = 3;
+    return 0;
+}
+
+/* host arrays: one memcpy each into the mapped pinned block, one launch that reads and writes the
+ * block in place, one stream synchronise, results copied out */
+int host_window_path(uwbgo_ctx *ctx, const TopoEntry &te, const DevCfg &cfg, const uwbgo_batch *in, uwbgo_result *out)
+{
+    const DevTopo &g = te.gen;
+    const size_t W = (size_t)in->n_windows, N = (size_t)g.N;
+    size_t o = 0;
+    auto take = [&](bool need, size_t bytes) {
+        size_t at = o;
+        if (need) o += (bytes + 63) & ~(size_t)63;
+        return at;
+    };
+    const size_t o_ant = take(g.K > 0, (size_t)g.K * 24);
+    const size_t o_t = take(true, W * N * 24), o_R = take(in->pose_R != nullptr, W * N * 72);
+    const size_t o_cnt = take(in->oplus_count != nullptr, W * N * 4);
+    const size_t o_an = take(g.A > 0, W * g.A * 24);
+    const size_t o_rd = take(g.Er > 0, W * g.Er * 8), o_ri = take(g.Er > 0, W * g.Er * 8);
+    const size_t o_pZ = take(g.Ep > 0, W * g.Ep * 96), o_pI = take(g.Ep > 0, W * g.Ep * 288);
+    const size_t o_sZ = take(g.Es > 0, W * g.Es * 96), o_sI = take(g.Es > 0, W * g.Es * 288);
+    const size_t r_t = take(true, W * N * 24), r_R = take(out->pose_R != nullptr, W * N * 72);
+    const size_t r_cnt = take(out->oplus_count != nullptr, W * N * 4);
+    const size_t r_chi = take(out->chi2 != nullptr, W * UWBGO_CHI2_STRIDE * 8);
+    const size_t r_st = take(out->status != nullptr, W * UWBGO_STATUS_STRIDE * 4);
+    int rc = ctx->pin.reserve(o);
+    if (rc) return rc;
+    char *h = static_cast<char *>(ctx->pin.p), *d = static_cast<char *>(ctx->pin.dp);
+    auto put = [&](const void *src, size_t off, size_t bytes) {
+        if (src && bytes) memcpy(h + off, src, bytes);
+    };
+    if (g.K > 0) put(in->ant_offsets, o_ant, (size_t)g.K * 24);
+    put(in->pose_t, o_t, W * N * 24);
+    put(in->pose_R, o_R, W * N * 72);
+    put(in->oplus_count, o_cnt, W * N * 4);
+    if (g.A > 0) put(in->anchors, o_an, W * g.A * 24);
+    if (g.Er > 0) {
+        put(in->range_d, o_rd, W * g.Er * 8);
+        put(in->range_info, o_ri, W * g.Er * 8);
+    }
+    if (g.Ep > 0) {
+        put(in->prior_Z, o_pZ, W * g.Ep * 96);
+        put(in->prior_info, o_pI, W * g.Ep * 288);
+    }
+    if (g.Es > 0) {
+        put(in->se3_Z, o_sZ, W * g.Es * 96);
+        put(in->se3_info, o_sI, W * g.Es * 288);
+    }
+    uwbgo_batch db{};
+    db.n_windows = in->n_windows;
+    db.pose_t = reinterpret_cast<double *>(d + o_t);
+    db.pose_R = in->pose_R ? reinterpret_cast<double *>(d + o_R) : nullptr;
+    db.oplus_count = in->oplus_count ? reinterpret_cast<int32_t *>(d + o_cnt) : nullptr;
+    db.anchors = reinterpret_cast<double *>(d + o_an);
+    db.range_d = reinterpret_cast<double *>(d + o_rd);
+    db.range_info = reinterpret_cast<double *>(d + o_ri);
+    db.prior_Z = reinterpret_cast<double *>(d + o_pZ);
+    db.prior_info = reinterpret_cast<double *>(d + o_pI);
+    db.se3_Z = reinterpret_cast<double *>(d + o_sZ);
+    db.se3_info = reinterpret_cast<double *>(d + o_sI);
+    uwbgo_result dr{};
+    dr.pose_t = reinterpret_cast<double *>(d + r_t);
+    dr.pose_R = out->pose_R ? reinterpret_cast<double *>(d + r_R) : nullptr;
+    dr.oplus_count = out->oplus_count ? reinterpret_cast<int32_t *>(d + r_cnt) : nullptr;
+    dr.chi2 = out->chi2 ? reinterpret_cast<double *>(d + r_chi) : nullptr;
+    dr.status = out->status ? reinterpret_cast<int32_t *>(d + r_st) : nullptr;
+    cudaStream_t st = ctx->lane[0].st;
+    if ((rc = run_window(ctx, te, cfg, &db, reinterpret_cast<const double *>(d + o_ant), &dr, st))) return rc;
+    CU(cudaStreamSynchronize(st));
+    memcpy(out->pose_t, h + r_t, W * N * 24);
+    if (out->pose_R) memcpy(out->pose_R, h + r_R, W * N * 72);
+    if (out->oplus_count) memcpy(out->oplus_count, h + r_cnt, W * N * 4);
+    if (out->chi2) memcpy(out->chi2, h + r_chi, W * UWBGO_CHI2_STRIDE * 8);
+    if (out->status) memcpy(out->status, h + r_st, W * UWBGO_STATUS_STRIDE * 4);
     return 0;
 }
 
@@ -647,6 +819,7 @@ void uwbgo_destroy(uwbgo_ctx *ctx)
     }
     ctx->misc.release();
     ctx->ant.release();
+    ctx->pin.release();
     for (auto &t : ctx->topos) cudaFree(t->dmem);
     if (ctx->ws_free) cudaEventDestroy(ctx->ws_free);
     for (int k = 0; k < uwbgo_ctx::K_RING; ++k) {
@@ -664,6 +837,13 @@ int uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes)
     ctx->chunk = (windows_per_chunk + 31) / 32 * 32;
     ctx->n_lanes = n_lanes;
     ctx->pipeline_set = true;
+    return 0;
+}
+
+int uwbgo_set_window_path(uwbgo_ctx *ctx, int64_t max_windows)
+{
+    if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
+    ctx->win_max = max_windows < 0 ? WIN_MAX_DEFAULT : max_windows;
     return 0;
 }
 
@@ -699,6 +879,8 @@ int uwbgo_solve_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo, const u
     if ((rc = user_stream_begin(ctx, st))) return rc;
     const double *d_ant = nullptr;
     if ((rc = upload_ant(ctx, te->gen, in, st, &d_ant))) return rc;
+    if (window_path_ok(ctx, *te, in->n_windows)) /* no workspace: nothing to order against other calls */
+        return run_window(ctx, *te, dc, in, d_ant, out, st);
     if ((rc = run_device(ctx, ctx->lane[0], *te, dc, in, d_ant, out, nullptr, st))) return rc;
     return user_stream_end(ctx, st);
 }
@@ -769,6 +951,7 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
     const DevTopo &g = te->gen;
     const int64_t W = in->n_windows;
     if (W == 0) return 0;
+    if (!linearize && window_path_ok(ctx, *te, W)) return host_window_path(ctx, *te, dc, in, out);
     if (ctx->ws_pending) { /* a device-API call may still own lane 0's workspace */
         CU(cudaEventSynchronize(ctx->ws_free));
         ctx->ws_pending = false;

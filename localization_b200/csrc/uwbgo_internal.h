@@ -79,6 +79,8 @@ struct DevTopo {
     const PoseOp *ops;          /* concatenated per-pose op lists                            */
     const int32_t *op_begin;    /* [N+1]                                                     */
     const int32_t *num_calls;   /* [N] numeric oplus calls per linearisation on pose i       */
+    const int32_t *slot_edge;   /* [Er + Ep + Es] edge index of every data slot: range slots, */
+                                /* then prior slots, then se3 slots                          */
 };
 
 struct DevCfg {
@@ -107,6 +109,20 @@ struct DevWs {
     double *echi;       /* [tile][E*2][32] per-edge chi2 | rho0 (general CTA kernel) */
 };
 
+/* WINDOW path (uwbgo_window.cu, one CTA per window): the window-major arrays of the public ABI,
+ * read and written in place -- device memory or mapped pinned host memory */
+struct WinIo {
+    int64_t W;
+    const double *pose_t, *pose_R; /* pose_R NULL = identity rotations */
+    const int32_t *cnt_in;         /* NULL = zeros                     */
+    const double *anchors, *rd, *ri, *pZ, *pI, *sZ, *sI;
+    const double *ant;             /* [K][3]                           */
+    double *o_pose_t, *o_pose_R;   /* o_pose_R, o_cnt, o_chi2, o_status may be NULL */
+    int32_t *o_cnt;
+    double *o_chi2;
+    int32_t *o_status;
+};
+
 /* pack / unpack job: transpose between window-major [W][C] and tile layout [tile][C][32] */
 struct XposeJob {
     const void *src;
@@ -131,6 +147,10 @@ cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st);
 cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st);
 cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,
                              cudaStream_t st);
+/* WINDOW path: whole LM solve, one CTA per window, state in shared memory (uwbgo_window.cu) */
+size_t window_path_smem_bytes(const DevTopo &topo);
+cudaError_t launch_solve_window(const DevTopo &topo, const DevCfg &cfg, const WinIo &io, int device,
+                                cudaStream_t st);
 /* CHAIN windows: linearise straight into the public window-major arrays, one kernel (+ chi2 pass) */
 bool linearize_chain_fused_ok(const DevTopo &topo, const double *H_diag, const double *H_off, const double *b);
 cudaError_t launch_linearize_chain_fused(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,

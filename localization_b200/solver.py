@@ -115,6 +115,10 @@ class Solver:
     def set_pipeline(self, windows_per_chunk: int, n_lanes: int):
         self._check(self._lib.uwbgo_set_pipeline(self._h, windows_per_chunk, n_lanes))
 
+    def set_window_path(self, max_windows: int):
+        """batches of up to max_windows windows take the one-CTA-per-window kernel (0 = never, < 0 = default)"""
+        self._check(self._lib.uwbgo_set_window_path(self._h, max_windows))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.uwbgo_launch_count(self._h))

@@ -373,8 +373,12 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     g.num_calls = reinterpret_cast<const int32_t *>(d + o_calls);
     g.sched = reinterpret_cast<const SchedOp *>(d + o_sched);
     g.n_sched = (int32_t)sched.size();
+    g.n_ops = (int32_t)ops.size();
     g.chain = reinterpret_cast<const ChainPose *>(d + o_chain);
     g.tree = tree ? 1 : 0;
+    g.simple_chain = 1;
+    for (int i = 1; i < N; ++i)
+        if (parent[i] != i - 1) g.simple_chain = 0;
     g.parent = reinterpret_cast<const int32_t *>(d + o_parent);
     g.child_begin = reinterpret_cast<const int32_t *>(d + o_cbegin);
     g.children = reinterpret_cast<const int32_t *>(d + o_children);
@@ -619,7 +623,7 @@ int upload_ant(uwbgo_ctx *ctx, const DevTopo &g, const uwbgo_batch *in, cudaStre
 /* WINDOW path eligibility: small batch, window state fits the shared memory of one SM */
 bool window_path_ok(const uwbgo_ctx *ctx, const TopoEntry &te, int64_t W)
 {
-    return W > 0 && W <= ctx->win_max && window_path_smem_bytes(te.gen) <= WIN_SMEM_LIMIT;
+    return W > 0 && W <= ctx->win_max && window_path_smem_bytes(te.gen, 1) <= WIN_SMEM_LIMIT;
 }
 
 /* WINDOW path on window-major arrays the device can address (device memory, or mapped pinned host
@@ -648,7 +652,9 @@ int run_window(uwbgo_ctx *ctx, const TopoEntry &te, const DevCfg &cfg, const uwb
     const bool timed = ctx->profile;
     const int kslot = (int)(ctx->k_count % uwbgo_ctx::K_RING);
     if (timed) CU(cudaEventRecord(ctx->k0[kslot], st));
-    CU(launch_solve_window(te.gen, cfg, io, ctx->device, st));
+    int ks = window_path_candidates(io.W); /* as many speculative trials as fit the shared memory */
+    while (ks > 1 && window_path_smem_bytes(te.gen, ks) > WIN_SMEM_LIMIT) ks /= 2;
+    CU(launch_solve_window(te.gen, cfg, io, ks, ctx->device, st));
     if (timed) {
         CU(cudaEventRecord(ctx->k1[kslot], st));
         ctx->k_count += 1;

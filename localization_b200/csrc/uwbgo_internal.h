@@ -69,7 +69,9 @@ struct DevTopo {
     int32_t fast;               /* 0 general 6x6 path; 1 translation-only path; 2 translation-only, */
                                 /* standard chain (straight-line sweeps)                            */
     int32_t n_sched;
+    int32_t n_ops;              /* length of `ops`                                           */
     int32_t tree;               /* 1: some pose's older neighbour is not its predecessor     */
+    int32_t simple_chain;       /* 1: parent(i) = i - 1 for every i > 0 (no roots inside)    */
     const ChainPose *chain;     /* [N], fast == 2 only                                       */
     const int32_t *parent;      /* [N] the one older neighbour of pose j, -1 = none          */
     const int32_t *child_begin; /* [N+1] CSR over `children`                                 */
@@ -148,9 +150,10 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
 cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,
                              cudaStream_t st);
 /* WINDOW path: whole LM solve, one CTA per window, state in shared memory (uwbgo_window.cu) */
-size_t window_path_smem_bytes(const DevTopo &topo);
-cudaError_t launch_solve_window(const DevTopo &topo, const DevCfg &cfg, const WinIo &io, int device,
-                                cudaStream_t st);
+int window_path_candidates(int64_t W); /* LM trials evaluated speculatively per round for a batch of W */
+size_t window_path_smem_bytes(const DevTopo &topo, int candidates);
+cudaError_t launch_solve_window(const DevTopo &topo, const DevCfg &cfg, const WinIo &io, int candidates,
+                                int device, cudaStream_t st);
 /* CHAIN windows: linearise straight into the public window-major arrays, one kernel (+ chi2 pass) */
 bool linearize_chain_fused_ok(const DevTopo &topo, const double *H_diag, const double *H_off, const double *b);
 cudaError_t launch_linearize_chain_fused(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,

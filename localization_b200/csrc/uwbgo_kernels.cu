@@ -1409,7 +1409,10 @@ UWBGO_DI unsigned long long mix64(unsigned long long z)
 UWBGO_DI double selftest_operand(unsigned long long r, int mode)
 {
     if (mode == 0) return __longlong_as_double((long long)r);
-    const unsigned long long mant = r & 0x000fffffffffffffULL;
+    unsigned long long mant = r & 0x000fffffffffffffULL;
+    /* one operand in eight ends in a run of ones: significands 1.11..1 and their neighbours are where a
+     * Newton reciprocal can miss the correctly rounded result by an ulp */
+    if (((r >> 59) & 7ULL) == 0) mant |= 0x000fffffffffffffULL >> ((r >> 52) & 3ULL), mant &= ~((r >> 54) & 1ULL);
     const unsigned long long e = 1023ULL - 60ULL + ((r >> 52) % 121ULL);
     const unsigned long long sign = (r >> 63) << 63;
     return __longlong_as_double((long long)(sign | (e << 52) | mant));
@@ -1442,7 +1445,10 @@ __global__ void __launch_bounds__(256) math_selftest_kernel(unsigned long long s
         bad = 0;
         const double lg = NbMath::log_(xs, bad);
         if (bad) ++flagged; else if (!same_bits(lg, det_log(xs))) ++wrong;
-        tried += 4;
+        bad = 0;
+        const double rp = NbMath::rsqrt_pivot(xs, bad); /* the Cholesky pivot of the WINDOW path */
+        if (bad) ++flagged; else if (!same_bits(rp, 1.0 / sqrt(xs))) ++wrong;
+        tried += 5;
     }
     atomicAdd(counts + 0, tried);
     atomicAdd(counts + 1, wrong);

@@ -15,20 +15,29 @@
  *   O   J^T Omega of the 6-D edges: one thread per entry
  *   H   every entry of H_ii (upper), H_{parent(i),i} and b_i is OWNED by one thread, which walks the
  *       pose's edges in g2o insertion order and adds their terms: every entry sees exactly the
- *       accumulation order of the oracle, no atomics, no reductions
+ *       accumulation order of the CPU checker, no atomics, no reductions
  * and per trial
- *   F   block elimination newest pose first on warp 0: the 21 + 6 entries of S_i and of the
+ *   F   block elimination newest pose first on ONE warp: the 21 + 6 entries of S_i and of the
  *       right-hand side are assembled by one lane each, every lane then runs the 6x6 potrf in
  *       registers (redundantly: the sqrt -> reciprocal chain is latency, not throughput), and lanes
  *       0..6 run the SAME triangular substitutions on seven right-hand sides: rows of
  *       H_{parent(i),i} give the rows of G_i and the columns of M_i, b_i gives z_i and c_i.
- *       Then the substitution x_i = c_i - M_i x_parent(i), one lane per row
- *   U   estimate (+) x_i, one thread per pose; computeScale() on the last warp meanwhile
- *   C   computeActiveErrors, one thread per edge; chi2 terms summed in insertion order by thread 0
- *   D   accept / reject, lambda update (thread 0)
- * Per-entry operation sequences are those of the tile kernels (uwbgo_general.cuh) and of the CPU checker:
- * the results are the same bits.
+ *       Then the substitution x_i = c_i - M_i x_parent(i), one lane per row, while a lane of the
+ *       helper warp follows it with the strictly ordered sum of computeScale()
+ *   U   estimate (+) x_i, one lane per pose
+ *   C   computeActiveErrors: 6-D edges on the trial's main warp, range edges on its helper warp
+ *   D   accept / reject, lambda update (thread 0), chi2 terms summed in insertion order
+ * SPECULATION.  What LM does after a REJECTED trial is known before the trial is evaluated: the
+ * same H and b with lambda * nu.  So a round evaluates up to KS candidates lambda, lambda nu,
+ * lambda nu 2nu, ... at once, each on its own pair of warps (F, U, C are per candidate), and D
+ * consumes them in order exactly as the serial loop would: the first accepted candidate ends the
+ * iteration, the others are discarded.  A rejection costs no extra round.  The oplus counter of a
+ * pose advances by one per CONSUMED trial, so candidate k updates with counter + k.
+ * Per-entry operation sequences are those of the tile kernels (uwbgo_general.cuh) and of the CPU
+ * checker: the results are the same bits.
  */
+#include <type_traits>
+
 #include "uwbgo_device.cuh"
 #ifdef UWBGO_WIN_TIMING
 #include <cstdio>
@@ -38,22 +47,40 @@ namespace uwbgo {
 
 namespace {
 
-#ifndef UWBGO_WIN_THREADS
-#define UWBGO_WIN_THREADS 256
+#ifdef UWBGO_WIN_TIMING
+__device__ __forceinline__ long long clk()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
 #endif
-constexpr int WT = UWBGO_WIN_THREADS;
-constexpr int WNW = WT / 32;
 
 /* per-edge linearisation records (doubles) */
 constexpr int RJ = 14;  /* range: A 6 | B 6 | Ow | omega_r                      */
 constexpr int PJ = 79;  /* prior: J 36 | J^T Ow 36 | omega_r 6 | rho1           */
 constexpr int SJ = 151; /* se3:   A 36 | B 36 | A^T Ow 36 | B^T Ow 36 | omega_r 6 | rho1 */
 
+constexpr int WIN_MAX_KS = 4;
+#ifndef UWBGO_WIN_IEEE
+#define UWBGO_WIN_IEEE 0 /* experiment: bit 0 C phase, bit 1 J phase, bit 2 U phase run the IEEE sequences */
+#endif
+using WMC = std::conditional<(UWBGO_WIN_IEEE & 1) != 0, IeeeMath, NbMath>::type;
+using WMJ = std::conditional<(UWBGO_WIN_IEEE & 2) != 0, IeeeMath, NbMath>::type;
+using WMU = std::conditional<(UWBGO_WIN_IEEE & 4) != 0, IeeeMath, NbMath>::type;
+#ifdef UWBGO_WIN_NO6D
+constexpr bool NO6D = true; /* experiment: range-only build, to see what the 6-D code costs in instruction fetch */
+#else
+constexpr bool NO6D = false;
+#endif
+
+/* shared-memory map, offsets in doubles */
 struct WinCarve {
-    int X0, X1, anch, ant, rd, ri, pZi, pI, sZi, sI, rJ, pJ, sJ, Hd, Ho, b, G, M, c, z, x, S, echi, cnt, edges, total;
+    int X, anch, ant, rd, ri, pZi, pI, sZi, sI, rJ, pJ, sJ, Hd, Ho, b, cand, cand_stride;
+    int cnt, parent, cbeg, chl, opb, ncalls, slot_edge, ops, edges, total;
 };
 
-__host__ __device__ inline WinCarve win_carve(const DevTopo &t)
+__host__ __device__ inline WinCarve win_carve(const DevTopo &t, int ks)
 {
     WinCarve c;
     int o = 0;
@@ -62,9 +89,9 @@ __host__ __device__ inline WinCarve win_carve(const DevTopo &t)
         o += (n + 1) & ~1; /* keep 16-byte alignment */
         return at;
     };
+    auto ints = [&](int n) { return take((n + 1) / 2); };
     const int N = t.N;
-    c.X0 = take(N * 12);
-    c.X1 = take(N * 12);
+    c.X = take((ks + 1) * N * 12); /* pool of ks + 1 pose buffers: the estimate and one trial per candidate */
     c.anch = take(t.A * 3);
     c.ant = take(t.K * 3);
     c.rd = take(t.Er);
@@ -79,28 +106,36 @@ __host__ __device__ inline WinCarve win_carve(const DevTopo &t)
     c.Hd = take(N * 21);
     c.Ho = take(N * 36);
     c.b = take(N * 6);
-    c.G = take(N * 36);
-    c.M = take(N * 36);
-    c.c = take(N * 6);
-    c.z = take(N * 6);
-    c.x = take(N * 6);
-    c.S = take(28);
-    c.echi = take(t.E * 2);
-    c.cnt = take((N + 1) / 2);                                  /* int32 [N]        */
-    c.edges = take((int)(sizeof(EdgeRec) / 8) * (t.E > 0 ? t.E : 1)); /* EdgeRec [E]      */
+    /* per candidate: G 36N | M 36N | c 6N | z 6N | x 6N | S 28 | L staging 2 x 22 | echi 2E | 42 zeros (the
+     * G and z of the child the newest pose does not have) */
+    c.cand_stride = ((90 * N + 28 + 44 + 2 * t.E + 1) & ~1) + 42;
+    c.cand = take(ks * c.cand_stride);
+    c.cnt = ints(N);
+    c.parent = ints(N);
+    c.cbeg = ints(N + 1);
+    c.chl = ints(N);
+    c.opb = ints(N + 1);
+    c.ncalls = ints(N);
+    c.slot_edge = ints(t.E > 0 ? t.E : 1);
+    c.ops = ints(2 * (t.n_ops > 0 ? t.n_ops : 1));
+    c.edges = take((int)(sizeof(EdgeRec) / 8) * (t.E > 0 ? t.E : 1));
     c.total = o;
     return c;
 }
 
 struct WinSm {
-    double *X[2], *anch, *ant, *rd, *ri, *pZi, *pI, *sZi, *sI, *rJ, *pJ, *sJ, *Hd, *Ho, *b, *G, *M, *c, *z, *x, *S, *echi;
-    int *cnt;
+    double *X, *anch, *ant, *rd, *ri, *pZi, *pI, *sZi, *sI, *rJ, *pJ, *sJ, *Hd, *Ho, *b, *cand;
+    int cand_stride, xstride;
+    int *cnt, *parent, *cbeg, *chl, *opb, *ncalls, *slot_edge;
+    int2 *ops;
     EdgeRec *edges;
 };
 
 struct WinCtl {
-    int go, lin, cur, ok;
-    double lambda, scale;
+    int go, lin, cur, nk, adv, first;
+    int ok[WIN_MAX_KS];
+    int redo[WIN_MAX_KS]; /* the branch-free arithmetic flagged an operand: the chain runs again with IEEE sequences */
+    double lam[WIN_MAX_KS], scale[WIN_MAX_KS];
 };
 
 UWBGO_DI void ld_pose(const double *p, Pose &X)
@@ -165,27 +200,64 @@ UWBGO_DI double chi2_6s(const double *O, const double *e, double *Oe)
     return chi;
 }
 
+/* Eigen Quaternion(Matrix3) followed by g2o's normalize() (unit length, w >= 0), q = {x,y,z,w}: R_to_quat of
+ * uwbgo_math.cuh with the roots and quotients of the math policy M (the rare trace <= 0 branches keep the
+ * IEEE operations; the bits are the same either way) */
+template <class M>
+UWBGO_DI void R_to_quat_m(const double *R, double *q, unsigned &bad)
+{
+    double t = (R[0] + R[4]) + R[8];
+    if (t > 0.0) {
+        t = M::sqrt_(t + 1.0, bad);
+        q[3] = 0.5 * t;
+        t = M::div(0.5, t, bad);
+        q[0] = (R[7] - R[5]) * t;
+        q[1] = (R[2] - R[6]) * t;
+        q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        if (i == 0) R_to_quat_branch<0>(R, q);
+        else if (i == 1) R_to_quat_branch<1>(R, q);
+        else R_to_quat_branch<2>(R, q);
+    }
+    const double n = M::sqrt_(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3], bad);
+    q[0] = M::div(q[0], n, bad);
+    q[1] = M::div(q[1], n, bad);
+    q[2] = M::div(q[2], n, bad);
+    q[3] = M::div(q[3], n, bad);
+    if (q[3] < 0.0) {
+        q[0] = -q[0];
+        q[1] = -q[1];
+        q[2] = -q[2];
+        q[3] = -q[3];
+    }
+}
+
 /* toVectorMQT(Zinv * X) and the product itself (EdgeSE3Prior::computeError, identity offset) */
-UWBGO_DI void prior_error(const double *Zi, const double *Xp, Pose &Dl, double *q, double *e6)
+template <class M>
+UWBGO_DI void prior_error(const double *Zi, const double *Xp, Pose &Dl, double *q, double *e6, unsigned &bad)
 {
     Pose Zinv, X;
     ld_pose(Zi, Zinv);
     ld_pose(Xp, X);
     pose_mul(Zinv, X, Dl);
-    R_to_quat(Dl.R, q);
+    R_to_quat_m<M>(Dl.R, q, bad);
     e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
     e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
 }
 
 /* toVectorMQT(Zinv * Xi^-1 * Xj), evaluated left to right (EdgeSE3::computeError) */
-UWBGO_DI void se3_error_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *e)
+template <class M>
+UWBGO_DI void se3_error_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *e, unsigned &bad)
 {
     Pose Xi_inv, T, Dl;
     pose_inv(Xi, Xi_inv);
     pose_mul(Zinv, Xi_inv, T);
     pose_mul(T, Xj, Dl);
     double q[4];
-    R_to_quat(Dl.R, q);
+    R_to_quat_m<M>(Dl.R, q, bad);
     e[0] = Dl.t[0]; e[1] = Dl.t[1]; e[2] = Dl.t[2];
     e[3] = q[0]; e[4] = q[1]; e[5] = q[2];
 }
@@ -217,7 +289,8 @@ UWBGO_DI void set_jqq_s(const double *q, double *J)
 
 /* analytic Jacobians of EdgeSE3 (g2o computeEdgeSE3Gradient with identity offsets), written to
  * shared memory */
-UWBGO_DI void se3_jacobians_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *Ji, double *Jj)
+template <class M>
+UWBGO_DI void se3_jacobians_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *Ji, double *Jj, unsigned &bad)
 {
     Pose Xi_inv, Bm, AB;
     pose_inv(Xi, Xi_inv);
@@ -229,7 +302,7 @@ UWBGO_DI void se3_jacobians_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, 
         Jj[k] = 0.0;
     }
     double qE[4];
-    R_to_quat(AB.R, qE);
+    R_to_quat_m<M>(AB.R, qE, bad);
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -249,8 +322,8 @@ UWBGO_DI void se3_jacobians_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, 
 #pragma unroll
         for (int c = 0; c < 3; ++c) Ji[6 * r + 3 + c] = RaS[3 * r + c];
     double qA[4], qB[4], Lm[16], Rm[16];
-    R_to_quat(Ra, qA);
-    R_to_quat(Bm.R, qB);
+    R_to_quat_m<M>(Ra, qA, bad);
+    R_to_quat_m<M>(Bm.R, qB, bad);
     quat_left_s(qA, Lm);
     quat_right_s(qB, Rm);
     double wAB = 0.0;
@@ -268,6 +341,36 @@ UWBGO_DI void se3_jacobians_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, 
         }
 }
 
+/* rotation part of fromVectorMQT and VertexSE3::oplusImpl (uwbgo_math.cuh) with the root of policy M */
+template <class M>
+UWBGO_DI void increment_R_m(const double *q, double *Rinc, unsigned &bad)
+{
+    const double n2 = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
+    double w = 1.0 - n2;
+    if (w < 0.0) {
+        Rinc[0] = 1.0; Rinc[1] = 0.0; Rinc[2] = 0.0;
+        Rinc[3] = 0.0; Rinc[4] = 1.0; Rinc[5] = 0.0;
+        Rinc[6] = 0.0; Rinc[7] = 0.0; Rinc[8] = 1.0;
+    } else {
+        w = M::sqrt_(w, bad);
+        quat_to_R(w, q[0], q[1], q[2], Rinc);
+    }
+}
+template <class M>
+UWBGO_DI void pose_oplus_m(Pose &X, const double *v, int &cnt, int mod, unsigned &bad)
+{
+    Pose inc;
+    increment_R_m<M>(v + 3, inc.R, bad);
+    inc.t[0] = v[0];
+    inc.t[1] = v[1];
+    inc.t[2] = v[2];
+    pose_mul(X, inc, X);
+    if (++cnt >= mod) {
+        cnt = 0;
+        orthogonalize(X.R);
+    }
+}
+
 /* ONE column of the numeric central-difference Jacobian of a range residual (g2o
  * BaseBinaryEdge::linearizeOplus): the pose Xp (shared memory, R|t) with antenna offset `ant` is
  * perturbed along dd, `other` is the other end point.  callbase = (counter of the pose at the start of
@@ -277,8 +380,9 @@ UWBGO_DI void se3_jacobians_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, 
  * a translation increment multiplies by the identity rotation, so the perturbed translation is
  * R[:,dd] * (+-delta) + t in one rounded product and one rounded sum; with the identity offset the
  * point is the translation, rotation columns are exactly 0 and a re-orthogonalisation is invisible. */
+template <class M>
 UWBGO_DI double range_jac_col(const WinSm &sm, const double *Xp, int ant, const double *other, double d, int dd,
-                              int callbase, int mod, double delta, double scalar)
+                              int callbase, int mod, double delta, double scalar, unsigned &bad)
 {
     if (dd >= 3 && ant <= 0) return 0.0;
     double epm[2];
@@ -308,81 +412,380 @@ UWBGO_DI double range_jac_col(const WinSm &sm, const double *Xp, int ant, const 
             }
         } else {
             const double *o = sm.ant + 3 * (ant - 1);
-            double q[3] = {0.0, 0.0, 0.0};
-            q[dd - 3] = v;
+            const double q[3] = {dd == 3 ? v : 0.0, dd == 4 ? v : 0.0, dd == 5 ? v : 0.0};
             double Rinc[9], Rp[9], R[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) R[k] = Xp[k];
-            increment_R(q, Rinc);
+            increment_R_m<M>(q, Rinc, bad);
             mat3_mul(R, Rinc, Rp);
             if (call == 0) orthogonalize(Rp);
             mat3_vec_add(Rp, o, Xp + 9, P);
         }
-        epm[sg] = d - dist3(P[0], P[1], P[2], other[0], other[1], other[2]);
+        epm[sg] = d - dist3m<M>(P[0], P[1], P[2], other[0], other[1], other[2], bad);
     }
     return scalar * (epm[0] - epm[1]);
 }
 
 /* computeError + chi2 of one edge at the estimates X: plain chi2 and its robustified value */
-UWBGO_DI void edge_chi(const WinSm &sm, const double *X, const EdgeRec &er, const Cauchy &ck, double &chi_out,
-                       double &rob_out)
+template <class M>
+UWBGO_DI void range_chi(const WinSm &sm, const double *X, const EdgeRec &er, const Cauchy &ck, double &chi, double &rob,
+                        unsigned &bad)
 {
-    double chi;
-    if (er.kind <= UWBGO_EDGE_RANGE_POSE) {
-        double P0[3], Q[3];
-        range_points(sm, X, er, P0, Q);
-        const double err = sm.rd[er.slot] - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
-        const double Oe = sm.ri[er.slot] * err;
-        chi = err * Oe;
-    } else if (er.kind == UWBGO_EDGE_PRIOR) {
+    double P0[3], Q[3];
+    range_points(sm, X, er, P0, Q);
+    const double err = sm.rd[er.slot] - dist3m<M>(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2], bad);
+    const double Oe = sm.ri[er.slot] * err;
+    chi = err * Oe;
+    rob = er.robust ? ck.rho0m<M>(chi, bad) : chi;
+}
+template <class M>
+UWBGO_DI void six_chi(const WinSm &sm, const double *X, const EdgeRec &er, const Cauchy &ck, double &chi, double &rob,
+                      unsigned &bad)
+{
+    double e6[6], Oe[6];
+    if (er.kind == UWBGO_EDGE_PRIOR) {
         Pose Dl;
-        double q[4], e6[6], Oe[6];
-        prior_error(sm.pZi + 12 * er.slot, X + 12 * er.a, Dl, q, e6);
+        double q[4];
+        prior_error<M>(sm.pZi + 12 * er.slot, X + 12 * er.a, Dl, q, e6, bad);
         chi = chi2_6s(sm.pI + 36 * er.slot, e6, Oe);
     } else {
         Pose Zinv, Xi, Xj;
         ld_pose(sm.sZi + 12 * er.slot, Zinv);
         ld_pose(X + 12 * er.a, Xi);
         ld_pose(X + 12 * er.b, Xj);
-        double e6[6], Oe[6];
-        se3_error_s(Zinv, Xi, Xj, e6);
+        se3_error_s<M>(Zinv, Xi, Xj, e6, bad);
         chi = chi2_6s(sm.sI + 36 * er.slot, e6, Oe);
     }
-    chi_out = chi;
-    rob_out = er.robust ? ck.rho0(chi) : chi;
+    rob = er.robust ? ck.rho0m<M>(chi, bad) : chi;
 }
 
-/* named barrier over the first `count` threads of the CTA */
+/* ---- J-phase items: what one thread computes for one edge (6-D), one range edge's weights, or one
+ * column of a range Jacobian.  Records: see RJ / PJ / SJ. ---------------------------------------------- */
+template <class M>
+UWBGO_DI void lin_six(const WinSm &sm, const double *X, const EdgeRec &er, const Cauchy &ck, unsigned &bad)
+{
+    double e6[6], Oe[6];
+    if (er.kind == UWBGO_EDGE_SE3) {
+        double *rec = sm.sJ + SJ * er.slot;
+        Pose Zinv, Xi, Xj;
+        ld_pose(sm.sZi + 12 * er.slot, Zinv);
+        ld_pose(X + 12 * er.a, Xi);
+        ld_pose(X + 12 * er.b, Xj);
+        se3_error_s<M>(Zinv, Xi, Xj, e6, bad);
+        se3_jacobians_s<M>(Zinv, Xi, Xj, rec, rec + 36, bad);
+        const double chi = chi2_6s(sm.sI + 36 * er.slot, e6, Oe);
+        const double r1 = er.robust ? ck.rho1m<M>(chi, bad) : 1.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double v = -Oe[j];
+            if (er.robust) v = v * r1;
+            rec[144 + j] = v;
+        }
+        rec[150] = r1;
+    } else {
+        double *rec = sm.pJ + PJ * er.slot;
+        Pose Dl;
+        double qq[4];
+        prior_error<M>(sm.pZi + 12 * er.slot, X + 12 * er.a, Dl, qq, e6, bad);
+        const double chi = chi2_6s(sm.pI + 36 * er.slot, e6, Oe);
+        const double r1 = er.robust ? ck.rho1m<M>(chi, bad) : 1.0;
+#pragma unroll
+        for (int j = 0; j < 36; ++j) rec[j] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rec[6 * r + c] = Dl.R[3 * r + c];
+        set_jqq_s(qq, rec);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double v = -Oe[j];
+            if (er.robust) v = v * r1;
+            rec[72 + j] = v;
+        }
+        rec[78] = r1;
+    }
+}
+template <class M>
+UWBGO_DI void lin_range_weights(const WinSm &sm, const double *X, const EdgeRec &er, const Cauchy &ck, unsigned &bad)
+{
+    const int k = er.slot;
+    double P0[3], Q[3];
+    range_points(sm, X, er, P0, Q);
+    const double info = sm.ri[k];
+    const double err = sm.rd[k] - dist3m<M>(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2], bad);
+    const double Oe = info * err;
+    double omega_r = -Oe, Ow = info;
+    if (er.robust) {
+        const double r1 = ck.rho1m<M>(err * Oe, bad);
+        omega_r = omega_r * r1;
+        Ow = r1 * info;
+    }
+    sm.rJ[RJ * k + 12] = Ow;
+    sm.rJ[RJ * k + 13] = omega_r;
+}
+template <class M>
+UWBGO_DI void lin_range_col(const WinSm &sm, const double *X, const EdgeRec &er, const int j, const int adv, const int mod,
+                            const double delta, const double scalar, unsigned &bad)
+{
+    const int k = er.slot, which = j / 6, dd = j - 6 * which;
+    double v = 0.0;
+    if (which == 0) {
+        double Q[3];
+        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR)
+            anchor_point(sm, er.b, er.ant_b, Q);
+        else
+            offset_point(sm, X + 12 * er.b, er.ant_b, Q);
+        v = range_jac_col<M>(sm, X + 12 * er.a, er.ant, Q, sm.rd[k], dd, (sm.cnt[er.a] + adv + er.base_a) % mod, mod,
+                             delta, scalar, bad);
+    } else if (er.kind == UWBGO_EDGE_RANGE_POSE) {
+        double P0[3];
+        offset_point(sm, X + 12 * er.a, er.ant, P0);
+        v = range_jac_col<M>(sm, X + 12 * er.b, er.ant_b, P0, sm.rd[k], dd, (sm.cnt[er.b] + adv + er.base_b) % mod, mod,
+                             delta, scalar, bad);
+    }
+    sm.rJ[RJ * k + j] = v;
+}
+
+/* named barrier over `count` threads */
 UWBGO_DI void bar_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-}  // namespace
+__constant__ unsigned char UP_R[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__constant__ unsigned char UP_C[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
 
-__global__ void __launch_bounds__(WT, 1)
+/* F, main warp of a candidate: block elimination of H + lam I, newest pose first.  cd = the candidate's
+ * block (G | M | c | z | x | S | echi), Lst = its two staging slots for L_i.  Per pose: the 21 + 6
+ * entries of S_i and of the right-hand side are assembled by one lane each, every lane runs the potrf,
+ * lanes 0..6 the forward substitutions; G_i, z_i and L_i go to shared memory and the helper warp is
+ * released (bar.sync with it: it is always waiting, its step is a tenth of this one).  Returns false
+ * when a pivot was not positive. */
+template <class MATH, bool CHAIN>
+UWBGO_DI bool factor_main(const WinSm &sm, double *cd, double *Lst, const int bar_id, const int N, const double lam,
+                          const int lane, unsigned &bad
+#ifdef UWBGO_WIN_TIMING
+                          , long long *tf
+#endif
+)
+{
+#ifdef UWBGO_WIN_TIMING
+    long long tq = clock64();
+#define F_TICK(k) do { long long tn_ = clock64(); tf[k] += tn_ - tq; tq = tn_; } while (0)
+#else
+#define F_TICK(k)
+#endif
+    double *G = cd, *zv = cd + 78 * N, *Sst = cd + 90 * N;
+    /* lane roles of the assembly: 0..20 entry (r, c) of the lower triangle of S, 21..26 row of the rhs */
+    int er_ = 0, ec_ = 0;
+    if (lane < 21) {
+        int kk = lane;
+        while (kk > er_) {
+            kk -= er_ + 1;
+            ++er_;
+        }
+        ec_ = kk;
+    } else if (lane < 27) {
+        er_ = lane - 21;
+    }
+    const int hd_idx = up_idx(6, ec_, er_);
+    /* operand offsets of the child update inside the candidate block: row er_ of G_c times row ec_ of G_c
+     * (S lanes) or times z_c (rhs lanes) */
+    const int a_off = 6 * er_, y_mul = lane < 21 ? 36 : 6, y_off = lane < 21 ? 6 * ec_ : 78 * N;
+    const int pad_off = sm.cand_stride - 42; /* 42 zeros at the end of the candidate block */
+    bool ok = true;
+    /* the assembly inputs of pose i are fetched during the potrf of pose i + 1 */
+    auto fetch = [&](int i, double &v, int &qb, int &qe) {
+        v = 0.0;
+        if (lane < 21)
+            v = sm.Hd[21 * i + hd_idx];
+        else if (lane < 27)
+            v = sm.b[6 * i + er_];
+        if (!CHAIN) {
+            qb = sm.cbeg[i];
+            qe = sm.cbeg[i + 1];
+        }
+    };
+    double vn;
+    int qbn = 0, qen = 0;
+    fetch(N - 1, vn, qbn, qen);
+    for (int i = N - 1; i >= 0; --i) {
+        double v = vn;
+        const int qb = qbn, qe = qen;
+        if (lane < 21 && er_ == ec_) v = v + lam;
+        if (CHAIN) {
+            /* the one child is pose i + 1; the newest pose reads the zero block instead, so the body has no
+             * branch: S(r, c) -= G[r,:] . G[c,:] and rhs(r) -= G[r,:] . z in one stream for all lanes */
+            const int gch = i < N - 1 ? 36 * (i + 1) : pad_off, zch = i < N - 1 ? 78 * N + 6 * (i + 1) : pad_off + 36;
+            const double2 *Ga = reinterpret_cast<const double2 *>(cd + gch + a_off);
+            const double2 *Yb = reinterpret_cast<const double2 *>(cd + (lane < 21 ? gch + 6 * ec_ : zch));
+            const double2 a0 = Ga[0], a1 = Ga[1], a2 = Ga[2], y0 = Yb[0], y1 = Yb[1], y2 = Yb[2];
+            v = fma(-a0.x, y0.x, v);
+            v = fma(-a0.y, y0.y, v);
+            v = fma(-a1.x, y1.x, v);
+            v = fma(-a1.y, y1.y, v);
+            v = fma(-a2.x, y2.x, v);
+            v = fma(-a2.y, y2.y, v);
+        } else {
+#pragma unroll 1
+            for (int qq = qb; qq < qe; ++qq) { /* children in descending order */
+                const int ch = sm.chl[qq];
+                const double2 *Ga = reinterpret_cast<const double2 *>(cd + 36 * ch + a_off);
+                const double2 *Yb = reinterpret_cast<const double2 *>(cd + y_mul * ch + y_off);
+                const double2 a0 = Ga[0], a1 = Ga[1], a2 = Ga[2], y0 = Yb[0], y1 = Yb[1], y2 = Yb[2];
+                v = fma(-a0.x, y0.x, v);
+                v = fma(-a0.y, y0.y, v);
+                v = fma(-a1.x, y1.x, v);
+                v = fma(-a1.y, y1.y, v);
+                v = fma(-a2.x, y2.x, v);
+                v = fma(-a2.y, y2.y, v);
+            }
+        }
+        if (lane < 27) Sst[lane] = v;
+        __syncwarp();
+        F_TICK(0);
+        const bool has_parent = CHAIN ? true : sm.parent[i] >= 0; /* chains: G_0 of the root is zero and unread */
+        double L[21], rhs[6], fw[6];
+        {
+            const double *src = lane < 6 ? sm.Ho + 36 * i + 6 * lane : Sst + 21;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) rhs[k] = src[k];
+        }
+        fetch(i > 0 ? i - 1 : 0, vn, qbn, qen);
+        /* potrf, every lane the whole block, S read where it is used; the diagonal slot keeps 1 / L_jj.
+         * (loops over the full 0..5 range with the triangle as a predicate: constant trip counts, so
+         * that they are all unrolled and L stays in registers) */
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double s = Sst[lo_idx(j, j)];
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if (k < j) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
+            if (!(s > 0.0)) ok = false;
+            const double inv = MATH::rsqrt_pivot(s, bad);
+            L[lo_idx(j, j)] = inv;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+                if (r > j) {
+                    double t = Sst[lo_idx(r, j)];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        if (k < j) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
+                    L[lo_idx(r, j)] = t * inv;
+                }
+        }
+        F_TICK(1);
+        /* forward substitution: row of G_i (lanes 0..5) or z_i (lane 6) */
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+            double s = rhs[cc];
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if (k < cc) s = fma(-fw[k], L[lo_idx(cc, k)], s);
+            fw[cc] = s * L[lo_idx(cc, cc)];
+        }
+        { /* G_i rows (lanes 0..5) and z_i (lane 6): one predicated stream of 16-byte stores */
+            double *dst = lane < 6 ? G + 36 * i + 6 * lane : zv + 6 * i;
+            if ((lane < 6 && has_parent) || lane == 6) {
+                *reinterpret_cast<double2 *>(dst) = make_double2(fw[0], fw[1]);
+                *reinterpret_cast<double2 *>(dst + 2) = make_double2(fw[2], fw[3]);
+                *reinterpret_cast<double2 *>(dst + 4) = make_double2(fw[4], fw[5]);
+            }
+            if (lane == 7) { /* L_i for the helper warp */
+                double *Lo = Lst + 22 * (i & 1);
+#pragma unroll
+                for (int k = 0; k < 20; k += 2) *reinterpret_cast<double2 *>(Lo + k) = make_double2(L[k], L[k + 1]);
+                Lo[20] = L[20];
+            }
+        }
+        F_TICK(2);
+        bar_named(bar_id, 64); /* G_i, z_i (the parent's step reads them) and L_i (the helper's) are visible */
+        F_TICK(3);
+    }
+    return ok;
+}
+
+/* F, helper warp of a candidate: behind every elimination step the backward substitutions
+ * M_i = L_i^-T G_i^T (lanes 0..5, a column each) and c_i = L_i^-T z_i (lane 6), which nothing in the
+ * elimination waits for */
+template <bool CHAIN>
+UWBGO_DI void factor_helper(const WinSm &sm, double *cd, const double *Lst, const int bar_id, const int N, const int lane)
+{
+    double *G = cd, *Mm = cd + 36 * N, *cv = cd + 72 * N, *zv = cd + 78 * N;
+    for (int i = N - 1; i >= 0; --i) {
+        bar_named(bar_id, 64);
+        const bool has_parent = CHAIN ? true : sm.parent[i] >= 0;
+        if (lane < 7 && (lane == 6 || has_parent)) {
+            const double *Li = Lst + 22 * (i & 1);
+            const double *src = lane < 6 ? G + 36 * i + 6 * lane : zv + 6 * i;
+            double L[21], fw[6], bw[6];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) L[k] = Li[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) fw[k] = src[k];
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+                const int r = 5 - rr;
+                double s = fw[r];
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    if (k > r) s = fma(-L[lo_idx(k, r)], bw[k], s);
+                bw[r] = s * L[lo_idx(r, r)];
+            }
+            if (lane < 6) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) Mm[36 * i + 6 * k + lane] = bw[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) cv[6 * i + k] = bw[k];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int KS, int NT>
+__global__ void __launch_bounds__(NT, 1)
 lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                  const __grid_constant__ WinIo io)
 {
+    static_assert(KS >= 1 && KS <= WIN_MAX_KS && 2 * KS * 32 <= NT, "one main and one helper warp per candidate");
     extern __shared__ __align__(16) double wsm[];
     __shared__ WinCtl ctl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef UWBGO_WIN_PAD
+    const int64_t w = blockIdx.x % io.W; /* experiment: redundant CTAs keep the other SMs busy */
+    const bool writer = blockIdx.x < io.W;
+#else
     const int64_t w = blockIdx.x;
+    const bool writer = true;
+#endif
     const int N = tp.N, NE = tp.E, mod = cfg.orth_mod;
-    const WinCarve cv = win_carve(tp);
+    const WinCarve cv = win_carve(tp, KS);
     WinSm sm;
-    sm.X[0] = wsm + cv.X0; sm.X[1] = wsm + cv.X1;
+    sm.X = wsm + cv.X; sm.xstride = N * 12;
     sm.anch = wsm + cv.anch; sm.ant = wsm + cv.ant; sm.rd = wsm + cv.rd; sm.ri = wsm + cv.ri;
     sm.pZi = wsm + cv.pZi; sm.pI = wsm + cv.pI; sm.sZi = wsm + cv.sZi; sm.sI = wsm + cv.sI;
     sm.rJ = wsm + cv.rJ; sm.pJ = wsm + cv.pJ; sm.sJ = wsm + cv.sJ;
     sm.Hd = wsm + cv.Hd; sm.Ho = wsm + cv.Ho; sm.b = wsm + cv.b;
-    sm.G = wsm + cv.G; sm.M = wsm + cv.M; sm.c = wsm + cv.c; sm.z = wsm + cv.z; sm.x = wsm + cv.x;
-    sm.S = wsm + cv.S; sm.echi = wsm + cv.echi;
+    sm.cand = wsm + cv.cand; sm.cand_stride = cv.cand_stride;
     sm.cnt = reinterpret_cast<int *>(wsm + cv.cnt);
+    sm.parent = reinterpret_cast<int *>(wsm + cv.parent);
+    sm.cbeg = reinterpret_cast<int *>(wsm + cv.cbeg);
+    sm.chl = reinterpret_cast<int *>(wsm + cv.chl);
+    sm.opb = reinterpret_cast<int *>(wsm + cv.opb);
+    sm.ncalls = reinterpret_cast<int *>(wsm + cv.ncalls);
+    sm.slot_edge = reinterpret_cast<int *>(wsm + cv.slot_edge);
+    sm.ops = reinterpret_cast<int2 *>(wsm + cv.ops);
     sm.edges = reinterpret_cast<EdgeRec *>(wsm + cv.edges);
     Cauchy ck;
     ck.init(cfg.kdelta);
     const double delta = cfg.jdelta, scalar = 1.0 / (2.0 * delta);
+    auto xbuf = [&](int k) { return sm.X + k * sm.xstride; };
+    auto cand = [&](int k) { return sm.cand + k * sm.cand_stride; };
+    auto cand_x = [&](int k) { return cand(k) + 84 * N; };
+    auto cand_L = [&](int k) { return cand(k) + 90 * N + 28; };
+    auto cand_echi = [&](int k) { return cand(k) + 90 * N + 72; };
 
-    /* ---- the window into shared memory -------------------------------------------------------- */
-    for (int k = tid; k < N * 12; k += WT) {
+    /* ---- the window and its topology into shared memory -------------------------------------- */
+    for (int k = tid; k < N * 12; k += NT) {
         const int i = k / 12, j = k - 12 * i;
         double v;
         if (j >= 9)
@@ -391,18 +794,37 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             v = io.pose_R[(w * N + i) * 9 + j];
         else
             v = (j == 0 || j == 4 || j == 8) ? 1.0 : 0.0;
-        sm.X[0][k] = v;
+        sm.X[k] = v;
     }
-    for (int k = tid; k < N; k += WT) sm.cnt[k] = io.cnt_in ? io.cnt_in[w * N + k] : 0;
-    for (int k = tid; k < tp.A * 3; k += WT) sm.anch[k] = io.anchors[w * tp.A * 3 + k];
-    for (int k = tid; k < tp.K * 3; k += WT) sm.ant[k] = io.ant[k];
-    for (int k = tid; k < tp.Er; k += WT) {
+    for (int k = tid; k < N; k += NT) {
+        sm.cnt[k] = io.cnt_in ? io.cnt_in[w * N + k] : 0;
+        sm.parent[k] = __ldg(tp.parent + k);
+        sm.ncalls[k] = __ldg(tp.num_calls + k);
+    }
+    for (int k = tid; k <= N; k += NT) {
+        sm.cbeg[k] = __ldg(tp.child_begin + k);
+        sm.opb[k] = __ldg(tp.op_begin + k);
+    }
+    {
+        const int nch = __ldg(tp.child_begin + N);
+        for (int k = tid; k < nch; k += NT) sm.chl[k] = __ldg(tp.children + k);
+        for (int k = tid; k < tp.n_ops; k += NT) sm.ops[k] = __ldg(reinterpret_cast<const int2 *>(tp.ops + k));
+        for (int k = tid; k < NE; k += NT) sm.slot_edge[k] = __ldg(tp.slot_edge + k);
+        const int words = (int)(sizeof(EdgeRec) / 4) * NE;
+        const int *src = reinterpret_cast<const int *>(tp.edges);
+        int *dst = reinterpret_cast<int *>(sm.edges);
+        for (int k = tid; k < words; k += NT) dst[k] = __ldg(src + k);
+    }
+    for (int k = tid; k < tp.A * 3; k += NT) sm.anch[k] = io.anchors[w * tp.A * 3 + k];
+    for (int k = tid; k < tp.K * 3; k += NT) sm.ant[k] = io.ant[k];
+    for (int k = tid; k < tp.Er; k += NT) {
         sm.rd[k] = io.rd[w * tp.Er + k];
         sm.ri[k] = io.ri[w * tp.Er + k];
     }
-    for (int k = tid; k < tp.Ep * 36; k += WT) sm.pI[k] = io.pI[w * tp.Ep * 36 + k];
-    for (int k = tid; k < tp.Es * 36; k += WT) sm.sI[k] = io.sI[w * tp.Es * 36 + k];
-    for (int k = tid; k < tp.Ep + tp.Es; k += WT) { /* measurement inverses, once */
+    for (int k = tid; k < tp.Ep * 36; k += NT) sm.pI[k] = io.pI[w * tp.Ep * 36 + k];
+    for (int k = tid; k < tp.Es * 36; k += NT) sm.sI[k] = io.sI[w * tp.Es * 36 + k];
+    for (int k = tid; k < KS * 42; k += NT) sm.cand[(k / 42) * sm.cand_stride + sm.cand_stride - 42 + k % 42] = 0.0;
+    for (int k = tid; k < tp.Ep + tp.Es; k += NT) { /* measurement inverses, once */
         const bool pr = k < tp.Ep;
         const int s = pr ? k : k - tp.Ep;
         const double *zp = pr ? io.pZ + (w * tp.Ep + s) * 12 : io.sZ + (w * tp.Es + s) * 12;
@@ -411,41 +833,53 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
         pose_inv(Z, Zinv);
         st_pose((pr ? sm.pZi : sm.sZi) + 12 * s, Zinv);
     }
-    {
-        const int words = (int)(sizeof(EdgeRec) / 4) * NE;
-        const int *src = reinterpret_cast<const int *>(tp.edges);
-        int *dst = reinterpret_cast<int *>(sm.edges);
-        for (int k = tid; k < words; k += WT) dst[k] = __ldg(src + k);
-    }
     __syncthreads();
 
-    /* phase C: chi2 terms of every edge at buffer `sel`; kinds are kept in separate warps */
-    const int nC = (WNW > 1 ? WNW - 1 : 1) * 32; /* threads of the U / C phases (the last warp sums computeScale) */
-    auto chi_phase = [&](int sel) {
-        const double *X = sm.X[sel];
-        const int *se = tp.slot_edge;
-        const int n6 = tp.Es + tp.Ep;
-        const int base = ((n6 + 31) & ~31) % nC;
-        for (int k = tid; k < n6; k += nC) { /* se3 slots, then prior slots */
-            const int e = __ldg(se + tp.Er + (k < tp.Es ? tp.Ep + k : k - tp.Es));
+    const int n6 = NO6D ? 0 : tp.Es + tp.Ep;
+    /* chi2 terms of the 6-D edges (se3 slots, then prior slots) resp. the range edges at the estimates X,
+     * over the lanes of one warp */
+    /* (branch-free arithmetic first; an item whose operands it flags is evaluated again with the IEEE
+     * sequences: same bits, and the cold copy stays out of the instruction stream) */
+    auto chi_six = [&](const double *X, double *echi) {
+        if (NO6D) return;
+        for (int k = lane; k < n6; k += 32) {
+            const int e = sm.slot_edge[tp.Er + (k < tp.Es ? tp.Ep + k : k - tp.Es)];
             double chi, rob;
-            edge_chi(sm, X, sm.edges[e], ck, chi, rob);
-            sm.echi[2 * e] = chi;
-            sm.echi[2 * e + 1] = rob;
-        }
-        for (int k = (tid - base + nC) % nC; k < tp.Er; k += nC) {
-            const int e = __ldg(se + k);
-            double chi, rob;
-            edge_chi(sm, X, sm.edges[e], ck, chi, rob);
-            sm.echi[2 * e] = chi;
-            sm.echi[2 * e + 1] = rob;
+            unsigned bad = 0;
+            six_chi<WMC>(sm, X, sm.edges[e], ck, chi, rob, bad);
+            if (bad) six_chi<IeeeMath>(sm, X, sm.edges[e], ck, chi, rob, bad);
+            echi[2 * e] = chi;
+            echi[2 * e + 1] = rob;
         }
     };
-    auto chi_sum = [&](double &p, double &r) {
+    auto chi_range = [&](const double *X, double *echi) {
+        for (int k = lane; k < tp.Er; k += 32) {
+            const int e = sm.slot_edge[k];
+            double chi, rob;
+            unsigned bad = 0;
+            range_chi<WMC>(sm, X, sm.edges[e], ck, chi, rob, bad);
+            if (bad) range_chi<IeeeMath>(sm, X, sm.edges[e], ck, chi, rob, bad);
+            echi[2 * e] = chi;
+            echi[2 * e + 1] = rob;
+        }
+    };
+    /* the two ordered sums over the edges: loads in blocks of 8 edges, then the additions */
+    auto chi_sum = [&](const double *echi, double &p, double &r) {
         double pp = 0.0, rr = 0.0;
-        for (int e = 0; e < NE; ++e) {
-            pp = pp + sm.echi[2 * e];
-            rr = rr + sm.echi[2 * e + 1];
+        int e = 0;
+        for (; e + 8 <= NE; e += 8) {
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = echi[2 * e + k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                pp = pp + v[2 * k];
+                rr = rr + v[2 * k + 1];
+            }
+        }
+        for (; e < NE; ++e) {
+            pp = pp + echi[2 * e];
+            rr = rr + echi[2 * e + 1];
         }
         p = pp;
         r = rr;
@@ -455,19 +889,38 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
     double lambda = 0.0, ni = 2.0, stale = 0.0, plainCur = 0.0, currentChi = 0.0, rho = 0.0;
     int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0, q = 0, it = 0;
     bool need_lin = true;
+    /* candidates of the next round: lambda, lambda nu, lambda nu 2nu, ... as many as trials are left */
+    auto publish_candidates = [&]() {
+        double l = lambda, n = ni;
+        int nk = cfg.max_trials - q;
+        if (nk > KS) nk = KS;
+        for (int k = 0; k < nk; ++k) {
+            ctl.lam[k] = l;
+            l = l * n;
+            n = n * 2.0;
+        }
+        ctl.nk = nk;
+    };
 
-    if (tid < nC) chi_phase(0);
+    /* initial computeActiveErrors at buffer 0 */
+    if (warp == 0) chi_six(xbuf(0), cand_echi(0));
+    else if (warp == 1) chi_range(xbuf(0), cand_echi(0));
     __syncthreads();
     if (tid == 0) {
-        chi_sum(plainCur, currentChi);
+        chi_sum(cand_echi(0), plainCur, currentChi);
         stale = plainCur;
         ctl.go = cfg.max_iterations > 0;
         ctl.lin = 1;
         ctl.cur = 0;
+        ctl.adv = 0;
+        ctl.first = 1;
     }
 
 #ifdef UWBGO_WIN_TIMING
-    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq = clock64();
+    __shared__ long long dbg[8];
+    if (tid < 8) dbg[tid] = 0;
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq = clock64(), tfac[4] = {0, 0, 0, 0};
+    int rounds = 0;
 #define WIN_TICK(k) do { long long tn_ = clock64(); tph[k] += tn_ - tq; tq = tn_; } while (0)
 #else
 #define WIN_TICK(k)
@@ -476,102 +929,43 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
         __syncthreads(); /* control published */
         WIN_TICK(7);
         if (!ctl.go) break;
+#ifdef UWBGO_WIN_TIMING
+        ++rounds;
+#endif
         const int cb = ctl.cur;
+        const double *X = xbuf(cb);
         if (ctl.lin) {
-            const double *X = sm.X[cb];
-            /* ---- J: Jacobians, errors, weights ---------------------------------------------- */
+            const int adv = ctl.adv; /* oplus calls of the trials consumed since the counters were last touched */
+            /* ---- J: Jacobians, errors, weights (branch-free arithmetic, IEEE on a flagged item) ---- */
             {
-                const int *se = tp.slot_edge;
-                const int n6 = tp.Es + tp.Ep;
-                for (int k = tid; k < n6; k += WT) {
-                    if (k < tp.Es) {
-                        const EdgeRec er = sm.edges[__ldg(se + tp.Er + tp.Ep + k)];
-                        double *rec = sm.sJ + SJ * er.slot;
-                        Pose Zinv, Xi, Xj;
-                        ld_pose(sm.sZi + 12 * er.slot, Zinv);
-                        ld_pose(X + 12 * er.a, Xi);
-                        ld_pose(X + 12 * er.b, Xj);
-                        double e6[6], Oe[6];
-                        se3_error_s(Zinv, Xi, Xj, e6);
-                        se3_jacobians_s(Zinv, Xi, Xj, rec, rec + 36);
-                        const double chi = chi2_6s(sm.sI + 36 * er.slot, e6, Oe);
-                        const double r1 = er.robust ? ck.rho1(chi) : 1.0;
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-                            double v = -Oe[j];
-                            if (er.robust) v = v * r1;
-                            rec[144 + j] = v;
-                        }
-                        rec[150] = r1;
-                    } else {
-                        const EdgeRec er = sm.edges[__ldg(se + tp.Er + (k - tp.Es))];
-                        double *rec = sm.pJ + PJ * er.slot;
-                        Pose Dl;
-                        double qq[4], e6[6], Oe[6];
-                        prior_error(sm.pZi + 12 * er.slot, X + 12 * er.a, Dl, qq, e6);
-                        const double chi = chi2_6s(sm.pI + 36 * er.slot, e6, Oe);
-                        const double r1 = er.robust ? ck.rho1(chi) : 1.0;
-#pragma unroll
-                        for (int j = 0; j < 36; ++j) rec[j] = 0.0;
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) rec[6 * r + c] = Dl.R[3 * r + c];
-                        set_jqq_s(qq, rec);
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-                            double v = -Oe[j];
-                            if (er.robust) v = v * r1;
-                            rec[72 + j] = v;
-                        }
-                        rec[78] = r1;
-                    }
+                for (int k = tid; k < n6; k += NT) {
+                    const EdgeRec er = sm.edges[sm.slot_edge[tp.Er + (k < tp.Es ? tp.Ep + k : k - tp.Es)]];
+                    unsigned bad = 0;
+                    lin_six<WMJ>(sm, X, er, ck, bad);
+                    if (bad) lin_six<IeeeMath>(sm, X, er, ck, bad);
                 }
-                const int base1 = ((n6 + 31) & ~31) % WT;
-                for (int k = (tid - base1 + WT) % WT; k < tp.Er; k += WT) { /* error and weights of a range edge */
-                    const EdgeRec er = sm.edges[__ldg(se + k)];
-                    double P0[3], Q[3];
-                    range_points(sm, X, er, P0, Q);
-                    const double info = sm.ri[k];
-                    const double err = sm.rd[k] - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
-                    const double Oe = info * err;
-                    double omega_r = -Oe, Ow = info;
-                    if (er.robust) {
-                        const double r1 = ck.rho1(err * Oe);
-                        omega_r = omega_r * r1;
-                        Ow = r1 * info;
-                    }
-                    sm.rJ[RJ * k + 12] = Ow;
-                    sm.rJ[RJ * k + 13] = omega_r;
+                const int base1 = ((n6 + 31) & ~31) % NT;
+                for (int k = (tid - base1 + NT) % NT; k < tp.Er; k += NT) {
+                    const EdgeRec er = sm.edges[sm.slot_edge[k]];
+                    unsigned bad = 0;
+                    lin_range_weights<WMJ>(sm, X, er, ck, bad);
+                    if (bad) lin_range_weights<IeeeMath>(sm, X, er, ck, bad);
                 }
-                const int base2 = (base1 + ((tp.Er + 31) & ~31)) % WT;
-                for (int u = (tid - base2 + WT) % WT; u < 12 * tp.Er; u += WT) { /* one Jacobian column */
-                    const int k = u / 12, j = u - 12 * k, which = j / 6, dd = j - 6 * which;
-                    const EdgeRec er = sm.edges[__ldg(se + k)];
-                    double v = 0.0;
-                    if (which == 0) {
-                        double Q[3];
-                        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR)
-                            anchor_point(sm, er.b, er.ant_b, Q);
-                        else
-                            offset_point(sm, X + 12 * er.b, er.ant_b, Q);
-                        v = range_jac_col(sm, X + 12 * er.a, er.ant, Q, sm.rd[k], dd, (sm.cnt[er.a] + er.base_a) % mod, mod,
-                                          delta, scalar);
-                    } else if (er.kind == UWBGO_EDGE_RANGE_POSE) {
-                        double P0[3];
-                        offset_point(sm, X + 12 * er.a, er.ant, P0);
-                        v = range_jac_col(sm, X + 12 * er.b, er.ant_b, P0, sm.rd[k], dd, (sm.cnt[er.b] + er.base_b) % mod,
-                                          mod, delta, scalar);
-                    }
-                    sm.rJ[RJ * k + j] = v;
+                const int base2 = (base1 + ((tp.Er + 31) & ~31)) % NT;
+                for (int u = (tid - base2 + NT) % NT; u < 12 * tp.Er; u += NT) {
+                    const int k = u / 12, j = u - 12 * k;
+                    const EdgeRec er = sm.edges[sm.slot_edge[k]];
+                    unsigned bad = 0;
+                    lin_range_col<WMJ>(sm, X, er, j, adv, mod, delta, scalar, bad);
+                    if (bad) lin_range_col<IeeeMath>(sm, X, er, j, adv, mod, delta, scalar, bad);
                 }
             }
             __syncthreads();
             WIN_TICK(0);
             /* ---- O: J^T Ow of the 6-D edges, one entry per thread; oplus counters advance ----- */
             {
-                const int nP = 36 * tp.Ep, nS = 72 * tp.Es;
-                for (int u = tid; u < nP + nS; u += WT) {
+                const int nP = NO6D ? 0 : 36 * tp.Ep, nS = NO6D ? 0 : 72 * tp.Es;
+                for (int u = tid; u < nP + nS; u += NT) {
                     const double *J, *O;
                     double *out;
                     double r1;
@@ -585,7 +979,7 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                         out = sm.sJ + SJ * s + 72 + 36 * which;
                         O = sm.sI + 36 * s;
                         r1 = rec[150];
-                        robust = sm.edges[__ldg(tp.slot_edge + tp.Er + tp.Ep + s)].robust != 0;
+                        robust = sm.edges[sm.slot_edge[tp.Er + tp.Ep + s]].robust != 0;
                     } else {
                         const int v = u - nS, s = v / 36;
                         rc = v - 36 * s;
@@ -594,7 +988,7 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                         out = sm.pJ + PJ * s + 36;
                         O = sm.pI + 36 * s;
                         r1 = rec[78];
-                        robust = sm.edges[__ldg(tp.slot_edge + tp.Er + s)].robust != 0;
+                        robust = sm.edges[sm.slot_edge[tp.Er + s]].robust != 0;
                     }
                     const int r = rc / 6, c = rc - 6 * r;
                     double ow[6];
@@ -608,26 +1002,21 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                     for (int k = 1; k < 6; ++k) s = fma(J[6 * k + r], ow[k], s);
                     out[rc] = s;
                 }
-                /* the numeric Jacobians made num_calls[i] oplus calls on pose i (all columns were read
-                 * before the barrier above) */
-                for (int i = tid; i < N; i += WT) sm.cnt[i] = (sm.cnt[i] + __ldg(tp.num_calls + i)) % mod;
+                /* the trials consumed so far made one oplus call each, the numeric Jacobians ncalls[i]
+                 * (all columns were read before the barrier above) */
+                for (int i = tid; i < N; i += NT) sm.cnt[i] = (sm.cnt[i] + adv + sm.ncalls[i]) % mod;
             }
             __syncthreads();
             WIN_TICK(1);
             /* ---- H: every entry of the H record of every pose, owned by one thread -------------- */
-            for (int u = tid; u < 63 * N; u += WT) {
+            for (int u = tid; u < 63 * N; u += NT) {
                 const int i = u / 63, k = u - 63 * i;
                 /* k < 21: H_ii upper (r, c); 21..56: H_{parent(i), i} (r, c); 57..62: b_i[r] */
                 int r, c, what;
                 if (k < 21) {
                     what = 0;
-                    r = 0;
-                    int kk = k;
-                    while (kk >= 6 - r) {
-                        kk -= 6 - r;
-                        ++r;
-                    }
-                    c = r + kk;
+                    r = UP_R[k];
+                    c = UP_C[k];
                 } else if (k < 57) {
                     what = 1;
                     r = (k - 21) / 6;
@@ -638,9 +1027,9 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                     c = 0;
                 }
                 double acc = 0.0;
-                const int ob = __ldg(tp.op_begin + i), oe = __ldg(tp.op_begin + i + 1);
+                const int ob = sm.opb[i], oe = sm.opb[i + 1];
                 for (int o = ob; o < oe; ++o) {
-                    const int2 op = __ldg(reinterpret_cast<const int2 *>(tp.ops + o));
+                    const int2 op = sm.ops[o];
                     const EdgeRec &er = sm.edges[op.x];
                     const int role = op.y;
                     if (er.kind <= UWBGO_EDGE_RANGE_POSE) {
@@ -653,7 +1042,7 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                             acc = fma(J[r], rec[13], acc);
                         else if (role == 1)
                             acc = fma(rec[r] * Ow, rec[6 + c], acc);
-                    } else {
+                    } else if (!NO6D) {
                         const bool se3 = er.kind == UWBGO_EDGE_SE3;
                         const double *rec = se3 ? sm.sJ + SJ * er.slot : sm.pJ + PJ * er.slot;
                         const double *J = rec + 36 * role;                          /* A or B           */
@@ -687,243 +1076,312 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             }
             __syncthreads();
             WIN_TICK(2);
+            if (tid == 0) { /* a new iteration starts */
+                stale = plainCur;
+                if (it == 0) {
+                    double maxdiag = 0.0;
+                    for (int i = 0; i < N; ++i)
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) {
+                            const double v = fabs(sm.Hd[21 * i + up_idx(6, r, r)]);
+                            if (v > maxdiag) maxdiag = v;
+                        }
+                    lambda = cfg.tau * maxdiag;
+                    ni = 2.0;
+                }
+                rho = 0.0;
+                q = 0;
+                need_lin = false;
+                if (ctl.first) publish_candidates();
+            }
+            if (ctl.first) __syncthreads(); /* lambda_0 needed H; later rounds publish their candidates in D */
         }
+        const int adv0 = ctl.lin ? 0 : ctl.adv; /* trials consumed since the counters were last advanced */
+        const int nk = ctl.nk;
 
-        /* ---- F: the trial's linear solve, warp 0 ------------------------------------------------ */
-        if (warp == 0) {
-            if (tid == 0) {
-                if (need_lin) {
-                    stale = plainCur;
-                    if (it == 0) {
-                        double maxdiag = 0.0;
-                        for (int i = 0; i < N; ++i)
-#pragma unroll
-                            for (int r = 0; r < 6; ++r) {
-                                const double v = fabs(sm.Hd[21 * i + up_idx(6, r, r)]);
-                                if (v > maxdiag) maxdiag = v;
-                            }
-                        lambda = cfg.tau * maxdiag;
-                        ni = 2.0;
-                    }
-                    rho = 0.0;
-                    q = 0;
-                    need_lin = false;
-                }
-                ctl.lambda = lambda;
-            }
-            __syncwarp();
-            const double lam = ctl.lambda;
-            /* lane roles of the assembly: 0..20 entry (r, c) of the lower triangle of S, 21..26 row of the
-             * right-hand side */
-            int er_ = 0, ec_ = 0;
-            if (lane < 21) {
-                int kk = lane;
-                while (kk > er_) {
-                    kk -= er_ + 1;
-                    ++er_;
-                }
-                ec_ = kk;
-            } else if (lane < 27) {
-                er_ = lane - 21;
-            }
-            bool ok = true;
-            for (int i = N - 1; i >= 0; --i) {
-                double v = 0.0;
-                if (lane < 21) {
-                    v = sm.Hd[21 * i + up_idx(6, ec_, er_)];
-                    if (er_ == ec_) v = v + lam;
-                } else if (lane < 27) {
-                    v = sm.b[6 * i + er_];
-                }
-                const int qb = __ldg(tp.child_begin + i), qe = __ldg(tp.child_begin + i + 1);
-                for (int qq = qb; qq < qe; ++qq) { /* children in descending order */
-                    const int ch = __ldg(tp.children + qq);
-                    const double *Gc = sm.G + 36 * ch, *zc = sm.z + 6 * ch;
-                    if (lane < 21) {
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) v = fma(-Gc[6 * er_ + k], Gc[6 * ec_ + k], v);
-                    } else if (lane < 27) {
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) v = fma(-Gc[6 * er_ + k], zc[k], v);
-                    }
-                }
-                if (lane < 27) sm.S[lane] = v;
-                __syncwarp();
-                double S[21], L[21], rhs[6], fw[6], bw[6];
-#pragma unroll
-                for (int k = 0; k < 21; ++k) S[k] = sm.S[k];
-                const bool has_parent = __ldg(tp.parent + i) >= 0;
-                {
-                    const double *src = lane < 6 ? sm.Ho + 36 * i + 6 * lane : sm.S + 21;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) rhs[k] = src[k];
-                }
-                __syncwarp();
-                /* potrf, every lane the whole block; the diagonal slot keeps 1 / L_jj */
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    double s = S[lo_idx(j, j)];
-#pragma unroll
-                    for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
-                    if (!(s > 0.0)) ok = false;
-                    const double inv = 1.0 / sqrt(s);
-                    L[lo_idx(j, j)] = inv;
-#pragma unroll
-                    for (int r = j + 1; r < 6; ++r) {
-                        double t = S[lo_idx(r, j)];
-#pragma unroll
-                        for (int k = 0; k < j; ++k) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
-                        L[lo_idx(r, j)] = t * inv;
-                    }
-                }
-                /* forward substitution: row of G_i (lanes 0..5) or z_i (lane 6) */
-#pragma unroll
-                for (int cc = 0; cc < 6; ++cc) {
-                    double s = rhs[cc];
-#pragma unroll
-                    for (int k = 0; k < cc; ++k) s = fma(-fw[k], L[lo_idx(cc, k)], s);
-                    fw[cc] = s * L[lo_idx(cc, cc)];
-                }
-                /* backward substitution: column of M_i (lanes 0..5) or c_i (lane 6) */
-#pragma unroll
-                for (int r = 5; r >= 0; --r) {
-                    double s = fw[r];
-#pragma unroll
-                    for (int k = r + 1; k < 6; ++k) s = fma(-L[lo_idx(k, r)], bw[k], s);
-                    bw[r] = s * L[lo_idx(r, r)];
-                }
-                if (lane < 6 && has_parent) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        sm.G[36 * i + 6 * lane + k] = fw[k];
-                        sm.M[36 * i + 6 * k + lane] = bw[k];
-                    }
-                } else if (lane == 6) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        sm.z[6 * i + k] = fw[k];
-                        sm.c[6 * i + k] = bw[k];
-                    }
-                }
-                __syncwarp();
+        /* ---- F: the linear solves of the candidates, a pair of warps each ----------------------- */
+        if (warp < nk) { /* main: the elimination chain */
+            double *cd = cand(warp);
+            const double lam = ctl.lam[warp];
+            unsigned bad = 0;
+#ifdef UWBGO_WIN_TIMING
+#define F_TARG , tfac
+#else
+#define F_TARG
+#endif
+            const bool chain = tp.simple_chain != 0;
+            bool ok = chain ? factor_main<NbMath, true>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG)
+                            : factor_main<NbMath, false>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
+            const bool redo = __any_sync(0xffffffffu, bad != 0);
+            if (lane == 0) ctl.redo[warp] = redo ? 1 : 0;
+            bar_named(1 + warp, 64);
+            if (redo) { /* operands outside the branch-free range: the IEEE sequences */
+                bad = 0;
+                ok = factor_main<IeeeMath, false>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
             }
             ok = __all_sync(0xffffffffu, ok);
+            if (lane == 0) ctl.ok[warp] = ok ? 1 : 0;
+            bar_named(1 + warp, 64);
             WIN_TICK(3);
-            /* substitution x_i = c_i - M_i x_parent(i), ascending */
-            for (int i = 0; i < N; ++i) {
-                const int par = __ldg(tp.parent + i);
-                if (lane < 6) {
-                    double s = sm.c[6 * i + lane];
-                    if (par >= 0) {
-                        const double *Mi = sm.M + 36 * i + 6 * lane, *xp = sm.x + 6 * par;
+        } else if (warp >= KS && warp - KS < nk) { /* helper: backward substitutions, then x and computeScale() */
+            const int k = warp - KS;
+            double *cd = cand(k);
+            if (tp.simple_chain) factor_helper<true>(sm, cd, cand_L(k), 1 + k, N, lane);
+            else factor_helper<false>(sm, cd, cand_L(k), 1 + k, N, lane);
+            bar_named(1 + k, 64);
+            if (ctl.redo[k]) factor_helper<false>(sm, cd, cand_L(k), 1 + k, N, lane);
+            bar_named(1 + k, 64);
+            const bool ok = ctl.ok[k] != 0;
+            const double lam = ctl.lam[k];
+#ifdef UWBGO_WIN_TIMING
+            const long long ts0 = clk();
+#endif
+            /* x_i = c_i - M_i x_parent(i), ascending, and computeScale() = sum over j of x_j (lambda x_j + b_j)
+             * strictly in order.  Lanes 0..5 own a row each; x_(i-1) travels between them by shuffle (every lane
+             * keeps all six), the row of M_(i+1) is fetched a pose ahead, and lane 0 adds the six terms of pose
+             * i - 1 in the shadow of pose i's FMA chain. */
+            {
+                const double *Mm = cd + 36 * N, *cvv = cd + 72 * N;
+                double *xv = cd + 84 * N;
+                const int r = lane < 6 ? lane : 0;
+                double scale = 0.0, tprev = 0.0;
+                double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                double mrow[6], ci, bi;
+                int par;
+                auto fetch = [&](int i) {
+                    const double2 *mp = reinterpret_cast<const double2 *>(Mm + 36 * i + 6 * r);
+                    const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2];
+                    mrow[0] = m0.x; mrow[1] = m0.y; mrow[2] = m1.x; mrow[3] = m1.y; mrow[4] = m2.x; mrow[5] = m2.y;
+                    ci = cvv[6 * i + r];
+                    bi = sm.b[6 * i + r];
+                    par = sm.parent[i];
+                };
+                fetch(0);
+                if (tp.simple_chain) {
+                    /* chains: parent(i) = i - 1.  No branch in the body (a lone warp pays for every one):
+                     * the fetch index is clamped, pose 0 multiplies zeros */
+#pragma unroll 2
+                    for (int i = 0; i < N; ++i) {
+                        double x = ci;
+                        const double b_i = bi;
+                        if (i > 0) {
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) s = fma(-Mi[j], xp[j], s);
+                            for (int j = 0; j < 6; ++j) x = fma(-mrow[j], xp[j], x);
+                        }
+                        fetch(i + 1 < N ? i + 1 : N - 1);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j); /* pose i - 1 */
+                        x = ok ? x : 0.0;
+                        if (lane < 6) xv[6 * i + lane] = x;
+                        tprev = x * (lam * x + b_i);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) xp[j] = __shfl_sync(0xffffffffu, x, j);
                     }
-                    sm.x[6 * i + lane] = ok ? s : 0.0;
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < N; ++i) {
+                        double x = ci;
+                        const double b_i = bi;
+                        const int p_i = par;
+                        if (p_i >= 0 && p_i != i - 1) { /* forests: the parent is not the previous pose */
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) xp[j] = xv[6 * p_i + j];
+                        }
+                        if (p_i >= 0) {
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) x = fma(-mrow[j], xp[j], x);
+                        }
+                        fetch(i + 1 < N ? i + 1 : N - 1);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j); /* pose i - 1 */
+                        x = ok ? x : 0.0;
+                        if (lane < 6) xv[6 * i + lane] = x;
+                        tprev = x * (lam * x + b_i);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) xp[j] = __shfl_sync(0xffffffffu, x, j);
+                    }
                 }
-                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 6; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j);
+                if (lane == 0) ctl.scale[k] = scale;
             }
-            if (tid == 0) {
-                ctl.ok = ok ? 1 : 0;
-                if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;
-            }
+            __syncwarp();
+#ifdef UWBGO_WIN_TIMING
+            if (warp == KS && lane == 0) dbg[7] += clk() - ts0;
+#endif
         }
+#ifdef UWBGO_WIN_TIMING
+        const long long ta0 = clk();
+#endif
+        __syncthreads();
+#ifdef UWBGO_WIN_TIMING
+        if (warp == KS && lane == 0) dbg[3] += clk() - ta0;
+#endif
+        WIN_TICK(6);
+
+        /* ---- U and C per candidate: main warp updates the poses and evaluates the 6-D edges, its helper
+         * the range edges ------------------------------------------------------------------------------ */
+#ifdef UWBGO_WIN_TIMING
+        long long t0_ = clk(), t1_ = t0_, t2_ = t0_, t3_ = t0_;
+#endif
+        if (warp < nk) {
+            const int k = warp;
+            double *Xn = xbuf((cb + 1 + k) % (KS + 1));
+            const double *xv = cand_x(k);
+#ifdef UWBGO_WIN_TIMING
+            long long u0 = clk(), u1 = u0, u2 = u0, u3 = u0;
+#endif
+            for (int i = lane; i < N; i += 32) {
+                Pose P;
+                ld_pose(X + 12 * i, P);
+                double dx[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) dx[j] = xv[6 * i + j];
+#ifdef UWBGO_WIN_TIMING
+                u1 = clk();
+#endif
+                int c0 = sm.cnt[i] + adv0 + k; /* cnt < mod, a handful of trials since: no division */
+                while (c0 >= mod) c0 -= mod;
+                int c = c0;
+#ifdef UWBGO_WIN_TIMING
+                if (c < 0) dx[0] = 0.0;
+                u2 = clk();
+#endif
+                unsigned bad = 0;
+                {
+                    Pose Q = P;
+                    pose_oplus_m<WMU>(Q, dx, c, mod, bad);
+                    if (bad) {
+                        c = c0;
+                        pose_oplus_m<IeeeMath>(P, dx, c, mod, bad);
+                    } else
+                        P = Q;
+                }
+#ifdef UWBGO_WIN_TIMING
+                if (P.R[0] == 12345.0) dx[0] = 0.0;
+                u3 = clk();
+#endif
+                st_pose(Xn + 12 * i, P);
+            }
+#ifdef UWBGO_WIN_TIMING
+            t1_ = clk();
+            if (tid == 0) { dbg[4] += u0 - t0_; }
+#endif
+            bar_named(1 + k, 64);
+#ifdef UWBGO_WIN_TIMING
+            t2_ = clk();
+#endif
+            chi_six(Xn, cand_echi(k));
+#ifdef UWBGO_WIN_TIMING
+            t3_ = clk();
+#endif
+        } else if (warp >= KS && warp - KS < nk) {
+            const int k = warp - KS;
+#ifdef UWBGO_WIN_TIMING
+            t1_ = clk();
+#endif
+            bar_named(1 + k, 64);
+#ifdef UWBGO_WIN_TIMING
+            t2_ = clk();
+#endif
+            chi_range(xbuf((cb + 1 + k) % (KS + 1)), cand_echi(k));
+#ifdef UWBGO_WIN_TIMING
+            t3_ = clk();
+#endif
+        }
+#ifdef UWBGO_WIN_TIMING
+        if (lane == 0 && (warp == 0 || warp == KS)) {
+            if (warp == 0) { dbg[0] += t1_ - t0_; dbg[1] += t2_ - t1_; dbg[2] += t3_ - t2_; }
+            else { dbg[5] += t2_ - t1_; dbg[6] += t3_ - t2_; }
+        }
+#endif
         __syncthreads();
         WIN_TICK(4);
 
-        /* ---- U: estimate (+) x into the trial buffer; computeScale() on the last warp ----------- */
-        if (tid < nC) {
-            const double *Xc = sm.X[cb];
-            double *Xn = sm.X[cb ^ 1];
-            for (int i = tid; i < N; i += nC) {
-                Pose X;
-                ld_pose(Xc + 12 * i, X);
-                double xv[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) xv[k] = sm.x[6 * i + k];
-                int c = sm.cnt[i];
-                pose_oplus(X, xv, c, mod);
-                sm.cnt[i] = c;
-                st_pose(Xn + 12 * i, X);
-            }
-            if (WNW > 1) bar_named(1, nC);
-            else __syncthreads();
-            chi_phase(cb ^ 1);
-        }
-        if (tid == WT - 1 || (WNW == 1 && tid == 0)) {
-            const double lam = ctl.lambda;
-            double scale = 0.0;
-            for (int j = 0; j < 6 * N; ++j) scale = scale + sm.x[j] * (lam * sm.x[j] + sm.b[j]);
-            ctl.scale = scale;
-        }
-        __syncthreads();
-        WIN_TICK(5);
-
-        /* ---- D: accept / reject ------------------------------------------------------------------ */
+        /* ---- D: the trials of this round, consumed in order --------------------------------------------- */
         if (tid == 0) {
-            const bool ok = ctl.ok != 0;
-            double scale = ctl.scale, tplain, tempChi;
-            chi_sum(tplain, tempChi);
-            stale = tplain;
-            if (!ok) tempChi = DBL_MAX;
-            scale = scale + 1e-3;
-            rho = (currentChi - tempChi) / scale;
-            const bool fin = isfinite(tempChi);
-            if (!fin) flags |= UWBGO_FLAG_NONFINITE;
-            if (rho > 0.0 && fin) {
-                double t = 2.0 * rho - 1.0;
-                double alpha = 1.0 - (t * t) * t;
-                alpha = (cfg.good_hi < alpha) ? cfg.good_hi : alpha;
-                double sf = (cfg.good_lo < alpha) ? alpha : cfg.good_lo;
-                lambda = lambda * sf;
-                ni = 2.0;
-                currentChi = tempChi;
-                plainCur = tplain;
-                cur ^= 1;
-            } else {
-                lambda = lambda * ni;
-                ni = ni * 2.0;
-            }
-            ++q;
-            ++trials_total;
-            bool done = false;
-            if (!(rho < 0.0 && q < cfg.max_trials)) { /* this iteration is over */
-                ++iterations;
-                qlast = q;
-                if (q == cfg.max_trials || rho == 0.0) {
-                    flags |= UWBGO_FLAG_TERMINATED;
-                    done = true;
-                } else if (++it >= cfg.max_iterations) {
-                    done = true;
+            int used = 0;
+            bool done = false, more = true;
+            while (more) {
+                const int k = used;
+                const bool ok = ctl.ok[k] != 0;
+                if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;
+                double scale = ctl.scale[k], tplain, tempChi;
+                chi_sum(cand_echi(k), tplain, tempChi);
+                stale = tplain;
+                if (!ok) tempChi = DBL_MAX;
+                scale = scale + 1e-3;
+                rho = (currentChi - tempChi) / scale;
+                const bool fin = isfinite(tempChi);
+                if (!fin) flags |= UWBGO_FLAG_NONFINITE;
+                ++used;
+                if (rho > 0.0 && fin) {
+                    double t = 2.0 * rho - 1.0;
+                    double alpha = 1.0 - (t * t) * t;
+                    alpha = (cfg.good_hi < alpha) ? cfg.good_hi : alpha;
+                    double sf = (cfg.good_lo < alpha) ? alpha : cfg.good_lo;
+                    lambda = lambda * sf;
+                    ni = 2.0;
+                    currentChi = tempChi;
+                    plainCur = tplain;
+                    cur = (cb + 1 + k) % (KS + 1);
                 } else {
-                    need_lin = true;
+                    lambda = lambda * ni;
+                    ni = ni * 2.0;
+                }
+                ++q;
+                ++trials_total;
+                if (!(rho < 0.0 && q < cfg.max_trials)) { /* this iteration is over */
+                    ++iterations;
+                    qlast = q;
+                    if (q == cfg.max_trials || rho == 0.0) {
+                        flags |= UWBGO_FLAG_TERMINATED;
+                        done = true;
+                    } else if (++it >= cfg.max_iterations) {
+                        done = true;
+                    } else {
+                        need_lin = true;
+                        q = 0;
+                    }
+                    more = false;
+                } else if (used == nk) {
+                    more = false; /* every candidate rejected: another round on the same H */
                 }
             }
             ctl.go = done ? 0 : 1;
             ctl.lin = need_lin ? 1 : 0;
             ctl.cur = cur;
-            WIN_TICK(6);
+            ctl.adv = adv0 + used;
+            ctl.first = 0;
+            if (!done) publish_candidates();
+            WIN_TICK(5);
         }
     }
 #ifdef UWBGO_WIN_TIMING
     if (tid == 0 && blockIdx.x == 0)
-        printf("window 0 cycles: J %lld  O %lld  H %lld  factor %lld  subst %lld  U+C %lld  D %lld  sync %lld  (trials %d, iterations %d)\n",
-               tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7], trials_total, iterations);
+        printf("window 0 cycles: J %lld  O %lld  H %lld  factor %lld (assemble %lld potrf %lld fwd+store %lld bar %lld)  wait for x %lld  U+C %lld  D %lld  sync %lld  (trials %d, iterations %d, rounds %d)\n",
+               tph[0], tph[1], tph[2], tph[3], tfac[0], tfac[1], tfac[2], tfac[3], tph[6], tph[4], tph[5], tph[7], trials_total, iterations, rounds);
+    if (tid == 0 && blockIdx.x == 0)
+        printf("   main 0: U %lld (pre %lld)  bar %lld  chi6 %lld   helper 0: subst %lld  wait at A %lld  bar %lld  chi-range %lld\n", dbg[0], dbg[4], dbg[1], dbg[2], dbg[7], dbg[3], dbg[5], dbg[6]);
 #endif
 
     /* ---- results ---------------------------------------------------------------------------------- */
-    const double *Xf = sm.X[ctl.cur];
-    for (int k = tid; k < N * 3; k += WT) {
+    if (!writer) return;
+    const double *Xf = xbuf(ctl.cur);
+    for (int k = tid; k < N * 3; k += NT) {
         const int i = k / 3, j = k - 3 * i;
         io.o_pose_t[(w * N + i) * 3 + j] = Xf[12 * i + 9 + j];
     }
     if (io.o_pose_R)
-        for (int k = tid; k < N * 9; k += WT) {
+        for (int k = tid; k < N * 9; k += NT) {
             const int i = k / 9, j = k - 9 * i;
             io.o_pose_R[(w * N + i) * 9 + j] = Xf[12 * i + j];
         }
-    if (io.o_cnt)
-        for (int k = tid; k < N; k += WT) io.o_cnt[w * N + k] = sm.cnt[k];
+    if (io.o_cnt) {
+        const int adv = ctl.adv;
+        for (int k = tid; k < N; k += NT) io.o_cnt[w * N + k] = (sm.cnt[k] + adv) % mod;
+    }
     if (tid == 0) {
         if (io.o_chi2) {
             double *o = io.o_chi2 + w * UWBGO_CHI2_STRIDE;
@@ -942,21 +1400,40 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
     }
 }
 
-size_t window_path_smem_bytes(const DevTopo &topo) { return sizeof(double) * (size_t)win_carve(topo).total; }
+}  // namespace
 
-cudaError_t launch_solve_window(const DevTopo &topo, const DevCfg &cfg, const WinIo &io, int device, cudaStream_t st)
+size_t window_path_smem_bytes(const DevTopo &topo, int ks) { return sizeof(double) * (size_t)win_carve(topo, ks).total; }
+
+/* candidates evaluated per round: 4 while the batch leaves SMs to spare, 1 (no speculation, 64 threads)
+ * when every SM has several windows to work on anyway */
+int window_path_candidates(int64_t W) { return W <= 148 ? 4 : (W <= 296 ? 2 : 1); }
+
+template <int KS, int NT>
+static cudaError_t launch_win(const DevTopo &topo, const DevCfg &cfg, const WinIo &io, int device, cudaStream_t st)
 {
-    if (io.W <= 0) return cudaSuccess;
-    const size_t sm = window_path_smem_bytes(topo);
+    const size_t sm = window_path_smem_bytes(topo, KS);
     static size_t configured[64] = {0}; /* the attribute is per device */
     size_t &conf = configured[device & 63];
     if (sm > conf) {
-        cudaError_t e = cudaFuncSetAttribute(lm_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaError_t e = cudaFuncSetAttribute(lm_window_kernel<KS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         conf = sm;
     }
-    lm_window_kernel<<<(unsigned)io.W, WT, sm, st>>>(topo, cfg, io);
+#ifdef UWBGO_WIN_PAD
+    lm_window_kernel<KS, NT><<<(unsigned)(io.W < UWBGO_WIN_PAD ? UWBGO_WIN_PAD : io.W), NT, sm, st>>>(topo, cfg, io);
+#else
+    lm_window_kernel<KS, NT><<<(unsigned)io.W, NT, sm, st>>>(topo, cfg, io);
+#endif
     return cudaGetLastError();
+}
+
+cudaError_t launch_solve_window(const DevTopo &topo, const DevCfg &cfg, const WinIo &io, int ks, int device,
+                                cudaStream_t st)
+{
+    if (io.W <= 0) return cudaSuccess;
+    if (ks >= 4) return launch_win<4, 256>(topo, cfg, io, device, st);
+    if (ks >= 2) return launch_win<2, 256>(topo, cfg, io, device, st);
+    return launch_win<1, 128>(topo, cfg, io, device, st);
 }
 
 }  // namespace uwbgo

@@ -13,9 +13,22 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session")
-def solver():
+def _gpu_solver():
     """One GPU context for the whole session; fails loudly when libuwbgo.so or the GPU is missing."""
     from localization_b200 import Solver
     s = Solver(0)
     yield s
     s.close()
+
+
+@pytest.fixture(params=["tile", "window"])
+def solver(request, _gpu_solver):
+    """Every parity test runs twice: through the tile kernels (lane = window, the large-batch path) and
+    through the WINDOW path (one CTA per window; windows too large for it fall back to the tile kernels).
+    `solver.path_ok(*tile_paths)` checks the path the last solve took in either mode."""
+    s = _gpu_solver
+    window = request.param == "window"
+    s.set_window_path(2048 if window else 0)  # larger batches belong to the tile kernels in both modes
+    s.path_ok = lambda *allowed: s.last_path in allowed or (window and s.last_path == 3)
+    yield s
+    s.set_window_path(-1)

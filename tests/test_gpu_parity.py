@@ -35,7 +35,7 @@ def test_uwb_only_fast_path(solver, W, N, A):
     topo, batch, _ = synthetic.uwb_only(W, N, A, seed=7 + W)
     cfg = Config(max_iterations=10)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path in (1, 2)
+    assert solver.path_ok(1, 2)
     ref = oracle.solve(topo, batch, cfg)
     assert_parity(got, ref)
     assert (ref.status[:, 0] == 10).all()
@@ -46,10 +46,10 @@ def test_general_path_equals_fast_path(solver):
     topo, batch, _ = synthetic.uwb_only(64, 20, 8, seed=3)
     cfg = Config(max_iterations=10)
     fast = solver.solve(topo, batch, cfg)
-    assert solver.last_path in (1, 2)
+    assert solver.path_ok(1, 2)
     batch.pose_R = np.tile(np.eye(3), (64, 20, 1, 1))
     gen = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 0
+    assert solver.path_ok(0)
     assert_parity(gen, fast)
     assert_parity(gen, oracle.solve(topo, batch, cfg))
 
@@ -58,7 +58,7 @@ def test_uwb_imu_lidar(solver):
     topo, batch, _ = synthetic.uwb_imu_lidar(128, 20, 8)
     cfg = Config(max_iterations=20)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 0
+    assert solver.path_ok(0)
     assert_parity(got, oracle.solve(topo, batch, cfg))
 
 
@@ -80,7 +80,7 @@ def test_uwb_pose_key_vertex_stars(solver, N, K):
     topo, batch, _ = synthetic.uwb_pose(96, N, 8, keyframe_len=K, seed=N)
     cfg = Config(max_iterations=10)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 0
+    assert solver.path_ok(0)
     assert_parity(got, oracle.solve(topo, batch, cfg))
     Hd, Ho, b, chi = solver.linearize(topo, batch, cfg)
     rHd, rHo, rb, rchi = oracle.linearize(topo, batch, cfg)
@@ -114,7 +114,7 @@ def test_oplus_counter_carry_and_reorthogonalisation(solver):
     batch.oplus_count = rng.integers(0, 1001, size=(40, 10)).astype(np.int32)
     cfg = Config(max_iterations=10)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path in (1, 2)
+    assert solver.path_ok(1, 2)
     assert_parity(got, oracle.solve(topo, batch, cfg))
 
 
@@ -257,7 +257,7 @@ def test_multiple_range_edges_per_pose_and_unordered_insertion(solver):
                   range_d=np.abs(rng.normal(3, 1, (W, er))), range_info=rng.uniform(10, 400, (W, er)))
     cfg = Config(max_iterations=6)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path in (1, 2)
+    assert solver.path_ok(1, 2)
     assert_parity(got, oracle.solve(topo, batch, cfg))
     # a third edge on the same pair exceeds the fast path's carry slots -> general path, same bits
     topo3 = Topology.from_edges(N, A, 0, edges + [(EDGE_RANGE_POSE, 2, 3, 0, 1)])
@@ -265,7 +265,7 @@ def test_multiple_range_edges_per_pose_and_unordered_insertion(solver):
                range_d=np.concatenate([batch.range_d, batch.range_d[:, :1]], 1),
                range_info=np.concatenate([batch.range_info, batch.range_info[:, :1]], 1))
     got = solver.solve(topo3, b3, cfg)
-    assert solver.last_path == 0
+    assert solver.path_ok(0)
     assert_parity(got, oracle.solve(topo3, b3, cfg))
 
 
@@ -282,7 +282,7 @@ def test_range_edges_between_non_adjacent_poses(solver):
                   range_d=np.abs(rng.normal(2, 1, (W, er))), range_info=rng.uniform(10, 400, (W, er)))
     cfg = Config(max_iterations=6)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 0
+    assert solver.path_ok(0)
     assert_parity(got, oracle.solve(topo, batch, cfg))
 
 
@@ -374,7 +374,7 @@ def test_general_properties_at_full_size(solver, make, iters):
     topo, batch, _ = make(W)
     cfg = Config(max_iterations=iters)
     got = solver.solve(topo, batch, cfg)
-    assert solver.last_path == 0
+    assert solver.path_ok(0)
     _, _, _, chi0 = solver.linearize(topo, batch.slice(0, 1024), cfg)
     assert (got.chi2[:1024, 1] <= chi0[:, 1]).all()
     R = got.pose_R.reshape(W, -1, 3, 3)
@@ -499,14 +499,18 @@ def test_abi_error_paths(solver):
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [0, 1])
 def test_branch_free_arithmetic_matches_ieee(solver, mode):
-    """The CHAIN kernels' branch-free sqrt / reciprocal / division / log sequences (NbMath) return the
-    bits of the IEEE operations whenever they do not flag their operand; flagged operands make the
-    solver re-run the trial with the IEEE operations.  2^28 operands per mode."""
+    """The branch-free sqrt / reciprocal / division / log / pivot sequences (NbMath) of the CHAIN and WINDOW
+    kernels return the bits of the IEEE operations whenever they do not flag their operand; flagged
+    operands make the solver re-run the trial (or the item) with the IEEE operations.  2^28 operands
+    per mode; one operand in eight is forced to a significand ending in a run of ones, the one
+    divisor class a Newton reciprocal can round wrongly (significand of ALL ones: flagged)."""
     compared, wrong, flagged = solver.selftest_math(1 << 28, mode=mode, seed=20260101 + mode)
     assert compared >= 1 << 28
     assert wrong == 0
     if mode == 1:
-        assert flagged == 0          # magnitudes the solver works with never leave the fast path
+        # magnitudes the solver works with leave the fast path only through the all-ones divisors:
+        # 1/8 forced x 1/4 with the full run x 1/2 not cleared, in 4 of the 5 operations
+        assert 0 < flagged < compared // 20
     else:
         assert 0 < flagged < compared  # NaN / inf / denormal / extreme exponents are flagged
 

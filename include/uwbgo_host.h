@@ -10,6 +10,14 @@
  * (publish_flag/..., localization.cpp:371,491,530,455,285) the window is queued, and
  * uwbgo_fleet_flush() solves all queued windows as one uwbgo_solve_batch per window structure and
  * then runs the queued publish() steps (chi2 gate, newest + mid-window pose, TUM log lines).
+ *
+ * Ordering rule of the deferred mode.  The reference solves inside the callback, so its graph never
+ * changes under a solve.  A queued window holds the member's vertices and a snapshot of their
+ * estimates; a member therefore never has more than one window queued, and a message (or a second
+ * solve) that reaches a member whose window is still queued first SETTLES that window: it is solved at
+ * once, on its own, outside the batch (counted in stats[6]).  Results are those of the reference's
+ * synchronous order either way; to get one batch per step, call uwbgo_fleet_flush() before feeding a
+ * member that has solved its next message.
  */
 #ifndef UWBGO_HOST_H
 #define UWBGO_HOST_H
@@ -76,6 +84,21 @@ int uwbgo_fleet_add_imu_each(uwbgo_fleet *f, uint32_t seq, uint32_t sec, uint32_
                              const char *frame_id, const double *orientation_xyzw /* [M][4] */,
                              const double *orientation_cov9 /* [9], shared */);
 
+/* A range edge built through the reference's edge classes between vertices the member already has:
+ * EDGE_RANGE = EdgeSE3Range with setVertexOffset(0 / 1, ...) (src/types/types_edge_se3range.cpp:99-114),
+ * EDGE_RANGE_OFFSET = EdgeSE3RangeOffset with setParameterId(0 / 1, ...) on a parameter table whose id k
+ * is antenna k, id 0 the identity (types_edge_se3range_offset.cpp:61-79,126-149).  from_age / to_age
+ * count ring slots from the oldest (to_age > from_age); to_anchor >= 0 names a fixed node id instead of
+ * to_age.  off_from / off_to: antenna numbers, 0 = identity.  An offset the solve path cannot carry is
+ * refused (UWBGO_E_INVALID, uwbgo_fleet_last_error), never dropped. */
+#define UWBGO_EDGE_CLASS_RANGE        0
+#define UWBGO_EDGE_CLASS_RANGE_OFFSET 1
+int uwbgo_fleet_add_typed_range_edge(uwbgo_fleet *f, int member, int edge_class, int from_age, int to_age,
+                                     int to_anchor, double measurement, double information, int off_from,
+                                     int off_to, int cauchy);
+/* solve() + publish() of one member now (queued for uwbgo_fleet_flush like a callback's solve) */
+int uwbgo_fleet_solve(uwbgo_fleet *f, int member);
+
 /* results of member `member` */
 int64_t uwbgo_fleet_published_count(const uwbgo_fleet *f, int member);
 /* k-th publish(): realtime / optimized = {stamp, x, y, z, qx, qy, qz, qw}; error = optimizer.chi2() */
@@ -84,9 +107,9 @@ int uwbgo_fleet_published(const uwbgo_fleet *f, int member, int64_t k, double *r
 /* all publishes of a member at once: arrays [count][8], [count][8], [count] */
 int uwbgo_fleet_published_all(const uwbgo_fleet *f, int member, double *realtime8, double *optimized8,
                               double *error);
-/* stats[0..5] = solves, rejected ranges, skipped publishes, errors, total windows solved by the
- * fleet, batches issued by the fleet */
-int uwbgo_fleet_stats(const uwbgo_fleet *f, int member, int64_t *stats6);
+/* stats[0..6] = solves, rejected ranges, skipped publishes, errors, total windows solved by the
+ * fleet's batches, batches issued by the fleet, windows of this member settled on their own */
+int uwbgo_fleet_stats(const uwbgo_fleet *f, int member, int64_t *stats7);
 /* chi2[4] and status[4] of the member's last solve */
 int uwbgo_fleet_last_solve(const uwbgo_fleet *f, int member, double *chi2_4, int32_t *status4);
 const char *uwbgo_fleet_last_error(const uwbgo_fleet *f, int member);

@@ -48,6 +48,9 @@ HOST_SYMBOLS = {
     "uwbgo_fleet_add_range_each": (C.c_int, [C.c_void_p, _u32, _u32, _u32, C.c_char_p, C.c_int, C.c_int,
                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]),
     "uwbgo_fleet_add_imu_each": (C.c_int, [C.c_void_p, _u32, _u32, _u32, C.c_char_p, _pd, _pd]),
+    "uwbgo_fleet_add_typed_range_edge": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                                   C.c_double, C.c_int, C.c_int, C.c_int]),
+    "uwbgo_fleet_solve": (C.c_int, [C.c_void_p, C.c_int]),
     "uwbgo_fleet_published_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "uwbgo_fleet_published": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _pd, _pd, _pd]),
     "uwbgo_fleet_published_all": (C.c_int, [C.c_void_p, C.c_int, _pd, _pd, _pd]),
@@ -206,6 +209,21 @@ class Fleet:
         self._lib.uwbgo_fleet_add_pose(self._h, member, seq, sec, nsec, frame_id.encode(),
                                        *[x.ctypes.data_as(_pd) for x in a])
 
+    EDGE_RANGE, EDGE_RANGE_OFFSET = 0, 1
+
+    def add_typed_range_edge(self, member, edge_class, from_age, to_age=-1, to_anchor=-1, measurement=0.0,
+                             information=1.0, off_from=0, off_to=0, cauchy=True):
+        """EdgeSE3Range (setVertexOffset) / EdgeSE3RangeOffset (setParameterId) between existing vertices;
+        raises on an offset the solve path cannot carry"""
+        rc = self._lib.uwbgo_fleet_add_typed_range_edge(self._h, member, edge_class, from_age, to_age, to_anchor,
+                                                        float(measurement), float(information), off_from, off_to,
+                                                        int(cauchy))
+        if rc != 0:
+            raise ValueError(self.last_error(member))
+
+    def solve(self, member):
+        self._lib.uwbgo_fleet_solve(self._h, member)
+
     # results ----------------------------------------------------------------------------------
     def published(self, member=0):
         """(realtime [n][8], optimized [n][8], error [n]); rows = stamp x y z qx qy qz qw"""
@@ -217,9 +235,10 @@ class Fleet:
         return rt, op, er
 
     def stats(self, member=0):
-        s = (C.c_int64 * 6)()
+        s = (C.c_int64 * 7)()
         self._lib.uwbgo_fleet_stats(self._h, member, s)
-        return dict(zip(("solves", "rejected", "skipped", "errors", "fleet_windows", "fleet_batches"), list(s)))
+        return dict(zip(("solves", "rejected", "skipped", "errors", "fleet_windows", "fleet_batches", "settled_alone"),
+                        list(s)))
 
     def last_solve(self, member=0):
         chi2, st = np.zeros(4), np.zeros(4, np.int32)

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <istream>
 #include <ostream>
+#include <string>
 
 namespace uwbgo {
 namespace host {
@@ -25,6 +26,18 @@ Isometry3d inverse(const Isometry3d &a)
         for (int c = 0; c < 3; ++c) o.R[3 * r + c] = a.R[3 * c + r];
     for (int r = 0; r < 3; ++r) o.t[r] = -(o.R[3 * r] * a.t[0] + o.R[3 * r + 1] * a.t[1] + o.R[3 * r + 2] * a.t[2]);
     return o;
+}
+
+int antenna_number(const Isometry3d &offset, const std::vector<Isometry3d> &antennas, const char *what)
+{
+    if (!offset.rotationIsIdentity())
+        throw std::invalid_argument(std::string(what) + ": the offset has a rotation; the solve path carries "
+                                    "translation-only lever arms (antenna numbers)");
+    if (offset.t[0] == 0 && offset.t[1] == 0 && offset.t[2] == 0) return 0;
+    for (size_t k = 0; k < antennas.size(); ++k)
+        if (antennas[k].t[0] == offset.t[0] && antennas[k].t[1] == offset.t[1] && antennas[k].t[2] == offset.t[2])
+            return (int)k + 1;
+    throw std::invalid_argument(std::string(what) + ": the lever arm is not in the window's antenna table");
 }
 
 static double range_between(const Isometry3d &p0, const Isometry3d &p1)
@@ -67,7 +80,7 @@ void EdgeSE3Range::computeError()
     error_ = measurement_ - range_between(compose(vertices_[0]->estimate(), offset[0]),
                                           compose(vertices_[1]->estimate(), offset[1]));
 }
-Edge EdgeSE3Range::asEdge(int antenna) const
+Edge EdgeSE3Range::asEdge(const std::vector<Isometry3d> &antennas) const
 {
     Edge e;
     e.kind = EdgeKind::Range;
@@ -76,7 +89,8 @@ Edge EdgeSE3Range::asEdge(int antenna) const
     e.range = measurement_;
     e.rangeInformation = information_;
     e.cauchy = cauchy_;
-    e.antenna = antenna;
+    e.antenna = antenna_number(offset[0], antennas, "EdgeSE3Range offset[0]");
+    e.antenna_b = antenna_number(offset[1], antennas, "EdgeSE3Range offset[1]");
     return e;
 }
 
@@ -117,8 +131,17 @@ void EdgeSE3RangeOffset::computeError()
     error_ = measurement_ - range_between(compose(vertices_[0]->estimate(), off(0)),
                                           compose(vertices_[1]->estimate(), off(1)));
 }
-Edge EdgeSE3RangeOffset::asEdge() const
+Edge EdgeSE3RangeOffset::asEdge(const std::vector<Isometry3d> &antennas) const
 {
+    auto off = [&](int k, const char *what) -> int {
+        if (!params_) { /* no parameter table: only the identity id 0 the reference registers */
+            if (pid_[k] != 0) throw std::invalid_argument(std::string(what) + ": parameter id without a parameter table");
+            return 0;
+        }
+        auto it = params_->find(pid_[k]);
+        if (it == params_->end()) throw std::invalid_argument(std::string(what) + ": unknown parameter id");
+        return antenna_number(it->second.offset(), antennas, what);
+    };
     Edge e;
     e.kind = EdgeKind::Range;
     e.from = vertices_[0];
@@ -126,7 +149,8 @@ Edge EdgeSE3RangeOffset::asEdge() const
     e.range = measurement_;
     e.rangeInformation = information_;
     e.cauchy = cauchy_;
-    e.antenna = pid_[0];
+    e.antenna = off(0, "EdgeSE3RangeOffset pidFrom");
+    e.antenna_b = off(1, "EdgeSE3RangeOffset pidTo");
     return e;
 }
 

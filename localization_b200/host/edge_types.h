@@ -7,6 +7,13 @@
  * initialEstimatePossible.  They are descriptors: asEdge() turns one into the plain Edge record
  * the window packer consumes; the batched solve never calls computeError() on the host (it exists
  * for inspection, initialEstimate and the outlier tooling, as in the reference).
+ *
+ * The solve path knows offsets as ANTENNA NUMBERS into the window's antenna table (translation-only
+ * lever arms, /uwb/antennaOffset, localization.cpp:111-123).  asEdge() therefore resolves both
+ * offsets of an edge -- offset[0] / offset[1], resp. the offsets of pidFrom / pidTo -- against that
+ * table and THROWS std::invalid_argument for an offset the solve path cannot honour (a rotation, or a
+ * lever arm that is not in the table): what computeError() evaluates on the host and what the GPU
+ * optimises are the same residual, or the call fails.
  */
 #ifndef UWBGO_HOST_EDGE_TYPES_H
 #define UWBGO_HOST_EDGE_TYPES_H
@@ -14,6 +21,7 @@
 #include <iosfwd>
 #include <map>
 #include <set>
+#include <stdexcept>
 #include <vector>
 
 #include "window_graph.h"
@@ -35,6 +43,9 @@ struct ParameterSE3Offset {
 
 Isometry3d compose(const Isometry3d &a, const Isometry3d &b);
 Isometry3d inverse(const Isometry3d &a);
+/* antenna number (1-based) of a translation-only offset in `antennas`, 0 for the identity; throws
+ * std::invalid_argument when the offset rotates or its lever arm is not in the table */
+int antenna_number(const Isometry3d &offset, const std::vector<Isometry3d> &antennas, const char *what);
 
 class RangeEdgeBase {
 public:
@@ -69,8 +80,8 @@ public:
     void computeError() override;
     void setVertexOffset(int vertex, Isometry3d &pose) { offset[(size_t)vertex] = pose; }
     std::vector<Isometry3d> offset = std::vector<Isometry3d>(2, Isometry3d::Identity());
-    /* antenna = index + 1 of offset[0] in the antenna table (0 = identity), as Localization sets it */
-    Edge asEdge(int antenna) const;
+    /* both offsets resolved against the window's antenna table (see the header comment) */
+    Edge asEdge(const std::vector<Isometry3d> &antennas) const;
     static const char *tag() { return "EDGE_RANGE"; }
 };
 
@@ -84,7 +95,9 @@ public:
     void computeError() override;
     bool setParameterId(int argNum, int paramId);
     int parameterId(int argNum) const { return pid_[argNum]; }
-    Edge asEdge() const; /* antenna = pidFrom (0 = the identity offset id the reference registers) */
+    /* the offsets of pidFrom / pidTo resolved against the window's antenna table; a parameter id that is
+     * not registered throws (g2o's resolveCaches() would fail, types_edge_se3range_offset.cpp:134-149) */
+    Edge asEdge(const std::vector<Isometry3d> &antennas) const;
     static const char *tag() { return "EDGE_RANGE_OFFSET"; }
 
 private:

@@ -172,6 +172,25 @@ int uwbgo_fleet_add_imu_each(uwbgo_fleet *f, uint32_t seq, uint32_t sec, uint32_
     return UWBGO_OK;
 }
 
+int uwbgo_fleet_add_typed_range_edge(uwbgo_fleet *f, int member, int edge_class, int from_age, int to_age, int to_anchor,
+                                     double measurement, double information, int off_from, int off_to, int cauchy)
+{
+    if (bad(f, member) || (edge_class != UWBGO_EDGE_CLASS_RANGE && edge_class != UWBGO_EDGE_CLASS_RANGE_OFFSET))
+        return UWBGO_E_INVALID;
+    return f->fleet->at((size_t)member).addTypedRangeEdge(edge_class == UWBGO_EDGE_CLASS_RANGE_OFFSET, from_age, to_age,
+                                                          to_anchor, measurement, information, off_from, off_to,
+                                                          cauchy != 0)
+               ? UWBGO_OK
+               : UWBGO_E_INVALID;
+}
+
+int uwbgo_fleet_solve(uwbgo_fleet *f, int member)
+{
+    if (bad(f, member)) return UWBGO_E_INVALID;
+    f->fleet->at((size_t)member).solve_and_publish();
+    return UWBGO_OK;
+}
+
 int64_t uwbgo_fleet_published_count(const uwbgo_fleet *f, int member)
 {
     return bad(f, member) ? -1 : (int64_t)f->fleet->at((size_t)member).published().size();
@@ -200,7 +219,7 @@ int uwbgo_fleet_published_all(const uwbgo_fleet *f, int member, double *realtime
     return UWBGO_OK;
 }
 
-int uwbgo_fleet_stats(const uwbgo_fleet *f, int member, int64_t *s)
+int uwbgo_fleet_stats(const uwbgo_fleet *f, int member, int64_t *s /* [7] */)
 {
     if (bad(f, member) || !s) return UWBGO_E_INVALID;
     Localization &m = f->fleet->at((size_t)member);
@@ -210,6 +229,7 @@ int uwbgo_fleet_stats(const uwbgo_fleet *f, int member, int64_t *s)
     s[3] = m.solver_errors();
     s[4] = f->fleet->windows_solved();
     s[5] = f->fleet->batches();
+    s[6] = m.settled_alone();
     return UWBGO_OK;
 }
 

@@ -125,7 +125,16 @@ std::vector<int32_t> PackedWindow::key() const
 {
     std::vector<int32_t> k{n_poses, n_anchors, n_antennas, identity_rotations ? 1 : 0, (int32_t)kind.size()};
     for (size_t e = 0; e < kind.size(); ++e) {
-        k.push_back(kind[e]); k.push_back(a[e]); k.push_back(b[e]); k.push_back(ant[e]); k.push_back(robust[e]);
+        k.push_back(kind[e]); k.push_back(a[e]); k.push_back(b[e]); k.push_back(ant[e]); k.push_back(ant_b[e]);
+        k.push_back(robust[e]);
+    }
+    /* one batch has ONE antenna table and ONE iteration limit (uwbgo_batch::ant_offsets, uwbgo_config):
+     * members that differ in either go to different batches */
+    k.push_back(iteration_max);
+    for (double x : antenna_xyz) {
+        int32_t bits[2];
+        std::memcpy(bits, &x, sizeof bits);
+        k.push_back(bits[0]); k.push_back(bits[1]);
     }
     return k;
 }
@@ -157,6 +166,8 @@ bool Localization::pack(PackedWindow &w, std::string &err)
     }
     w.n_poses = (int)w.pose_vertices.size();
     w.n_antennas = (int)offsets.size();
+    w.iteration_max = iteration_max;
+    for (const Isometry3d &o : offsets) w.antenna_xyz.insert(w.antenna_xyz.end(), o.t, o.t + 3);
     std::vector<bool> zero_offset(offsets.size());
     for (size_t k = 0; k < offsets.size(); ++k)
         zero_offset[k] = offsets[k].t[0] == 0 && offsets[k].t[1] == 0 && offsets[k].t[2] == 0;
@@ -186,10 +197,16 @@ bool Localization::pack(PackedWindow &w, std::string &err)
             err = "edge whose vertex 0 is not a pose of the window";
             return false;
         }
-        int kind, b = 0, ant = 0;
+        int kind, b = 0, ant = 0, ant_b = 0;
         if (e.kind == EdgeKind::Range) {
+            if (e.antenna < 0 || (size_t)e.antenna > offsets.size() || e.antenna_b < 0 || (size_t)e.antenna_b > offsets.size()) {
+                err = "range edge with an antenna number outside the antenna table";
+                return false;
+            }
             ant = e.antenna;
+            ant_b = e.antenna_b;
             if (ant > 0 && zero_offset[(size_t)ant - 1]) ant = 0; /* a zero lever arm is the identity offset, bit for bit */
+            if (ant_b > 0 && zero_offset[(size_t)ant_b - 1]) ant_b = 0;
             if (e.to->fixed()) {
                 kind = UWBGO_EDGE_RANGE_ANCHOR;
                 b = anchor_of(e.to);
@@ -223,6 +240,7 @@ bool Localization::pack(PackedWindow &w, std::string &err)
         w.a.push_back(pa->second);
         w.b.push_back(b);
         w.ant.push_back(ant);
+        w.ant_b.push_back(ant_b);
         w.robust.push_back(e.cauchy ? 1 : 0);
     }
     w.n_anchors = (int)anchor_index.size();
@@ -244,11 +262,11 @@ void Localization::unpack(const PackedWindow &w, const double *pose_t, const dou
     ++n_solves_;
 }
 
-static void fill_abi(const PackedWindow &w, const std::vector<double> &antenna_xyz, int64_t n_windows,
-                     uwbgo_topology &t, uwbgo_batch &b)
+static void fill_abi(const PackedWindow &w, int64_t n_windows, uwbgo_topology &t, uwbgo_batch &b)
 {
+    const std::vector<double> &antenna_xyz = w.antenna_xyz;
     t = uwbgo_topology{w.n_poses, w.n_anchors, w.n_antennas, (int32_t)w.kind.size(), w.kind.data(), w.a.data(),
-                       w.b.data(), w.ant.data(), w.robust.data()};
+                       w.b.data(), w.ant.data(), w.robust.data(), w.ant_b.data()};
     b = uwbgo_batch{};
     b.n_windows = n_windows;
     b.pose_t = w.pose_t.data();
@@ -264,29 +282,15 @@ static void fill_abi(const PackedWindow &w, const std::vector<double> &antenna_x
     b.se3_info = w.se3_info.data();
 }
 
-/* replaces localization.cpp:164-192 */
-void Localization::solve()
+/* one window through the solver right now (the reference's synchronous optimize()) */
+bool Localization::solve_window(const PackedWindow &w)
 {
-    std::string err;
-    PackedWindow w;
-    if (!pack(w, err)) {
-        last_error_ = err;
-        ++n_errors_;
-        return;
-    }
-    if (fleet_) { /* lockstep mode: Fleet::flush() issues the batch */
-        pending_ = std::move(w);
-        solve_pending_ = true;
-        return;
-    }
-    std::vector<double> antenna_xyz;
-    for (const Isometry3d &o : offsets) antenna_xyz.insert(antenna_xyz.end(), o.t, o.t + 3);
     uwbgo_topology topo;
     uwbgo_batch in;
-    fill_abi(w, antenna_xyz, 1, topo, in);
+    fill_abi(w, 1, topo, in);
     uwbgo_config cfg;
     uwbgo_config_default(&cfg);
-    cfg.max_iterations = iteration_max;
+    cfg.max_iterations = w.iteration_max;
     std::vector<double> pose_t(w.pose_t.size()), pose_R(w.pose_R.size());
     std::vector<int32_t> oplus(w.oplus.size());
     double chi2[UWBGO_CHI2_STRIDE];
@@ -296,9 +300,53 @@ void Localization::solve()
     if (rc != UWBGO_OK) { /* the reference ignores optimize()'s return value; we at least count it */
         last_error_ = std::string("uwbgo_solve_batch failed: ") + uwbgo_last_error();
         ++n_errors_;
-        return;
+        return false;
     }
     unpack(w, pose_t.data(), pose_R.data(), oplus.data(), chi2, status);
+    return true;
+}
+
+/* Deferred (fleet) mode parks a packed window -- vertex pointers and a snapshot of the estimates --
+ * until Fleet::flush().  The reference solves synchronously, so the graph can never change under a
+ * solve; here every callback that is about to touch the graph settles a parked window first (solved on
+ * its own, outside the fleet's batch) so that neither a dangling vertex nor a stale snapshot can occur. */
+void Localization::settle()
+{
+    if (!solve_pending_) return;
+    solve_pending_ = false;
+    ++n_settled_;
+    const bool ok = solve_window(pending_);
+    pending_ = PackedWindow();
+    if (publish_pending_) {
+        publish_pending_ = false;
+        if (ok) publish(); else ++n_skipped_;
+    }
+}
+
+/* replaces localization.cpp:164-192; false = no solve ran (counted in solver_errors()) */
+bool Localization::solve()
+{
+    settle();
+    std::string err;
+    PackedWindow w;
+    if (!pack(w, err)) {
+        last_error_ = err;
+        ++n_errors_;
+        return false;
+    }
+    if (fleet_) { /* lockstep mode: Fleet::flush() issues the batch */
+        pending_ = std::move(w);
+        solve_pending_ = true;
+        return true;
+    }
+    return solve_window(w);
+}
+
+/* what every callback does where the reference has "solve(); publish();": a publish() after a solve
+ * that did not run would gate on the previous solve's chi2 and log an un-optimised estimate */
+void Localization::solve_and_publish()
+{
+    if (solve()) publish(); else ++n_skipped_;
 }
 
 /* replaces localization.cpp:195-251 (ROS publishers / TF become records, log files stay) */
@@ -337,7 +385,62 @@ Edge Localization::make_range_edge(VertexSE3 *v1, VertexSE3 *v2, double distance
     edge.setMeasurement(distance);
     edge.setInformation(1.0 / covariance); /* 1x1 covariance_matrix.inverse() */
     edge.setRobustKernel(new RobustKernelCauchy());
-    return edge.asEdge(0);
+    return edge.asEdge(offsets);
+}
+
+/* the two range edge classes of src/types/ driven the way a g2o user drives them; see the header */
+bool Localization::addTypedRangeEdge(bool parameter_offsets, int from_age, int to_age, int to_anchor,
+                                     double measurement, double information, int off_from, int off_to, bool cauchy)
+{
+    settle();
+    Robot &me = robots.at(self_id);
+    auto fail = [&](const char *why) {
+        last_error_ = why;
+        ++n_errors_;
+        return false;
+    };
+    if (from_age < 0 || from_age >= me.length()) return fail("typed range edge: vertex 0 is not a pose of the ring");
+    VertexSE3 *v0 = me.by_age(from_age), *v1 = nullptr;
+    if (to_anchor >= 0) {
+        if (!robots.count(to_anchor) || !robots.at(to_anchor).is_static()) return fail("typed range edge: unknown anchor id");
+        v1 = robots.at(to_anchor).last_vertex();
+    } else {
+        if (to_age <= from_age || to_age >= me.length()) return fail("typed range edge: vertex 1 is not a newer pose of the ring");
+        v1 = me.by_age(to_age);
+    }
+    if (off_from < 0 || (size_t)off_from > offsets.size() || off_to < 0 || (size_t)off_to > offsets.size())
+        return fail("typed range edge: antenna number outside the antenna table");
+    try {
+        if (parameter_offsets) { /* EDGE_RANGE_OFFSET: offsets by parameter id, id 0 = identity (types_edge_se3range_offset.cpp:61-79) */
+            std::map<int, ParameterSE3Offset> params;
+            params[0].setId(0);
+            for (size_t k = 0; k < offsets.size(); ++k) {
+                params[(int)k + 1].setId((int)k + 1);
+                params[(int)k + 1].setOffset(offsets[k]);
+            }
+            EdgeSE3RangeOffset edge(&params);
+            edge.vertices()[0] = v0;
+            edge.vertices()[1] = v1;
+            edge.setMeasurement(measurement);
+            edge.setInformation(information);
+            if (cauchy) edge.setRobustKernel(new RobustKernelCauchy());
+            if (!edge.setParameterId(0, off_from) || !edge.setParameterId(1, off_to)) return fail("typed range edge: unknown parameter id");
+            optimizer.addEdge(edge.asEdge(offsets));
+        } else { /* EDGE_RANGE: offsets by value (types_edge_se3range.cpp:99-114) */
+            EdgeSE3Range edge;
+            edge.vertices()[0] = v0;
+            edge.vertices()[1] = v1;
+            edge.setMeasurement(measurement);
+            edge.setInformation(information);
+            if (cauchy) edge.setRobustKernel(new RobustKernelCauchy());
+            if (off_from > 0) edge.setVertexOffset(0, offsets[(size_t)off_from - 1]);
+            if (off_to > 0) edge.setVertexOffset(1, offsets[(size_t)off_to - 1]);
+            optimizer.addEdge(edge.asEdge(offsets));
+        }
+    } catch (const std::invalid_argument &e) {
+        return fail(e.what());
+    }
+    return true;
 }
 
 /* localization.cpp:560-605 */
@@ -361,6 +464,7 @@ Edge Localization::make_se3_edge_from_twist(VertexSE3 *v1, VertexSE3 *v2, const 
 /* localization.cpp:297-376 */
 void Localization::addRangeEdge(const UwbRange &uwb)
 {
+    settle();
     ++number_measurements;
     if (!robots.count(uwb.requester_id) || !robots.count(uwb.responder_id)) {
         last_error_ = "range between unknown nodes";
@@ -405,14 +509,14 @@ void Localization::addRangeEdge(const UwbRange &uwb)
         optimizer.addEdge(make_range_edge(vertex_last_responder, vertex_responder, 0, cov_responder));
     }
     if (prm.publish_range && number_measurements > trajectory_length) {
-        solve();
-        publish();
+        solve_and_publish();
     }
 }
 
 /* localization.cpp:254-290: EdgeSE3 from the key vertex of the current keyframe to the new vertex */
 void Localization::addPoseEdge(const PoseWithCovarianceStamped &pose_cov)
 {
+    settle();
     Robot &me = robots.at(self_id);
     if (pose_cov.header.frame_id != me.last_header(sensor_type.pose).frame_id) key_vertex = me.last_vertex(sensor_type.pose);
     VertexSE3 *fresh = me.new_vertex(sensor_type.pose, pose_cov.header, optimizer);
@@ -429,14 +533,14 @@ void Localization::addPoseEdge(const PoseWithCovarianceStamped &pose_cov)
     e.cauchy = true;
     optimizer.addEdge(e);
     if (prm.publish_pose) {
-        solve();
-        publish();
+        solve_and_publish();
     }
 }
 
 /* localization.cpp:462-496 */
 void Localization::addLidarEdge(const PoseWithCovarianceStamped &pose_cov)
 {
+    settle();
     Robot &me = robots.at(self_id);
     if (me.last_header().frame_id.find(pose_cov.header.frame_id) == std::string::npos) {
         me.append_last_header(pose_cov.header.frame_id);
@@ -452,14 +556,14 @@ void Localization::addLidarEdge(const PoseWithCovarianceStamped &pose_cov)
         optimizer.addEdge(prior);
     }
     if (prm.publish_lidar) {
-        solve();
-        publish();
+        solve_and_publish();
     }
 }
 
 /* localization.cpp:499-535 */
 void Localization::addImuEdge(const Imu &imu)
 {
+    settle();
     Robot &me = robots.at(self_id);
     if (me.last_header().frame_id.find(imu.header.frame_id) == std::string::npos) {
         me.append_last_header(imu.header.frame_id);
@@ -478,22 +582,21 @@ void Localization::addImuEdge(const Imu &imu)
         optimizer.addEdge(prior);
     }
     if (prm.publish_imu) {
-        solve();
-        publish();
+        solve_and_publish();
     }
 }
 
 /* localization.cpp:438-459 */
 void Localization::addTwistEdge(const TwistWithCovarianceStamped &twist)
 {
+    settle();
     Robot &me = robots.at(self_id);
     const double dt = twist.header.stamp.toSec() - me.last_header().stamp.toSec();
     VertexSE3 *last = me.last_vertex();
     VertexSE3 *fresh = me.new_vertex(sensor_type.twist, twist.header, optimizer);
     optimizer.addEdge(make_se3_edge_from_twist(last, fresh, twist, dt));
     if (prm.publish_twist) {
-        solve();
-        publish();
+        solve_and_publish();
     }
 }
 
@@ -586,14 +689,12 @@ int Fleet::flush()
         gather(&PackedWindow::se3_info);
         cat.oplus.clear();
         for (Localization *m : mem) cat.oplus.insert(cat.oplus.end(), m->pending_.oplus.begin(), m->pending_.oplus.end());
-        std::vector<double> antenna_xyz; /* one antenna table per structure: members of a fleet share it */
-        for (const Isometry3d &o : mem[0]->offsets) antenna_xyz.insert(antenna_xyz.end(), o.t, o.t + 3);
-        uwbgo_topology topo;
+        uwbgo_topology topo; /* antenna table and iteration limit are part of the key: equal within the group */
         uwbgo_batch in;
-        fill_abi(cat, antenna_xyz, W, topo, in);
+        fill_abi(cat, W, topo, in);
         uwbgo_config cfg;
         uwbgo_config_default(&cfg);
-        cfg.max_iterations = mem[0]->iteration_max;
+        cfg.max_iterations = w0.iteration_max;
         const size_t N = (size_t)w0.n_poses;
         std::vector<double> pose_t((size_t)W * N * 3), pose_R((size_t)W * N * 9), chi2((size_t)W * UWBGO_CHI2_STRIDE);
         std::vector<int32_t> oplus((size_t)W * N), status((size_t)W * UWBGO_STATUS_STRIDE);
@@ -614,8 +715,9 @@ int Fleet::flush()
             m->solve_pending_ = false;
             if (m->publish_pending_) {
                 m->publish_pending_ = false;
-                if (rc == UWBGO_OK) m->publish();
+                if (rc == UWBGO_OK) m->publish(); else ++m->n_skipped_;
             }
+            m->pending_ = PackedWindow();
         }
     }
     return rc_all;

@@ -55,8 +55,9 @@ struct Params {
 
 /* one window as the C ABI wants it, plus the way back to the vertices */
 struct PackedWindow {
-    std::vector<int32_t> kind, a, b, ant, robust;
-    int n_poses = 0, n_anchors = 0, n_antennas = 0;
+    std::vector<int32_t> kind, a, b, ant, ant_b, robust;
+    int n_poses = 0, n_anchors = 0, n_antennas = 0, iteration_max = 0;
+    std::vector<double> antenna_xyz; /* [n_antennas][3] */
     bool identity_rotations = true;
     std::vector<double> pose_t, pose_R, anchors, range_d, range_info, prior_Z, prior_info, se3_Z, se3_info;
     std::vector<int32_t> oplus;
@@ -77,8 +78,19 @@ public:
     Localization(const Params &, SolveBackend backend);
     ~Localization();
 
-    void solve();
+    bool solve();   /* false: no solve ran (pack or solver error, counted in solver_errors()) */
     void publish();
+    void solve_and_publish(); /* "solve(); publish();" of the callbacks; no publish after a failed solve */
+    /* deferred mode: solve a window parked for Fleet::flush() now, on its own (see settle() in the .cpp);
+     * every callback calls it before it touches the graph */
+    void settle();
+    int settled_alone() const { return n_settled_; }
+    /* range edges built through the reference's edge classes (types_edge_se3range*.cpp) between vertices
+     * of the window: from_age / to_age count from the oldest ring slot, to_anchor >= 0 names a fixed node
+     * id instead.  off_from / off_to are antenna numbers: EdgeSE3Range gets setVertexOffset(0 / 1, ...),
+     * EdgeSE3RangeOffset gets setParameterId(0 / 1, ...) on a table whose id k holds offsets[k-1] */
+    bool addTypedRangeEdge(bool parameter_offsets, int from_age, int to_age, int to_anchor, double measurement,
+                           double information, int off_from, int off_to, bool cauchy);
     void addRangeEdge(const UwbRange &);
     void addPoseEdge(const PoseWithCovarianceStamped &);
     void addLidarEdge(const PoseWithCovarianceStamped &);
@@ -109,6 +121,7 @@ public:
 
 private:
     friend class Fleet;
+    bool solve_window(const PackedWindow &w);
     Edge make_range_edge(VertexSE3 *v1, VertexSE3 *v2, double distance, double covariance);
     Edge make_se3_edge_from_twist(VertexSE3 *v1, VertexSE3 *v2, const TwistWithCovarianceStamped &, double dt);
     void save_file(const PoseStamped &pose, const std::string &filename);
@@ -133,7 +146,7 @@ private:
 
     std::vector<Published> published_;
     std::vector<PoseStamped> republished_;
-    int n_solves_ = 0, n_rejected_ = 0, n_skipped_ = 0, n_errors_ = 0;
+    int n_solves_ = 0, n_rejected_ = 0, n_skipped_ = 0, n_errors_ = 0, n_settled_ = 0;
     double last_chi2_[UWBGO_CHI2_STRIDE] = {0, 0, 0, 0};
     int32_t last_status_[UWBGO_STATUS_STRIDE] = {0, 0, 0, 0};
     std::string last_error_;

@@ -68,7 +68,33 @@ int main()
     CHECK(!eo.setParameterId(0, 7)); /* unknown parameter id */
     std::stringstream s3;
     CHECK(eo.write(s3) && s3.str() == "1 0 5.5 4");
-    CHECK(eo.asEdge().antenna == 1 && e.asEdge(2).antenna == 2);
+    /* asEdge resolves BOTH offsets against the antenna table, and refuses what the solve path cannot carry */
+    {
+        Isometry3d other;
+        other.t[0] = 0.5;
+        std::vector<Isometry3d> table{other, off};
+        Edge pe = eo.asEdge(table), re = e.asEdge(table);
+        CHECK(pe.antenna == 2 && pe.antenna_b == 0 && re.antenna == 2 && re.antenna_b == 0);
+        e.setVertexOffset(1, other);
+        re = e.asEdge(table);
+        CHECK(re.antenna == 2 && re.antenna_b == 1);
+        CHECK(eo.setParameterId(1, 1));
+        pe = eo.asEdge(table);
+        CHECK(pe.antenna == 2 && pe.antenna_b == 2);
+        bool threw = false;
+        try { e.asEdge(std::vector<Isometry3d>{off}); } catch (const std::invalid_argument &) { threw = true; }
+        CHECK(threw); /* offset[1] is not in the table */
+        Isometry3d rot = off;
+        rot.R[0] = 0; rot.R[1] = -1; rot.R[3] = 1; rot.R[4] = 0;
+        e.setVertexOffset(0, rot);
+        threw = false;
+        try { e.asEdge(table); } catch (const std::invalid_argument &) { threw = true; }
+        CHECK(threw); /* a rotating offset */
+        e.setVertexOffset(0, off);
+        Isometry3d id = Isometry3d::Identity();
+        e.setVertexOffset(1, id);
+        CHECK(eo.setParameterId(1, 0));
+    }
 
     /* initialEstimate: slide vertex 1 along the line of sight to the measured distance */
     EdgeSE3Range ie;

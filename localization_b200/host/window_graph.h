@@ -66,6 +66,7 @@ struct Edge {
     bool cauchy = false;                      /* setRobustKernel(new RobustKernelCauchy()) */
     double range = 0.0, rangeInformation = 0.0;
     int antenna = 0;                          /* setVertexOffset(0, offsets[antenna-1]); 0: none */
+    int antenna_b = 0;                        /* setVertexOffset(1, offsets[antenna_b-1]) / pidTo; 0: none */
     Isometry3d measurement;                   /* EdgeSE3 / EdgeSE3Prior */
     double information[36] = {0};             /* 6x6 row-major */
 };

@@ -164,3 +164,101 @@ def test_pose_edges_to_a_key_vertex():
     assert st["errors"] == 0 and st["solves"] == 20, fleet.last_error(0)
     assert rec[-1][0] == 8 and rec[-1][4]           # full window of 8 poses, rotations present
     assert len(fleet.published(0)[0]) > 0
+
+
+def oracle_backend_recording_offsets(rec):
+    lib = oracle.load()
+
+    def fn(_user, topo, batch, cfg, out):
+        t = topo.contents
+        E = t.n_edges
+        rec.append(([t.edge_kind[e] for e in range(E)], [t.edge_ant[e] for e in range(E)],
+                    [t.edge_ant_b[e] for e in range(E)] if t.edge_ant_b else None, int(batch.contents.n_windows)))
+        return lib.uwbgo_oracle_solve_batch(topo, batch, cfg, out, None, 1)
+    return fn
+
+
+def test_typed_edges_carry_both_offsets_to_the_solver():
+    """EdgeSE3Range::setVertexOffset(0/1) and EdgeSE3RangeOffset::setParameterId(0/1) reach the C ABI as
+    edge_ant / edge_ant_b; nothing is dropped on the way (types_edge_se3range.cpp:99-114,
+    types_edge_se3range_offset.cpp:126-149)"""
+    from typed_edge_scenario import drive
+    rec = []
+    fleet = Fleet(solve_fn=oracle_backend_recording_offsets(rec))
+    out = drive(fleet, MSGS, members=1, rounds=2)
+    assert fleet.stats(0)["errors"] == 0, fleet.last_error(0)
+    kinds, ant, ant_b, _ = rec[-1]
+    pairs = [(a, b) for k, a, b in zip(kinds, ant, ant_b) if k in (0, 1)]
+    for want in ((2, 1), (0, 3), (1, 3), (0, 2)):
+        assert want in pairs, (want, pairs)
+    assert any(k == 2 for k in kinds)                # IMU priors: the window has rotations
+    chi2, status = out[-1][0][1], out[-1][0][2]
+    assert np.isfinite(chi2).all() and status[0] >= 1
+
+
+def test_typed_edge_with_an_offset_the_solver_cannot_carry_is_refused():
+    msgs = load_messages(MSGS)
+    fleet = Fleet(solve_fn=oracle_backend())
+    fleet.add(node_params(msgs, LocParams(**UWB_ONLY, antenna_offset=[0.1, 0.0, 0.0])))
+    with pytest.raises(ValueError, match="antenna"):
+        fleet.add_typed_range_edge(0, Fleet.EDGE_RANGE, from_age=0, to_age=1, off_from=2)      # not in the table
+    with pytest.raises(ValueError, match="newer pose"):
+        fleet.add_typed_range_edge(0, Fleet.EDGE_RANGE_OFFSET, from_age=3, to_age=2, off_from=1)
+    with pytest.raises(ValueError, match="anchor"):
+        fleet.add_typed_range_edge(0, Fleet.EDGE_RANGE, from_age=0, to_anchor=555)
+    assert fleet.stats(0)["errors"] == 3
+
+
+def test_deferred_mode_settles_a_queued_window_before_the_graph_changes():
+    """range -> twist with no flush in between: the twist evicts the oldest vertex of the queued window.
+    The queued window is solved first (on its own), so the stream equals the flush-every-message stream."""
+    msgs = load_messages(MSGS)
+    cov = (np.eye(6) * 1e-2).reshape(-1)
+
+    def run(flush_every):
+        fleet = Fleet(solve_fn=oracle_backend())
+        fleet.add(node_params(msgs, LocParams(**{**UWB_ONLY, "trajectory_length": 6})))
+        for i in range(40):
+            fleet.add_range(0, i, int(msgs["uwb_sec"][i]), int(msgs["uwb_nsec"][i]), "uwb", 200,
+                            int(msgs["uwb_responder"][i]), float(msgs["uwb_distance"][i]),
+                            float(msgs["uwb_distance_err"][i]), 0)
+            if flush_every:
+                fleet.flush()
+            fleet.add_twist(0, i, int(msgs["uwb_sec"][i]), int(msgs["uwb_nsec"][i]) + 2000, "odom",
+                            [0.1, 0.0, 0.0], [0.0, 0.0, 0.01], cov)
+            if i % 7 == 0:
+                fleet.solve(0)      # a second solve while one may be queued
+                if flush_every:
+                    fleet.flush()
+        fleet.flush()
+        return fleet
+
+    a, b = run(True), run(False)
+    assert a.stats(0)["errors"] == 0 and b.stats(0)["errors"] == 0
+    assert a.stats(0)["solves"] == b.stats(0)["solves"] > 30
+    assert b.stats(0)["settled_alone"] > 25 and a.stats(0)["settled_alone"] == 0
+    for x, y in zip(a.published(0), b.published(0)):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a.window_poses(0), b.window_poses(0))
+
+
+def test_fleet_members_with_different_antenna_tables_or_iteration_limits_do_not_share_a_batch():
+    msgs = load_messages(MSGS)
+    rec = []
+    fleet = Fleet(solve_fn=oracle_backend_recording_offsets(rec))
+    base = {**UWB_ONLY, "trajectory_length": 5}
+    fleet.add(node_params(msgs, LocParams(**base, antenna_offset=[0.1, 0.0, 0.0])))
+    fleet.add(node_params(msgs, LocParams(**base, antenna_offset=[0.1, 0.0, 0.0])))
+    fleet.add(node_params(msgs, LocParams(**base, antenna_offset=[0.2, 0.0, 0.0])))
+    fleet.add(node_params(msgs, LocParams(**{**base, "maximum_iteration": 3}, antenna_offset=[0.1, 0.0, 0.0])))
+    for i in range(8):
+        for mem in range(4):
+            fleet.add_range(mem, i, int(msgs["uwb_sec"][i]), int(msgs["uwb_nsec"][i]), "uwb", 200,
+                            int(msgs["uwb_responder"][i]), float(msgs["uwb_distance"][i]),
+                            float(msgs["uwb_distance_err"][i]), 1)
+        n0 = len(rec)
+        fleet.flush()
+        if len(rec) > n0:
+            assert sorted(r[3] for r in rec[n0:]) == [1, 1, 2]     # {0, 1} together, 2 and 3 alone
+    assert len(rec) >= 6
+    assert fleet.last_solve(3)[1][0] <= 3 < fleet.last_solve(0)[1][0]

@@ -365,6 +365,28 @@ def test_properties_at_full_size(solver):
     assert np.array_equal(got.status[idx], ref.status)
 
 
+def test_c5_properties_at_full_size(_gpu_solver):
+    """BASELINE C5 on one GPU (131,072 windows x N=200, A=16: the largest configuration): the same
+    size-independent properties, and every 257th window against the oracle bit for bit"""
+    solver = _gpu_solver
+    W = 131072
+    topo, batch, truth = synthetic.uwb_only(W, 200, 16, seed=synthetic.SEED_C3 + 5)
+    cfg = Config(max_iterations=10)
+    got = solver.solve(topo, batch, cfg)
+    assert solver.last_path in (1, 2)
+    _, _, _, chi0 = solver.linearize(topo, batch.slice(0, 2048), cfg)
+    assert (got.chi2[:2048, 1] <= chi0[:, 1]).all()
+    assert (got.status[:, 0] == 10).all() and (got.status[:, 2] == 0).all()
+    assert np.abs(got.pose_t - truth).mean() < np.abs(batch.pose_t - truth).mean()
+    idx = np.arange(0, W, 257)
+    sub = Batch(pose_t=batch.pose_t[idx], anchors=batch.anchors[idx], range_d=batch.range_d[idx],
+                range_info=batch.range_info[idx])
+    ref = oracle.solve(topo, sub, cfg)
+    assert np.array_equal(got.pose_t[idx], ref.pose_t)
+    assert np.array_equal(got.chi2[idx], ref.chi2)
+    assert np.array_equal(got.status[idx], ref.status)
+
+
 @pytest.mark.parametrize("make,iters", [(synthetic.uwb_imu_lidar, 20), (synthetic.uwb_twist, 12)])
 def test_general_properties_at_full_size(solver, make, iters):
     """BASELINE C4 size (two halves of 8,192 windows, 6x6 blocks, CTA-per-tile kernel, one chunk):

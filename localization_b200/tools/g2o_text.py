@@ -73,14 +73,15 @@ def write_window(path: str, topo: Topology, batch: Batch, w: int = 0, self_id: i
     sr = sp = ss = 0
     for e in range(topo.n_edges):
         k, a, b, ant = topo.edge_kind[e], topo.edge_a[e], topo.edge_b[e], topo.edge_ant[e]
+        ant_b = 0 if topo.edge_ant_b is None else topo.edge_ant_b[e]
         if topo.edge_robust[e]:
             lines.append(f"# ROBUST {e}")
         if k in (EDGE_RANGE_ANCHOR, EDGE_RANGE_POSE):
             v1 = anchor_ids[b] if k == EDGE_RANGE_ANCHOR else pid(b)
             d, info = batch.range_d[w].reshape(-1)[sr], batch.range_info[w].reshape(-1)[sr]
             sr += 1
-            if ant > 0:
-                lines.append(f"EDGE_RANGE_OFFSET {pid(a)} {v1} {ant} 0 {_f(d)} {_f(info)}")
+            if ant > 0 or ant_b > 0:
+                lines.append(f"EDGE_RANGE_OFFSET {pid(a)} {v1} {ant} {ant_b} {_f(d)} {_f(info)}")
             else:
                 lines.append(f"EDGE_RANGE {pid(a)} {v1} {_f(d)} {_f(info)}")
         elif k == EDGE_PRIOR:
@@ -118,9 +119,9 @@ def read_window(path: str):
             elif tag == "PARAMS_SE3OFFSET":
                 params[int(x[0])] = np.array(x[1:8], float)
             elif tag == "EDGE_RANGE":
-                edges.append(("range", int(x[0]), int(x[1]), 0, float(x[2]), float(x[3])))
+                edges.append(("range", int(x[0]), int(x[1]), 0, float(x[2]), float(x[3]), 0))
             elif tag == "EDGE_RANGE_OFFSET":
-                edges.append(("range", int(x[0]), int(x[1]), int(x[2]), float(x[4]), float(x[5])))
+                edges.append(("range", int(x[0]), int(x[1]), int(x[2]), float(x[4]), float(x[5]), int(x[3])))
             elif tag in ("EDGE_SE3:QUAT", "EDGE_SE3_PRIOR"):
                 vals = np.array(x[2:], float)
                 I = np.zeros((6, 6))
@@ -140,11 +141,11 @@ def read_window(path: str):
     for e, ed in enumerate(edges):
         rb = 1 if e in robust else 0
         if ed[0] == "range":
-            _, v0, v1, ant, d, info = ed
+            _, v0, v1, ant, d, info, ant_b = ed
             if v1 in aidx:
-                te.append((EDGE_RANGE_ANCHOR, pidx[v0], aidx[v1], ant, rb))
+                te.append((EDGE_RANGE_ANCHOR, pidx[v0], aidx[v1], ant, rb, ant_b))
             else:
-                te.append((EDGE_RANGE_POSE, pidx[v0], pidx[v1], ant, rb))
+                te.append((EDGE_RANGE_POSE, pidx[v0], pidx[v1], ant, rb, ant_b))
             rd.append(d)
             ri.append(info)
         elif ed[0] == "prior":

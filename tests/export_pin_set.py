@@ -8,10 +8,12 @@ the one open point of DESIGN.md section 2 ("parity unpinned").  TEST INFRASTRUCT
 writes, per window, <shape>_<k>.g2o (localization_b200/tools/g2o_text.py: VERTEX_SE3:QUAT, FIX, EDGE_RANGE,
 EDGE_RANGE_OFFSET, EDGE_SE3:QUAT, EDGE_SE3_PRIOR; '# ROBUST <edge>' comment lines mark the Cauchy edges) and
 expected.json: final translations / rotations, {plain, robust, g2o-stale} chi2, final lambda, iterations, trials.
-On the g2o side (C++, ~30 lines): load the file with the reference's libtypes_edge_se3range registered, set
-RobustKernelCauchy(delta = 1) on the marked edges, BlockSolver_6_3 + LinearSolverCholmod +
-OptimizationAlgorithmLevenberg as in localization.cpp:44-52, initializeOptimization(); optimize(iterations);
-then compare: poses within 1e-6 m, chi2 within 1e-9 relative (BASELINE.json north_star)."""
+and <shape>_<k>.expected (the same numbers as plain "key value" lines, %.17g, for the C++ checker).
+The g2o side is tools/pin_check/ (C++ + CMake): it loads each file with the reference's own edge types
+compiled from the reference's sources, sets RobustKernelCauchy on the marked edges, builds BlockSolver_6_3 +
+LinearSolverCholmod + OptimizationAlgorithmLevenberg as in localization.cpp:44-52, runs
+initializeOptimization(); optimize(iterations); and compares: poses within 1e-6 m, chi2 within 1e-9 relative
+(BASELINE.json north_star), equal iteration and trial counts."""
 import argparse
 import json
 import os
@@ -53,6 +55,20 @@ def main():
                 "chi2_g2o_stale": float(ref.chi2[w, 2]), "lambda": float(ref.chi2[w, 3]),
                 "iterations": int(ref.status[w, 0]), "trials": int(ref.status[w, 1]), "flags": int(ref.status[w, 2]),
             }
+            x = expected[f]
+            N = topo.n_poses
+            R = ref.pose_R[w].reshape(N, 9) if ref.pose_R is not None else [[1, 0, 0, 0, 1, 0, 0, 0, 1]] * N
+            g = lambda v: "%.17g" % float(v)
+            lines = [f"iterations_max {iters}", f"iterations {x['iterations']}", f"trials {x['trials']}",
+                     f"flags {x['flags']}", f"chi2_plain {g(x['chi2_plain'])}", f"chi2_robust {g(x['chi2_robust'])}",
+                     f"chi2_g2o_stale {g(x['chi2_g2o_stale'])}", f"lambda {g(x['lambda'])}"]
+            for i in range(N):   # vertex ids as g2o_text.write_window assigns them: slot * 300 + self id (robot.cpp:43,94)
+                lines.append(f"pose {i * 300 + 200} " + " ".join(g(v) for v in list(ref.pose_t[w, i]) + list(R[i])))
+            if getattr(ref, "edge_chi2", None) is not None:
+                lines.append("edge_chi2 " + " ".join(g(v) for v in ref.edge_chi2[w]))
+                x["edge_chi2"] = ref.edge_chi2[w].tolist()
+            with open(os.path.join(a.out, f[:-4] + ".expected"), "w") as fh:
+                fh.write("\n".join(lines) + "\n")
     with open(os.path.join(a.out, "expected.json"), "w") as fh:
         json.dump(expected, fh, indent=1)
     print(f"{len(expected)} windows + expected.json in {a.out}")

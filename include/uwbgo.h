@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UWBGO_ABI_VERSION 2
+#define UWBGO_ABI_VERSION 3
 
 /* error codes */
 #define UWBGO_OK              0
@@ -80,6 +80,32 @@ typedef struct uwbgo_topology {
                                 /*     (what Localization creates, localization.cpp:333)           */
 } uwbgo_topology;
 
+/*
+ * Compact form of the range data: the FIELDS OF THE RANGE MESSAGES instead of the edge parameters
+ * (optional, uwbgo_batch::range_msgs).  The edge parameters are then built on the device with the
+ * arithmetic of Localization::addRangeEdge / create_range_edge (localization.cpp:316-319,331,338,350,
+ * 608-627), bit for bit -- all in FP64 after an exact widening of the float32 message fields:
+ *   k-th RANGE_ANCHOR edge:  measurement = distance[w][k]
+ *                            cov = distance_err[w][k]^2                        (separate vertex, :318,331)
+ *                                  + (v_max * dt_anchor[w][k] / 3)^2           (merged branch :350; only
+ *                                                                              when dt_anchor != NULL)
+ *   k-th RANGE_POSE edge:    measurement = 0,  cov = (v_max * dt_pose[w][k] / 3)^2     (:319,338)
+ *   information = 1 / cov.   x^2 is x * x (what pow(x, 2) compiles to), v_max * dt / 3 = (v_max * dt) / 3.
+ * Era / Erp = number of RANGE_ANCHOR / RANGE_POSE edges, each kind counted in insertion order.
+ * Half the host->device bytes of range_d + range_info on the windows addRangeEdge builds.  Batches in
+ * this form take the tile kernels (not the WINDOW path).
+ */
+typedef struct uwbgo_range_msgs {
+    const float  *distance;      /* [W][Era]  UwbRange::distance     (float32 on the wire)        */
+    const float  *distance_err;  /* [W][Era]  UwbRange::distance_err (float32 on the wire)        */
+    const double *dt_anchor;     /* [W][Era]  stamp - requester's last stamp, or NULL             */
+    const double *dt_pose;       /* [W][Erp]  stamp - the robot's last stamp; NULL iff Erp == 0   */
+    double        v_max;         /* robot/maximum_velocity (localization.cpp:76)                  */
+} uwbgo_range_msgs;
+
+#define UWBGO_SHARED_ANCHORS 1   /* uwbgo_batch::shared: `anchors` is [A][3], one constellation for */
+                                 /* every window of the batch (a fleet in one anchor field)         */
+
 /* Per-window numeric data, window-major.  Er/Ep/Es = number of RANGE_*, PRIOR, SE3 edges. */
 typedef struct uwbgo_batch {
     int64_t n_windows;            /* W */
@@ -94,6 +120,10 @@ typedef struct uwbgo_batch {
     const double  *prior_info;    /* [W][Ep][36] information, row-major                           */
     const double  *se3_Z;         /* [W][Es][12] EdgeSE3 measurement                              */
     const double  *se3_info;      /* [W][Es][36] information, row-major                           */
+    /* optional compact forms; zero / NULL = the arrays above are complete */
+    const uwbgo_range_msgs *range_msgs; /* replaces range_d and range_info (both must then be NULL)  */
+    int32_t shared;               /* bit mask of UWBGO_SHARED_*                                   */
+    int32_t reserved;
 } uwbgo_batch;
 
 /* Solver constants; uwbgo_config_default() fills g2o's defaults at the pinned commit. */
@@ -125,6 +155,18 @@ typedef struct uwbgo_result {
     int32_t *oplus_count;  /* [W][N];    may be NULL                      */
     double  *chi2;         /* [W][UWBGO_CHI2_STRIDE]                      */
     int32_t *status;       /* [W][UWBGO_STATUS_STRIDE]                    */
+    /* Optional extras: what the commented-out tail of Localization::solve() would read
+     * (localization.cpp:172-189).  NULL = not wanted.  Batches that ask for them take the tile kernels. */
+    double  *edge_chi2;    /* [W][E]  edge->chi2() of every edge after optimize(), insertion order: the */
+                           /*         errors of the LAST trial (accepted or not), i.e. the terms of    */
+                           /*         chi2[w][2] -- their sum in edge order is chi2[w][2], bit for bit  */
+                           /*         (the outlier pruning of localization.cpp:172-181 tests these)    */
+    double  *marginal;     /* [W][36] computeMarginals(spinv, last_vertex) (localization.cpp:185-189):  */
+                           /*         the 6x6 block of H^-1 that belongs to the NEWEST pose, row-major, */
+                           /*         H = the system of the last buildSystem() without damping          */
+    int32_t *marginal_ok;  /* [W]     1 = computed; 0 = H is not positive definite ("can't compute":    */
+                           /*         e.g. UWB-only windows, whose rotations are unobserved); the        */
+                           /*         marginal is then all NaN.  May be NULL                             */
 } uwbgo_result;
 
 typedef struct uwbgo_ctx uwbgo_ctx;

@@ -9,7 +9,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+SHARED_ANCHORS = 1
 
 EDGE_RANGE_ANCHOR = 0
 EDGE_RANGE_POSE = 1
@@ -37,12 +38,22 @@ class CTopology(C.Structure):
     ]
 
 
+_pf = C.POINTER(C.c_float)
+
+
+class CRangeMsgs(C.Structure):
+    _fields_ = [
+        ("distance", _pf), ("distance_err", _pf), ("dt_anchor", _pd), ("dt_pose", _pd), ("v_max", C.c_double),
+    ]
+
+
 class CBatch(C.Structure):
     _fields_ = [
         ("n_windows", C.c_int64),
         ("pose_t", _pd), ("pose_R", _pd), ("oplus_count", _pi), ("anchors", _pd),
         ("ant_offsets", _pd), ("range_d", _pd), ("range_info", _pd),
         ("prior_Z", _pd), ("prior_info", _pd), ("se3_Z", _pd), ("se3_info", _pd),
+        ("range_msgs", C.POINTER(CRangeMsgs)), ("shared", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -58,6 +69,7 @@ class CConfig(C.Structure):
 class CResult(C.Structure):
     _fields_ = [
         ("pose_t", _pd), ("pose_R", _pd), ("oplus_count", _pi), ("chi2", _pd), ("status", _pi),
+        ("edge_chi2", _pd), ("marginal", _pd), ("marginal_ok", _pi),
     ]
 
 

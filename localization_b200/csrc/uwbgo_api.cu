@@ -36,6 +36,11 @@ int fail_cuda(cudaError_t e, const char *what)
         if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
     } while (0)
 
+#ifndef UWBGO_GEN_CTA
+#define UWBGO_GEN_CTA 1 /* same switch as in uwbgo_kernels.cu: the 6x6 LM kernel is the CTA-per-tile one */
+#endif
+#define UWBGO_GEN_CTA_BUILD UWBGO_GEN_CTA
+
 /* grow-only device buffer */
 struct DevBuf {
     void *p = nullptr;
@@ -322,6 +327,14 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
         slot_edge[(size_t)at + edges[e].slot] = e;
     }
 
+    /* compact range form: per range slot, the index of its edge among the edges of its own kind */
+    std::vector<int32_t> range_sub((size_t)std::max(sl.Er, 1), 0);
+    int era = 0, erp = 0;
+    for (int e = 0; e < E; ++e) {
+        if (edges[e].kind == UWBGO_EDGE_RANGE_ANCHOR) range_sub[(size_t)edges[e].slot] = era++;
+        if (edges[e].kind == UWBGO_EDGE_RANGE_POSE) range_sub[(size_t)edges[e].slot] = 0x40000000 | erp++;
+    }
+
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o_edges = 0;
     size_t o_fedges = o_edges + al(sizeof(EdgeRec) * std::max(E, 1));
@@ -334,8 +347,10 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     size_t o_cbegin = o_parent + al(sizeof(int32_t) * N);
     size_t o_children = o_cbegin + al(sizeof(int32_t) * (N + 1));
     size_t o_slotedge = o_children + al(sizeof(int32_t) * std::max<size_t>(children.size(), 1));
-    size_t total = o_slotedge + al(sizeof(int32_t) * slot_edge.size());
+    size_t o_rsub = o_slotedge + al(sizeof(int32_t) * slot_edge.size());
+    size_t total = o_rsub + al(sizeof(int32_t) * range_sub.size());
     std::vector<char> host(total, 0);
+    memcpy(host.data() + o_rsub, range_sub.data(), sizeof(int32_t) * range_sub.size());
     memcpy(host.data() + o_slotedge, slot_edge.data(), sizeof(int32_t) * slot_edge.size());
     if (E) {
         memcpy(host.data() + o_edges, edges.data(), sizeof(EdgeRec) * E);
@@ -383,6 +398,9 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     g.child_begin = reinterpret_cast<const int32_t *>(d + o_cbegin);
     g.children = reinterpret_cast<const int32_t *>(d + o_children);
     g.slot_edge = reinterpret_cast<const int32_t *>(d + o_slotedge);
+    g.range_sub = reinterpret_cast<const int32_t *>(d + o_rsub);
+    g.Era = era;
+    g.Erp = erp;
     ent->gen = g;
     ent->fast = g;
     ent->fast.fast = chain_ok ? 2 : 1;
@@ -430,7 +448,14 @@ int check_batch(const TopoEntry &te, const uwbgo_batch *in)
     if (!in->pose_t) return fail(UWBGO_E_INVALID, "pose_t is NULL");
     if (g.A > 0 && !in->anchors) return fail(UWBGO_E_INVALID, "anchors is NULL");
     if (g.K > 0 && !in->ant_offsets) return fail(UWBGO_E_INVALID, "ant_offsets is NULL");
-    if (g.Er > 0 && (!in->range_d || !in->range_info)) return fail(UWBGO_E_INVALID, "range data NULL");
+    if (in->shared & ~UWBGO_SHARED_ANCHORS) return fail(UWBGO_E_INVALID, "unknown bit in batch.shared");
+    if (in->range_msgs) {
+        const uwbgo_range_msgs *m = in->range_msgs;
+        if (in->range_d || in->range_info) return fail(UWBGO_E_INVALID, "range_msgs replaces range_d / range_info: pass one form");
+        if (g.Era > 0 && (!m->distance || !m->distance_err)) return fail(UWBGO_E_INVALID, "range_msgs: distance / distance_err NULL");
+        if (g.Erp > 0 && !m->dt_pose) return fail(UWBGO_E_INVALID, "range_msgs: dt_pose NULL");
+    } else if (g.Er > 0 && (!in->range_d || !in->range_info))
+        return fail(UWBGO_E_INVALID, "range data NULL");
     if (g.Ep > 0 && (!in->prior_Z || !in->prior_info)) return fail(UWBGO_E_INVALID, "prior data NULL");
     if (g.Es > 0 && (!in->se3_Z || !in->se3_info)) return fail(UWBGO_E_INVALID, "se3 data NULL");
     return 0;
@@ -440,9 +465,10 @@ int check_batch(const TopoEntry &te, const uwbgo_batch *in)
 struct TileLayout {
     size_t bytes = 0;
     size_t off_T[2], off_R[2], off_cnt, off_anch, off_rd, off_ri, off_pZ, off_pI, off_sZ, off_sI, off_HB,
-        off_LR, off_chi2, off_status, off_echi;
+        off_LR, off_chi2, off_status, off_echi, off_sel, off_mg;
 };
-TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bool want_LR)
+TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bool want_LR, bool want_sel = false,
+                       bool want_marginal = false)
 {
     TileLayout L;
     const size_t tw = (size_t)n_tiles(W) * TILE; /* padded window count */
@@ -472,6 +498,8 @@ TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bo
     L.off_status = take(4, 4);
     /* per-edge chi2 terms: the general LM kernel, and the fused linearise stage of CHAIN windows */
     L.off_echi = ((!fast && want_LR) || (fast && !want_LR)) ? take((size_t)t.E * 2, 8) : 0;
+    L.off_sel = want_sel ? take(1, 4) : 0;
+    L.off_mg = (want_marginal && !fast) ? take(marginal_scratch_bytes(t, TILE) / (TILE * 8), 8) : 0;
     L.bytes = o;
     return L;
 }
@@ -490,7 +518,10 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     const bool fast = te.fast_ok && in->pose_R == nullptr;
     const DevTopo &tp = fast ? te.fast : te.gen;
     const bool want_cnt = (in->oplus_count != nullptr) || (out && out->oplus_count != nullptr);
-    TileLayout L = tile_layout(tp, fast, W, want_cnt, so == nullptr);
+    const bool want_echi = !so && out->edge_chi2 != nullptr, want_marg = !so && out->marginal != nullptr;
+    if ((want_echi || want_marg) && !fast && !UWBGO_GEN_CTA_BUILD)
+        return fail(UWBGO_E_INVALID, "edge_chi2 / marginal need the CTA-per-tile kernel (library built with -DUWBGO_GEN_CTA=0)");
+    TileLayout L = tile_layout(tp, fast, W, want_cnt, so == nullptr, want_echi && fast, want_marg);
     int rc = ln.tile.reserve(L.bytes);
     if (rc) return rc;
     char *base = static_cast<char *>(ln.tile.p);
@@ -517,6 +548,7 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     ws.chi2 = reinterpret_cast<double *>(base + L.off_chi2);
     ws.status = reinterpret_cast<int32_t *>(base + L.off_status);
     ws.echi = ((!fast && !so) || (fast && so)) ? reinterpret_cast<double *>(base + L.off_echi) : nullptr;
+    ws.stale_sel = (want_echi && fast) ? reinterpret_cast<int32_t *>(base + L.off_sel) : nullptr;
 
     XposeJobs pj{};
     pj.W = W;
@@ -543,15 +575,23 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
         else
             add(pj, nullptr, ws.cnt, tp.N, 4, 3);
     }
-    add(pj, in->anchors, const_cast<double *>(ws.anch), tp.A * 3, 8, 0);
-    add(pj, in->range_d, const_cast<double *>(ws.rd), tp.Er, 8, 0);
-    add(pj, in->range_info, const_cast<double *>(ws.ri), tp.Er, 8, 0);
+    add(pj, in->anchors, const_cast<double *>(ws.anch), tp.A * 3, 8, (in->shared & UWBGO_SHARED_ANCHORS) ? 4 : 0);
+    if (!in->range_msgs) {
+        add(pj, in->range_d, const_cast<double *>(ws.rd), tp.Er, 8, 0);
+        add(pj, in->range_info, const_cast<double *>(ws.ri), tp.Er, 8, 0);
+    }
     add(pj, in->prior_Z, const_cast<double *>(ws.pZ), tp.Ep * 12, 8, 0);
     add(pj, in->prior_info, const_cast<double *>(ws.pI), tp.Ep * 36, 8, 0);
     add(pj, in->se3_Z, const_cast<double *>(ws.sZ), tp.Es * 12, 8, 0);
     add(pj, in->se3_info, const_cast<double *>(ws.sI), tp.Es * 36, 8, 0);
     CU(launch_pack(pj, st));
     ctx->launches += 1;
+    if (in->range_msgs && tp.Er > 0) { /* create_range_edge on the device */
+        const uwbgo_range_msgs *m = in->range_msgs;
+        RangeMsgsDev md{m->distance, m->distance_err, m->dt_anchor, m->dt_pose, m->v_max};
+        CU(launch_pack_range_msgs(tp, md, W, const_cast<double *>(ws.rd), const_cast<double *>(ws.ri), st));
+        ctx->launches += 1;
+    }
 
     XposeJobs uj{};
     uj.W = W;
@@ -586,6 +626,15 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
         if (out->oplus_count) add(uj, ws.cnt, out->oplus_count, tp.N, 4, 0);
         if (out->chi2) add(uj, ws.chi2, out->chi2, 4, 8, 0);
         if (out->status) add(uj, ws.status, out->status, 4, 4, 0);
+        if (want_echi && tp.E > 0) {
+            CU(launch_edge_chi2_out(tp, ws, out->edge_chi2, st));
+            ctx->launches += 1;
+        }
+        if (want_marg) {
+            CU(launch_marginal(tp, ws, fast ? nullptr : reinterpret_cast<double *>(base + L.off_mg), out->marginal,
+                               out->marginal_ok, st));
+            ctx->launches += 1;
+        }
     }
     if (uj.n) {
         CU(launch_unpack(uj, st));
@@ -621,8 +670,11 @@ int upload_ant(uwbgo_ctx *ctx, const DevTopo &g, const uwbgo_batch *in, cudaStre
 }
 
 /* WINDOW path eligibility: small batch, window state fits the shared memory of one SM */
-bool window_path_ok(const uwbgo_ctx *ctx, const TopoEntry &te, int64_t W)
+bool window_path_ok(const uwbgo_ctx *ctx, const TopoEntry &te, int64_t W, const uwbgo_batch *in = nullptr,
+                    const uwbgo_result *out = nullptr)
 {
+    if (in && (in->range_msgs || in->shared)) return false;                    /* compact inputs: tile kernels */
+    if (out && (out->edge_chi2 || out->marginal)) return false;                /* extras: tile kernels          */
     return W > 0 && W <= ctx->win_max && window_path_smem_bytes(te.gen, 1) <= WIN_SMEM_LIMIT;
 }
 
@@ -885,7 +937,7 @@ int uwbgo_solve_batch_device(uwbgo_ctx *ctx, const uwbgo_topology *topo, const u
     if ((rc = user_stream_begin(ctx, st))) return rc;
     const double *d_ant = nullptr;
     if ((rc = upload_ant(ctx, te->gen, in, st, &d_ant))) return rc;
-    if (window_path_ok(ctx, *te, in->n_windows)) /* no workspace: nothing to order against other calls */
+    if (window_path_ok(ctx, *te, in->n_windows, in, out)) /* no workspace: nothing to order against other calls */
         return run_window(ctx, *te, dc, in, d_ant, out, st);
     if ((rc = run_device(ctx, ctx->lane[0], *te, dc, in, d_ant, out, nullptr, st))) return rc;
     return user_stream_end(ctx, st);
@@ -938,7 +990,8 @@ namespace {
 struct StageLayout {
     size_t bytes = 0;
     size_t in_pose_t, in_pose_R, in_cnt, in_anch, in_rd, in_ri, in_pZ, in_pI, in_sZ, in_sI;
-    size_t out_pose_t, out_pose_R, out_cnt, out_chi2, out_status;
+    size_t in_md, in_me, in_mta, in_mtp; /* compact range form */
+    size_t out_pose_t, out_pose_R, out_cnt, out_chi2, out_status, out_echi, out_marg, out_mok;
     size_t out_Hd, out_Ho, out_b;
 };
 }  // namespace
@@ -957,7 +1010,7 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
     const DevTopo &g = te->gen;
     const int64_t W = in->n_windows;
     if (W == 0) return 0;
-    if (!linearize && window_path_ok(ctx, *te, W)) return host_window_path(ctx, *te, dc, in, out);
+    if (!linearize && window_path_ok(ctx, *te, W, in, out)) return host_window_path(ctx, *te, dc, in, out);
     if (ctx->ws_pending) { /* a device-API call may still own lane 0's workspace */
         CU(cudaEventSynchronize(ctx->ws_free));
         ctx->ws_pending = false;
@@ -966,6 +1019,8 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
     if ((rc = upload_ant(ctx, g, in, ctx->lane[0].st, &d_ant))) return rc;
 
     const size_t N = (size_t)g.N;
+    const uwbgo_range_msgs *msgs = in->range_msgs;
+    const bool shared_anch = (in->shared & UWBGO_SHARED_ANCHORS) != 0;
     /* the LM kernel's duration is set by per-window latency, not by the chunk size, so a batch
      * that fits n_lanes chunks is split evenly and all its chunks run concurrently */
     int64_t chunk = std::min<int64_t>(ctx->chunk, (W + 31) / 32 * 32);
@@ -986,9 +1041,13 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         S.in_pose_t = take(true, N * 3 * 8);
         S.in_pose_R = take(in->pose_R != nullptr, N * 9 * 8);
         S.in_cnt = take(in->oplus_count != nullptr, N * 4);
-        S.in_anch = take(g.A > 0, (size_t)g.A * 3 * 8);
-        S.in_rd = take(g.Er > 0, (size_t)g.Er * 8);
-        S.in_ri = take(g.Er > 0, (size_t)g.Er * 8);
+        S.in_anch = take(g.A > 0, (size_t)g.A * 3 * 8); /* (shared anchors use the first A*3 doubles of it) */
+        S.in_rd = take(g.Er > 0 && !msgs, (size_t)g.Er * 8);
+        S.in_ri = take(g.Er > 0 && !msgs, (size_t)g.Er * 8);
+        S.in_md = take(msgs && g.Era > 0, (size_t)g.Era * 4);
+        S.in_me = take(msgs && g.Era > 0, (size_t)g.Era * 4);
+        S.in_mta = take(msgs && g.Era > 0 && msgs->dt_anchor, (size_t)g.Era * 8);
+        S.in_mtp = take(msgs && g.Erp > 0, (size_t)g.Erp * 8);
         S.in_pZ = take(g.Ep > 0, (size_t)g.Ep * 12 * 8);
         S.in_pI = take(g.Ep > 0, (size_t)g.Ep * 36 * 8);
         S.in_sZ = take(g.Es > 0, (size_t)g.Es * 12 * 8);
@@ -1004,6 +1063,9 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
             S.out_cnt = take(out->oplus_count != nullptr, N * 4);
             S.out_chi2 = take(out->chi2 != nullptr, 4 * 8);
             S.out_status = take(out->status != nullptr, 4 * 4);
+            S.out_echi = take(out->edge_chi2 != nullptr && g.E > 0, (size_t)g.E * 8);
+            S.out_marg = take(out->marginal != nullptr, 36 * 8);
+            S.out_mok = take(out->marginal != nullptr && out->marginal_ok != nullptr, 4);
         }
         S.bytes = o;
     }
@@ -1011,6 +1073,16 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
     for (int k = 0; k < n_lanes; ++k)
         if ((rc = ctx->lane[k].stage.reserve(S.bytes))) return rc;
 
+    /* inside the chunk loop an error must not return: earlier chunks may still have copies in flight against the
+     * caller's buffers.  Every error path falls through to the per-lane synchronisation below */
+#define CUL(call)                                        \
+    {                                                    \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) {                        \
+            first_err = fail_cuda(e__, #call);           \
+            break;                                       \
+        }                                                \
+    }
     int first_err = 0;
     int64_t c = 0;
     for (int64_t w0 = 0; w0 < W; w0 += chunk, ++c) {
@@ -1028,16 +1100,33 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
             return cudaMemcpyAsync(static_cast<char *>(dst) + (size_t)w0 * per_window, sb + off,
                                    (size_t)wc * per_window, cudaMemcpyDeviceToHost, st);
         };
-        CU(h2d(in->pose_t, S.in_pose_t, N * 3 * 8));
-        CU(h2d(in->pose_R, S.in_pose_R, N * 9 * 8));
-        CU(h2d(in->oplus_count, S.in_cnt, N * 4));
-        CU(h2d(g.A > 0 ? in->anchors : nullptr, S.in_anch, (size_t)g.A * 3 * 8));
-        CU(h2d(g.Er > 0 ? in->range_d : nullptr, S.in_rd, (size_t)g.Er * 8));
-        CU(h2d(g.Er > 0 ? in->range_info : nullptr, S.in_ri, (size_t)g.Er * 8));
-        CU(h2d(g.Ep > 0 ? in->prior_Z : nullptr, S.in_pZ, (size_t)g.Ep * 12 * 8));
-        CU(h2d(g.Ep > 0 ? in->prior_info : nullptr, S.in_pI, (size_t)g.Ep * 36 * 8));
-        CU(h2d(g.Es > 0 ? in->se3_Z : nullptr, S.in_sZ, (size_t)g.Es * 12 * 8));
-        CU(h2d(g.Es > 0 ? in->se3_info : nullptr, S.in_sI, (size_t)g.Es * 36 * 8));
+        CUL(h2d(in->pose_t, S.in_pose_t, N * 3 * 8));
+        CUL(h2d(in->pose_R, S.in_pose_R, N * 9 * 8));
+        CUL(h2d(in->oplus_count, S.in_cnt, N * 4));
+        if (g.A > 0 && shared_anch) { /* one constellation: A*3 doubles per chunk instead of per window */
+            CUL(cudaMemcpyAsync(sb + S.in_anch, in->anchors, (size_t)g.A * 3 * 8, cudaMemcpyHostToDevice, st));
+        } else {
+            CUL(h2d(g.A > 0 ? in->anchors : nullptr, S.in_anch, (size_t)g.A * 3 * 8));
+        }
+        uwbgo_range_msgs dm{};
+        if (msgs) {
+            CUL(h2d(g.Era > 0 ? msgs->distance : nullptr, S.in_md, (size_t)g.Era * 4));
+            CUL(h2d(g.Era > 0 ? msgs->distance_err : nullptr, S.in_me, (size_t)g.Era * 4));
+            CUL(h2d(g.Era > 0 ? msgs->dt_anchor : nullptr, S.in_mta, (size_t)g.Era * 8));
+            CUL(h2d(g.Erp > 0 ? msgs->dt_pose : nullptr, S.in_mtp, (size_t)g.Erp * 8));
+            dm.distance = reinterpret_cast<float *>(sb + S.in_md);
+            dm.distance_err = reinterpret_cast<float *>(sb + S.in_me);
+            dm.dt_anchor = msgs->dt_anchor ? reinterpret_cast<double *>(sb + S.in_mta) : nullptr;
+            dm.dt_pose = reinterpret_cast<double *>(sb + S.in_mtp);
+            dm.v_max = msgs->v_max;
+        } else {
+            CUL(h2d(g.Er > 0 ? in->range_d : nullptr, S.in_rd, (size_t)g.Er * 8));
+            CUL(h2d(g.Er > 0 ? in->range_info : nullptr, S.in_ri, (size_t)g.Er * 8));
+        }
+        CUL(h2d(g.Ep > 0 ? in->prior_Z : nullptr, S.in_pZ, (size_t)g.Ep * 12 * 8));
+        CUL(h2d(g.Ep > 0 ? in->prior_info : nullptr, S.in_pI, (size_t)g.Ep * 36 * 8));
+        CUL(h2d(g.Es > 0 ? in->se3_Z : nullptr, S.in_sZ, (size_t)g.Es * 12 * 8));
+        CUL(h2d(g.Es > 0 ? in->se3_info : nullptr, S.in_sI, (size_t)g.Es * 36 * 8));
         uwbgo_batch db{};
         db.n_windows = wc;
         db.pose_t = reinterpret_cast<double *>(sb + S.in_pose_t);
@@ -1045,8 +1134,10 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         db.oplus_count = in->oplus_count ? reinterpret_cast<int32_t *>(sb + S.in_cnt) : nullptr;
         db.anchors = reinterpret_cast<double *>(sb + S.in_anch);
         db.ant_offsets = in->ant_offsets;
-        db.range_d = reinterpret_cast<double *>(sb + S.in_rd);
-        db.range_info = reinterpret_cast<double *>(sb + S.in_ri);
+        db.range_d = msgs ? nullptr : reinterpret_cast<double *>(sb + S.in_rd);
+        db.range_info = msgs ? nullptr : reinterpret_cast<double *>(sb + S.in_ri);
+        db.range_msgs = msgs ? &dm : nullptr;
+        db.shared = in->shared;
         db.prior_Z = reinterpret_cast<double *>(sb + S.in_pZ);
         db.prior_info = reinterpret_cast<double *>(sb + S.in_pI);
         db.se3_Z = reinterpret_cast<double *>(sb + S.in_sZ);
@@ -1058,10 +1149,10 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
                         chi2 ? reinterpret_cast<double *>(sb + S.out_chi2) : nullptr};
             rc = run_device(ctx, ln, *te, dc, &db, d_ant, nullptr, &so, st);
             if (rc) { first_err = rc; break; }
-            CU(d2h(H_diag, S.out_Hd, N * 36 * 8));
-            if (N > 1) CU(d2h(H_off, S.out_Ho, (N - 1) * 36 * 8));
-            CU(d2h(b, S.out_b, N * 6 * 8));
-            CU(d2h(chi2, S.out_chi2, 2 * 8));
+            CUL(d2h(H_diag, S.out_Hd, N * 36 * 8));
+            if (N > 1) CUL(d2h(H_off, S.out_Ho, (N - 1) * 36 * 8));
+            CUL(d2h(b, S.out_b, N * 6 * 8));
+            CUL(d2h(chi2, S.out_chi2, 2 * 8));
         } else {
             uwbgo_result dr{};
             dr.pose_t = reinterpret_cast<double *>(sb + S.out_pose_t);
@@ -1069,19 +1160,26 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
             dr.oplus_count = out->oplus_count ? reinterpret_cast<int32_t *>(sb + S.out_cnt) : nullptr;
             dr.chi2 = out->chi2 ? reinterpret_cast<double *>(sb + S.out_chi2) : nullptr;
             dr.status = out->status ? reinterpret_cast<int32_t *>(sb + S.out_status) : nullptr;
+            dr.edge_chi2 = (out->edge_chi2 && g.E > 0) ? reinterpret_cast<double *>(sb + S.out_echi) : nullptr;
+            dr.marginal = out->marginal ? reinterpret_cast<double *>(sb + S.out_marg) : nullptr;
+            dr.marginal_ok = (out->marginal && out->marginal_ok) ? reinterpret_cast<int32_t *>(sb + S.out_mok) : nullptr;
             rc = run_device(ctx, ln, *te, dc, &db, d_ant, &dr, nullptr, st);
             if (rc) { first_err = rc; break; }
-            CU(d2h(out->pose_t, S.out_pose_t, N * 3 * 8));
-            CU(d2h(out->pose_R, S.out_pose_R, N * 9 * 8));
-            CU(d2h(out->oplus_count, S.out_cnt, N * 4));
-            CU(d2h(out->chi2, S.out_chi2, 4 * 8));
-            CU(d2h(out->status, S.out_status, 4 * 4));
+            CUL(d2h(out->pose_t, S.out_pose_t, N * 3 * 8));
+            CUL(d2h(out->pose_R, S.out_pose_R, N * 9 * 8));
+            CUL(d2h(out->oplus_count, S.out_cnt, N * 4));
+            CUL(d2h(out->chi2, S.out_chi2, 4 * 8));
+            CUL(d2h(out->status, S.out_status, 4 * 4));
+            CUL(d2h(g.E > 0 ? out->edge_chi2 : nullptr, S.out_echi, (size_t)g.E * 8));
+            CUL(d2h(out->marginal, S.out_marg, 36 * 8));
+            CUL(d2h(out->marginal ? out->marginal_ok : nullptr, S.out_mok, 4));
         }
     }
     for (int k = 0; k < n_lanes; ++k) {
         cudaError_t e = cudaStreamSynchronize(ctx->lane[k].st);
         if (e != cudaSuccess && !first_err) first_err = fail_cuda(e, "cudaStreamSynchronize");
     }
+#undef CUL
     return first_err;
 }
 

@@ -258,7 +258,7 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
     }
     /* LM state, chain warp only */
     double lambda = 0.0, ni = 2.0, stale = 0.0, plainCur = 0.0, currentChi = 0.0, rho = 0.0;
-    int iterations = 0, trials_total = 0, flags = 0, qlast = 0, q = 0, it = 0, cur = 0;
+    int iterations = 0, trials_total = 0, flags = 0, qlast = 0, q = 0, it = 0, cur = 0, last_rej = 0;
     bool done = !valid || cfg.max_iterations <= 0;
     double maxdiag = 0.0;
     if (warp == 1) {
@@ -488,10 +488,12 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
                     ni = 2.0;
                     currentChi = tempChi;
                     plainCur = tplain;
+                    last_rej = 0;
                     cur ^= 1; /* the trial buffer becomes the current estimate of this window */
                 } else {
                     lambda = lambda * ni;
                     ni = ni * 2.0;
+                    last_rej = 1;
                 }
                 ++q;
                 ++trials_total;
@@ -527,9 +529,7 @@ lm_chain_tma_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ 
         ROW(status_out, 1) = trials_total;
         ROW(status_out, 2) = flags;
         ROW(status_out, 3) = qlast;
-        if (cur) {
-            for (int r = 0; r < N * 3; ++r) ROW(E.p.T0, r) = ROW(E.p.T1, r);
-        }
+        finish_estimates(ws, tile, lane, E.p.T0, E.p.T1, N * 3, cur, last_rej);
         if (E.p.cnt) {
             for (int i = 0; i < N; ++i) {
                 long long cc = (long long)E.p.cnt[(size_t)i * TILE] + (long long)iterations * __ldg(tp.num_calls + i) + trials_total;

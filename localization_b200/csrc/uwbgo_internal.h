@@ -83,6 +83,16 @@ struct DevTopo {
     const int32_t *num_calls;   /* [N] numeric oplus calls per linearisation on pose i       */
     const int32_t *slot_edge;   /* [Er + Ep + Es] edge index of every data slot: range slots, */
                                 /* then prior slots, then se3 slots                          */
+    const int32_t *range_sub;   /* [Er] per range slot: index of the edge among the edges of  */
+                                /* its own kind; bit 30 set = RANGE_POSE (compact range form) */
+    int32_t Era, Erp;           /* number of RANGE_ANCHOR / RANGE_POSE edges                  */
+};
+
+/* uwbgo_range_msgs with device pointers (window-major, as the caller passed them) */
+struct RangeMsgsDev {
+    const float *distance, *distance_err;
+    const double *dt_anchor, *dt_pose;
+    double v_max;
 };
 
 struct DevCfg {
@@ -109,6 +119,8 @@ struct DevWs {
     double *chi2;       /* [tile][4][32] (solve) or [tile][2][32]     */
     int32_t *status;    /* [tile][4][32]                              */
     double *echi;       /* [tile][E*2][32] per-edge chi2 | rho0 (general CTA kernel) */
+    int32_t *stale_sel; /* [tile][32] or NULL.  Non-NULL = the caller wants uwbgo_result::edge_chi2: the      */
+                        /* translation-only kernels then leave the last trial's estimates in buffer stale_sel */
 };
 
 /* WINDOW path (uwbgo_window.cu, one CTA per window): the window-major arrays of the public ABI,
@@ -132,7 +144,8 @@ struct XposeJob {
     int32_t C;       /* columns per window                                  */
     int32_t elem;    /* element size: 8 (double) or 4 (int32)               */
     int32_t mode;    /* 0 transpose; 1 identity rotations (tile layout dst); 2 identity rotations */
-                     /* (window-major dst); 3 zero fill (tile layout dst)                       */
+                     /* (window-major dst); 3 zero fill (tile layout dst); 4 broadcast of one    */
+                     /* shared row src[C] to every window (tile layout dst)                      */
     int32_t aux;
 };
 constexpr int MAX_XPOSE_JOBS = 12;
@@ -145,6 +158,15 @@ struct XposeJobs {
 
 /* launchers (uwbgo_kernels.cu); all asynchronous on `st`, return cudaGetLastError() */
 cudaError_t launch_pack(const XposeJobs &jobs, cudaStream_t st);
+/* compact range form -> measurement / information rows of the tile layout (create_range_edge on the device) */
+cudaError_t launch_pack_range_msgs(const DevTopo &topo, const RangeMsgsDev &m, int64_t W, double *rd, double *ri,
+                                   cudaStream_t st);
+/* uwbgo_result::edge_chi2 [W][E] after launch_solve (window-major device array) */
+cudaError_t launch_edge_chi2_out(const DevTopo &topo, const DevWs &ws, double *edge_chi2, cudaStream_t st);
+/* uwbgo_result::marginal [W][36] / marginal_ok [W] after launch_solve; scratch: marginal_scratch_bytes() */
+size_t marginal_scratch_bytes(const DevTopo &topo, int64_t W);
+cudaError_t launch_marginal(const DevTopo &topo, const DevWs &ws, double *scratch, double *marginal,
+                            int32_t *marginal_ok, cudaStream_t st);
 cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st);
 cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st);
 cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,

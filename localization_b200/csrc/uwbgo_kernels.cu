@@ -102,8 +102,9 @@ struct Path<0> {
  * per-window arithmetic and its order are unchanged. */
 template <int MODE>
 UWBGO_DI void lm_window(const Path<MODE> &P, const DevCfg &cfg, double *chi2_out,
-                        int32_t *status_out, int &cur_out)
+                        int32_t *status_out, int &cur_out, int &last_rejected)
 {
+    last_rejected = 0;
     constexpr bool FAST = MODE != 0;
     double lambda = 0.0, ni = 2.0, stale, plainCur, currentChi, rho = 0.0;
     int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0, q = 0, it = 0;
@@ -145,9 +146,11 @@ UWBGO_DI void lm_window(const Path<MODE> &P, const DevCfg &cfg, double *chi2_out
             currentChi = tempChi;
             plainCur = tplain;
             cur ^= 1;
+            last_rejected = 0;
         } else {
             lambda = lambda * ni;
             ni = ni * 2.0;
+            last_rejected = 1;
         }
         ++q;
         ++trials_total;
@@ -199,6 +202,25 @@ UWBGO_DI void fast_env_init(FastEnv &E, const DevTopo &tp, const DevCfg &cfg, co
     }
 }
 
+/* The result always leaves in buffer 0.  Normally that is a copy; when the caller wants the per-edge chi2 of
+ * the LAST trial (uwbgo_result::edge_chi2) the buffers are swapped instead, so that a rejected last trial's
+ * estimates survive in buffer 1, and stale_sel says which buffer the last trial's estimates are in. */
+UWBGO_DI void finish_estimates(const DevWs &ws, int64_t tile, int lane, double *T0, double *T1, int rows, int cur,
+                               int last_rejected)
+{
+    if (ws.stale_sel) {
+        if (cur)
+            for (int r = 0; r < rows; ++r) {
+                const double a = ROW(T0, r), b = ROW(T1, r);
+                ROW(T0, r) = b;
+                ROW(T1, r) = a;
+            }
+        ws.stale_sel[tile * TILE + lane] = last_rejected;
+    } else if (cur) {
+        for (int r = 0; r < rows; ++r) ROW(T0, r) = ROW(T1, r);
+    }
+}
+
 template <int MODE>
 UWBGO_DI void lm_fast_body(const DevTopo &tp, const DevCfg &cfg, const DevWs &ws, int anchors_in_smem,
                            double *smem)
@@ -209,11 +231,9 @@ UWBGO_DI void lm_fast_body(const DevTopo &tp, const DevCfg &cfg, const DevWs &ws
     fast_env_init(P.E, tp, cfg, ws, w, smem, anchors_in_smem);
     const int64_t tile = w / TILE;
     const int lane = (int)(w % TILE);
-    int cur;
-    lm_window<MODE>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
-    if (cur) { /* result always leaves in buffer 0 */
-        for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T0, r) = ROW(P.E.p.T1, r);
-    }
+    int cur, last_rej;
+    lm_window<MODE>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur, last_rej);
+    finish_estimates(ws, tile, lane, P.E.p.T0, P.E.p.T1, tp.N * 3, cur, last_rej);
     if (P.E.p.cnt) { /* VertexSE3::_numOplusCalls: 12 per range edge end per linearisation, 1 per trial */
         const int it = ROW(ws.status + tile * 4 * TILE + lane, 0), tr = ROW(ws.status + tile * 4 * TILE + lane, 1);
         for (int i = 0; i < tp.N; ++i) {
@@ -297,7 +317,7 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
 
     /* LM state, chain warp only */
     double lambda = 0.0, ni = 2.0, stale = 0.0, plainCur = 0.0, currentChi = 0.0, rho = 0.0;
-    int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0, q = 0, it = 0;
+    int iterations = 0, trials_total = 0, flags = 0, qlast = 0, cur = 0, q = 0, it = 0, last_rej = 0;
     bool done = !valid || cfg.max_iterations <= 0;
     if (warp == 1) {
         fast_chi_pass(E, E.p.T0, plainCur, currentChi);
@@ -571,10 +591,12 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
                     ni = 2.0;
                     currentChi = tempChi;
                     plainCur = tplain;
+                    last_rej = 0;
                     cur ^= 1;
                 } else {
                     lambda = lambda * ni;
                     ni = ni * 2.0;
+                    last_rej = 1;
                 }
                 ++q;
                 ++trials_total;
@@ -608,9 +630,7 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
         ROW(status_out, 1) = trials_total;
         ROW(status_out, 2) = flags;
         ROW(status_out, 3) = qlast;
-        if (cur) {
-            for (int r = 0; r < N * 3; ++r) ROW(E.p.T0, r) = ROW(E.p.T1, r);
-        }
+        finish_estimates(ws, w / TILE, lane, E.p.T0, E.p.T1, N * 3, cur, last_rej);
         if (E.p.cnt) {
             for (int i = 0; i < N; ++i) {
                 long long cc = (long long)E.p.cnt[(size_t)i * TILE] + (long long)iterations * __ldg(tp.num_calls + i) + trials_total;
@@ -652,8 +672,8 @@ lm_general_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ De
     gen_env_init(P.E, tp, cfg, ws, w, s_ant);
     const int64_t tile = w / TILE;
     const int lane = (int)(w % TILE);
-    int cur;
-    lm_window<0>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur);
+    int cur, last_rej; /* (edge_chi2 / marginals of 6x6 windows come from the CTA kernel's scratch, not from here) */
+    lm_window<0>(P, cfg, ws.chi2 + tile * 4 * TILE + lane, ws.status + tile * 4 * TILE + lane, cur, last_rej);
     if (cur) {
         for (int r = 0; r < tp.N * 3; ++r) ROW(P.E.p.T0, r) = ROW(P.E.p.T1, r);
         for (int r = 0; r < tp.N * 9; ++r) ROW(P.E.p.Rm0, r) = ROW(P.E.p.Rm1, r);
@@ -821,6 +841,16 @@ __global__ void __launch_bounds__(256) xpose_kernel(XposeJobs jobs)
         }
         return;
     }
+    if (j.mode == 4) { /* one shared row (UWBGO_SHARED_ANCHORS) to every window of a tile-layout array */
+        const int64_t tile = blockIdx.x;
+        const int c0 = blockIdx.y * 32;
+        for (int y = threadIdx.y; y < 32; y += 8) {
+            int c = c0 + y;
+            if (c >= j.C) continue;
+            static_cast<double *>(j.dst)[(tile * j.C + c) * TILE + threadIdx.x] = static_cast<const double *>(j.src)[c];
+        }
+        return;
+    }
     if (j.elem == 8)
         xpose_body<double, PACK>(j, jobs.W, sm);
     else
@@ -844,6 +874,248 @@ cudaError_t launch_pack(const XposeJobs &jobs, cudaStream_t st) { return launch_
 cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st) { return launch_xpose(jobs, false, st); }
 
 static unsigned window_blocks(int64_t W) { return (unsigned)((W + CTA_THREADS - 1) / CTA_THREADS); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* compact range form: the edge parameters of Localization::addRangeEdge / create_range_edge     */
+/* (reference localization.cpp:316-319,331,338,350,608-627) built on the device, straight into   */
+/* the measurement / information rows of the tile layout.  FP64 after an exact widening of the   */
+/* float32 message fields; x^2 = x * x; (v_max * dt) / 3; one IEEE division: the bits of the host.*/
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256)
+pack_range_msgs_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ RangeMsgsDev m, int64_t W,
+                       double *__restrict__ rd, double *__restrict__ ri)
+{
+    const int64_t tile = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int64_t w = tile * TILE + lane;
+    for (int s = blockIdx.y * 8 + threadIdx.y; s < tp.Er; s += 8 * gridDim.y) {
+        const int sub = __ldg(tp.range_sub + s);
+        const int k = sub & 0x3fffffff;
+        double d = 0.0, info = 0.0; /* pad lanes of the last tile: zero rows, as the transposing pack leaves them */
+        if (w < W) {
+            if (sub & 0x40000000) {
+                const double mv = m.v_max * m.dt_pose[w * tp.Erp + k] / 3.0;
+                info = 1.0 / (mv * mv);
+            } else {
+                const double derr = (double)m.distance_err[w * tp.Era + k];
+                double cov = derr * derr;
+                if (m.dt_anchor) {
+                    const double mv = m.v_max * m.dt_anchor[w * tp.Era + k] / 3.0;
+                    cov = cov + mv * mv;
+                }
+                d = (double)m.distance[w * tp.Era + k];
+                info = 1.0 / cov;
+            }
+        }
+        rd[(tile * tp.Er + s) * TILE + lane] = d;
+        ri[(tile * tp.Er + s) * TILE + lane] = info;
+    }
+}
+
+cudaError_t launch_pack_range_msgs(const DevTopo &topo, const RangeMsgsDev &m, int64_t W, double *rd, double *ri,
+                                   cudaStream_t st)
+{
+    if (W <= 0 || topo.Er <= 0) return cudaSuccess;
+    dim3 grid((unsigned)n_tiles(W), (unsigned)std::min(4, (topo.Er + 7) / 8));
+    pack_range_msgs_kernel<<<grid, dim3(32, 8), 0, st>>>(topo, m, W, rd, ri);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* uwbgo_result::edge_chi2: edge->chi2() of every edge as g2o holds it after optimize() -- the    */
+/* errors of the LAST trial (reference localization.cpp:172-181 would test these).                */
+/*   6x6 windows: the CTA kernel's per-edge scratch still holds the last trial's terms.           */
+/*   translation-only windows: recomputed from the estimate buffer the last trial wrote           */
+/*   (DevWs::stale_sel), with the expression of fast_chi_pass / chain_solve_chi.                  */
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(CTA_THREADS)
+edge_chi2_out_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevWs ws, double *__restrict__ out)
+{
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (w >= ws.W) return;
+    const int64_t tile = w / TILE;
+    const int lane = (int)(w % TILE);
+    double *o = out + w * tp.E;
+    if (!tp.fast) {
+        const double *echi = ws.echi + (tile * tp.E * 2) * TILE + lane;
+        for (int e = 0; e < tp.E; ++e) o[e] = ROW(echi, 2 * e);
+        return;
+    }
+    const int sel = ws.stale_sel[tile * TILE + lane];
+    const double *T = ws.T[sel] + (tile * (size_t)tp.N * 3) * TILE + lane;
+    const double *anch = ws.anch + (tile * (size_t)tp.A * 3) * TILE + lane;
+    const double *rd = ws.rd + (tile * (size_t)tp.Er) * TILE + lane, *ri = ws.ri + (tile * (size_t)tp.Er) * TILE + lane;
+    for (int e = 0; e < tp.E; ++e) {
+        const EdgeRec er = load_edge(tp.edges + e);
+        const double *ta = T + (size_t)er.a * 3 * TILE;
+        double qx, qy, qz;
+        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+            qx = ROW(anch, er.b * 3); qy = ROW(anch, er.b * 3 + 1); qz = ROW(anch, er.b * 3 + 2);
+        } else {
+            const double *tb = T + (size_t)er.b * 3 * TILE;
+            qx = ROW(tb, 0); qy = ROW(tb, 1); qz = ROW(tb, 2);
+        }
+        const double n = dist3(ROW(ta, 0), ROW(ta, 1), ROW(ta, 2), qx, qy, qz);
+        const double err = ROW(rd, er.slot) - n;
+        const double Oe = ROW(ri, er.slot) * err;
+        o[e] = err * Oe;
+    }
+}
+
+cudaError_t launch_edge_chi2_out(const DevTopo &topo, const DevWs &ws, double *edge_chi2, cudaStream_t st)
+{
+    if (ws.W <= 0 || topo.E <= 0) return cudaSuccess;
+    edge_chi2_out_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, ws, edge_chi2);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* uwbgo_result::marginal: computeMarginals(spinv, newest vertex) (reference localization.cpp:    */
+/* 185-189): the diagonal block of H^-1 of the newest pose, H = the H records of the last         */
+/* buildSystem (no damping).  Elimination newest pose first as in the LM trials, lambda = 0:      */
+/*   S_i = H_ii - sum over children G_c G_c^T = L_i L_i^T,  G_i = H_{p(i),i} L_i^-T,              */
+/*   M_i = L_i^-T G_i^T; then along the path root -> newest:                                      */
+/*   Sigma_root = S_root^-1,  Sigma_i = S_i^-1 + M_i Sigma_p(i) M_i^T.                            */
+/* One thread per window; scratch [tile][N * 108][32] (G | M | S^-1 per pose).  Run once per      */
+/* solve, after the LM kernel: plain loops, nothing here is on the hot path.                      */
+/* ------------------------------------------------------------------------------------------ */
+constexpr int MG_ROWS = 108;
+size_t marginal_scratch_bytes(const DevTopo &topo, int64_t W)
+{
+    return topo.fast ? 0 : sizeof(double) * (size_t)n_tiles(W) * TILE * (size_t)topo.N * MG_ROWS;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS)
+marginal_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevWs ws, double *__restrict__ scratch,
+                double *__restrict__ out, int32_t *__restrict__ okv)
+{
+    const int64_t w = (int64_t)blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (w >= ws.W) return;
+    const int64_t tile = w / TILE;
+    const int lane = (int)(w % TILE);
+    const int N = tp.N;
+    double *o = out + w * 36;
+    const int iterations = ROW(ws.status + tile * 4 * TILE + lane, 0);
+    bool good = !tp.fast && iterations > 0; /* translation-only windows: the rotations are unobserved, H is singular */
+    if (good) {
+        const double *HB = ws.HB + (tile * (size_t)N * HR_GEN) * TILE + lane;
+        double *mg = scratch + (tile * (size_t)N * MG_ROWS) * TILE + lane;
+        for (int i = N - 1; i >= 0 && good; --i) {
+            double S[36], L[36], Li[36];
+            const double *h = HB + (size_t)i * HR_GEN * TILE;
+            double *G = mg + (size_t)i * MG_ROWS * TILE, *M = G + 36 * TILE, *Sinv = G + 72 * TILE;
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c <= r; ++c) S[6 * r + c] = ROW(h, up_idx(6, c, r));
+            for (int ci = __ldg(tp.child_begin + i); ci < __ldg(tp.child_begin + i + 1); ++ci) { /* children, descending */
+                const double *Gc = mg + (size_t)__ldg(tp.children + ci) * MG_ROWS * TILE;
+                for (int r = 0; r < 6; ++r)
+                    for (int c = 0; c <= r; ++c) {
+                        double s = S[6 * r + c];
+                        for (int k = 0; k < 6; ++k) s = fma(-ROW(Gc, 6 * r + k), ROW(Gc, 6 * c + k), s);
+                        S[6 * r + c] = s;
+                    }
+            }
+            for (int k = 0; k < 36; ++k) L[k] = 0.0;
+            for (int j = 0; j < 6; ++j) {
+                double s = S[6 * j + j];
+                for (int k = 0; k < j; ++k) s = fma(-L[6 * j + k], L[6 * j + k], s);
+                if (!(s > 0.0)) {
+                    good = false;
+                    break;
+                }
+                const double inv = 1.0 / sqrt(s);
+                L[6 * j + j] = inv; /* the diagonal slot stores 1/L_jj */
+                for (int r = j + 1; r < 6; ++r) {
+                    double t = S[6 * r + j];
+                    for (int k = 0; k < j; ++k) t = fma(-L[6 * r + k], L[6 * j + k], t);
+                    L[6 * r + j] = t * inv;
+                }
+            }
+            if (!good) break;
+            for (int k = 0; k < 36; ++k) Li[k] = 0.0;
+            for (int j = 0; j < 6; ++j) { /* Li = L^-1 (lower), then S^-1 = Li^T Li */
+                Li[6 * j + j] = L[6 * j + j];
+                for (int r = j + 1; r < 6; ++r) {
+                    double s = 0.0;
+                    for (int k = j; k < r; ++k) s = fma(-L[6 * r + k], Li[6 * k + j], s);
+                    Li[6 * r + j] = s * L[6 * r + r];
+                }
+            }
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c <= r; ++c) {
+                    double s = 0.0;
+                    for (int k = r; k < 6; ++k) s = fma(Li[6 * k + r], Li[6 * k + c], s);
+                    ROW(Sinv, 6 * r + c) = s;
+                    ROW(Sinv, 6 * c + r) = s;
+                }
+            if (__ldg(tp.parent + i) >= 0) {
+                double Gl[36], Ml[36];
+                for (int r = 0; r < 6; ++r)
+                    for (int cc = 0; cc < 6; ++cc) {
+                        double s = ROW(h, 21 + r * 6 + cc);
+                        for (int k = 0; k < cc; ++k) s = fma(-Gl[6 * r + k], L[6 * cc + k], s);
+                        Gl[6 * r + cc] = s * L[6 * cc + cc];
+                    }
+                for (int j = 0; j < 6; ++j)
+                    for (int r = 5; r >= 0; --r) {
+                        double s = Gl[6 * j + r];
+                        for (int k = r + 1; k < 6; ++k) s = fma(-L[6 * k + r], Ml[6 * k + j], s);
+                        Ml[6 * r + j] = s * L[6 * r + r];
+                    }
+                for (int k = 0; k < 36; ++k) {
+                    ROW(G, k) = Gl[k];
+                    ROW(M, k) = Ml[k];
+                }
+            }
+        }
+        if (good) { /* the path from the newest pose up to its root, walked back down */
+            int root = N - 1, len = 1;
+            while (__ldg(tp.parent + root) >= 0) {
+                root = __ldg(tp.parent + root);
+                ++len;
+            }
+            double Sg[36];
+            {
+                const double *Sinv = mg + ((size_t)root * MG_ROWS + 72) * TILE;
+                for (int k = 0; k < 36; ++k) Sg[k] = ROW(Sinv, k);
+            }
+            for (int step = len - 2; step >= 0; --step) {
+                int i = N - 1;
+                for (int k = 0; k < step; ++k) i = __ldg(tp.parent + i); /* the pose `step` links above the newest */
+                const double *M = mg + ((size_t)i * MG_ROWS + 36) * TILE, *Sinv = M + 36 * TILE;
+                double T[36], Nw[36];
+                for (int r = 0; r < 6; ++r)
+                    for (int c = 0; c < 6; ++c) {
+                        double s = 0.0;
+                        for (int j = 0; j < 6; ++j) s = fma(ROW(M, 6 * r + j), Sg[6 * j + c], s);
+                        T[6 * r + c] = s;
+                    }
+                for (int r = 0; r < 6; ++r)
+                    for (int c = 0; c <= r; ++c) {
+                        double s = ROW(Sinv, 6 * r + c);
+                        for (int j = 0; j < 6; ++j) s = fma(T[6 * r + j], ROW(M, 6 * c + j), s);
+                        Nw[6 * r + c] = s;
+                        Nw[6 * c + r] = s;
+                    }
+                for (int k = 0; k < 36; ++k) Sg[k] = Nw[k];
+            }
+            for (int k = 0; k < 36; ++k) o[k] = Sg[k];
+        }
+    }
+    if (!good) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int k = 0; k < 36; ++k) o[k] = nan;
+    }
+    if (okv) okv[w] = good ? 1 : 0;
+}
+
+cudaError_t launch_marginal(const DevTopo &topo, const DevWs &ws, double *scratch, double *marginal,
+                            int32_t *marginal_ok, cudaStream_t st)
+{
+    if (ws.W <= 0) return cudaSuccess;
+    marginal_kernel<<<window_blocks(ws.W), CTA_THREADS, 0, st>>>(topo, ws, scratch, marginal, marginal_ok);
+    return cudaGetLastError();
+}
 
 /* dynamic shared memory of a FAST launch; anchors go to shared memory when 4 CTAs/SM still fit */
 static size_t fast_smem_bytes(const DevTopo &topo, int threads, int *anchors_in_smem)

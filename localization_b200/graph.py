@@ -150,6 +150,64 @@ class Topology:
 
 
 @dataclass
+class RangeMsgs:
+    """Compact form of the range data (uwbgo_range_msgs): message fields instead of edge parameters; the
+    device builds measurement and information as Localization::addRangeEdge does
+    (localization.cpp:316-319,331,338,350)."""
+    distance: np.ndarray                    # [W][Era] float32
+    distance_err: np.ndarray                # [W][Era] float32
+    dt_pose: np.ndarray | None = None       # [W][Erp] float64
+    dt_anchor: np.ndarray | None = None     # [W][Era] float64, merged-covariance branch
+    v_max: float = 1.0
+
+    def __post_init__(self):
+        self.distance = np.ascontiguousarray(self.distance, np.float32)
+        self.distance_err = np.ascontiguousarray(self.distance_err, np.float32)
+        if self.dt_pose is not None:
+            self.dt_pose = _f64(self.dt_pose)
+        if self.dt_anchor is not None:
+            self.dt_anchor = _f64(self.dt_anchor)
+
+    def slice(self, lo, hi):
+        s = lambda a: None if a is None else a[lo:hi]
+        return RangeMsgs(s(self.distance), s(self.distance_err), s(self.dt_pose), s(self.dt_anchor), self.v_max)
+
+    def expand(self, topo: "Topology"):
+        """(range_d, range_info) [W][Er] in FP64: the numpy statement of the device-side expansion (x * x for the
+        squares, (v_max * dt) / 3, one IEEE division)"""
+        W = self.distance.shape[0]
+        kinds = [k for k in topo.edge_kind if k in (EDGE_RANGE_ANCHOR, EDGE_RANGE_POSE)]
+        rd, ri = np.zeros((W, len(kinds))), np.zeros((W, len(kinds)))
+        ka = kp = 0
+        for s_, k in enumerate(kinds):
+            if k == EDGE_RANGE_ANCHOR:
+                e = self.distance_err[:, ka].astype(np.float64)
+                cov = e * e
+                if self.dt_anchor is not None:
+                    m = (self.v_max * self.dt_anchor[:, ka]) / 3.0
+                    cov = cov + m * m
+                rd[:, s_] = self.distance[:, ka].astype(np.float64)
+                ka += 1
+            else:
+                m = (self.v_max * self.dt_pose[:, kp]) / 3.0
+                cov = m * m
+                kp += 1
+            ri[:, s_] = 1.0 / cov
+        return rd, ri
+
+    def c_struct(self) -> _ffi.CRangeMsgs:
+        m = _ffi.CRangeMsgs()
+        pf = lambda a: None if a is None else a.ctypes.data_as(_ffi._pf)
+        m.distance, m.distance_err = pf(self.distance), pf(self.distance_err)
+        m.dt_anchor, m.dt_pose, m.v_max = _pd(self.dt_anchor), _pd(self.dt_pose), float(self.v_max)
+        return m
+
+    @property
+    def nbytes(self):
+        return sum(a.nbytes for a in (self.distance, self.distance_err, self.dt_pose, self.dt_anchor) if a is not None)
+
+
+@dataclass
 class Batch:
     """Per-window numbers of W windows sharing one Topology (see include/uwbgo.h)."""
     pose_t: np.ndarray                      # [W][N][3]
@@ -163,6 +221,8 @@ class Batch:
     prior_info: np.ndarray | None = None    # [W][Ep][6][6]
     se3_Z: np.ndarray | None = None         # [W][Es][12]
     se3_info: np.ndarray | None = None      # [W][Es][6][6]
+    range_msgs: RangeMsgs | None = None     # compact form, instead of range_d / range_info
+    shared_anchors: bool = False            # anchors is [A][3], one constellation for all windows
 
     def __post_init__(self):
         self.pose_t = _f64(self.pose_t)
@@ -194,10 +254,22 @@ class Batch:
             raise ValueError("pose_R must be [W][N][3][3]")
         if self.oplus_count is not None and self.oplus_count.size != W * N:
             raise ValueError("oplus_count must be [W][N]")
-        need("anchors", self.anchors, W * topo.n_anchors * 3)
+        need("anchors", self.anchors, (1 if self.shared_anchors else W) * topo.n_anchors * 3)
         need("ant_offsets", self.ant_offsets, topo.n_antennas * 3)
-        need("range_d", self.range_d, W * er)
-        need("range_info", self.range_info, W * er)
+        if self.range_msgs is not None:
+            if self.range_d is not None or self.range_info is not None:
+                raise ValueError("range_msgs replaces range_d / range_info")
+            era = int(np.sum(topo.edge_kind == EDGE_RANGE_ANCHOR))
+            erp = int(np.sum(topo.edge_kind == EDGE_RANGE_POSE))
+            m = self.range_msgs
+            need("range_msgs.distance", m.distance, W * era)
+            need("range_msgs.distance_err", m.distance_err, W * era)
+            need("range_msgs.dt_pose", m.dt_pose, W * erp)
+            if m.dt_anchor is not None:
+                need("range_msgs.dt_anchor", m.dt_anchor, W * era)
+        else:
+            need("range_d", self.range_d, W * er)
+            need("range_info", self.range_info, W * er)
         need("prior_Z", self.prior_Z, W * ep * 12)
         need("prior_info", self.prior_info, W * ep * 36)
         need("se3_Z", self.se3_Z, W * es * 12)
@@ -206,7 +278,9 @@ class Batch:
     def slice(self, lo: int, hi: int) -> "Batch":
         def s(a):
             return None if a is None else a[lo:hi]
-        return Batch(pose_t=s(self.pose_t), anchors=s(self.anchors), range_d=s(self.range_d),
+        return Batch(pose_t=s(self.pose_t), anchors=self.anchors if self.shared_anchors else s(self.anchors),
+                     range_msgs=None if self.range_msgs is None else self.range_msgs.slice(lo, hi),
+                     shared_anchors=self.shared_anchors, range_d=s(self.range_d),
                      range_info=s(self.range_info), pose_R=s(self.pose_R),
                      oplus_count=s(self.oplus_count), ant_offsets=self.ant_offsets,
                      prior_Z=s(self.prior_Z), prior_info=s(self.prior_info), se3_Z=s(self.se3_Z),
@@ -220,7 +294,22 @@ class Batch:
         b.range_d, b.range_info = _pd(self.range_d), _pd(self.range_info)
         b.prior_Z, b.prior_info = _pd(self.prior_Z), _pd(self.prior_info)
         b.se3_Z, b.se3_info = _pd(self.se3_Z), _pd(self.se3_info)
+        if self.range_msgs is not None:
+            self._msgs_c = self.range_msgs.c_struct()   # kept alive with the Batch
+            b.range_msgs = C.pointer(self._msgs_c)
+        b.shared = _ffi.SHARED_ANCHORS if self.shared_anchors else 0
         return b
+
+    def expanded(self, topo: Topology) -> "Batch":
+        """the same windows with range_d / range_info written out and per-window anchors"""
+        rd, ri = (self.range_d, self.range_info) if self.range_msgs is None else self.range_msgs.expand(topo)
+        anchors = self.anchors
+        if self.shared_anchors:
+            anchors = np.ascontiguousarray(np.broadcast_to(self.anchors.reshape(1, -1, 3),
+                                                           (self.n_windows, topo.n_anchors, 3)))
+        return Batch(pose_t=self.pose_t, anchors=anchors, range_d=rd, range_info=ri, pose_R=self.pose_R,
+                     oplus_count=self.oplus_count, ant_offsets=self.ant_offsets, prior_Z=self.prior_Z,
+                     prior_info=self.prior_info, se3_Z=self.se3_Z, se3_info=self.se3_info)
 
 
 @dataclass
@@ -254,14 +343,23 @@ class Result:
     chi2: np.ndarray          # [W][4] plain, robust, g2o-stale, final lambda
     status: np.ndarray        # [W][4] iterations, trials, flags, trials of last iteration
     trace: np.ndarray | None = field(default=None)
+    edge_chi2: np.ndarray | None = field(default=None)    # [W][E]  per-edge chi2 of the last trial (sums to chi2[:, 2])
+    marginal: np.ndarray | None = field(default=None)     # [W][6][6] covariance block of the newest pose
+    marginal_ok: np.ndarray | None = field(default=None)  # [W]
 
     @staticmethod
-    def empty(W: int, N: int) -> "Result":
-        return Result(np.zeros((W, N, 3)), np.zeros((W, N, 3, 3)), np.zeros((W, N), np.int32),
-                      np.zeros((W, 4)), np.zeros((W, 4), np.int32))
+    def empty(W: int, N: int, n_edges: int | None = None, marginals: bool = False) -> "Result":
+        r = Result(np.zeros((W, N, 3)), np.zeros((W, N, 3, 3)), np.zeros((W, N), np.int32),
+                   np.zeros((W, 4)), np.zeros((W, 4), np.int32))
+        if n_edges is not None:
+            r.edge_chi2 = np.zeros((W, n_edges))
+        if marginals:
+            r.marginal, r.marginal_ok = np.zeros((W, 6, 6)), np.zeros(W, np.int32)
+        return r
 
     def c_struct(self) -> _ffi.CResult:
         r = _ffi.CResult()
         r.pose_t, r.pose_R, r.oplus_count = _pd(self.pose_t), _pd(self.pose_R), _pi(self.oplus_count)
         r.chi2, r.status = _pd(self.chi2), _pi(self.status)
+        r.edge_chi2, r.marginal, r.marginal_ok = _pd(self.edge_chi2), _pd(self.marginal), _pi(self.marginal_ok)
         return r

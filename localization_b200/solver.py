@@ -50,10 +50,12 @@ class Solver:
 
     # -- host-array entry points ------------------------------------------------------------
     def solve(self, topo: Topology, batch: Batch, cfg: Config | None = None,
-              out: Result | None = None) -> Result:
+              out: Result | None = None, edge_chi2: bool = False, marginals: bool = False) -> Result:
+        """edge_chi2 / marginals: the extras of uwbgo_result (per-edge chi2 of the last trial, covariance block of the
+        newest pose)"""
         cfg = cfg or Config()
         batch.check(topo)
-        res = out or Result.empty(batch.n_windows, topo.n_poses)
+        res = out or Result.empty(batch.n_windows, topo.n_poses, topo.n_edges if edge_chi2 else None, marginals)
         t, b, c, r = topo.c_struct(), batch.c_struct(), cfg.c_struct(), res.c_struct()
         self._check(self._lib.uwbgo_solve_batch(self._h, C.byref(t), C.byref(b), C.byref(c), C.byref(r)))
         return res

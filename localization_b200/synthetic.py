@@ -54,7 +54,7 @@ def _trajectory(rng, W, N):
     return p, vel, dt
 
 
-def _ranges(rng, truth_points, anchors, A):
+def _ranges(rng, truth_points, anchors, A, with_err=False):
     """d = float32(|p_i - a_(i mod A)| + N(0, 0.05^2)); distance_err in {0.055 (75 %), 0.024}."""
     W, N, _ = truth_points.shape
     idx = np.arange(N) % A
@@ -62,19 +62,34 @@ def _ranges(rng, truth_points, anchors, A):
     d = np.linalg.norm(truth_points - a, axis=2) + rng.normal(0.0, 0.05, size=(W, N))
     d = d.astype(np.float32).astype(np.float64)
     err = np.where(rng.uniform(size=(W, N)) < 0.75, np.float32(0.055), np.float32(0.024)).astype(np.float64)
+    if with_err:
+        return d, 1.0 / (err * err), err
     return d, 1.0 / (err * err)
 
 
-def uwb_only(W: int, N: int = 50, A: int = 8, v_max: float = 5.0, seed: int = SEED_C3):
-    """C3 / C5: UWB-only chain windows.  Returns (Topology, Batch, truth [W][N][3])."""
+def uwb_only(W: int, N: int = 50, A: int = 8, v_max: float = 5.0, seed: int = SEED_C3, compact: bool = False,
+             shared_anchors: bool = False):
+    """C3 / C5: UWB-only chain windows.  Returns (Topology, Batch, truth [W][N][3]).
+    compact: the range data as message fields (RangeMsgs: float32 distance / distance_err, the stamp
+    differences dt) instead of the edge parameters -- the same numbers, the expansion is exact.
+    shared_anchors: one anchor constellation for the whole batch (a fleet in one anchor field) instead of a
+    jittered one per window."""
     rng = np.random.default_rng(seed)
     anchors = _anchors(rng, W, A)
+    if shared_anchors:
+        anchors = np.ascontiguousarray(np.broadcast_to(anchors[:1], anchors.shape))
     p, _, dt = _trajectory(rng, W, N)
-    d, info = _ranges(rng, p, anchors, A)
+    d, info, err = _ranges(rng, p, anchors, A, with_err=True)
     init = p + rng.normal(0.0, 0.1, size=(W, N, 3))
     if N > 1:
         init[:, N - 1] = init[:, N - 2]
     topo = Topology.uwb_chain(N, A)
+    if compact:
+        from .graph import RangeMsgs
+        msgs = RangeMsgs(distance=d.astype(np.float32), distance_err=err.astype(np.float32),
+                         dt_pose=np.ascontiguousarray(dt[:, :N - 1]), v_max=v_max)
+        return topo, Batch(pose_t=init, anchors=anchors[0] if shared_anchors else anchors, range_msgs=msgs,
+                           shared_anchors=shared_anchors), p
     er = topo.counts()[0]
     rd = np.zeros((W, er))
     ri = np.zeros((W, er))

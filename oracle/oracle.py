@@ -54,12 +54,12 @@ def _pd(a):
 
 
 def solve(topo: Topology, batch: Batch, cfg: Config | None = None, n_threads: int = 0,
-          trace: bool = False) -> Result:
+          trace: bool = False, edge_chi2: bool = False, marginals: bool = False) -> Result:
     lib = load()
     cfg = cfg or Config()
     batch.check(topo)
     W, N = batch.n_windows, topo.n_poses
-    res = Result.empty(W, N)
+    res = Result.empty(W, N, topo.n_edges if edge_chi2 else None, marginals)
     tr = np.zeros((W, max(cfg.max_iterations, 1), 4)) if trace else None
     t, b, c, r = topo.c_struct(), batch.c_struct(), cfg.c_struct(), res.c_struct()
     nt = n_threads or (os.cpu_count() or 1)

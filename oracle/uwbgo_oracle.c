@@ -307,6 +307,10 @@ typedef struct {
     double *Lo;   /* [N-1][36] scratch G_i */
     double *y;    /* [N][6] c_i */
     double *zs;   /* [N][6] z_i */
+    double *rd_own, *ri_own; /* [Er] edge parameters built from range messages (compact input form) */
+    double *estale;          /* [E] chi2() of every edge at the last computeActiveErrors of optimize() */
+    double *mg;              /* [N][36 + 36 + 36] marginal scratch: G_i | M_i | S_i^-1 */
+    int built;               /* build_system() ran at least once */
 } window_t;
 
 static const double ZERO3[3] = {0.0, 0.0, 0.0};
@@ -787,6 +791,104 @@ static int factor_solve(int N, const int32_t *parent, const double *Hd, const do
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* computeMarginals(spinv, newest vertex) -- the commented-out tail of Localization::solve(),     */
+/* localization.cpp:185-189: the diagonal block of H^-1 that belongs to the newest pose, H as the  */
+/* last buildSystem() left it (no damping).  Same elimination as factor_solve (newest pose first,  */
+/* lambda = 0): S_i = H_ii - sum over children G_c G_c^T = L_i L_i^T, G_i = H_{p(i),i} L_i^-T,      */
+/* M_i = L_i^-T G_i^T.  x_i given x_p(i) is Gaussian with mean c_i - M_i x_p(i) and covariance      */
+/* S_i^-1, so along the path root -> ... -> newest                                                  */
+/*     Sigma_root = S_root^-1,      Sigma_i = S_i^-1 + M_i Sigma_p(i) M_i^T.                        */
+/* mg: [N][108] scratch (G_i | M_i | S_i^-1).  Returns 0 when a pivot is not positive.              */
+/* ------------------------------------------------------------------------------------------ */
+static int marginal_newest(int N, const int32_t *parent, const double *Hd, const double *Ho, double *mg,
+                           double *Sigma /* 36 */)
+{
+    for (int i = N - 1; i >= 0; --i) {
+        double S[36], L[36], Li[36];
+        double *G = mg + 108 * (size_t)i, *M = G + 36, *Sinv = G + 72;
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c <= r; ++c) S[6 * r + c] = Hd[36 * i + 6 * r + c];
+        for (int ch = N - 1; ch > i; --ch) {
+            if (parent[ch] != i) continue;
+            const double *Gc = mg + 108 * (size_t)ch;
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c <= r; ++c) {
+                    double s = S[6 * r + c];
+                    for (int k = 0; k < 6; ++k) s = fma(-Gc[6 * r + k], Gc[6 * c + k], s);
+                    S[6 * r + c] = s;
+                }
+        }
+        memset(L, 0, sizeof L);
+        for (int j = 0; j < 6; ++j) {
+            double s = S[6 * j + j];
+            for (int k = 0; k < j; ++k) s = fma(-L[6 * j + k], L[6 * j + k], s);
+            if (!(s > 0.0)) return 0;
+            double inv = 1.0 / sqrt(s);
+            L[6 * j + j] = inv; /* the diagonal slot stores 1/L_jj */
+            for (int r = j + 1; r < 6; ++r) {
+                double t = S[6 * r + j];
+                for (int k = 0; k < j; ++k) t = fma(-L[6 * r + k], L[6 * j + k], t);
+                L[6 * r + j] = t * inv;
+            }
+        }
+        /* Li = L^-1 (lower), then S^-1 = Li^T Li */
+        memset(Li, 0, sizeof Li);
+        for (int j = 0; j < 6; ++j) {
+            Li[6 * j + j] = L[6 * j + j];
+            for (int r = j + 1; r < 6; ++r) {
+                double s = 0.0;
+                for (int k = j; k < r; ++k) s = fma(-L[6 * r + k], Li[6 * k + j], s);
+                Li[6 * r + j] = s * L[6 * r + r];
+            }
+        }
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c <= r; ++c) {
+                double s = 0.0;
+                for (int k = r; k < 6; ++k) s = fma(Li[6 * k + r], Li[6 * k + c], s);
+                Sinv[6 * r + c] = s;
+                Sinv[6 * c + r] = s;
+            }
+        if (parent[i] >= 0) {
+            for (int r = 0; r < 6; ++r)
+                for (int cc = 0; cc < 6; ++cc) {
+                    double s = Ho[36 * i + 6 * r + cc];
+                    for (int k = 0; k < cc; ++k) s = fma(-G[6 * r + k], L[6 * cc + k], s);
+                    G[6 * r + cc] = s * L[6 * cc + cc];
+                }
+            for (int j = 0; j < 6; ++j)
+                for (int r = 5; r >= 0; --r) {
+                    double s = G[6 * j + r];
+                    for (int k = r + 1; k < 6; ++k) s = fma(-L[6 * k + r], M[6 * k + j], s);
+                    M[6 * r + j] = s * L[6 * r + r];
+                }
+        }
+    }
+    /* the path from the newest pose up to its root, walked back down */
+    int path[4096], len = 0;
+    for (int i = N - 1; i >= 0 && len < 4096; i = parent[i]) path[len++] = i;
+    memcpy(Sigma, mg + 108 * (size_t)path[len - 1] + 72, 36 * sizeof(double));
+    for (int k = len - 2; k >= 0; --k) {
+        const double *M = mg + 108 * (size_t)path[k] + 36, *Sinv = M + 36;
+        double T[36], Nw[36];
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c) {
+                double s = 0.0;
+                for (int j = 0; j < 6; ++j) s = fma(M[6 * r + j], Sigma[6 * j + c], s);
+                T[6 * r + c] = s;
+            }
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c <= r; ++c) {
+                double s = Sinv[6 * r + c];
+                for (int j = 0; j < 6; ++j) s = fma(T[6 * r + j], M[6 * c + j], s);
+                Nw[6 * r + c] = s;
+                Nw[6 * c + r] = s;
+            }
+        memcpy(Sigma, Nw, sizeof Nw);
+    }
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* window set-up / tear-down                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 /* per-kind data slots, argument checks, and the parent of every pose: the one older neighbour it
@@ -857,8 +959,12 @@ static int window_alloc(window_t *W, const uwbgo_topology *T, const uwbgo_config
     W->Lo = (double *)malloc(N * 36 * sizeof(double));
     W->y = (double *)malloc(N * 6 * sizeof(double));
     W->zs = (double *)malloc(N * 6 * sizeof(double));
+    W->rd_own = (double *)malloc(((size_t)Er + 1) * sizeof(double));
+    W->ri_own = (double *)malloc(((size_t)Er + 1) * sizeof(double));
+    W->estale = (double *)calloc(E + 1, sizeof(double));
+    W->mg = (double *)malloc(N * 108 * sizeof(double));
     return (W->X && W->Xbak && W->cnt && W->err && W->Hd && W->Ho && W->b && W->x && W->Ld &&
-            W->Lo && W->y && W->zs)
+            W->Lo && W->y && W->zs && W->rd_own && W->ri_own && W->estale && W->mg)
                ? 0
                : UWBGO_E_NOMEM;
 }
@@ -867,6 +973,7 @@ static void window_free(window_t *W)
 {
     free(W->X); free(W->Xbak); free(W->cnt); free(W->err); free(W->Hd); free(W->Ho);
     free(W->b); free(W->x); free(W->Ld); free(W->Lo); free(W->y); free(W->zs);
+    free(W->rd_own); free(W->ri_own); free(W->estale); free(W->mg);
 }
 
 static void window_load(window_t *W, const uwbgo_batch *in, int64_t w)
@@ -882,10 +989,46 @@ static void window_load(window_t *W, const uwbgo_batch *in, int64_t w)
         }
         W->cnt[i] = in->oplus_count ? in->oplus_count[(size_t)w * N + i] : 0;
     }
-    W->anchors = in->anchors ? in->anchors + (size_t)w * W->A * 3 : NULL;
+    W->built = 0;
+    /* UWBGO_SHARED_ANCHORS: one constellation for every window */
+    W->anchors = in->anchors ? in->anchors + ((in->shared & UWBGO_SHARED_ANCHORS) ? 0 : (size_t)w * W->A * 3) : NULL;
     W->ant = in->ant_offsets;
     W->range_d = in->range_d ? in->range_d + (size_t)w * W->Er : NULL;
     W->range_info = in->range_info ? in->range_info + (size_t)w * W->Er : NULL;
+    if (in->range_msgs) {
+        /* compact form: the edge parameters as Localization::addRangeEdge / create_range_edge compute them
+         * (localization.cpp:316-319: distance_cov = pow(distance_err, 2), cov_requester =
+         * pow(robot_max_velocity * dt_requester / 3, 2); :331 (distance, distance_cov); :338 (0, cov_requester);
+         * :350 (distance, distance_cov + cov_requester); :613 information = covariance_matrix.inverse()) */
+        const uwbgo_range_msgs *m = in->range_msgs;
+        const uwbgo_topology *T = W->topo;
+        int era = 0, erp = 0, ka = 0, kp = 0;
+        for (int e = 0; e < T->n_edges; ++e) {
+            era += T->edge_kind[e] == UWBGO_EDGE_RANGE_ANCHOR;
+            erp += T->edge_kind[e] == UWBGO_EDGE_RANGE_POSE;
+        }
+        for (int e = 0; e < T->n_edges; ++e) {
+            const int kind = T->edge_kind[e];
+            if (kind == UWBGO_EDGE_RANGE_ANCHOR) {
+                const double derr = (double)m->distance_err[(size_t)w * era + ka];
+                double cov = derr * derr;
+                if (m->dt_anchor) {
+                    const double mv = m->v_max * m->dt_anchor[(size_t)w * era + ka] / 3;
+                    cov = cov + mv * mv;
+                }
+                W->rd_own[W->slot[e]] = (double)m->distance[(size_t)w * era + ka];
+                W->ri_own[W->slot[e]] = 1.0 / cov;
+                ++ka;
+            } else if (kind == UWBGO_EDGE_RANGE_POSE) {
+                const double mv = m->v_max * m->dt_pose[(size_t)w * erp + kp] / 3;
+                W->rd_own[W->slot[e]] = 0.0;
+                W->ri_own[W->slot[e]] = 1.0 / (mv * mv);
+                ++kp;
+            }
+        }
+        W->range_d = W->rd_own;
+        W->range_info = W->ri_own;
+    }
     W->prior_Z = in->prior_Z ? in->prior_Z + (size_t)w * W->Ep * 12 : NULL;
     W->prior_info = in->prior_info ? in->prior_info + (size_t)w * W->Ep * 36 : NULL;
     W->se3_Z = in->se3_Z ? in->se3_Z + (size_t)w * W->Es * 12 : NULL;
@@ -895,8 +1038,15 @@ static void window_load(window_t *W, const uwbgo_batch *in, int64_t w)
 /* ------------------------------------------------------------------------------------------ */
 /* optimize(iteration_max) with OptimizationAlgorithmLevenberg — SURVEY.md A.2                  */
 /* ------------------------------------------------------------------------------------------ */
+/* edge->chi2() of every edge as the last computeActiveErrors left it */
+static void snapshot_edge_chi2(window_t *W, int want)
+{
+    if (!want) return;
+    for (int e = 0; e < W->E; ++e) W->estale[e] = edge_chi2(W, e, NULL);
+}
+
 static void solve_window(window_t *W, double *chi2_out, int32_t *status_out, double *trace,
-                         int trace_stride)
+                         int trace_stride, int want_edge_chi2)
 {
     const uwbgo_config *cfg = W->cfg;
     int N = W->N;
@@ -907,6 +1057,7 @@ static void solve_window(window_t *W, double *chi2_out, int32_t *status_out, dou
         compute_errors(W);
         chi2_sums(W, &p, &r);
         stale = p;
+        snapshot_edge_chi2(W, want_edge_chi2);
     }
     for (int it = 0; it < cfg->max_iterations; ++it) {
         double plain, currentChi;
@@ -914,6 +1065,7 @@ static void solve_window(window_t *W, double *chi2_out, int32_t *status_out, dou
         chi2_sums(W, &plain, &currentChi);
         stale = plain;
         build_system(W);
+        W->built = 1;
         if (it == 0) {
             double maxdiag = 0.0;
             for (int i = 0; i < N; ++i)
@@ -939,6 +1091,7 @@ static void solve_window(window_t *W, double *chi2_out, int32_t *status_out, dou
             compute_errors(W);
             chi2_sums(W, &tplain, &tempChi);
             stale = tplain;
+            snapshot_edge_chi2(W, want_edge_chi2);
             if (!ok) tempChi = DBL_MAX;
             double scale = 0.0;
             for (int j = 0; j < 6 * N; ++j) scale = scale + W->x[j] * (lambda * W->x[j] + W->b[j]);
@@ -1020,7 +1173,17 @@ static void *worker(void *arg)
             double chi2[UWBGO_CHI2_STRIDE];
             int32_t status[UWBGO_STATUS_STRIDE];
             solve_window(&W, chi2, status,
-                         J->trace ? J->trace + (size_t)w * J->cfg->max_iterations * 4 : NULL, 4);
+                         J->trace ? J->trace + (size_t)w * J->cfg->max_iterations * 4 : NULL, 4,
+                         J->out->edge_chi2 != NULL);
+            if (J->out->edge_chi2)
+                memcpy(J->out->edge_chi2 + (size_t)w * W.E, W.estale, (size_t)W.E * sizeof(double));
+            if (J->out->marginal) {
+                double *Sg = J->out->marginal + (size_t)w * 36;
+                int good = W.built && N <= 4096 && marginal_newest(N, W.parent, W.Hd, W.Ho, W.mg, Sg);
+                if (!good)
+                    for (int k = 0; k < 36; ++k) Sg[k] = NAN;
+                if (J->out->marginal_ok) J->out->marginal_ok[w] = good;
+            }
             for (int i = 0; i < N; ++i) {
                 memcpy(J->out->pose_t + ((size_t)w * N + i) * 3, W.X[i].t, 3 * sizeof(double));
                 if (J->out->pose_R)

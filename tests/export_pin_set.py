@@ -43,7 +43,7 @@ def main():
     for name, (make, iters) in SHAPES.items():
         topo, batch, _ = make(a.windows)
         cfg = Config(max_iterations=iters)
-        ref = oracle.solve(topo, batch, cfg)
+        ref = oracle.solve(topo, batch, cfg, edge_chi2=True)
         for w in range(a.windows):
             f = f"{name}_{w}.g2o"
             g2o_text.write_window(os.path.join(a.out, f), topo, batch, w)

@@ -45,9 +45,10 @@ def test_host_library_exports_every_declared_symbol():
 
 def test_structs_match_header_layout():
     assert ctypes.sizeof(_ffi.CTopology) == 16 + 6 * 8
-    assert ctypes.sizeof(_ffi.CBatch) == 8 + 11 * 8
+    assert ctypes.sizeof(_ffi.CBatch) == 8 + 11 * 8 + 8 + 2 * 4
+    assert ctypes.sizeof(_ffi.CRangeMsgs) == 4 * 8 + 8
     assert ctypes.sizeof(_ffi.CConfig) == 16 + 5 * 8
-    assert ctypes.sizeof(_ffi.CResult) == 5 * 8
+    assert ctypes.sizeof(_ffi.CResult) == 8 * 8
     c = _ffi.CConfig()
     _ffi.load_library().uwbgo_config_default(ctypes.byref(c))
     d = Config()

@@ -168,3 +168,102 @@ def test_forest_rule():
               se3_info=np.tile(np.eye(6), (1, 4, 1, 1)))
     with pytest.raises(RuntimeError):
         oracle.solve(topo, b, Config(max_iterations=1))
+
+
+def test_compact_range_form_is_the_expanded_form():
+    """uwbgo_range_msgs (message fields: float32 distance / distance_err, stamp differences) expands to exactly
+    the edge parameters Localization::addRangeEdge computes (localization.cpp:316-319,331,338,350); shared
+    anchors are the per-window anchors of a fleet in one anchor field"""
+    cfg = Config(max_iterations=10)
+    t, b, _ = synthetic.uwb_only(48, 14, 4, seed=21)
+    tc, bc, _ = synthetic.uwb_only(48, 14, 4, seed=21, compact=True)
+    e = bc.expanded(tc)
+    assert np.array_equal(e.range_d, b.range_d) and np.array_equal(e.range_info, b.range_info)
+    r0, r1 = oracle.solve(t, b, cfg), oracle.solve(tc, bc, cfg)
+    assert np.array_equal(r0.pose_t, r1.pose_t) and np.array_equal(r0.chi2, r1.chi2) and np.array_equal(r0.status, r1.status)
+    ts, bs, _ = synthetic.uwb_only(48, 14, 4, seed=21, compact=True, shared_anchors=True)
+    assert bs.anchors.shape == (4, 3)
+    r2, r3 = oracle.solve(ts, bs, cfg), oracle.solve(ts, bs.expanded(ts), cfg)
+    assert np.array_equal(r2.pose_t, r3.pose_t) and np.array_equal(r2.chi2, r3.chi2)
+    assert not np.array_equal(r2.pose_t, r0.pose_t)
+    # merged-covariance branch (localization.cpp:350): an anchor edge that carries the motion term as well
+    from localization_b200.graph import RangeMsgs
+    rng = np.random.default_rng(2)
+    m = RangeMsgs(distance=bc.range_msgs.distance, distance_err=bc.range_msgs.distance_err, dt_pose=bc.range_msgs.dt_pose,
+                  dt_anchor=rng.uniform(0.0, 0.04, bc.range_msgs.distance.shape), v_max=3.0)
+    bm = Batch(pose_t=bc.pose_t, anchors=bc.anchors, range_msgs=m)
+    rd, ri = m.expand(tc)
+    e64 = m.distance_err.astype(np.float64)
+    k = 0
+    assert np.array_equal(ri[:, 0], 1.0 / (e64[:, 0] * e64[:, 0] + (3.0 * m.dt_anchor[:, 0] / 3.0) ** 2))
+    r4 = oracle.solve(tc, bm, cfg)
+    r5 = oracle.solve(tc, Batch(pose_t=bc.pose_t, anchors=bc.anchors, range_d=rd, range_info=ri), cfg)
+    assert np.array_equal(r4.pose_t, r5.pose_t) and np.array_equal(r4.chi2, r5.chi2)
+    with pytest.raises(ValueError):
+        Batch(pose_t=bc.pose_t, anchors=bc.anchors, range_msgs=m, range_d=rd, range_info=ri).check(tc)
+
+
+def _last_linearisation_point(t, b, K):
+    """estimates (and oplus counters) at which iteration K of optimize(K) linearises: the result of optimize(K-1)"""
+    rp = oracle.solve(t, b, Config(max_iterations=K - 1))
+    kw = {k: getattr(b, k) for k in ("anchors", "range_d", "range_info", "ant_offsets", "prior_Z", "prior_info",
+                                     "se3_Z", "se3_info")}
+    return rp, Batch(pose_t=rp.pose_t, pose_R=rp.pose_R, oplus_count=rp.oplus_count, **kw)
+
+
+@pytest.mark.parametrize("make,K", [(lambda: synthetic.uwb_twist(12, 15, 8, seed=6), 12),
+                                    (lambda: synthetic.uwb_pose(12, 12, 8, seed=7), 10)])
+def test_marginal_of_the_newest_pose_against_dense_inverse(make, K):
+    """computeMarginals(spinv, last_vertex) (localization.cpp:185-189): the newest pose's block of H^-1, H from the
+    last buildSystem; checked against numpy's dense inverse to 1e-9 (chains and key-vertex stars)"""
+    t, b, _ = make()
+    r = oracle.solve(t, b, Config(max_iterations=K), marginals=True)
+    rp, at = _last_linearisation_point(t, b, K)
+    Hd, Ho, _, _ = oracle.linearize(t, at, Config())
+    checked = 0
+    H = dense_H(Hd, Ho, t.parents())
+    for w in range(b.n_windows):
+        if rp.status[w, 0] != K - 1 or r.status[w, 0] != K:
+            continue          # terminated early: the last buildSystem was somewhere else
+        assert r.marginal_ok[w] == 1
+        S = np.linalg.inv(H[w])[-6:, -6:]
+        assert np.abs(S - r.marginal[w]).max() <= 1e-9 * np.abs(S).max()
+        assert np.array_equal(r.marginal[w], r.marginal[w].T)
+        checked += 1
+    assert checked >= 8
+
+
+def test_marginal_is_refused_when_H_is_singular():
+    """UWB-only windows never observe the rotations, and in the uwb_imu stream the newest pose has no IMU prior yet
+    when solve() runs: g2o would print "can't compute" (localization.cpp:187-188)"""
+    for t, b in (synthetic.uwb_only(4, 10, 4, seed=3)[:2], synthetic.uwb_imu_lidar(4, 12, 4, antennas=0, lidar=False, seed=3)[:2]):
+        r = oracle.solve(t, b, Config(max_iterations=5), marginals=True)
+        assert (r.marginal_ok == 0).all() and np.isnan(r.marginal).all()
+    t, b, _ = synthetic.uwb_twist(4, 15, 8, seed=6)
+    r = oracle.solve(t, b, Config(max_iterations=0), marginals=True)      # no buildSystem ran at all
+    assert (r.marginal_ok == 0).all()
+
+
+@pytest.mark.parametrize("make,K", [(lambda: synthetic.uwb_only(64, 12, 4, seed=11), 10),
+                                    (lambda: synthetic.uwb_imu_lidar(16, 20, 8, seed=4), 20),
+                                    (lambda: synthetic.uwb_twist(16, 15, 8, seed=6), 12)])
+def test_edge_chi2_is_the_last_trials(make, K):
+    """edge->chi2() after optimize() (what the pruning of localization.cpp:172-181 would test): the terms of
+    optimizer.chi2() -- the LAST trial's errors, accepted or not"""
+    t, b, _ = make()
+    r = oracle.solve(t, b, Config(max_iterations=K), edge_chi2=True)
+    s = np.zeros(b.n_windows)
+    for e in range(t.n_edges):
+        s = s + r.edge_chi2[:, e]
+    assert np.array_equal(s, r.chi2[:, 2])
+    assert (r.edge_chi2 >= 0).all()
+    # where the last trial was accepted the terms are those of the final estimate: re-evaluate them there
+    kw = {k: getattr(b, k) for k in ("anchors", "range_d", "range_info", "ant_offsets", "prior_Z", "prior_info",
+                                     "se3_Z", "se3_info")}
+    at = Batch(pose_t=r.pose_t, pose_R=None if b.pose_R is None else r.pose_R, **kw)
+    r0 = oracle.solve(t, at, Config(max_iterations=0), edge_chi2=True)
+    accepted = r.chi2[:, 0] == r.chi2[:, 2]
+    assert accepted.any()
+    assert np.array_equal(r0.edge_chi2[accepted], r.edge_chi2[accepted])
+    if (~accepted).any():
+        assert not np.array_equal(r0.edge_chi2[~accepted], r.edge_chi2[~accepted])

@@ -556,3 +556,129 @@ def test_coincident_points_and_extreme_magnitudes(solver):
     assert np.array_equal(got.status, ref.status)
     assert np.array_equal(got.pose_t, ref.pose_t, equal_nan=True)
     assert np.array_equal(got.chi2, ref.chi2, equal_nan=True)
+
+
+def test_compact_range_form_and_shared_anchors(solver):
+    """uwbgo_range_msgs + UWBGO_SHARED_ANCHORS: the edge parameters of create_range_edge built on the device
+    (localization.cpp:316-319,331,338,350) give the bits of the expanded form, through the chunked host pipeline
+    and through the device-pointer entry point"""
+    import ctypes as C
+    import torch
+    from localization_b200 import _ffi
+    cfg = Config(max_iterations=10)
+    W = 1000                                                         # ragged last tile
+    tc, bc, _ = synthetic.uwb_only(W, 20, 8, seed=31, compact=True, shared_anchors=True)
+    ref = oracle.solve(tc, bc.expanded(tc), cfg)
+    solver.set_pipeline(128, 3)
+    try:
+        got = solver.solve(tc, bc, cfg)                              # compact form, host pointers, 8 chunks
+    finally:
+        solver.set_pipeline(8192, 8)
+    assert solver.last_path == 2
+    assert_parity(got, ref)
+    assert_parity(solver.solve(tc, bc.expanded(tc), cfg), ref)       # expanded form
+    # merged-covariance branch and a non-chain structure (table-driven kernel), per-window anchors
+    from localization_b200.graph import RangeMsgs
+    rng = np.random.default_rng(5)
+    edges = []
+    for k in range(9):
+        edges += [(EDGE_RANGE_ANCHOR, k, k % 4, 0, 1), (EDGE_RANGE_ANCHOR, k, (k + 1) % 4, 0, 0)]
+        if k > 0:
+            edges.append((EDGE_RANGE_POSE, k - 1, k, 0, 1))
+    t2 = Topology.from_edges(9, 4, 0, edges)
+    W2 = 77
+    anchors = np.array([[3., 3, 0.5], [-3, 3, 2], [-3, -3, 0.5], [3, -3, 2]])[None] + rng.uniform(-0.2, 0.2, (W2, 4, 3))
+    p = rng.uniform(-1, 1, (W2, 9, 3))
+    m = RangeMsgs(distance=rng.uniform(2, 5, (W2, 18)), distance_err=rng.choice([0.055, 0.024], (W2, 18)),
+                  dt_pose=rng.uniform(0.02, 0.05, (W2, 8)), dt_anchor=rng.uniform(0.0, 0.05, (W2, 18)), v_max=2.5)
+    b2 = Batch(pose_t=p, anchors=anchors, range_msgs=m)
+    got2, ref2 = solver.solve(t2, b2, cfg), oracle.solve(t2, b2.expanded(t2), cfg)
+    assert solver.last_path == 1
+    assert_parity(got2, ref2)
+    assert_parity(oracle.solve(t2, b2, cfg), ref2)
+    # device-pointer entry point
+    dev = torch.device("cuda", 0)
+    pd = lambda x: C.cast(C.c_void_p(x.data_ptr()), C.POINTER(C.c_double))
+    pf = lambda x: C.cast(C.c_void_p(x.data_ptr()), C.POINTER(C.c_float))
+    d = {k: torch.from_numpy(v).to(dev) for k, v in dict(pose_t=bc.pose_t, anchors=bc.anchors, dist=bc.range_msgs.distance,
+                                                          err=bc.range_msgs.distance_err, dtp=bc.range_msgs.dt_pose).items()}
+    cm = _ffi.CRangeMsgs()
+    cm.distance, cm.distance_err, cm.dt_pose, cm.v_max = pf(d["dist"]), pf(d["err"]), pd(d["dtp"]), bc.range_msgs.v_max
+    cb = _ffi.CBatch()
+    cb.n_windows, cb.pose_t, cb.anchors = W, pd(d["pose_t"]), pd(d["anchors"])
+    cb.range_msgs, cb.shared = C.pointer(cm), _ffi.SHARED_ANCHORS
+    o_t = torch.empty((W, 20, 3), dtype=torch.float64, device=dev)
+    o_c = torch.empty((W, 4), dtype=torch.float64, device=dev)
+    cr = _ffi.CResult()
+    cr.pose_t, cr.chi2 = pd(o_t), pd(o_c)
+    solver.solve_device(tc, cb, cfg, cr, torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize(dev)
+    assert np.array_equal(o_t.cpu().numpy(), ref.pose_t) and np.array_equal(o_c.cpu().numpy(), ref.chi2)
+    # one form only
+    bad = Batch(pose_t=bc.pose_t, anchors=bc.anchors, range_msgs=bc.range_msgs, shared_anchors=True)
+    cbad = bad.c_struct()
+    e = bc.expanded(tc)
+    cbad.range_d = e.range_d.ctypes.data_as(C.POINTER(C.c_double))
+    res = __import__("localization_b200").Result.empty(W, 20)
+    t_, c_, r_ = tc.c_struct(), cfg.c_struct(), res.c_struct()
+    assert solver._lib.uwbgo_solve_batch(solver._h, C.byref(t_), C.byref(cbad), C.byref(c_), C.byref(r_)) == _ffi.E_INVALID
+
+
+@pytest.mark.parametrize("make,iters,path", [
+    (lambda: synthetic.uwb_only(300, 50, 8, seed=41), 10, 2),
+    (lambda: synthetic.uwb_only(40, 12, 4, seed=42), 3, 2),
+    (lambda: synthetic.uwb_imu_lidar(70, 20, 8, seed=43), 20, 0),
+    (lambda: synthetic.uwb_imu_lidar(33, 12, 4, antennas=0, lidar=False, seed=44), 10, 0),
+    (lambda: synthetic.uwb_twist(70, 15, 8, seed=45), 12, 0),
+    (lambda: synthetic.uwb_pose(40, 24, 8, seed=46), 10, 0),
+])
+def test_edge_chi2_and_marginals(solver, make, iters, path):
+    """the extras of Localization::solve()'s commented-out tail (localization.cpp:172-189): per-edge chi2 of the
+    last trial and the covariance block of the newest pose, bit-identical to the oracle; the solve itself is
+    unchanged by asking for them"""
+    topo, batch, _ = make()
+    cfg = Config(max_iterations=iters)
+    ref = oracle.solve(topo, batch, cfg, edge_chi2=True, marginals=True)
+    got = solver.solve(topo, batch, cfg, edge_chi2=True, marginals=True)
+    assert solver.last_path == path                                   # extras always take the tile kernels
+    assert_parity(got, ref)
+    assert np.array_equal(got.edge_chi2, ref.edge_chi2)
+    assert np.array_equal(got.marginal_ok, ref.marginal_ok)
+    assert np.array_equal(got.marginal, ref.marginal, equal_nan=True)
+    s = np.zeros(batch.n_windows)
+    for e in range(topo.n_edges):
+        s = s + got.edge_chi2[:, e]
+    assert np.array_equal(s, got.chi2[:, 2])
+    plain = solver.solve(topo, batch, cfg)
+    assert np.array_equal(plain.pose_t, got.pose_t) and np.array_equal(plain.chi2, got.chi2)
+
+
+def test_edge_chi2_after_a_rejected_last_trial_and_table_driven_path(solver):
+    """max_trials = 1 ends many windows on a REJECTED trial: edge_chi2 must describe that trial's estimates, which
+    the translation-only kernels keep in the other pose buffer; non-chain structure -> lm_fast_kernel"""
+    rng = np.random.default_rng(9)
+    edges = []
+    for k in range(7):
+        edges += [(EDGE_RANGE_ANCHOR, k, k % 4, 0, 1), (EDGE_RANGE_ANCHOR, k, (k + 2) % 4, 0, 1)]
+        if k > 0:
+            edges.append((EDGE_RANGE_POSE, k - 1, k, 0, 1))
+    t = Topology.from_edges(7, 4, 0, edges)
+    W = 130
+    anchors = np.array([[3., 3, 0.5], [-3, 3, 2], [-3, -3, 0.5], [3, -3, 2]])[None] + rng.uniform(-0.2, 0.2, (W, 4, 3))
+    b = Batch(pose_t=rng.uniform(-1.5, 1.5, (W, 7, 3)), anchors=anchors, range_d=rng.uniform(0.5, 6, (W, 20)),
+              range_info=rng.uniform(50, 400, (W, 20)))
+    tc, bc, _ = synthetic.uwb_only(130, 10, 4, seed=8)   # CHAIN windows with inconsistent ranges: first steps get rejected
+    bc = Batch(pose_t=bc.pose_t, anchors=bc.anchors, range_info=bc.range_info,
+               range_d=np.where(bc.range_d > 0, rng.uniform(0.5, 6, bc.range_d.shape), 0.0))
+    rej = oracle.solve(tc, bc, Config(max_iterations=6, max_trials=2, tau=1e-10))
+    assert (rej.chi2[:, 0] != rej.chi2[:, 2]).sum() > 60
+    for topo, batch, path in ((t, b, 1), (tc, bc, 2)):
+        for cfg in (Config(max_iterations=6, max_trials=1, tau=1e-9), Config(max_iterations=6, max_trials=2, tau=1e-10),
+                    Config(max_iterations=0)):
+            ref = oracle.solve(topo, batch, cfg, edge_chi2=True)
+            got = solver.solve(topo, batch, cfg, edge_chi2=True)
+            assert solver.last_path == path
+            assert_parity(got, ref)
+            assert np.array_equal(got.edge_chi2, ref.edge_chi2)
+    rej = oracle.solve(t, b, Config(max_iterations=6, max_trials=1))
+    assert (rej.chi2[:, 0] != rej.chi2[:, 2]).sum() > 10             # the case is really exercised

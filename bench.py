@@ -35,8 +35,9 @@ WINDOWS_PER_GPU = 65536
 N_POSES, N_ANCHORS, LM_ITERS = 50, 8, 10
 METRIC = "LM-solved UWB windows/sec"
 UNIT = "windows/s"
-WORKLOAD = ("C3: synthetic UWB-only windows, 65536 per GPU, 8 anchors, 50-pose window, "
-            "10 LM iterations, 99 edges (50 anchor-range + 49 trajectory), Cauchy kernel")
+WORKLOAD = ("C3: synthetic UWB-only windows, 65536 per GPU, 8 anchors (one constellation for the fleet), 50-pose window, "
+            "10 LM iterations, 99 edges (50 anchor-range + 49 trajectory), Cauchy kernel; range data passed as message "
+            "fields (float32 distance / distance_err, stamp differences), edge parameters built on the device")
 # algorithmic bytes per window of the fused solve (inputs 4,584 + outputs 2,824)
 ALGO_BYTES_SOLVE = 7408
 ALGO_BYTES_LINEARIZE = 35496
@@ -57,7 +58,13 @@ NOTE_GENERAL = ("6x6 windows (rotations, antenna offsets, EdgeSE3Prior / EdgeSE3
 ARRAYS = ("pose_t", "pose_R", "anchors", "range_d", "range_info", "prior_Z", "prior_info", "se3_Z", "se3_info")
 # name -> (description, default windows per GPU, generator, LM iterations, SURVEY algorithmic bytes per window or None)
 WORKLOADS = {
-    "c3": (WORKLOAD, WINDOWS_PER_GPU, lambda syn, W, seed: syn.uwb_only(W, N_POSES, N_ANCHORS, seed=seed), LM_ITERS, ALGO_BYTES_SOLVE),
+    "c3": (WORKLOAD, WINDOWS_PER_GPU,
+           lambda syn, W, seed: syn.uwb_only(W, N_POSES, N_ANCHORS, seed=seed, compact=True, shared_anchors=True),
+           LM_ITERS, ALGO_BYTES_SOLVE),
+    # the same windows with the range data expanded on the host and per-window (jittered) anchors: round 1's input form
+    "c3x": (WORKLOAD.split(";")[0].replace(" (one constellation for the fleet)", "") + "; expanded input form "
+            "(range_d / range_info doubles, per-window anchors)", WINDOWS_PER_GPU,
+            lambda syn, W, seed: syn.uwb_only(W, N_POSES, N_ANCHORS, seed=seed), LM_ITERS, ALGO_BYTES_SOLVE),
     "c4a": ("C4a: synthetic uwb_imu_lidar windows, 8 anchors, 20-pose window, 3 antennas with lever arms, IMU + lidar "
             "EdgeSE3Prior on every pose but the newest, 20 LM iterations", 8192,
             lambda syn, W, seed: syn.uwb_imu_lidar(W, 20, 8, seed=seed), 20, None),
@@ -66,7 +73,7 @@ WORKLOADS = {
             lambda syn, W, seed: syn.uwb_twist(W, 15, 8, seed=seed), 12, None),
     "c5": ("C5: synthetic UWB-only Monte-Carlo windows, 16 anchors, 200-pose window, 10 LM iterations "
            "(1,048,576 windows over 8 GPUs = 131,072 per GPU)", 131072,
-           lambda syn, W, seed: syn.uwb_only(W, 200, 16, seed=seed), 10, 29200),
+           lambda syn, W, seed: syn.uwb_only(W, 200, 16, seed=seed, compact=True, shared_anchors=True), 10, 29200),
 }
 
 
@@ -190,7 +197,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     cfg = Config(max_iterations=LM_ITERS)
     n = WINDOWS_PER_GPU
-    topo, batch, _ = synthetic.uwb_only(n, N_POSES, N_ANCHORS, seed=synthetic.SEED_C3)
+    topo, batch, _ = WORKLOADS["c3"][2](synthetic, n, synthetic.SEED_C3)   # the windows rank 0 of the GPU arm solves
     t0 = time.perf_counter()
     oracle.solve(topo, batch.slice(0, 64 * cores), cfg, n_threads=cores)
     rate = 64 * cores / (time.perf_counter() - t0)
@@ -374,6 +381,18 @@ def main():
         N = topo.n_poses
         present = [k for k in ARRAYS if getattr(batch, k) is not None]
         general = batch.pose_R is not None
+        msgs = batch.range_msgs
+        MSG = (("distance", np.float32), ("distance_err", np.float32), ("dt_anchor", np.float64), ("dt_pose", np.float64))
+        pf = lambda t: C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_float))
+
+        def range_msgs_struct(arrays, as_ptr):
+            """uwbgo_range_msgs over `arrays` (name -> tensor / ndarray of the message fields)"""
+            cm = _ffi.CRangeMsgs()
+            for name, dt in MSG:
+                if arrays.get(name) is not None:
+                    setattr(cm, name, as_ptr(arrays[name], dt))
+            cm.v_max = msgs.v_max
+            return cm
         # ---- device-resident leg: results in ONE buffer per rank (poses | chi2 | status | rotations), so the
         # one gather north_star allows carries final poses, chi2 and status words (SURVEY 8e)
         d_in = {k: torch.from_numpy(getattr(batch, k)).to(dev) for k in present}
@@ -388,6 +407,11 @@ def main():
         cb.n_windows = W
         for k in present:
             setattr(cb, k, pd(d_in[k]))
+        cb.shared = _ffi.SHARED_ANCHORS if batch.shared_anchors else 0
+        if msgs is not None:
+            d_msg = {n: torch.from_numpy(getattr(msgs, n)).to(dev) for n, _ in MSG if getattr(msgs, n) is not None}
+            cm_dev = range_msgs_struct(d_msg, lambda t, dt: pf(t) if dt == np.float32 else pd(t))
+            cb.range_msgs = C.pointer(cm_dev)
         if batch.ant_offsets is not None:
             cb.ant_offsets = batch.ant_offsets.ctypes.data_as(C.POINTER(C.c_double))
         cr = _ffi.CResult()
@@ -434,16 +458,25 @@ def main():
             out["shards_verified"] = ok
 
         # ---- end-to-end leg: host buffers through uwbgo_solve_batch ----------------------------
-        hb = Batch(pose_t=batch.pose_t, ant_offsets=batch.ant_offsets)
+        hb = Batch(pose_t=batch.pose_t, ant_offsets=batch.ant_offsets, shared_anchors=batch.shared_anchors)
         for k in present:
             a = pinned_empty(getattr(batch, k).shape)
             a[...] = getattr(batch, k)
             setattr(hb, k, a)
+        h_msg = {}
+        if msgs is not None:
+            for n, dt in MSG:
+                if getattr(msgs, n) is not None:
+                    h_msg[n] = pinned_empty(getattr(msgs, n).shape, dt)
+                    h_msg[n][...] = getattr(msgs, n)
         hres = Result(pinned_empty((W, N, 3)), pinned_empty((W, N, 3, 3)) if general else None, None,
                       pinned_empty((W, 4)), pinned_empty((W, 4), np.int32))
-        h2d = sum(getattr(hb, k).nbytes for k in present)
+        h2d = sum(getattr(hb, k).nbytes for k in present) + sum(a.nbytes for a in h_msg.values())
         d2h = hres.pose_t.nbytes + hres.chi2.nbytes + hres.status.nbytes + (hres.pose_R.nbytes if general else 0)
         t_, b_, c_ = topo.c_struct(), hb.c_struct(), cfg.c_struct()
+        if msgs is not None:
+            cm_host = range_msgs_struct(h_msg, lambda a, dt: a.ctypes.data_as(C.POINTER(C.c_float if dt == np.float32 else C.c_double)))
+            b_.range_msgs = C.pointer(cm_host)
         r_ = _ffi.CResult()
         r_.pose_t, r_.chi2 = pd_np(hres.pose_t), pd_np(hres.chi2)
         if general:
@@ -489,7 +522,8 @@ def main():
         k_best = m["kernel_ms"] if m["kernel_ms"] and m["kernel_ms"] > 0 else None
         achieved = wl_bytes * W / (k_best * 1e-3) / 1e9 if k_best else None
         traffic, traffic_src, fp64_flop, fp64_pipe = None, None, None, None
-        tkey = {"c3": ("lm_chain_tma_kernel", WINDOWS_PER_GPU), "c4a": ("lm_general_cta_kernel", 8192)}.get(args.workload)
+        tkey = {"c3": ("lm_chain_tma_kernel", WINDOWS_PER_GPU), "c3x": ("lm_chain_tma_kernel", WINDOWS_PER_GPU),
+                "c4a": ("lm_general_cta_kernel", 8192)}.get(args.workload)
         for tp in (os.path.join(ROOT, "profiles", "r02_traffic.json"), os.path.join(ROOT, "profiles", "r01_traffic.json")):
             if os.path.exists(tp) and tkey and W == tkey[1]:
                 with open(tp) as f:
@@ -514,13 +548,13 @@ def main():
                 "traffic": traffic, "traffic_unit": "GB per launch (dram read+write, ncu)", "traffic_source": traffic_src,
                 "hbm": {"algorithmic_bytes_per_window": wl_bytes, "achieved_gbs": achieved, "peak_gbs": hbm,
                         "frac": achieved / hbm if achieved else None, "peak_source": how},
-                "note": NOTE_C3 if args.workload in ("c3", "c5") else NOTE_GENERAL}
+                "note": NOTE_C3 if args.workload in ("c3", "c3x", "c5") else NOTE_GENERAL}
         if traffic and k_best:
             roof["hbm"]["traffic_rate_gbs"] = traffic / (k_best * 1e-3)
             roof["hbm"]["traffic_frac"] = roof["hbm"]["traffic_rate_gbs"] / hbm
         stages = None
-        if (args.stages or world == 1) and not args.no_stages and args.workload == "c3" and W == WINDOWS_PER_GPU:
-            stages = time_stages(solver, topo, batch, cfg, dev, hbm)
+        if (args.stages or world == 1) and not args.no_stages and args.workload in ("c3", "c3x") and W == WINDOWS_PER_GPU:
+            stages = time_stages(solver, topo, batch.expanded(topo), cfg, dev, hbm)
         # the CPU leg runs at N = 1 only (the contract; at N > 1 this rank is bound to its GPU's CPUs)
         cpu = None if (args.no_cpu or world > 1) else cpu_baseline(topo, batch, cfg, name=args.workload.upper())
         line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -305,7 +305,7 @@ def run_latency(args):
                          "note": "one window is a serial chain: iterations x poses x six Cholesky pivots, each a dependent "
                                  "sqrt -> reciprocal -> multiply -> FMA sequence (~165 cycles of FP64 latency); neither HBM nor "
                                  "the FP64 pipe is loaded by a single window, the measure is microseconds per call next to "
-                                 "the CPU (DESIGN.md section 4.4)"},
+                                 "the CPU (DESIGN.md section 4.3)"},
             "cpu_baseline": {"value": one["cpu_1_thread_us"], "unit": "us per call", "cores": 1, "kind": "port",
                              "sample": f"{max(calls // 4, 5)} calls of the oracle on the same window, one host thread "
                                        "(one window cannot use more)"},

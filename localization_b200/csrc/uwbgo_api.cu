@@ -137,6 +137,7 @@ struct uwbgo_ctx {
     DevBuf ant;
     std::vector<double> ant_host; /* the antenna table `ant` holds */
     int64_t win_max = WIN_MAX_DEFAULT; /* batches up to this size take the WINDOW path */
+    int64_t batch_windows = 0;         /* host pipeline: windows of the call whose chunks are being launched */
     PinBuf pin;           /* mapped pinned staging of the WINDOW path (host API) */
     std::vector<std::unique_ptr<TopoEntry>> topos;
     uint64_t stamp = 0;
@@ -527,6 +528,7 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     char *base = static_cast<char *>(ln.tile.p);
     DevWs ws{};
     ws.W = W;
+    ws.W_batch = ctx->batch_windows;
     ws.T[0] = reinterpret_cast<double *>(base + L.off_T[0]);
     ws.T[1] = reinterpret_cast<double *>(base + L.off_T[1]);
     if (!fast) {
@@ -1085,6 +1087,7 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
     }
     int first_err = 0;
     int64_t c = 0;
+    ctx->batch_windows = W; /* the chunks run concurrently: kernels choose their shape by the whole batch */
     for (int64_t w0 = 0; w0 < W; w0 += chunk, ++c) {
         Lane &ln = ctx->lane[c % n_lanes];
         const int64_t wc = std::min<int64_t>(chunk, W - w0);
@@ -1175,6 +1178,7 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
             CUL(d2h(out->marginal ? out->marginal_ok : nullptr, S.out_mok, 4));
         }
     }
+    ctx->batch_windows = 0;
     for (int k = 0; k < n_lanes; ++k) {
         cudaError_t e = cudaStreamSynchronize(ctx->lane[k].st);
         if (e != cudaSuccess && !first_err) first_err = fail_cuda(e, "cudaStreamSynchronize");

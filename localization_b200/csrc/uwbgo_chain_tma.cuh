@@ -147,6 +147,9 @@ struct alignas(128) TmaShared {
     unsigned bad[2];         /* per warp: some active lane left the safe range of NbMath          */
     unsigned long long fbar[2];          /* factor sweep: one per step parity                     */
     unsigned long long sbar[SUBST_RING]; /* substitution sweep: one per ring slot                 */
+#ifdef UWBGO_TMA_PAD /* experiment: fewer resident tiles per SM (a smaller working set in L2) at unchanged registers */
+    char pad[UWBGO_TMA_PAD];
+#endif
 };
 static_assert(sizeof(((TmaShared *)nullptr)->in) >= TMA_STASH_DOUBLES * sizeof(double), "stash must fit in the staging area");
 

@@ -119,6 +119,8 @@ struct DevWs {
     double *chi2;       /* [tile][4][32] (solve) or [tile][2][32]     */
     int32_t *status;    /* [tile][4][32]                              */
     double *echi;       /* [tile][E*2][32] per-edge chi2 | rho0 (general CTA kernel) */
+    int64_t W_batch;    /* windows of the whole call when this launch is one chunk of a pipelined batch whose chunks
+                         * run concurrently (0: this launch is the batch); picks the CHAIN kernel's warps per tile */
     int32_t *stale_sel; /* [tile][32] or NULL.  Non-NULL = the caller wants uwbgo_result::edge_chi2: the      */
                         /* translation-only kernels then leave the last trial's estimates in buffer stale_sel */
 };

@@ -642,6 +642,7 @@ lm_chain_ws_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ D
 
 }  // namespace uwbgo
 #include "uwbgo_chain_tma.cuh"
+#include "uwbgo_chain_tma4.cuh"
 namespace uwbgo {
 
 /* antenna lever arms: a handful of doubles every range edge reads -> shared memory, loaded once */
@@ -1127,6 +1128,28 @@ static size_t fast_smem_bytes(const DevTopo &topo, int threads, int *anchors_in_
     return stash + (*anchors_in_smem ? anch : 0);
 }
 
+#ifndef UWBGO_CHAIN_WARPS
+#define UWBGO_CHAIN_WARPS 0 /* warps per tile of the CHAIN kernel: 2 (lm_chain_tma_kernel), 3 or 4 (lm_chain_tma4_kernel); 0 = by batch size */
+#endif
+/* Two warps per tile and eight tiles per SM retire the most tiles per second once the device is full; up to one
+ * wave of the three-warp kernel (five tiles per SM) the kernel time is the latency of ONE tile, and the third
+ * warp shortens it (8,192 windows: 1.91 instead of 2.11 ms; 2,048: 1.76 instead of 2.10 ms;
+ * profiles/r02_chain_warps_ab.txt).  Developer switch: the environment variable UWBGO_CHAIN_WARPS overrides. */
+static int chain_warps_per_tile(int64_t tiles)
+{
+    static int forced = -1, sms = 0;
+    if (forced < 0) {
+        const char *e = getenv("UWBGO_CHAIN_WARPS");
+        forced = e ? atoi(e) : 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (forced) return forced;
+    if (UWBGO_CHAIN_WARPS) return UWBGO_CHAIN_WARPS;
+    return tiles <= (int64_t)UWBGO_TMA3_MINB * sms ? 3 : 2;
+}
+
 cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st)
 {
     if (ws.W <= 0) return cudaSuccess;
@@ -1138,7 +1161,13 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
 #define UWBGO_CHAIN_TMA 1 /* 1: operands of the warp-specialised CHAIN kernel staged by the copy engine */
 #endif
         if (topo.fast == 2 && UWBGO_CHAIN_WS && UWBGO_CHAIN_TMA) {
-            lm_chain_tma_kernel<<<(unsigned)n_tiles(ws.W), 64, 0, st>>>(topo, cfg, ws);
+            const int nw = chain_warps_per_tile(n_tiles(ws.W_batch > ws.W ? ws.W_batch : ws.W));
+            if (nw == 4)
+                lm_chain_tma4_kernel<4><<<(unsigned)n_tiles(ws.W), 128, 0, st>>>(topo, cfg, ws);
+            else if (nw == 3)
+                lm_chain_tma4_kernel<3><<<(unsigned)n_tiles(ws.W), 96, 0, st>>>(topo, cfg, ws);
+            else
+                lm_chain_tma_kernel<<<(unsigned)n_tiles(ws.W), 64, 0, st>>>(topo, cfg, ws);
             return cudaGetLastError();
         }
         if (topo.fast == 2 && UWBGO_CHAIN_WS) {

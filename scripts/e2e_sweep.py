@@ -5,12 +5,25 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from localization_b200 import Batch, Config, Result, Solver, synthetic, _ffi
 from localization_b200.solver import pinned_empty
 W, N, A = 65536, 50, 8
-topo, batch, _ = synthetic.uwb_only(W, N, A)
+COMPACT = "--expanded" not in sys.argv
+topo, batch, _ = synthetic.uwb_only(W, N, A, compact=COMPACT, shared_anchors=COMPACT)
 cfg = Config(max_iterations=10)
 s = Solver(0)
-hb = Batch(pose_t=batch.pose_t, anchors=batch.anchors, range_d=batch.range_d, range_info=batch.range_info)
+hb = Batch(pose_t=batch.pose_t, anchors=batch.anchors, range_d=batch.range_d, range_info=batch.range_info,
+           shared_anchors=batch.shared_anchors)
 for k in ("pose_t", "anchors", "range_d", "range_info"):
-    a = pinned_empty(getattr(batch, k).shape); a[...] = getattr(batch, k); setattr(hb, k, a)
+    if getattr(batch, k) is not None:
+        a = pinned_empty(getattr(batch, k).shape); a[...] = getattr(batch, k); setattr(hb, k, a)
+if batch.range_msgs is not None:
+    from localization_b200.graph import RangeMsgs
+    m = batch.range_msgs
+    pin = lambda x, dt: None if x is None else np.copyto(pinned_empty(x.shape, dt), x) or None
+    def pinned(x, dt):
+        if x is None: return None
+        a = pinned_empty(x.shape, dt); a[...] = x; return a
+    hb.range_msgs = RangeMsgs.__new__(RangeMsgs)
+    hb.range_msgs.distance, hb.range_msgs.distance_err = pinned(m.distance, np.float32), pinned(m.distance_err, np.float32)
+    hb.range_msgs.dt_pose, hb.range_msgs.dt_anchor, hb.range_msgs.v_max = pinned(m.dt_pose, np.float64), None, m.v_max
 res = Result(pinned_empty((W, N, 3)), None, None, pinned_empty((W, 4)), pinned_empty((W, 4), np.int32))
 def run():
     s.solve(topo, hb, cfg, out=res)

@@ -12,8 +12,8 @@ flop = (2 * float(d["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cyc
         + float(d["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed"][0])
         + float(d["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed"][0])) * cyc
 ms = float(d["gpu__time_duration.sum"][0]) * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}[d["gpu__time_duration.sum"][1]]
-p = "profiles/r01_traffic.json"
-j = json.load(open(p))
+p = sys.argv[5] if len(sys.argv) > 5 else "profiles/r01_traffic.json"
+j = json.load(open(p)) if __import__("os").path.exists(p) else {}
 j[key] = {"dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
           "windows_per_launch": windows, "kernel_ms_under_ncu": ms, "fp64_flop_per_launch": flop,
           "fp64_pipe_active_pct": float(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"][0]),

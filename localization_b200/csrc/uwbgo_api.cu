@@ -466,7 +466,7 @@ int check_batch(const TopoEntry &te, const uwbgo_batch *in)
 struct TileLayout {
     size_t bytes = 0;
     size_t off_T[2], off_R[2], off_cnt, off_anch, off_rd, off_ri, off_pZ, off_pI, off_sZ, off_sI, off_HB,
-        off_LR, off_chi2, off_status, off_echi, off_sel, off_mg;
+        off_LR, off_chi2, off_status, off_echi, off_sel, off_mg, off_jrec;
 };
 TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bool want_LR, bool want_sel = false,
                        bool want_marginal = false)
@@ -499,6 +499,7 @@ TileLayout tile_layout(const DevTopo &t, bool fast, int64_t W, bool want_cnt, bo
     L.off_status = take(4, 4);
     /* per-edge chi2 terms: the general LM kernel, and the fused linearise stage of CHAIN windows */
     L.off_echi = ((!fast && want_LR) || (fast && !want_LR)) ? take((size_t)t.E * 2, 8) : 0;
+    L.off_jrec = (!fast && want_LR && !t.tree) ? take(general_items_jrec_rows(t), 8) : 0;
     L.off_sel = want_sel ? take(1, 4) : 0;
     L.off_mg = (want_marginal && !fast) ? take(marginal_scratch_bytes(t, TILE) / (TILE * 8), 8) : 0;
     L.bytes = o;
@@ -550,6 +551,7 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
     ws.chi2 = reinterpret_cast<double *>(base + L.off_chi2);
     ws.status = reinterpret_cast<int32_t *>(base + L.off_status);
     ws.echi = ((!fast && !so) || (fast && so)) ? reinterpret_cast<double *>(base + L.off_echi) : nullptr;
+    ws.jrec = (!fast && !so && !tp.tree) ? reinterpret_cast<double *>(base + L.off_jrec) : nullptr;
     ws.stale_sel = (want_echi && fast) ? reinterpret_cast<int32_t *>(base + L.off_sel) : nullptr;
 
     XposeJobs pj{};

@@ -638,7 +638,7 @@ UWBGO_DI double gen_linearize_pose(const GenEnv &E, const PoseBuf &T, const int 
 
 /* BlockSolver::buildSystem, general edges, one thread per window.  Advances the oplus counters by
  * the numeric-Jacobian calls.  Returns max |H_kk|. */
-__device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
+static __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
 {
     const DevTopo &tp = *E.tp;
     const int N = tp.N, mod = E.cfg->orth_mod;
@@ -655,7 +655,7 @@ __device__ __noinline__ double gen_linearize(const GenEnv &E, const PoseBuf &T)
  * older neighbour parent(i) < i, not necessarily i-1.  Same elimination as factor_sweep<6>, newest
  * pose first and therefore without fill, but a pose may have several children, whose G and z are
  * read back from their L records:  L record (tree) = c 6 | M 36 | G 36 | z 6 | x 6. */
-__device__ __noinline__ bool factor_sweep_tree(const DevTopo &tp, const double *__restrict__ HB,
+static __device__ __noinline__ bool factor_sweep_tree(const DevTopo &tp, const double *__restrict__ HB,
                                                double *__restrict__ LR, double lambda)
 {
     const int N = tp.N;
@@ -764,7 +764,7 @@ __device__ __noinline__ bool factor_sweep_tree(const DevTopo &tp, const double *
     return ok;
 }
 
-__device__ __noinline__ double gen_solve_update(const GenEnv &E, bool ok, double lambda,
+static __device__ __noinline__ double gen_solve_update(const GenEnv &E, bool ok, double lambda,
                                                 const PoseBuf &Tc, const PoseBuf &Tn)
 {
     const int N = E.tp->N, mod = E.cfg->orth_mod;
@@ -813,7 +813,7 @@ __device__ __noinline__ double gen_solve_update(const GenEnv &E, bool ok, double
 /* gen_solve_update cut in two for the CTA kernel.  First the serial part, one thread per window:
  * the substitution x_i = c_i - M_i x_parent(i) and computeScale(); x_i is left in the L record
  * (chain: over c_i, which is dead once x_i exists; forest: its x slot). */
-__device__ __noinline__ double gen_subst_scale(const GenEnv &E, bool ok, double lambda)
+static __device__ __noinline__ double gen_subst_scale(const GenEnv &E, bool ok, double lambda)
 {
     const int N = E.tp->N;
     double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};

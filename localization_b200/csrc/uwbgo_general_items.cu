@@ -1,0 +1,1053 @@
+/*
+ * uwbgo_general_items.cu — GENERAL path (6x6 blocks), ITEM kernel: one CTA per tile of 32 windows, lane = window,
+ * and every phase of the LM trial cut into ITEMS small enough to run at 128 registers per thread, so that a tile
+ * has 8 warps (two tiles per SM) instead of the 4 warps at 255 registers of lm_general_cta_kernel
+ * (uwbgo_general_cta.cuh), whose linearisation of a whole pose holds ~170 doubles per thread and spills.
+ *
+ * The arithmetic is Localization::solve()'s optimize(iteration_max) (reference src/localization/localization.cpp:164-192)
+ * over the graph of localization.cpp:254-376,462-605, as restated by the CPU checker; every H / b entry, every
+ * chi2 term and every elimination step sees the operation sequence of lm_general_cta_kernel, so the results are
+ * the same bits.  What changes is who computes what:
+ *
+ *   J   buildSystem, part 1: one item per 6-D edge (error, Jacobians, weights), per range edge (error, weights,
+ *       numeric Jacobian wrt vertex 0) and per pose-pose range edge (numeric Jacobian wrt vertex 1); warp k takes
+ *       items k, k + NW, ...; the records go to a per-tile scratch (tile layout, L2)
+ *   H   buildSystem, part 2: one item per (pose, row of H_ii + b_i) and per (pose, row of H_{i-1,i}); the item
+ *       walks the pose's edges in g2o insertion order and adds their terms (J^T Omega rows of the 6-D edges are
+ *       formed on the fly), so every entry is accumulated by one thread in the order of the checker
+ *   F   the serial chain of the window on TWO warps: warp 0 eliminates (S_i, potrf, z_i, G_i; G of the child pose
+ *       is read from shared memory), warp 1 follows one pose behind with what nothing in the elimination waits for
+ *       (c_i, M_i and the L record store) and then runs the substitution and computeScale()
+ *   U   estimate (+) x, one item per pose;  C  computeActiveErrors, one item per edge, chi2 terms to shared memory
+ *   D   warp 0: ordered sums, accept / reject (the flat LM loop of lm_general_cta_kernel)
+ *
+ * Chains only (parent(i) = i - 1 or none); forest windows (pose edges to a key vertex) keep lm_general_cta_kernel.
+ */
+#include "uwbgo_general.cuh"
+#ifdef UWBGO_GIT_TIMING
+#include <cstdio>
+#endif
+
+namespace uwbgo {
+
+namespace {
+
+constexpr int GIT_MAX_SMEM_ANTENNAS = 16;
+
+/* per-edge linearisation records, rows of the per-tile scratch (DevWs::jrec) */
+constexpr int GR_RANGE = 14; /* A 6 | B 6 | Ow | omega_r                                   */
+constexpr int GR_PRIOR = 27; /* the edge's terms of H_ii (upper, 21) and of b_i (6): J^T Ow J and J^T omega_r */
+constexpr int GR_SE3 = 151;  /* A 36 | B 36 | omega_r 6 | rho1 | A^T Ow 36 | B^T Ow 36     */
+
+/* hand-off buffer of the elimination, one per step parity: G_i 36 | L_i 21 | z_i 6, [row][lane] */
+constexpr int GIT_HAND = 63;
+
+struct GitShared {
+    double ant[3 * GIT_MAX_SMEM_ANTENNAS];
+    double lam[TILE];                 /* F: lambda of the trial (warp 0 -> warp 1)                        */
+    double tscale[TILE];              /* F -> D: computeScale() of the trial (warp 1 -> warp 0)           */
+    int tok[TILE];                    /* F: the factorisation succeeded (warp 0 -> warp 1)                */
+    int lin[TILE];                    /* D -> all: window starts an iteration (buildSystem)               */
+    int cur[TILE];                    /* D -> all: which pose buffer holds the estimate                   */
+    int act[TILE];                    /* D -> all: window still being optimised                           */
+    int go, anylin, redo;
+    int zero;                         /* 0, read through a volatile pointer: keeps per-phase address arithmetic per phase */
+    /* LM state of every window, parked here between the phases of warp 0 */
+    double lm_d[6][TILE]; /* lambda, ni, stale, plainCur, currentChi, rho */
+    int lm_i[8][TILE];    /* iterations, trials_total, flags, qlast, cur, q, it, bit 0 need_lin | bit 1 done */
+};
+
+struct LmState {
+    double lambda, ni, stale, plainCur, currentChi, rho;
+    int iterations, trials_total, flags, qlast, cur, q, it;
+    bool need_lin, done;
+    UWBGO_DI void load(const GitShared &sh, int lane)
+    {
+        lambda = sh.lm_d[0][lane]; ni = sh.lm_d[1][lane]; stale = sh.lm_d[2][lane];
+        plainCur = sh.lm_d[3][lane]; currentChi = sh.lm_d[4][lane]; rho = sh.lm_d[5][lane];
+        iterations = sh.lm_i[0][lane]; trials_total = sh.lm_i[1][lane]; flags = sh.lm_i[2][lane]; qlast = sh.lm_i[3][lane];
+        cur = sh.lm_i[4][lane]; q = sh.lm_i[5][lane]; it = sh.lm_i[6][lane];
+        need_lin = (sh.lm_i[7][lane] & 1) != 0;
+        done = (sh.lm_i[7][lane] & 2) != 0;
+    }
+    UWBGO_DI void store(GitShared &sh, int lane) const
+    {
+        sh.lm_d[0][lane] = lambda; sh.lm_d[1][lane] = ni; sh.lm_d[2][lane] = stale;
+        sh.lm_d[3][lane] = plainCur; sh.lm_d[4][lane] = currentChi; sh.lm_d[5][lane] = rho;
+        sh.lm_i[0][lane] = iterations; sh.lm_i[1][lane] = trials_total; sh.lm_i[2][lane] = flags; sh.lm_i[3][lane] = qlast;
+        sh.lm_i[4][lane] = cur; sh.lm_i[5][lane] = q; sh.lm_i[6][lane] = it;
+        sh.lm_i[7][lane] = (need_lin ? 1 : 0) | (done ? 2 : 0);
+    }
+};
+
+UWBGO_DI void bar_pair() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+/* asynchronous copies global -> shared (LDGSTS), 16 bytes per lane and instruction, past L1 */
+UWBGO_DI void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+UWBGO_DI void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+UWBGO_DI void cp_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+/* one warp stages `rows` consecutive rows of a tile array ([row][32] doubles, contiguous) */
+UWBGO_DI void stage_rows(double *dst, const double *src, int rows, int lane)
+{
+    const int chunks = rows * (TILE * (int)sizeof(double) / 16);
+    for (int c = lane; c < chunks; c += 32)
+        cp_async16(reinterpret_cast<char *>(dst) + 16 * c, reinterpret_cast<const char *>(src) + 16 * c);
+}
+
+struct GitEnv {
+    GenEnv E;
+    double *jrec; /* this lane's column of the tile's linearisation records */
+    int Er, Ep, Es;
+};
+
+/* the topology tables every item walks, copied to shared memory once per CTA (they are the same for all tiles) */
+struct GitTopo {
+    const EdgeRec *edges; /* [E]     */
+    const int2 *ops;      /* [n_ops] */
+    const int *op_begin;  /* [N + 1] */
+    const int *slot_edge; /* [E]     */
+};
+UWBGO_DI EdgeRec smem_edge(const EdgeRec *e)
+{
+    const int4 *p = reinterpret_cast<const int4 *>(e);
+    const int4 u = p[0], v = p[1];
+    EdgeRec r;
+    r.kind = u.x; r.a = u.y; r.b = u.z; r.slot = u.w;
+    r.ant = v.x; r.robust = v.y; r.base_a = v.z; r.base_b = v.w;
+    r.ant_b = e->ant_b;
+    return r;
+}
+
+/* ---- J items ------------------------------------------------------------------------------------------------ */
+
+/* range edge, slot k: error, weights and the numeric Jacobian wrt vertex 0 (gen_linearize_pose_acc, role 0) */
+UWBGO_DI void item_range_v0(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int k)
+{
+    const GenEnv &E = G.E;
+    const EdgeRec er = smem_edge(tt.edges + tt.slot_edge[k]);
+    double *rec = G.jrec + (size_t)k * GR_RANGE * TILE;
+    const double d = ROW(E.p.rd, er.slot), info = ROW(E.p.ri, er.slot);
+    Pose Xa;
+    load_pose(T, er.a, Xa);
+    double P0[3], Q[3], A[6];
+    offset_point(E, Xa, er.ant, P0);
+    if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+        anchor_point(E, er.b, er.ant_b, Q);
+    } else if (er.ant_b > 0) {
+        Pose Xb;
+        load_pose(T, er.b, Xb);
+        offset_point(E, Xb, er.ant_b, Q);
+    } else {
+        const double *tb = T.t + (size_t)er.b * 3 * TILE;
+        Q[0] = ROW(tb, 0); Q[1] = ROW(tb, 1); Q[2] = ROW(tb, 2);
+    }
+    const double err = d - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
+    const double Oe = info * err;
+    double omega_r = -Oe, Ow = info;
+    if (er.robust) {
+        const double r1 = E.ck.rho1(err * Oe);
+        omega_r = omega_r * r1;
+        Ow = r1 * info;
+    }
+    gen_jac_v0(E, Xa, er.ant, Q, d, E.p.cnt[(size_t)er.a * TILE], er.base_a, A);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ROW(rec, j) = A[j];
+    ROW(rec, 12) = Ow;
+    ROW(rec, 13) = omega_r;
+}
+
+/* pose-pose range edge, slot k: numeric Jacobian wrt vertex 1 (gen_linearize_pose_acc, role 1) */
+UWBGO_DI void item_range_v1(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int k)
+{
+    const GenEnv &E = G.E;
+    const EdgeRec er = smem_edge(tt.edges + tt.slot_edge[k]);
+    if (er.kind != UWBGO_EDGE_RANGE_POSE) return;
+    double *rec = G.jrec + (size_t)k * GR_RANGE * TILE;
+    const double d = ROW(E.p.rd, er.slot);
+    Pose Xa, Xb;
+    load_pose(T, er.a, Xa);
+    load_pose(T, er.b, Xb);
+    double P0[3], B[6];
+    offset_point(E, Xa, er.ant, P0);
+    if (er.ant_b > 0)
+        gen_jac_v0<true>(E, Xb, er.ant_b, P0, d, E.p.cnt[(size_t)er.b * TILE], er.base_b, B);
+    else
+        gen_jac_v1(E, P0, Xb, d, B);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ROW(rec, 6 + j) = B[j];
+}
+
+/* J^T Ow of a 6-D edge (jt_omega of uwbgo_general.cuh), column by column, straight into the record: J is in
+ * registers with its structural zeros, Ow = rho1 * Omega when the edge is robust */
+UWBGO_DI void store_jto(const double *J, const double *__restrict__ O, bool robust, double r1, double *out)
+{
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double ow[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double v = ROW(O, 6 * k + c);
+            ow[k] = robust ? r1 * v : v;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double s = J[r] * ow[0];
+#pragma unroll
+            for (int k = 1; k < 6; ++k) s = fma(J[6 * k + r], ow[k], s);
+            ROW(out, 6 * r + c) = s;
+        }
+    }
+}
+
+/* EdgeSE3Prior, slot s: the edge touches one pose, so its whole contribution to H_ii and b_i is formed here
+ * (error, rho1, omega_r, J, J^T Ow, then the sums of acc6_b / acc6_diag) and the H item only adds it */
+UWBGO_DI void item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int s)
+{
+    const GenEnv &E = G.E;
+    const EdgeRec er = smem_edge(tt.edges + tt.slot_edge[G.Er + s]);
+    double *rec = G.jrec + ((size_t)G.Er * GR_RANGE + (size_t)s * GR_PRIOR) * TILE;
+    Pose Zinv, Xi, Dl;
+    load_pose(T, er.a, Xi);
+    load_Zinv(E.p.pZ, er.slot, Zinv);
+    pose_mul(Zinv, Xi, Dl);
+    double q[4], e6[6], Oe[6];
+    R_to_quat(Dl.R, q);
+    e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
+    e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
+    const double chi = chi2_6(E.p.pI, er.slot, e6, Oe);
+    const double r1 = er.robust ? E.ck.rho1(chi) : 1.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        Oe[k] = -Oe[k];
+        if (er.robust) Oe[k] = Oe[k] * r1;
+    }
+    double J[36], JtO[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) J[k] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) J[6 * r + c] = Dl.R[3 * r + c];
+    set_jqq(q, J);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { /* acc6_b */
+        double v = J[r] * Oe[0];
+#pragma unroll
+        for (int k = 1; k < 6; ++k) v = fma(J[6 * k + r], Oe[k], v);
+        ROW(rec, 21 + r) = v;
+    }
+    jt_omega(J, E.p.pI + (size_t)er.slot * 36 * TILE, er.robust != 0, r1, JtO);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) /* acc6_diag */
+#pragma unroll
+        for (int c = r; c < 6; ++c) {
+            double v = JtO[6 * r] * J[c];
+#pragma unroll
+            for (int k = 1; k < 6; ++k) v = fma(JtO[6 * r + k], J[6 * k + c], v);
+            ROW(rec, up_idx(6, r, c)) = v;
+        }
+}
+
+/* EdgeSE3, slot s: error, rho1, omega_r and both analytic Jacobians */
+UWBGO_DI void item_se3(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int s)
+{
+    const GenEnv &E = G.E;
+    const EdgeRec er = smem_edge(tt.edges + tt.slot_edge[G.Er + G.Ep + s]);
+    double *rec = G.jrec + ((size_t)G.Er * GR_RANGE + (size_t)G.Ep * GR_PRIOR + (size_t)s * GR_SE3) * TILE;
+    Pose Zinv, Xi, Xj;
+    load_Zinv(E.p.sZ, er.slot, Zinv);
+    load_pose(T, er.a, Xi);
+    load_pose(T, er.b, Xj);
+    double e6[6], Oe[6];
+    se3_error(Zinv, Xi, Xj, e6);
+    const double chi = chi2_6(E.p.sI, er.slot, e6, Oe);
+    const double r1 = er.robust ? E.ck.rho1(chi) : 1.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double v = -Oe[k];
+        if (er.robust) v = v * r1;
+        ROW(rec, 72 + k) = v;
+    }
+    ROW(rec, 78) = r1;
+    double Ji[36], Jj[36];
+    se3_jacobians(Zinv, Xi, Xj, Ji, Jj, true);
+#pragma unroll
+    for (int k = 0; k < 36; ++k) ROW(rec, k) = Ji[k];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) ROW(rec, 36 + k) = Jj[k];
+    const double *O = E.p.sI + (size_t)er.slot * 36 * TILE;
+    store_jto(Ji, O, er.robust != 0, r1, rec + (size_t)79 * TILE);
+    store_jto(Jj, O, er.robust != 0, r1, rec + (size_t)115 * TILE);
+}
+
+/* ---- H items ------------------------------------------------------------------------------------------------ */
+
+/* the Jacobian of a 6-D edge wrt the pose playing `role` into registers, structural zeros included (they take
+ * part in the sums exactly as in gen_linearize_pose_acc); prior records keep the two 3x3 diagonal blocks only */
+UWBGO_DI void load_six_J(const double *rec, bool prior, int role, double *J)
+{
+    if (prior) {
+#pragma unroll
+        for (int k = 0; k < 36; ++k) J[k] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                J[6 * r + c] = ROW(rec, 3 * r + c);
+                J[6 * (3 + r) + 3 + c] = ROW(rec, 9 + 3 * r + c);
+            }
+    } else {
+        const double *p = rec + (size_t)(36 * role) * TILE;
+#pragma unroll
+        for (int k = 0; k < 36; ++k) J[k] = ROW(p, k);
+    }
+}
+
+/* H_ii (upper) and b_i of pose i, gathered from the records of the edges touching it in insertion order (the
+ * accumulation part of gen_linearize_pose_acc); returns max |H_ii(k, k)| */
+UWBGO_DI double item_h_diag(const GitEnv &G, const GitTopo &tt, int i)
+{
+    const GenEnv &E = G.E;
+    double hd[21], bb[6];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) hd[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bb[k] = 0.0;
+    const int ob = tt.op_begin[i], oe = tt.op_begin[i + 1];
+    for (int o = ob; o < oe; ++o) {
+        const int2 op = tt.ops[o];
+        const EdgeRec er = smem_edge(tt.edges + op.x);
+        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
+            const double *rec = G.jrec + (size_t)er.slot * GR_RANGE * TILE;
+            const double *Jp = rec + (size_t)(6 * op.y) * TILE;
+            double J[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) J[k] = ROW(Jp, k);
+            acc1_diag(J, ROW(rec, 12), ROW(rec, 13), hd, bb);
+        } else if (er.kind == UWBGO_EDGE_PRIOR) {
+            const double *rec = G.jrec + ((size_t)G.Er * GR_RANGE + (size_t)er.slot * GR_PRIOR) * TILE;
+            double v[27];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) v[k] = ROW(rec, k);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) bb[k] = bb[k] + v[21 + k];
+#pragma unroll
+            for (int k = 0; k < 21; ++k) hd[k] = hd[k] + v[k];
+        } else {
+            const double *rec = G.jrec + ((size_t)G.Er * GR_RANGE + (size_t)G.Ep * GR_PRIOR + (size_t)er.slot * GR_SE3) * TILE;
+            const double *om = rec + (size_t)72 * TILE;
+            const double *jto = rec + (size_t)(79 + 36 * op.y) * TILE;
+            double J[36], omv[6];
+            load_six_J(rec, false, op.y, J);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) omv[k] = ROW(om, k);
+            acc6_b(J, omv, bb);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { /* acc6_diag, J^T Ow read row by row */
+                double t[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) t[k] = ROW(jto, 6 * r + k);
+#pragma unroll
+                for (int c = r; c < 6; ++c) {
+                    double s = t[0] * J[c];
+#pragma unroll
+                    for (int k = 1; k < 6; ++k) s = fma(t[k], J[6 * k + c], s);
+                    hd[up_idx(6, r, c)] = hd[up_idx(6, r, c)] + s;
+                }
+            }
+        }
+    }
+    double *h = E.p.HB + (size_t)i * HR_GEN * TILE;
+#pragma unroll
+    for (int k = 0; k < 21; ++k) ROW(h, k) = hd[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ROW(h, 57 + k) = bb[k];
+    double maxdiag = 0.0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const double v = fabs(hd[up_idx(6, r, r)]);
+        if (v > maxdiag) maxdiag = v;
+    }
+    return maxdiag;
+}
+
+/* H_{a, i} (rows of the older pose a, columns of pose i): the pose-pose edges in which pose i is vertex 1 */
+UWBGO_DI void item_h_off(const GitEnv &G, const GitTopo &tt, int i)
+{
+    const GenEnv &E = G.E;
+    double ho[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) ho[k] = 0.0;
+    const int ob = tt.op_begin[i], oe = tt.op_begin[i + 1];
+    for (int o = ob; o < oe; ++o) {
+        const int2 op = tt.ops[o];
+        if (op.y != 1) continue;
+        const EdgeRec er = smem_edge(tt.edges + op.x);
+        if (er.kind == UWBGO_EDGE_RANGE_POSE) {
+            const double *rec = G.jrec + (size_t)er.slot * GR_RANGE * TILE;
+            double A[6], B[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                A[k] = ROW(rec, k);
+                B[k] = ROW(rec, 6 + k);
+            }
+            acc1_off(A, B, ROW(rec, 12), ho);
+        } else if (er.kind == UWBGO_EDGE_SE3) {
+            const double *rec = G.jrec + ((size_t)G.Er * GR_RANGE + (size_t)G.Ep * GR_PRIOR + (size_t)er.slot * GR_SE3) * TILE;
+            const double *ato = rec + (size_t)79 * TILE;
+            double B[36];
+            load_six_J(rec, false, 1, B);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { /* acc6_off, A^T Ow read row by row */
+                double t[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) t[k] = ROW(ato, 6 * r + k);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    double s = t[0] * B[c];
+#pragma unroll
+                    for (int k = 1; k < 6; ++k) s = fma(t[k], B[6 * k + c], s);
+                    ho[6 * r + c] = ho[6 * r + c] + s;
+                }
+            }
+        }
+    }
+    double *h = E.p.HB + (size_t)i * HR_GEN * TILE;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) ROW(h, 21 + k) = ho[k];
+}
+
+/* ---- C item: computeError + chi2 of edge e (gen_edge_chi with the information matrix streamed) ---------------- */
+UWBGO_DI void item_chi(const GenEnv &E, const GitTopo &tt, const PoseBuf &T, int e, double &chi_out, double &rob_out)
+{
+    const EdgeRec er = smem_edge(tt.edges + e);
+    double chi;
+    if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
+        Pose Xa;
+        load_pose(T, er.a, Xa);
+        double P0[3], Q[3];
+        offset_point(E, Xa, er.ant, P0);
+        if (er.kind == UWBGO_EDGE_RANGE_ANCHOR) {
+            anchor_point(E, er.b, er.ant_b, Q);
+        } else if (er.ant_b > 0) {
+            Pose Xb;
+            load_pose(T, er.b, Xb);
+            offset_point(E, Xb, er.ant_b, Q);
+        } else {
+            const double *tb = T.t + (size_t)er.b * 3 * TILE;
+            Q[0] = ROW(tb, 0); Q[1] = ROW(tb, 1); Q[2] = ROW(tb, 2);
+        }
+        const double err = ROW(E.p.rd, er.slot) - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
+        const double Oe = ROW(E.p.ri, er.slot) * err;
+        chi = err * Oe;
+    } else if (er.kind == UWBGO_EDGE_PRIOR) {
+        Pose Zinv, X, Dl;
+        load_pose(T, er.a, X);
+        load_Zinv(E.p.pZ, er.slot, Zinv);
+        pose_mul(Zinv, X, Dl);
+        double q[4], e6[6], Oe[6];
+        R_to_quat(Dl.R, q);
+        e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
+        e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
+        chi = chi2_6(E.p.pI, er.slot, e6, Oe);
+    } else {
+        Pose Zinv, Xi, Xj;
+        load_pose(T, er.a, Xi);
+        load_pose(T, er.b, Xj);
+        load_Zinv(E.p.sZ, er.slot, Zinv);
+        double e6[6], Oe[6];
+        se3_error(Zinv, Xi, Xj, e6);
+        chi = chi2_6(E.p.sI, er.slot, e6, Oe);
+    }
+    chi_out = chi;
+    rob_out = er.robust ? E.ck.rho0(chi) : chi;
+}
+
+/* ---- F: the elimination chain on warp 0, the back-substitutions of every step on warp 1 ---------------------- */
+
+/* factor_step<6> of uwbgo_block_solver.cuh cut in two.  Warp 0, pose i: S_i = H_ii + lambda I - G_c G_c^T, its
+ * Cholesky factor (the diagonal slot keeps 1 / L_jj), z_i, and G_i = H_{i-1,i} L_i^-T; G_i, L_i, z_i go to the
+ * hand-off buffer of the step's parity, where the next step (G_i, z_i) and warp 1 (all three) read them. */
+/* 0 for every double arithmetic produces, but not provably so: an address that depends on it cannot be formed, and
+ * its loads cannot be hoisted, before the value exists (ptxas otherwise lifts every shared-memory load of the step
+ * to its top and spills what it loaded; a spill is an L2 round trip at the L1 size this kernel leaves) */
+UWBGO_DI int after(double v) { return ((__double2hiint(v) & 0x7fffffff) == 0x7ff12345) ? 1 : 0; }
+
+template <class M>
+UWBGO_DI unsigned factor_main_step(const double *__restrict__ h, const double *__restrict__ Gc,
+                                                         double *__restrict__ Gn, bool link, bool has_prev, double lambda)
+{
+    /* its own register frame (not inlined); returns bit 0 = a pivot was not positive, bit 1 = the branch-free roots
+     * flagged an operand.  z of the child pose is read from the child's hand-off buffer. */
+    bool ok = true;
+    unsigned bad = 0;
+    double L[21], z[6];
+    int dep = 0;
+    /* column j of S is formed right before the potrf eliminates it (same sums, fewer values alive) */
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const double *hj = h + dep, *Gj = Gc + dep;
+        double gj[6], col[6];
+        if (link) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) gj[k] = ROW(Gj, j * 6 + k);
+        }
+#pragma unroll
+        for (int r = j; r < 6; ++r) {
+            double s = ROW(hj, up_idx(6, j, r));
+            if (r == j) s = s + lambda;
+            if (link) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s = fma(-(r == j ? gj[k] : ROW(Gj, r * 6 + k)), gj[k], s);
+            }
+            col[r] = s;
+        }
+        double s = col[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
+        if (!(s > 0.0)) ok = false;
+        const double inv = M::rsqrt_pivot(s, bad);
+        L[lo_idx(j, j)] = inv;
+        dep = after(inv);
+#pragma unroll
+        for (int r = j + 1; r < 6; ++r) {
+            double t = col[r];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
+            L[lo_idx(r, j)] = t * inv;
+        }
+    }
+    {
+        const double *hz = h + dep, *Gz = Gc + dep;
+        double zn[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (link) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) zn[k] = ROW(Gz, 57 + k);
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double s = ROW(hz, 57 + r);
+            if (link) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s = fma(-ROW(Gz, r * 6 + k), zn[k], s);
+            }
+#pragma unroll
+            for (int k = 0; k < r; ++k) s = fma(-L[lo_idx(r, k)], z[k], s);
+            z[r] = s * L[lo_idx(r, r)];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ROW(Gn, 57 + k) = z[k];
+    dep = after(z[5]);
+    if (has_prev) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const double *hr = h + dep;
+            double g[6];
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) {
+                double s = ROW(hr, 21 + r * 6 + cc);
+#pragma unroll
+                for (int k = 0; k < cc; ++k) s = fma(-g[k], L[lo_idx(cc, k)], s);
+                g[cc] = s * L[lo_idx(cc, cc)];
+            }
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) ROW(Gn, r * 6 + cc) = g[cc];
+            if (r == 2) dep = after(g[5]); /* rows 3..5 after rows 0..2 */
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 21; ++k) ROW(Gn, 36 + k) = L[k];
+    return (ok ? 0u : 1u) | (bad ? 2u : 0u);
+}
+
+/* warp 1, pose i: c_i = L_i^-T z_i and M_i = L_i^-T G_i^T into the L record */
+UWBGO_DI void factor_helper_step(const double *__restrict__ Gn, double *__restrict__ l, bool has_prev)
+{
+    double L[21], z[6], c[6];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) L[k] = ROW(Gn, 36 + k);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) z[k] = ROW(Gn, 57 + k);
+#pragma unroll
+    for (int r = 5; r >= 0; --r) {
+        double s = z[r];
+#pragma unroll
+        for (int k = r + 1; k < 6; ++k) s = fma(-L[lo_idx(k, r)], c[k], s);
+        c[r] = s * L[lo_idx(r, r)];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ROW(l, k) = c[k];
+    if (has_prev) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double g[6], m[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) g[r] = ROW(Gn, j * 6 + r);
+#pragma unroll
+            for (int r = 5; r >= 0; --r) {
+                double s = g[r];
+#pragma unroll
+                for (int k = r + 1; k < 6; ++k) s = fma(-L[lo_idx(k, r)], m[k], s);
+                m[r] = s * L[lo_idx(r, r)];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) ROW(l, 6 + r * 6 + j) = m[r];
+        }
+    }
+}
+
+/* warp 1 after the last step: x_i = c_i - M_i x_{i-1} in ascending order and computeScale() (gen_subst_scale,
+ * chain case); x_i is left over c_i in the L record.  The L record and b of pose i + 1 are staged into shared
+ * memory (two buffers of GIT_HAND rows, tile base `stage`) while pose i is substituted. */
+UWBGO_DI double subst_scale_chain(const GenEnv &E, double *stage, int lane, bool ok, double lambda)
+{
+    const int N = E.tp->N;
+    const double *LRt = E.p.LR - lane, *HBt = E.p.HB - lane;
+    auto pf = [&](int i) {
+        double *dst = stage + (size_t)(i & 1) * GIT_HAND * TILE;
+        stage_rows(dst, LRt + (size_t)i * LR_GEN * TILE, LR_GEN, lane);
+        stage_rows(dst + LR_GEN * TILE, HBt + ((size_t)i * HR_GEN + 57) * TILE, 6, lane);
+        cp_commit();
+    };
+    __syncwarp(); /* the records were stored by the lanes of this warp */
+    pf(0);
+    double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double scale = 0.0;
+    for (int i = 0; i < N; ++i) {
+        if (i + 1 < N) {
+            pf(i + 1);
+            cp_wait<1>();
+        } else
+            cp_wait<0>();
+        __syncwarp();
+        const double *l = stage + (size_t)(i & 1) * GIT_HAND * TILE + lane;
+        double *lp = E.p.LR + (size_t)i * LR_GEN * TILE;
+        double x[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { /* subst_step<6> */
+            double v = ROW(l, r);
+            if (i > 0) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v = fma(-ROW(l, 6 + r * 6 + j), xp[j], v);
+            }
+            x[r] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) xp[k] = ok ? x[k] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ROW(lp, k) = xp[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) scale = scale + xp[k] * (lambda * xp[k] + ROW(l, LR_GEN + k));
+        __syncwarp(); /* the buffer is refilled two poses on */
+    }
+    return scale;
+}
+
+template <int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
+                        const __grid_constant__ DevWs ws, const int echi_smem)
+{
+    static_assert(NW >= 2 && NW <= 2 * GIT_HAND, "warp 0 eliminates, warp 1 follows");
+    __shared__ GitShared sh;
+    extern __shared__ __align__(16) double dyn[]; /* topology | hand-off 2 x [63][32] | staging 2 x [63][32] | chi2 terms [2E][32] */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (tp.K <= GIT_MAX_SMEM_ANTENNAS)
+        for (int k = threadIdx.x; k < 3 * tp.K; k += NW * 32) sh.ant[k] = ws.ant[k];
+    if (threadIdx.x == 0) sh.zero = 0;
+    /* topology tables first (16-byte aligned records), then the double-precision areas */
+    GitTopo tt;
+    size_t tbytes = 0;
+    {
+        unsigned char *tb = reinterpret_cast<unsigned char *>(dyn);
+        const size_t o_edges = 0, o_ops = o_edges + sizeof(EdgeRec) * (size_t)tp.E, o_opb = o_ops + sizeof(int2) * (size_t)tp.n_ops,
+                     o_se = o_opb + sizeof(int) * (size_t)(tp.N + 1);
+        tbytes = (o_se + sizeof(int) * (size_t)tp.E + 15) & ~(size_t)15;
+        EdgeRec *edges = reinterpret_cast<EdgeRec *>(tb + o_edges);
+        int2 *ops = reinterpret_cast<int2 *>(tb + o_ops);
+        int *opb = reinterpret_cast<int *>(tb + o_opb), *se = reinterpret_cast<int *>(tb + o_se);
+        const int words = (int)(sizeof(EdgeRec) / 4) * tp.E;
+        for (int k = threadIdx.x; k < words; k += NW * 32) reinterpret_cast<int *>(edges)[k] = __ldg(reinterpret_cast<const int *>(tp.edges) + k);
+        for (int k = threadIdx.x; k < tp.n_ops; k += NW * 32) ops[k] = __ldg(reinterpret_cast<const int2 *>(tp.ops + k));
+        for (int k = threadIdx.x; k <= tp.N; k += NW * 32) opb[k] = __ldg(tp.op_begin + k);
+        for (int k = threadIdx.x; k < tp.E; k += NW * 32) se[k] = __ldg(tp.slot_edge + k);
+        tt.edges = edges;
+        tt.ops = ops;
+        tt.op_begin = opb;
+        tt.slot_edge = se;
+    }
+    double *const dsm = dyn + tbytes / sizeof(double);
+    const int N = tp.N, NE = tp.E;
+    const bool valid = (int64_t)blockIdx.x * TILE + lane < ws.W; /* workspaces are padded to whole tiles */
+
+    /* the thread's view of the workspace, built where a phase needs it (a volatile zero in the lane index keeps
+     * the fifteen pointers from living in registers across the phases that do not use them) */
+    auto env = [&]() {
+        const int ln = lane + *reinterpret_cast<volatile int *>(&sh.zero);
+        GitEnv G;
+        G.E.tp = &tp;
+        G.E.cfg = &cfg;
+        G.E.p = thread_ptrs<HR_GEN, LR_GEN>(tp, ws, (int64_t)blockIdx.x * TILE + ln);
+        G.E.ant = (tp.K > 0 && tp.K <= GIT_MAX_SMEM_ANTENNAS) ? sh.ant : ws.ant;
+        G.E.ck.init(cfg.kdelta);
+        G.E.delta = cfg.jdelta;
+        G.E.scalar = 1.0 / (2.0 * cfg.jdelta);
+        G.Er = tp.Er;
+        G.Ep = tp.Ep;
+        G.Es = tp.Es;
+        G.jrec = ws.jrec + (size_t)blockIdx.x * ((size_t)tp.Er * GR_RANGE + (size_t)tp.Ep * GR_PRIOR + (size_t)tp.Es * GR_SE3) * TILE + ln;
+        return G;
+    };
+    auto echi_ptr = [&]() {
+        const int ln = lane + *reinterpret_cast<volatile int *>(&sh.zero);
+        return echi_smem ? dsm + 4 * GIT_HAND * TILE + ln : ws.echi + ((size_t)blockIdx.x * tp.E * 2) * TILE + ln;
+    };
+
+    auto chi_phase = [&](const int *who, int sel) {
+        if (who[lane]) {
+            const GitEnv G = env();
+            double *echi = echi_ptr();
+            const int b = sh.cur[lane] ^ sel;
+            const PoseBuf T{G.E.p.T(b), G.E.p.Rm(b)};
+            for (int e = warp; e < NE; e += NW) {
+                double chi, rob;
+                item_chi(G.E, tt, T, e, chi, rob);
+                ROW(echi, 2 * e) = chi;
+                ROW(echi, 2 * e + 1) = rob;
+            }
+        }
+    };
+    auto chi_sum = [&](double &p, double &r) {
+        const double *echi = echi_ptr();
+        double pp = 0.0, rr = 0.0;
+        int e = 0;
+        for (; e + 8 <= NE; e += 8) { /* loads first, then the two ordered sums */
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = ROW(echi, 2 * e + k);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                pp = pp + v[2 * k];
+                rr = rr + v[2 * k + 1];
+            }
+        }
+        for (; e < NE; ++e) {
+            pp = pp + ROW(echi, 2 * e);
+            rr = rr + ROW(echi, 2 * e + 1);
+        }
+        p = pp;
+        r = rr;
+    };
+    auto publish = [&](const LmState &st) { /* warp 0 */
+        sh.lin[lane] = (!st.done && st.need_lin) ? 1 : 0;
+        sh.cur[lane] = st.cur;
+        sh.act[lane] = st.done ? 0 : 1;
+        const unsigned g = __ballot_sync(0xffffffffu, !st.done);
+        const unsigned l = __ballot_sync(0xffffffffu, !st.done && st.need_lin);
+        if (lane == 0) {
+            sh.go = g != 0;
+            sh.anylin = l != 0;
+        }
+    };
+
+    /* initial computeActiveErrors: every real window, buffer 0 */
+    if (warp == 0) {
+        sh.cur[lane] = 0;
+        sh.act[lane] = valid ? 1 : 0;
+    }
+    __syncthreads();
+    chi_phase(sh.act, 0);
+    __syncthreads();
+    if (warp == 0) {
+        LmState st;
+        st.lambda = 0.0; st.ni = 2.0; st.stale = 0.0; st.plainCur = 0.0; st.currentChi = 0.0; st.rho = 0.0;
+        st.iterations = 0; st.trials_total = 0; st.flags = 0; st.qlast = 0; st.cur = 0; st.q = 0; st.it = 0;
+        st.need_lin = true;
+        st.done = !valid || cfg.max_iterations <= 0;
+        if (valid) chi_sum(st.plainCur, st.currentChi);
+        st.stale = st.plainCur;
+        st.store(sh, lane);
+        publish(st);
+    }
+    __syncthreads();
+
+#ifdef UWBGO_GIT_TIMING
+    long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tq = clock64();
+#define GIT_TICK(k) do { long long tn_ = clock64(); tph[k] += tn_ - tq; tq = tn_; } while (0)
+#else
+#define GIT_TICK(k)
+#endif
+    const int n6 = tp.Ep + tp.Es;
+    while (sh.go) {
+        if (sh.anylin) {
+            /* ---- J ---- */
+            if (sh.lin[lane]) {
+                const GitEnv G = env();
+                const int b = sh.cur[lane];
+                const PoseBuf T{G.E.p.T(b), G.E.p.Rm(b)};
+                const int nJ = tp.Er + n6 + tp.Er;
+                for (int u = warp; u < nJ; u += NW) {
+                    if (u < tp.Er)
+                        item_range_v0(G, tt, T, u);
+                    else if (u < tp.Er + tp.Es)
+                        item_se3(G, tt, T, u - tp.Er);
+                    else if (u < tp.Er + n6)
+                        item_prior(G, tt, T, u - tp.Er - tp.Es);
+                    else
+                        item_range_v1(G, tt, T, u - tp.Er - n6);
+                }
+            }
+            GIT_TICK(8);
+            __syncthreads();
+            GIT_TICK(0);
+            /* ---- H ---- */
+            double md = 0.0;
+            if (sh.lin[lane]) {
+                const GitEnv G = env();
+                /* the diagonal blocks, then the off-diagonal blocks */
+                for (int u = warp; u < 2 * N; u += NW) {
+                    if (u < N) {
+                        const double m = item_h_diag(G, tt, u);
+                        if (m > md) md = m;
+                    } else
+                        item_h_off(G, tt, u - N);
+                }
+            }
+            dsm[warp * TILE + lane] = md; /* H -> F: max |H_kk| over the blocks each warp assembled; the hand-off area is idle */
+            GIT_TICK(9);
+            __syncthreads();
+            GIT_TICK(1);
+        }
+        /* ---- F ---- */
+        if (warp == 0) {
+            double lambda;
+            {
+                LmState st;
+                st.load(sh, lane);
+                if (!st.done && st.need_lin) {
+                    st.stale = st.plainCur;
+                    double maxdiag = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        const double m = dsm[k * TILE + lane];
+                        if (m > maxdiag) maxdiag = m;
+                    }
+                    if (st.it == 0) {
+                        st.lambda = cfg.tau * maxdiag;
+                        st.ni = 2.0;
+                    }
+                    st.rho = 0.0;
+                    st.q = 0;
+                    st.need_lin = false;
+                    st.store(sh, lane);
+                }
+                lambda = st.lambda;
+            }
+            sh.lam[lane] = lambda;
+            __syncwarp(); /* every lane has read its maxima before the hand-off area is written */
+            const GitEnv G = env();
+            double *hand = dsm + lane, *stage = dsm + 2 * GIT_HAND * TILE;
+            const double *HBt = G.E.p.HB - lane;
+            const bool active = sh.act[lane] != 0;
+            /* one pass over the chain; the H record of pose i - 1 is staged into shared memory while pose i is
+             * eliminated.  Returns true when an active lane's operands left the range of the branch-free roots. */
+            auto sweep = [&](auto math) -> bool {
+                using MATH = decltype(math);
+                unsigned fl = 0;
+                bool redo = false;
+                stage_rows(stage + (size_t)((N - 1) & 1) * GIT_HAND * TILE, HBt + (size_t)(N - 1) * HR_GEN * TILE, HR_GEN, lane);
+                cp_commit();
+                for (int i = N - 1; i >= 0; --i) {
+                    if (i > 0) {
+                        stage_rows(stage + (size_t)((i - 1) & 1) * GIT_HAND * TILE, HBt + (size_t)(i - 1) * HR_GEN * TILE, HR_GEN, lane);
+                        cp_commit();
+                        cp_wait<1>();
+                    } else
+                        cp_wait<0>();
+                    __syncwarp();
+                    fl |= factor_main_step<MATH>(stage + (size_t)(i & 1) * GIT_HAND * TILE + lane, hand + (size_t)((i + 1) & 1) * GIT_HAND * TILE,
+                                                 hand + (size_t)(i & 1) * GIT_HAND * TILE, i + 1 < N, i > 0, lambda);
+                    if (i == 0) {
+                        sh.tok[lane] = (fl & 1u) ? 0 : 1;
+                        redo = __any_sync(0xffffffffu, active && (fl & 2u) != 0);
+                        if (lane == 0) sh.redo = redo ? 1 : 0;
+                    }
+                    bar_pair();
+                }
+                return redo;
+            };
+            if (sweep(NbMath{})) sweep(IeeeMath{}); /* a trial only writes scratch: the repeat gives the IEEE bits */
+            GIT_TICK(6);
+        } else if (warp == 1) {
+            const GitEnv G = env();
+            double *hand = dsm + lane, *stage = dsm + 2 * GIT_HAND * TILE;
+            do {
+                for (int i = N - 1; i >= 0; --i) {
+                    bar_pair();
+                    factor_helper_step(hand + (size_t)(i & 1) * GIT_HAND * TILE, G.E.p.LR + (size_t)i * LR_GEN * TILE, i > 0);
+                }
+            } while (*reinterpret_cast<volatile int *>(&sh.redo)); /* written before the last barrier of the sweep */
+            sh.tscale[lane] = subst_scale_chain(G.E, stage, lane, sh.tok[lane] != 0, sh.lam[lane]);
+        }
+        __syncthreads();
+        GIT_TICK(2);
+        /* ---- U ---- */
+        if (sh.act[lane]) {
+            const GitEnv G = env();
+            const int c = sh.cur[lane];
+            const bool lin = sh.lin[lane] != 0;
+            const PoseBuf Tc{G.E.p.T(c), G.E.p.Rm(c)}, Tn{G.E.p.T(c ^ 1), G.E.p.Rm(c ^ 1)};
+            for (int i = warp; i < N; i += NW) gen_update_pose(G.E, i, Tc, Tn, lin);
+        }
+        GIT_TICK(11);
+        __syncthreads();
+        GIT_TICK(3);
+        /* ---- C ---- */
+        chi_phase(sh.act, 1);
+        GIT_TICK(12);
+        __syncthreads();
+        GIT_TICK(4);
+        /* ---- D ---- */
+        if (warp == 0) {
+            LmState st;
+            st.load(sh, lane);
+            if (!st.done) {
+                const bool ok = sh.tok[lane] != 0;
+                if (!ok) st.flags |= UWBGO_FLAG_CHOL_FAIL;
+                double scale = sh.tscale[lane], tplain, tempChi;
+                chi_sum(tplain, tempChi);
+                st.stale = tplain;
+                if (!ok) tempChi = DBL_MAX;
+                scale = scale + 1e-3;
+                st.rho = (st.currentChi - tempChi) / scale;
+                const bool fin = isfinite(tempChi);
+                if (!fin) st.flags |= UWBGO_FLAG_NONFINITE;
+                if (st.rho > 0.0 && fin) {
+                    double t = 2.0 * st.rho - 1.0;
+                    double alpha = 1.0 - (t * t) * t;
+                    alpha = (cfg.good_hi < alpha) ? cfg.good_hi : alpha;
+                    double sf = (cfg.good_lo < alpha) ? alpha : cfg.good_lo;
+                    st.lambda = st.lambda * sf;
+                    st.ni = 2.0;
+                    st.currentChi = tempChi;
+                    st.plainCur = tplain;
+                    st.cur ^= 1;
+                } else {
+                    st.lambda = st.lambda * st.ni;
+                    st.ni = st.ni * 2.0;
+                }
+                ++st.q;
+                ++st.trials_total;
+                if (!(st.rho < 0.0 && st.q < cfg.max_trials)) { /* this iteration is over */
+                    ++st.iterations;
+                    st.qlast = st.q;
+                    if (st.q == cfg.max_trials || st.rho == 0.0) {
+                        st.flags |= UWBGO_FLAG_TERMINATED;
+                        st.done = true;
+                    } else if (++st.it >= cfg.max_iterations) {
+                        st.done = true;
+                    } else {
+                        st.need_lin = true;
+                    }
+                }
+                st.store(sh, lane);
+            }
+            publish(st);
+        }
+        __syncthreads();
+        GIT_TICK(5);
+    }
+#ifdef UWBGO_GIT_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 2)
+        printf("tile %d cycles (warp 0's own items + wait at the barrier): J %lld + %lld  H %lld + %lld  F %lld + %lld  U %lld + %lld  C %lld + %lld  D %lld\n",
+               (int)blockIdx.x, tph[8], tph[0], tph[9], tph[1], tph[6], tph[2], tph[11], tph[3], tph[12], tph[4], tph[5]);
+#endif
+
+    if (warp == 0 && valid) {
+        LmState st;
+        st.load(sh, lane);
+        double *chi2_out = ws.chi2 + (int64_t)blockIdx.x * 4 * TILE + lane;
+        int32_t *status_out = ws.status + (int64_t)blockIdx.x * 4 * TILE + lane;
+        ROW(chi2_out, 0) = st.plainCur;
+        ROW(chi2_out, 1) = st.currentChi;
+        ROW(chi2_out, 2) = st.stale;
+        ROW(chi2_out, 3) = st.lambda;
+        ROW(status_out, 0) = st.iterations;
+        ROW(status_out, 1) = st.trials_total;
+        ROW(status_out, 2) = st.flags;
+        ROW(status_out, 3) = st.qlast;
+    }
+    {
+        const GitEnv G = env();
+        if (valid && sh.cur[lane]) { /* result always leaves in buffer 0 */
+            for (int r = warp; r < N * 3; r += NW) ROW(G.E.p.T0, r) = ROW(G.E.p.T1, r);
+            for (int r = warp; r < N * 9; r += NW) ROW(G.E.p.Rm0, r) = ROW(G.E.p.Rm1, r);
+        }
+        if (echi_smem) { /* the last trial's terms stay behind for uwbgo_result::edge_chi2 */
+            const double *echi = echi_ptr();
+            double *echi_g = ws.echi + ((size_t)blockIdx.x * tp.E * 2) * TILE + lane;
+            for (int k = warp; k < 2 * NE; k += NW) ROW(echi_g, k) = ROW(echi, k);
+        }
+    }
+}
+
+}  // namespace
+
+size_t general_items_jrec_rows(const DevTopo &t) { return (size_t)t.Er * GR_RANGE + (size_t)t.Ep * GR_PRIOR + (size_t)t.Es * GR_SE3; }
+
+#ifndef UWBGO_GIT_WARPS
+#define UWBGO_GIT_WARPS 8
+#endif
+#ifndef UWBGO_GIT_MINB
+#define UWBGO_GIT_MINB 2
+#endif
+
+/* shared memory of one CTA: topology tables | hand-off 2 x 63 rows | staging 2 x 63 rows | per-edge chi2 terms
+ * (the last only when two CTAs still fit an SM with them) */
+static size_t git_topo_bytes(const DevTopo &t)
+{
+    return (sizeof(EdgeRec) * (size_t)t.E + sizeof(int2) * (size_t)t.n_ops + sizeof(int) * (size_t)(t.N + 1 + t.E) + 15) & ~(size_t)15;
+}
+constexpr size_t GIT_SMEM_TWO = 115000;     /* dynamic + static bytes at which two CTAs share an SM */
+constexpr size_t GIT_SMEM_MAX = 200 * 1024; /* beyond this the CTA kernel takes the batch           */
+constexpr size_t GIT_HAND_BYTES = 4 * (size_t)GIT_HAND * TILE * sizeof(double);
+
+bool general_items_ok(const DevTopo &t, const DevWs &ws)
+{
+    return !t.fast && !t.tree && t.N >= 1 && ws.jrec != nullptr && ws.echi != nullptr && ws.LR != nullptr &&
+           git_topo_bytes(t) + GIT_HAND_BYTES + sizeof(GitShared) <= GIT_SMEM_MAX;
+}
+
+cudaError_t launch_solve_general_items(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st)
+{
+    const size_t echi = 2 * (size_t)topo.E * TILE * sizeof(double);
+    const size_t base = git_topo_bytes(topo) + GIT_HAND_BYTES;
+#ifndef UWBGO_GIT_ECHI_SMEM
+#define UWBGO_GIT_ECHI_SMEM 0 /* 1: the per-edge chi2 terms of the tile in shared memory (39 KB on C4a).  Measured slower: the
+                               * carve-out then leaves ~28 KB of L1 for two CTAs, and every spilled register becomes an L2
+                               * round trip (C4a, 8,192 windows: 11.2 ms with, 10.0 ms without; 65,536: 85.6 / 77.6 ms) */
+#endif
+    const int echi_smem = UWBGO_GIT_ECHI_SMEM && base + echi + sizeof(GitShared) <= GIT_SMEM_TWO;
+    const size_t sm = base + (echi_smem ? echi : 0);
+    auto kern = lm_general_items_kernel<UWBGO_GIT_WARPS, UWBGO_GIT_MINB>;
+    static bool configured[64] = {false}; /* the attribute is per device */
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GIT_SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = true;
+    }
+    kern<<<(unsigned)n_tiles(ws.W), UWBGO_GIT_WARPS * 32, sm, st>>>(topo, cfg, ws, echi_smem);
+    return cudaGetLastError();
+}
+
+}  // namespace uwbgo

@@ -119,6 +119,7 @@ struct DevWs {
     double *chi2;       /* [tile][4][32] (solve) or [tile][2][32]     */
     int32_t *status;    /* [tile][4][32]                              */
     double *echi;       /* [tile][E*2][32] per-edge chi2 | rho0 (general CTA kernel) */
+    double *jrec;       /* [tile][general_items_jrec_rows][32] per-edge linearisation records (general ITEM kernel) */
     int64_t W_batch;    /* windows of the whole call when this launch is one chunk of a pipelined batch whose chunks
                          * run concurrently (0: this launch is the batch); picks the CHAIN kernel's warps per tile */
     int32_t *stale_sel; /* [tile][32] or NULL.  Non-NULL = the caller wants uwbgo_result::edge_chi2: the      */
@@ -173,6 +174,10 @@ cudaError_t launch_unpack(const XposeJobs &jobs, cudaStream_t st);
 cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st);
 cudaError_t launch_linearize(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws,
                              cudaStream_t st);
+/* GENERAL path, ITEM kernel (uwbgo_general_items.cu): chains of 6x6 blocks, 8 warps per tile at 128 registers */
+size_t general_items_jrec_rows(const DevTopo &topo);
+bool general_items_ok(const DevTopo &topo, const DevWs &ws);
+cudaError_t launch_solve_general_items(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws, cudaStream_t st);
 /* WINDOW path: whole LM solve, one CTA per window, state in shared memory (uwbgo_window.cu) */
 int window_path_candidates(int64_t W); /* LM trials evaluated speculatively per round for a batch of W */
 size_t window_path_smem_bytes(const DevTopo &topo, int candidates);

@@ -31,6 +31,8 @@
  *
  * Compile with --fmad=false (see uwbgo_math.cuh).
  */
+#include <cstdlib>
+#include <cstring>
 #include "uwbgo_fast.cuh"
 #include "uwbgo_general.cuh"
 
@@ -1185,14 +1187,26 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
 #ifndef UWBGO_GEN_CTA
 #define UWBGO_GEN_CTA 1 /* 1: one CTA per tile, phases split over its warps; 0: one thread per window */
 #endif
+#ifndef UWBGO_GEN_ITEMS
+#define UWBGO_GEN_ITEMS 1 /* 1: chains take the ITEM kernel (uwbgo_general_items.cu); UWBGO_GENERAL_KERNEL=cta in the
+                           * environment selects the CTA kernel at run time (A/B runs, tests of both) */
+#endif
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const unsigned tiles = (unsigned)n_tiles(ws.W);
+        if (UWBGO_GEN_CTA && UWBGO_GEN_ITEMS && general_items_ok(topo, ws)) {
+            /* chains beyond one tile per SM take the ITEM kernel (8 warps per tile at 128 registers, two tiles per
+             * SM); up to one tile per SM the 8-warp CTA kernel below has the SM to itself and is faster (2,048 C4a
+             * windows: 6.1 vs 6.8 ms).  UWBGO_GENERAL_KERNEL=cta | items overrides the choice (A/B runs, tests). */
+            const char *sel = getenv("UWBGO_GENERAL_KERNEL");
+            const bool items = sel ? strcmp(sel, "items") == 0 : (int)tiles > sms;
+            if (items && !(sel && strcmp(sel, "cta") == 0)) return launch_solve_general_items(topo, cfg, ws, st);
+        }
         if (UWBGO_GEN_CTA && ws.echi) {
-            static int sms = 0;
-            if (!sms) {
-                int dev = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            }
-            const unsigned tiles = (unsigned)n_tiles(ws.W);
 #ifndef UWBGO_GCTA_WIDE
 #define UWBGO_GCTA_WIDE 1 /* 8-warp CTAs for batches of at most one tile per SM */
 #endif

@@ -13,7 +13,8 @@ for r in rows[h + 1:]:
 import os
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd="/tmp", capture_output=True)
 import glob
-cubin = sorted(glob.glob("/tmp/*uwbgo_kernels*.cubin"))[-1]
+pat = sys.argv[5] if len(sys.argv) > 5 else "uwbgo_kernels"
+cubin = sorted(glob.glob("/tmp/*" + pat + "*.cubin"))[-1]
 dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout
 cur, infn, lines = None, False, []
 for ln in dis.splitlines():

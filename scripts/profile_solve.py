@@ -18,6 +18,7 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--kind", default="uwb_only", choices=["uwb_only", "imu_lidar", "twist"])
 ap.add_argument("--stage", default="solve", choices=["solve", "linearize"])
+ap.add_argument("--window-path", type=int, default=-1, help="force the WINDOW path for batches up to this many windows")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 if a.kind == "uwb_only":
@@ -28,6 +29,8 @@ else:
     topo, batch, _ = synthetic.uwb_twist(a.windows, a.poses, a.anchors)
 cfg = Config(max_iterations=a.iters)
 s = Solver(0)
+if a.window_path >= 0:
+    s.set_window_path(a.window_path)
 W, N = batch.n_windows, topo.n_poses
 keep = {}
 cb = _ffi.CBatch()

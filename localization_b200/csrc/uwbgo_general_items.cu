@@ -26,6 +26,18 @@
 #include "uwbgo_general.cuh"
 #ifdef UWBGO_GIT_TIMING
 #include <cstdio>
+/* (clock64() may be moved across barriers by the compiler; the volatile asm with a memory clobber may not) */
+__device__ __forceinline__ long long git_clk()
+{
+    /* the clock is read behind a shared-memory load whose value it formally depends on: a barrier releases the
+     * warp's next memory access, not its next instruction, and a bare clock read after bar.sync returns early */
+    extern __shared__ double git_clk_dyn[];
+    long long t;
+    unsigned z;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(z) : "r"((uint32_t)__cvta_generic_to_shared(git_clk_dyn)) : "memory");
+    asm volatile("{\n\t.reg .u64 c;\n\tmov.u64 c, %%clock64;\n\tand.b32 %1, %1, 0;\n\tcvt.u64.u32 %0, %1;\n\tadd.u64 %0, %0, c;\n\t}" : "=l"(t), "+r"(z)::"memory");
+    return t;
+}
 #endif
 
 namespace uwbgo {
@@ -51,6 +63,9 @@ struct GitShared {
     int cur[TILE];                    /* D -> all: which pose buffer holds the estimate                   */
     int act[TILE];                    /* D -> all: window still being optimised                           */
     int go, anylin, redo;
+    double rinc[6][9];                /* the six rotation increments of the numeric Jacobians: fromVectorMQT(+-delta e_k) */
+    int diag;                         /* every prior information matrix of the tile is diagonal (bit patterns) */
+    int ctr[4];                       /* next item of the J, H, U, C phase: the warps of the tile draw their items from a queue */
     int zero;                         /* 0, read through a volatile pointer: keeps per-phase address arithmetic per phase */
     /* LM state of every window, parked here between the phases of warp 0 */
     double lm_d[6][TILE]; /* lambda, ni, stale, plainCur, currentChi, rho */
@@ -104,6 +119,7 @@ UWBGO_DI void stage_rows(double *dst, const double *src, int rows, int lane)
 struct GitEnv {
     GenEnv E;
     double *jrec; /* this lane's column of the tile's linearisation records */
+    const double *rinc; /* [6][9] rotation increments of the numeric Jacobians (shared memory) */
     int Er, Ep, Es;
 };
 
@@ -125,11 +141,168 @@ UWBGO_DI EdgeRec smem_edge(const EdgeRec *e)
     return r;
 }
 
+/* The information matrix of an EdgeSE3Prior.  The priors Localization builds are diagonal (lidar: one entry,
+ * localization.cpp:478-479; IMU: three, localization.cpp:515-518), and a tile whose prior information matrices all have
+ * exactly +0.0 off the diagonal (checked once per launch, bit patterns) reads the six diagonal rows only: the thirty
+ * zeros become literals, every product and sum of chi2_6 / jt_omega is still executed, so the bits are those of the
+ * dense arithmetic.  Anything else takes the dense reads. */
+template <bool DIAG>
+UWBGO_DI double info_at(const double *__restrict__ O, int k, int c)
+{
+    if (DIAG) return k == c ? ROW(O, 7 * k) : 0.0;
+    return ROW(O, 6 * k + c);
+}
+template <bool DIAG>
+UWBGO_DI double chi2_6_t(const double *__restrict__ O, const double *e, double *Oe)
+{
+    double chi = 0.0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double s = info_at<DIAG>(O, r, 0) * e[0];
+#pragma unroll
+        for (int c = 1; c < 6; ++c) s = s + info_at<DIAG>(O, r, c) * e[c];
+        Oe[r] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) chi = chi + e[r] * Oe[r];
+    return chi;
+}
+template <bool DIAG>
+UWBGO_DI void jt_omega_t(const double *J, const double *__restrict__ O, bool robust, double r1, double *JtO)
+{
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double ow[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double v = info_at<DIAG>(O, k, c);
+            ow[k] = robust ? r1 * v : v;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double s = J[r] * ow[0];
+#pragma unroll
+            for (int k = 1; k < 6; ++k) s = fma(J[6 * k + r], ow[k], s);
+            JtO[6 * r + c] = s;
+        }
+    }
+}
+
+/* gen_jac_v0 / gen_jac_v1 of uwbgo_general.cuh with the roots of a math policy M (NbMath: branch-free, so that the
+ * twelve perturbed residuals of an edge interleave; an operand outside its range raises `bad` and the item is
+ * evaluated again with IeeeMath: same bits) */
+template <class M, bool SECOND = false>
+UWBGO_DI void jac_v0_m(const GenEnv &E, const double *rinc, const Pose &X, int ant, const double *Q, double d, int c0, int base,
+                       double *J, unsigned &bad)
+{
+    const int mod = E.cfg->orth_mod;
+    double o[3] = {0.0, 0.0, 0.0};
+    if (ant > 0) {
+        o[0] = E.ant[3 * (ant - 1)];
+        o[1] = E.ant[3 * (ant - 1) + 1];
+        o[2] = E.ant[3 * (ant - 1) + 2];
+    }
+    int call = (c0 + base) % mod;
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+        double epm[2];
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            if (++call == mod) call = 0;
+            const double v = sg == 0 ? E.delta : -E.delta;
+            double tp[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) tp[r] = X.R[3 * r + dd] * v + X.t[r];
+            double P[3];
+            if (ant > 0) {
+                if (call == 0) {
+                    double Rp[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Rp[k] = X.R[k];
+                    orthogonalize(Rp);
+                    mat3_vec_add(Rp, o, tp, P);
+                } else
+                    mat3_vec_add(X.R, o, tp, P);
+            } else {
+                P[0] = tp[0]; P[1] = tp[1]; P[2] = tp[2];
+            }
+            epm[sg] = SECOND ? d - dist3m<M>(Q[0], Q[1], Q[2], P[0], P[1], P[2], bad)
+                             : d - dist3m<M>(P[0], P[1], P[2], Q[0], Q[1], Q[2], bad);
+        }
+        J[dd] = E.scalar * (epm[0] - epm[1]);
+    }
+    if (ant > 0) {
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd) {
+            double epm[2];
+#pragma unroll
+            for (int sg = 0; sg < 2; ++sg) {
+                if (++call == mod) call = 0;
+                /* the increment depends on delta alone: the six matrices are formed once per CTA (same operations) */
+                double Rinc[9], Rp[9], P[3];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Rinc[k] = rinc[9 * (2 * dd + sg) + k];
+                mat3_mul(X.R, Rinc, Rp);
+                if (call == 0) orthogonalize(Rp);
+                mat3_vec_add(Rp, o, X.t, P);
+                epm[sg] = SECOND ? d - dist3m<M>(Q[0], Q[1], Q[2], P[0], P[1], P[2], bad)
+                                 : d - dist3m<M>(P[0], P[1], P[2], Q[0], Q[1], Q[2], bad);
+            }
+            J[3 + dd] = E.scalar * (epm[0] - epm[1]);
+        }
+    } else {
+        J[3] = 0.0; J[4] = 0.0; J[5] = 0.0;
+    }
+}
+template <class M>
+UWBGO_DI void jac_v1_m(const GenEnv &E, const double *P0, const Pose &X, double d, double *J, unsigned &bad)
+{
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+        double epm[2];
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+            const double v = sg == 0 ? E.delta : -E.delta;
+            double tp[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) tp[r] = X.R[3 * r + dd] * v + X.t[r];
+            epm[sg] = d - dist3m<M>(P0[0], P0[1], P0[2], tp[0], tp[1], tp[2], bad);
+        }
+        J[dd] = E.scalar * (epm[0] - epm[1]);
+    }
+    J[3] = 0.0; J[4] = 0.0; J[5] = 0.0;
+}
+/* toVectorMQT(Zinv * Xi^-1 * Xj) (se3_error of uwbgo_general.cuh) */
+template <class M>
+UWBGO_DI void se3_error_m(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *e, unsigned &bad)
+{
+    Pose Xi_inv, T, Dl;
+    pose_inv(Xi, Xi_inv);
+    pose_mul(Zinv, Xi_inv, T);
+    pose_mul(T, Xj, Dl);
+    double q[4];
+    R_to_quat_m<M>(Dl.R, q, bad);
+    e[0] = Dl.t[0]; e[1] = Dl.t[1]; e[2] = Dl.t[2];
+    e[3] = q[0]; e[4] = q[1]; e[5] = q[2];
+}
+
+/* the next item of a phase for this warp (items are queued heaviest kind first; a static round robin leaves warps
+ * idle: the edges of a pose repeat with a period that divides the warp count, so every warp would always get the
+ * same kind -- measured on C4a: the residual phase took 6.1 M cycles with 5.2 M of them one warp's wait) */
+UWBGO_DI int next_item(int *ctr, int lane)
+{
+    int u = 0;
+    if (lane == 0) u = atomicAdd(ctr, 1);
+    return __shfl_sync(0xffffffffu, u, 0);
+}
+
 /* ---- J items ------------------------------------------------------------------------------------------------ */
 
 /* range edge, slot k: error, weights and the numeric Jacobian wrt vertex 0 (gen_linearize_pose_acc, role 0) */
-UWBGO_DI void item_range_v0(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int k)
+template <class M>
+UWBGO_DI unsigned item_range_v0(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int k)
 {
+    unsigned bad = 0;
     const GenEnv &E = G.E;
     const EdgeRec er = smem_edge(tt.edges + tt.slot_edge[k]);
     double *rec = G.jrec + (size_t)k * GR_RANGE * TILE;
@@ -148,27 +321,30 @@ UWBGO_DI void item_range_v0(const GitEnv &G, const GitTopo &tt, const PoseBuf &T
         const double *tb = T.t + (size_t)er.b * 3 * TILE;
         Q[0] = ROW(tb, 0); Q[1] = ROW(tb, 1); Q[2] = ROW(tb, 2);
     }
-    const double err = d - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
+    const double err = d - dist3m<M>(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2], bad);
     const double Oe = info * err;
     double omega_r = -Oe, Ow = info;
     if (er.robust) {
-        const double r1 = E.ck.rho1(err * Oe);
+        const double r1 = E.ck.rho1m<M>(err * Oe, bad);
         omega_r = omega_r * r1;
         Ow = r1 * info;
     }
-    gen_jac_v0(E, Xa, er.ant, Q, d, E.p.cnt[(size_t)er.a * TILE], er.base_a, A);
+    jac_v0_m<M>(E, G.rinc, Xa, er.ant, Q, d, E.p.cnt[(size_t)er.a * TILE], er.base_a, A, bad);
 #pragma unroll
     for (int j = 0; j < 6; ++j) ROW(rec, j) = A[j];
     ROW(rec, 12) = Ow;
     ROW(rec, 13) = omega_r;
+    return bad;
 }
 
 /* pose-pose range edge, slot k: numeric Jacobian wrt vertex 1 (gen_linearize_pose_acc, role 1) */
-UWBGO_DI void item_range_v1(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int k)
+template <class M>
+UWBGO_DI unsigned item_range_v1(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int k)
 {
+    unsigned bad = 0;
     const GenEnv &E = G.E;
     const EdgeRec er = smem_edge(tt.edges + tt.slot_edge[k]);
-    if (er.kind != UWBGO_EDGE_RANGE_POSE) return;
+    if (er.kind != UWBGO_EDGE_RANGE_POSE) return 0;
     double *rec = G.jrec + (size_t)k * GR_RANGE * TILE;
     const double d = ROW(E.p.rd, er.slot);
     Pose Xa, Xb;
@@ -177,11 +353,12 @@ UWBGO_DI void item_range_v1(const GitEnv &G, const GitTopo &tt, const PoseBuf &T
     double P0[3], B[6];
     offset_point(E, Xa, er.ant, P0);
     if (er.ant_b > 0)
-        gen_jac_v0<true>(E, Xb, er.ant_b, P0, d, E.p.cnt[(size_t)er.b * TILE], er.base_b, B);
+        jac_v0_m<M, true>(E, G.rinc, Xb, er.ant_b, P0, d, E.p.cnt[(size_t)er.b * TILE], er.base_b, B, bad);
     else
-        gen_jac_v1(E, P0, Xb, d, B);
+        jac_v1_m<M>(E, P0, Xb, d, B, bad);
 #pragma unroll
     for (int j = 0; j < 6; ++j) ROW(rec, 6 + j) = B[j];
+    return bad;
 }
 
 /* J^T Ow of a 6-D edge (jt_omega of uwbgo_general.cuh), column by column, straight into the record: J is in
@@ -208,8 +385,10 @@ UWBGO_DI void store_jto(const double *J, const double *__restrict__ O, bool robu
 
 /* EdgeSE3Prior, slot s: the edge touches one pose, so its whole contribution to H_ii and b_i is formed here
  * (error, rho1, omega_r, J, J^T Ow, then the sums of acc6_b / acc6_diag) and the H item only adds it */
-UWBGO_DI void item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int s)
+template <class M, bool DIAG>
+UWBGO_DI unsigned item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int s)
 {
+    unsigned bad = 0;
     const GenEnv &E = G.E;
     const EdgeRec er = smem_edge(tt.edges + tt.slot_edge[G.Er + s]);
     double *rec = G.jrec + ((size_t)G.Er * GR_RANGE + (size_t)s * GR_PRIOR) * TILE;
@@ -218,11 +397,12 @@ UWBGO_DI void item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, i
     load_Zinv(E.p.pZ, er.slot, Zinv);
     pose_mul(Zinv, Xi, Dl);
     double q[4], e6[6], Oe[6];
-    R_to_quat(Dl.R, q);
+    R_to_quat_m<M>(Dl.R, q, bad);
     e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
     e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
-    const double chi = chi2_6(E.p.pI, er.slot, e6, Oe);
-    const double r1 = er.robust ? E.ck.rho1(chi) : 1.0;
+    const double *O = E.p.pI + (size_t)er.slot * 36 * TILE;
+    const double chi = chi2_6_t<DIAG>(O, e6, Oe);
+    const double r1 = er.robust ? E.ck.rho1m<M>(chi, bad) : 1.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         Oe[k] = -Oe[k];
@@ -243,7 +423,7 @@ UWBGO_DI void item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, i
         for (int k = 1; k < 6; ++k) v = fma(J[6 * k + r], Oe[k], v);
         ROW(rec, 21 + r) = v;
     }
-    jt_omega(J, E.p.pI + (size_t)er.slot * 36 * TILE, er.robust != 0, r1, JtO);
+    jt_omega_t<DIAG>(J, O, er.robust != 0, r1, JtO);
 #pragma unroll
     for (int r = 0; r < 6; ++r) /* acc6_diag */
 #pragma unroll
@@ -253,6 +433,7 @@ UWBGO_DI void item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, i
             for (int k = 1; k < 6; ++k) v = fma(JtO[6 * r + k], J[6 * k + c], v);
             ROW(rec, up_idx(6, r, c)) = v;
         }
+    return bad;
 }
 
 /* EdgeSE3, slot s: error, rho1, omega_r and both analytic Jacobians */
@@ -424,9 +605,37 @@ UWBGO_DI void item_h_off(const GitEnv &G, const GitTopo &tt, int i)
     for (int k = 0; k < 36; ++k) ROW(h, 21 + k) = ho[k];
 }
 
-/* ---- C item: computeError + chi2 of edge e (gen_edge_chi with the information matrix streamed) ---------------- */
-UWBGO_DI void item_chi(const GenEnv &E, const GitTopo &tt, const PoseBuf &T, int e, double &chi_out, double &rob_out)
+/* ---- U item: estimate (+) x_i into the trial buffer, oplus counter advanced (gen_update_pose with the branch-free
+ * root first) ---- */
+UWBGO_DI void item_update(const GenEnv &E, int i, const PoseBuf &Tc, const PoseBuf &Tn, bool linearised)
 {
+    const double *lp = E.p.LR + (size_t)i * LR_GEN * TILE;
+    double x[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = ROW(lp, k);
+    Pose X;
+    load_pose(Tc, i, X);
+    int c = E.p.cnt[(size_t)i * TILE];
+    /* the numeric Jacobians of this iteration's buildSystem advanced the counter first */
+    if (linearised) c = (c + __ldg(E.tp->num_calls + i)) % E.cfg->orth_mod;
+    Pose Q = X;
+    int cq = c;
+    unsigned bad = 0;
+    pose_oplus_m<NbMath>(Q, x, cq, E.cfg->orth_mod, bad);
+    if (bad) {
+        Q = X;
+        cq = c;
+        pose_oplus_m<IeeeMath>(Q, x, cq, E.cfg->orth_mod, bad);
+    }
+    E.p.cnt[(size_t)i * TILE] = cq;
+    store_pose(Tn, i, Q);
+}
+
+/* ---- C item: computeError + chi2 of edge e (gen_edge_chi with the information matrix streamed) ---------------- */
+template <class M, bool DIAG>
+UWBGO_DI unsigned item_chi(const GenEnv &E, const GitTopo &tt, const PoseBuf &T, int e, double &chi_out, double &rob_out)
+{
+    unsigned bad = 0;
     const EdgeRec er = smem_edge(tt.edges + e);
     double chi;
     if (er.kind == UWBGO_EDGE_RANGE_ANCHOR || er.kind == UWBGO_EDGE_RANGE_POSE) {
@@ -444,7 +653,7 @@ UWBGO_DI void item_chi(const GenEnv &E, const GitTopo &tt, const PoseBuf &T, int
             const double *tb = T.t + (size_t)er.b * 3 * TILE;
             Q[0] = ROW(tb, 0); Q[1] = ROW(tb, 1); Q[2] = ROW(tb, 2);
         }
-        const double err = ROW(E.p.rd, er.slot) - dist3(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2]);
+        const double err = ROW(E.p.rd, er.slot) - dist3m<M>(P0[0], P0[1], P0[2], Q[0], Q[1], Q[2], bad);
         const double Oe = ROW(E.p.ri, er.slot) * err;
         chi = err * Oe;
     } else if (er.kind == UWBGO_EDGE_PRIOR) {
@@ -453,21 +662,22 @@ UWBGO_DI void item_chi(const GenEnv &E, const GitTopo &tt, const PoseBuf &T, int
         load_Zinv(E.p.pZ, er.slot, Zinv);
         pose_mul(Zinv, X, Dl);
         double q[4], e6[6], Oe[6];
-        R_to_quat(Dl.R, q);
+        R_to_quat_m<M>(Dl.R, q, bad);
         e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
         e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
-        chi = chi2_6(E.p.pI, er.slot, e6, Oe);
+        chi = chi2_6_t<DIAG>(E.p.pI + (size_t)er.slot * 36 * TILE, e6, Oe);
     } else {
         Pose Zinv, Xi, Xj;
         load_pose(T, er.a, Xi);
         load_pose(T, er.b, Xj);
         load_Zinv(E.p.sZ, er.slot, Zinv);
         double e6[6], Oe[6];
-        se3_error(Zinv, Xi, Xj, e6);
+        se3_error_m<M>(Zinv, Xi, Xj, e6, bad);
         chi = chi2_6(E.p.sI, er.slot, e6, Oe);
     }
     chi_out = chi;
-    rob_out = er.robust ? E.ck.rho0(chi) : chi;
+    rob_out = er.robust ? E.ck.rho0m<M>(chi, bad) : chi;
+    return bad;
 }
 
 /* ---- F: the elimination chain on warp 0, the back-substitutions of every step on warp 1 ---------------------- */
@@ -662,7 +872,16 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (tp.K <= GIT_MAX_SMEM_ANTENNAS)
         for (int k = threadIdx.x; k < 3 * tp.K; k += NW * 32) sh.ant[k] = ws.ant[k];
-    if (threadIdx.x == 0) sh.zero = 0;
+    if (threadIdx.x < 6) { /* increment_R of uwbgo_math.cuh on (+-delta) e_k, k = threadIdx.x / 2 */
+        double q[3] = {0.0, 0.0, 0.0};
+        q[threadIdx.x >> 1] = (threadIdx.x & 1) ? -cfg.jdelta : cfg.jdelta;
+        increment_R(q, sh.rinc[threadIdx.x]);
+    }
+    if (threadIdx.x == 0) {
+        sh.zero = 0;
+        sh.ctr[0] = sh.ctr[1] = sh.ctr[2] = sh.ctr[3] = 0;
+        sh.diag = 1;
+    }
     /* topology tables first (16-byte aligned records), then the double-precision areas */
     GitTopo tt;
     size_t tbytes = 0;
@@ -700,33 +919,44 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
         G.E.ck.init(cfg.kdelta);
         G.E.delta = cfg.jdelta;
         G.E.scalar = 1.0 / (2.0 * cfg.jdelta);
+        G.rinc = &sh.rinc[0][0];
         G.Er = tp.Er;
         G.Ep = tp.Ep;
         G.Es = tp.Es;
         G.jrec = ws.jrec + (size_t)blockIdx.x * ((size_t)tp.Er * GR_RANGE + (size_t)tp.Ep * GR_PRIOR + (size_t)tp.Es * GR_SE3) * TILE + ln;
         return G;
     };
-    auto echi_ptr = [&]() {
+    /* per-edge chi2 terms: always to the workspace (uwbgo_result::edge_chi2 reads the last trial's there), and, when
+     * they fit, also into the hand-off / staging area, which is idle between the C and D phases: the ordered sums of
+     * D then read shared memory instead of making fifteen L2 round trips */
+    auto echi_glob = [&]() {
         const int ln = lane + *reinterpret_cast<volatile int *>(&sh.zero);
-        return echi_smem ? dsm + 4 * GIT_HAND * TILE + ln : ws.echi + ((size_t)blockIdx.x * tp.E * 2) * TILE + ln;
+        return ws.echi + ((size_t)blockIdx.x * tp.E * 2) * TILE + ln;
     };
 
     auto chi_phase = [&](const int *who, int sel) {
-        if (who[lane]) {
-            const GitEnv G = env();
-            double *echi = echi_ptr();
-            const int b = sh.cur[lane] ^ sel;
-            const PoseBuf T{G.E.p.T(b), G.E.p.Rm(b)};
-            for (int e = warp; e < NE; e += NW) {
+        const bool on = who[lane] != 0, diag = sh.diag != 0;
+        const GitEnv G = env();
+        double *echi = echi_glob(), *echi_s = dsm + lane;
+        const int b = sh.cur[lane] ^ sel;
+        const PoseBuf T{G.E.p.T(b), G.E.p.Rm(b)};
+        for (int u = next_item(&sh.ctr[3], lane); u < NE; u = next_item(&sh.ctr[3], lane)) {
+            const int e = tt.slot_edge[NE - 1 - u]; /* 6-D edges first: slots are ordered range | prior | se3 */
+            if (on) {
                 double chi, rob;
-                item_chi(G.E, tt, T, e, chi, rob);
+                if (diag ? item_chi<NbMath, true>(G.E, tt, T, e, chi, rob) : item_chi<NbMath, false>(G.E, tt, T, e, chi, rob))
+                    item_chi<IeeeMath, false>(G.E, tt, T, e, chi, rob);
                 ROW(echi, 2 * e) = chi;
                 ROW(echi, 2 * e + 1) = rob;
+                if (echi_smem) {
+                    ROW(echi_s, 2 * e) = chi;
+                    ROW(echi_s, 2 * e + 1) = rob;
+                }
             }
         }
     };
     auto chi_sum = [&](double &p, double &r) {
-        const double *echi = echi_ptr();
+        const double *echi = echi_smem ? dsm + lane : echi_glob();
         double pp = 0.0, rr = 0.0;
         int e = 0;
         for (; e + 8 <= NE; e += 8) { /* loads first, then the two ordered sums */
@@ -755,9 +985,23 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
         if (lane == 0) {
             sh.go = g != 0;
             sh.anylin = l != 0;
+            sh.ctr[0] = sh.ctr[1] = sh.ctr[2] = sh.ctr[3] = 0; /* every queue is drained: the next round starts over */
         }
     };
 
+    /* are the prior information matrices of this tile diagonal?  (one pass over them; see info_at) */
+    __syncthreads();
+    {
+        const GitEnv G = env();
+        bool ok = true;
+        for (int sl = warp; sl < tp.Ep; sl += NW) {
+            const double *O = G.E.p.pI + (size_t)sl * 36 * TILE;
+#pragma unroll
+            for (int k = 0; k < 36; ++k)
+                if (k % 7 != 0 && __double_as_longlong(ROW(O, k)) != 0) ok = false;
+        }
+        if (!__all_sync(0xffffffffu, ok || !valid) && lane == 0) atomicAnd(&sh.diag, 0);
+    }
     /* initial computeActiveErrors: every real window, buffer 0 */
     if (warp == 0) {
         sh.cur[lane] = 0;
@@ -780,8 +1024,8 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
     __syncthreads();
 
 #ifdef UWBGO_GIT_TIMING
-    long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tq = clock64();
-#define GIT_TICK(k) do { long long tn_ = clock64(); tph[k] += tn_ - tq; tq = tn_; } while (0)
+    long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tq = git_clk();
+#define GIT_TICK(k) do { long long tn_ = git_clk(); tph[k] += tn_ - tq; tq = tn_; } while (0)
 #else
 #define GIT_TICK(k)
 #endif
@@ -789,20 +1033,27 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
     while (sh.go) {
         if (sh.anylin) {
             /* ---- J ---- */
-            if (sh.lin[lane]) {
+            {
+                const bool on = sh.lin[lane] != 0, diag = sh.diag != 0;
                 const GitEnv G = env();
                 const int b = sh.cur[lane];
                 const PoseBuf T{G.E.p.T(b), G.E.p.Rm(b)};
-                const int nJ = tp.Er + n6 + tp.Er;
-                for (int u = warp; u < nJ; u += NW) {
-                    if (u < tp.Er)
-                        item_range_v0(G, tt, T, u);
-                    else if (u < tp.Er + tp.Es)
-                        item_se3(G, tt, T, u - tp.Er);
-                    else if (u < tp.Er + n6)
-                        item_prior(G, tt, T, u - tp.Er - tp.Es);
-                    else
-                        item_range_v1(G, tt, T, u - tp.Er - n6);
+                /* heaviest kind first: EdgeSE3, priors, range edges (vertex 0, then vertex 1).  Branch-free
+                 * arithmetic first; an item whose operands it flags is evaluated again with the IEEE sequences (an
+                 * item only writes its own record) */
+                const int nJ = n6 + tp.Er + tp.Er;
+                for (int u = next_item(&sh.ctr[0], lane); u < nJ; u = next_item(&sh.ctr[0], lane)) {
+                    if (!on) continue;
+                    if (u < tp.Es)
+                        item_se3(G, tt, T, u);
+                    else if (u < n6) {
+                        if (diag ? item_prior<NbMath, true>(G, tt, T, u - tp.Es) : item_prior<NbMath, false>(G, tt, T, u - tp.Es))
+                            item_prior<IeeeMath, false>(G, tt, T, u - tp.Es);
+                    } else if (u < n6 + tp.Er) {
+                        if (item_range_v0<NbMath>(G, tt, T, u - n6)) item_range_v0<IeeeMath>(G, tt, T, u - n6);
+                    } else {
+                        if (item_range_v1<NbMath>(G, tt, T, u - n6 - tp.Er)) item_range_v1<IeeeMath>(G, tt, T, u - n6 - tp.Er);
+                    }
                 }
             }
             GIT_TICK(8);
@@ -810,10 +1061,12 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
             GIT_TICK(0);
             /* ---- H ---- */
             double md = 0.0;
-            if (sh.lin[lane]) {
+            {
+                const bool on = sh.lin[lane] != 0;
                 const GitEnv G = env();
                 /* the diagonal blocks, then the off-diagonal blocks */
-                for (int u = warp; u < 2 * N; u += NW) {
+                for (int u = next_item(&sh.ctr[1], lane); u < 2 * N; u = next_item(&sh.ctr[1], lane)) {
+                    if (!on) continue;
                     if (u < N) {
                         const double m = item_h_diag(G, tt, u);
                         if (m > md) md = m;
@@ -900,12 +1153,14 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
         __syncthreads();
         GIT_TICK(2);
         /* ---- U ---- */
-        if (sh.act[lane]) {
+        {
+            const bool on = sh.act[lane] != 0;
             const GitEnv G = env();
             const int c = sh.cur[lane];
             const bool lin = sh.lin[lane] != 0;
             const PoseBuf Tc{G.E.p.T(c), G.E.p.Rm(c)}, Tn{G.E.p.T(c ^ 1), G.E.p.Rm(c ^ 1)};
-            for (int i = warp; i < N; i += NW) gen_update_pose(G.E, i, Tc, Tn, lin);
+            for (int i = next_item(&sh.ctr[2], lane); i < N; i = next_item(&sh.ctr[2], lane))
+                if (on) item_update(G.E, i, Tc, Tn, lin);
         }
         GIT_TICK(11);
         __syncthreads();
@@ -919,11 +1174,13 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
         if (warp == 0) {
             LmState st;
             st.load(sh, lane);
+            GIT_TICK(13);
             if (!st.done) {
                 const bool ok = sh.tok[lane] != 0;
                 if (!ok) st.flags |= UWBGO_FLAG_CHOL_FAIL;
                 double scale = sh.tscale[lane], tplain, tempChi;
                 chi_sum(tplain, tempChi);
+                GIT_TICK(14);
                 st.stale = tplain;
                 if (!ok) tempChi = DBL_MAX;
                 scale = scale + 1e-3;
@@ -961,14 +1218,15 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
                 st.store(sh, lane);
             }
             publish(st);
+            GIT_TICK(15);
         }
         __syncthreads();
         GIT_TICK(5);
     }
 #ifdef UWBGO_GIT_TIMING
     if (threadIdx.x == 0 && blockIdx.x < 2)
-        printf("tile %d cycles (warp 0's own items + wait at the barrier): J %lld + %lld  H %lld + %lld  F %lld + %lld  U %lld + %lld  C %lld + %lld  D %lld\n",
-               (int)blockIdx.x, tph[8], tph[0], tph[9], tph[1], tph[6], tph[2], tph[11], tph[3], tph[12], tph[4], tph[5]);
+        printf("tile %d cycles (warp 0's own items + wait at the barrier): J %lld + %lld  H %lld + %lld  F %lld + %lld  U %lld + %lld  C %lld + %lld  D (load %lld, sums %lld, decision %lld, barrier %lld)\n",
+               (int)blockIdx.x, tph[8], tph[0], tph[9], tph[1], tph[6], tph[2], tph[11], tph[3], tph[12], tph[4], tph[13], tph[14], tph[15], tph[5]);
 #endif
 
     if (warp == 0 && valid) {
@@ -990,11 +1248,6 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
         if (valid && sh.cur[lane]) { /* result always leaves in buffer 0 */
             for (int r = warp; r < N * 3; r += NW) ROW(G.E.p.T0, r) = ROW(G.E.p.T1, r);
             for (int r = warp; r < N * 9; r += NW) ROW(G.E.p.Rm0, r) = ROW(G.E.p.Rm1, r);
-        }
-        if (echi_smem) { /* the last trial's terms stay behind for uwbgo_result::edge_chi2 */
-            const double *echi = echi_ptr();
-            double *echi_g = ws.echi + ((size_t)blockIdx.x * tp.E * 2) * TILE + lane;
-            for (int k = warp; k < 2 * NE; k += NW) ROW(echi_g, k) = ROW(echi, k);
         }
     }
 }
@@ -1030,13 +1283,11 @@ cudaError_t launch_solve_general_items(const DevTopo &topo, const DevCfg &cfg, c
 {
     const size_t echi = 2 * (size_t)topo.E * TILE * sizeof(double);
     const size_t base = git_topo_bytes(topo) + GIT_HAND_BYTES;
-#ifndef UWBGO_GIT_ECHI_SMEM
-#define UWBGO_GIT_ECHI_SMEM 0 /* 1: the per-edge chi2 terms of the tile in shared memory (39 KB on C4a).  Measured slower: the
-                               * carve-out then leaves ~28 KB of L1 for two CTAs, and every spilled register becomes an L2
-                               * round trip (C4a, 8,192 windows: 11.2 ms with, 10.0 ms without; 65,536: 85.6 / 77.6 ms) */
-#endif
-    const int echi_smem = UWBGO_GIT_ECHI_SMEM && base + echi + sizeof(GitShared) <= GIT_SMEM_TWO;
-    const size_t sm = base + (echi_smem ? echi : 0);
+    /* (a shared-memory area of their own for the chi2 terms was measured slower: 39 KB more per CTA on C4a leave ~28 KB
+     * of L1 for two CTAs, and every spilled register becomes an L2 round trip: 11.2 vs 10.0 ms at 8,192 windows,
+     * 85.6 vs 77.6 ms at 65,536) */
+    const int echi_smem = echi <= GIT_HAND_BYTES;
+    const size_t sm = base;
     auto kern = lm_general_items_kernel<UWBGO_GIT_WARPS, UWBGO_GIT_MINB>;
     static bool configured[64] = {false}; /* the attribute is per device */
     int dev = 0;

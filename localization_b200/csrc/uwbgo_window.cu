@@ -200,41 +200,6 @@ UWBGO_DI double chi2_6s(const double *O, const double *e, double *Oe)
     return chi;
 }
 
-/* Eigen Quaternion(Matrix3) followed by g2o's normalize() (unit length, w >= 0), q = {x,y,z,w}: R_to_quat of
- * uwbgo_math.cuh with the roots and quotients of the math policy M (the rare trace <= 0 branches keep the
- * IEEE operations; the bits are the same either way) */
-template <class M>
-UWBGO_DI void R_to_quat_m(const double *R, double *q, unsigned &bad)
-{
-    double t = (R[0] + R[4]) + R[8];
-    if (t > 0.0) {
-        t = M::sqrt_(t + 1.0, bad);
-        q[3] = 0.5 * t;
-        t = M::div(0.5, t, bad);
-        q[0] = (R[7] - R[5]) * t;
-        q[1] = (R[2] - R[6]) * t;
-        q[2] = (R[3] - R[1]) * t;
-    } else {
-        int i = 0;
-        if (R[4] > R[0]) i = 1;
-        if (R[8] > R[4 * i]) i = 2;
-        if (i == 0) R_to_quat_branch<0>(R, q);
-        else if (i == 1) R_to_quat_branch<1>(R, q);
-        else R_to_quat_branch<2>(R, q);
-    }
-    const double n = M::sqrt_(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3], bad);
-    q[0] = M::div(q[0], n, bad);
-    q[1] = M::div(q[1], n, bad);
-    q[2] = M::div(q[2], n, bad);
-    q[3] = M::div(q[3], n, bad);
-    if (q[3] < 0.0) {
-        q[0] = -q[0];
-        q[1] = -q[1];
-        q[2] = -q[2];
-        q[3] = -q[3];
-    }
-}
-
 /* toVectorMQT(Zinv * X) and the product itself (EdgeSE3Prior::computeError, identity offset) */
 template <class M>
 UWBGO_DI void prior_error(const double *Zi, const double *Xp, Pose &Dl, double *q, double *e6, unsigned &bad)
@@ -339,36 +304,6 @@ UWBGO_DI void se3_jacobians_s(const Pose &Zinv, const Pose &Xi, const Pose &Xj, 
             for (int k = 0; k < 4; ++k) s = s + Lm[4 * (r + 1) + k] * Rm[4 * k + (c + 1)];
             Ji[6 * (3 + r) + 3 + c] = sgn * s;
         }
-}
-
-/* rotation part of fromVectorMQT and VertexSE3::oplusImpl (uwbgo_math.cuh) with the root of policy M */
-template <class M>
-UWBGO_DI void increment_R_m(const double *q, double *Rinc, unsigned &bad)
-{
-    const double n2 = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
-    double w = 1.0 - n2;
-    if (w < 0.0) {
-        Rinc[0] = 1.0; Rinc[1] = 0.0; Rinc[2] = 0.0;
-        Rinc[3] = 0.0; Rinc[4] = 1.0; Rinc[5] = 0.0;
-        Rinc[6] = 0.0; Rinc[7] = 0.0; Rinc[8] = 1.0;
-    } else {
-        w = M::sqrt_(w, bad);
-        quat_to_R(w, q[0], q[1], q[2], Rinc);
-    }
-}
-template <class M>
-UWBGO_DI void pose_oplus_m(Pose &X, const double *v, int &cnt, int mod, unsigned &bad)
-{
-    Pose inc;
-    increment_R_m<M>(v + 3, inc.R, bad);
-    inc.t[0] = v[0];
-    inc.t[1] = v[1];
-    inc.t[2] = v[2];
-    pose_mul(X, inc, X);
-    if (++cnt >= mod) {
-        cnt = 0;
-        orthogonalize(X.R);
-    }
 }
 
 /* ONE column of the numeric central-difference Jacobian of a range residual (g2o

@@ -62,6 +62,26 @@ def test_uwb_imu_lidar(solver):
     assert_parity(got, oracle.solve(topo, batch, cfg))
 
 
+def test_prior_information_diagonal_and_dense_tiles(solver):
+    """the 6x6 ITEM kernel reads only the diagonal of the prior information matrices of a tile when every one of
+    them has exactly +0.0 elsewhere (the matrices Localization builds, localization.cpp:478-479,515-518), literal
+    zeros taking the place of the rest: tiles that qualify, tiles that hold one dense matrix, one -0.0 or one NaN
+    off the diagonal all give the bits of the dense arithmetic"""
+    topo, batch, _ = synthetic.uwb_imu_lidar(160, 12, 6, seed=21)
+    cfg = Config(max_iterations=6)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))      # five diagonal tiles
+    batch.prior_info[40, 3, 1, 4] = 0.25                                               # tile 1: one dense matrix
+    batch.prior_info[40, 3, 4, 1] = 0.25
+    batch.prior_info[70, 5, 0, 2] = -0.0                                               # tile 2: a negative zero
+    batch.prior_info[130, 1, 5, 0] = np.nan                                            # tile 4: a NaN
+    got, ref = solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg)
+    ok = np.setdiff1d(np.arange(160), [130])
+    assert np.array_equal(got.status, ref.status)
+    assert np.array_equal(got.pose_t[ok], ref.pose_t[ok]) and np.array_equal(got.pose_R[ok], ref.pose_R[ok])
+    assert np.array_equal(got.chi2[ok], ref.chi2[ok])
+    assert np.array_equal(got.pose_t[130], ref.pose_t[130], equal_nan=True)
+
+
 def test_uwb_imu_c2_shape(solver):
     topo, batch, _ = synthetic.uwb_imu_lidar(64, 12, 4, v_max=3.0, antennas=0, lidar=False, seed=11)
     cfg = Config(max_iterations=10)

@@ -80,9 +80,12 @@ lm_general_cta_kernel(const __grid_constant__ DevTopo tp, const __grid_constant_
     auto chi_phase = [&](const int *who, int sel) {
         if (who[lane]) {
             const PoseBuf T = buf(sh.cur[lane] ^ sel);
-            for (int e = warp; e < NE; e += NW) {
+            /* edges in slot order, 6-D kinds first (slots: range | prior | se3): in insertion order the kinds of a
+             * pose's edges repeat with a period that divides NW and every warp would get one kind only */
+            for (int u = warp; u < NE; u += NW) {
+                const int e = __ldg(tp.slot_edge + (NE - 1 - u));
                 double chi, rob;
-                if ((UWBGO_GCTA_PF & 2) && e + NW < NE) gen_edge_prefetch(E, T, e + NW);
+                if ((UWBGO_GCTA_PF & 2) && u + NW < NE) gen_edge_prefetch(E, T, __ldg(tp.slot_edge + (NE - 1 - u - NW)));
                 gen_edge_chi(E, T, e, chi, rob);
                 ROW(echi, 2 * e) = chi;
                 ROW(echi, 2 * e + 1) = rob;

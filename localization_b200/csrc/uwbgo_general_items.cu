@@ -23,6 +23,7 @@
  *
  * Chains only (parent(i) = i - 1 or none); forest windows (pose edges to a key vertex) keep lm_general_cta_kernel.
  */
+#include <cstdlib>
 #include "uwbgo_general.cuh"
 #ifdef UWBGO_GIT_TIMING
 #include <cstdio>
@@ -1262,6 +1263,9 @@ size_t general_items_jrec_rows(const DevTopo &t) { return (size_t)t.Er * GR_RANG
 #ifndef UWBGO_GIT_MINB
 #define UWBGO_GIT_MINB 2
 #endif
+#ifndef UWBGO_GIT_WIDE_WARPS
+#define UWBGO_GIT_WIDE_WARPS 16
+#endif
 
 /* shared memory of one CTA: topology tables | hand-off 2 x 63 rows | staging 2 x 63 rows | per-edge chi2 terms
  * (the last only when two CTAs still fit an SM with them) */
@@ -1288,16 +1292,26 @@ cudaError_t launch_solve_general_items(const DevTopo &topo, const DevCfg &cfg, c
      * 85.6 vs 77.6 ms at 65,536) */
     const int echi_smem = echi <= GIT_HAND_BYTES;
     const size_t sm = base;
-    auto kern = lm_general_items_kernel<UWBGO_GIT_WARPS, UWBGO_GIT_MINB>;
     static bool configured[64] = {false}; /* the attribute is per device */
+    static int sms[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
+    auto narrow = lm_general_items_kernel<UWBGO_GIT_WARPS, UWBGO_GIT_MINB>;
+    auto wide = lm_general_items_kernel<UWBGO_GIT_WIDE_WARPS, 1>;
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GIT_SMEM_MAX);
+        cudaError_t e = cudaFuncSetAttribute(narrow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GIT_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GIT_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    kern<<<(unsigned)n_tiles(ws.W), UWBGO_GIT_WARPS * 32, sm, st>>>(topo, cfg, ws, echi_smem);
+    /* up to one tile per SM: sixteen warps per tile, one CTA per SM (twice the warps in the item phases) */
+    const char *w = getenv("UWBGO_GIT_WIDE");
+    const bool use_wide = w ? atoi(w) != 0 : n_tiles(ws.W) <= sms[dev & 63];
+    if (use_wide)
+        wide<<<(unsigned)n_tiles(ws.W), UWBGO_GIT_WIDE_WARPS * 32, sm, st>>>(topo, cfg, ws, echi_smem);
+    else
+        narrow<<<(unsigned)n_tiles(ws.W), UWBGO_GIT_WARPS * 32, sm, st>>>(topo, cfg, ws, echi_smem);
     return cudaGetLastError();
 }
 

@@ -437,36 +437,96 @@ UWBGO_DI unsigned item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &
     return bad;
 }
 
-/* EdgeSE3, slot s: error, rho1, omega_r and both analytic Jacobians */
-UWBGO_DI void item_se3(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int s)
+/* one of the two analytic Jacobians of EdgeSE3 (se3_jacobians of uwbgo_general.cuh, g2o computeEdgeSE3Gradient with
+ * identity offsets): WHICH = 0 wrt vertex 0 (Ji), 1 wrt vertex 1 (Jj) */
+template <class M, int WHICH>
+UWBGO_DI void se3_jacobian_m(const Pose &Zinv, const Pose &Xi, const Pose &Xj, double *J, unsigned &bad)
 {
+    Pose Xi_inv, Bm;
+    pose_inv(Xi, Xi_inv);
+    pose_mul(Xi_inv, Xj, Bm);
+#pragma unroll
+    for (int k = 0; k < 36; ++k) J[k] = 0.0;
+    if (WHICH == 1) {
+        Pose AB;
+        pose_mul(Zinv, Bm, AB);
+        double qE[4];
+        R_to_quat_m<M>(AB.R, qE, bad);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) J[6 * r + c] = AB.R[3 * r + c];
+        set_jqq(qE, J);
+        return;
+    }
+    const double *Ra = Zinv.R, *tb = Bm.t;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) J[6 * r + c] = -Ra[3 * r + c];
+    double S[9] = {0.0, -2.0 * tb[2], 2.0 * tb[1], 2.0 * tb[2], 0.0, -2.0 * tb[0], -2.0 * tb[1], 2.0 * tb[0], 0.0};
+    double RaS[9];
+    mat3_mul(Ra, S, RaS);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) J[6 * r + 3 + c] = RaS[3 * r + c];
+    double qA[4], qB[4], Lm[16], Rm[16];
+    R_to_quat_m<M>(Ra, qA, bad);
+    R_to_quat_m<M>(Bm.R, qB, bad);
+    quat_left(qA, Lm);
+    quat_right(qB, Rm);
+    double wAB = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wAB = wAB + Lm[k] * Rm[4 * k];
+    const double sgn = wAB < 0.0 ? 1.0 : -1.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v = v + Lm[4 * (r + 1) + k] * Rm[4 * k + (c + 1)];
+            J[6 * (3 + r) + 3 + c] = sgn * v;
+        }
+}
+
+/* EdgeSE3, slot s, one item per vertex: the vertex's Jacobian and its J^T Ow (item 0 also leaves omega_r); each
+ * item evaluates the error it needs for rho1 itself, so that neither holds both Jacobians */
+template <class M, int WHICH>
+UWBGO_DI unsigned item_se3(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int s)
+{
+    unsigned bad = 0;
     const GenEnv &E = G.E;
     const EdgeRec er = smem_edge(tt.edges + tt.slot_edge[G.Er + G.Ep + s]);
     double *rec = G.jrec + ((size_t)G.Er * GR_RANGE + (size_t)G.Ep * GR_PRIOR + (size_t)s * GR_SE3) * TILE;
+    const double *O = E.p.sI + (size_t)er.slot * 36 * TILE;
     Pose Zinv, Xi, Xj;
     load_Zinv(E.p.sZ, er.slot, Zinv);
     load_pose(T, er.a, Xi);
     load_pose(T, er.b, Xj);
-    double e6[6], Oe[6];
-    se3_error(Zinv, Xi, Xj, e6);
-    const double chi = chi2_6(E.p.sI, er.slot, e6, Oe);
-    const double r1 = er.robust ? E.ck.rho1(chi) : 1.0;
+    double r1 = 1.0;
+    if (WHICH == 0 || er.robust) {
+        double e6[6], Oe[6];
+        se3_error_m<M>(Zinv, Xi, Xj, e6, bad);
+        const double chi = chi2_6_t<false>(O, e6, Oe);
+        if (er.robust) r1 = E.ck.rho1m<M>(chi, bad);
+        if (WHICH == 0) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        double v = -Oe[k];
-        if (er.robust) v = v * r1;
-        ROW(rec, 72 + k) = v;
+            for (int k = 0; k < 6; ++k) {
+                double v = -Oe[k];
+                if (er.robust) v = v * r1;
+                ROW(rec, 72 + k) = v;
+            }
+            ROW(rec, 78) = r1;
+        }
     }
-    ROW(rec, 78) = r1;
-    double Ji[36], Jj[36];
-    se3_jacobians(Zinv, Xi, Xj, Ji, Jj, true);
+    double J[36];
+    se3_jacobian_m<M, WHICH>(Zinv, Xi, Xj, J, bad);
 #pragma unroll
-    for (int k = 0; k < 36; ++k) ROW(rec, k) = Ji[k];
-#pragma unroll
-    for (int k = 0; k < 36; ++k) ROW(rec, 36 + k) = Jj[k];
-    const double *O = E.p.sI + (size_t)er.slot * 36 * TILE;
-    store_jto(Ji, O, er.robust != 0, r1, rec + (size_t)79 * TILE);
-    store_jto(Jj, O, er.robust != 0, r1, rec + (size_t)115 * TILE);
+    for (int k = 0; k < 36; ++k) ROW(rec, 36 * WHICH + k) = J[k];
+    store_jto(J, O, er.robust != 0, r1, rec + (size_t)(79 + 36 * WHICH) * TILE);
+    return bad;
 }
 
 /* ---- H items ------------------------------------------------------------------------------------------------ */
@@ -945,7 +1005,9 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
             const int e = tt.slot_edge[NE - 1 - u]; /* 6-D edges first: slots are ordered range | prior | se3 */
             if (on) {
                 double chi, rob;
-                if (diag ? item_chi<NbMath, true>(G.E, tt, T, e, chi, rob) : item_chi<NbMath, false>(G.E, tt, T, e, chi, rob))
+                /* (EdgeSE3 with the IEEE sequences at once, see the J phase) */
+                if (tt.edges[e].kind == UWBGO_EDGE_SE3 ||
+                    (diag ? item_chi<NbMath, true>(G.E, tt, T, e, chi, rob) : item_chi<NbMath, false>(G.E, tt, T, e, chi, rob)))
                     item_chi<IeeeMath, false>(G.E, tt, T, e, chi, rob);
                 ROW(echi, 2 * e) = chi;
                 ROW(echi, 2 * e + 1) = rob;
@@ -1042,18 +1104,24 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
                 /* heaviest kind first: EdgeSE3, priors, range edges (vertex 0, then vertex 1).  Branch-free
                  * arithmetic first; an item whose operands it flags is evaluated again with the IEEE sequences (an
                  * item only writes its own record) */
-                const int nJ = n6 + tp.Er + tp.Er;
+                const int nS = 2 * tp.Es, nJ = nS + tp.Ep + tp.Er + tp.Er;
                 for (int u = next_item(&sh.ctr[0], lane); u < nJ; u = next_item(&sh.ctr[0], lane)) {
                     if (!on) continue;
-                    if (u < tp.Es)
-                        item_se3(G, tt, T, u);
-                    else if (u < n6) {
-                        if (diag ? item_prior<NbMath, true>(G, tt, T, u - tp.Es) : item_prior<NbMath, false>(G, tt, T, u - tp.Es))
-                            item_prior<IeeeMath, false>(G, tt, T, u - tp.Es);
-                    } else if (u < n6 + tp.Er) {
-                        if (item_range_v0<NbMath>(G, tt, T, u - n6)) item_range_v0<IeeeMath>(G, tt, T, u - n6);
+                    if (u < nS) {
+                        /* (IEEE sequences at once: the quaternion of a near-identity rotation divides by 2 - ulp, the one
+                         * divisor class the branch-free quotient refuses, and a twist chain is full of them) */
+                        if (u & 1)
+                            item_se3<IeeeMath, 1>(G, tt, T, u >> 1);
+                        else
+                            item_se3<IeeeMath, 0>(G, tt, T, u >> 1);
+                    }
+                    else if (u < nS + tp.Ep) {
+                        if (diag ? item_prior<NbMath, true>(G, tt, T, u - nS) : item_prior<NbMath, false>(G, tt, T, u - nS))
+                            item_prior<IeeeMath, false>(G, tt, T, u - nS);
+                    } else if (u < nS + tp.Ep + tp.Er) {
+                        if (item_range_v0<NbMath>(G, tt, T, u - nS - tp.Ep)) item_range_v0<IeeeMath>(G, tt, T, u - nS - tp.Ep);
                     } else {
-                        if (item_range_v1<NbMath>(G, tt, T, u - n6 - tp.Er)) item_range_v1<IeeeMath>(G, tt, T, u - n6 - tp.Er);
+                        if (item_range_v1<NbMath>(G, tt, T, u - nS - tp.Ep - tp.Er)) item_range_v1<IeeeMath>(G, tt, T, u - nS - tp.Ep - tp.Er);
                     }
                 }
             }

@@ -50,9 +50,11 @@ NOTE_C3 = ("7.4 KB of algorithmic bytes per window against ~1.1 Mflop of FP64 pe
                         "traffic_frac of the HBM peak -- the kernel is bounded by its own scratch traffic and by FP64 "
                         "issue latency at the same time (DESIGN.md section 4)")
 NOTE_GENERAL = ("6x6 windows (rotations, antenna offsets, EdgeSE3Prior / EdgeSE3): by the algorithmic bytes the fused solve is "
-                "far from the HBM roof; the CTA-per-tile kernel runs 8 warps per SM at 255 registers and is bounded by FP64 / "
-                "load latency (DESIGN.md sections 3.2 and 4.2); traffic = H and L records, information matrices and spills "
-                "streamed once per LM trial")
+                "far from the HBM roof; the ITEM kernel (one CTA of 8 warps per tile of 32 windows at 128 registers, two tiles "
+                "per SM, the LM trial cut into per-edge / per-pose items drawn from a queue, the serial elimination on two "
+                "warps) is bounded by L2 / FP64 latency with 16 warps per SM, 8,192 windows being 1.7 tiles per SM "
+                "(DESIGN.md sections 3.2 and 4.2); traffic = linearisation, H and L records, information matrices and "
+                "spills streamed once per LM trial")
 
 
 ARRAYS = ("pose_t", "pose_R", "anchors", "range_d", "range_info", "prior_Z", "prior_info", "se3_Z", "se3_info")
@@ -523,7 +525,7 @@ def main():
         achieved = wl_bytes * W / (k_best * 1e-3) / 1e9 if k_best else None
         traffic, traffic_src, fp64_flop, fp64_pipe = None, None, None, None
         tkey = {"c3": ("lm_chain_tma_kernel", WINDOWS_PER_GPU), "c3x": ("lm_chain_tma_kernel", WINDOWS_PER_GPU),
-                "c4a": ("lm_general_cta_kernel", 8192)}.get(args.workload)
+                "c4a": ("lm_general_items_kernel_c4a", 8192), "c4b": ("lm_general_items_kernel_c4b", 8192)}.get(args.workload)
         for tp in (os.path.join(ROOT, "profiles", "r02_traffic.json"), os.path.join(ROOT, "profiles", "r01_traffic.json")):
             if os.path.exists(tp) and tkey and W == tkey[1]:
                 with open(tp) as f:
@@ -533,7 +535,9 @@ def main():
                     fp64_flop = tj.get("fp64_flop_per_launch")
                     fp64_pipe = tj.get("fp64_pipe_active_pct")
                     break
-        kname = {1: "lm_fast_kernel", 2: "lm_chain_tma_kernel", 3: "lm_window_kernel"}.get(m["path"], "lm_general_cta_kernel")
+        # 6x6 chains: the ITEM kernel (uwbgo_general_items.cu); forests (pose edges to a key vertex) keep the CTA kernel
+        kname = {1: "lm_fast_kernel", 2: "lm_chain_tma_kernel", 3: "lm_window_kernel"}.get(
+            m["path"], "lm_general_cta_kernel" if getattr(topo, "is_forest", False) else "lm_general_items_kernel")
         fp64, _ = solver.measure_fp64_peak()
         # The fused LM kernel is bounded by FP64 arithmetic (issue latency of dependent chains), not by its
         # algorithmic bytes: frac = FP64 flop executed (ncu, Newton steps of sqrt and division included) / kernel

@@ -749,6 +749,10 @@ UWBGO_DI unsigned item_chi(const GenEnv &E, const GitTopo &tt, const PoseBuf &T,
 /* 0 for every double arithmetic produces, but not provably so: an address that depends on it cannot be formed, and
  * its loads cannot be hoisted, before the value exists (ptxas otherwise lifts every shared-memory load of the step
  * to its top and spills what it loaded; a spill is an L2 round trip at the L1 size this kernel leaves) */
+#ifndef UWBGO_GIT_TIES
+#define UWBGO_GIT_TIES 0 /* experiment, bit 0: S columns behind the previous pivot, bit 1: G rows behind z, bit 2: G rows 3..5 behind
+                          * rows 0..2 (fewer spills, but C4a 8,192 windows 9.9 ms with all three against 9.4 ms without) */
+#endif
 UWBGO_DI int after(double v) { return ((__double2hiint(v) & 0x7fffffff) == 0x7ff12345) ? 1 : 0; }
 
 template <class M>
@@ -786,7 +790,9 @@ UWBGO_DI unsigned factor_main_step(const double *__restrict__ h, const double *_
         if (!(s > 0.0)) ok = false;
         const double inv = M::rsqrt_pivot(s, bad);
         L[lo_idx(j, j)] = inv;
+#if UWBGO_GIT_TIES & 1
         dep = after(inv);
+#endif
 #pragma unroll
         for (int r = j + 1; r < 6; ++r) {
             double t = col[r];
@@ -816,7 +822,9 @@ UWBGO_DI unsigned factor_main_step(const double *__restrict__ h, const double *_
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) ROW(Gn, 57 + k) = z[k];
+#if UWBGO_GIT_TIES & 2
     dep = after(z[5]);
+#endif
     if (has_prev) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
@@ -831,7 +839,9 @@ UWBGO_DI unsigned factor_main_step(const double *__restrict__ h, const double *_
             }
 #pragma unroll
             for (int cc = 0; cc < 6; ++cc) ROW(Gn, r * 6 + cc) = g[cc];
+#if UWBGO_GIT_TIES & 4
             if (r == 2) dep = after(g[5]); /* rows 3..5 after rows 0..2 */
+#endif
         }
     }
 #pragma unroll

@@ -82,6 +82,15 @@ def test_prior_information_diagonal_and_dense_tiles(solver):
     assert np.array_equal(got.pose_t[130], ref.pose_t[130], equal_nan=True)
 
 
+@pytest.mark.parametrize("make,N,iters", [(synthetic.uwb_imu_lidar, 120, 4), (synthetic.uwb_twist, 200, 3)])
+def test_long_general_chains(solver, make, N, iters):
+    """6x6 chains far longer than the BASELINE shapes (topology tables of the ITEM kernel beyond 48 KB of shared
+    memory, hundreds of staged elimination steps), ragged batch"""
+    topo, batch, _ = make(45, N, 8, seed=N)
+    cfg = Config(max_iterations=iters)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+
+
 def test_uwb_imu_c2_shape(solver):
     topo, batch, _ = synthetic.uwb_imu_lidar(64, 12, 4, v_max=3.0, antennas=0, lidar=False, seed=11)
     cfg = Config(max_iterations=10)

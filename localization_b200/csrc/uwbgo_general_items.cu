@@ -144,9 +144,9 @@ UWBGO_DI EdgeRec smem_edge(const EdgeRec *e)
 
 /* The information matrix of an EdgeSE3Prior.  The priors Localization builds are diagonal (lidar: one entry,
  * localization.cpp:478-479; IMU: three, localization.cpp:515-518), and a tile whose prior information matrices all have
- * exactly +0.0 off the diagonal (checked once per launch, bit patterns) reads the six diagonal rows only: the thirty
- * zeros become literals, every product and sum of chi2_6 / jt_omega is still executed, so the bits are those of the
- * dense arithmetic.  Anything else takes the dense reads. */
+ * exactly +0.0 off the diagonal (checked once per launch, bit patterns) reads the six diagonal rows only and forms
+ * the sums of the terms that are not structurally zero (prior_terms_diag: same chains, same bits in H, b and chi2).
+ * Anything else takes the dense reads and loops. */
 template <bool DIAG>
 UWBGO_DI double info_at(const double *__restrict__ O, int k, int c)
 {
@@ -384,6 +384,52 @@ UWBGO_DI void store_jto(const double *J, const double *__restrict__ O, bool robu
     }
 }
 
+/* The sums of acc6_b / jt_omega / acc6_diag for a prior whose information matrix is diagonal, restricted to the terms
+ * that are not structurally zero: J is block diagonal (two 3x3 blocks), so J^T Ow and J^T Ow J are, and every sum is
+ * the three-term chain of its own block in the order of the dense loops.  What the dense loops add on top are
+ * products of a FINITE number with a literal zero: they leave a non-zero partial sum unchanged, and where the sum
+ * is zero they can only change its sign, which the accumulators of the H item (started at +0.0) absorb.  The caller
+ * guards finiteness (any NaN / inf operand -> the dense arithmetic). */
+UWBGO_DI void prior_terms_diag(const double *J, const double *Oe, const double *od, bool robust, double r1, double *rec)
+{
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { /* acc6_b */
+        const int k0 = r < 3 ? 0 : 3;
+        double v = J[6 * k0 + r] * Oe[k0];
+        v = fma(J[6 * (k0 + 1) + r], Oe[k0 + 1], v);
+        v = fma(J[6 * (k0 + 2) + r], Oe[k0 + 2], v);
+        ROW(rec, 21 + r) = v;
+    }
+    double ow[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) ow[c] = robust ? r1 * od[c] : od[c];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const int k0 = r < 3 ? 0 : 3;
+        double jto[3]; /* J^T Ow (r, k0 .. k0 + 2) */
+#pragma unroll
+        for (int k = 0; k < 3; ++k) jto[k] = J[6 * (k0 + k) + r] * ow[k0 + k];
+#pragma unroll
+        for (int c = r; c < 6; ++c) {
+            double v = 0.0;
+            if ((c < 3) == (r < 3)) {
+                v = jto[0] * J[6 * k0 + c];
+                v = fma(jto[1], J[6 * (k0 + 1) + c], v);
+                v = fma(jto[2], J[6 * (k0 + 2) + c], v);
+            }
+            ROW(rec, up_idx(6, r, c)) = v;
+        }
+    }
+}
+/* NaN if any of the n values is not finite, else 0 */
+UWBGO_DI double nonfinite_probe(const double *x, int n, double t)
+{
+#pragma unroll
+    for (int k = 0; k < 36; ++k)
+        if (k < n) t = fma(x[k], 0.0, t);
+    return t;
+}
+
 /* EdgeSE3Prior, slot s: the edge touches one pose, so its whole contribution to H_ii and b_i is formed here
  * (error, rho1, omega_r, J, J^T Ow, then the sums of acc6_b / acc6_diag) and the H item only adds it */
 template <class M, bool DIAG>
@@ -402,14 +448,25 @@ UWBGO_DI unsigned item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &
     e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
     e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
     const double *O = E.p.pI + (size_t)er.slot * 36 * TILE;
-    const double chi = chi2_6_t<DIAG>(O, e6, Oe);
+    double od[6];
+    double chi;
+    if (DIAG) { /* Oe = Omega e and chi2 = e . Oe, the non-zero terms (see prior_terms_diag) */
+#pragma unroll
+        for (int k = 0; k < 6; ++k) od[k] = ROW(O, 7 * k);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Oe[k] = od[k] * e6[k];
+        chi = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) chi = chi + e6[k] * Oe[k];
+    } else
+        chi = chi2_6_t<false>(O, e6, Oe);
     const double r1 = er.robust ? E.ck.rho1m<M>(chi, bad) : 1.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         Oe[k] = -Oe[k];
         if (er.robust) Oe[k] = Oe[k] * r1;
     }
-    double J[36], JtO[36];
+    double J[36];
 #pragma unroll
     for (int k = 0; k < 36; ++k) J[k] = 0.0;
 #pragma unroll
@@ -417,6 +474,16 @@ UWBGO_DI unsigned item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &
 #pragma unroll
         for (int c = 0; c < 3; ++c) J[6 * r + c] = Dl.R[3 * r + c];
     set_jqq(q, J);
+    if (DIAG) {
+        double t = nonfinite_probe(Dl.R, 9, 0.0);
+        t = nonfinite_probe(e6, 6, t);
+        t = nonfinite_probe(od, 6, t);
+        t = fma(q[3], 0.0, fma(r1, 0.0, t));
+        if (t != t) bad |= 1u; /* a NaN / inf operand: the dense IEEE arithmetic decides what it propagates to */
+        prior_terms_diag(J, Oe, od, er.robust != 0, r1, rec);
+        return bad;
+    }
+    double JtO[36];
 #pragma unroll
     for (int r = 0; r < 6; ++r) { /* acc6_b */
         double v = J[r] * Oe[0];
@@ -424,7 +491,7 @@ UWBGO_DI unsigned item_prior(const GitEnv &G, const GitTopo &tt, const PoseBuf &
         for (int k = 1; k < 6; ++k) v = fma(J[6 * k + r], Oe[k], v);
         ROW(rec, 21 + r) = v;
     }
-    jt_omega_t<DIAG>(J, O, er.robust != 0, r1, JtO);
+    jt_omega_t<false>(J, O, er.robust != 0, r1, JtO);
 #pragma unroll
     for (int r = 0; r < 6; ++r) /* acc6_diag */
 #pragma unroll
@@ -726,7 +793,20 @@ UWBGO_DI unsigned item_chi(const GenEnv &E, const GitTopo &tt, const PoseBuf &T,
         R_to_quat_m<M>(Dl.R, q, bad);
         e6[0] = Dl.t[0]; e6[1] = Dl.t[1]; e6[2] = Dl.t[2];
         e6[3] = q[0]; e6[4] = q[1]; e6[5] = q[2];
-        chi = chi2_6_t<DIAG>(E.p.pI + (size_t)er.slot * 36 * TILE, e6, Oe);
+        const double *O = E.p.pI + (size_t)er.slot * 36 * TILE;
+        if (DIAG) { /* the non-zero terms of Omega e and e . Oe (see prior_terms_diag); NaN / inf -> dense arithmetic */
+            double od[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) od[k] = ROW(O, 7 * k);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Oe[k] = od[k] * e6[k];
+            chi = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) chi = chi + e6[k] * Oe[k];
+            const double t = nonfinite_probe(od, 6, nonfinite_probe(e6, 6, 0.0));
+            if (t != t) bad |= 1u;
+        } else
+            chi = chi2_6_t<false>(O, e6, Oe);
     } else {
         Pose Zinv, Xi, Xj;
         load_pose(T, er.a, Xi);

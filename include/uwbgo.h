@@ -180,7 +180,7 @@ void uwbgo_destroy(uwbgo_ctx *ctx);
 const char *uwbgo_last_error(void);
 
 /* Tuning of the host-pointer entry points: windows per pipeline chunk (rounded up to 32) and
- * number of concurrent stream lanes (1..8).  Defaults: 8192 windows, 8 lanes. */
+ * number of concurrent stream lanes (1..16).  Defaults: 8192 windows, 8 lanes. */
 int  uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes);
 /* Small batches -- the reference's own call pattern is ONE window per range message
  * (localization.cpp:371-375) -- take the WINDOW path: one CTA per window, the window's state in

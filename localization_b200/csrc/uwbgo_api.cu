@@ -121,9 +121,10 @@ struct Lane {
     cudaStream_t st = nullptr;
     DevBuf stage; /* window-major staging (host API only) */
     DevBuf tile;  /* tile-layout workspace */
+    cudaEvent_t in_ready = nullptr; /* host pipeline: the inputs of the lane's chunk have arrived */
 };
 
-constexpr int MAX_LANES = 8;
+constexpr int MAX_LANES = 16;
 
 }  // namespace
 
@@ -849,8 +850,10 @@ int uwbgo_create(int device, uwbgo_ctx **out)
     CU(cudaSetDevice(device));
     auto ctx = new uwbgo_ctx();
     ctx->device = device;
+    e = cudaSuccess;
     for (int k = 0; k < MAX_LANES; ++k) {
-        e = cudaStreamCreateWithFlags(&ctx->lane[k].st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->lane[k].st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lane[k].in_ready, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             uwbgo_destroy(ctx);
             return fail_cuda(e, "stream/event creation");
@@ -878,6 +881,7 @@ void uwbgo_destroy(uwbgo_ctx *ctx)
         ctx->lane[k].stage.release();
         ctx->lane[k].tile.release();
         if (ctx->lane[k].st) cudaStreamDestroy(ctx->lane[k].st);
+        if (ctx->lane[k].in_ready) cudaEventDestroy(ctx->lane[k].in_ready);
     }
     ctx->misc.release();
     ctx->ant.release();
@@ -895,7 +899,7 @@ int uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes)
 {
     if (!ctx) return fail(UWBGO_E_INVALID, "ctx is NULL");
     if (windows_per_chunk < 32 || n_lanes < 1 || n_lanes > MAX_LANES)
-        return fail(UWBGO_E_INVALID, "windows_per_chunk >= 32 and 1 <= n_lanes <= 8 required");
+        return fail(UWBGO_E_INVALID, "windows_per_chunk >= 32 and 1 <= n_lanes <= 16 required");
     ctx->chunk = (windows_per_chunk + 31) / 32 * 32;
     ctx->n_lanes = n_lanes;
     ctx->pipeline_set = true;
@@ -1089,16 +1093,38 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
     }
     int first_err = 0;
     int64_t c = 0;
+    /* UWBGO_PIPE_TRACE=1: per-chunk event times of this call on stderr (diagnosis only) */
+    static const bool trace = getenv("UWBGO_PIPE_TRACE") != nullptr;
+    static const bool ordered_h2d = !(getenv("UWBGO_PIPE_H2D") && !strcmp(getenv("UWBGO_PIPE_H2D"), "lanes"));
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tev.push_back(e);
+    };
+    if (trace) {
+        for (int k = 0; k < n_lanes; ++k) cudaStreamSynchronize(ctx->lane[k].st);
+        mark(ctx->lane[0].st);
+    }
     ctx->batch_windows = W; /* the chunks run concurrently: kernels choose their shape by the whole batch */
     for (int64_t w0 = 0; w0 < W; w0 += chunk, ++c) {
         Lane &ln = ctx->lane[c % n_lanes];
         const int64_t wc = std::min<int64_t>(chunk, W - w0);
         char *sb = static_cast<char *>(ln.stage.p);
         cudaStream_t st = ln.st;
+        /* Inputs cross the link in chunk order: issued independently from the lanes' streams, the copies of all
+         * chunks share it, every chunk arrives late and the device idles meanwhile (C3: first chunk on the
+         * device after 0.86 ms instead of 0.3 ms).  A lane's copies therefore wait for the event the previous
+         * chunk's lane records after its own (a stream of its own for the inputs aliases a lane's hardware
+         * queue once there are more streams than connections and stalls behind that lane's kernels) */
+        cudaStream_t sin = st;
+        if (ordered_h2d && c > 0) CUL(cudaStreamWaitEvent(st, ctx->lane[(c - 1) % n_lanes].in_ready, 0));
         auto h2d = [&](const void *src, size_t off, size_t per_window) -> cudaError_t {
             if (!src) return cudaSuccess;
             return cudaMemcpyAsync(sb + off, static_cast<const char *>(src) + (size_t)w0 * per_window,
-                                   (size_t)wc * per_window, cudaMemcpyHostToDevice, st);
+                                   (size_t)wc * per_window, cudaMemcpyHostToDevice, sin);
         };
         auto d2h = [&](void *dst, size_t off, size_t per_window) -> cudaError_t {
             if (!dst) return cudaSuccess;
@@ -1109,7 +1135,7 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         CUL(h2d(in->pose_R, S.in_pose_R, N * 9 * 8));
         CUL(h2d(in->oplus_count, S.in_cnt, N * 4));
         if (g.A > 0 && shared_anch) { /* one constellation: A*3 doubles per chunk instead of per window */
-            CUL(cudaMemcpyAsync(sb + S.in_anch, in->anchors, (size_t)g.A * 3 * 8, cudaMemcpyHostToDevice, st));
+            CUL(cudaMemcpyAsync(sb + S.in_anch, in->anchors, (size_t)g.A * 3 * 8, cudaMemcpyHostToDevice, sin));
         } else {
             CUL(h2d(g.A > 0 ? in->anchors : nullptr, S.in_anch, (size_t)g.A * 3 * 8));
         }
@@ -1132,6 +1158,8 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         CUL(h2d(g.Ep > 0 ? in->prior_info : nullptr, S.in_pI, (size_t)g.Ep * 36 * 8));
         CUL(h2d(g.Es > 0 ? in->se3_Z : nullptr, S.in_sZ, (size_t)g.Es * 12 * 8));
         CUL(h2d(g.Es > 0 ? in->se3_info : nullptr, S.in_sI, (size_t)g.Es * 36 * 8));
+        if (ordered_h2d) CUL(cudaEventRecord(ln.in_ready, st));
+        mark(st);
         uwbgo_batch db{};
         db.n_windows = wc;
         db.pose_t = reinterpret_cast<double *>(sb + S.in_pose_t);
@@ -1170,6 +1198,7 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
             dr.marginal_ok = (out->marginal && out->marginal_ok) ? reinterpret_cast<int32_t *>(sb + S.out_mok) : nullptr;
             rc = run_device(ctx, ln, *te, dc, &db, d_ant, &dr, nullptr, st);
             if (rc) { first_err = rc; break; }
+            mark(st);
             CUL(d2h(out->pose_t, S.out_pose_t, N * 3 * 8));
             CUL(d2h(out->pose_R, S.out_pose_R, N * 9 * 8));
             CUL(d2h(out->oplus_count, S.out_cnt, N * 4));
@@ -1178,6 +1207,7 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
             CUL(d2h(g.E > 0 ? out->edge_chi2 : nullptr, S.out_echi, (size_t)g.E * 8));
             CUL(d2h(out->marginal, S.out_marg, 36 * 8));
             CUL(d2h(out->marginal ? out->marginal_ok : nullptr, S.out_mok, 4));
+            mark(st);
         }
     }
     ctx->batch_windows = 0;
@@ -1185,6 +1215,18 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         cudaError_t e = cudaStreamSynchronize(ctx->lane[k].st);
         if (e != cudaSuccess && !first_err) first_err = fail_cuda(e, "cudaStreamSynchronize");
     }
+    if (trace && !linearize && !first_err && tev.size() == 1 + 3 * (size_t)c) {
+        fprintf(stderr, "pipe trace: %lld windows, chunk %lld, %d lanes (ms after the start: inputs on the device, results ready, results on the host)\n",
+                (long long)W, (long long)chunk, n_lanes);
+        for (int64_t k = 0; k < c; ++k) {
+            float a = 0, b2 = 0, d = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * k]);
+            cudaEventElapsedTime(&b2, tev[0], tev[2 + 3 * k]);
+            cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * k]);
+            fprintf(stderr, "  chunk %2lld  h2d %7.3f  solved %7.3f  d2h %7.3f\n", (long long)k, a, b2, d);
+        }
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
 #undef CUL
     return first_err;
 }

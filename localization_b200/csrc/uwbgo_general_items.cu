@@ -965,6 +965,168 @@ UWBGO_DI void factor_helper_step(const double *__restrict__ Gn, double *__restri
     }
 }
 
+/* ---- F, cooperative form (UWBGO_GIT_COOP, default) -------------------------------------------------------------
+ * The elimination step of a pose cut along its data dependences, so that only the potrf is one warp's chain:
+ *   A  every warp: entries of S_i = H_ii + lambda I - G_c G_c^T and the G_c z_c part of z_i (27 sums of 6 FMAs,
+ *      written over the staged H record in place: hd rows 0..20, b rows 57..62);
+ *   B  warp 0: potrf of S_i (registers only) -> L_i into the hand-off buffer; the other warps meanwhile: c and the
+ *      columns of M of pose i + 1 (what factor_helper_step did one pose behind) and the staging of H_{i-1};
+ *   C  the other warps: the rows of G_i = H_{i-1,i} L_i^-T and z_i.
+ * Every entry is produced by the operation sequence of factor_main_step / factor_helper_step (same operands, same
+ * order), by one thread: the bits do not change, only who computes them. */
+#ifndef UWBGO_GIT_COOP
+#define UWBGO_GIT_COOP 1
+#endif
+
+UWBGO_DI void coop_upper_jr(int t, int &j, int &r) /* t = up_idx(6, j, r) */
+{
+    int base = 0;
+    j = 0;
+    while (t >= base + 6 - j) {
+        base += 6 - j;
+        ++j;
+    }
+    r = j + (t - base);
+}
+
+template <int NW>
+UWBGO_DI void coop_form_S(double *__restrict__ h, const double *__restrict__ Gc, bool link, double lambda, int warp)
+{
+    constexpr int PER = (27 + NW - 1) / NW;
+    double v[PER];
+    int row[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int t = warp + q * NW;
+        row[q] = -1;
+        v[q] = 0.0;
+        if (t < 21) {
+            int j, r;
+            coop_upper_jr(t, j, r);
+            row[q] = t;
+            double s = ROW(h, t);
+            if (r == j) s = s + lambda;
+            if (link) {
+                const double *gr = Gc + (size_t)(r * 6) * TILE, *gj = Gc + (size_t)(j * 6) * TILE;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s = fma(-ROW(gr, k), ROW(gj, k), s);
+            }
+            v[q] = s;
+        } else if (t < 27) {
+            const int r = t - 21;
+            row[q] = 57 + r;
+            double s = ROW(h, 57 + r);
+            if (link) {
+                const double *gr = Gc + (size_t)(r * 6) * TILE;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s = fma(-ROW(gr, k), ROW(Gc, 57 + k), s);
+            }
+            v[q] = s;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+        if (row[q] >= 0) ROW(h, row[q]) = v[q];
+}
+
+/* warp 0: the Cholesky factor of S_i (rows 0..20 of the staged record after phase A); the diagonal slot keeps
+ * 1 / L_jj.  Returns bit 0 = a pivot was not positive, bit 1 = the branch-free roots flagged an operand */
+template <class M>
+UWBGO_DI unsigned coop_potrf(const double *__restrict__ h, double *__restrict__ Gn)
+{
+    bool ok = true;
+    unsigned bad = 0;
+    double S[21], L[21];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) S[k] = ROW(h, k);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double s = S[up_idx(6, j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
+        if (!(s > 0.0)) ok = false;
+        const double inv = M::rsqrt_pivot(s, bad);
+        L[lo_idx(j, j)] = inv;
+#pragma unroll
+        for (int r = j + 1; r < 6; ++r) {
+            double t = S[up_idx(6, j, r)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
+            L[lo_idx(r, j)] = t * inv;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 21; ++k) ROW(Gn, 36 + k) = L[k];
+    return (ok ? 0u : 1u) | (bad ? 2u : 0u);
+}
+
+/* task u of pose p's L record: u = 6: c_p = L_p^-T z_p; u < 6: column u of M_p = L_p^-T G_p^T */
+UWBGO_DI void coop_helper_task(const double *__restrict__ Gn, double *__restrict__ l, int u, bool has_prev)
+{
+    if (u < 6 && !has_prev) return;
+    double L[21], g[6], m[6];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) L[k] = ROW(Gn, 36 + k);
+    const double *src = Gn + (size_t)(u < 6 ? u * 6 : 57) * TILE;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) g[r] = ROW(src, r);
+#pragma unroll
+    for (int r = 5; r >= 0; --r) {
+        double s = g[r];
+#pragma unroll
+        for (int k = r + 1; k < 6; ++k) s = fma(-L[lo_idx(k, r)], m[k], s);
+        m[r] = s * L[lo_idx(r, r)];
+    }
+    if (u == 6) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ROW(l, k) = m[k];
+    } else {
+        double *dst = l + (size_t)(6 + u) * TILE;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) ROW(dst, r * 6) = m[r];
+    }
+}
+
+/* task v of step i: v = 6: z_i from its G_c z_c part (rows 57..62 of the staged record after phase A); v < 6: row v
+ * of G_i = H_{i-1,i} L_i^-T */
+UWBGO_DI void coop_trsm_task(const double *__restrict__ h, double *__restrict__ Gn, int v, bool has_prev)
+{
+    if (v < 6 && !has_prev) return;
+    double L[21], g[6];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) L[k] = ROW(Gn, 36 + k);
+    const double *src = h + (size_t)(v < 6 ? 21 + v * 6 : 57) * TILE;
+    double *dst = Gn + (size_t)(v < 6 ? v * 6 : 57) * TILE;
+    if (v == 6) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double s = ROW(src, r);
+#pragma unroll
+            for (int k = 0; k < r; ++k) s = fma(-L[lo_idx(r, k)], g[k], s);
+            g[r] = s * L[lo_idx(r, r)];
+        }
+    } else {
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+            double s = ROW(src, cc);
+#pragma unroll
+            for (int k = 0; k < cc; ++k) s = fma(-g[k], L[lo_idx(cc, k)], s);
+            g[cc] = s * L[lo_idx(cc, cc)];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ROW(dst, k) = g[k];
+}
+
+/* warps 1 .. NW-1 together stage `rows` consecutive rows of a tile array */
+template <int NW>
+UWBGO_DI void stage_rows_coop(double *dst, const double *src, int rows, int warp, int lane)
+{
+    const int chunks = rows * (TILE * (int)sizeof(double) / 16);
+    for (int c = (warp - 1) * 32 + lane; c < chunks; c += (NW - 1) * 32)
+        cp_async16(reinterpret_cast<char *>(dst) + 16 * c, reinterpret_cast<const char *>(src) + 16 * c);
+}
+
 /* warp 1 after the last step: x_i = c_i - M_i x_{i-1} in ascending order and computeScale() (gen_subst_scale,
  * chain case); x_i is left over c_i in the L record.  The L record and b of pose i + 1 are staged into shared
  * memory (two buffers of GIT_HAND rows, tile base `stage`) while pose i is substituted. */
@@ -1239,6 +1401,80 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
             GIT_TICK(1);
         }
         /* ---- F ---- */
+#if UWBGO_GIT_COOP
+        {
+            if (warp == 0) {
+                LmState st;
+                st.load(sh, lane);
+                if (!st.done && st.need_lin) {
+                    st.stale = st.plainCur;
+                    double maxdiag = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        const double m = dsm[k * TILE + lane];
+                        if (m > maxdiag) maxdiag = m;
+                    }
+                    if (st.it == 0) {
+                        st.lambda = cfg.tau * maxdiag;
+                        st.ni = 2.0;
+                    }
+                    st.rho = 0.0;
+                    st.q = 0;
+                    st.need_lin = false;
+                    st.store(sh, lane);
+                }
+                sh.lam[lane] = st.lambda;
+            }
+            const GitEnv G = env();
+            double *hand = dsm + lane, *stage = dsm + 2 * GIT_HAND * TILE;
+            const double *HBt = G.E.p.HB - lane;
+            /* one pass over the chain, three barriers per pose (phases A | B | C above) */
+            auto sweep = [&](auto math) -> bool {
+                using MATH = decltype(math);
+                unsigned fl = 0;
+                if (warp > 0) {
+                    stage_rows_coop<NW>(stage + (size_t)((N - 1) & 1) * GIT_HAND * TILE, HBt + (size_t)(N - 1) * HR_GEN * TILE, HR_GEN, warp, lane);
+                    cp_commit();
+                    cp_wait<0>();
+                }
+                __syncthreads(); /* (also: lambda is published, the maxima of the H phase have been read) */
+                const double lambda = sh.lam[lane];
+                for (int i = N - 1; i >= 0; --i) {
+                    double *hi = stage + (size_t)(i & 1) * GIT_HAND * TILE + lane;
+                    double *Gc = hand + (size_t)((i + 1) & 1) * GIT_HAND * TILE, *Gn = hand + (size_t)(i & 1) * GIT_HAND * TILE;
+                    coop_form_S<NW>(hi, Gc, i + 1 < N, lambda, warp);
+                    __syncthreads();
+                    if (warp == 0)
+                        fl |= coop_potrf<MATH>(hi, Gn);
+                    else {
+                        if (i > 0) {
+                            stage_rows_coop<NW>(stage + (size_t)((i - 1) & 1) * GIT_HAND * TILE, HBt + (size_t)(i - 1) * HR_GEN * TILE, HR_GEN, warp, lane);
+                            cp_commit();
+                        }
+                        if (i + 1 < N)
+                            for (int u = warp - 1; u < 7; u += NW - 1) coop_helper_task(Gc, G.E.p.LR + (size_t)(i + 1) * LR_GEN * TILE, u, true);
+                    }
+                    __syncthreads();
+                    if (warp > 0) {
+                        for (int v = warp - 1; v < 7; v += NW - 1) coop_trsm_task(hi, Gn, v, i > 0);
+                        cp_wait<0>();
+                    }
+                    __syncthreads();
+                }
+                if (warp == 0) {
+                    sh.tok[lane] = (fl & 1u) ? 0 : 1;
+                    const bool redo = __any_sync(0xffffffffu, sh.act[lane] != 0 && (fl & 2u) != 0);
+                    if (lane == 0) sh.redo = redo ? 1 : 0;
+                } else
+                    for (int u = warp - 1; u < 7; u += NW - 1) coop_helper_task(hand + (size_t)0 * GIT_HAND * TILE, G.E.p.LR, u, false);
+                __syncthreads();
+                return sh.redo != 0;
+            };
+            if (sweep(NbMath{})) sweep(IeeeMath{}); /* a trial only writes scratch: the repeat gives the IEEE bits */
+            if (warp == 0) GIT_TICK(6);
+            if (warp == 1) sh.tscale[lane] = subst_scale_chain(G.E, stage, lane, sh.tok[lane] != 0, sh.lam[lane]);
+        }
+#else
         if (warp == 0) {
             double lambda;
             {
@@ -1309,6 +1545,7 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
             } while (*reinterpret_cast<volatile int *>(&sh.redo)); /* written before the last barrier of the sweep */
             sh.tscale[lane] = subst_scale_chain(G.E, stage, lane, sh.tok[lane] != 0, sh.lam[lane]);
         }
+#endif
         __syncthreads();
         GIT_TICK(2);
         /* ---- U ---- */

@@ -97,6 +97,8 @@ struct LmState {
 };
 
 UWBGO_DI void bar_pair() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+/* barrier 0 over the whole CTA from warp-specialised branches (what __syncthreads() compiles to) */
+UWBGO_DI void cta_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 /* asynchronous copies global -> shared (LDGSTS), 16 bytes per lane and instruction, past L1 */
 UWBGO_DI void cp_async16(void *smem, const void *gmem)
@@ -978,86 +980,269 @@ UWBGO_DI void factor_helper_step(const double *__restrict__ Gn, double *__restri
 #define UWBGO_GIT_COOP 1
 #endif
 
-UWBGO_DI void coop_upper_jr(int t, int &j, int &r) /* t = up_idx(6, j, r) */
+/* phase A, row R of the upper triangle: S(j, R) for j <= R and the G_c z_c part of z_i[R]; G_c row R and z_c stay in
+ * registers, the rows j < R stream through */
+template <int R>
+UWBGO_DI void coop_S_row(double *__restrict__ h, const double *__restrict__ Gc, bool link, double lambda)
 {
-    int base = 0;
-    j = 0;
-    while (t >= base + 6 - j) {
-        base += 6 - j;
-        ++j;
+    double acc[R + 2];
+#pragma unroll
+    for (int j = 0; j <= R; ++j) acc[j] = ROW(h, up_idx(6, j, R));
+    acc[R] = acc[R] + lambda;
+    acc[R + 1] = ROW(h, 57 + R);
+    if (link) {
+        double gr[6], zn[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            gr[k] = ROW(Gc, R * 6 + k);
+            zn[k] = ROW(Gc, 57 + k);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            double gj[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) gj[k] = ROW(Gc, j * 6 + k);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[j] = fma(-gr[k], gj[k], acc[j]);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[R] = fma(-gr[k], gr[k], acc[R]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[R + 1] = fma(-gr[k], zn[k], acc[R + 1]);
     }
-    r = j + (t - base);
+#pragma unroll
+    for (int j = 0; j <= R; ++j) ROW(h, up_idx(6, j, R)) = acc[j];
+    ROW(h, 57 + R) = acc[R + 1];
 }
 
-template <int NW>
+/* warps 1, 2, 3 take the row pairs (0, 5), (1, 4), (2, 3): nine sums and ~48 shared-memory loads each (every further
+ * warp would load the rows of G_c again: a row is 256 bytes, two cycles of the SM's shared-memory pipe) */
 UWBGO_DI void coop_form_S(double *__restrict__ h, const double *__restrict__ Gc, bool link, double lambda, int warp)
 {
-    constexpr int PER = (27 + NW - 1) / NW;
-    double v[PER];
-    int row[PER];
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int t = warp + q * NW;
-        row[q] = -1;
-        v[q] = 0.0;
-        if (t < 21) {
-            int j, r;
-            coop_upper_jr(t, j, r);
-            row[q] = t;
-            double s = ROW(h, t);
-            if (r == j) s = s + lambda;
-            if (link) {
-                const double *gr = Gc + (size_t)(r * 6) * TILE, *gj = Gc + (size_t)(j * 6) * TILE;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) s = fma(-ROW(gr, k), ROW(gj, k), s);
-            }
-            v[q] = s;
-        } else if (t < 27) {
-            const int r = t - 21;
-            row[q] = 57 + r;
-            double s = ROW(h, 57 + r);
-            if (link) {
-                const double *gr = Gc + (size_t)(r * 6) * TILE;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) s = fma(-ROW(gr, k), ROW(Gc, 57 + k), s);
-            }
-            v[q] = s;
-        }
+    if (warp == 1) {
+        coop_S_row<5>(h, Gc, link, lambda);
+        coop_S_row<0>(h, Gc, link, lambda);
+    } else if (warp == 2) {
+        coop_S_row<4>(h, Gc, link, lambda);
+        coop_S_row<1>(h, Gc, link, lambda);
+    } else if (warp == 3) {
+        coop_S_row<3>(h, Gc, link, lambda);
+        coop_S_row<2>(h, Gc, link, lambda);
     }
-#pragma unroll
-    for (int q = 0; q < PER; ++q)
-        if (row[q] >= 0) ROW(h, row[q]) = v[q];
 }
 
-/* warp 0: the Cholesky factor of S_i (rows 0..20 of the staged record after phase A); the diagonal slot keeps
- * 1 / L_jj.  Returns bit 0 = a pivot was not positive, bit 1 = the branch-free roots flagged an operand */
+/* warp 0, phases B and C: the Cholesky factor of S_i (rows 0..20 of the staged record after phase A; the diagonal slot
+ * keeps 1 / L_jj) into the hand-off buffer, then, behind the barrier that releases the G rows, z_i from its G_c z_c
+ * part (rows 57..62) with L_i still in registers.  Straight-line code on scalars (generated; the loops of
+ * factor_step<6> written out in their order): as loops over L[21] ptxas keeps the array in local memory.  Column
+ * j + 1 of S is loaded behind the pivot operand of column j (see after()): it arrives during that pivot's root and
+ * the 21 loads cannot all be lifted to the top.  fl: bit 0 = a pivot was not positive, bit 1 = the branch-free roots
+ * flagged an operand */
 template <class M>
-UWBGO_DI unsigned coop_potrf(const double *__restrict__ h, double *__restrict__ Gn)
+UWBGO_DI void coop_potrf_z(const double *__restrict__ h, double *__restrict__ Gn, unsigned &fl)
 {
     bool ok = true;
     unsigned bad = 0;
-    double S[21], L[21];
+    double s;
+    double c0 = ROW(h, 0), c1 = ROW(h, 1), c2 = ROW(h, 2), c3 = ROW(h, 3), c4 = ROW(h, 4), c5 = ROW(h, 5);
+    /* column 0 */
+    s = c0;
+    const double *h1 = h + after(s);
+    const double n1_1 = ROW(h1, 6), n1_2 = ROW(h1, 7), n1_3 = ROW(h1, 8), n1_4 = ROW(h1, 9), n1_5 = ROW(h1, 10);
+    if (!(s > 0.0)) ok = false;
+    const double l00 = M::rsqrt_pivot(s, bad);
+    s = c1;
+    const double l10 = s * l00;
+    s = c2;
+    const double l20 = s * l00;
+    s = c3;
+    const double l30 = s * l00;
+    s = c4;
+    const double l40 = s * l00;
+    s = c5;
+    const double l50 = s * l00;
+    c1 = n1_1;
+    c2 = n1_2;
+    c3 = n1_3;
+    c4 = n1_4;
+    c5 = n1_5;
+    /* column 1 */
+    s = c1;
+    s = fma(-l10, l10, s);
+    const double *h2 = h + after(s);
+    const double n2_2 = ROW(h2, 11), n2_3 = ROW(h2, 12), n2_4 = ROW(h2, 13), n2_5 = ROW(h2, 14);
+    if (!(s > 0.0)) ok = false;
+    const double l11 = M::rsqrt_pivot(s, bad);
+    s = c2;
+    s = fma(-l20, l10, s);
+    const double l21 = s * l11;
+    s = c3;
+    s = fma(-l30, l10, s);
+    const double l31 = s * l11;
+    s = c4;
+    s = fma(-l40, l10, s);
+    const double l41 = s * l11;
+    s = c5;
+    s = fma(-l50, l10, s);
+    const double l51 = s * l11;
+    c2 = n2_2;
+    c3 = n2_3;
+    c4 = n2_4;
+    c5 = n2_5;
+    /* column 2 */
+    s = c2;
+    s = fma(-l20, l20, s);
+    s = fma(-l21, l21, s);
+    const double *h3 = h + after(s);
+    const double n3_3 = ROW(h3, 15), n3_4 = ROW(h3, 16), n3_5 = ROW(h3, 17);
+    if (!(s > 0.0)) ok = false;
+    const double l22 = M::rsqrt_pivot(s, bad);
+    s = c3;
+    s = fma(-l30, l20, s);
+    s = fma(-l31, l21, s);
+    const double l32 = s * l22;
+    s = c4;
+    s = fma(-l40, l20, s);
+    s = fma(-l41, l21, s);
+    const double l42 = s * l22;
+    s = c5;
+    s = fma(-l50, l20, s);
+    s = fma(-l51, l21, s);
+    const double l52 = s * l22;
+    c3 = n3_3;
+    c4 = n3_4;
+    c5 = n3_5;
+    /* column 3 */
+    s = c3;
+    s = fma(-l30, l30, s);
+    s = fma(-l31, l31, s);
+    s = fma(-l32, l32, s);
+    const double *h4 = h + after(s);
+    const double n4_4 = ROW(h4, 18), n4_5 = ROW(h4, 19);
+    if (!(s > 0.0)) ok = false;
+    const double l33 = M::rsqrt_pivot(s, bad);
+    s = c4;
+    s = fma(-l40, l30, s);
+    s = fma(-l41, l31, s);
+    s = fma(-l42, l32, s);
+    const double l43 = s * l33;
+    s = c5;
+    s = fma(-l50, l30, s);
+    s = fma(-l51, l31, s);
+    s = fma(-l52, l32, s);
+    const double l53 = s * l33;
+    c4 = n4_4;
+    c5 = n4_5;
+    /* column 4 */
+    s = c4;
+    s = fma(-l40, l40, s);
+    s = fma(-l41, l41, s);
+    s = fma(-l42, l42, s);
+    s = fma(-l43, l43, s);
+    const double *h5 = h + after(s);
+    const double n5_5 = ROW(h5, 20);
+    if (!(s > 0.0)) ok = false;
+    const double l44 = M::rsqrt_pivot(s, bad);
+    s = c5;
+    s = fma(-l50, l40, s);
+    s = fma(-l51, l41, s);
+    s = fma(-l52, l42, s);
+    s = fma(-l53, l43, s);
+    const double l54 = s * l44;
+    c5 = n5_5;
+    /* column 5 */
+    s = c5;
+    s = fma(-l50, l50, s);
+    s = fma(-l51, l51, s);
+    s = fma(-l52, l52, s);
+    s = fma(-l53, l53, s);
+    s = fma(-l54, l54, s);
+    if (!(s > 0.0)) ok = false;
+    const double l55 = M::rsqrt_pivot(s, bad);
+    ROW(Gn, 36) = l00;
+    ROW(Gn, 37) = l10;
+    ROW(Gn, 38) = l11;
+    ROW(Gn, 39) = l20;
+    ROW(Gn, 40) = l21;
+    ROW(Gn, 41) = l22;
+    ROW(Gn, 42) = l30;
+    ROW(Gn, 43) = l31;
+    ROW(Gn, 44) = l32;
+    ROW(Gn, 45) = l33;
+    ROW(Gn, 46) = l40;
+    ROW(Gn, 47) = l41;
+    ROW(Gn, 48) = l42;
+    ROW(Gn, 49) = l43;
+    ROW(Gn, 50) = l44;
+    ROW(Gn, 51) = l50;
+    ROW(Gn, 52) = l51;
+    ROW(Gn, 53) = l52;
+    ROW(Gn, 54) = l53;
+    ROW(Gn, 55) = l54;
+    ROW(Gn, 56) = l55;
+    fl |= (ok ? 0u : 1u) | (bad ? 2u : 0u);
+    double z0 = ROW(h, 57), z1 = ROW(h, 58), z2 = ROW(h, 59), z3 = ROW(h, 60), z4 = ROW(h, 61), z5 = ROW(h, 62);
+    cta_bar();
+    s = z0;
+    z0 = s * l00;
+    s = z1;
+    s = fma(-l10, z0, s);
+    z1 = s * l11;
+    s = z2;
+    s = fma(-l20, z0, s);
+    s = fma(-l21, z1, s);
+    z2 = s * l22;
+    s = z3;
+    s = fma(-l30, z0, s);
+    s = fma(-l31, z1, s);
+    s = fma(-l32, z2, s);
+    z3 = s * l33;
+    s = z4;
+    s = fma(-l40, z0, s);
+    s = fma(-l41, z1, s);
+    s = fma(-l42, z2, s);
+    s = fma(-l43, z3, s);
+    z4 = s * l44;
+    s = z5;
+    s = fma(-l50, z0, s);
+    s = fma(-l51, z1, s);
+    s = fma(-l52, z2, s);
+    s = fma(-l53, z3, s);
+    s = fma(-l54, z4, s);
+    z5 = s * l55;
+    ROW(Gn, 57) = z0;
+    ROW(Gn, 58) = z1;
+    ROW(Gn, 59) = z2;
+    ROW(Gn, 60) = z3;
+    ROW(Gn, 61) = z4;
+    ROW(Gn, 62) = z5;
+}
+
+/* warps 1, 2, 3, phase C: rows 2 (warp - 1) and 2 (warp - 1) + 1 of G_i = H_{i-1,i} L_i^-T (one load of L_i for both) */
+UWBGO_DI void coop_G_rows(const double *__restrict__ h, double *__restrict__ Gn, int r0)
+{
+    double L[21], g[2][6];
 #pragma unroll
-    for (int k = 0; k < 21; ++k) S[k] = ROW(h, k);
+    for (int k = 0; k < 21; ++k) L[k] = ROW(Gn, 36 + k);
+    const double *src = h + (size_t)(21 + r0 * 6) * TILE;
+    double *dst = Gn + (size_t)(r0 * 6) * TILE;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double s = S[up_idx(6, j, j)];
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int k = 0; k < j; ++k) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
-        if (!(s > 0.0)) ok = false;
-        const double inv = M::rsqrt_pivot(s, bad);
-        L[lo_idx(j, j)] = inv;
+        for (int cc = 0; cc < 6; ++cc) g[q][cc] = ROW(src, q * 6 + cc);
 #pragma unroll
-        for (int r = j + 1; r < 6; ++r) {
-            double t = S[up_idx(6, j, r)];
+    for (int cc = 0; cc < 6; ++cc)
 #pragma unroll
-            for (int k = 0; k < j; ++k) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
-            L[lo_idx(r, j)] = t * inv;
+        for (int q = 0; q < 2; ++q) {
+            double s = g[q][cc];
+#pragma unroll
+            for (int k = 0; k < cc; ++k) s = fma(-g[q][k], L[lo_idx(cc, k)], s);
+            g[q][cc] = s * L[lo_idx(cc, cc)];
         }
-    }
 #pragma unroll
-    for (int k = 0; k < 21; ++k) ROW(Gn, 36 + k) = L[k];
-    return (ok ? 0u : 1u) | (bad ? 2u : 0u);
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) ROW(dst, q * 6 + cc) = g[q][cc];
 }
 
 /* task u of pose p's L record: u = 6: c_p = L_p^-T z_p; u < 6: column u of M_p = L_p^-T G_p^T */
@@ -1085,37 +1270,6 @@ UWBGO_DI void coop_helper_task(const double *__restrict__ Gn, double *__restrict
 #pragma unroll
         for (int r = 0; r < 6; ++r) ROW(dst, r * 6) = m[r];
     }
-}
-
-/* task v of step i: v = 6: z_i from its G_c z_c part (rows 57..62 of the staged record after phase A); v < 6: row v
- * of G_i = H_{i-1,i} L_i^-T */
-UWBGO_DI void coop_trsm_task(const double *__restrict__ h, double *__restrict__ Gn, int v, bool has_prev)
-{
-    if (v < 6 && !has_prev) return;
-    double L[21], g[6];
-#pragma unroll
-    for (int k = 0; k < 21; ++k) L[k] = ROW(Gn, 36 + k);
-    const double *src = h + (size_t)(v < 6 ? 21 + v * 6 : 57) * TILE;
-    double *dst = Gn + (size_t)(v < 6 ? v * 6 : 57) * TILE;
-    if (v == 6) {
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            double s = ROW(src, r);
-#pragma unroll
-            for (int k = 0; k < r; ++k) s = fma(-L[lo_idx(r, k)], g[k], s);
-            g[r] = s * L[lo_idx(r, r)];
-        }
-    } else {
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) {
-            double s = ROW(src, cc);
-#pragma unroll
-            for (int k = 0; k < cc; ++k) s = fma(-g[k], L[lo_idx(cc, k)], s);
-            g[cc] = s * L[lo_idx(cc, cc)];
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) ROW(dst, k) = g[k];
 }
 
 /* warps 1 .. NW-1 together stage `rows` consecutive rows of a tile array */
@@ -1174,12 +1328,64 @@ UWBGO_DI double subst_scale_chain(const GenEnv &E, double *stage, int lane, bool
     return scale;
 }
 
+/* subst_scale_chain with the records of FOUR poses in flight: once the elimination is over the hand-off and staging
+ * areas are one idle block of 4 x GIT_HAND rows, which holds a ring of five (L record | b) slots.  One pose ahead,
+ * every step waited out an L2 round trip for its 12 KB (1,450 cycles per pose on C4a) */
+UWBGO_DI double subst_scale_ring(const GenEnv &E, double *ring, int lane, bool ok, double lambda)
+{
+    constexpr int RING = 5, SROWS = LR_GEN + 6;
+    static_assert(RING * SROWS <= 4 * GIT_HAND, "the ring lives in the hand-off + staging areas");
+    const int N = E.tp->N;
+    const double *LRt = E.p.LR - lane, *HBt = E.p.HB - lane;
+    auto pf = [&](int i, int slot) {
+        double *dst = ring + (size_t)slot * SROWS * TILE;
+        stage_rows(dst, LRt + (size_t)i * LR_GEN * TILE, LR_GEN, lane);
+        stage_rows(dst + LR_GEN * TILE, HBt + ((size_t)i * HR_GEN + 57) * TILE, 6, lane);
+    };
+    for (int i = 0; i < RING - 1; ++i) { /* (a group may be empty: the count per step stays the same) */
+        if (i < N) pf(i, i);
+        cp_commit();
+    }
+    double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double scale = 0.0;
+    int slot = 0, slot_pf = RING - 1;
+    for (int i = 0; i < N; ++i) {
+        if (i + RING - 1 < N) pf(i + RING - 1, slot_pf); /* the slot read in step i - 1 */
+        cp_commit();
+        cp_wait<RING - 1>();
+        __syncwarp();
+        const double *l = ring + (size_t)slot * SROWS * TILE + lane;
+        double *lp = E.p.LR + (size_t)i * LR_GEN * TILE;
+        double x[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { /* subst_step<6> */
+            double v = ROW(l, r);
+            if (i > 0) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v = fma(-ROW(l, 6 + r * 6 + j), xp[j], v);
+            }
+            x[r] = v;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) xp[k] = ok ? x[k] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ROW(lp, k) = xp[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) scale = scale + xp[k] * (lambda * xp[k] + ROW(l, LR_GEN + k));
+        __syncwarp(); /* the slot is refilled in the next step */
+        slot = slot + 1 == RING ? 0 : slot + 1;
+        slot_pf = slot_pf + 1 == RING ? 0 : slot_pf + 1;
+    }
+    cp_wait<0>();
+    return scale;
+}
+
 template <int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                         const __grid_constant__ DevWs ws, const int echi_smem)
 {
-    static_assert(NW >= 2 && NW <= 2 * GIT_HAND, "warp 0 eliminates, warp 1 follows");
+    static_assert(NW >= 4 && NW <= 2 * GIT_HAND, "warp 0 eliminates, warps 1..3 form S and G, the others follow");
     __shared__ GitShared sh;
     extern __shared__ __align__(16) double dyn[]; /* topology | hand-off 2 x [63][32] | staging 2 x [63][32] | chi2 terms [2E][32] */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1340,9 +1546,17 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
 
 #ifdef UWBGO_GIT_TIMING
     long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tq = git_clk();
+    long long tf[4] = {0, 0, 0, 0}; /* cooperative F, warp 0: phase A, potrf, wait for C, prologue / epilogue */
 #define GIT_TICK(k) do { long long tn_ = git_clk(); tph[k] += tn_ - tq; tq = tn_; } while (0)
+#define GIT_FTICK(k) do { long long tn_ = git_clk(); tf[k] += tn_ - tq; tph[6] += tn_ - tq; tq = tn_; } while (0)
+    long long tg[6] = {0, 0, 0, 0, 0, 0}, tw = 0; /* cooperative F, warp 1: work and barrier wait of the phases A, B, C */
+#define GIT_WTICK0() do { tw = git_clk(); } while (0)
+#define GIT_WTICK(k) do { long long tn_ = git_clk(); tg[k] += tn_ - tw; tw = tn_; } while (0)
 #else
+#define GIT_WTICK0()
+#define GIT_WTICK(k)
 #define GIT_TICK(k)
+#define GIT_FTICK(k)
 #endif
     const int n6 = tp.Ep + tp.Es;
     while (sh.go) {
@@ -1437,29 +1651,38 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
                     cp_commit();
                     cp_wait<0>();
                 }
-                __syncthreads(); /* (also: lambda is published, the maxima of the H phase have been read) */
+                cta_bar(); /* (also: lambda is published, the maxima of the H phase have been read) */
+                GIT_FTICK(3);
                 const double lambda = sh.lam[lane];
                 for (int i = N - 1; i >= 0; --i) {
                     double *hi = stage + (size_t)(i & 1) * GIT_HAND * TILE + lane;
                     double *Gc = hand + (size_t)((i + 1) & 1) * GIT_HAND * TILE, *Gn = hand + (size_t)(i & 1) * GIT_HAND * TILE;
-                    coop_form_S<NW>(hi, Gc, i + 1 < N, lambda, warp);
-                    __syncthreads();
-                    if (warp == 0)
-                        fl |= coop_potrf<MATH>(hi, Gn);
-                    else {
+                    GIT_WTICK0();
+                    coop_form_S(hi, Gc, i + 1 < N, lambda, warp);
+                    GIT_WTICK(0);
+                    cta_bar();
+                    GIT_WTICK(1);
+                    GIT_FTICK(0);
+                    if (warp == 0) {
+                        coop_potrf_z<MATH>(hi, Gn, fl); /* (holds the barrier between phases B and C) */
+                        GIT_FTICK(1);
+                    } else {
                         if (i > 0) {
                             stage_rows_coop<NW>(stage + (size_t)((i - 1) & 1) * GIT_HAND * TILE, HBt + (size_t)(i - 1) * HR_GEN * TILE, HR_GEN, warp, lane);
                             cp_commit();
                         }
                         if (i + 1 < N)
                             for (int u = warp - 1; u < 7; u += NW - 1) coop_helper_task(Gc, G.E.p.LR + (size_t)(i + 1) * LR_GEN * TILE, u, true);
-                    }
-                    __syncthreads();
-                    if (warp > 0) {
-                        for (int v = warp - 1; v < 7; v += NW - 1) coop_trsm_task(hi, Gn, v, i > 0);
+                        GIT_WTICK(2);
+                        cta_bar();
+                        GIT_WTICK(3);
+                        if (warp <= 3 && i > 0) coop_G_rows(hi, Gn, 2 * (warp - 1));
                         cp_wait<0>();
+                        GIT_WTICK(4);
                     }
-                    __syncthreads();
+                    cta_bar();
+                    GIT_WTICK(5);
+                    GIT_FTICK(2);
                 }
                 if (warp == 0) {
                     sh.tok[lane] = (fl & 1u) ? 0 : 1;
@@ -1467,12 +1690,13 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
                     if (lane == 0) sh.redo = redo ? 1 : 0;
                 } else
                     for (int u = warp - 1; u < 7; u += NW - 1) coop_helper_task(hand + (size_t)0 * GIT_HAND * TILE, G.E.p.LR, u, false);
-                __syncthreads();
+                cta_bar();
+                GIT_FTICK(3);
                 return sh.redo != 0;
             };
             if (sweep(NbMath{})) sweep(IeeeMath{}); /* a trial only writes scratch: the repeat gives the IEEE bits */
             if (warp == 0) GIT_TICK(6);
-            if (warp == 1) sh.tscale[lane] = subst_scale_chain(G.E, stage, lane, sh.tok[lane] != 0, sh.lam[lane]);
+            if (warp == 1) sh.tscale[lane] = subst_scale_ring(G.E, dsm, lane, sh.tok[lane] != 0, sh.lam[lane]);
         }
 #else
         if (warp == 0) {
@@ -1623,6 +1847,14 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
     if (threadIdx.x == 0 && blockIdx.x < 2)
         printf("tile %d cycles (warp 0's own items + wait at the barrier): J %lld + %lld  H %lld + %lld  F %lld + %lld  U %lld + %lld  C %lld + %lld  D (load %lld, sums %lld, decision %lld, barrier %lld)\n",
                (int)blockIdx.x, tph[8], tph[0], tph[9], tph[1], tph[6], tph[2], tph[11], tph[3], tph[12], tph[4], tph[13], tph[14], tph[15], tph[5]);
+#if UWBGO_GIT_COOP
+    if (threadIdx.x == 0 && blockIdx.x < 2)
+        printf("tile %d cooperative elimination, warp 0: phase A + barrier %lld, potrf %lld, waits out phases B / C %lld, prologue / epilogue %lld\n",
+               (int)blockIdx.x, tf[0], tf[1], tf[2], tf[3]);
+    if (threadIdx.x == 32 && blockIdx.x < 2)
+        printf("tile %d cooperative elimination, warp 1: A work %lld + barrier %lld, B work %lld + barrier %lld, C work %lld + barrier %lld\n",
+               (int)blockIdx.x, tg[0], tg[1], tg[2], tg[3], tg[4], tg[5]);
+#endif
 #endif
 
     if (warp == 0 && valid) {

@@ -24,6 +24,7 @@
  * Chains only (parent(i) = i - 1 or none); forest windows (pose edges to a key vertex) keep lm_general_cta_kernel.
  */
 #include <cstdlib>
+#include <type_traits>
 #include "uwbgo_general.cuh"
 #ifdef UWBGO_GIT_TIMING
 #include <cstdio>
@@ -65,6 +66,7 @@ struct GitShared {
     int act[TILE];                    /* D -> all: window still being optimised                           */
     int go, anylin, redo;
     double rinc[6][9];                /* the six rotation increments of the numeric Jacobians: fromVectorMQT(+-delta e_k) */
+    int rinc_sparse;                  /* each of them is I plus one antisymmetric pair (bit patterns), see jac_v0_m */
     int diag;                         /* every prior information matrix of the tile is diagonal (bit patterns) */
     int ctr[4];                       /* next item of the J, H, U, C phase: the warps of the tile draw their items from a queue */
     int zero;                         /* 0, read through a volatile pointer: keeps per-phase address arithmetic per phase */
@@ -123,6 +125,7 @@ struct GitEnv {
     GenEnv E;
     double *jrec; /* this lane's column of the tile's linearisation records */
     const double *rinc; /* [6][9] rotation increments of the numeric Jacobians (shared memory) */
+    bool rinc_sparse;
     int Er, Ep, Es;
 };
 
@@ -194,10 +197,24 @@ UWBGO_DI void jt_omega_t(const double *J, const double *__restrict__ O, bool rob
 /* gen_jac_v0 / gen_jac_v1 of uwbgo_general.cuh with the roots of a math policy M (NbMath: branch-free, so that the
  * twelve perturbed residuals of an edge interleave; an operand outside its range raises `bad` and the item is
  * evaluated again with IeeeMath: same bits) */
-template <class M, bool SECOND = false>
-UWBGO_DI void jac_v0_m(const GenEnv &E, const double *rinc, const Pose &X, int ant, const double *Q, double d, int c0, int base,
-                       double *J, unsigned &bad)
+template <class M, bool SPARSE, bool SECOND = false>
+UWBGO_DI void jac_v0_m(const GenEnv &E, const double *rinc, const Pose &X, int ant, const double *Q, double d, int c0,
+                       int base, double *J, unsigned &bad)
 {
+    /* Sparse increments (rinc_sparse: B = I + B[j][k] + B[k][j], every other entry 1 or (+-)0): mat3_mul's
+     * (A[r][0] B[0][c] + A[r][1] B[1][c]) + A[r][2] B[2][c] is then A[r][c] plus at most one rounded product -- the terms
+     * dropped are products of a FINITE number with a zero, which leave a non-zero sum unchanged, and where the sum is
+     * zero they can only change its sign, which the squares of dist3 absorb (the perturbed rotation is used for this
+     * residual alone).  12 instead of 45 operations per perturbed rotation, same bits in J.  Only with the branch-free
+     * policy: a non-finite rotation entry raises `bad`, and the repeat with IeeeMath takes the dense product. */
+    static_assert(!SPARSE || std::is_same<M, NbMath>::value, "the sparse product is the branch-free policy's");
+    constexpr bool sparse = SPARSE;
+    if (sparse && ant > 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) t = fma(X.R[k], 0.0, t);
+        if (t != t) bad |= 1u;
+    }
     const int mod = E.cfg->orth_mod;
     double o[3] = {0.0, 0.0, 0.0};
     if (ant > 0) {
@@ -242,10 +259,22 @@ UWBGO_DI void jac_v0_m(const GenEnv &E, const double *rinc, const Pose &X, int a
             for (int sg = 0; sg < 2; ++sg) {
                 if (++call == mod) call = 0;
                 /* the increment depends on delta alone: the six matrices are formed once per CTA (same operations) */
-                double Rinc[9], Rp[9], P[3];
+                double Rp[9], P[3];
+                if (sparse) {
+                    const int jj = (dd + 1) % 3, kk = (dd + 2) % 3;
+                    const double bjk = rinc[9 * (2 * dd + sg) + 3 * jj + kk], bkj = rinc[9 * (2 * dd + sg) + 3 * kk + jj];
 #pragma unroll
-                for (int k = 0; k < 9; ++k) Rinc[k] = rinc[9 * (2 * dd + sg) + k];
-                mat3_mul(X.R, Rinc, Rp);
+                    for (int r = 0; r < 3; ++r) {
+                        Rp[3 * r + dd] = X.R[3 * r + dd];
+                        Rp[3 * r + kk] = X.R[3 * r + kk] + X.R[3 * r + jj] * bjk;
+                        Rp[3 * r + jj] = X.R[3 * r + jj] + X.R[3 * r + kk] * bkj;
+                    }
+                } else {
+                    double Rinc[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Rinc[k] = rinc[9 * (2 * dd + sg) + k];
+                    mat3_mul(X.R, Rinc, Rp);
+                }
                 if (call == 0) orthogonalize(Rp);
                 mat3_vec_add(Rp, o, X.t, P);
                 epm[sg] = SECOND ? d - dist3m<M>(Q[0], Q[1], Q[2], P[0], P[1], P[2], bad)
@@ -302,7 +331,7 @@ UWBGO_DI int next_item(int *ctr, int lane)
 /* ---- J items ------------------------------------------------------------------------------------------------ */
 
 /* range edge, slot k: error, weights and the numeric Jacobian wrt vertex 0 (gen_linearize_pose_acc, role 0) */
-template <class M>
+template <class M, bool SPARSE = false>
 UWBGO_DI unsigned item_range_v0(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int k)
 {
     unsigned bad = 0;
@@ -332,7 +361,7 @@ UWBGO_DI unsigned item_range_v0(const GitEnv &G, const GitTopo &tt, const PoseBu
         omega_r = omega_r * r1;
         Ow = r1 * info;
     }
-    jac_v0_m<M>(E, G.rinc, Xa, er.ant, Q, d, E.p.cnt[(size_t)er.a * TILE], er.base_a, A, bad);
+    jac_v0_m<M, SPARSE>(E, G.rinc, Xa, er.ant, Q, d, E.p.cnt[(size_t)er.a * TILE], er.base_a, A, bad);
 #pragma unroll
     for (int j = 0; j < 6; ++j) ROW(rec, j) = A[j];
     ROW(rec, 12) = Ow;
@@ -341,7 +370,7 @@ UWBGO_DI unsigned item_range_v0(const GitEnv &G, const GitTopo &tt, const PoseBu
 }
 
 /* pose-pose range edge, slot k: numeric Jacobian wrt vertex 1 (gen_linearize_pose_acc, role 1) */
-template <class M>
+template <class M, bool SPARSE = false>
 UWBGO_DI unsigned item_range_v1(const GitEnv &G, const GitTopo &tt, const PoseBuf &T, int k)
 {
     unsigned bad = 0;
@@ -356,7 +385,7 @@ UWBGO_DI unsigned item_range_v1(const GitEnv &G, const GitTopo &tt, const PoseBu
     double P0[3], B[6];
     offset_point(E, Xa, er.ant, P0);
     if (er.ant_b > 0)
-        jac_v0_m<M, true>(E, G.rinc, Xb, er.ant_b, P0, d, E.p.cnt[(size_t)er.b * TILE], er.base_b, B, bad);
+        jac_v0_m<M, SPARSE, true>(E, G.rinc, Xb, er.ant_b, P0, d, E.p.cnt[(size_t)er.b * TILE], er.base_b, B, bad);
     else
         jac_v1_m<M>(E, P0, Xb, d, B, bad);
 #pragma unroll
@@ -979,6 +1008,9 @@ UWBGO_DI void factor_helper_step(const double *__restrict__ Gn, double *__restri
 #ifndef UWBGO_GIT_COOP
 #define UWBGO_GIT_COOP 1
 #endif
+#ifndef UWBGO_GIT_SPARSE_RINC
+#define UWBGO_GIT_SPARSE_RINC 1 /* 0: dense rotation increments in the numeric Jacobians (A/B) */
+#endif
 
 /* phase A, row R of the upper triangle: S(j, R) for j <= R and the G_c z_c part of z_i[R]; G_c row R and z_c stay in
  * registers, the rows j < R stream through */
@@ -1328,32 +1360,49 @@ UWBGO_DI double subst_scale_chain(const GenEnv &E, double *stage, int lane, bool
     return scale;
 }
 
-/* subst_scale_chain with the records of FOUR poses in flight: once the elimination is over the hand-off and staging
- * areas are one idle block of 4 x GIT_HAND rows, which holds a ring of five (L record | b) slots.  One pose ahead,
- * every step waited out an L2 round trip for its 12 KB (1,450 cycles per pose on C4a) */
-UWBGO_DI double subst_scale_ring(const GenEnv &E, double *ring, int lane, bool ok, double lambda)
+/* subst_scale_chain on four warps: warp 1 substitutes, warps 2..4 feed it.  Once the elimination is over the hand-off
+ * and staging areas are one idle block of 4 x GIT_HAND rows, which holds a ring of five (L record | b) slots; each
+ * feeding warp copies a third of a slot three poses ahead and releases pose i at one named barrier per pose (a slot
+ * is refilled two barriers after its last read).  Alone, warp 1 spent 1,450 cycles per pose issuing its own copies
+ * and waiting out the L2 round trip behind them */
+UWBGO_DI void bar_subst() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+UWBGO_DI double subst_scale_split(const GenEnv &E, double *ring, int lane, int role, bool ok, double lambda)
 {
-    constexpr int RING = 5, SROWS = LR_GEN + 6;
+    constexpr int RING = 5, DIST = 3, SROWS = LR_GEN + 6;
     static_assert(RING * SROWS <= 4 * GIT_HAND, "the ring lives in the hand-off + staging areas");
+    static_assert(LR_GEN == 42 && SROWS == 48, "three feeding warps, sixteen rows each");
     const int N = E.tp->N;
-    const double *LRt = E.p.LR - lane, *HBt = E.p.HB - lane;
-    auto pf = [&](int i, int slot) {
-        double *dst = ring + (size_t)slot * SROWS * TILE;
-        stage_rows(dst, LRt + (size_t)i * LR_GEN * TILE, LR_GEN, lane);
-        stage_rows(dst + LR_GEN * TILE, HBt + ((size_t)i * HR_GEN + 57) * TILE, 6, lane);
-    };
-    for (int i = 0; i < RING - 1; ++i) { /* (a group may be empty: the count per step stays the same) */
-        if (i < N) pf(i, i);
-        cp_commit();
+    if (role > 0) {
+        const double *LRt = E.p.LR - lane, *HBt = E.p.HB - lane;
+        auto pf = [&](int i, int slot) {
+            double *dst = ring + (size_t)slot * SROWS * TILE;
+            if (role < 3)
+                stage_rows(dst + (size_t)(16 * (role - 1)) * TILE, LRt + ((size_t)i * LR_GEN + 16 * (role - 1)) * TILE, 16, lane);
+            else {
+                stage_rows(dst + (size_t)32 * TILE, LRt + ((size_t)i * LR_GEN + 32) * TILE, LR_GEN - 32, lane);
+                stage_rows(dst + (size_t)LR_GEN * TILE, HBt + ((size_t)i * HR_GEN + 57) * TILE, 6, lane);
+            }
+        };
+        for (int i = 0; i < DIST; ++i) { /* (a group may be empty: the count per step stays the same) */
+            if (i < N) pf(i, i);
+            cp_commit();
+        }
+        int slot_pf = DIST;
+        for (int i = 0; i < N; ++i) {
+            if (i + DIST < N) pf(i + DIST, slot_pf);
+            cp_commit();
+            cp_wait<DIST>();
+            bar_subst(); /* pose i is in its slot */
+            slot_pf = slot_pf + 1 == RING ? 0 : slot_pf + 1;
+        }
+        cp_wait<0>();
+        return 0.0;
     }
     double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double scale = 0.0;
-    int slot = 0, slot_pf = RING - 1;
+    int slot = 0;
     for (int i = 0; i < N; ++i) {
-        if (i + RING - 1 < N) pf(i + RING - 1, slot_pf); /* the slot read in step i - 1 */
-        cp_commit();
-        cp_wait<RING - 1>();
-        __syncwarp();
+        bar_subst();
         const double *l = ring + (size_t)slot * SROWS * TILE + lane;
         double *lp = E.p.LR + (size_t)i * LR_GEN * TILE;
         double x[6];
@@ -1372,11 +1421,8 @@ UWBGO_DI double subst_scale_ring(const GenEnv &E, double *ring, int lane, bool o
         for (int k = 0; k < 6; ++k) ROW(lp, k) = xp[k];
 #pragma unroll
         for (int k = 0; k < 6; ++k) scale = scale + xp[k] * (lambda * xp[k] + ROW(l, LR_GEN + k));
-        __syncwarp(); /* the slot is refilled in the next step */
         slot = slot + 1 == RING ? 0 : slot + 1;
-        slot_pf = slot_pf + 1 == RING ? 0 : slot_pf + 1;
     }
-    cp_wait<0>();
     return scale;
 }
 
@@ -1385,16 +1431,29 @@ __global__ void __launch_bounds__(NW * 32, MINB)
 lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                         const __grid_constant__ DevWs ws, const int echi_smem)
 {
-    static_assert(NW >= 4 && NW <= 2 * GIT_HAND, "warp 0 eliminates, warps 1..3 form S and G, the others follow");
+    static_assert(NW >= 5 && NW <= 2 * GIT_HAND, "warp 0 eliminates, warps 1..3 form S and G, warps 1..4 substitute");
     __shared__ GitShared sh;
     extern __shared__ __align__(16) double dyn[]; /* topology | hand-off 2 x [63][32] | staging 2 x [63][32] | chi2 terms [2E][32] */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (tp.K <= GIT_MAX_SMEM_ANTENNAS)
         for (int k = threadIdx.x; k < 3 * tp.K; k += NW * 32) sh.ant[k] = ws.ant[k];
-    if (threadIdx.x < 6) { /* increment_R of uwbgo_math.cuh on (+-delta) e_k, k = threadIdx.x / 2 */
-        double q[3] = {0.0, 0.0, 0.0};
-        q[threadIdx.x >> 1] = (threadIdx.x & 1) ? -cfg.jdelta : cfg.jdelta;
-        increment_R(q, sh.rinc[threadIdx.x]);
+    if (warp == 0) { /* increment_R of uwbgo_math.cuh on (+-delta) e_k, k = threadIdx.x / 2 */
+        bool sparse = true;
+        if (threadIdx.x < 6) {
+            double q[3] = {0.0, 0.0, 0.0};
+            const int ax = threadIdx.x >> 1;
+            q[ax] = (threadIdx.x & 1) ? -cfg.jdelta : cfg.jdelta;
+            double *B = sh.rinc[threadIdx.x];
+            increment_R(q, B);
+            /* for delta = 1e-9 the increment is I plus the pair B[j][k] = -B[k][j] = -+2 delta (1 - 2 delta^2 rounds to 1);
+             * tested on the bit patterns: unit diagonal, (+-)0 in row and column `ax`, the pair finite */
+            const int j = (ax + 1) % 3, k = (ax + 2) % 3;
+            auto is0 = [](double v) { return (__double_as_longlong(v) & 0x7fffffffffffffffLL) == 0; };
+            sparse = B[0] == 1.0 && B[4] == 1.0 && B[8] == 1.0 && is0(B[3 * ax + j]) && is0(B[3 * ax + k]) && is0(B[3 * j + ax]) &&
+                     is0(B[3 * k + ax]) && isfinite(B[3 * j + k]) && isfinite(B[3 * k + j]);
+        }
+        const bool all = __all_sync(0xffffffffu, sparse);
+        if (lane == 0) sh.rinc_sparse = (all && UWBGO_GIT_SPARSE_RINC) ? 1 : 0;
     }
     if (threadIdx.x == 0) {
         sh.zero = 0;
@@ -1439,6 +1498,7 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
         G.E.delta = cfg.jdelta;
         G.E.scalar = 1.0 / (2.0 * cfg.jdelta);
         G.rinc = &sh.rinc[0][0];
+        G.rinc_sparse = sh.rinc_sparse != 0;
         G.Er = tp.Er;
         G.Ep = tp.Ep;
         G.Es = tp.Es;
@@ -1585,9 +1645,12 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
                         if (diag ? item_prior<NbMath, true>(G, tt, T, u - nS) : item_prior<NbMath, false>(G, tt, T, u - nS))
                             item_prior<IeeeMath, false>(G, tt, T, u - nS);
                     } else if (u < nS + tp.Ep + tp.Er) {
-                        if (item_range_v0<NbMath>(G, tt, T, u - nS - tp.Ep)) item_range_v0<IeeeMath>(G, tt, T, u - nS - tp.Ep);
+                        if (G.rinc_sparse ? item_range_v0<NbMath, true>(G, tt, T, u - nS - tp.Ep) : item_range_v0<NbMath>(G, tt, T, u - nS - tp.Ep))
+                            item_range_v0<IeeeMath>(G, tt, T, u - nS - tp.Ep);
                     } else {
-                        if (item_range_v1<NbMath>(G, tt, T, u - nS - tp.Ep - tp.Er)) item_range_v1<IeeeMath>(G, tt, T, u - nS - tp.Ep - tp.Er);
+                        if (G.rinc_sparse ? item_range_v1<NbMath, true>(G, tt, T, u - nS - tp.Ep - tp.Er)
+                                          : item_range_v1<NbMath>(G, tt, T, u - nS - tp.Ep - tp.Er))
+                            item_range_v1<IeeeMath>(G, tt, T, u - nS - tp.Ep - tp.Er);
                     }
                 }
             }
@@ -1696,7 +1759,10 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
             };
             if (sweep(NbMath{})) sweep(IeeeMath{}); /* a trial only writes scratch: the repeat gives the IEEE bits */
             if (warp == 0) GIT_TICK(6);
-            if (warp == 1) sh.tscale[lane] = subst_scale_ring(G.E, dsm, lane, sh.tok[lane] != 0, sh.lam[lane]);
+            if (warp >= 1 && warp <= 4) {
+                const double sc = subst_scale_split(G.E, dsm, lane, warp - 1, sh.tok[lane] != 0, sh.lam[lane]);
+                if (warp == 1) sh.tscale[lane] = sc;
+            }
         }
 #else
         if (warp == 0) {

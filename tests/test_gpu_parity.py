@@ -82,6 +82,28 @@ def test_prior_information_diagonal_and_dense_tiles(solver):
     assert np.array_equal(got.pose_t[130], ref.pose_t[130], equal_nan=True)
 
 
+@pytest.mark.parametrize("jdelta", [1e-9, 1e-3, 3e-8])
+def test_rotation_increments_sparse_and_dense(solver, jdelta):
+    """the numeric Jacobians of range edges with lever arms perturb the rotation by fromVectorMQT(+-delta e_k); for the
+    default delta = 1e-9 those six matrices are I plus one antisymmetric pair and the ITEM kernel forms the perturbed
+    rotation from the two products that are not structurally zero; a step whose increments are dense (1e-3: 1 - 2
+    delta^2 != 1) takes the dense product.  Identity rotations, rotations with negative zeros and a NaN rotation
+    entry all give the oracle's bits"""
+    topo, batch, _ = synthetic.uwb_imu_lidar(96, 10, 6, seed=33)
+    cfg = Config(max_iterations=5, jacobian_delta=jdelta)
+    assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+    batch.pose_R[:32] = np.eye(3)                                   # tile 0: exact zeros and ones
+    batch.pose_R[32:64] = np.diag([1.0, -1.0, -1.0])                # tile 1: a half turn about x ...
+    batch.pose_R[32:64][batch.pose_R[32:64] == 0.0] = -0.0          # ... with negative zeros off the diagonal
+    batch.pose_R[70, 3, 1, 2] = np.nan                              # tile 2: one window with a NaN rotation entry
+    got, ref = solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg)
+    ok = np.setdiff1d(np.arange(96), [70])
+    assert np.array_equal(got.status[ok], ref.status[ok])
+    assert np.array_equal(got.pose_t[ok], ref.pose_t[ok]) and np.array_equal(got.pose_R[ok], ref.pose_R[ok])
+    assert np.array_equal(got.chi2[ok], ref.chi2[ok])
+    assert np.array_equal(got.pose_t[70], ref.pose_t[70], equal_nan=True)
+
+
 @pytest.mark.parametrize("make,N,iters", [(synthetic.uwb_imu_lidar, 120, 4), (synthetic.uwb_twist, 200, 3)])
 def test_long_general_chains(solver, make, N, iters):
     """6x6 chains far longer than the BASELINE shapes (topology tables of the ITEM kernel beyond 48 KB of shared

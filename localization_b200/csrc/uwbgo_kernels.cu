@@ -1200,11 +1200,12 @@ cudaError_t launch_solve(const DevTopo &topo, const DevCfg &cfg, const DevWs &ws
         const unsigned tiles = (unsigned)n_tiles(ws.W);
         if (UWBGO_GEN_CTA && UWBGO_GEN_ITEMS && general_items_ok(topo, ws)) {
             /* chains take the ITEM kernel (eight warps per tile at 128 registers and two tiles per SM; sixteen warps and
-             * one tile per SM up to one tile per SM).  Up to one tile per SM, windows with EdgeSE3 edges are 5 % faster
-             * on the 8-warp CTA kernel below (4,096 C4b windows: 2.78 vs 2.91 ms; C4a: 7.10 vs 6.29 ms for the ITEM
-             * kernel).  UWBGO_GENERAL_KERNEL=cta | items overrides the choice (A/B runs, tests). */
+             * one tile per SM up to one tile per SM) at every batch size: with the cooperative elimination it is ahead
+             * of the 8-warp CTA kernel below for EdgeSE3 windows too (4,096 C4b windows: 2.23 vs 2.74 ms, 2,048: 1.63 vs
+             * 2.43 ms; C4a 4,096: 4.72 vs 7.08 ms).  UWBGO_GENERAL_KERNEL=cta | items overrides the choice (A/B runs,
+             * tests of both). */
             const char *sel = getenv("UWBGO_GENERAL_KERNEL");
-            const bool items = sel ? strcmp(sel, "items") == 0 : ((int)tiles > sms || topo.Es == 0);
+            const bool items = sel ? strcmp(sel, "items") == 0 : true;
             if (items && !(sel && strcmp(sel, "cta") == 0)) return launch_solve_general_items(topo, cfg, ws, st);
         }
         if (UWBGO_GEN_CTA && ws.echi) {

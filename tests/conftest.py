@@ -21,19 +21,20 @@ def _gpu_solver():
     s.close()
 
 
-@pytest.fixture(params=["tile", "items", "window"])
+@pytest.fixture(params=["tile", "cta", "window"])
 def solver(request, _gpu_solver):
     """Every parity test runs three times: through the tile kernels as the library picks them (lane = window,
-    the large-batch path), through the tile kernels with the 6x6 ITEM kernel forced for every chain whatever the
-    batch size (uwbgo_general_items.cu; by default it takes batches beyond one tile per SM), and through the
-    WINDOW path (one CTA per window; windows too large for it fall back to the tile kernels).
+    the large-batch path; 6x6 chains take the ITEM kernel of uwbgo_general_items.cu), through the tile kernels
+    with the 6x6 CTA kernel forced for every chain (lm_general_cta_kernel: the kernel of forests, and the A/B
+    partner of the ITEM kernel), and through the WINDOW path (one CTA per window; windows too large for it fall
+    back to the tile kernels).
     `solver.path_ok(*tile_paths)` checks the path the last solve took in either mode."""
     s = _gpu_solver
     window = request.param == "window"
     s.set_window_path(2048 if window else 0)  # larger batches belong to the tile kernels in both modes
     s.path_ok = lambda *allowed: s.last_path in allowed or (window and s.last_path == 3)
-    if request.param == "items":
-        os.environ["UWBGO_GENERAL_KERNEL"] = "items"  # read by launch_solve at every launch
+    if request.param == "cta":
+        os.environ["UWBGO_GENERAL_KERNEL"] = "cta"  # read by launch_solve at every launch
     yield s
     os.environ.pop("UWBGO_GENERAL_KERNEL", None)
     s.set_window_path(-1)

@@ -57,6 +57,11 @@ NOTE_GENERAL = ("6x6 windows (rotations, antenna offsets, EdgeSE3Prior / EdgeSE3
                 "spills streamed once per LM trial")
 
 
+def _info_diag(made):
+    topo, batch, extra = made
+    return topo, batch.with_info_diag(), extra
+
+
 ARRAYS = ("pose_t", "pose_R", "anchors", "range_d", "range_info", "prior_Z", "prior_info", "se3_Z", "se3_info")
 # name -> (description, default windows per GPU, generator, LM iterations, SURVEY algorithmic bytes per window or None)
 WORKLOADS = {
@@ -68,11 +73,18 @@ WORKLOADS = {
             "(range_d / range_info doubles, per-window anchors)", WINDOWS_PER_GPU,
             lambda syn, W, seed: syn.uwb_only(W, N_POSES, N_ANCHORS, seed=seed), LM_ITERS, ALGO_BYTES_SOLVE),
     "c4a": ("C4a: synthetic uwb_imu_lidar windows, 8 anchors, 20-pose window, 3 antennas with lever arms, IMU + lidar "
-            "EdgeSE3Prior on every pose but the newest, 20 LM iterations", 8192,
-            lambda syn, W, seed: syn.uwb_imu_lidar(W, 20, 8, seed=seed), 20, None),
+            "EdgeSE3Prior on every pose but the newest, 20 LM iterations; information matrices of the priors passed as "
+            "their diagonals (UWBGO_DIAG_INFO: what Localization builds is diagonal), rebuilt on the device", 8192,
+            lambda syn, W, seed: _info_diag(syn.uwb_imu_lidar(W, 20, 8, seed=seed)), 20, None),
     "c4b": ("C4b: synthetic uwb_twist windows, 8 anchors, 15-pose window, twist EdgeSE3 chain, merged-covariance "
-            "ranges with 3 antennas, 12 LM iterations", 8192,
-            lambda syn, W, seed: syn.uwb_twist(W, 15, 8, seed=seed), 12, None),
+            "ranges with 3 antennas, 12 LM iterations; information matrices of the twist edges passed as their "
+            "diagonals (UWBGO_DIAG_INFO), rebuilt on the device", 8192,
+            lambda syn, W, seed: _info_diag(syn.uwb_twist(W, 15, 8, seed=seed)), 12, None),
+    # the same windows with full 6x6 information matrices on the wire (the input form of the first half of round 2)
+    "c4ax": ("C4a with full 6x6 information matrices on the wire", 8192,
+             lambda syn, W, seed: syn.uwb_imu_lidar(W, 20, 8, seed=seed), 20, None),
+    "c4bx": ("C4b with full 6x6 information matrices on the wire", 8192,
+             lambda syn, W, seed: syn.uwb_twist(W, 15, 8, seed=seed), 12, None),
     "c5": ("C5: synthetic UWB-only Monte-Carlo windows, 16 anchors, 200-pose window, 10 LM iterations "
            "(1,048,576 windows over 8 GPUs = 131,072 per GPU)", 131072,
            lambda syn, W, seed: syn.uwb_only(W, 200, 16, seed=seed, compact=True, shared_anchors=True), 10, 29200),
@@ -409,7 +421,7 @@ def main():
         cb.n_windows = W
         for k in present:
             setattr(cb, k, pd(d_in[k]))
-        cb.shared = _ffi.SHARED_ANCHORS if batch.shared_anchors else 0
+        cb.shared = (_ffi.SHARED_ANCHORS if batch.shared_anchors else 0) | (_ffi.DIAG_INFO if batch.info_diag else 0)
         if msgs is not None:
             d_msg = {n: torch.from_numpy(getattr(msgs, n)).to(dev) for n, _ in MSG if getattr(msgs, n) is not None}
             cm_dev = range_msgs_struct(d_msg, lambda t, dt: pf(t) if dt == np.float32 else pd(t))
@@ -460,7 +472,8 @@ def main():
             out["shards_verified"] = ok
 
         # ---- end-to-end leg: host buffers through uwbgo_solve_batch ----------------------------
-        hb = Batch(pose_t=batch.pose_t, ant_offsets=batch.ant_offsets, shared_anchors=batch.shared_anchors)
+        hb = Batch(pose_t=batch.pose_t, ant_offsets=batch.ant_offsets, shared_anchors=batch.shared_anchors,
+                   info_diag=batch.info_diag)
         for k in present:
             a = pinned_empty(getattr(batch, k).shape)
             a[...] = getattr(batch, k)
@@ -525,7 +538,8 @@ def main():
         achieved = wl_bytes * W / (k_best * 1e-3) / 1e9 if k_best else None
         traffic, traffic_src, fp64_flop, fp64_pipe = None, None, None, None
         tkey = {"c3": ("lm_chain_tma_kernel", WINDOWS_PER_GPU), "c3x": ("lm_chain_tma_kernel", WINDOWS_PER_GPU),
-                "c4a": ("lm_general_items_kernel_c4a", 8192), "c4b": ("lm_general_items_kernel_c4b", 8192)}.get(args.workload)
+                "c4a": ("lm_general_items_kernel_c4a", 8192), "c4b": ("lm_general_items_kernel_c4b", 8192),
+                "c4ax": ("lm_general_items_kernel_c4a", 8192), "c4bx": ("lm_general_items_kernel_c4b", 8192)}.get(args.workload)
         for tp in (os.path.join(ROOT, "profiles", "r02_traffic.json"), os.path.join(ROOT, "profiles", "r01_traffic.json")):
             if os.path.exists(tp) and tkey and W == tkey[1]:
                 with open(tp) as f:

@@ -105,6 +105,14 @@ typedef struct uwbgo_range_msgs {
 
 #define UWBGO_SHARED_ANCHORS 1   /* uwbgo_batch::shared: `anchors` is [A][3], one constellation for */
                                  /* every window of the batch (a fleet in one anchor field)         */
+#define UWBGO_DIAG_INFO      2   /* uwbgo_batch::shared: prior_info is [W][Ep][6] and se3_info is   */
+                                 /* [W][Es][6]: the DIAGONALS of the information matrices.  What    */
+                                 /* Localization builds is diagonal (lidar: information(2,2),       */
+                                 /* localization.cpp:478-479; IMU: the three rotation entries,      */
+                                 /* :515-518); the 6x6 matrices are rebuilt on the device with +0.0 */
+                                 /* elsewhere, so the solve sees the same bits at a sixth of the    */
+                                 /* host->device bytes (C4a: 9.0 of 17.2 KB per window less).       */
+                                 /* Batches in this form take the tile kernels                      */
 
 /* Per-window numeric data, window-major.  Er/Ep/Es = number of RANGE_*, PRIOR, SE3 edges. */
 typedef struct uwbgo_batch {
@@ -117,9 +125,9 @@ typedef struct uwbgo_batch {
     const double  *range_d;       /* [W][Er]    EdgeSE3Range measurement                          */
     const double  *range_info;    /* [W][Er]    EdgeSE3Range information (1x1)                    */
     const double  *prior_Z;       /* [W][Ep][12] EdgeSE3Prior measurement: R row-major (9), t (3) */
-    const double  *prior_info;    /* [W][Ep][36] information, row-major                           */
+    const double  *prior_info;    /* [W][Ep][36] information, row-major ([W][Ep][6] with UWBGO_DIAG_INFO) */
     const double  *se3_Z;         /* [W][Es][12] EdgeSE3 measurement                              */
-    const double  *se3_info;      /* [W][Es][36] information, row-major                           */
+    const double  *se3_info;      /* [W][Es][36] information, row-major ([W][Es][6] with UWBGO_DIAG_INFO) */
     /* optional compact forms; zero / NULL = the arrays above are complete */
     const uwbgo_range_msgs *range_msgs; /* replaces range_d and range_info (both must then be NULL)  */
     int32_t shared;               /* bit mask of UWBGO_SHARED_*                                   */

@@ -11,6 +11,7 @@ import os
 
 ABI_VERSION = 3
 SHARED_ANCHORS = 1
+DIAG_INFO = 2
 
 EDGE_RANGE_ANCHOR = 0
 EDGE_RANGE_POSE = 1

@@ -450,7 +450,7 @@ int check_batch(const TopoEntry &te, const uwbgo_batch *in)
     if (!in->pose_t) return fail(UWBGO_E_INVALID, "pose_t is NULL");
     if (g.A > 0 && !in->anchors) return fail(UWBGO_E_INVALID, "anchors is NULL");
     if (g.K > 0 && !in->ant_offsets) return fail(UWBGO_E_INVALID, "ant_offsets is NULL");
-    if (in->shared & ~UWBGO_SHARED_ANCHORS) return fail(UWBGO_E_INVALID, "unknown bit in batch.shared");
+    if (in->shared & ~(UWBGO_SHARED_ANCHORS | UWBGO_DIAG_INFO)) return fail(UWBGO_E_INVALID, "unknown bit in batch.shared");
     if (in->range_msgs) {
         const uwbgo_range_msgs *m = in->range_msgs;
         if (in->range_d || in->range_info) return fail(UWBGO_E_INVALID, "range_msgs replaces range_d / range_info: pass one form");
@@ -586,9 +586,11 @@ int run_device(uwbgo_ctx *ctx, Lane &ln, const TopoEntry &te, const DevCfg &cfg,
         add(pj, in->range_info, const_cast<double *>(ws.ri), tp.Er, 8, 0);
     }
     add(pj, in->prior_Z, const_cast<double *>(ws.pZ), tp.Ep * 12, 8, 0);
-    add(pj, in->prior_info, const_cast<double *>(ws.pI), tp.Ep * 36, 8, 0);
+    /* UWBGO_DIAG_INFO: the matrices are rebuilt from their diagonals on the way into the tile layout */
+    const int info_mode = (in->shared & UWBGO_DIAG_INFO) ? 5 : 0;
+    add(pj, in->prior_info, const_cast<double *>(ws.pI), tp.Ep * 36, 8, info_mode);
     add(pj, in->se3_Z, const_cast<double *>(ws.sZ), tp.Es * 12, 8, 0);
-    add(pj, in->se3_info, const_cast<double *>(ws.sI), tp.Es * 36, 8, 0);
+    add(pj, in->se3_info, const_cast<double *>(ws.sI), tp.Es * 36, 8, info_mode);
     CU(launch_pack(pj, st));
     ctx->launches += 1;
     if (in->range_msgs && tp.Er > 0) { /* create_range_edge on the device */
@@ -1029,6 +1031,7 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
     const size_t N = (size_t)g.N;
     const uwbgo_range_msgs *msgs = in->range_msgs;
     const bool shared_anch = (in->shared & UWBGO_SHARED_ANCHORS) != 0;
+    const size_t info_n = (in->shared & UWBGO_DIAG_INFO) ? 6 : 36; /* doubles per information matrix on the wire */
     /* the LM kernel's duration is set by per-window latency, not by the chunk size, so a batch
      * that fits n_lanes chunks is split evenly and all its chunks run concurrently */
     int64_t chunk = std::min<int64_t>(ctx->chunk, (W + 31) / 32 * 32);
@@ -1057,9 +1060,9 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         S.in_mta = take(msgs && g.Era > 0 && msgs->dt_anchor, (size_t)g.Era * 8);
         S.in_mtp = take(msgs && g.Erp > 0, (size_t)g.Erp * 8);
         S.in_pZ = take(g.Ep > 0, (size_t)g.Ep * 12 * 8);
-        S.in_pI = take(g.Ep > 0, (size_t)g.Ep * 36 * 8);
+        S.in_pI = take(g.Ep > 0, (size_t)g.Ep * info_n * 8);
         S.in_sZ = take(g.Es > 0, (size_t)g.Es * 12 * 8);
-        S.in_sI = take(g.Es > 0, (size_t)g.Es * 36 * 8);
+        S.in_sI = take(g.Es > 0, (size_t)g.Es * info_n * 8);
         if (linearize) {
             S.out_Hd = take(true, N * 36 * 8);
             S.out_Ho = take(N > 1, (N - 1) * 36 * 8);
@@ -1155,9 +1158,9 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
             CUL(h2d(g.Er > 0 ? in->range_info : nullptr, S.in_ri, (size_t)g.Er * 8));
         }
         CUL(h2d(g.Ep > 0 ? in->prior_Z : nullptr, S.in_pZ, (size_t)g.Ep * 12 * 8));
-        CUL(h2d(g.Ep > 0 ? in->prior_info : nullptr, S.in_pI, (size_t)g.Ep * 36 * 8));
+        CUL(h2d(g.Ep > 0 ? in->prior_info : nullptr, S.in_pI, (size_t)g.Ep * info_n * 8));
         CUL(h2d(g.Es > 0 ? in->se3_Z : nullptr, S.in_sZ, (size_t)g.Es * 12 * 8));
-        CUL(h2d(g.Es > 0 ? in->se3_info : nullptr, S.in_sI, (size_t)g.Es * 36 * 8));
+        CUL(h2d(g.Es > 0 ? in->se3_info : nullptr, S.in_sI, (size_t)g.Es * info_n * 8));
         if (ordered_h2d) CUL(cudaEventRecord(ln.in_ready, st));
         mark(st);
         uwbgo_batch db{};

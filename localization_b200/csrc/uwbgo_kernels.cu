@@ -854,6 +854,21 @@ __global__ void __launch_bounds__(256) xpose_kernel(XposeJobs jobs)
         }
         return;
     }
+    if (j.mode == 5) { /* UWBGO_DIAG_INFO: src is [W][C / 36][6], the diagonals of 6x6 matrices; dst the tile-layout
+                        * [tile][C][32] array of the full matrices, +0.0 off the diagonal */
+        const int64_t tile = blockIdx.x;
+        const int c0 = blockIdx.y * 32;
+        const int64_t w = tile * TILE + threadIdx.x;
+        for (int y = threadIdx.y; y < 32; y += 8) {
+            int c = c0 + y;
+            if (c >= j.C) continue;
+            const int k = c % 36;
+            double v = 0.0;
+            if (k % 7 == 0 && w < jobs.W) v = static_cast<const double *>(j.src)[w * (int64_t)(j.C / 6) + (c / 36) * 6 + k / 7];
+            static_cast<double *>(j.dst)[(tile * j.C + c) * TILE + threadIdx.x] = v;
+        }
+        return;
+    }
     if (j.elem == 8)
         xpose_body<double, PACK>(j, jobs.W, sm);
     else

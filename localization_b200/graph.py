@@ -223,6 +223,7 @@ class Batch:
     se3_info: np.ndarray | None = None      # [W][Es][6][6]
     range_msgs: RangeMsgs | None = None     # compact form, instead of range_d / range_info
     shared_anchors: bool = False            # anchors is [A][3], one constellation for all windows
+    info_diag: bool = False                 # prior_info / se3_info are [W][E*][6]: the diagonals (UWBGO_DIAG_INFO)
 
     def __post_init__(self):
         self.pose_t = _f64(self.pose_t)
@@ -271,16 +272,16 @@ class Batch:
             need("range_d", self.range_d, W * er)
             need("range_info", self.range_info, W * er)
         need("prior_Z", self.prior_Z, W * ep * 12)
-        need("prior_info", self.prior_info, W * ep * 36)
+        need("prior_info", self.prior_info, W * ep * (6 if self.info_diag else 36))
         need("se3_Z", self.se3_Z, W * es * 12)
-        need("se3_info", self.se3_info, W * es * 36)
+        need("se3_info", self.se3_info, W * es * (6 if self.info_diag else 36))
 
     def slice(self, lo: int, hi: int) -> "Batch":
         def s(a):
             return None if a is None else a[lo:hi]
         return Batch(pose_t=s(self.pose_t), anchors=self.anchors if self.shared_anchors else s(self.anchors),
                      range_msgs=None if self.range_msgs is None else self.range_msgs.slice(lo, hi),
-                     shared_anchors=self.shared_anchors, range_d=s(self.range_d),
+                     shared_anchors=self.shared_anchors, info_diag=self.info_diag, range_d=s(self.range_d),
                      range_info=s(self.range_info), pose_R=s(self.pose_R),
                      oplus_count=s(self.oplus_count), ant_offsets=self.ant_offsets,
                      prior_Z=s(self.prior_Z), prior_info=s(self.prior_info), se3_Z=s(self.se3_Z),
@@ -297,19 +298,41 @@ class Batch:
         if self.range_msgs is not None:
             self._msgs_c = self.range_msgs.c_struct()   # kept alive with the Batch
             b.range_msgs = C.pointer(self._msgs_c)
-        b.shared = _ffi.SHARED_ANCHORS if self.shared_anchors else 0
+        b.shared = (_ffi.SHARED_ANCHORS if self.shared_anchors else 0) | (_ffi.DIAG_INFO if self.info_diag else 0)
         return b
 
     def expanded(self, topo: Topology) -> "Batch":
-        """the same windows with range_d / range_info written out and per-window anchors"""
+        """the same windows with range_d / range_info written out, per-window anchors and full information matrices"""
         rd, ri = (self.range_d, self.range_info) if self.range_msgs is None else self.range_msgs.expand(topo)
         anchors = self.anchors
         if self.shared_anchors:
             anchors = np.ascontiguousarray(np.broadcast_to(self.anchors.reshape(1, -1, 3),
                                                            (self.n_windows, topo.n_anchors, 3)))
+        def full(a):
+            if a is None or not self.info_diag:
+                return a
+            d = a.reshape(a.shape[0], -1, 6)
+            m = np.zeros(d.shape + (6,))
+            m[..., np.arange(6), np.arange(6)] = d
+            return m
         return Batch(pose_t=self.pose_t, anchors=anchors, range_d=rd, range_info=ri, pose_R=self.pose_R,
                      oplus_count=self.oplus_count, ant_offsets=self.ant_offsets, prior_Z=self.prior_Z,
-                     prior_info=self.prior_info, se3_Z=self.se3_Z, se3_info=self.se3_info)
+                     prior_info=full(self.prior_info), se3_Z=self.se3_Z, se3_info=full(self.se3_info))
+
+    def with_info_diag(self) -> "Batch":
+        """the same windows with the information matrices of the 6-D edges passed as their diagonals; raises if a
+        matrix has a non-zero (or -0.0) entry off the diagonal"""
+        def diag(a):
+            if a is None:
+                return None
+            m = a.reshape(a.shape[0], -1, 6, 6)
+            off = m.copy()
+            off[..., np.arange(6), np.arange(6)] = 0.0
+            if np.any(off.view(np.int64) != 0):
+                raise ValueError("information matrix with entries off the diagonal")
+            return np.ascontiguousarray(m[..., np.arange(6), np.arange(6)])
+        import dataclasses
+        return dataclasses.replace(self, prior_info=diag(self.prior_info), se3_info=diag(self.se3_info), info_diag=True)
 
 
 @dataclass

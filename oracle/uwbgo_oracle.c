@@ -308,6 +308,7 @@ typedef struct {
     double *y;    /* [N][6] c_i */
     double *zs;   /* [N][6] z_i */
     double *rd_own, *ri_own; /* [Er] edge parameters built from range messages (compact input form) */
+    double *pi_own, *si_own; /* [Ep][36], [Es][36] information matrices rebuilt from their diagonals (UWBGO_DIAG_INFO) */
     double *estale;          /* [E] chi2() of every edge at the last computeActiveErrors of optimize() */
     double *mg;              /* [N][36 + 36 + 36] marginal scratch: G_i | M_i | S_i^-1 */
     int built;               /* build_system() ran at least once */
@@ -961,10 +962,12 @@ static int window_alloc(window_t *W, const uwbgo_topology *T, const uwbgo_config
     W->zs = (double *)malloc(N * 6 * sizeof(double));
     W->rd_own = (double *)malloc(((size_t)Er + 1) * sizeof(double));
     W->ri_own = (double *)malloc(((size_t)Er + 1) * sizeof(double));
+    W->pi_own = (double *)calloc((size_t)W->Ep * 36 + 1, sizeof(double));
+    W->si_own = (double *)calloc((size_t)W->Es * 36 + 1, sizeof(double));
     W->estale = (double *)calloc(E + 1, sizeof(double));
     W->mg = (double *)malloc(N * 108 * sizeof(double));
     return (W->X && W->Xbak && W->cnt && W->err && W->Hd && W->Ho && W->b && W->x && W->Ld &&
-            W->Lo && W->y && W->zs && W->rd_own && W->ri_own && W->estale && W->mg)
+            W->Lo && W->y && W->zs && W->rd_own && W->ri_own && W->pi_own && W->si_own && W->estale && W->mg)
                ? 0
                : UWBGO_E_NOMEM;
 }
@@ -973,7 +976,7 @@ static void window_free(window_t *W)
 {
     free(W->X); free(W->Xbak); free(W->cnt); free(W->err); free(W->Hd); free(W->Ho);
     free(W->b); free(W->x); free(W->Ld); free(W->Lo); free(W->y); free(W->zs);
-    free(W->rd_own); free(W->ri_own); free(W->estale); free(W->mg);
+    free(W->rd_own); free(W->ri_own); free(W->pi_own); free(W->si_own); free(W->estale); free(W->mg);
 }
 
 static void window_load(window_t *W, const uwbgo_batch *in, int64_t w)
@@ -1033,6 +1036,16 @@ static void window_load(window_t *W, const uwbgo_batch *in, int64_t w)
     W->prior_info = in->prior_info ? in->prior_info + (size_t)w * W->Ep * 36 : NULL;
     W->se3_Z = in->se3_Z ? in->se3_Z + (size_t)w * W->Es * 12 : NULL;
     W->se3_info = in->se3_info ? in->se3_info + (size_t)w * W->Es * 36 : NULL;
+    if (in->shared & UWBGO_DIAG_INFO) {
+        /* the information matrices as Localization fills them: Matrix<double, 6, 6>::Zero() plus the diagonal
+         * entries (localization.cpp:478-479, 515-518); pi_own / si_own were calloc'ed, only the diagonals change */
+        for (int k = 0; k < W->Ep; ++k)
+            for (int d = 0; d < 6; ++d) W->pi_own[(size_t)k * 36 + 7 * d] = in->prior_info[((size_t)w * W->Ep + k) * 6 + d];
+        for (int k = 0; k < W->Es; ++k)
+            for (int d = 0; d < 6; ++d) W->si_own[(size_t)k * 36 + 7 * d] = in->se3_info[((size_t)w * W->Es + k) * 6 + d];
+        W->prior_info = W->Ep ? W->pi_own : NULL;
+        W->se3_info = W->Es ? W->si_own : NULL;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -170,6 +170,33 @@ def test_forest_rule():
         oracle.solve(topo, b, Config(max_iterations=1))
 
 
+def test_diagonal_information_form_is_the_full_form():
+    """UWBGO_DIAG_INFO: the information matrices of EdgeSE3Prior / EdgeSE3 passed as their diagonals ([W][E*][6];
+    what Localization builds is Matrix<6,6>::Zero() plus diagonal entries, localization.cpp:478-479,515-518) are
+    rebuilt with +0.0 elsewhere: the oracle gives the bits of the full form; a matrix with an entry (or a -0.0) off
+    the diagonal cannot be passed this way"""
+    for make, iters in ((lambda: synthetic.uwb_imu_lidar(40, 10, 6, seed=5), 5), (lambda: synthetic.uwb_twist(40, 8, 6, seed=6), 4)):
+        topo, b, _ = make()
+        bd = b.with_info_diag()
+        assert bd.info_diag and (bd.prior_info is None or bd.prior_info.shape[-1] == 6 and bd.prior_info.ndim == 3)
+        bd.check(topo)
+        e = bd.expanded(topo)
+        for name in ("prior_info", "se3_info"):
+            assert (getattr(b, name) is None) == (getattr(e, name) is None)
+            if getattr(b, name) is not None:
+                assert np.array_equal(getattr(e, name).reshape(-1), getattr(b, name).reshape(-1))
+        cfg = Config(max_iterations=iters)
+        r0, r1 = oracle.solve(topo, b, cfg), oracle.solve(topo, bd, cfg)
+        assert np.array_equal(r0.pose_t, r1.pose_t) and np.array_equal(r0.pose_R, r1.pose_R)
+        assert np.array_equal(r0.chi2, r1.chi2) and np.array_equal(r0.status, r1.status)
+        assert np.array_equal(bd.slice(3, 9).prior_info if bd.prior_info is not None else bd.slice(3, 9).se3_info,
+                              (bd.prior_info if bd.prior_info is not None else bd.se3_info)[3:9])
+    topo, b, _ = synthetic.uwb_imu_lidar(8, 6, 4, seed=1)
+    b.prior_info[2, 1, 0, 3] = -0.0
+    with pytest.raises(ValueError):
+        b.with_info_diag()
+
+
 def test_compact_range_form_is_the_expanded_form():
     """uwbgo_range_msgs (message fields: float32 distance / distance_err, stamp differences) expands to exactly
     the edge parameters Localization::addRangeEdge computes (localization.cpp:316-319,331,338,350); shared

@@ -609,6 +609,51 @@ def test_coincident_points_and_extreme_magnitudes(solver):
     assert np.array_equal(got.chi2, ref.chi2, equal_nan=True)
 
 
+@pytest.mark.parametrize("make,iters", [(lambda W: synthetic.uwb_imu_lidar(W, 12, 6, seed=41), 6),
+                                        (lambda W: synthetic.uwb_twist(W, 9, 6, seed=42), 5)])
+def test_diagonal_information_form(solver, make, iters):
+    """UWBGO_DIAG_INFO: prior_info / se3_info as [W][E*][6] diagonals, the 6x6 matrices rebuilt on the device on the
+    way into the tile layout (+0.0 off the diagonal): the bits of the full form, through the chunked host pipeline
+    (ragged last tile, three lanes) and through the device-pointer entry point"""
+    import ctypes as C
+    import torch
+    from localization_b200 import _ffi
+    W = 333
+    topo, b, _ = make(W)
+    bd = b.with_info_diag()
+    cfg = Config(max_iterations=iters)
+    ref = oracle.solve(topo, b, cfg)
+    solver.set_pipeline(96, 3)
+    try:
+        got = solver.solve(topo, bd, cfg)
+    finally:
+        solver.set_pipeline(8192, 8)
+    assert solver.last_path == 0                                     # compact inputs take the tile kernels
+    assert_parity(got, ref)
+    dev = torch.device("cuda", 0)
+    keep, cb = {}, _ffi.CBatch()
+    cb.n_windows, cb.shared = W, _ffi.DIAG_INFO
+    for k in ("pose_t", "pose_R", "anchors", "range_d", "range_info", "prior_Z", "prior_info", "se3_Z", "se3_info"):
+        v = getattr(bd, k)
+        if v is not None:
+            keep[k] = torch.from_numpy(v).to(dev)
+            setattr(cb, k, C.cast(C.c_void_p(keep[k].data_ptr()), C.POINTER(C.c_double)))
+    if bd.ant_offsets is not None:
+        cb.ant_offsets = bd.ant_offsets.ctypes.data_as(C.POINTER(C.c_double))
+    N = topo.n_poses
+    pose = torch.empty((W, N, 3), dtype=torch.float64, device=dev)
+    rot = torch.empty((W, N, 9), dtype=torch.float64, device=dev)
+    chi2 = torch.empty((W, 4), dtype=torch.float64, device=dev)
+    cr = _ffi.CResult()
+    cr.pose_t = C.cast(C.c_void_p(pose.data_ptr()), C.POINTER(C.c_double))
+    cr.pose_R = C.cast(C.c_void_p(rot.data_ptr()), C.POINTER(C.c_double))
+    cr.chi2 = C.cast(C.c_void_p(chi2.data_ptr()), C.POINTER(C.c_double))
+    solver.solve_device(topo, cb, cfg, cr, torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize(dev)
+    assert np.array_equal(pose.cpu().numpy(), ref.pose_t) and np.array_equal(chi2.cpu().numpy(), ref.chi2)
+    assert np.array_equal(rot.cpu().numpy().reshape(W, N, 3, 3), ref.pose_R)
+
+
 def test_compact_range_form_and_shared_anchors(solver):
     """uwbgo_range_msgs + UWBGO_SHARED_ANCHORS: the edge parameters of create_range_edge built on the device
     (localization.cpp:316-319,331,338,350) give the bits of the expanded form, through the chunked host pipeline

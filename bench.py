@@ -539,7 +539,8 @@ def main():
         traffic, traffic_src, fp64_flop, fp64_pipe = None, None, None, None
         tkey = {"c3": ("lm_chain_tma_kernel", WINDOWS_PER_GPU), "c3x": ("lm_chain_tma_kernel", WINDOWS_PER_GPU),
                 "c4a": ("lm_general_items_kernel_c4a", 8192), "c4b": ("lm_general_items_kernel_c4b", 8192),
-                "c4ax": ("lm_general_items_kernel_c4a", 8192), "c4bx": ("lm_general_items_kernel_c4b", 8192)}.get(args.workload)
+                "c4ax": ("lm_general_items_kernel_c4a", 8192), "c4bx": ("lm_general_items_kernel_c4b", 8192),
+                "c5": ("lm_chain_tma_kernel_c5", 131072)}.get(args.workload)
         for tp in (os.path.join(ROOT, "profiles", "r02_traffic.json"), os.path.join(ROOT, "profiles", "r01_traffic.json")):
             if os.path.exists(tp) and tkey and W == tkey[1]:
                 with open(tp) as f:

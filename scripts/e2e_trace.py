@@ -34,6 +34,16 @@ for chunk, lanes in settings:
     devnull = os.open(os.devnull, os.O_WRONLY); saved = os.dup(2)
     os.dup2(devnull, 2)
     for _ in range(3): run()
+    nb = int(os.environ.get("UWBGO_TRACE_BARRIER", "0"))
+    if nb:  # several processes, one per GPU: start the traced calls together and keep every GPU busy around them
+        open(f"/tmp/uwbgo_ready_{os.environ['UWBGO_TRACE_RANK']}", "w").close()
+        while sum(os.path.exists(f"/tmp/uwbgo_ready_{k}") for k in range(nb)) < nb:
+            time.sleep(0.001)
+        for _ in range(20): run()
     os.dup2(saved, 2)
     t0 = time.perf_counter(); run(); dt = time.perf_counter() - t0
+    if nb:
+        os.dup2(devnull, 2)
+        for _ in range(10): run()
+        os.dup2(saved, 2)
     print(f"chunk={chunk:6d} lanes={lanes}  {dt*1e3:7.2f} ms wall (traced call)", file=sys.stderr, flush=True)

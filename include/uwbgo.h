@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UWBGO_ABI_VERSION 3
+#define UWBGO_ABI_VERSION 4
 
 /* error codes */
 #define UWBGO_OK              0
@@ -243,6 +243,39 @@ int uwbgo_factor_solve_batch(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_windows,
 int uwbgo_factor_solve_batch_device(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_windows,
                                     const double *H_diag, const double *H_off, const double *b,
                                     const double *lambda, double *x, int32_t *ok, void *stream);
+
+/* ---- resident fleet: the sliding windows of W robots stay on the device ---------------------- */
+/*
+ * The reference's own call pattern at fleet scale.  Localization::addRangeEdge (localization.cpp:297-376)
+ * handles ONE range message per robot: a new vertex whose estimate is a copy of the newest one, the range
+ * edge to the anchor (distance, cov = distance_err^2, :316-331), the zero-length trajectory edge to the
+ * previous vertex (cov = (v_max dt / 3)^2, :319,338), the oldest vertex and its edges dropped from the
+ * ring (robot.cpp:75-110), then solve() (:371-375).  A uwbgo_stream keeps the N-pose windows of W robots
+ * in HBM between messages -- the estimates of the last solve and the message fields of the N range
+ * edges -- so that a step moves only the new message to the device (16 bytes per robot) and the newest
+ * pose, chi2 and status back (72 bytes), instead of whole windows (C3: 1,992 + 1,248 bytes).  The solve is
+ * the one of uwbgo_solve_batch_device on the window the reference would hold: the same bits (tested
+ * against windows shifted on the host).  All robots range the same anchor in a step (one TDMA slot per
+ * anchor); anchors are one constellation for the fleet.  UWB-only windows (uwb_only.yaml).
+ */
+typedef struct uwbgo_stream uwbgo_stream;
+int  uwbgo_stream_create(uwbgo_ctx *ctx, int32_t n_poses, int32_t n_anchors, int64_t n_windows,
+                         const double *anchors /* [A][3] */, double v_max, const uwbgo_config *cfg,
+                         uwbgo_stream **out);
+void uwbgo_stream_destroy(uwbgo_stream *s);
+/* the windows as they stand (host arrays): estimates [W][N][3], the anchor of each pose's range edge [N],
+ * distance / distance_err [W][N] (float32, as on the wire), stamp differences dt [W][N-1] */
+int  uwbgo_stream_load(uwbgo_stream *s, const double *pose_t, const int32_t *anchor_of_pose,
+                       const float *distance, const float *distance_err, const double *dt);
+/* one range message per robot (host arrays [W]) from anchor `anchor`: shift the windows, append the new
+ * vertex and its two edges, optimise, return the newest pose [W][3], chi2 [W][4] and status [W][4] (as
+ * uwbgo_result; any may be NULL).  Returns when the results are in the host arrays. */
+int  uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, const float *distance_err,
+                       const double *dt, double *newest_pose, double *chi2, int32_t *status);
+/* all estimates of the windows as the last step left them, [W][N][3] (host array) */
+int  uwbgo_stream_read(uwbgo_stream *s, double *pose_t);
+/* kernels launched / duration of the LM kernel of the last step (ms; needs uwbgo_set_profiling) come
+ * from the context: uwbgo_launch_count, uwbgo_last_kernel_ms */
 
 /* ---- introspection ---------------------------------------------------------------------- */
 /* number of kernels this library launched on ctx since creation (bench "gpu_launches") */

@@ -1,0 +1,269 @@
+/* uwbgo_stream: the sliding windows of a fleet resident in HBM (include/uwbgo.h, "resident fleet").
+ *
+ * The host-side caller of the hot path in the reference is Localization::addRangeEdge
+ * (localization.cpp:297-376) on the Robot ring (robot.cpp:75-110): per range message a new vertex (estimate =
+ * copy of the newest), two edges, the oldest vertex dropped, solve().  Here that bookkeeping runs on the
+ * device for W robots at once: one small kernel shifts the estimates and the message fields by one pose and
+ * appends the new message, the solve is uwbgo_solve_batch_device on the compact range form (edge parameters
+ * built on the device, one anchor constellation), one small kernel gathers the newest poses.  Only the new
+ * message goes in and the newest pose, chi2 and status come out.
+ *
+ * Layout: window-major device arrays (the layout of the ABI), two copies of the message fields (a step reads
+ * one and writes the other), estimates in `res` (what the last solve left) and `in` (what the next one
+ * starts from). */
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/uwbgo.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+stream_shift_kernel(int64_t W, int N, const double *__restrict__ res, double *__restrict__ in,
+                    const float *__restrict__ d_old, const float *__restrict__ e_old, const double *__restrict__ dt_old,
+                    float *__restrict__ d_new, float *__restrict__ e_new, double *__restrict__ dt_new,
+                    const float *__restrict__ msg_d, const float *__restrict__ msg_e, const double *__restrict__ msg_dt)
+{
+    /* one thread per (window, pose): pose i of the new window is pose i + 1 of the old one; the new vertex
+     * starts at the estimate of the newest (robot.cpp: new_vertex copies the last estimate) */
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W * N) return;
+    const int64_t w = t / N;
+    const int i = (int)(t - w * N);
+    const int src = i + 1 < N ? i + 1 : N - 1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) in[t * 3 + k] = res[(w * N + src) * 3 + k];
+    d_new[t] = i + 1 < N ? d_old[w * N + i + 1] : msg_d[w];
+    e_new[t] = i + 1 < N ? e_old[w * N + i + 1] : msg_e[w];
+    if (i + 1 < N) dt_new[w * (N - 1) + i] = i + 2 < N ? dt_old[w * (N - 1) + i + 1] : msg_dt[w];
+}
+
+__global__ void __launch_bounds__(256) stream_newest_kernel(int64_t W, int N, const double *__restrict__ res, double *__restrict__ newest)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W * 3) return;
+    const int64_t w = t / 3;
+    newest[t] = res[(w * N + (N - 1)) * 3 + (t - w * 3)];
+}
+
+thread_local std::string g_stream_error;
+
+}  // namespace
+
+struct uwbgo_stream {
+    uwbgo_ctx *ctx = nullptr;
+    int N = 0, A = 0;
+    int64_t W = 0;
+    double v_max = 0.0;
+    uwbgo_config cfg{};
+    std::vector<int32_t> anchor_of_pose;
+    std::vector<int32_t> ek, ea, eb, eant, erob; /* topology arrays of the current window */
+    char *dev = nullptr;                          /* one device allocation */
+    double *res = nullptr, *in = nullptr, *dt[2] = {nullptr, nullptr}, *anchors = nullptr, *chi2 = nullptr, *newest = nullptr, *msg_dt = nullptr;
+    float *d[2] = {nullptr, nullptr}, *e[2] = {nullptr, nullptr}, *msg_d = nullptr, *msg_e = nullptr;
+    int32_t *status = nullptr;
+    char *pin = nullptr; /* pinned staging: message in | newest, chi2, status out */
+    size_t pin_in = 0, pin_out = 0;
+    int cur = 0;
+    bool loaded = false;
+    cudaStream_t st = nullptr;
+};
+
+namespace {
+
+#define SCU(call)                                                         \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) {                                         \
+            fprintf(stderr, "uwbgo_stream: %s: %s\n", #call, cudaGetErrorString(e__)); \
+            return UWBGO_E_CUDA;                                          \
+        }                                                                 \
+    } while (0)
+
+size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+void build_topology(uwbgo_stream *s)
+{
+    /* the window addRangeEdge builds (localization.cpp:331-340): per pose its anchor edge, then the trajectory
+     * edge to its predecessor; Cauchy kernel on both */
+    s->ek.clear(); s->ea.clear(); s->eb.clear(); s->eant.clear(); s->erob.clear();
+    for (int k = 0; k < s->N; ++k) {
+        s->ek.push_back(UWBGO_EDGE_RANGE_ANCHOR); s->ea.push_back(k); s->eb.push_back(s->anchor_of_pose[k]);
+        s->eant.push_back(0); s->erob.push_back(1);
+        if (k > 0) {
+            s->ek.push_back(UWBGO_EDGE_RANGE_POSE); s->ea.push_back(k - 1); s->eb.push_back(k);
+            s->eant.push_back(0); s->erob.push_back(1);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int uwbgo_stream_create(uwbgo_ctx *ctx, int32_t n_poses, int32_t n_anchors, int64_t n_windows, const double *anchors,
+                        double v_max, const uwbgo_config *cfg, uwbgo_stream **out)
+{
+    if (!out) return UWBGO_E_INVALID;
+    *out = nullptr;
+    if (!ctx || !anchors || !cfg || n_poses < 2 || n_anchors < 1 || n_windows < 1) return UWBGO_E_INVALID;
+    auto s = new uwbgo_stream();
+    s->ctx = ctx;
+    s->N = n_poses;
+    s->A = n_anchors;
+    s->W = n_windows;
+    s->v_max = v_max;
+    s->cfg = *cfg;
+    const size_t W = (size_t)n_windows, N = (size_t)n_poses;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += up256(bytes); return at; };
+    const size_t o_res = take(W * N * 24), o_in = take(W * N * 24), o_dt0 = take(W * (N - 1) * 8), o_dt1 = take(W * (N - 1) * 8),
+                 o_d0 = take(W * N * 4), o_d1 = take(W * N * 4), o_e0 = take(W * N * 4), o_e1 = take(W * N * 4),
+                 o_anch = take((size_t)n_anchors * 24), o_chi = take(W * 32), o_stat = take(W * 16), o_new = take(W * 24),
+                 o_md = take(W * 4), o_me = take(W * 4), o_mdt = take(W * 8);
+    if (cudaMalloc(&s->dev, o) != cudaSuccess) {
+        cudaGetLastError();
+        delete s;
+        return UWBGO_E_NOMEM;
+    }
+    s->res = reinterpret_cast<double *>(s->dev + o_res);
+    s->in = reinterpret_cast<double *>(s->dev + o_in);
+    s->dt[0] = reinterpret_cast<double *>(s->dev + o_dt0);
+    s->dt[1] = reinterpret_cast<double *>(s->dev + o_dt1);
+    s->d[0] = reinterpret_cast<float *>(s->dev + o_d0);
+    s->d[1] = reinterpret_cast<float *>(s->dev + o_d1);
+    s->e[0] = reinterpret_cast<float *>(s->dev + o_e0);
+    s->e[1] = reinterpret_cast<float *>(s->dev + o_e1);
+    s->anchors = reinterpret_cast<double *>(s->dev + o_anch);
+    s->chi2 = reinterpret_cast<double *>(s->dev + o_chi);
+    s->status = reinterpret_cast<int32_t *>(s->dev + o_stat);
+    s->newest = reinterpret_cast<double *>(s->dev + o_new);
+    s->msg_d = reinterpret_cast<float *>(s->dev + o_md);
+    s->msg_e = reinterpret_cast<float *>(s->dev + o_me);
+    s->msg_dt = reinterpret_cast<double *>(s->dev + o_mdt);
+    s->pin_in = up256(W * 4) * 2 + up256(W * 8);
+    s->pin_out = up256(W * 24) + up256(W * 32) + up256(W * 16);
+    if (cudaHostAlloc(reinterpret_cast<void **>(&s->pin), s->pin_in + s->pin_out, cudaHostAllocDefault) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMemcpy(s->anchors, anchors, (size_t)n_anchors * 24, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        uwbgo_stream_destroy(s);
+        return UWBGO_E_CUDA;
+    }
+    *out = s;
+    return 0;
+}
+
+void uwbgo_stream_destroy(uwbgo_stream *s)
+{
+    if (!s) return;
+    if (s->st) {
+        cudaStreamSynchronize(s->st);
+        cudaStreamDestroy(s->st);
+    }
+    if (s->pin) cudaFreeHost(s->pin);
+    if (s->dev) cudaFree(s->dev);
+    delete s;
+}
+
+int uwbgo_stream_load(uwbgo_stream *s, const double *pose_t, const int32_t *anchor_of_pose, const float *distance,
+                      const float *distance_err, const double *dt)
+{
+    if (!s || !pose_t || !anchor_of_pose || !distance || !distance_err || !dt) return UWBGO_E_INVALID;
+    const size_t W = (size_t)s->W, N = (size_t)s->N;
+    for (int k = 0; k < s->N; ++k)
+        if (anchor_of_pose[k] < 0 || anchor_of_pose[k] >= s->A) return UWBGO_E_INVALID;
+    s->anchor_of_pose.assign(anchor_of_pose, anchor_of_pose + s->N);
+    SCU(cudaStreamSynchronize(s->st));
+    s->cur = 0;
+    SCU(cudaMemcpy(s->res, pose_t, W * N * 24, cudaMemcpyHostToDevice));
+    SCU(cudaMemcpy(s->d[0], distance, W * N * 4, cudaMemcpyHostToDevice));
+    SCU(cudaMemcpy(s->e[0], distance_err, W * N * 4, cudaMemcpyHostToDevice));
+    SCU(cudaMemcpy(s->dt[0], dt, W * (N - 1) * 8, cudaMemcpyHostToDevice));
+    s->loaded = true;
+    return 0;
+}
+
+int uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, const float *distance_err, const double *dt,
+                      double *newest_pose, double *chi2, int32_t *status)
+{
+    if (!s || !s->loaded || !distance || !distance_err || !dt || anchor < 0 || anchor >= s->A) return UWBGO_E_INVALID;
+    const size_t W = (size_t)s->W;
+    const int N = s->N;
+    /* the message through pinned staging (the caller's arrays may be pageable), one copy per field */
+    float *h_d = reinterpret_cast<float *>(s->pin), *h_e = reinterpret_cast<float *>(s->pin + up256(W * 4));
+    double *h_dt = reinterpret_cast<double *>(s->pin + 2 * up256(W * 4));
+    memcpy(h_d, distance, W * 4);
+    memcpy(h_e, distance_err, W * 4);
+    memcpy(h_dt, dt, W * 8);
+    SCU(cudaMemcpyAsync(s->msg_d, h_d, W * 4, cudaMemcpyHostToDevice, s->st));
+    SCU(cudaMemcpyAsync(s->msg_e, h_e, W * 4, cudaMemcpyHostToDevice, s->st));
+    SCU(cudaMemcpyAsync(s->msg_dt, h_dt, W * 8, cudaMemcpyHostToDevice, s->st));
+    const int nxt = s->cur ^ 1;
+    const int64_t threads = (int64_t)W * N;
+    stream_shift_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s->st>>>(
+        (int64_t)W, N, s->res, s->in, s->d[s->cur], s->e[s->cur], s->dt[s->cur], s->d[nxt], s->e[nxt], s->dt[nxt], s->msg_d,
+        s->msg_e, s->msg_dt);
+    SCU(cudaGetLastError());
+    s->cur = nxt;
+    /* drop-oldest: the anchor pattern moves with the poses */
+    for (int k = 0; k + 1 < N; ++k) s->anchor_of_pose[k] = s->anchor_of_pose[k + 1];
+    s->anchor_of_pose[N - 1] = anchor;
+    build_topology(s);
+    uwbgo_topology T{};
+    T.n_poses = N;
+    T.n_anchors = s->A;
+    T.n_antennas = 0;
+    T.n_edges = (int32_t)s->ek.size();
+    T.edge_kind = s->ek.data();
+    T.edge_a = s->ea.data();
+    T.edge_b = s->eb.data();
+    T.edge_ant = s->eant.data();
+    T.edge_robust = s->erob.data();
+    T.edge_ant_b = nullptr;
+    uwbgo_range_msgs m{};
+    m.distance = s->d[nxt];
+    m.distance_err = s->e[nxt];
+    m.dt_anchor = nullptr;
+    m.dt_pose = s->dt[nxt];
+    m.v_max = s->v_max;
+    uwbgo_batch b{};
+    b.n_windows = (int64_t)W;
+    b.pose_t = s->in;
+    b.anchors = s->anchors;
+    b.range_msgs = &m;
+    b.shared = UWBGO_SHARED_ANCHORS;
+    uwbgo_result r{};
+    r.pose_t = s->res;
+    r.chi2 = s->chi2;
+    r.status = s->status;
+    int rc = uwbgo_solve_batch_device(s->ctx, &T, &b, &s->cfg, &r, s->st);
+    if (rc) return rc;
+    stream_newest_kernel<<<(unsigned)((W * 3 + 255) / 256), 256, 0, s->st>>>((int64_t)W, N, s->res, s->newest);
+    SCU(cudaGetLastError());
+    char *ho = s->pin + s->pin_in;
+    double *h_new = reinterpret_cast<double *>(ho), *h_chi = reinterpret_cast<double *>(ho + up256(W * 24));
+    int32_t *h_st = reinterpret_cast<int32_t *>(ho + up256(W * 24) + up256(W * 32));
+    if (newest_pose) SCU(cudaMemcpyAsync(h_new, s->newest, W * 24, cudaMemcpyDeviceToHost, s->st));
+    if (chi2) SCU(cudaMemcpyAsync(h_chi, s->chi2, W * 32, cudaMemcpyDeviceToHost, s->st));
+    if (status) SCU(cudaMemcpyAsync(h_st, s->status, W * 16, cudaMemcpyDeviceToHost, s->st));
+    SCU(cudaStreamSynchronize(s->st));
+    if (newest_pose) memcpy(newest_pose, h_new, W * 24);
+    if (chi2) memcpy(chi2, h_chi, W * 32);
+    if (status) memcpy(status, h_st, W * 16);
+    return 0;
+}
+
+int uwbgo_stream_read(uwbgo_stream *s, double *pose_t)
+{
+    if (!s || !s->loaded || !pose_t) return UWBGO_E_INVALID;
+    SCU(cudaStreamSynchronize(s->st));
+    SCU(cudaMemcpy(pose_t, s->res, (size_t)s->W * s->N * 24, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -10,6 +10,7 @@ nvcc $FLAGS -c uwbgo_kernels.cu -o /tmp/uwbgo_kernels_$1.o &
 nvcc $FLAGS -c uwbgo_general_items.cu -o /tmp/uwbgo_general_items_$1.o &
 nvcc $FLAGS -c uwbgo_window.cu -o /tmp/uwbgo_window_$1.o &
 nvcc $FLAGS -c uwbgo_api.cu -o /tmp/uwbgo_api_$1.o &
+nvcc $FLAGS -c uwbgo_stream.cu -o /tmp/uwbgo_stream_$1.o &
 wait
-nvcc $ARCH -shared -o ../../variants/libuwbgo_$1.so /tmp/uwbgo_kernels_$1.o /tmp/uwbgo_general_items_$1.o /tmp/uwbgo_window_$1.o /tmp/uwbgo_api_$1.o
+nvcc $ARCH -shared -o ../../variants/libuwbgo_$1.so /tmp/uwbgo_kernels_$1.o /tmp/uwbgo_general_items_$1.o /tmp/uwbgo_window_$1.o /tmp/uwbgo_api_$1.o /tmp/uwbgo_stream_$1.o
 echo built variants/libuwbgo_$1.so

@@ -1,0 +1,70 @@
+"""uwbgo_stream (resident fleet): the windows stay on the device, a step sends one range message per robot.  Every
+step must give the bits of the oracle on the window the reference would hold -- Localization::addRangeEdge
+(localization.cpp:297-376): new vertex = copy of the newest estimate, range edge to the anchor, zero-length
+trajectory edge to the previous vertex, oldest vertex dropped (robot.cpp:75-110) -- built here by shifting the
+arrays on the host."""
+import numpy as np
+import pytest
+
+from localization_b200 import Batch, Config
+from localization_b200.graph import RangeMsgs
+from localization_b200.stream import ResidentFleet, chain_topology
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("W,N,A,steps", [(200, 12, 4, 9), (33, 5, 3, 7), (1000, 50, 8, 3)])
+def test_resident_fleet_matches_shifted_windows(_gpu_solver, W, N, A, steps):
+    rng = np.random.default_rng(100 + N)
+    v_max = 5.0
+    cfg = Config(max_iterations=10)
+    anchors = rng.uniform(-6.0, 6.0, (A, 3)) + np.array([0.0, 0.0, 2.0])
+    T = N + steps
+    vel = rng.normal(0.0, 0.6, (W, 1, 3))
+    truth = rng.uniform(-3.0, 3.0, (W, 1, 3)) + np.cumsum(np.broadcast_to(vel, (W, T, 3)) * 0.04 + rng.normal(0, 0.01, (W, T, 3)), axis=1)
+    aop_all = np.arange(T) % A
+    d_all = (np.linalg.norm(truth - anchors[aop_all][None], axis=2) + rng.normal(0, 0.05, (W, T))).astype(np.float32)
+    e_all = np.where(rng.uniform(size=(W, T)) < 0.7, np.float32(0.055), np.float32(0.024)).astype(np.float32)
+    dt_all = rng.uniform(0.02, 0.06, (W, T))                     # dt_all[:, k]: stamp of pose k minus stamp of pose k - 1
+    pose = truth[:, :N] + rng.normal(0, 0.1, (W, N, 3))
+    d, e, dt, aop = d_all[:, :N].copy(), e_all[:, :N].copy(), dt_all[:, 1:N].copy(), list(aop_all[:N])
+    fleet = ResidentFleet(_gpu_solver, N, anchors, W, v_max, cfg)
+    try:
+        fleet.load(pose, aop, d, e, dt)
+        assert np.array_equal(fleet.read(), pose)
+        for s in range(steps):
+            k = N + s
+            a = int(aop_all[k])
+            pose_in = np.concatenate([pose[:, 1:], pose[:, -1:]], axis=1)
+            d = np.concatenate([d[:, 1:], d_all[:, k:k + 1]], axis=1)
+            e = np.concatenate([e[:, 1:], e_all[:, k:k + 1]], axis=1)
+            dt = np.concatenate([dt[:, 1:], dt_all[:, k:k + 1]], axis=1)
+            aop = aop[1:] + [a]
+            topo = chain_topology(N, A, aop)
+            batch = Batch(pose_t=pose_in, anchors=anchors, shared_anchors=True,
+                          range_msgs=RangeMsgs(distance=d, distance_err=e, dt_pose=np.ascontiguousarray(dt), v_max=v_max))
+            ref = oracle.solve(topo, batch, cfg)
+            newest, chi2, status = fleet.step(a, d_all[:, k], e_all[:, k], dt_all[:, k])
+            assert _gpu_solver.last_path == 2                    # the straight-line CHAIN kernel
+            assert np.array_equal(newest, ref.pose_t[:, -1]), (s, np.abs(newest - ref.pose_t[:, -1]).max())
+            assert np.array_equal(chi2, ref.chi2) and np.array_equal(status, ref.status)
+            pose = ref.pose_t
+        assert np.array_equal(fleet.read(), pose)
+    finally:
+        fleet.close()
+
+
+def test_resident_fleet_rejects_bad_arguments(_gpu_solver):
+    cfg = Config(max_iterations=3)
+    anchors = np.zeros((4, 3))
+    fleet = ResidentFleet(_gpu_solver, 6, anchors, 8, 5.0, cfg)
+    try:
+        z = np.zeros(8, np.float32)
+        with pytest.raises(Exception):
+            fleet.step(0, z, z, np.zeros(8))                     # nothing loaded yet
+        fleet.load(np.zeros((8, 6, 3)), [0, 1, 2, 3, 0, 1], np.ones((8, 6), np.float32), np.ones((8, 6), np.float32), np.ones((8, 5)))
+        with pytest.raises(Exception):
+            fleet.step(4, z, z, np.zeros(8))                     # anchor out of range
+    finally:
+        fleet.close()

@@ -338,6 +338,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--stages", action="store_true", help="(default on C3 at N=1) also time the linearise stage kernel")
     ap.add_argument("--no-stages", action="store_true", help="skip the linearise stage timing")
+    ap.add_argument("--no-resident", action="store_true", help="skip the resident-fleet (uwbgo_stream) leg")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + sorted(LATENCY_WORKLOADS),
                     help="c3 = BASELINE metric config (default); c1 / c2 = one window per call (latency); "
                          "the others are the remaining BASELINE configs")
@@ -515,6 +516,50 @@ def main():
                     "same": bool(np.array_equal(hres.pose_t, d_pose.cpu().numpy())
                                  and np.array_equal(hres.chi2, d_chi2.cpu().numpy())
                                  and np.array_equal(hres.status, d_status.cpu().numpy()))})
+        # ---- resident fleet (uwbgo_stream): the same robots, their windows kept on the device; a step = one range
+        # message per robot in (host arrays), shift + solve on the device, newest pose + chi2 + status out.  UWB-only
+        # chain windows in the compact form with one anchor constellation (c3 / c5)
+        if msgs is not None and batch.shared_anchors and not general and not args.no_resident:
+            from localization_b200.stream import ResidentFleet
+            fleet = ResidentFleet(solver, N, batch.anchors, W, msgs.v_max, cfg)
+            A = topo.n_anchors
+            fleet.load(batch.pose_t, np.arange(N) % A, msgs.distance, msgs.distance_err, msgs.dt_pose)
+            # the messages of the steps: the fields of the window's own edges, taken round robin (same statistics)
+            def pinned_col(a, k, dt):
+                c = pinned_empty((W,), dt)
+                c[...] = a[:, k]
+                return c
+            m_d = [pinned_col(msgs.distance, k % N, np.float32) for k in range(8)]
+            m_e = [pinned_col(msgs.distance_err, k % N, np.float32) for k in range(8)]
+            m_t = [pinned_col(msgs.dt_pose, k % (N - 1), np.float64) for k in range(8)]
+            step_no = [0]
+
+            def step_resident():
+                k = step_no[0]
+                step_no[0] += 1
+                fleet.step((N + k) % A, m_d[k % 8], m_e[k % 8], m_t[k % 8])
+
+            for _ in range(args.warmup):
+                step_resident()
+            barrier()
+            l1 = solver.launch_count
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_resident()
+            barrier()
+            res_s = max_over_ranks(time.perf_counter() - t0)
+            out["resident"] = {"value": W * world * args.steps / res_s, "unit": UNIT, "ms_per_step": res_s / args.steps * 1e3,
+                               "h2d_bytes_per_step": W * 16, "d2h_bytes_per_step": W * 72,
+                               "kernel_ms": solver.mean_kernel_ms(min(args.steps, 64)),
+                               "gpu_launches": int(solver.launch_count - l1) + 2 * args.steps,
+                               "what": ("uwbgo_stream_step: the windows of the same robots RESIDENT in HBM (the reference's call "
+                                        "pattern: one range message per robot -> new vertex = copy of the newest estimate, "
+                                        "oldest vertex dropped, solve; localization.cpp:297-376, robot.cpp:75-110); per step "
+                                        "one message per robot host -> device (16 B) and the newest pose + chi2 + status "
+                                        "device -> host (72 B) inside the timed region, every step a full "
+                                        f"{wl_iters}-iteration LM solve of a {N}-pose window; bit-identical to the oracle on "
+                                        "host-shifted windows (tests/test_gpu_stream.py)")}
+            fleet.close()
         return out
 
     sampler = ClockSampler(local)
@@ -592,6 +637,8 @@ def main():
                 "gpu_launches": m["launches"], "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         if "shards_verified" in m:
             line["shards_verified"] = m["shards_verified"]
+        if "resident" in m:
+            line["e2e_resident"] = m["resident"]
         if other:
             line["strong" if args.scaling == "weak" else "weak"] = {
                 "value": other["value"], "unit": UNIT, "ms_per_step": other["ms_per_step"],
@@ -599,6 +646,7 @@ def main():
                 "e2e": {"value": other["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": other["h2d"],
                         "d2h_bytes_per_step": other["d2h"], "matches_device_leg": other["same"]},
                 "gpu_launches": other["launches"],
+                **({"e2e_resident": other["resident"]} if "resident" in other else {}),
                 "what": ("strong scaling: the workload's windows in TOTAL, split over the ranks (north_star quotes its "
                          "target on 65,536 windows at 8 GPUs)") if args.scaling == "weak"
                         else "weak scaling: the workload's windows per GPU"}

@@ -269,7 +269,8 @@ int  uwbgo_stream_load(uwbgo_stream *s, const double *pose_t, const int32_t *anc
                        const float *distance, const float *distance_err, const double *dt);
 /* one range message per robot (host arrays [W]) from anchor `anchor`: shift the windows, append the new
  * vertex and its two edges, optimise, return the newest pose [W][3], chi2 [W][4] and status [W][4] (as
- * uwbgo_result; any may be NULL).  Returns when the results are in the host arrays. */
+ * uwbgo_result; any may be NULL).  Returns when the results are in the host arrays.  Page-locked arrays
+ * (uwbgo_host_alloc) are copied without staging. */
 int  uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, const float *distance_err,
                        const double *dt, double *newest_pose, double *chi2, int32_t *status);
 /* all estimates of the windows as the last step left them, [W][N][3] (host array) */

@@ -66,8 +66,6 @@ struct uwbgo_stream {
     double *res = nullptr, *in = nullptr, *dt[2] = {nullptr, nullptr}, *anchors = nullptr, *chi2 = nullptr, *newest = nullptr, *msg_dt = nullptr;
     float *d[2] = {nullptr, nullptr}, *e[2] = {nullptr, nullptr}, *msg_d = nullptr, *msg_e = nullptr;
     int32_t *status = nullptr;
-    char *pin = nullptr; /* pinned staging: message in | newest, chi2, status out */
-    size_t pin_in = 0, pin_out = 0;
     int cur = 0;
     bool loaded = false;
     cudaStream_t st = nullptr;
@@ -145,10 +143,7 @@ int uwbgo_stream_create(uwbgo_ctx *ctx, int32_t n_poses, int32_t n_anchors, int6
     s->msg_d = reinterpret_cast<float *>(s->dev + o_md);
     s->msg_e = reinterpret_cast<float *>(s->dev + o_me);
     s->msg_dt = reinterpret_cast<double *>(s->dev + o_mdt);
-    s->pin_in = up256(W * 4) * 2 + up256(W * 8);
-    s->pin_out = up256(W * 24) + up256(W * 32) + up256(W * 16);
-    if (cudaHostAlloc(reinterpret_cast<void **>(&s->pin), s->pin_in + s->pin_out, cudaHostAllocDefault) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMemcpy(s->anchors, anchors, (size_t)n_anchors * 24, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaGetLastError();
         uwbgo_stream_destroy(s);
@@ -165,7 +160,6 @@ void uwbgo_stream_destroy(uwbgo_stream *s)
         cudaStreamSynchronize(s->st);
         cudaStreamDestroy(s->st);
     }
-    if (s->pin) cudaFreeHost(s->pin);
     if (s->dev) cudaFree(s->dev);
     delete s;
 }
@@ -194,15 +188,11 @@ int uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, co
     if (!s || !s->loaded || !distance || !distance_err || !dt || anchor < 0 || anchor >= s->A) return UWBGO_E_INVALID;
     const size_t W = (size_t)s->W;
     const int N = s->N;
-    /* the message through pinned staging (the caller's arrays may be pageable), one copy per field */
-    float *h_d = reinterpret_cast<float *>(s->pin), *h_e = reinterpret_cast<float *>(s->pin + up256(W * 4));
-    double *h_dt = reinterpret_cast<double *>(s->pin + 2 * up256(W * 4));
-    memcpy(h_d, distance, W * 4);
-    memcpy(h_e, distance_err, W * 4);
-    memcpy(h_dt, dt, W * 8);
-    SCU(cudaMemcpyAsync(s->msg_d, h_d, W * 4, cudaMemcpyHostToDevice, s->st));
-    SCU(cudaMemcpyAsync(s->msg_e, h_e, W * 4, cudaMemcpyHostToDevice, s->st));
-    SCU(cudaMemcpyAsync(s->msg_dt, h_dt, W * 8, cudaMemcpyHostToDevice, s->st));
+    /* the message straight from the caller's arrays (page-locked ones -- uwbgo_host_alloc -- make the copies
+     * asynchronous; pageable ones work, the runtime stages them) */
+    SCU(cudaMemcpyAsync(s->msg_d, distance, W * 4, cudaMemcpyHostToDevice, s->st));
+    SCU(cudaMemcpyAsync(s->msg_e, distance_err, W * 4, cudaMemcpyHostToDevice, s->st));
+    SCU(cudaMemcpyAsync(s->msg_dt, dt, W * 8, cudaMemcpyHostToDevice, s->st));
     const int nxt = s->cur ^ 1;
     const int64_t threads = (int64_t)W * N;
     stream_shift_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s->st>>>(
@@ -245,16 +235,10 @@ int uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, co
     if (rc) return rc;
     stream_newest_kernel<<<(unsigned)((W * 3 + 255) / 256), 256, 0, s->st>>>((int64_t)W, N, s->res, s->newest);
     SCU(cudaGetLastError());
-    char *ho = s->pin + s->pin_in;
-    double *h_new = reinterpret_cast<double *>(ho), *h_chi = reinterpret_cast<double *>(ho + up256(W * 24));
-    int32_t *h_st = reinterpret_cast<int32_t *>(ho + up256(W * 24) + up256(W * 32));
-    if (newest_pose) SCU(cudaMemcpyAsync(h_new, s->newest, W * 24, cudaMemcpyDeviceToHost, s->st));
-    if (chi2) SCU(cudaMemcpyAsync(h_chi, s->chi2, W * 32, cudaMemcpyDeviceToHost, s->st));
-    if (status) SCU(cudaMemcpyAsync(h_st, s->status, W * 16, cudaMemcpyDeviceToHost, s->st));
+    if (newest_pose) SCU(cudaMemcpyAsync(newest_pose, s->newest, W * 24, cudaMemcpyDeviceToHost, s->st));
+    if (chi2) SCU(cudaMemcpyAsync(chi2, s->chi2, W * 32, cudaMemcpyDeviceToHost, s->st));
+    if (status) SCU(cudaMemcpyAsync(status, s->status, W * 16, cudaMemcpyDeviceToHost, s->st));
     SCU(cudaStreamSynchronize(s->st));
-    if (newest_pose) memcpy(newest_pose, h_new, W * 24);
-    if (chi2) memcpy(chi2, h_chi, W * 32);
-    if (status) memcpy(status, h_st, W * 16);
     return 0;
 }
 

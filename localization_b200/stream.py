@@ -7,7 +7,7 @@ import numpy as np
 
 from . import _ffi
 from .graph import Config, Topology
-from .solver import Solver, UwbgoError
+from .solver import Solver, UwbgoError, pinned_empty
 
 
 def _pf(a):
@@ -31,9 +31,9 @@ class ResidentFleet:
                                            C.byref(self._h))
         if rc != 0:
             raise UwbgoError(f"uwbgo_stream_create failed: {rc}")
-        self._newest = np.empty((self.W, 3))
-        self._chi2 = np.empty((self.W, 4))
-        self._status = np.empty((self.W, 4), np.int32)
+        self._newest = pinned_empty((self.W, 3))
+        self._chi2 = pinned_empty((self.W, 4))
+        self._status = pinned_empty((self.W, 4), np.int32)
 
     def _check(self, rc, what):
         if rc != 0:

@@ -12,8 +12,6 @@
  * one and writes the other), estimates in `res` (what the last solve left) and `in` (what the next one
  * starts from). */
 #include <cstdio>
-#include <cstring>
-#include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -49,8 +47,6 @@ __global__ void __launch_bounds__(256) stream_newest_kernel(int64_t W, int N, co
     const int64_t w = t / 3;
     newest[t] = res[(w * N + (N - 1)) * 3 + (t - w * 3)];
 }
-
-thread_local std::string g_stream_error;
 
 }  // namespace
 

@@ -32,6 +32,21 @@ def test_library_exports_every_declared_symbol():
     assert _ffi.load_library().uwbgo_abi_version() == _ffi.ABI_VERSION
 
 
+def test_stream_entry_points_reject_null_arguments():
+    """uwbgo_stream_* (resident fleet) check their arguments before touching the device"""
+    lib = _ffi.load_library()
+    h = ctypes.c_void_p()
+    cfg = _ffi.CConfig()
+    lib.uwbgo_config_default(ctypes.byref(cfg))
+    anchors = (ctypes.c_double * 12)()
+    assert lib.uwbgo_stream_create(None, 10, 4, 8, anchors, 5.0, ctypes.byref(cfg), ctypes.byref(h)) == -1   # UWBGO_E_INVALID
+    assert not h
+    assert lib.uwbgo_stream_step(None, 0, None, None, None, None, None, None) == -1
+    assert lib.uwbgo_stream_load(None, None, None, None, None, None) == -1
+    assert lib.uwbgo_stream_read(None, None) == -1
+    lib.uwbgo_stream_destroy(None)
+
+
 def test_host_library_exports_every_declared_symbol():
     from localization_b200 import host
     lib = host.load_host_library()

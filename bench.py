@@ -523,7 +523,6 @@ def main():
             from localization_b200.stream import ResidentFleet
             fleet = ResidentFleet(solver, N, batch.anchors, W, msgs.v_max, cfg)
             A = topo.n_anchors
-            fleet.load(batch.pose_t, np.arange(N) % A, msgs.distance, msgs.distance_err, msgs.dt_pose)
             # the messages of the steps: the fields of the window's own edges, taken round robin (same statistics)
             def pinned_col(a, k, dt):
                 c = pinned_empty((W,), dt)
@@ -532,33 +531,46 @@ def main():
             m_d = [pinned_col(msgs.distance, k % N, np.float32) for k in range(8)]
             m_e = [pinned_col(msgs.distance_err, k % N, np.float32) for k in range(8)]
             m_t = [pinned_col(msgs.dt_pose, k % (N - 1), np.float64) for k in range(8)]
-            step_no = [0]
 
-            def step_resident():
-                k = step_no[0]
-                step_no[0] += 1
-                fleet.step((N + k) % A, m_d[k % 8], m_e[k % 8], m_t[k % 8])
+            def run_resident(per_robot):
+                # per_robot: every robot ranges its own anchor in a step (robot w starts its round robin at w), the
+                # anchor id is a fifth message field; else one anchor per step for the whole fleet
+                first = (np.arange(W, dtype=np.int64) % A)[:, None] if per_robot else 0
+                aop = ((np.arange(N)[None, :] + first) % A).astype(np.int32) if per_robot else np.arange(N) % A
+                fleet.load(batch.pose_t, aop, msgs.distance, msgs.distance_err, msgs.dt_pose)
+                m_a = [pinned_col(((N + k + first) % A).astype(np.int32), 0, np.int32) for k in range(A)] if per_robot else None
+                step_no = [0]
 
-            for _ in range(args.warmup):
-                step_resident()
-            barrier()
-            l1 = solver.launch_count
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                step_resident()
-            barrier()
-            res_s = max_over_ranks(time.perf_counter() - t0)
-            out["resident"] = {"value": W * world * args.steps / res_s, "unit": UNIT, "ms_per_step": res_s / args.steps * 1e3,
-                               "h2d_bytes_per_step": W * 16, "d2h_bytes_per_step": W * 72,
-                               "kernel_ms": solver.mean_kernel_ms(min(args.steps, 64)),
-                               "gpu_launches": int(solver.launch_count - l1) + 2 * args.steps,
-                               "what": ("uwbgo_stream_step: the windows of the same robots RESIDENT in HBM (the reference's call "
-                                        "pattern: one range message per robot -> new vertex = copy of the newest estimate, "
-                                        "oldest vertex dropped, solve; localization.cpp:297-376, robot.cpp:75-110); per step "
-                                        "one message per robot host -> device (16 B) and the newest pose + chi2 + status "
-                                        "device -> host (72 B) inside the timed region, every step a full "
-                                        f"{wl_iters}-iteration LM solve of a {N}-pose window; bit-identical to the oracle on "
-                                        "host-shifted windows (tests/test_gpu_stream.py)")}
+                def step_resident():
+                    k = step_no[0]
+                    step_no[0] += 1
+                    fleet.step(m_a[k % A] if per_robot else (N + k) % A, m_d[k % 8], m_e[k % 8], m_t[k % 8])
+
+                for _ in range(args.warmup):
+                    step_resident()
+                barrier()
+                l1 = solver.launch_count
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    step_resident()
+                barrier()
+                res_s = max_over_ranks(time.perf_counter() - t0)
+                return {"value": W * world * args.steps / res_s, "unit": UNIT, "ms_per_step": res_s / args.steps * 1e3,
+                        "h2d_bytes_per_step": W * (20 if per_robot else 16), "d2h_bytes_per_step": W * 72,
+                        "kernel_ms": solver.mean_kernel_ms(min(args.steps, 64)),
+                        "gpu_launches": int(solver.launch_count - l1) + 2 * args.steps}
+
+            out["resident"] = run_resident(False)
+            out["resident"]["what"] = ("uwbgo_stream_step: the windows of the same robots RESIDENT in HBM (the reference's call "
+                                       "pattern: one range message per robot -> new vertex = copy of the newest estimate, "
+                                       "oldest vertex dropped, solve; localization.cpp:297-376, robot.cpp:75-110); per step "
+                                       "one message per robot host -> device (16 B) and the newest pose + chi2 + status "
+                                       "device -> host (72 B) inside the timed region, every step a full "
+                                       f"{wl_iters}-iteration LM solve of a {N}-pose window; bit-identical to the oracle on "
+                                       "host-shifted windows (tests/test_gpu_stream.py)")
+            out["resident"]["per_robot_anchors"] = run_resident(True)
+            out["resident"]["per_robot_anchors"]["what"] = ("uwbgo_stream_step_robots: the same with one anchor sequence per robot "
+                                                            "(the anchor id is a fifth message field, 20 B per robot and step)")
             fleet.close()
         return out
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UWBGO_ABI_VERSION 4
+#define UWBGO_ABI_VERSION 5
 
 /* error codes */
 #define UWBGO_OK              0
@@ -255,8 +255,11 @@ int uwbgo_factor_solve_batch_device(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_w
  * edges -- so that a step moves only the new message to the device (16 bytes per robot) and the newest
  * pose, chi2 and status back (72 bytes), instead of whole windows (C3: 1,992 + 1,248 bytes).  The solve is
  * the one of uwbgo_solve_batch_device on the window the reference would hold: the same bits (tested
- * against windows shifted on the host).  All robots range the same anchor in a step (one TDMA slot per
- * anchor); anchors are one constellation for the fleet.  UWB-only windows (uwb_only.yaml).
+ * against windows shifted on the host).  Anchors are one constellation for the fleet.  Either all robots
+ * range the same anchor in a step (one TDMA slot per anchor: _load / _step) or every robot has its own
+ * anchor sequence (_load_robots / _step_robots: the anchor id is one more message field, 4 bytes per robot;
+ * on the device the ids move with the poses and each window reads its own N anchor positions, so the graph
+ * structure is one for the whole fleet and for every step).  UWB-only windows (uwb_only.yaml).
  */
 typedef struct uwbgo_stream uwbgo_stream;
 int  uwbgo_stream_create(uwbgo_ctx *ctx, int32_t n_poses, int32_t n_anchors, int64_t n_windows,
@@ -273,6 +276,14 @@ int  uwbgo_stream_load(uwbgo_stream *s, const double *pose_t, const int32_t *anc
  * (uwbgo_host_alloc) are copied without staging. */
 int  uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, const float *distance_err,
                        const double *dt, double *newest_pose, double *chi2, int32_t *status);
+/* the same with one anchor sequence PER ROBOT: anchor_of_pose is [W][N], a step's anchor ids are [W]
+ * (UwbRange::responder_id mapped to the anchor's row, localization.cpp:305-306,331).  A stream is stepped the way
+ * it was loaded (else UWBGO_E_INVALID); ids outside [0, A) are refused before anything is queued. */
+int  uwbgo_stream_load_robots(uwbgo_stream *s, const double *pose_t, const int32_t *anchor_of_pose,
+                              const float *distance, const float *distance_err, const double *dt);
+int  uwbgo_stream_step_robots(uwbgo_stream *s, const int32_t *anchor, const float *distance,
+                              const float *distance_err, const double *dt, double *newest_pose, double *chi2,
+                              int32_t *status);
 /* all estimates of the windows as the last step left them, [W][N][3] (host array) */
 int  uwbgo_stream_read(uwbgo_stream *s, double *pose_t);
 /* kernels launched / duration of the LM kernel of the last step (ms; needs uwbgo_set_profiling) come

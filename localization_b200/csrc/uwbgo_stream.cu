@@ -24,7 +24,9 @@ __global__ void __launch_bounds__(256)
 stream_shift_kernel(int64_t W, int N, const double *__restrict__ res, double *__restrict__ in,
                     const float *__restrict__ d_old, const float *__restrict__ e_old, const double *__restrict__ dt_old,
                     float *__restrict__ d_new, float *__restrict__ e_new, double *__restrict__ dt_new,
-                    const float *__restrict__ msg_d, const float *__restrict__ msg_e, const double *__restrict__ msg_dt)
+                    const float *__restrict__ msg_d, const float *__restrict__ msg_e, const double *__restrict__ msg_dt,
+                    const int32_t *__restrict__ a_old, int32_t *__restrict__ a_new, const int32_t *__restrict__ msg_a,
+                    const double *__restrict__ anchors, double *__restrict__ anch_w)
 {
     /* one thread per (window, pose): pose i of the new window is pose i + 1 of the old one; the new vertex
      * starts at the estimate of the newest (robot.cpp: new_vertex copies the last estimate) */
@@ -38,6 +40,14 @@ stream_shift_kernel(int64_t W, int N, const double *__restrict__ res, double *__
     d_new[t] = i + 1 < N ? d_old[w * N + i + 1] : msg_d[w];
     e_new[t] = i + 1 < N ? e_old[w * N + i + 1] : msg_e[w];
     if (i + 1 < N) dt_new[w * (N - 1) + i] = i + 2 < N ? dt_old[w * (N - 1) + i + 1] : msg_dt[w];
+    if (a_new) {
+        /* per-robot anchor sequences: the anchor id of every range edge moves with its pose, and the solve
+         * reads the anchor of pose i of window w at anch_w[w][i] (a window-private "constellation" of N) */
+        const int32_t a = i + 1 < N ? a_old[w * N + i + 1] : msg_a[w];
+        a_new[t] = a;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) anch_w[t * 3 + k] = anchors[(size_t)a * 3 + k];
+    }
 }
 
 __global__ void __launch_bounds__(256) stream_newest_kernel(int64_t W, int N, const double *__restrict__ res, double *__restrict__ newest)
@@ -62,6 +72,11 @@ struct uwbgo_stream {
     double *res = nullptr, *in = nullptr, *dt[2] = {nullptr, nullptr}, *anchors = nullptr, *chi2 = nullptr, *newest = nullptr, *msg_dt = nullptr;
     float *d[2] = {nullptr, nullptr}, *e[2] = {nullptr, nullptr}, *msg_d = nullptr, *msg_e = nullptr;
     int32_t *status = nullptr;
+    /* per-robot anchor sequences (uwbgo_stream_load_robots / _step_robots): one more allocation, made on first use */
+    char *dev_r = nullptr;
+    int32_t *aid[2] = {nullptr, nullptr}, *msg_a = nullptr;
+    double *anch_w = nullptr;
+    bool per_robot = false;
     int cur = 0;
     bool loaded = false;
     cudaStream_t st = nullptr;
@@ -157,19 +172,59 @@ void uwbgo_stream_destroy(uwbgo_stream *s)
         cudaStreamDestroy(s->st);
     }
     if (s->dev) cudaFree(s->dev);
+    if (s->dev_r) cudaFree(s->dev_r);
     delete s;
 }
 
-int uwbgo_stream_load(uwbgo_stream *s, const double *pose_t, const int32_t *anchor_of_pose, const float *distance,
-                      const float *distance_err, const double *dt)
+}  // extern "C"
+
+namespace {
+
+int ensure_robot_arrays(uwbgo_stream *s)
+{
+    if (s->dev_r) return 0;
+    const size_t W = (size_t)s->W, N = (size_t)s->N;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += up256(bytes); return at; };
+    const size_t o_a0 = take(W * N * 4), o_a1 = take(W * N * 4), o_ma = take(W * 4), o_aw = take(W * N * 24);
+    if (cudaMalloc(&s->dev_r, o) != cudaSuccess) {
+        cudaGetLastError();
+        s->dev_r = nullptr;
+        return UWBGO_E_NOMEM;
+    }
+    s->aid[0] = reinterpret_cast<int32_t *>(s->dev_r + o_a0);
+    s->aid[1] = reinterpret_cast<int32_t *>(s->dev_r + o_a1);
+    s->msg_a = reinterpret_cast<int32_t *>(s->dev_r + o_ma);
+    s->anch_w = reinterpret_cast<double *>(s->dev_r + o_aw);
+    return 0;
+}
+
+/* anchor_of_pose: [N] (one sequence for the fleet) or, per_robot, [W][N] */
+int load_impl(uwbgo_stream *s, bool per_robot, const double *pose_t, const int32_t *anchor_of_pose, const float *distance,
+              const float *distance_err, const double *dt)
 {
     if (!s || !pose_t || !anchor_of_pose || !distance || !distance_err || !dt) return UWBGO_E_INVALID;
     const size_t W = (size_t)s->W, N = (size_t)s->N;
-    for (int k = 0; k < s->N; ++k)
+    const size_t n_ids = per_robot ? W * N : N;
+    for (size_t k = 0; k < n_ids; ++k)
         if (anchor_of_pose[k] < 0 || anchor_of_pose[k] >= s->A) return UWBGO_E_INVALID;
-    s->anchor_of_pose.assign(anchor_of_pose, anchor_of_pose + s->N);
+    if (per_robot) {
+        int rc = ensure_robot_arrays(s);
+        if (rc) return rc;
+    }
     SCU(cudaStreamSynchronize(s->st));
+    s->loaded = false;
+    s->per_robot = per_robot;
     s->cur = 0;
+    if (per_robot) {
+        /* every window brings its own anchors: pose k reads "anchor k" of its window (anch_w[w][k]), so the
+         * structure of the graph is the same for every robot and every step */
+        s->anchor_of_pose.resize(N);
+        for (size_t k = 0; k < N; ++k) s->anchor_of_pose[k] = (int32_t)k;
+        SCU(cudaMemcpy(s->aid[0], anchor_of_pose, W * N * 4, cudaMemcpyHostToDevice));
+    } else {
+        s->anchor_of_pose.assign(anchor_of_pose, anchor_of_pose + N);
+    }
     SCU(cudaMemcpy(s->res, pose_t, W * N * 24, cudaMemcpyHostToDevice));
     SCU(cudaMemcpy(s->d[0], distance, W * N * 4, cudaMemcpyHostToDevice));
     SCU(cudaMemcpy(s->e[0], distance_err, W * N * 4, cudaMemcpyHostToDevice));
@@ -178,31 +233,44 @@ int uwbgo_stream_load(uwbgo_stream *s, const double *pose_t, const int32_t *anch
     return 0;
 }
 
-int uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, const float *distance_err, const double *dt,
-                      double *newest_pose, double *chi2, int32_t *status)
+/* anchor_w != NULL: one anchor id per robot (per_robot streams); else `anchor` for the whole fleet */
+int step_impl(uwbgo_stream *s, int32_t anchor, const int32_t *anchor_w, const float *distance, const float *distance_err,
+              const double *dt, double *newest_pose, double *chi2, int32_t *status)
 {
-    if (!s || !s->loaded || !distance || !distance_err || !dt || anchor < 0 || anchor >= s->A) return UWBGO_E_INVALID;
+    if (!s || !s->loaded || !distance || !distance_err || !dt) return UWBGO_E_INVALID;
+    const bool per_robot = anchor_w != nullptr;
+    if (per_robot != s->per_robot) return UWBGO_E_INVALID; /* the step must match the load */
     const size_t W = (size_t)s->W;
     const int N = s->N;
+    if (per_robot) {
+        for (size_t w = 0; w < W; ++w)
+            if (anchor_w[w] < 0 || anchor_w[w] >= s->A) return UWBGO_E_INVALID;
+    } else if (anchor < 0 || anchor >= s->A) {
+        return UWBGO_E_INVALID;
+    }
     /* the message straight from the caller's arrays (page-locked ones -- uwbgo_host_alloc -- make the copies
      * asynchronous; pageable ones work, the runtime stages them) */
     SCU(cudaMemcpyAsync(s->msg_d, distance, W * 4, cudaMemcpyHostToDevice, s->st));
     SCU(cudaMemcpyAsync(s->msg_e, distance_err, W * 4, cudaMemcpyHostToDevice, s->st));
     SCU(cudaMemcpyAsync(s->msg_dt, dt, W * 8, cudaMemcpyHostToDevice, s->st));
+    if (per_robot) SCU(cudaMemcpyAsync(s->msg_a, anchor_w, W * 4, cudaMemcpyHostToDevice, s->st));
     const int nxt = s->cur ^ 1;
     const int64_t threads = (int64_t)W * N;
     stream_shift_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s->st>>>(
         (int64_t)W, N, s->res, s->in, s->d[s->cur], s->e[s->cur], s->dt[s->cur], s->d[nxt], s->e[nxt], s->dt[nxt], s->msg_d,
-        s->msg_e, s->msg_dt);
+        s->msg_e, s->msg_dt, per_robot ? s->aid[s->cur] : nullptr, per_robot ? s->aid[nxt] : nullptr, s->msg_a, s->anchors,
+        s->anch_w);
     SCU(cudaGetLastError());
     s->cur = nxt;
-    /* drop-oldest: the anchor pattern moves with the poses */
-    for (int k = 0; k + 1 < N; ++k) s->anchor_of_pose[k] = s->anchor_of_pose[k + 1];
-    s->anchor_of_pose[N - 1] = anchor;
+    if (!per_robot) {
+        /* drop-oldest: the anchor pattern moves with the poses */
+        for (int k = 0; k + 1 < N; ++k) s->anchor_of_pose[k] = s->anchor_of_pose[k + 1];
+        s->anchor_of_pose[N - 1] = anchor;
+    }
     build_topology(s);
     uwbgo_topology T{};
     T.n_poses = N;
-    T.n_anchors = s->A;
+    T.n_anchors = per_robot ? N : s->A;
     T.n_antennas = 0;
     T.n_edges = (int32_t)s->ek.size();
     T.edge_kind = s->ek.data();
@@ -220,9 +288,9 @@ int uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, co
     uwbgo_batch b{};
     b.n_windows = (int64_t)W;
     b.pose_t = s->in;
-    b.anchors = s->anchors;
+    b.anchors = per_robot ? s->anch_w : s->anchors;
     b.range_msgs = &m;
-    b.shared = UWBGO_SHARED_ANCHORS;
+    b.shared = per_robot ? 0 : UWBGO_SHARED_ANCHORS;
     uwbgo_result r{};
     r.pose_t = s->res;
     r.chi2 = s->chi2;
@@ -236,6 +304,35 @@ int uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, co
     if (status) SCU(cudaMemcpyAsync(status, s->status, W * 16, cudaMemcpyDeviceToHost, s->st));
     SCU(cudaStreamSynchronize(s->st));
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uwbgo_stream_load(uwbgo_stream *s, const double *pose_t, const int32_t *anchor_of_pose, const float *distance,
+                      const float *distance_err, const double *dt)
+{
+    return load_impl(s, false, pose_t, anchor_of_pose, distance, distance_err, dt);
+}
+
+int uwbgo_stream_load_robots(uwbgo_stream *s, const double *pose_t, const int32_t *anchor_of_pose, const float *distance,
+                             const float *distance_err, const double *dt)
+{
+    return load_impl(s, true, pose_t, anchor_of_pose, distance, distance_err, dt);
+}
+
+int uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, const float *distance_err, const double *dt,
+                      double *newest_pose, double *chi2, int32_t *status)
+{
+    return step_impl(s, anchor, nullptr, distance, distance_err, dt, newest_pose, chi2, status);
+}
+
+int uwbgo_stream_step_robots(uwbgo_stream *s, const int32_t *anchor, const float *distance, const float *distance_err,
+                             const double *dt, double *newest_pose, double *chi2, int32_t *status)
+{
+    if (!anchor) return UWBGO_E_INVALID;
+    return step_impl(s, 0, anchor, distance, distance_err, dt, newest_pose, chi2, status);
 }
 
 int uwbgo_stream_read(uwbgo_stream *s, double *pose_t)

@@ -45,21 +45,32 @@ class ResidentFleet:
         d = np.ascontiguousarray(distance, dtype=np.float32)
         e = np.ascontiguousarray(distance_err, dtype=np.float32)
         dt = np.ascontiguousarray(dt, dtype=np.float64)
-        assert pose_t.shape == (self.W, self.N, 3) and aop.shape == (self.N,)
+        assert pose_t.shape == (self.W, self.N, 3) and aop.shape in ((self.N,), (self.W, self.N))
         assert d.shape == (self.W, self.N) and e.shape == (self.W, self.N) and dt.shape == (self.W, self.N - 1)
-        self._check(self._lib.uwbgo_stream_load(self._h, _pd(pose_t), aop.ctypes.data_as(C.POINTER(C.c_int32)), _pf(d), _pf(e),
-                                                _pd(dt)), "uwbgo_stream_load")
+        # anchor_of_pose [N]: one anchor sequence for the fleet; [W][N]: one per robot
+        fn, what = ((self._lib.uwbgo_stream_load, "uwbgo_stream_load") if aop.ndim == 1 else
+                    (self._lib.uwbgo_stream_load_robots, "uwbgo_stream_load_robots"))
+        self._check(fn(self._h, _pd(pose_t), aop.ctypes.data_as(C.POINTER(C.c_int32)), _pf(d), _pf(e), _pd(dt)), what)
 
-    def step(self, anchor: int, distance, distance_err, dt):
-        """one range message per robot from `anchor`; returns (newest pose [W][3], chi2 [W][4], status [W][4]) --
-        views of buffers the next step overwrites"""
+    def step(self, anchor, distance, distance_err, dt):
+        """one range message per robot from `anchor` (an int: the same anchor for the fleet; an array [W]: one
+        per robot, for a fleet loaded with anchor_of_pose [W][N]); returns (newest pose [W][3], chi2 [W][4],
+        status [W][4]) -- views of buffers the next step overwrites"""
         d = np.ascontiguousarray(distance, dtype=np.float32)
         e = np.ascontiguousarray(distance_err, dtype=np.float32)
         dt = np.ascontiguousarray(dt, dtype=np.float64)
         assert d.shape == (self.W,) and e.shape == (self.W,) and dt.shape == (self.W,)
-        self._check(self._lib.uwbgo_stream_step(self._h, int(anchor), _pf(d), _pf(e), _pd(dt), _pd(self._newest),
-                                                _pd(self._chi2), self._status.ctypes.data_as(C.POINTER(C.c_int32))),
-                    "uwbgo_stream_step")
+        if np.ndim(anchor) == 0:
+            self._check(self._lib.uwbgo_stream_step(self._h, int(anchor), _pf(d), _pf(e), _pd(dt), _pd(self._newest),
+                                                    _pd(self._chi2), self._status.ctypes.data_as(C.POINTER(C.c_int32))),
+                        "uwbgo_stream_step")
+        else:
+            a = np.ascontiguousarray(anchor, dtype=np.int32)
+            assert a.shape == (self.W,)
+            self._check(self._lib.uwbgo_stream_step_robots(self._h, a.ctypes.data_as(C.POINTER(C.c_int32)), _pf(d), _pf(e),
+                                                           _pd(dt), _pd(self._newest), _pd(self._chi2),
+                                                           self._status.ctypes.data_as(C.POINTER(C.c_int32))),
+                        "uwbgo_stream_step_robots")
         return self._newest, self._chi2, self._status
 
     def read(self) -> np.ndarray:

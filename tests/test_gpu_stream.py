@@ -55,6 +55,67 @@ def test_resident_fleet_matches_shifted_windows(_gpu_solver, W, N, A, steps):
         fleet.close()
 
 
+@pytest.mark.parametrize("W,N,A,steps", [(200, 12, 4, 6), (33, 5, 3, 5), (1000, 50, 8, 2)])
+def test_resident_fleet_with_one_anchor_sequence_per_robot(_gpu_solver, W, N, A, steps):
+    """_load_robots / _step_robots: every robot ranges its own anchor in a step (UwbRange::responder_id,
+    localization.cpp:305-306,331).  The oracle solves each robot's window with the anchor ids of ITS edges: all
+    windows at once through window-private anchor rows, and a sample of them one by one on the topology the
+    reference would hold (anchor ids in the edge list, one shared constellation) -- the same bits either way."""
+    rng = np.random.default_rng(300 + N)
+    v_max = 5.0
+    cfg = Config(max_iterations=10)
+    anchors = rng.uniform(-6.0, 6.0, (A, 3)) + np.array([0.0, 0.0, 2.0])
+    T = N + steps
+    vel = rng.normal(0.0, 0.6, (W, 1, 3))
+    truth = rng.uniform(-3.0, 3.0, (W, 1, 3)) + np.cumsum(np.broadcast_to(vel, (W, T, 3)) * 0.04 + rng.normal(0, 0.01, (W, T, 3)), axis=1)
+    aop_all = rng.integers(0, A, (W, T)).astype(np.int32)
+    d_all = (np.linalg.norm(truth - anchors[aop_all], axis=2) + rng.normal(0, 0.05, (W, T))).astype(np.float32)
+    e_all = np.where(rng.uniform(size=(W, T)) < 0.7, np.float32(0.055), np.float32(0.024)).astype(np.float32)
+    dt_all = rng.uniform(0.02, 0.06, (W, T))
+    pose = truth[:, :N] + rng.normal(0, 0.1, (W, N, 3))
+    d, e, dt, aop = d_all[:, :N].copy(), e_all[:, :N].copy(), dt_all[:, 1:N].copy(), aop_all[:, :N].copy()
+    topo_rows = chain_topology(N, N, np.arange(N))               # pose k reads row k of its window's anchors
+    fleet = ResidentFleet(_gpu_solver, N, anchors, W, v_max, cfg)
+    try:
+        fleet.load(pose, aop, d, e, dt)
+        assert np.array_equal(fleet.read(), pose)
+        with pytest.raises(Exception):
+            fleet.step(0, d_all[:, N], e_all[:, N], dt_all[:, N])   # loaded per robot: a fleet-wide anchor is refused
+        for s in range(steps):
+            k = N + s
+            pose_in = np.concatenate([pose[:, 1:], pose[:, -1:]], axis=1)
+            d = np.concatenate([d[:, 1:], d_all[:, k:k + 1]], axis=1)
+            e = np.concatenate([e[:, 1:], e_all[:, k:k + 1]], axis=1)
+            dt = np.concatenate([dt[:, 1:], dt_all[:, k:k + 1]], axis=1)
+            aop = np.concatenate([aop[:, 1:], aop_all[:, k:k + 1]], axis=1)
+            msgs = RangeMsgs(distance=d, distance_err=e, dt_pose=np.ascontiguousarray(dt), v_max=v_max)
+            ref = oracle.solve(topo_rows, Batch(pose_t=pose_in, anchors=np.ascontiguousarray(anchors[aop]), range_msgs=msgs), cfg)
+            for w in range(0, W, max(1, W // 5)):
+                one = oracle.solve(chain_topology(N, A, aop[w]),
+                                   Batch(pose_t=pose_in[w:w + 1], anchors=anchors, shared_anchors=True,
+                                         range_msgs=RangeMsgs(distance=d[w:w + 1], distance_err=e[w:w + 1],
+                                                              dt_pose=np.ascontiguousarray(dt[w:w + 1]), v_max=v_max)), cfg)
+                assert np.array_equal(one.pose_t[0], ref.pose_t[w]) and np.array_equal(one.chi2[0], ref.chi2[w])
+            newest, chi2, status = fleet.step(aop_all[:, k], d_all[:, k], e_all[:, k], dt_all[:, k])
+            assert _gpu_solver.last_path == 2                    # the straight-line CHAIN kernel
+            assert np.array_equal(newest, ref.pose_t[:, -1]), (s, np.abs(newest - ref.pose_t[:, -1]).max())
+            assert np.array_equal(chi2, ref.chi2) and np.array_equal(status, ref.status)
+            pose = ref.pose_t
+        assert np.array_equal(fleet.read(), pose)
+        bad = aop_all[:, -1].copy()
+        bad[W // 2] = A
+        with pytest.raises(Exception):
+            fleet.step(bad, d_all[:, -1], e_all[:, -1], dt_all[:, -1])   # one id out of range: nothing is queued
+        assert np.array_equal(fleet.read(), pose)
+        # a stream can be reloaded the other way
+        fleet.load(pose, list(np.arange(N) % A), d, e, dt)
+        with pytest.raises(Exception):
+            fleet.step(aop_all[:, -1], d_all[:, -1], e_all[:, -1], dt_all[:, -1])
+        fleet.step(0, d_all[:, -1], e_all[:, -1], dt_all[:, -1])
+    finally:
+        fleet.close()
+
+
 def test_resident_fleet_rejects_bad_arguments(_gpu_solver):
     cfg = Config(max_iterations=3)
     anchors = np.zeros((4, 3))

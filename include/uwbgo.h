@@ -156,6 +156,8 @@ typedef struct uwbgo_config {
 #define UWBGO_FLAG_CHOL_FAIL   1  /* some trial hit a non-positive pivot (trial rejected)          */
 #define UWBGO_FLAG_TERMINATED  2  /* LM returned Terminate (max trials reached or rho == 0)        */
 #define UWBGO_FLAG_NONFINITE   4  /* a trial produced a non-finite robust chi2                     */
+#define UWBGO_FLAG_REJECTED    8  /* uwbgo_stream only: the robot's message was refused by the     */
+                                  /* outlier gate, nothing was solved (localization.cpp:309-313)   */
 
 typedef struct uwbgo_result {
     double  *pose_t;       /* [W][N][3]                                   */
@@ -284,6 +286,15 @@ int  uwbgo_stream_load_robots(uwbgo_stream *s, const double *pose_t, const int32
 int  uwbgo_stream_step_robots(uwbgo_stream *s, const int32_t *anchor, const float *distance,
                               const float *distance_err, const double *dt, double *newest_pose, double *chi2,
                               int32_t *status);
+/* The outlier gate of addRangeEdge (localization.cpp:305-313; robot/distance_outlier, :78; the stream holds full
+ * windows, so the gate's "window has filled" condition is met): a message whose range differs from the distance
+ * between the robot's newest estimate and the anchor by more than distance_outlier is refused -- that robot's
+ * window stays as it is and nothing is solved for it, as in the reference; the step returns its unchanged newest
+ * pose, the chi2 of its last accepted message (zeros before the first) and status {0, 0, UWBGO_FLAG_REJECTED, 0}.
+ * The caller keeps the stamp of a robot's last ACCEPTED message for the next dt, as Robot::last_header() does.
+ * distance_outlier < 0 switches the gate off (the default).  Per-robot streams only (_load_robots): a refused
+ * message would desynchronise a fleet-wide anchor sequence, so _step answers UWBGO_E_INVALID while the gate is on. */
+int  uwbgo_stream_set_outlier_gate(uwbgo_stream *s, double distance_outlier);
 /* all estimates of the windows as the last step left them, [W][N][3] (host array) */
 int  uwbgo_stream_read(uwbgo_stream *s, double *pose_t);
 /* kernels launched / duration of the LM kernel of the last step (ms; needs uwbgo_set_profiling) come

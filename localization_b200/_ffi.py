@@ -104,6 +104,7 @@ SYMBOLS = {
     "uwbgo_stream_step": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), _pd, _pd, _pd, _pi]),
     "uwbgo_stream_load_robots": (C.c_int, [_vp, _pd, _pi, C.POINTER(C.c_float), C.POINTER(C.c_float), _pd]),
     "uwbgo_stream_step_robots": (C.c_int, [_vp, _pi, C.POINTER(C.c_float), C.POINTER(C.c_float), _pd, _pd, _pd, _pi]),
+    "uwbgo_stream_set_outlier_gate": (C.c_int, [_vp, C.c_double]),
     "uwbgo_stream_read": (C.c_int, [_vp, _pd]),
     "uwbgo_launch_count": (C.c_int64, [_vp]),
     "uwbgo_last_path": (C.c_int, [_vp]),

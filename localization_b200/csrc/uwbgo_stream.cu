@@ -26,7 +26,7 @@ stream_shift_kernel(int64_t W, int N, const double *__restrict__ res, double *__
                     float *__restrict__ d_new, float *__restrict__ e_new, double *__restrict__ dt_new,
                     const float *__restrict__ msg_d, const float *__restrict__ msg_e, const double *__restrict__ msg_dt,
                     const int32_t *__restrict__ a_old, int32_t *__restrict__ a_new, const int32_t *__restrict__ msg_a,
-                    const double *__restrict__ anchors, double *__restrict__ anch_w)
+                    const double *__restrict__ anchors, double *__restrict__ anch_w, const int32_t *__restrict__ rej)
 {
     /* one thread per (window, pose): pose i of the new window is pose i + 1 of the old one; the new vertex
      * starts at the estimate of the newest (robot.cpp: new_vertex copies the last estimate) */
@@ -34,6 +34,20 @@ stream_shift_kernel(int64_t W, int N, const double *__restrict__ res, double *__
     if (t >= W * N) return;
     const int64_t w = t / N;
     const int i = (int)(t - w * N);
+    if (rej && rej[w]) {
+        /* message refused by the outlier gate (localization.cpp:309-313 returns before touching the graph): the
+         * window stays as it is; stream_finish_kernel puts its estimates back after the batch solve */
+#pragma unroll
+        for (int k = 0; k < 3; ++k) in[t * 3 + k] = res[t * 3 + k];
+        d_new[t] = d_old[t];
+        e_new[t] = e_old[t];
+        if (i + 1 < N) dt_new[w * (N - 1) + i] = dt_old[w * (N - 1) + i];
+        const int32_t a = a_old[t];
+        a_new[t] = a;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) anch_w[t * 3 + k] = anchors[(size_t)a * 3 + k];
+        return;
+    }
     const int src = i + 1 < N ? i + 1 : N - 1;
 #pragma unroll
     for (int k = 0; k < 3; ++k) in[t * 3 + k] = res[(w * N + src) * 3 + k];
@@ -50,12 +64,45 @@ stream_shift_kernel(int64_t W, int N, const double *__restrict__ res, double *__
     }
 }
 
-__global__ void __launch_bounds__(256) stream_newest_kernel(int64_t W, int N, const double *__restrict__ res, double *__restrict__ newest)
+/* the outlier gate of Localization::addRangeEdge (localization.cpp:305-313): distance between the newest estimate
+ * of the robot and the anchor (Eigen's norm of a 3-vector: sqrt((x^2 + y^2) + z^2)) against the measured range
+ * (float32 on the wire, widened), refused when they differ by more than robot/distance_outlier */
+__global__ void __launch_bounds__(256)
+stream_gate_kernel(int64_t W, int N, const double *__restrict__ res, const double *__restrict__ anchors,
+                   const int32_t *__restrict__ msg_a, const float *__restrict__ msg_d, double outlier, int32_t *__restrict__ rej)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= W * 3) return;
-    const int64_t w = t / 3;
-    newest[t] = res[(w * N + (N - 1)) * 3 + (t - w * 3)];
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const double *p = res + (w * N + (N - 1)) * 3, *q = anchors + (size_t)msg_a[w] * 3;
+    const double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+    const double est = sqrt(dx * dx + dy * dy + dz * dz);
+    rej[w] = fabs(est - (double)msg_d[w]) > outlier ? 1 : 0;
+}
+
+/* after the solve: the newest pose of every robot; a robot whose message was refused gets its window back (the
+ * batch solve ran on it and is discarded: the reference does not call solve() for a refused message), the chi2 of
+ * its last accepted message and status = {0, 0, UWBGO_FLAG_REJECTED, 0} */
+__global__ void __launch_bounds__(256)
+stream_finish_kernel(int64_t W, int N, double *__restrict__ res, const double *__restrict__ in, double *__restrict__ newest,
+                     const int32_t *__restrict__ rej, double *__restrict__ chi2, double *__restrict__ chi2_prev,
+                     int32_t *__restrict__ status)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    if (rej) {
+        if (rej[w]) {
+            for (int i = 0; i < N * 3; ++i) res[w * N * 3 + i] = in[w * N * 3 + i];
+            for (int k = 0; k < UWBGO_CHI2_STRIDE; ++k) chi2[w * UWBGO_CHI2_STRIDE + k] = chi2_prev[w * UWBGO_CHI2_STRIDE + k];
+            status[w * UWBGO_STATUS_STRIDE + 0] = 0;
+            status[w * UWBGO_STATUS_STRIDE + 1] = 0;
+            status[w * UWBGO_STATUS_STRIDE + 2] = UWBGO_FLAG_REJECTED;
+            status[w * UWBGO_STATUS_STRIDE + 3] = 0;
+        } else {
+            for (int k = 0; k < UWBGO_CHI2_STRIDE; ++k) chi2_prev[w * UWBGO_CHI2_STRIDE + k] = chi2[w * UWBGO_CHI2_STRIDE + k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) newest[w * 3 + k] = res[(w * N + (N - 1)) * 3 + k];
 }
 
 }  // namespace
@@ -75,8 +122,11 @@ struct uwbgo_stream {
     /* per-robot anchor sequences (uwbgo_stream_load_robots / _step_robots): one more allocation, made on first use */
     char *dev_r = nullptr;
     int32_t *aid[2] = {nullptr, nullptr}, *msg_a = nullptr;
-    double *anch_w = nullptr;
+    double *anch_w = nullptr, *chi2_prev = nullptr;
+    int32_t *rej = nullptr;
     bool per_robot = false;
+    bool gate = false;      /* outlier gate of addRangeEdge (uwbgo_stream_set_outlier_gate) */
+    double outlier = 0.0;   /* robot/distance_outlier */
     int cur = 0;
     bool loaded = false;
     cudaStream_t st = nullptr;
@@ -186,7 +236,8 @@ int ensure_robot_arrays(uwbgo_stream *s)
     const size_t W = (size_t)s->W, N = (size_t)s->N;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += up256(bytes); return at; };
-    const size_t o_a0 = take(W * N * 4), o_a1 = take(W * N * 4), o_ma = take(W * 4), o_aw = take(W * N * 24);
+    const size_t o_a0 = take(W * N * 4), o_a1 = take(W * N * 4), o_ma = take(W * 4), o_aw = take(W * N * 24),
+                 o_rej = take(W * 4), o_cp = take(W * 32);
     if (cudaMalloc(&s->dev_r, o) != cudaSuccess) {
         cudaGetLastError();
         s->dev_r = nullptr;
@@ -196,6 +247,8 @@ int ensure_robot_arrays(uwbgo_stream *s)
     s->aid[1] = reinterpret_cast<int32_t *>(s->dev_r + o_a1);
     s->msg_a = reinterpret_cast<int32_t *>(s->dev_r + o_ma);
     s->anch_w = reinterpret_cast<double *>(s->dev_r + o_aw);
+    s->rej = reinterpret_cast<int32_t *>(s->dev_r + o_rej);
+    s->chi2_prev = reinterpret_cast<double *>(s->dev_r + o_cp);
     return 0;
 }
 
@@ -222,6 +275,7 @@ int load_impl(uwbgo_stream *s, bool per_robot, const double *pose_t, const int32
         s->anchor_of_pose.resize(N);
         for (size_t k = 0; k < N; ++k) s->anchor_of_pose[k] = (int32_t)k;
         SCU(cudaMemcpy(s->aid[0], anchor_of_pose, W * N * 4, cudaMemcpyHostToDevice));
+        SCU(cudaMemset(s->chi2_prev, 0, W * 32)); /* what a robot reports if its very first message is refused */
     } else {
         s->anchor_of_pose.assign(anchor_of_pose, anchor_of_pose + N);
     }
@@ -240,6 +294,8 @@ int step_impl(uwbgo_stream *s, int32_t anchor, const int32_t *anchor_w, const fl
     if (!s || !s->loaded || !distance || !distance_err || !dt) return UWBGO_E_INVALID;
     const bool per_robot = anchor_w != nullptr;
     if (per_robot != s->per_robot) return UWBGO_E_INVALID; /* the step must match the load */
+    if (s->gate && !per_robot) return UWBGO_E_INVALID;     /* a refused message desynchronises a fleet-wide anchor sequence */
+    const int32_t *rej = s->gate ? s->rej : nullptr;
     const size_t W = (size_t)s->W;
     const int N = s->N;
     if (per_robot) {
@@ -254,12 +310,17 @@ int step_impl(uwbgo_stream *s, int32_t anchor, const int32_t *anchor_w, const fl
     SCU(cudaMemcpyAsync(s->msg_e, distance_err, W * 4, cudaMemcpyHostToDevice, s->st));
     SCU(cudaMemcpyAsync(s->msg_dt, dt, W * 8, cudaMemcpyHostToDevice, s->st));
     if (per_robot) SCU(cudaMemcpyAsync(s->msg_a, anchor_w, W * 4, cudaMemcpyHostToDevice, s->st));
+    if (rej) {
+        stream_gate_kernel<<<(unsigned)((W + 255) / 256), 256, 0, s->st>>>((int64_t)W, N, s->res, s->anchors, s->msg_a, s->msg_d,
+                                                                          s->outlier, s->rej);
+        SCU(cudaGetLastError());
+    }
     const int nxt = s->cur ^ 1;
     const int64_t threads = (int64_t)W * N;
     stream_shift_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s->st>>>(
         (int64_t)W, N, s->res, s->in, s->d[s->cur], s->e[s->cur], s->dt[s->cur], s->d[nxt], s->e[nxt], s->dt[nxt], s->msg_d,
         s->msg_e, s->msg_dt, per_robot ? s->aid[s->cur] : nullptr, per_robot ? s->aid[nxt] : nullptr, s->msg_a, s->anchors,
-        s->anch_w);
+        s->anch_w, rej);
     SCU(cudaGetLastError());
     s->cur = nxt;
     if (!per_robot) {
@@ -297,7 +358,8 @@ int step_impl(uwbgo_stream *s, int32_t anchor, const int32_t *anchor_w, const fl
     r.status = s->status;
     int rc = uwbgo_solve_batch_device(s->ctx, &T, &b, &s->cfg, &r, s->st);
     if (rc) return rc;
-    stream_newest_kernel<<<(unsigned)((W * 3 + 255) / 256), 256, 0, s->st>>>((int64_t)W, N, s->res, s->newest);
+    stream_finish_kernel<<<(unsigned)((W + 255) / 256), 256, 0, s->st>>>((int64_t)W, N, s->res, s->in, s->newest, rej, s->chi2,
+                                                                        s->chi2_prev, s->status);
     SCU(cudaGetLastError());
     if (newest_pose) SCU(cudaMemcpyAsync(newest_pose, s->newest, W * 24, cudaMemcpyDeviceToHost, s->st));
     if (chi2) SCU(cudaMemcpyAsync(chi2, s->chi2, W * 32, cudaMemcpyDeviceToHost, s->st));
@@ -333,6 +395,14 @@ int uwbgo_stream_step_robots(uwbgo_stream *s, const int32_t *anchor, const float
 {
     if (!anchor) return UWBGO_E_INVALID;
     return step_impl(s, 0, anchor, distance, distance_err, dt, newest_pose, chi2, status);
+}
+
+int uwbgo_stream_set_outlier_gate(uwbgo_stream *s, double distance_outlier)
+{
+    if (!s || distance_outlier != distance_outlier) return UWBGO_E_INVALID;
+    s->gate = distance_outlier >= 0.0;
+    s->outlier = distance_outlier;
+    return 0;
 }
 
 int uwbgo_stream_read(uwbgo_stream *s, double *pose_t)

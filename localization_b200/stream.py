@@ -18,6 +18,9 @@ def _pd(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+FLAG_REJECTED = 8  # UWBGO_FLAG_REJECTED
+
+
 class ResidentFleet:
     def __init__(self, solver: Solver, n_poses: int, anchors: np.ndarray, n_windows: int, v_max: float, cfg: Config):
         self._lib = _ffi.load_library()
@@ -72,6 +75,11 @@ class ResidentFleet:
                                                            self._status.ctypes.data_as(C.POINTER(C.c_int32))),
                         "uwbgo_stream_step_robots")
         return self._newest, self._chi2, self._status
+
+    def set_outlier_gate(self, distance_outlier: float):
+        """robot/distance_outlier of addRangeEdge (localization.cpp:305-313); negative = off.  Per-robot fleets only:
+        a refused robot keeps its window and reports status[2] == FLAG_REJECTED"""
+        self._check(self._lib.uwbgo_stream_set_outlier_gate(self._h, float(distance_outlier)), "uwbgo_stream_set_outlier_gate")
 
     def read(self) -> np.ndarray:
         out = np.empty((self.W, self.N, 3))

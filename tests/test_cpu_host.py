@@ -44,6 +44,7 @@ def test_stream_entry_points_reject_null_arguments():
     assert lib.uwbgo_stream_step(None, 0, None, None, None, None, None, None) == -1
     assert lib.uwbgo_stream_load(None, None, None, None, None, None) == -1
     assert lib.uwbgo_stream_load_robots(None, None, None, None, None, None) == -1
+    assert lib.uwbgo_stream_set_outlier_gate(None, 1.0) == -1
     assert lib.uwbgo_stream_step_robots(None, None, None, None, None, None, None, None) == -1
     assert lib.uwbgo_stream_read(None, None) == -1
     lib.uwbgo_stream_destroy(None)

@@ -116,6 +116,74 @@ def test_resident_fleet_with_one_anchor_sequence_per_robot(_gpu_solver, W, N, A,
         fleet.close()
 
 
+@pytest.mark.parametrize("W,N,A,steps", [(300, 12, 4, 8), (64, 50, 8, 3)])
+def test_resident_fleet_outlier_gate(_gpu_solver, W, N, A, steps):
+    """the outlier gate of addRangeEdge (localization.cpp:305-313): a robot whose message is refused keeps its window
+    (estimates, message fields, anchor ids), nothing is solved for it; the others step as usual.  Host restatement
+    of the gate: Eigen's norm of the 3-vector, |estimate - float32 range| > distance_outlier."""
+    from localization_b200.stream import FLAG_REJECTED
+    rng = np.random.default_rng(500 + N)
+    v_max, outlier = 5.0, 1.0
+    cfg = Config(max_iterations=10)
+    anchors = rng.uniform(-6.0, 6.0, (A, 3)) + np.array([0.0, 0.0, 2.0])
+    T = N + steps
+    vel = rng.normal(0.0, 0.6, (W, 1, 3))
+    truth = rng.uniform(-3.0, 3.0, (W, 1, 3)) + np.cumsum(np.broadcast_to(vel, (W, T, 3)) * 0.04 + rng.normal(0, 0.01, (W, T, 3)), axis=1)
+    aop_all = rng.integers(0, A, (W, T)).astype(np.int32)
+    d_all = np.linalg.norm(truth - anchors[aop_all], axis=2) + rng.normal(0, 0.05, (W, T))
+    d_all[:, N:] += np.where(rng.uniform(size=(W, steps)) < 0.2, rng.choice([-2.5, 2.5, 0.9, 1.1], (W, steps)), 0.0)  # multipath spikes
+    d_all = d_all.astype(np.float32)
+    e_all = np.full((W, T), 0.055, np.float32)
+    dt_all = rng.uniform(0.02, 0.06, (W, T))
+    pose = truth[:, :N] + rng.normal(0, 0.1, (W, N, 3))
+    d, e, dt, aop = d_all[:, :N].copy(), e_all[:, :N].copy(), dt_all[:, 1:N].copy(), aop_all[:, :N].copy()
+    chi2_prev = np.zeros((W, 4))
+    topo_rows = chain_topology(N, N, np.arange(N))
+    fleet = ResidentFleet(_gpu_solver, N, anchors, W, v_max, cfg)
+    n_rejected = 0
+    try:
+        fleet.load(pose, aop, d, e, dt)
+        fleet.set_outlier_gate(outlier)
+        for s in range(steps):
+            k = N + s
+            diff = pose[:, -1] - anchors[aop_all[:, k]]
+            est = np.sqrt(diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1] + diff[:, 2] * diff[:, 2])
+            rej = np.abs(est - d_all[:, k].astype(np.float64)) > outlier
+            n_rejected += int(rej.sum())
+            acc = ~rej
+            pose_in = np.concatenate([pose[:, 1:], pose[:, -1:]], axis=1)
+            d_s = np.concatenate([d[:, 1:], d_all[:, k:k + 1]], axis=1)
+            e_s = np.concatenate([e[:, 1:], e_all[:, k:k + 1]], axis=1)
+            dt_s = np.concatenate([dt[:, 1:], dt_all[:, k:k + 1]], axis=1)
+            aop_s = np.concatenate([aop[:, 1:], aop_all[:, k:k + 1]], axis=1)
+            ref = oracle.solve(topo_rows, Batch(pose_t=pose_in, anchors=np.ascontiguousarray(anchors[aop_s]),
+                                                range_msgs=RangeMsgs(distance=d_s, distance_err=e_s,
+                                                                     dt_pose=np.ascontiguousarray(dt_s), v_max=v_max)), cfg)
+            m = acc[:, None]
+            pose = np.where(acc[:, None, None], ref.pose_t, pose)
+            d, e, dt, aop = np.where(m, d_s, d), np.where(m, e_s, e), np.where(m, dt_s, dt), np.where(m, aop_s, aop)
+            chi2_exp = np.where(m, ref.chi2, chi2_prev)
+            status_exp = np.where(m, ref.status, np.array([0, 0, FLAG_REJECTED, 0], np.int32)[None])
+            newest, chi2, status = fleet.step(aop_all[:, k], d_all[:, k], e_all[:, k], dt_all[:, k])
+            assert np.array_equal(status[:, 2] == FLAG_REJECTED, rej)
+            assert np.array_equal(newest, pose[:, -1]), (s, np.abs(newest - pose[:, -1]).max())
+            assert np.array_equal(chi2, chi2_exp) and np.array_equal(status, status_exp)
+            assert np.array_equal(fleet.read(), pose)
+            chi2_prev = chi2_exp
+        assert 0 < n_rejected < W * steps
+        # the gate off again: every message is taken
+        fleet.set_outlier_gate(-1.0)
+        _, _, status = fleet.step(aop_all[:, -1], d_all[:, -1] + np.float32(5.0), e_all[:, -1], dt_all[:, -1])
+        assert not (status[:, 2] & FLAG_REJECTED).any()
+        # fleet-wide anchor sequences cannot take the gate
+        fleet.load(pose, list(np.arange(N) % A), d, e, dt)
+        fleet.set_outlier_gate(outlier)
+        with pytest.raises(Exception):
+            fleet.step(0, d_all[:, -1], e_all[:, -1], dt_all[:, -1])
+    finally:
+        fleet.close()
+
+
 def test_resident_fleet_rejects_bad_arguments(_gpu_solver):
     cfg = Config(max_iterations=3)
     anchors = np.zeros((4, 3))

@@ -685,6 +685,9 @@ bool window_path_ok(const uwbgo_ctx *ctx, const TopoEntry &te, int64_t W, const 
     return W > 0 && W <= ctx->win_max && window_path_smem_bytes(te.gen, 1) <= WIN_SMEM_LIMIT;
 }
 
+#ifndef UWBGO_WIN_NO_T3
+#define UWBGO_WIN_NO_T3 0 /* A/B: 1 = translation-only windows take the 6x6 WINDOW kernel too */
+#endif
 /* WINDOW path on window-major arrays the device can address (device memory, or mapped pinned host
  * memory): ONE launch, no transposition */
 int run_window(uwbgo_ctx *ctx, const TopoEntry &te, const DevCfg &cfg, const uwbgo_batch *in, const double *d_ant,
@@ -708,6 +711,7 @@ int run_window(uwbgo_ctx *ctx, const TopoEntry &te, const DevCfg &cfg, const uwb
     io.o_cnt = out->oplus_count;
     io.o_chi2 = out->chi2;
     io.o_status = out->status;
+    io.t3 = (te.fast_ok && in->pose_R == nullptr && te.gen.simple_chain && !UWBGO_WIN_NO_T3) ? 1 : 0;
     const bool timed = ctx->profile;
     const int kslot = (int)(ctx->k_count % uwbgo_ctx::K_RING);
     if (timed) CU(cudaEventRecord(ctx->k0[kslot], st));

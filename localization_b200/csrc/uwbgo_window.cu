@@ -493,7 +493,13 @@ __constant__ unsigned char UP_C[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4,
  * lanes 0..6 the forward substitutions; G_i, z_i and L_i go to shared memory and the helper warp is
  * released (bar.sync with it: it is always waiting, its step is a tenth of this one).  Returns false
  * when a pivot was not positive. */
-template <class MATH, bool CHAIN>
+/* D = 6: the full blocks.  D = 3 (windows of range edges only, identity rotations, no lever arms, see
+ * WinIo::t3): the rotation rows and columns of every block are exact zeros -- S_i is diag(T_i, lam I), the
+ * rotation parts of L_i off its diagonal, of G_i, M_i, z_i, c_i and x_i are zeros -- and a zero operand leaves
+ * an fma chain's value as it is, so only the translation entries are formed: the same operations in the same
+ * order on them, half the dependent sqrt -> reciprocal pivots.  The rotation pivots are lam itself, which
+ * leaves their positivity test.  Same storage strides as D = 6. */
+template <class MATH, bool CHAIN, int D>
 UWBGO_DI bool factor_main(const WinSm &sm, double *cd, double *Lst, const int bar_id, const int N, const double lam,
                           const int lane, unsigned &bad
 #ifdef UWBGO_WIN_TIMING
@@ -507,31 +513,32 @@ UWBGO_DI bool factor_main(const WinSm &sm, double *cd, double *Lst, const int ba
 #else
 #define F_TICK(k)
 #endif
+    constexpr int NS = D * (D + 1) / 2;
     double *G = cd, *zv = cd + 78 * N, *Sst = cd + 90 * N;
-    /* lane roles of the assembly: 0..20 entry (r, c) of the lower triangle of S, 21..26 row of the rhs */
+    /* lane roles of the assembly: 0..NS-1 entry (r, c) of the lower triangle of S, NS..NS+D-1 row of the rhs */
     int er_ = 0, ec_ = 0;
-    if (lane < 21) {
+    if (lane < NS) {
         int kk = lane;
         while (kk > er_) {
             kk -= er_ + 1;
             ++er_;
         }
         ec_ = kk;
-    } else if (lane < 27) {
-        er_ = lane - 21;
+    } else if (lane < NS + D) {
+        er_ = lane - NS;
     }
     const int hd_idx = up_idx(6, ec_, er_);
     /* operand offsets of the child update inside the candidate block: row er_ of G_c times row ec_ of G_c
      * (S lanes) or times z_c (rhs lanes) */
-    const int a_off = 6 * er_, y_mul = lane < 21 ? 36 : 6, y_off = lane < 21 ? 6 * ec_ : 78 * N;
+    const int a_off = 6 * er_, y_mul = lane < NS ? 36 : 6, y_off = lane < NS ? 6 * ec_ : 78 * N;
     const int pad_off = sm.cand_stride - 42; /* 42 zeros at the end of the candidate block */
-    bool ok = true;
+    bool ok = D == 6 || lam > 0.0; /* D = 3: the rotation pivots are (0 + lam) - 0 */
     /* the assembly inputs of pose i are fetched during the potrf of pose i + 1 */
     auto fetch = [&](int i, double &v, int &qb, int &qe) {
         v = 0.0;
-        if (lane < 21)
+        if (lane < NS)
             v = sm.Hd[21 * i + hd_idx];
-        else if (lane < 27)
+        else if (lane < NS + D)
             v = sm.b[6 * i + er_];
         if (!CHAIN) {
             qb = sm.cbeg[i];
@@ -544,90 +551,100 @@ UWBGO_DI bool factor_main(const WinSm &sm, double *cd, double *Lst, const int ba
     for (int i = N - 1; i >= 0; --i) {
         double v = vn;
         const int qb = qbn, qe = qen;
-        if (lane < 21 && er_ == ec_) v = v + lam;
+        if (lane < NS && er_ == ec_) v = v + lam;
         if (CHAIN) {
             /* the one child is pose i + 1; the newest pose reads the zero block instead, so the body has no
              * branch: S(r, c) -= G[r,:] . G[c,:] and rhs(r) -= G[r,:] . z in one stream for all lanes */
             const int gch = i < N - 1 ? 36 * (i + 1) : pad_off, zch = i < N - 1 ? 78 * N + 6 * (i + 1) : pad_off + 36;
             const double2 *Ga = reinterpret_cast<const double2 *>(cd + gch + a_off);
-            const double2 *Yb = reinterpret_cast<const double2 *>(cd + (lane < 21 ? gch + 6 * ec_ : zch));
-            const double2 a0 = Ga[0], a1 = Ga[1], a2 = Ga[2], y0 = Yb[0], y1 = Yb[1], y2 = Yb[2];
+            const double2 *Yb = reinterpret_cast<const double2 *>(cd + (lane < NS ? gch + 6 * ec_ : zch));
+            const double2 a0 = Ga[0], a1 = Ga[1], y0 = Yb[0], y1 = Yb[1];
             v = fma(-a0.x, y0.x, v);
             v = fma(-a0.y, y0.y, v);
             v = fma(-a1.x, y1.x, v);
-            v = fma(-a1.y, y1.y, v);
-            v = fma(-a2.x, y2.x, v);
-            v = fma(-a2.y, y2.y, v);
+            if (D == 6) {
+                const double2 a2 = Ga[2], y2 = Yb[2];
+                v = fma(-a1.y, y1.y, v);
+                v = fma(-a2.x, y2.x, v);
+                v = fma(-a2.y, y2.y, v);
+            }
         } else {
 #pragma unroll 1
             for (int qq = qb; qq < qe; ++qq) { /* children in descending order */
                 const int ch = sm.chl[qq];
                 const double2 *Ga = reinterpret_cast<const double2 *>(cd + 36 * ch + a_off);
                 const double2 *Yb = reinterpret_cast<const double2 *>(cd + y_mul * ch + y_off);
-                const double2 a0 = Ga[0], a1 = Ga[1], a2 = Ga[2], y0 = Yb[0], y1 = Yb[1], y2 = Yb[2];
+                const double2 a0 = Ga[0], a1 = Ga[1], y0 = Yb[0], y1 = Yb[1];
                 v = fma(-a0.x, y0.x, v);
                 v = fma(-a0.y, y0.y, v);
                 v = fma(-a1.x, y1.x, v);
-                v = fma(-a1.y, y1.y, v);
-                v = fma(-a2.x, y2.x, v);
-                v = fma(-a2.y, y2.y, v);
+                if (D == 6) {
+                    const double2 a2 = Ga[2], y2 = Yb[2];
+                    v = fma(-a1.y, y1.y, v);
+                    v = fma(-a2.x, y2.x, v);
+                    v = fma(-a2.y, y2.y, v);
+                }
             }
         }
-        if (lane < 27) Sst[lane] = v;
+        if (lane < NS + D) Sst[lane] = v;
         __syncwarp();
         F_TICK(0);
         const bool has_parent = CHAIN ? true : sm.parent[i] >= 0; /* chains: G_0 of the root is zero and unread */
-        double L[21], rhs[6], fw[6];
+        double L[NS], rhs[D], fw[D];
         {
-            const double *src = lane < 6 ? sm.Ho + 36 * i + 6 * lane : Sst + 21;
+            const double *src = lane < D ? sm.Ho + 36 * i + 6 * lane : Sst + NS;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) rhs[k] = src[k];
+            for (int k = 0; k < D; ++k) rhs[k] = src[k];
         }
         fetch(i > 0 ? i - 1 : 0, vn, qbn, qen);
         /* potrf, every lane the whole block, S read where it is used; the diagonal slot keeps 1 / L_jj.
          * (loops over the full 0..5 range with the triangle as a predicate: constant trip counts, so
          * that they are all unrolled and L stays in registers) */
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
+        for (int j = 0; j < D; ++j) {
             double s = Sst[lo_idx(j, j)];
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
+            for (int k = 0; k < D; ++k)
                 if (k < j) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
             if (!(s > 0.0)) ok = false;
             const double inv = MATH::rsqrt_pivot(s, bad);
             L[lo_idx(j, j)] = inv;
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
+            for (int r = 0; r < D; ++r)
                 if (r > j) {
                     double t = Sst[lo_idx(r, j)];
 #pragma unroll
-                    for (int k = 0; k < 6; ++k)
+                    for (int k = 0; k < D; ++k)
                         if (k < j) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
                     L[lo_idx(r, j)] = t * inv;
                 }
         }
         F_TICK(1);
-        /* forward substitution: row of G_i (lanes 0..5) or z_i (lane 6) */
+        /* forward substitution: row of G_i (lanes 0..D-1) or z_i (lane D) */
 #pragma unroll
-        for (int cc = 0; cc < 6; ++cc) {
+        for (int cc = 0; cc < D; ++cc) {
             double s = rhs[cc];
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
+            for (int k = 0; k < D; ++k)
                 if (k < cc) s = fma(-fw[k], L[lo_idx(cc, k)], s);
             fw[cc] = s * L[lo_idx(cc, cc)];
         }
-        { /* G_i rows (lanes 0..5) and z_i (lane 6): one predicated stream of 16-byte stores */
-            double *dst = lane < 6 ? G + 36 * i + 6 * lane : zv + 6 * i;
-            if ((lane < 6 && has_parent) || lane == 6) {
+        { /* G_i rows (lanes 0..D-1) and z_i (lane D): one predicated stream of 16-byte stores */
+            double *dst = lane < D ? G + 36 * i + 6 * lane : zv + 6 * i;
+            if ((lane < D && has_parent) || lane == D) {
                 *reinterpret_cast<double2 *>(dst) = make_double2(fw[0], fw[1]);
-                *reinterpret_cast<double2 *>(dst + 2) = make_double2(fw[2], fw[3]);
-                *reinterpret_cast<double2 *>(dst + 4) = make_double2(fw[4], fw[5]);
+                if (D == 6) {
+                    *reinterpret_cast<double2 *>(dst + 2) = make_double2(fw[2], fw[3]);
+                    *reinterpret_cast<double2 *>(dst + 4) = make_double2(fw[D - 2], fw[D - 1]);
+                } else {
+                    dst[2] = fw[2];
+                }
             }
-            if (lane == 7) { /* L_i for the helper warp */
+            if (lane == D + 1) { /* L_i for the helper warp */
                 double *Lo = Lst + 22 * (i & 1);
 #pragma unroll
-                for (int k = 0; k < 20; k += 2) *reinterpret_cast<double2 *>(Lo + k) = make_double2(L[k], L[k + 1]);
-                Lo[20] = L[20];
+                for (int k = 0; k + 1 < NS; k += 2) *reinterpret_cast<double2 *>(Lo + k) = make_double2(L[k], L[k + 1]);
+                if (NS & 1) Lo[NS - 1] = L[NS - 1];
             }
         }
         F_TICK(2);
@@ -640,43 +657,46 @@ UWBGO_DI bool factor_main(const WinSm &sm, double *cd, double *Lst, const int ba
 /* F, helper warp of a candidate: behind every elimination step the backward substitutions
  * M_i = L_i^-T G_i^T (lanes 0..5, a column each) and c_i = L_i^-T z_i (lane 6), which nothing in the
  * elimination waits for */
-template <bool CHAIN>
+template <bool CHAIN, int D>
 UWBGO_DI void factor_helper(const WinSm &sm, double *cd, const double *Lst, const int bar_id, const int N, const int lane)
 {
     double *G = cd, *Mm = cd + 36 * N, *cv = cd + 72 * N, *zv = cd + 78 * N;
     for (int i = N - 1; i >= 0; --i) {
         bar_named(bar_id, 64);
         const bool has_parent = CHAIN ? true : sm.parent[i] >= 0;
-        if (lane < 7 && (lane == 6 || has_parent)) {
+        if (lane <= D && (lane == D || has_parent)) {
+            constexpr int NS = D * (D + 1) / 2;
             const double *Li = Lst + 22 * (i & 1);
-            const double *src = lane < 6 ? G + 36 * i + 6 * lane : zv + 6 * i;
-            double L[21], fw[6], bw[6];
+            const double *src = lane < D ? G + 36 * i + 6 * lane : zv + 6 * i;
+            double L[NS], fw[D], bw[D];
 #pragma unroll
-            for (int k = 0; k < 21; ++k) L[k] = Li[k];
+            for (int k = 0; k < NS; ++k) L[k] = Li[k];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) fw[k] = src[k];
+            for (int k = 0; k < D; ++k) fw[k] = src[k];
 #pragma unroll
-            for (int rr = 0; rr < 6; ++rr) {
-                const int r = 5 - rr;
+            for (int rr = 0; rr < D; ++rr) {
+                const int r = D - 1 - rr;
                 double s = fw[r];
 #pragma unroll
-                for (int k = 0; k < 6; ++k)
+                for (int k = 0; k < D; ++k)
                     if (k > r) s = fma(-L[lo_idx(k, r)], bw[k], s);
                 bw[r] = s * L[lo_idx(r, r)];
             }
-            if (lane < 6) {
+            if (lane < D) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) Mm[36 * i + 6 * k + lane] = bw[k];
+                for (int k = 0; k < D; ++k) Mm[36 * i + 6 * k + lane] = bw[k];
             } else {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) cv[6 * i + k] = bw[k];
+                for (int k = 0; k < D; ++k) cv[6 * i + k] = bw[k];
             }
         }
     }
     __syncwarp();
 }
 
-template <int KS, int NT>
+/* T3: windows whose 6x6 blocks are zero outside the translation entries (WinIo::t3 says when): the H phase, the
+ * elimination and the substitution run on the 3x3 blocks (factor_main), and the 6-D edge code is not compiled in */
+template <int KS, int NT, bool T3>
 __global__ void __launch_bounds__(NT, 1)
 lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ DevCfg cfg,
                  const __grid_constant__ WinIo io)
@@ -692,6 +712,8 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
     const int64_t w = blockIdx.x;
     const bool writer = true;
 #endif
+    constexpr bool NO6 = NO6D || T3; /* no EdgeSE3Prior / EdgeSE3 in a T3 window */
+    constexpr int DB = T3 ? 3 : 6;    /* block dimension of the linear solve */
     const int N = tp.N, NE = tp.E, mod = cfg.orth_mod;
     const WinCarve cv = win_carve(tp, KS);
     WinSm sm;
@@ -770,13 +792,13 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
     }
     __syncthreads();
 
-    const int n6 = NO6D ? 0 : tp.Es + tp.Ep;
+    const int n6 = NO6 ? 0 : tp.Es + tp.Ep;
     /* chi2 terms of the 6-D edges (se3 slots, then prior slots) resp. the range edges at the estimates X,
      * over the lanes of one warp */
     /* (branch-free arithmetic first; an item whose operands it flags is evaluated again with the IEEE
      * sequences: same bits, and the cold copy stays out of the instruction stream) */
     auto chi_six = [&](const double *X, double *echi) {
-        if (NO6D) return;
+        if (NO6) return;
         for (int k = lane; k < n6; k += 32) {
             const int e = sm.slot_edge[tp.Er + (k < tp.Es ? tp.Ep + k : k - tp.Es)];
             double chi, rob;
@@ -899,7 +921,7 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             WIN_TICK(0);
             /* ---- O: J^T Ow of the 6-D edges, one entry per thread; oplus counters advance ----- */
             {
-                const int nP = NO6D ? 0 : 36 * tp.Ep, nS = NO6D ? 0 : 72 * tp.Es;
+                const int nP = NO6 ? 0 : 36 * tp.Ep, nS = NO6 ? 0 : 72 * tp.Es;
                 for (int u = tid; u < nP + nS; u += NT) {
                     const double *J, *O;
                     double *out;
@@ -944,21 +966,23 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             __syncthreads();
             WIN_TICK(1);
             /* ---- H: every entry of the H record of every pose, owned by one thread -------------- */
-            for (int u = tid; u < 63 * N; u += NT) {
-                const int i = u / 63, k = u - 63 * i;
-                /* k < 21: H_ii upper (r, c); 21..56: H_{parent(i), i} (r, c); 57..62: b_i[r] */
+            constexpr int HN = T3 ? 18 : 63, HU = T3 ? 6 : 21, HO = DB * DB;
+            for (int u = tid; u < HN * N; u += NT) {
+                const int i = u / HN, k = u - HN * i;
+                /* k < HU: H_ii upper (r, c); then H_{parent(i), i} (r, c); the last DB: b_i[r].  (T3: the entries of
+                 * the translation blocks; the others are exact zeros nobody reads) */
                 int r, c, what;
-                if (k < 21) {
+                if (k < HU) {
                     what = 0;
-                    r = UP_R[k];
-                    c = UP_C[k];
-                } else if (k < 57) {
+                    r = T3 ? (k < 3 ? 0 : (k < 5 ? 1 : 2)) : UP_R[k];
+                    c = T3 ? (k < 3 ? k : (k < 5 ? k - 2 : 2)) : UP_C[k];
+                } else if (k < HU + HO) {
                     what = 1;
-                    r = (k - 21) / 6;
-                    c = (k - 21) - 6 * r;
+                    r = (k - HU) / DB;
+                    c = (k - HU) - DB * r;
                 } else {
                     what = 2;
-                    r = k - 57;
+                    r = k - HU - HO;
                     c = 0;
                 }
                 double acc = 0.0;
@@ -977,7 +1001,7 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                             acc = fma(J[r], rec[13], acc);
                         else if (role == 1)
                             acc = fma(rec[r] * Ow, rec[6 + c], acc);
-                    } else if (!NO6D) {
+                    } else if (!NO6) {
                         const bool se3 = er.kind == UWBGO_EDGE_SE3;
                         const double *rec = se3 ? sm.sJ + SJ * er.slot : sm.pJ + PJ * er.slot;
                         const double *J = rec + 36 * role;                          /* A or B           */
@@ -1003,9 +1027,9 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                     }
                 }
                 if (what == 0)
-                    sm.Hd[21 * i + k] = acc;
+                    sm.Hd[21 * i + up_idx(6, r, c)] = acc;
                 else if (what == 1)
-                    sm.Ho[36 * i + (k - 21)] = acc;
+                    sm.Ho[36 * i + 6 * r + c] = acc;
                 else
                     sm.b[6 * i + r] = acc;
             }
@@ -1017,7 +1041,7 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                     double maxdiag = 0.0;
                     for (int i = 0; i < N; ++i)
 #pragma unroll
-                        for (int r = 0; r < 6; ++r) {
+                        for (int r = 0; r < DB; ++r) { /* (T3: the rotation diagonal is +0) */
                             const double v = fabs(sm.Hd[21 * i + up_idx(6, r, r)]);
                             if (v > maxdiag) maxdiag = v;
                         }
@@ -1045,14 +1069,14 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
 #define F_TARG
 #endif
             const bool chain = tp.simple_chain != 0;
-            bool ok = chain ? factor_main<NbMath, true>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG)
-                            : factor_main<NbMath, false>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
+            bool ok = (T3 || chain) ? factor_main<NbMath, true, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG)
+                                    : factor_main<NbMath, false, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
             const bool redo = __any_sync(0xffffffffu, bad != 0);
             if (lane == 0) ctl.redo[warp] = redo ? 1 : 0;
             bar_named(1 + warp, 64);
             if (redo) { /* operands outside the branch-free range: the IEEE sequences */
                 bad = 0;
-                ok = factor_main<IeeeMath, false>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
+                ok = factor_main<IeeeMath, false, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
             }
             ok = __all_sync(0xffffffffu, ok);
             if (lane == 0) ctl.ok[warp] = ok ? 1 : 0;
@@ -1061,10 +1085,10 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
         } else if (warp >= KS && warp - KS < nk) { /* helper: backward substitutions, then x and computeScale() */
             const int k = warp - KS;
             double *cd = cand(k);
-            if (tp.simple_chain) factor_helper<true>(sm, cd, cand_L(k), 1 + k, N, lane);
-            else factor_helper<false>(sm, cd, cand_L(k), 1 + k, N, lane);
+            if (T3 || tp.simple_chain) factor_helper<true, DB>(sm, cd, cand_L(k), 1 + k, N, lane);
+            else factor_helper<false, DB>(sm, cd, cand_L(k), 1 + k, N, lane);
             bar_named(1 + k, 64);
-            if (ctl.redo[k]) factor_helper<false>(sm, cd, cand_L(k), 1 + k, N, lane);
+            if (ctl.redo[k]) factor_helper<false, DB>(sm, cd, cand_L(k), 1 + k, N, lane);
             bar_named(1 + k, 64);
             const bool ok = ctl.ok[k] != 0;
             const double lam = ctl.lam[k];
@@ -1078,15 +1102,19 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             {
                 const double *Mm = cd + 36 * N, *cvv = cd + 72 * N;
                 double *xv = cd + 84 * N;
-                const int r = lane < 6 ? lane : 0;
+                const int r = lane < DB ? lane : 0;
                 double scale = 0.0, tprev = 0.0;
                 double xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                double mrow[6], ci, bi;
+                double mrow[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, ci, bi;
                 int par;
                 auto fetch = [&](int i) {
                     const double2 *mp = reinterpret_cast<const double2 *>(Mm + 36 * i + 6 * r);
-                    const double2 m0 = mp[0], m1 = mp[1], m2 = mp[2];
-                    mrow[0] = m0.x; mrow[1] = m0.y; mrow[2] = m1.x; mrow[3] = m1.y; mrow[4] = m2.x; mrow[5] = m2.y;
+                    const double2 m0 = mp[0], m1 = mp[1];
+                    mrow[0] = m0.x; mrow[1] = m0.y; mrow[2] = m1.x;
+                    if (DB == 6) {
+                        const double2 m2 = mp[2];
+                        mrow[3] = m1.y; mrow[4] = m2.x; mrow[5] = m2.y;
+                    }
                     ci = cvv[6 * i + r];
                     bi = sm.b[6 * i + r];
                     par = sm.parent[i];
@@ -1101,16 +1129,17 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                         const double b_i = bi;
                         if (i > 0) {
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) x = fma(-mrow[j], xp[j], x);
+                            for (int j = 0; j < DB; ++j) x = fma(-mrow[j], xp[j], x);
                         }
                         fetch(i + 1 < N ? i + 1 : N - 1);
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j); /* pose i - 1 */
+                        for (int j = 0; j < DB; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j); /* pose i - 1 */
                         x = ok ? x : 0.0;
-                        if (lane < 6) xv[6 * i + lane] = x;
+                        if (lane < DB) xv[6 * i + lane] = x;
+                        else if (T3 && lane < 6) xv[6 * i + lane] = 0.0; /* the rotation increment: zero */
                         tprev = x * (lam * x + b_i);
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) xp[j] = __shfl_sync(0xffffffffu, x, j);
+                        for (int j = 0; j < DB; ++j) xp[j] = __shfl_sync(0xffffffffu, x, j);
                     }
                 } else {
 #pragma unroll 1
@@ -1121,24 +1150,25 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                         if (p_i >= 0 && p_i != i - 1) { /* forests: the parent is not the previous pose */
                             __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) xp[j] = xv[6 * p_i + j];
+                            for (int j = 0; j < DB; ++j) xp[j] = xv[6 * p_i + j];
                         }
                         if (p_i >= 0) {
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) x = fma(-mrow[j], xp[j], x);
+                            for (int j = 0; j < DB; ++j) x = fma(-mrow[j], xp[j], x);
                         }
                         fetch(i + 1 < N ? i + 1 : N - 1);
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j); /* pose i - 1 */
+                        for (int j = 0; j < DB; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j); /* pose i - 1 */
                         x = ok ? x : 0.0;
-                        if (lane < 6) xv[6 * i + lane] = x;
+                        if (lane < DB) xv[6 * i + lane] = x;
+                        else if (T3 && lane < 6) xv[6 * i + lane] = 0.0; /* the rotation increment: zero */
                         tprev = x * (lam * x + b_i);
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) xp[j] = __shfl_sync(0xffffffffu, x, j);
+                        for (int j = 0; j < DB; ++j) xp[j] = __shfl_sync(0xffffffffu, x, j);
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 6; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j);
+                for (int j = 0; j < DB; ++j) scale = scale + __shfl_sync(0xffffffffu, tprev, j);
                 if (lane == 0) ctl.scale[k] = scale;
             }
             __syncwarp();
@@ -1343,21 +1373,21 @@ size_t window_path_smem_bytes(const DevTopo &topo, int ks) { return sizeof(doubl
  * when every SM has several windows to work on anyway */
 int window_path_candidates(int64_t W) { return W <= 148 ? 4 : (W <= 296 ? 2 : 1); }
 
-template <int KS, int NT>
+template <int KS, int NT, bool T3>
 static cudaError_t launch_win(const DevTopo &topo, const DevCfg &cfg, const WinIo &io, int device, cudaStream_t st)
 {
     const size_t sm = window_path_smem_bytes(topo, KS);
     static size_t configured[64] = {0}; /* the attribute is per device */
     size_t &conf = configured[device & 63];
     if (sm > conf) {
-        cudaError_t e = cudaFuncSetAttribute(lm_window_kernel<KS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaError_t e = cudaFuncSetAttribute(lm_window_kernel<KS, NT, T3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         conf = sm;
     }
 #ifdef UWBGO_WIN_PAD
-    lm_window_kernel<KS, NT><<<(unsigned)(io.W < UWBGO_WIN_PAD ? UWBGO_WIN_PAD : io.W), NT, sm, st>>>(topo, cfg, io);
+    lm_window_kernel<KS, NT, T3><<<(unsigned)(io.W < UWBGO_WIN_PAD ? UWBGO_WIN_PAD : io.W), NT, sm, st>>>(topo, cfg, io);
 #else
-    lm_window_kernel<KS, NT><<<(unsigned)io.W, NT, sm, st>>>(topo, cfg, io);
+    lm_window_kernel<KS, NT, T3><<<(unsigned)io.W, NT, sm, st>>>(topo, cfg, io);
 #endif
     return cudaGetLastError();
 }
@@ -1366,9 +1396,14 @@ cudaError_t launch_solve_window(const DevTopo &topo, const DevCfg &cfg, const Wi
                                 cudaStream_t st)
 {
     if (io.W <= 0) return cudaSuccess;
-    if (ks >= 4) return launch_win<4, 256>(topo, cfg, io, device, st);
-    if (ks >= 2) return launch_win<2, 256>(topo, cfg, io, device, st);
-    return launch_win<1, 128>(topo, cfg, io, device, st);
+    if (io.t3) {
+        if (ks >= 4) return launch_win<4, 256, true>(topo, cfg, io, device, st);
+        if (ks >= 2) return launch_win<2, 256, true>(topo, cfg, io, device, st);
+        return launch_win<1, 128, true>(topo, cfg, io, device, st);
+    }
+    if (ks >= 4) return launch_win<4, 256, false>(topo, cfg, io, device, st);
+    if (ks >= 2) return launch_win<2, 256, false>(topo, cfg, io, device, st);
+    return launch_win<1, 128, false>(topo, cfg, io, device, st);
 }
 
 }  // namespace uwbgo

@@ -136,6 +136,9 @@ struct WinCtl {
     int ok[WIN_MAX_KS];
     int redo[WIN_MAX_KS]; /* the branch-free arithmetic flagged an operand: the chain runs again with IEEE sequences */
     double lam[WIN_MAX_KS], scale[WIN_MAX_KS];
+    /* per candidate, formed by lane 0 of its main warp before D: the two chi2 sums and the gain ratio */
+    double tplain[WIN_MAX_KS], tchi[WIN_MAX_KS], rho[WIN_MAX_KS];
+    double chi_cur; /* robust chi2 at the current estimate (thread 0's currentChi) */
 };
 
 UWBGO_DI void ld_pose(const double *p, Pose &X)
@@ -866,6 +869,7 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
     if (tid == 0) {
         chi_sum(cand_echi(0), plainCur, currentChi);
         stale = plainCur;
+        ctl.chi_cur = currentChi;
         ctl.go = cfg.max_iterations > 0;
         ctl.lin = 1;
         ctl.cur = 0;
@@ -1263,6 +1267,17 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
 #endif
         __syncthreads();
         WIN_TICK(4);
+        /* the ordered chi2 sums and the gain ratio of every candidate, side by side (the current chi2 is the same
+         * for all of them: an accepted candidate ends the round) */
+        if (lane == 0 && warp < nk) {
+            double tp_, tc_;
+            chi_sum(cand_echi(warp), tp_, tc_);
+            if (ctl.ok[warp] == 0) tc_ = DBL_MAX;
+            ctl.tplain[warp] = tp_;
+            ctl.tchi[warp] = tc_;
+            ctl.rho[warp] = (ctl.chi_cur - tc_) / (ctl.scale[warp] + 1e-3);
+        }
+        __syncthreads();
 
         /* ---- D: the trials of this round, consumed in order --------------------------------------------- */
         if (tid == 0) {
@@ -1272,12 +1287,9 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                 const int k = used;
                 const bool ok = ctl.ok[k] != 0;
                 if (!ok) flags |= UWBGO_FLAG_CHOL_FAIL;
-                double scale = ctl.scale[k], tplain, tempChi;
-                chi_sum(cand_echi(k), tplain, tempChi);
+                const double tplain = ctl.tplain[k], tempChi = ctl.tchi[k];
                 stale = tplain;
-                if (!ok) tempChi = DBL_MAX;
-                scale = scale + 1e-3;
-                rho = (currentChi - tempChi) / scale;
+                rho = ctl.rho[k];
                 const bool fin = isfinite(tempChi);
                 if (!fin) flags |= UWBGO_FLAG_NONFINITE;
                 ++used;
@@ -1319,6 +1331,7 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             ctl.cur = cur;
             ctl.adv = adv0 + used;
             ctl.first = 0;
+            ctl.chi_cur = currentChi;
             if (!done) publish_candidates();
             WIN_TICK(5);
         }

@@ -112,6 +112,8 @@ struct TopoEntry {
     DevTopo fast{};       /* edge table with carry slots (fast-eligible only)  */
     bool fast_ok = false;
     bool chain_ok = false; /* standard addRangeEdge chain: straight-line sweeps */
+    bool bd_ok = false;    /* range edges without lever arms + priors only on a simple chain (WINDOW path: */
+                           /* block-diagonal elimination when the priors' information allows)              */
     void *dmem = nullptr;
     uint64_t stamp = 0;
 };
@@ -253,7 +255,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     std::vector<EdgeRec> edges((size_t)E), fedges((size_t)E);
     std::vector<int32_t> calls((size_t)N, 0), carry((size_t)N, 0);
     std::vector<std::vector<PoseOp>> per_pose((size_t)N);
-    bool fast_ok = true;
+    bool fast_ok = true, bd_ok = true;
     for (int e = 0; e < E; ++e) {
         EdgeRec r{};
         r.kind = T->edge_kind[e];
@@ -277,6 +279,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
             per_pose[r.b].push_back(PoseOp{e, 1});
         EdgeRec f = r;
         if (r.kind > UWBGO_EDGE_RANGE_POSE || r.ant != 0 || r.ant_b != 0) fast_ok = false;
+        if (r.kind == UWBGO_EDGE_SE3 || (r.kind <= UWBGO_EDGE_RANGE_POSE && (r.ant != 0 || r.ant_b != 0))) bd_ok = false;
         if (r.kind == UWBGO_EDGE_RANGE_POSE) {
             int k = carry[r.a]++;
             if (k >= 2 || r.b != r.a + 1) fast_ok = false;
@@ -409,6 +412,7 @@ int compile_topology(uwbgo_ctx *ctx, const uwbgo_topology *T, TopoEntry **out)
     ent->chain_ok = chain_ok;
     ent->fast.edges = reinterpret_cast<const EdgeRec *>(d + o_fedges);
     ent->fast_ok = fast_ok;
+    ent->bd_ok = bd_ok && g.simple_chain;
     ent->key = std::move(key);
     ent->stamp = ++ctx->stamp;
     if (ctx->topos.size() >= 32) { /* evict the least recently used */
@@ -712,6 +716,7 @@ int run_window(uwbgo_ctx *ctx, const TopoEntry &te, const DevCfg &cfg, const uwb
     io.o_chi2 = out->chi2;
     io.o_status = out->status;
     io.t3 = (te.fast_ok && in->pose_R == nullptr && te.gen.simple_chain && !UWBGO_WIN_NO_T3) ? 1 : 0;
+    io.bd_ok = (te.bd_ok && !io.t3 && !UWBGO_WIN_NO_T3) ? 1 : 0;
     const bool timed = ctx->profile;
     const int kslot = (int)(ctx->k_count % uwbgo_ctx::K_RING);
     if (timed) CU(cudaEventRecord(ctx->k0[kslot], st));

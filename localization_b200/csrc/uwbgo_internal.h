@@ -138,6 +138,8 @@ struct WinIo {
     int32_t *o_cnt;
     double *o_chi2;
     int32_t *o_status;
+    int32_t bd_ok;                 /* 1: range edges without lever arms and EdgeSE3Prior edges only, a simple chain: */
+                                   /* the window is block-diagonal if its priors' information has no cross blocks    */
     int32_t t3;                    /* 1: range edges only, identity rotations, no lever arms, a simple chain: every */
                                    /* 6x6 block is zero outside its translation entries (3x3 solve, same bits)      */
 };

@@ -139,6 +139,7 @@ struct WinCtl {
     /* per candidate, formed by lane 0 of its main warp before D: the two chi2 sums and the gain ratio */
     double tplain[WIN_MAX_KS], tchi[WIN_MAX_KS], rho[WIN_MAX_KS];
     double chi_cur; /* robust chi2 at the current estimate (thread 0's currentChi) */
+    int bd;         /* block-diagonal window (factor_main_bd) */
 };
 
 UWBGO_DI void ld_pose(const double *p, Pose &X)
@@ -489,6 +490,11 @@ UWBGO_DI void bar_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"
 
 __constant__ unsigned char UP_R[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
 __constant__ unsigned char UP_C[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+/* the entries of a pose's H record that a block-diagonal window forms, as indices of the 63-entry enumeration
+ * (0..20 H_ii upper, 21..56 H_{parent,i} row-major, 57..62 b_i): both diagonal blocks, the translation block of
+ * H_{parent,i}, b_i */
+__constant__ unsigned char BD_ENTRY[27] = {0,  1,  2,  6,  7,  11, 15, 16, 17, 18, 19, 20, 21, 22,
+                                           23, 27, 28, 29, 33, 34, 35, 57, 58, 59, 60, 61, 62};
 
 /* F, main warp of a candidate: block elimination of H + lam I, newest pose first.  cd = the candidate's
  * block (G | M | c | z | x | S | echi), Lst = its two staging slots for L_i.  Per pose: the 21 + 6
@@ -697,6 +703,150 @@ UWBGO_DI void factor_helper(const WinSm &sm, double *cd, const double *Lst, cons
     __syncwarp();
 }
 
+/* BLOCK-DIAGONAL windows (WinCtl::bd): range edges without lever arms plus EdgeSE3Prior edges whose information
+ * has zero translation / rotation cross blocks (what Localization builds for IMU and lidar, localization.cpp:478-479,
+ * 515-518), on a simple chain.  Every H_ii is then diag(T_i, R_i) up to exact zeros and H_{i-1,i} has translation
+ * entries only: the translation blocks form the chain, the rotation blocks are not coupled at all.  The two halves
+ * of the main warp run the SAME 3x3 instruction stream side by side -- lanes 0..15 on T_i (with the child update),
+ * lanes 16..31 on R_i (whose child update reads the zero pad) -- so a pose costs three dependent pivots instead of
+ * six.  Entry by entry the operations are those of the 6x6 elimination minus terms with an exact-zero operand:
+ * the same bits.  M_i keeps zeros outside its translation block (zeroed once), so the substitution and
+ * computeScale() run unchanged on all six rows. */
+template <class MATH>
+UWBGO_DI bool factor_main_bd(const WinSm &sm, double *cd, double *Lst, const int bar_id, const int N, const double lam,
+                             const int lane, unsigned &bad)
+{
+    double *G = cd, *zv = cd + 78 * N, *Sst = cd + 90 * N;
+    const int hb = lane >> 4, l = lane & 15; /* half: 0 = translation block, 1 = rotation block */
+    int er_ = 0, ec_ = 0;
+    if (l < 6) {
+        int kk = l;
+        while (kk > er_) {
+            kk -= er_ + 1;
+            ++er_;
+        }
+        ec_ = kk;
+    } else if (l < 9) {
+        er_ = l - 6;
+    }
+    const int hd_idx = up_idx(6, ec_ + 3 * hb, er_ + 3 * hb);
+    const int pad_off = sm.cand_stride - 42;
+    double *Sh = Sst + 12 * hb;
+    bool ok = true;
+    auto fetch = [&](int i, double &v) {
+        v = 0.0;
+        if (l < 6)
+            v = sm.Hd[21 * i + hd_idx];
+        else if (l < 9)
+            v = sm.b[6 * i + er_ + 3 * hb];
+    };
+    double vn;
+    fetch(N - 1, vn);
+    for (int i = N - 1; i >= 0; --i) {
+        double v = vn;
+        if (l < 6 && er_ == ec_) v = v + lam;
+        {
+            /* child i + 1 (translation half); the rotation half and the newest pose read zeros */
+            const bool upd = hb == 0 && i < N - 1;
+            const int gch = upd ? 36 * (i + 1) : pad_off, zch = upd ? 78 * N + 6 * (i + 1) : pad_off + 36;
+            const double2 *Ga = reinterpret_cast<const double2 *>(cd + gch + 6 * er_);
+            const double2 *Yb = reinterpret_cast<const double2 *>(cd + (l < 6 ? gch + 6 * ec_ : zch));
+            const double2 a0 = Ga[0], a1 = Ga[1], y0 = Yb[0], y1 = Yb[1];
+            v = fma(-a0.x, y0.x, v);
+            v = fma(-a0.y, y0.y, v);
+            v = fma(-a1.x, y1.x, v);
+        }
+        if (l < 9) Sh[l] = v;
+        __syncwarp();
+        double L[6], rhs[3], fw[3];
+        {
+            const double *src = (hb == 0 && l < 3) ? sm.Ho + 36 * i + 6 * l : Sh + 6;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rhs[k] = src[k];
+        }
+        fetch(i > 0 ? i - 1 : 0, vn);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double s = Sh[lo_idx(j, j)];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < j) s = fma(-L[lo_idx(j, k)], L[lo_idx(j, k)], s);
+            if (!(s > 0.0)) ok = false;
+            const double inv = MATH::rsqrt_pivot(s, bad);
+            L[lo_idx(j, j)] = inv;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                if (r > j) {
+                    double t = Sh[lo_idx(r, j)];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (k < j) t = fma(-L[lo_idx(r, k)], L[lo_idx(j, k)], t);
+                    L[lo_idx(r, j)] = t * inv;
+                }
+        }
+        /* forward substitution: rows of G_i (translation half, lanes 0..2), z_i (lane 3 of either half) */
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            double s = rhs[cc];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < cc) s = fma(-fw[k], L[lo_idx(cc, k)], s);
+            fw[cc] = s * L[lo_idx(cc, cc)];
+        }
+        {
+            double *dst = l < 3 ? G + 36 * i + 6 * l : zv + 6 * i + 3 * hb;
+            if ((hb == 0 && l < 3) || l == 3) {
+                dst[0] = fw[0];
+                dst[1] = fw[1];
+                dst[2] = fw[2];
+            }
+            if (l == 4) { /* L_i of this half for the helper warp */
+                double *Lo = Lst + 22 * (i & 1) + 6 * hb;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) Lo[k] = L[k];
+            }
+        }
+        bar_named(bar_id, 64);
+    }
+    return ok;
+}
+
+/* helper warp: M_i = L_T^-T G_i^T (lanes 0..2, a column each), c_i = L^-T z_i of each half (lanes 3 and 19) */
+UWBGO_DI void factor_helper_bd(double *cd, const double *Lst, const int bar_id, const int N, const int lane)
+{
+    double *G = cd, *Mm = cd + 36 * N, *cv = cd + 72 * N, *zv = cd + 78 * N;
+    const int hb = lane >> 4, l = lane & 15;
+    for (int i = N - 1; i >= 0; --i) {
+        bar_named(bar_id, 64);
+        if ((hb == 0 && l < 3) || l == 3) {
+            const double *Li = Lst + 22 * (i & 1) + 6 * hb;
+            const double *src = l < 3 ? G + 36 * i + 6 * l : zv + 6 * i + 3 * hb;
+            double L[6], fw[3], bw[3];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) L[k] = Li[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) fw[k] = src[k];
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const int r = 2 - rr;
+                double s = fw[r];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k > r) s = fma(-L[lo_idx(k, r)], bw[k], s);
+                bw[r] = s * L[lo_idx(r, r)];
+            }
+            if (l < 3) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Mm[36 * i + 6 * k + l] = bw[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) cv[6 * i + 3 * hb + k] = bw[k];
+            }
+        }
+    }
+    __syncwarp();
+}
+
 /* T3: windows whose 6x6 blocks are zero outside the translation entries (WinIo::t3 says when): the H phase, the
  * elimination and the substitution run on the 3x3 blocks (factor_main), and the 6-D edge code is not compiled in */
 template <int KS, int NT, bool T3>
@@ -794,6 +944,22 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
         st_pose((pr ? sm.pZi : sm.sZi) + 12 * s, Zinv);
     }
     __syncthreads();
+    /* block-diagonal window?  The structure (io.bd_ok: range edges without lever arms and priors only, a simple
+     * chain) is the host's; the data condition is that no prior's information couples translation and rotation */
+    bool bd = false;
+    if (!T3 && io.bd_ok) { /* (uniform over the CTA) */
+        int clean = 1;
+        for (int k = tid; k < tp.Ep * 18; k += NT) {
+            const int s = k / 18, j = k - 18 * s, r = (j / 3) % 3, c = j % 3;
+            const double v = sm.pI[36 * s + (j < 9 ? 6 * r + 3 + c : 6 * (3 + r) + c)];
+            if (!(v == 0.0)) clean = 0;
+        }
+        bd = __syncthreads_and(clean) != 0;
+        if (bd) { /* M keeps zeros outside its translation block: only that block is ever written */
+            for (int k = tid; k < KS * 36 * N; k += NT) sm.cand[(k / (36 * N)) * sm.cand_stride + 36 * N + k % (36 * N)] = 0.0;
+            __syncthreads();
+        }
+    }
 
     const int n6 = NO6 ? 0 : tp.Es + tp.Ep;
     /* chi2 terms of the 6-D edges (se3 slots, then prior slots) resp. the range edges at the estimates X,
@@ -971,8 +1137,12 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             WIN_TICK(1);
             /* ---- H: every entry of the H record of every pose, owned by one thread -------------- */
             constexpr int HN = T3 ? 18 : 63, HU = T3 ? 6 : 21, HO = DB * DB;
-            for (int u = tid; u < HN * N; u += NT) {
-                const int i = u / HN, k = u - HN * i;
+            /* block-diagonal windows: 12 + 9 + 6 of the 63 entries per pose (the others are exact zeros nobody reads) */
+            const int hn = bd ? 27 : HN;
+            for (int u = tid; u < hn * N; u += NT) {
+                const int i = u / hn;
+                int k = u - hn * i;
+                if (bd) k = BD_ENTRY[k];
                 /* k < HU: H_ii upper (r, c); then H_{parent(i), i} (r, c); the last DB: b_i[r].  (T3: the entries of
                  * the translation blocks; the others are exact zeros nobody reads) */
                 int r, c, what;
@@ -1073,14 +1243,21 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
 #define F_TARG
 #endif
             const bool chain = tp.simple_chain != 0;
-            bool ok = (T3 || chain) ? factor_main<NbMath, true, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG)
-                                    : factor_main<NbMath, false, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
+            bool ok;
+            if (!T3 && bd)
+                ok = factor_main_bd<NbMath>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad);
+            else
+                ok = (T3 || chain) ? factor_main<NbMath, true, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG)
+                                   : factor_main<NbMath, false, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
             const bool redo = __any_sync(0xffffffffu, bad != 0);
             if (lane == 0) ctl.redo[warp] = redo ? 1 : 0;
             bar_named(1 + warp, 64);
             if (redo) { /* operands outside the branch-free range: the IEEE sequences */
                 bad = 0;
-                ok = factor_main<IeeeMath, false, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
+                if (!T3 && bd)
+                    ok = factor_main_bd<IeeeMath>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad);
+                else
+                    ok = factor_main<IeeeMath, false, DB>(sm, cd, cand_L(warp), 1 + warp, N, lam, lane, bad F_TARG);
             }
             ok = __all_sync(0xffffffffu, ok);
             if (lane == 0) ctl.ok[warp] = ok ? 1 : 0;
@@ -1089,10 +1266,14 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
         } else if (warp >= KS && warp - KS < nk) { /* helper: backward substitutions, then x and computeScale() */
             const int k = warp - KS;
             double *cd = cand(k);
-            if (T3 || tp.simple_chain) factor_helper<true, DB>(sm, cd, cand_L(k), 1 + k, N, lane);
+            if (!T3 && bd) factor_helper_bd(cd, cand_L(k), 1 + k, N, lane);
+            else if (T3 || tp.simple_chain) factor_helper<true, DB>(sm, cd, cand_L(k), 1 + k, N, lane);
             else factor_helper<false, DB>(sm, cd, cand_L(k), 1 + k, N, lane);
             bar_named(1 + k, 64);
-            if (ctl.redo[k]) factor_helper<false, DB>(sm, cd, cand_L(k), 1 + k, N, lane);
+            if (ctl.redo[k]) {
+                if (!T3 && bd) factor_helper_bd(cd, cand_L(k), 1 + k, N, lane);
+                else factor_helper<false, DB>(sm, cd, cand_L(k), 1 + k, N, lane);
+            }
             bar_named(1 + k, 64);
             const bool ok = ctl.ok[k] != 0;
             const double lam = ctl.lam[k];

@@ -119,6 +119,34 @@ def test_uwb_imu_c2_shape(solver):
     assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
 
 
+def test_block_diagonal_windows(solver):
+    """WINDOW path, block-diagonal elimination (uwbgo_window.cu factor_main_bd): range edges without lever arms plus
+    priors whose information has no translation / rotation cross terms -- IMU rotation priors (localization.cpp:515-518)
+    and lidar z priors (:478-479) -- solve on the 3x3 diagonal blocks.  A window whose prior information DOES couple
+    the two (one symmetric cross term), or holds a -0.0 there, or a NaN measurement, shares the batch: the kernel decides per
+    window, every window gives the oracle's bits."""
+    cfg = Config(max_iterations=10)
+    for lidar, N in ((False, 12), (True, 9)):
+        topo, batch, _ = synthetic.uwb_imu_lidar(48, N, 4, v_max=3.0, antennas=0, lidar=lidar, seed=21 + N)
+        info = batch.prior_info.reshape(48, -1, 6, 6)
+        info[3, 2, 1, 4] = info[3, 2, 4, 1] = 0.37       # couples y translation and pitch: the 6x6 blocks
+        info[5, :, 0, 3] = -0.0                          # a negative zero is a zero
+        info[7, 1, 2, 5] = info[7, 1, 5, 2] = 1e-300     # tiny, but not zero
+        assert_parity(solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg))
+        batch.prior_Z.reshape(48, -1, 12)[9, 0, 10] = np.nan   # a NaN measurement reaches b, not H: the pivots stay positive
+        info[11, 0, 3, 3] = np.nan                              # a NaN on the diagonal: no pivot
+        info[13, 1, 0, 4] = np.nan                              # a NaN in a cross block: not block-diagonal
+        got, ref = solver.solve(topo, batch, cfg), oracle.solve(topo, batch, cfg)
+        ok = np.setdiff1d(np.arange(48), [9, 11, 13])
+        assert np.array_equal(got.status, ref.status)
+        assert np.array_equal(got.pose_t[ok], ref.pose_t[ok]) and np.array_equal(got.pose_R[ok], ref.pose_R[ok])
+        assert np.array_equal(got.chi2[ok], ref.chi2[ok])
+        for w in (9, 11, 13):
+            assert np.array_equal(got.pose_t[w], ref.pose_t[w], equal_nan=True)
+            assert np.array_equal(got.pose_R[w], ref.pose_R[w], equal_nan=True)
+            assert np.array_equal(got.chi2[w], ref.chi2[w], equal_nan=True)
+
+
 def test_uwb_twist(solver):
     topo, batch, _ = synthetic.uwb_twist(128, 15, 8)
     cfg = Config(max_iterations=12)

@@ -195,7 +195,7 @@ int  uwbgo_set_pipeline(uwbgo_ctx *ctx, int64_t windows_per_chunk, int n_lanes);
 /* Small batches -- the reference's own call pattern is ONE window per range message
  * (localization.cpp:371-375) -- take the WINDOW path: one CTA per window, the window's state in
  * shared memory, the arrays of uwbgo_batch read in place, one kernel launch per call.  Batches of up
- * to `max_windows` windows go that way (default 296; 0 switches the path off, a negative value
+ * to `max_windows` windows go that way (default 592; 0 switches the path off, a negative value
  * restores the default); larger ones, and windows whose state does not fit the shared memory of
  * one SM, take the tile kernels.  Results are the same bits either way. */
 int  uwbgo_set_window_path(uwbgo_ctx *ctx, int64_t max_windows);

@@ -100,9 +100,10 @@ struct PinBuf {
     }
 };
 
-/* largest batch the WINDOW path takes by default: about two CTAs per SM; beyond that the tile kernels
- * (lane = window) have enough windows to fill their warps */
-constexpr int64_t WIN_MAX_DEFAULT = 296;
+/* largest batch the WINDOW path takes by default: four CTAs per SM; beyond that the tile kernels
+ * (lane = window) have enough windows to fill their warps (scripts/window_crossover.py: ahead at 592 windows and
+ * behind at 888 on every window shape, profiles/r02_window_crossover.txt) */
+constexpr int64_t WIN_MAX_DEFAULT = 592;
 constexpr size_t WIN_SMEM_LIMIT = 227 * 1024 - 256;
 
 /* a compiled topology, resident on the device */
@@ -1120,6 +1121,29 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         for (int k = 0; k < n_lanes; ++k) cudaStreamSynchronize(ctx->lane[k].st);
         mark(ctx->lane[0].st);
     }
+    /* Results bound for PAGEABLE host memory (a std::vector of the caller's; uwbgo_host_alloc gives page-locked
+     * arrays): such a copy blocks the calling thread until it is done, i.e. until the chunk's kernel has finished,
+     * so issued inside the loop it would keep the next chunk from even being launched and the chunks would run one
+     * after the other (148 UWB-only windows of 50 poses: 9.1 ms instead of 2.0 ms).  While every chunk has a lane of
+     * its own, those copies are issued after the loop, once all chunks are in flight */
+    struct D2HJob {
+        void *dst;
+        const void *src;
+        size_t bytes;
+        cudaStream_t st;
+    };
+    std::vector<D2HJob> deferred;
+    bool defer = false;
+    if (!trace && (W + chunk - 1) / chunk <= n_lanes) {
+        cudaPointerAttributes pa{};
+        const void *probe = linearize ? static_cast<const void *>(H_diag) : static_cast<const void *>(out->pose_t);
+        if (cudaPointerGetAttributes(&pa, probe) != cudaSuccess) {
+            cudaGetLastError();
+            defer = true;
+        } else {
+            defer = pa.type == cudaMemoryTypeUnregistered;
+        }
+    }
     ctx->batch_windows = W; /* the chunks run concurrently: kernels choose their shape by the whole batch */
     for (int64_t w0 = 0; w0 < W; w0 += chunk, ++c) {
         Lane &ln = ctx->lane[c % n_lanes];
@@ -1140,6 +1164,10 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         };
         auto d2h = [&](void *dst, size_t off, size_t per_window) -> cudaError_t {
             if (!dst) return cudaSuccess;
+            if (defer) {
+                deferred.push_back(D2HJob{static_cast<char *>(dst) + (size_t)w0 * per_window, sb + off, (size_t)wc * per_window, st});
+                return cudaSuccess;
+            }
             return cudaMemcpyAsync(static_cast<char *>(dst) + (size_t)w0 * per_window, sb + off,
                                    (size_t)wc * per_window, cudaMemcpyDeviceToHost, st);
         };
@@ -1223,6 +1251,14 @@ static int host_pipeline(uwbgo_ctx *ctx, const uwbgo_topology *topo, const uwbgo
         }
     }
     ctx->batch_windows = 0;
+    if (!first_err)
+        for (const D2HJob &j : deferred) {
+            cudaError_t e = cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, j.st);
+            if (e != cudaSuccess) {
+                first_err = fail_cuda(e, "cudaMemcpyAsync (results)");
+                break;
+            }
+        }
     for (int k = 0; k < n_lanes; ++k) {
         cudaError_t e = cudaStreamSynchronize(ctx->lane[k].st);
         if (e != cudaSuccess && !first_err) first_err = fail_cuda(e, "cudaStreamSynchronize");

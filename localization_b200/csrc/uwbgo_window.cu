@@ -957,6 +957,8 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
         bd = __syncthreads_and(clean) != 0;
         if (bd) { /* M keeps zeros outside its translation block: only that block is ever written */
             for (int k = tid; k < KS * 36 * N; k += NT) sm.cand[(k / (36 * N)) * sm.cand_stride + 36 * N + k % (36 * N)] = 0.0;
+            /* rotation columns of the range Jacobians: zeros, never recomputed (J phase) */
+            for (int k = tid; k < 6 * tp.Er; k += NT) sm.rJ[RJ * (k / 6) + (k % 6 < 3 ? 3 + k % 6 : 6 + k % 6)] = 0.0;
             __syncthreads();
         }
     }
@@ -1079,8 +1081,13 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                     if (bad) lin_range_weights<IeeeMath>(sm, X, er, ck, bad);
                 }
                 const int base2 = (base1 + ((tp.Er + 31) & ~31)) % NT;
-                for (int u = (tid - base2 + NT) % NT; u < 12 * tp.Er; u += NT) {
-                    const int k = u / 12, j = u - 12 * k;
+                /* translation-only and block-diagonal windows: the rotation columns of a range edge (no lever arms)
+                 * are (e - e) / 2 delta = +0 -- the perturbed point IS the point -- and they are the longest items
+                 * of the phase.  T3 never reads them; block-diagonal windows hold zeros there, written once */
+                const bool tcols = T3 || bd;
+                const int per = tcols ? 6 : 12;
+                for (int u = (tid - base2 + NT) % NT; u < per * tp.Er; u += NT) {
+                    const int k = u / per, jj = u - per * k, j = (tcols && jj >= 3) ? jj + 3 : jj;
                     const EdgeRec er = sm.edges[sm.slot_edge[k]];
                     unsigned bad = 0;
                     lin_range_col<WMJ>(sm, X, er, j, adv, mod, delta, scalar, bad);

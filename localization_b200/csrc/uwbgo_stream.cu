@@ -64,6 +64,36 @@ stream_shift_kernel(int64_t W, int N, const double *__restrict__ res, double *__
     }
 }
 
+/* Small fleets: the edge parameters window-major, in the expanded form of the ABI (range_d / range_info [W][2N-1],
+ * slots in insertion order: anchor edge of pose 0, then per pose k its anchor edge and the trajectory edge
+ * (k-1, k)), so that the solve can take the WINDOW kernels (one CTA per robot).  The arithmetic of
+ * Localization::addRangeEdge / create_range_edge as uwbgo.h states it for uwbgo_range_msgs: cov = err * err resp.
+ * ((v_max dt) / 3)^2, information = 1 / cov, all in FP64 after the exact widening of the float32 fields */
+__global__ void __launch_bounds__(256)
+stream_expand_kernel(int64_t W, int N, const float *__restrict__ d, const float *__restrict__ e, const double *__restrict__ dt,
+                     double v_max, double *__restrict__ rd, double *__restrict__ ri)
+{
+    const int Er = 2 * N - 1;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W * Er) return;
+    const int64_t w = t / Er;
+    const int s = (int)(t - w * Er);
+    double meas, cov;
+    if (s == 0 || (s & 1)) { /* anchor edge of pose k */
+        const int k = (s + 1) >> 1;
+        const double err = (double)e[w * N + k];
+        meas = (double)d[w * N + k];
+        cov = err * err;
+    } else { /* trajectory edge (k - 1, k) */
+        const int k = s >> 1;
+        const double x = (v_max * dt[w * (N - 1) + (k - 1)]) / 3.0;
+        meas = 0.0;
+        cov = x * x;
+    }
+    rd[t] = meas;
+    ri[t] = 1.0 / cov;
+}
+
 /* the outlier gate of Localization::addRangeEdge (localization.cpp:305-313): distance between the newest estimate
  * of the robot and the anchor (Eigen's norm of a 3-vector: sqrt((x^2 + y^2) + z^2)) against the measured range
  * (float32 on the wire, widened), refused when they differ by more than robot/distance_outlier */
@@ -122,7 +152,7 @@ struct uwbgo_stream {
     /* per-robot anchor sequences (uwbgo_stream_load_robots / _step_robots): one more allocation, made on first use */
     char *dev_r = nullptr;
     int32_t *aid[2] = {nullptr, nullptr}, *msg_a = nullptr;
-    double *anch_w = nullptr, *chi2_prev = nullptr;
+    double *anch_w = nullptr, *chi2_prev = nullptr, *rd = nullptr, *ri = nullptr; /* rd / ri: small fleets only */
     int32_t *rej = nullptr;
     bool per_robot = false;
     bool gate = false;      /* outlier gate of addRangeEdge (uwbgo_stream_set_outlier_gate) */
@@ -144,6 +174,10 @@ namespace {
     } while (0)
 
 size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+/* per-robot fleets of up to this many robots hand the solve the expanded window-major form, which the WINDOW
+ * kernels read (the library's default batch limit of that path, uwbgo_set_window_path) */
+constexpr int64_t SMALL_FLEET = 592;
 
 void build_topology(uwbgo_stream *s)
 {
@@ -238,6 +272,8 @@ int ensure_robot_arrays(uwbgo_stream *s)
     auto take = [&](size_t bytes) { size_t at = o; o += up256(bytes); return at; };
     const size_t o_a0 = take(W * N * 4), o_a1 = take(W * N * 4), o_ma = take(W * 4), o_aw = take(W * N * 24),
                  o_rej = take(W * 4), o_cp = take(W * 32);
+    const bool small = (int64_t)W <= SMALL_FLEET;
+    const size_t o_rd = take(small ? W * (2 * N - 1) * 8 : 0), o_ri = take(small ? W * (2 * N - 1) * 8 : 0);
     if (cudaMalloc(&s->dev_r, o) != cudaSuccess) {
         cudaGetLastError();
         s->dev_r = nullptr;
@@ -249,6 +285,10 @@ int ensure_robot_arrays(uwbgo_stream *s)
     s->anch_w = reinterpret_cast<double *>(s->dev_r + o_aw);
     s->rej = reinterpret_cast<int32_t *>(s->dev_r + o_rej);
     s->chi2_prev = reinterpret_cast<double *>(s->dev_r + o_cp);
+    if (small) {
+        s->rd = reinterpret_cast<double *>(s->dev_r + o_rd);
+        s->ri = reinterpret_cast<double *>(s->dev_r + o_ri);
+    }
     return 0;
 }
 
@@ -352,6 +392,15 @@ int step_impl(uwbgo_stream *s, int32_t anchor, const int32_t *anchor_w, const fl
     b.anchors = per_robot ? s->anch_w : s->anchors;
     b.range_msgs = &m;
     b.shared = per_robot ? 0 : UWBGO_SHARED_ANCHORS;
+    if (per_robot && s->rd) { /* a small fleet: one CTA per robot (uwbgo_window.cu) if the context's limit allows */
+        const int64_t n = (int64_t)W * (2 * N - 1);
+        stream_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s->st>>>((int64_t)W, N, s->d[nxt], s->e[nxt], s->dt[nxt], s->v_max,
+                                                                            s->rd, s->ri);
+        SCU(cudaGetLastError());
+        b.range_msgs = nullptr;
+        b.range_d = s->rd;
+        b.range_info = s->ri;
+    }
     uwbgo_result r{};
     r.pose_t = s->res;
     r.chi2 = s->chi2;

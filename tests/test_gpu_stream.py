@@ -55,12 +55,16 @@ def test_resident_fleet_matches_shifted_windows(_gpu_solver, W, N, A, steps):
         fleet.close()
 
 
-@pytest.mark.parametrize("W,N,A,steps", [(200, 12, 4, 6), (33, 5, 3, 5), (1000, 50, 8, 2)])
-def test_resident_fleet_with_one_anchor_sequence_per_robot(_gpu_solver, W, N, A, steps):
+@pytest.mark.parametrize("W,N,A,steps,window", [(200, 12, 4, 6, True), (200, 12, 4, 3, False), (33, 5, 3, 5, True),
+                                                (1000, 50, 8, 2, True)])
+def test_resident_fleet_with_one_anchor_sequence_per_robot(_gpu_solver, W, N, A, steps, window):
     """_load_robots / _step_robots: every robot ranges its own anchor in a step (UwbRange::responder_id,
     localization.cpp:305-306,331).  The oracle solves each robot's window with the anchor ids of ITS edges: all
     windows at once through window-private anchor rows, and a sample of them one by one on the topology the
-    reference would hold (anchor ids in the edge list, one shared constellation) -- the same bits either way."""
+    reference would hold (anchor ids in the edge list, one shared constellation) -- the same bits either way.
+    Fleets of up to 592 robots hand the solve the expanded window-major form and take the WINDOW kernels (one CTA
+    per robot) unless that path is switched off; larger ones the tile kernels on the message fields."""
+    _gpu_solver.set_window_path(-1 if window else 0)
     rng = np.random.default_rng(300 + N)
     v_max = 5.0
     cfg = Config(max_iterations=10)
@@ -97,7 +101,7 @@ def test_resident_fleet_with_one_anchor_sequence_per_robot(_gpu_solver, W, N, A,
                                                               dt_pose=np.ascontiguousarray(dt[w:w + 1]), v_max=v_max)), cfg)
                 assert np.array_equal(one.pose_t[0], ref.pose_t[w]) and np.array_equal(one.chi2[0], ref.chi2[w])
             newest, chi2, status = fleet.step(aop_all[:, k], d_all[:, k], e_all[:, k], dt_all[:, k])
-            assert _gpu_solver.last_path == 2                    # the straight-line CHAIN kernel
+            assert _gpu_solver.last_path == (3 if window and W <= 592 else 2)   # WINDOW kernels / straight-line CHAIN kernel
             assert np.array_equal(newest, ref.pose_t[:, -1]), (s, np.abs(newest - ref.pose_t[:, -1]).max())
             assert np.array_equal(chi2, ref.chi2) and np.array_equal(status, ref.status)
             pose = ref.pose_t
@@ -114,6 +118,7 @@ def test_resident_fleet_with_one_anchor_sequence_per_robot(_gpu_solver, W, N, A,
         fleet.step(0, d_all[:, -1], e_all[:, -1], dt_all[:, -1])
     finally:
         fleet.close()
+        _gpu_solver.set_window_path(-1)
 
 
 @pytest.mark.parametrize("W,N,A,steps", [(300, 12, 4, 8), (64, 50, 8, 3)])

@@ -261,7 +261,8 @@ int uwbgo_factor_solve_batch_device(uwbgo_ctx *ctx, int32_t n_poses, int64_t n_w
  * range the same anchor in a step (one TDMA slot per anchor: _load / _step) or every robot has its own
  * anchor sequence (_load_robots / _step_robots: the anchor id is one more message field, 4 bytes per robot;
  * on the device the ids move with the poses and each window reads its own N anchor positions, so the graph
- * structure is one for the whole fleet and for every step).  UWB-only windows (uwb_only.yaml).
+ * structure is one for the whole fleet and for every step).  Fleets of up to 592 robots are solved by the WINDOW
+ * kernels (one CTA per robot), larger ones by the tile kernels.  UWB-only windows (uwb_only.yaml).
  */
 typedef struct uwbgo_stream uwbgo_stream;
 int  uwbgo_stream_create(uwbgo_ctx *ctx, int32_t n_poses, int32_t n_anchors, int64_t n_windows,

@@ -155,6 +155,7 @@ struct uwbgo_stream {
     double *anch_w = nullptr, *chi2_prev = nullptr, *rd = nullptr, *ri = nullptr; /* rd / ri: small fleets only */
     int32_t *rej = nullptr;
     bool per_robot = false;
+    bool api_per_robot = false; /* how the caller loaded it: a small fleet-wide stream is per_robot inside */
     bool gate = false;      /* outlier gate of addRangeEdge (uwbgo_stream_set_outlier_gate) */
     double outlier = 0.0;   /* robot/distance_outlier */
     int cur = 0;
@@ -424,25 +425,45 @@ extern "C" {
 int uwbgo_stream_load(uwbgo_stream *s, const double *pose_t, const int32_t *anchor_of_pose, const float *distance,
                       const float *distance_err, const double *dt)
 {
-    return load_impl(s, false, pose_t, anchor_of_pose, distance, distance_err, dt);
+    if (s && anchor_of_pose && s->W <= SMALL_FLEET) {
+        /* a small fleet: the same anchor sequence for every robot, held per robot, so that the solve takes the
+         * WINDOW kernels (the per-robot form has one graph structure for all steps and window-private anchors) */
+        std::vector<int32_t> rows((size_t)s->W * s->N);
+        for (int64_t w = 0; w < s->W; ++w)
+            for (int k = 0; k < s->N; ++k) rows[(size_t)w * s->N + k] = anchor_of_pose[k];
+        const int rc = load_impl(s, true, pose_t, rows.data(), distance, distance_err, dt);
+        if (rc == 0) s->api_per_robot = false;
+        return rc;
+    }
+    const int rc = load_impl(s, false, pose_t, anchor_of_pose, distance, distance_err, dt);
+    if (rc == 0) s->api_per_robot = false;
+    return rc;
 }
 
 int uwbgo_stream_load_robots(uwbgo_stream *s, const double *pose_t, const int32_t *anchor_of_pose, const float *distance,
                              const float *distance_err, const double *dt)
 {
-    return load_impl(s, true, pose_t, anchor_of_pose, distance, distance_err, dt);
+    const int rc = load_impl(s, true, pose_t, anchor_of_pose, distance, distance_err, dt);
+    if (rc == 0) s->api_per_robot = true;
+    return rc;
 }
 
 int uwbgo_stream_step(uwbgo_stream *s, int32_t anchor, const float *distance, const float *distance_err, const double *dt,
                       double *newest_pose, double *chi2, int32_t *status)
 {
+    if (!s || !s->loaded || s->api_per_robot || s->gate) return UWBGO_E_INVALID; /* (the gate: per-robot streams only) */
+    if (s->per_robot) { /* small fleet held per robot: every robot hears this anchor */
+        if (anchor < 0 || anchor >= s->A) return UWBGO_E_INVALID;
+        const std::vector<int32_t> a((size_t)s->W, anchor);
+        return step_impl(s, 0, a.data(), distance, distance_err, dt, newest_pose, chi2, status);
+    }
     return step_impl(s, anchor, nullptr, distance, distance_err, dt, newest_pose, chi2, status);
 }
 
 int uwbgo_stream_step_robots(uwbgo_stream *s, const int32_t *anchor, const float *distance, const float *distance_err,
                              const double *dt, double *newest_pose, double *chi2, int32_t *status)
 {
-    if (!anchor) return UWBGO_E_INVALID;
+    if (!anchor || !s || !s->api_per_robot) return UWBGO_E_INVALID;
     return step_impl(s, 0, anchor, distance, distance_err, dt, newest_pose, chi2, status);
 }
 

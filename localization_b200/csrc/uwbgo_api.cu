@@ -716,8 +716,11 @@ int run_window(uwbgo_ctx *ctx, const TopoEntry &te, const DevCfg &cfg, const uwb
     io.o_cnt = out->oplus_count;
     io.o_chi2 = out->chi2;
     io.o_status = out->status;
-    io.t3 = (te.fast_ok && in->pose_R == nullptr && te.gen.simple_chain && !UWBGO_WIN_NO_T3) ? 1 : 0;
-    io.bd_ok = (te.bd_ok && !io.t3 && !UWBGO_WIN_NO_T3) ? 1 : 0;
+    /* UWBGO_WIN_BLOCKS=6 in the environment: every window on the full 6x6 blocks (A/B runs) */
+    static const bool full_blocks = getenv("UWBGO_WIN_BLOCKS") && !strcmp(getenv("UWBGO_WIN_BLOCKS"), "6");
+    const bool small_blocks = !UWBGO_WIN_NO_T3 && !full_blocks;
+    io.t3 = (te.fast_ok && in->pose_R == nullptr && te.gen.simple_chain && small_blocks) ? 1 : 0;
+    io.bd_ok = (te.bd_ok && !io.t3 && small_blocks) ? 1 : 0;
     const bool timed = ctx->profile;
     const int kslot = (int)(ctx->k_count % uwbgo_ctx::K_RING);
     if (timed) CU(cudaEventRecord(ctx->k0[kslot], st));

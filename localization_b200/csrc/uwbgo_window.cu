@@ -48,6 +48,7 @@ namespace uwbgo {
 namespace {
 
 #ifdef UWBGO_WIN_TIMING
+__device__ unsigned long long g_bad_chi6 = 0, g_bad_lin6 = 0, g_n_chi6 = 0, g_n_lin6 = 0; /* IEEE re-evaluations */
 __device__ __forceinline__ long long clk()
 {
     long long t;
@@ -65,9 +66,29 @@ constexpr int WIN_MAX_KS = 4;
 #ifndef UWBGO_WIN_IEEE
 #define UWBGO_WIN_IEEE 0 /* experiment: bit 0 C phase, bit 1 J phase, bit 2 U phase run the IEEE sequences */
 #endif
-using WMC = std::conditional<(UWBGO_WIN_IEEE & 1) != 0, IeeeMath, NbMath>::type;
-using WMJ = std::conditional<(UWBGO_WIN_IEEE & 2) != 0, IeeeMath, NbMath>::type;
-using WMU = std::conditional<(UWBGO_WIN_IEEE & 4) != 0, IeeeMath, NbMath>::type;
+/* The branch-free policy of the WINDOW kernel.  NbMath::div flags a divisor with a significand of all ones (its
+ * Newton sequence is not guaranteed to round correctly there) and the caller then repeats the WHOLE item with the
+ * IEEE sequences.  That divisor is systematic here: the quaternion of a near-identity rotation divides by
+ * sqrt(4 - 2 ulp) = 2 - ulp, and the error rotation of an IMU prior on the pose whose estimate the same message
+ * set (localization.cpp:499-535) is exactly that -- one prior per window sent every J and C phase of its warp
+ * through both code paths.  Here such a quotient alone is formed by the IEEE division (same bits, by definition)
+ * and the item is not flagged. */
+struct NbMathW : NbMath {
+    static UWBGO_DI double div(double a, double b, unsigned &bad)
+    {
+        const unsigned ones = all_ones(b);
+        bad |= (mid_range(b) & (mid_range(a) | (a == 0.0 ? 1u : 0u))) ^ 1u;
+        const double y = rcp_core(b);
+        const double q0 = a * y;
+        const double r = fma(-b, q0, a);
+        double q = fma(y, r, q0);
+        if (ones) q = a / b;
+        return q;
+    }
+};
+using WMC = std::conditional<(UWBGO_WIN_IEEE & 1) != 0, IeeeMath, NbMathW>::type;
+using WMJ = std::conditional<(UWBGO_WIN_IEEE & 2) != 0, IeeeMath, NbMathW>::type;
+using WMU = std::conditional<(UWBGO_WIN_IEEE & 4) != 0, IeeeMath, NbMathW>::type;
 #ifdef UWBGO_WIN_NO6D
 constexpr bool NO6D = true; /* experiment: range-only build, to see what the 6-D code costs in instruction fetch */
 #else
@@ -975,6 +996,10 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             double chi, rob;
             unsigned bad = 0;
             six_chi<WMC>(sm, X, sm.edges[e], ck, chi, rob, bad);
+#ifdef UWBGO_WIN_TIMING
+            atomicAdd(&g_n_chi6, 1ull);
+            if (bad) atomicAdd(&g_bad_chi6, 1ull);
+#endif
             if (bad) six_chi<IeeeMath>(sm, X, sm.edges[e], ck, chi, rob, bad);
             echi[2 * e] = chi;
             echi[2 * e + 1] = rob;
@@ -1071,6 +1096,10 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
                     const EdgeRec er = sm.edges[sm.slot_edge[tp.Er + (k < tp.Es ? tp.Ep + k : k - tp.Es)]];
                     unsigned bad = 0;
                     lin_six<WMJ>(sm, X, er, ck, bad);
+#ifdef UWBGO_WIN_TIMING
+                    atomicAdd(&g_n_lin6, 1ull);
+                    if (bad) atomicAdd(&g_bad_lin6, 1ull);
+#endif
                     if (bad) lin_six<IeeeMath>(sm, X, er, ck, bad);
                 }
                 const int base1 = ((n6 + 31) & ~31) % NT;
@@ -1528,6 +1557,8 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
     if (tid == 0 && blockIdx.x == 0)
         printf("window 0 cycles: J %lld  O %lld  H %lld  factor %lld (assemble %lld potrf %lld fwd+store %lld bar %lld)  wait for x %lld  U+C %lld  D %lld  sync %lld  (trials %d, iterations %d, rounds %d)\n",
                tph[0], tph[1], tph[2], tph[3], tfac[0], tfac[1], tfac[2], tfac[3], tph[6], tph[4], tph[5], tph[7], trials_total, iterations, rounds);
+    if (tid == 0 && blockIdx.x == 0)
+        printf("   IEEE re-evaluations so far: chi6 %llu of %llu, lin6 %llu of %llu\n", g_bad_chi6, g_n_chi6, g_bad_lin6, g_n_lin6);
     if (tid == 0 && blockIdx.x == 0)
         printf("   main 0: U %lld (pre %lld)  bar %lld  chi6 %lld   helper 0: subst %lld  wait at A %lld  bar %lld  chi-range %lld\n", dbg[0], dbg[4], dbg[1], dbg[2], dbg[7], dbg[3], dbg[5], dbg[6]);
 #endif

@@ -316,7 +316,7 @@ def run_latency(args):
             "roofline": {"bound": "fp64-latency", "kernel": "lm_window_kernel (one CTA per window, state in shared memory)",
                          "kernel_us": one["window_path_kernel_us"], "achieved": None, "peak": None, "unit": None, "frac": None,
                          "traffic": None,
-                         "note": "one window is a serial chain: iterations x poses x six Cholesky pivots, each a dependent "
+                         "note": "one window is a serial chain: iterations x poses x Cholesky pivots (three per pose on translation-only and block-diagonal windows, six on full 6x6 blocks), each a dependent "
                                  "sqrt -> reciprocal -> multiply -> FMA sequence (~165 cycles of FP64 latency); neither HBM nor "
                                  "the FP64 pipe is loaded by a single window, the measure is microseconds per call next to "
                                  "the CPU (DESIGN.md section 4.3)"},

@@ -1175,9 +1175,12 @@ lm_window_kernel(const __grid_constant__ DevTopo tp, const __grid_constant__ Dev
             constexpr int HN = T3 ? 18 : 63, HU = T3 ? 6 : 21, HO = DB * DB;
             /* block-diagonal windows: 12 + 9 + 6 of the 63 entries per pose (the others are exact zeros nobody reads) */
             const int hn = bd ? 27 : HN;
+            /* entry-major: the threads of a warp own the SAME entry of consecutive poses, so that they walk the
+             * same kind of term through the same branches (pose-major, a warp mixed diagonal, off-diagonal and
+             * right-hand-side entries and ran each path in turn) */
             for (int u = tid; u < hn * N; u += NT) {
-                const int i = u / hn;
-                int k = u - hn * i;
+                int k = u / N;
+                const int i = u - N * k;
                 if (bd) k = BD_ENTRY[k];
                 /* k < HU: H_ii upper (r, c); then H_{parent(i), i} (r, c); the last DB: b_i[r].  (T3: the entries of
                  * the translation blocks; the others are exact zeros nobody reads) */

@@ -1525,7 +1525,7 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
                 double chi, rob;
                 /* (EdgeSE3 with the IEEE sequences at once, see the J phase) */
                 if (tt.edges[e].kind == UWBGO_EDGE_SE3 ||
-                    (diag ? item_chi<NbMath, true>(G.E, tt, T, e, chi, rob) : item_chi<NbMath, false>(G.E, tt, T, e, chi, rob)))
+                    (diag ? item_chi<NbMathW, true>(G.E, tt, T, e, chi, rob) : item_chi<NbMathW, false>(G.E, tt, T, e, chi, rob)))
                     item_chi<IeeeMath, false>(G.E, tt, T, e, chi, rob);
                 ROW(echi, 2 * e) = chi;
                 ROW(echi, 2 * e + 1) = rob;
@@ -1635,14 +1635,16 @@ lm_general_items_kernel(const __grid_constant__ DevTopo tp, const __grid_constan
                     if (!on) continue;
                     if (u < nS) {
                         /* (IEEE sequences at once: the quaternion of a near-identity rotation divides by 2 - ulp, the one
-                         * divisor class the branch-free quotient refuses, and a twist chain is full of them) */
+                         * divisor class the branch-free quotient refuses, and a twist chain is full of them.  NbMathW,
+                         * which forms that quotient by the IEEE division on the spot, was tried here too: more spills,
+                         * C4b 3.86 instead of 3.77 ms) */
                         if (u & 1)
                             item_se3<IeeeMath, 1>(G, tt, T, u >> 1);
                         else
                             item_se3<IeeeMath, 0>(G, tt, T, u >> 1);
                     }
                     else if (u < nS + tp.Ep) {
-                        if (diag ? item_prior<NbMath, true>(G, tt, T, u - nS) : item_prior<NbMath, false>(G, tt, T, u - nS))
+                        if (diag ? item_prior<NbMathW, true>(G, tt, T, u - nS) : item_prior<NbMathW, false>(G, tt, T, u - nS))
                             item_prior<IeeeMath, false>(G, tt, T, u - nS);
                     } else if (u < nS + tp.Ep + tp.Er) {
                         if (G.rinc_sparse ? item_range_v0<NbMath, true>(G, tt, T, u - nS - tp.Ep) : item_range_v0<NbMath>(G, tt, T, u - nS - tp.Ep))

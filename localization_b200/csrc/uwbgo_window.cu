@@ -73,19 +73,6 @@ constexpr int WIN_MAX_KS = 4;
  * set (localization.cpp:499-535) is exactly that -- one prior per window sent every J and C phase of its warp
  * through both code paths.  Here such a quotient alone is formed by the IEEE division (same bits, by definition)
  * and the item is not flagged. */
-struct NbMathW : NbMath {
-    static UWBGO_DI double div(double a, double b, unsigned &bad)
-    {
-        const unsigned ones = all_ones(b);
-        bad |= (mid_range(b) & (mid_range(a) | (a == 0.0 ? 1u : 0u))) ^ 1u;
-        const double y = rcp_core(b);
-        const double q0 = a * y;
-        const double r = fma(-b, q0, a);
-        double q = fma(y, r, q0);
-        if (ones) q = a / b;
-        return q;
-    }
-};
 using WMC = std::conditional<(UWBGO_WIN_IEEE & 1) != 0, IeeeMath, NbMathW>::type;
 using WMJ = std::conditional<(UWBGO_WIN_IEEE & 2) != 0, IeeeMath, NbMathW>::type;
 using WMU = std::conditional<(UWBGO_WIN_IEEE & 4) != 0, IeeeMath, NbMathW>::type;
